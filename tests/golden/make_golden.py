@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference (`/root/reference/lib`) is imported as-is behind two import shims
+(`torch._six`, `termcolor` — SURVEY.md §8c).  Nothing from the reference is copied; only
+its inputs/outputs on seeded synthetic data are stored as small .npz files.
+"""
+import collections.abc
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+_six = types.ModuleType('torch._six')
+_six.container_abcs = collections.abc
+sys.modules['torch._six'] = _six
+_tc = types.ModuleType('termcolor')
+_tc.colored = lambda s, *a, **k: s
+sys.modules['termcolor'] = _tc
+sys.path.insert(0, '/root/reference')
+
+import lib.layers as layers  # noqa: E402
+import lib.layers.base as base_layers  # noqa: E402
+import lib.layers.broyden as ref_broyden_mod  # noqa: E402
+import lib.layers.implicit_block as ref_imblock_mod  # noqa: E402
+from lib.implicit_flow import ImplicitFlow  # noqa: E402
+
+torch.set_num_threads(4)
+
+
+def sd_np(module, prefix=''):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print('wrote', path, '%.1f KB' % (os.path.getsize(path) / 1024))
+
+
+class SolveRecorder:
+    """Wraps the reference broyden() to record nstep / lowest_step / trace of each call."""
+
+    def __init__(self):
+        self.calls = []
+        self._orig = ref_broyden_mod.broyden
+
+    def __enter__(self):
+        def wrapped(g, x0, threshold, eps, ls=False, name='unknown'):
+            out = self._orig(g, x0, threshold, eps, ls=ls, name=name)
+            self.calls.append((name, out['nstep'], out['lowest_step'], list(out['trace'])))
+            return out
+        ref_imblock_mod.broyden = wrapped
+        return self
+
+    def __exit__(self, *a):
+        ref_imblock_mod.broyden = self._orig
+
+    def nsteps(self, name):
+        return np.array([c[1] for c in self.calls if c[0] == name], dtype=np.int64)
+
+    def traces(self, name):
+        tr = [c[3] for c in self.calls if c[0] == name]
+        n = max(len(t) for t in tr) if tr else 0
+        out = np.full((len(tr), n), np.nan, dtype=np.float64)
+        for i, t in enumerate(tr):
+            out[i, :len(t)] = t
+        return out
+
+
+def replay_probes(seed, shape_x, shape_z):
+    """The two Rademacher draws _logdetgrad makes right after torch.manual_seed(seed)."""
+    torch.manual_seed(seed)
+    B = torch.distributions.bernoulli.Bernoulli(torch.Tensor([0.5]))
+    vx = B.sample(shape_x).reshape(shape_x) * 2 - 1
+    vz = B.sample(shape_z).reshape(shape_z) * 2 - 1
+    return vx.numpy(), vz.numpy()
+
+
+# ----------------------------------------------------------------------------------------------
+# 1. broyden() on analytic maps
+# ----------------------------------------------------------------------------------------------
+
+def gen_broyden():
+    out = {}
+    rng = np.random.RandomState(1)
+
+    def run(tag, B, d, T, eps, scale=0.5, gain=None, zero_row=False):
+        W = (rng.randn(d, d) / np.sqrt(d)).astype(np.float32)
+        c = rng.randn(B, d).astype(np.float32)
+        if zero_row:
+            c[0] = 0.
+        Wt, ct = torch.from_numpy(W), torch.from_numpy(c)
+        if gain is None:
+            g = lambda x: ct - scale * torch.tanh(x @ Wt) - x
+        else:
+            g = lambda x: ct + gain * x
+        res = ref_broyden_mod.broyden(g, torch.zeros(B, d), T, eps)
+        out[tag + '_W'] = W
+        out[tag + '_c'] = c
+        out[tag + '_meta'] = np.array([B, d, T, eps, scale, -1. if gain is None else gain], dtype=np.float64)
+        out[tag + '_result'] = res['result'].numpy()
+        out[tag + '_ints'] = np.array([res['nstep'], res['lowest_step'], int(res['prot_break'])], dtype=np.int64)
+        out[tag + '_trace'] = np.array(res['trace'], dtype=np.float64)
+        out[tag + '_diff_detail'] = res['diff_detail'].numpy()
+        out[tag + '_diff'] = np.array(res['diff'], dtype=np.float64)
+        print(tag, 'nstep', res['nstep'], 'lowest', res['lowest_step'], 'prot', res['prot_break'],
+              'trace', ['%.3g' % t for t in res['trace']])
+
+    run('small', 7, 5, 30, 1e-6, zero_row=True)
+    run('wide', 64, 300, 30, 1e-6, scale=0.9)
+    run('capped', 9, 12, 3, 1e-9, scale=0.95)
+    run('long', 5, 40, 30, 1e-9, scale=2.5)
+    run('protbreak', 4, 6, 30, 1e-6, gain=1e7)
+    save('broyden_analytic', **out)
+
+
+# ----------------------------------------------------------------------------------------------
+# 2. imBlock with MLP branches (toy / tabular shapes)
+# ----------------------------------------------------------------------------------------------
+
+def build_mlp(dims, coeff, n_iterations, tol, data_dim):
+    nnet = []
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        if i > 0:
+            nnet.append(base_layers.Sin())
+        nnet.append(base_layers.get_linear(a, b, coeff=coeff, n_iterations=n_iterations, atol=tol, rtol=tol,
+                                           domain=2, codomain=2, zero_init=(b == data_dim)))
+    return torch.nn.Sequential(*nnet)
+
+
+def std_normal_logprob(z):
+    return -0.5 * np.log(2 * np.pi) - z.pow(2) / 2
+
+
+def run_block(tag, blk, x, seed, training, out, with_grad=True, weight_perturb=None):
+    if weight_perturb:
+        # move the zero-init last layers away from ~0 so that the solves do real work
+        with torch.no_grad():
+            for n, p in blk.named_parameters():
+                if n.endswith('weight') and p.requires_grad:
+                    p.mul_(weight_perturb)
+        blk.nnet_x_copy.load_state_dict(blk.nnet_x.state_dict())
+        blk.nnet_z_copy.load_state_dict(blk.nnet_z.state_dict())
+    blk.train(training)
+    for k, v in sd_np(blk).items():
+        out[tag + '_sd_' + k] = v
+    x = x.clone().requires_grad_(with_grad)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    with SolveRecorder() as rec:
+        z, dlogp = blk(x, torch.zeros(x.shape[0], 1))
+        out[tag + '_x'] = x.detach().numpy()
+        out[tag + '_z'] = z.detach().numpy()
+        out[tag + '_dlogp'] = dlogp.detach().numpy()
+        if with_grad:
+            logpz = std_normal_logprob(z).view(z.size(0), -1).sum(1, keepdim=True)
+            loss = -(logpz - dlogp).mean()
+            loss.backward()
+            out[tag + '_loss'] = np.array(loss.item())
+            out[tag + '_grad_x'] = x.grad.numpy()
+            for n, p in blk.named_parameters():
+                if p.grad is not None:
+                    out[tag + '_grad_' + n] = p.grad.numpy()
+    out[tag + '_fwd_nstep'] = rec.nsteps('forward')
+    out[tag + '_bwd_nstep'] = rec.nsteps('backward')
+    out[tag + '_fwd_trace'] = rec.traces('forward')
+    out[tag + '_bwd_trace'] = rec.traces('backward')
+    out[tag + '_seed'] = np.array(seed)
+    out[tag + '_n_draws'] = blk.last_n_samples.numpy().copy()
+    vx, vz = replay_probes(seed, tuple(x.shape), tuple(z.shape))
+    out[tag + '_vareps_x'] = vx
+    out[tag + '_vareps_z'] = vz
+    print(tag, 'fwd', rec.nsteps('forward'), 'bwd', rec.nsteps('backward'),
+          'dlogp[:2]', dlogp.detach().flatten()[:2].numpy(), 'n', blk.last_n_samples.numpy())
+    # inverse reconstructs x from z
+    blk.eval()
+    with torch.no_grad(), SolveRecorder() as rec2:
+        x_rec = blk.inverse(z.detach())
+    out[tag + '_x_rec'] = x_rec.numpy()
+    out[tag + '_inv_nstep'] = rec2.nsteps('forward')
+
+
+def gen_imblock_mlp():
+    out = {}
+    # toy: d=2, brute force log-det (train_toy.py:224-242, run_toy.sh)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    dims = [2, 32, 32, 2]
+    blk = layers.imBlock(build_mlp(dims, 0.99, 20, None, 2), build_mlp(dims, 0.99, 20, None, 2),
+                         n_dist='geometric', brute_force=True, n_samples=1, neumann_grad=False,
+                         grad_in_forward=False)
+    x = torch.rand(50, 2) * 4 - 2
+    run_block('toy', blk, x, 11, True, out, weight_perturb=300.)
+
+    # tabular d=6: basic estimator in training (train_tabular.py:314-336, run_tabular.sh)
+    torch.manual_seed(1)
+    np.random.seed(1)
+    dims = [6, 64, 64, 6]
+    blk = layers.imBlock(build_mlp(dims, 0.99, None, 1e-3, 6), build_mlp(dims, 0.99, None, 1e-3, 6),
+                         n_dist='geometric', n_samples=1, n_exact_terms=2, neumann_grad=False,
+                         grad_in_forward=False, eps_forward=1e-5)
+    x = torch.randn(40, 6)
+    run_block('tab6', blk, x, 12, True, out, weight_perturb=300.)
+    # same block in eval mode -> brute force because d <= 10
+    out_eval = {}
+    run_block('tab6eval', blk, x, 13, False, out_eval, with_grad=False)
+    for k in ('tab6eval_z', 'tab6eval_dlogp', 'tab6eval_fwd_nstep'):
+        out[k] = out_eval[k]
+
+    # tabular d=43: roulette in train and (20 exact terms) in eval
+    torch.manual_seed(2)
+    np.random.seed(2)
+    dims = [43, 64, 64, 43]
+    blk = layers.imBlock(build_mlp(dims, 0.99, None, 1e-3, 43), build_mlp(dims, 0.99, None, 1e-3, 43),
+                         n_dist='geometric', n_samples=1, n_exact_terms=2, neumann_grad=False,
+                         grad_in_forward=False, eps_forward=1e-5)
+    x = torch.randn(24, 43)
+    run_block('tab43', blk, x, 14, True, out, weight_perturb=300.)
+    out_eval = {}
+    run_block('tab43eval', blk, x, 15, False, out_eval, with_grad=False)
+    for k in ('tab43eval_z', 'tab43eval_dlogp', 'tab43eval_fwd_nstep', 'tab43eval_n_draws', 'tab43eval_seed',
+              'tab43eval_vareps_x', 'tab43eval_vareps_z'):
+        out[k] = out_eval[k]
+    # eval-mode draw is not stored by the reference in last_n_samples: replay it
+    np.random.seed(15)
+    out['tab43eval_n_draws'] = np.random.geometric(0.5, 1).astype(np.float32)
+    save('imblock_mlp', **out)
+
+
+# ----------------------------------------------------------------------------------------------
+# 3. imBlock with conv branches (CIFAR-style 3-1-3 LipSwish, classifier-style 3-3 ReLU)
+# ----------------------------------------------------------------------------------------------
+
+def build_conv_branch(c, idim, coeff, tol, leading_act):
+    nnet = []
+    if leading_act:
+        nnet.append(base_layers.Swish())
+    nnet.append(base_layers.get_conv2d(c, idim, 3, 1, 1, coeff=coeff, n_iterations=None, domain=2, codomain=2,
+                                       atol=tol, rtol=tol))
+    nnet.append(base_layers.Swish())
+    nnet.append(base_layers.get_conv2d(idim, idim, 1, 1, 0, coeff=coeff, n_iterations=None, domain=2, codomain=2,
+                                       atol=tol, rtol=tol))
+    nnet.append(base_layers.Swish())
+    nnet.append(base_layers.get_conv2d(idim, c, 3, 1, 1, coeff=coeff, n_iterations=None, domain=2, codomain=2,
+                                       atol=tol, rtol=tol))
+    return torch.nn.Sequential(*nnet)
+
+
+def build_cls_branch(c, hidden, coeff, tol):
+    mk = lambda a, b: base_layers.get_conv2d(a, b, kernel_size=3, stride=1, padding=1, bias=False, coeff=coeff,
+                                             n_iterations=None, domain=2, codomain=2, atol=tol, rtol=tol)
+    return torch.nn.Sequential(mk(c, hidden), torch.nn.ReLU(), mk(hidden, c), torch.nn.ReLU())
+
+
+def gen_imblock_conv():
+    out = {}
+    torch.manual_seed(3)
+    np.random.seed(3)
+    c, idim, hw, B = 4, 32, 8, 4
+    blk = layers.imBlock(build_conv_branch(c, idim, 0.9, 1e-3, True), build_conv_branch(c, idim, 0.9, 1e-3, True),
+                         n_dist='poisson', n_samples=1, n_exact_terms=3, neumann_grad=True, grad_in_forward=True)
+    x = torch.randn(B, c, hw, hw)
+    with torch.no_grad():
+        blk(x, restore=True)      # lazy u/v shaping (train_img.py:502-507)
+    run_block('cifar', blk, x, 21, True, out)
+
+    torch.manual_seed(4)
+    np.random.seed(4)
+    blk = layers.imBlock(build_conv_branch(c, idim, 0.9, 1e-3, False), build_conv_branch(c, idim, 0.9, 1e-3, False),
+                         n_dist='poisson', n_samples=1, n_exact_terms=3, neumann_grad=False, grad_in_forward=False)
+    with torch.no_grad():
+        blk(x, restore=True)
+    run_block('cifar_basic', blk, x, 22, True, out)
+
+    # classifier-style block, no log-det (train_classification.py:135-188)
+    torch.manual_seed(5)
+    np.random.seed(5)
+    c, hidden = 8, 16
+    blk = layers.imBlock(build_cls_branch(c, hidden, 0.9, 1e-3), build_cls_branch(c, hidden, 0.9, 1e-3))
+    x = torch.rand(B, c, hw, hw)
+    with torch.no_grad():
+        blk(x, restore=True)
+    blk.train(True)
+    for k, v in sd_np(blk).items():
+        out['cls_sd_' + k] = v
+    xg = x.clone().requires_grad_(True)
+    with SolveRecorder() as rec:
+        z = blk(xg)
+        loss = (z ** 2).mean()
+        loss.backward()
+    out['cls_x'] = x.numpy()
+    out['cls_z'] = z.detach().numpy()
+    out['cls_loss'] = np.array(loss.item())
+    out['cls_grad_x'] = xg.grad.numpy()
+    for n, p in blk.named_parameters():
+        if p.grad is not None:
+            out['cls_grad_' + n] = p.grad.numpy()
+    out['cls_fwd_nstep'] = rec.nsteps('forward')
+    out['cls_bwd_nstep'] = rec.nsteps('backward')
+    out['cls_fwd_trace'] = rec.traces('forward')
+    out['cls_bwd_trace'] = rec.traces('backward')
+    print('cls fwd', rec.nsteps('forward'), 'bwd', rec.nsteps('backward'))
+    save('imblock_conv', **out)
+
+
+# ----------------------------------------------------------------------------------------------
+# 4. induced-norm layers
+# ----------------------------------------------------------------------------------------------
+
+def gen_induced_norm():
+    out = {}
+    torch.manual_seed(6)
+    lin = base_layers.InducedNormLinear(6, 16, coeff=0.5, domain=2, codomain=2, atol=1e-3, rtol=1e-3)
+    for k, v in sd_np(lin).items():
+        out['lin_init_' + k] = v
+    with torch.no_grad():
+        lin.weight.add_(0.3 * torch.randn_like(lin.weight))
+    out['lin_weight2'] = lin.weight.detach().numpy().copy()
+    W = lin.compute_weight(update=True)
+    out['lin_W_tol'] = W.detach().numpy()
+    out['lin_u_tol'], out['lin_v_tol'] = lin.u.numpy().copy(), lin.v.numpy().copy()
+    out['lin_scale_tol'] = lin.scale.numpy().copy()
+    W = lin.compute_weight(update=True, n_iterations=5)
+    out['lin_W_it5'] = W.detach().numpy()
+    out['lin_u_it5'], out['lin_v_it5'] = lin.u.numpy().copy(), lin.v.numpy().copy()
+    out['lin_scale_it5'] = lin.scale.numpy().copy()
+    xin = torch.randn(5, 6)
+    out['lin_x'] = xin.numpy()
+    out['lin_y'] = lin(xin).detach().numpy()
+    # gradient through sigma
+    lin.zero_grad()
+    lin(xin).pow(2).sum().backward()
+    out['lin_grad_weight'] = lin.weight.grad.numpy().copy()
+
+    torch.manual_seed(7)
+    conv = base_layers.InducedNormConv2d(5, 8, 3, 1, 1, coeff=0.4, domain=2, codomain=2, atol=1e-3, rtol=1e-3)
+    xin = torch.randn(2, 5, 6, 6)
+    y0 = conv(xin)                                  # lazy init of u/v at spatial dims 6x6
+    for k, v in sd_np(conv).items():
+        out['conv_init_' + k] = v
+    out['conv_x'] = xin.numpy()
+    out['conv_y'] = y0.detach().numpy()
+    with torch.no_grad():
+        conv.weight.add_(0.2 * torch.randn_like(conv.weight))
+    out['conv_weight2'] = conv.weight.detach().numpy().copy()
+    W = conv.compute_weight(update=True)
+    out['conv_W_tol'] = W.detach().numpy()
+    out['conv_u_tol'], out['conv_v_tol'] = conv.u.numpy().copy(), conv.v.numpy().copy()
+    out['conv_scale_tol'] = conv.scale.numpy().copy()
+    conv.zero_grad()
+    conv(xin).pow(2).sum().backward()
+    out['conv_grad_weight'] = conv.weight.grad.numpy().copy()
+
+    torch.manual_seed(8)
+    c1 = base_layers.InducedNormConv2d(8, 8, 1, 1, 0, coeff=0.3, domain=2, codomain=2, atol=1e-3, rtol=1e-3)
+    xin = torch.randn(2, 8, 4, 4)
+    y0 = c1(xin)
+    for k, v in sd_np(c1).items():
+        out['c1_init_' + k] = v
+    out['c1_x'] = xin.numpy()
+    out['c1_y'] = y0.detach().numpy()
+    with torch.no_grad():
+        c1.weight.add_(0.2 * torch.randn_like(c1.weight))
+    out['c1_weight2'] = c1.weight.detach().numpy().copy()
+    W = c1.compute_weight(update=True)
+    out['c1_W_tol'] = W.detach().numpy()
+    out['c1_u_tol'], out['c1_v_tol'] = c1.u.numpy().copy(), c1.v.numpy().copy()
+    out['c1_scale_tol'] = c1.scale.numpy().copy()
+    save('induced_norm', **out)
+
+
+# ----------------------------------------------------------------------------------------------
+# 5. activations
+# ----------------------------------------------------------------------------------------------
+
+def gen_activations():
+    out = {}
+    x = torch.linspace(-6, 6, 241).requires_grad_(True)
+    for name, mod in (('sin', base_layers.Sin()), ('swish', base_layers.Swish())):
+        y = mod(x)
+        (d1,) = torch.autograd.grad(y.sum(), x, create_graph=True)
+        (d2,) = torch.autograd.grad(d1.sum(), x, create_graph=True)
+        (d3,) = torch.autograd.grad(d2.sum(), x)
+        out[name + '_y'], out[name + '_d1'] = y.detach().numpy(), d1.detach().numpy()
+        out[name + '_d2'], out[name + '_d3'] = d2.detach().numpy(), d3.detach().numpy()
+    sw = base_layers.Swish()
+    y = sw(x)
+    w = torch.cos(x.detach())
+    (gb,) = torch.autograd.grad((y * w).sum(), sw.beta)
+    out['swish_grad_beta'] = gb.numpy()
+    out['swish_w'] = w.numpy()
+    out['x'] = x.detach().numpy()
+    save('activations', **out)
+
+
+# ----------------------------------------------------------------------------------------------
+# 6. a small multiscale ImplicitFlow, density-training step (train_img.py:517-549)
+# ----------------------------------------------------------------------------------------------
+
+def gen_flow():
+    out = {}
+    torch.manual_seed(9)
+    np.random.seed(9)
+    B, c, hw = 4, 3, 8
+    model = ImplicitFlow(
+        (B, c, hw, hw), n_blocks=[1, 1], intermediate_dim=16, factor_out=False, quadratic=False,
+        init_layer=layers.LogitTransform(0.05), actnorm=True, fc_actnorm=False, batchnorm=False, dropout=0.,
+        fc=False, coeff=0.9, vnorms='2222', n_lipschitz_iters=None, sn_atol=1e-3, sn_rtol=1e-3,
+        n_power_series=None, n_dist='poisson', n_samples=1, kernels='3-1-3', activation_fn='swish', fc_end=False,
+        fc_idim=128, n_exact_terms=3, preact=True, neumann_grad=True, grad_in_forward=True, first_resblock=True,
+        learn_p=False, classification=False, classification_hdim=64, n_classes=10)
+    x = torch.rand(B, c, hw, hw)
+    with torch.no_grad():
+        model(x, restore=True)
+    model.train()
+    for k, v in sd_np(model).items():
+        out['sd_' + k] = v
+    np.random.seed(31)
+    torch.manual_seed(31)
+    with SolveRecorder() as rec:
+        z, dlogp = model(x, 0)
+        logpz = std_normal_logprob(z).view(z.size(0), -1).sum(1, keepdim=True)
+        ndim = c * hw * hw
+        logpx = logpz - dlogp - np.log(256) * ndim
+        bpd = -torch.mean(logpx) / ndim / np.log(2)
+        bpd.backward()
+    out['x'], out['z'], out['dlogp'], out['bpd'] = x.numpy(), z.detach().numpy(), dlogp.detach().numpy(), np.array(bpd.item())
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            out['grad_' + n] = p.grad.numpy()
+    out['fwd_nstep'], out['bwd_nstep'] = rec.nsteps('forward'), rec.nsteps('backward')
+    out['n_draws'] = np.stack([m.last_n_samples.numpy() for m in model.modules() if isinstance(m, layers.imBlock)])
+    out['seed'] = np.array(31)
+    print('flow bpd', bpd.item(), 'fwd', rec.nsteps('forward'), 'bwd', rec.nsteps('backward'))
+    model.eval()
+    with torch.no_grad():
+        out['x_rec'] = model(z.detach(), inverse=True).numpy()
+    save('flow_small', **out)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['broyden', 'mlp', 'conv', 'norm', 'act', 'flow']
+    if 'broyden' in which: gen_broyden()
+    if 'mlp' in which: gen_imblock_mlp()
+    if 'conv' in which: gen_imblock_conv()
+    if 'norm' in which: gen_induced_norm()
+    if 'act' in which: gen_activations()
+    if 'flow' in which: gen_flow()
