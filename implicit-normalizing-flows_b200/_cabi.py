@@ -1,0 +1,101 @@
+"""ctypes binding of libimpflow_b200.so (C ABI declared in include/impflow_b200.h).
+
+There is no CPU fallback: if the library is missing, or a tensor is not a dense fp32 CUDA
+tensor, the call raises."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libimpflow_b200.so')
+
+_c_fp = ctypes.c_void_p
+_ll = ctypes.c_longlong
+_i = ctypes.c_int
+_f = ctypes.c_float
+_d = ctypes.c_double
+
+# name -> (restype, argtypes); mirrors include/impflow_b200.h one to one
+SIGNATURES = {
+    'impflow_version': (_i, []),
+    'impflow_last_error': (ctypes.c_char_p, []),
+    'impflow_launch_count': (_ll, []),
+    'impflow_broyden_state_bytes': (ctypes.c_size_t, []),
+    'impflow_broyden_workspace_floats': (ctypes.c_size_t, [_i, _ll, _i]),
+    'impflow_broyden_begin': (_i, [_c_fp] * 9 + [_i, _ll, _i, _d, _c_fp]),
+    'impflow_broyden_step': (_i, [_c_fp] * 12 + [_i, _ll, _i, _c_fp]),
+    'impflow_act_mul': (_i, [_c_fp, _c_fp, _c_fp, _ll, _i, _i, _c_fp, _c_fp]),
+    'impflow_reduce_workspace_floats': (ctypes.c_size_t, [_ll]),
+    'impflow_act_beta_grad': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _ll, _i, _c_fp, _c_fp]),
+    'impflow_lincomb3': (_i, [_c_fp, _f, _c_fp, _f, _c_fp, _f, _c_fp, _ll, _c_fp]),
+    'impflow_rowdot': (_i, [_c_fp, _c_fp, _c_fp, _i, _ll, _f, _f, _c_fp]),
+    'impflow_colsum': (_i, [_c_fp, _c_fp, _ll, _i, _c_fp]),
+    'impflow_transpose': (_i, [_c_fp, _c_fp, _ll, _ll, _c_fp]),
+    'impflow_im2col3x3': (_i, [_c_fp, _c_fp, _i, _i, _i, _i, _c_fp]),
+    'impflow_col2im3x3': (_i, [_c_fp, _i, _i, _i, _i, _c_fp, _c_fp, _c_fp, _c_fp, _i, _c_fp, _c_fp]),
+    'impflow_gemm_nt': (_i, [_c_fp, _ll, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
+    'impflow_gemm_nt_tc': (_i, [_c_fp, _c_fp, _ll, _c_fp, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp,
+                                _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
+    'impflow_split_tf32': (_i, [_c_fp, _c_fp, _c_fp, _ll, _c_fp]),
+    'impflow_sn_power_iter': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _i, _i, _i, _f, _f, _c_fp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and type the shared library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('libimpflow_b200.so is not built: run `python -c "import __graft_entry__ as g; g.build()"` '
+                          '(there is no CPU / PyTorch fallback for the ImpFlow hot path)')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            continue   # test_cabi checks the export list against the header
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().impflow_last_error().decode()
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError('%s failed (%d): %s' % (what, rc, last_error()))
+
+
+def ptr(t, name='tensor', allow_none=False):
+    """Device pointer of a dense fp32 CUDA tensor (memory order is the caller's business)."""
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError('%s is None' % name)
+    if not t.is_cuda:
+        raise RuntimeError('impflow_b200: %s must be a CUDA tensor (no CPU fallback exists for this path)' % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError('impflow_b200: %s must be float32, got %s' % (name, t.dtype))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def iptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(load().impflow_launch_count())

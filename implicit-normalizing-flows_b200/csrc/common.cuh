@@ -1,0 +1,135 @@
+// Shared helpers for libimpflow_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/impflow_b200.h"
+
+namespace impflow {
+
+// thread-local error string behind impflow_last_error()
+void set_error(const char* fmt, ...);
+extern long long g_launch_count;
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return -1;
+  }
+  ++g_launch_count;
+  return 0;
+}
+
+#define IMPFLOW_REQUIRE(cond, ...)        \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::impflow::set_error(__VA_ARGS__);  \
+      return -3;                          \
+    }                                     \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Activations and their derivatives (reference: lib/layers/base/activations.py:7-12 Sin,
+// :64-71 Swish (LipSwish), torch.nn.ReLU).  order = derivative order in x.
+// ---------------------------------------------------------------------------------------
+constexpr float kTwoPi = 6.283185307179586f;
+
+template <int KIND>
+__device__ __forceinline__ float act_eval(float x, int order, float beta) {
+  if (KIND == IMPFLOW_ACT_NONE) {
+    return order == 0 ? x : (order == 1 ? 1.f : 0.f);
+  } else if (KIND == IMPFLOW_ACT_SIN) {
+    float s, c;
+    sincosf(kTwoPi * x, &s, &c);
+    switch (order) {
+      case 0: return s / 3.141592653589793f * 0.5f;
+      case 1: return c;
+      case 2: return -kTwoPi * s;
+      default: return -kTwoPi * kTwoPi * c;
+    }
+  } else if (KIND == IMPFLOW_ACT_RELU) {
+    if (order == 0) return x > 0.f ? x : 0.f;
+    if (order == 1) return x > 0.f ? 1.f : 0.f;
+    return 0.f;
+  } else {  // LipSwish: f = x*sigmoid(beta*x)/1.1
+    const float bx = beta * x;
+    const float s = 1.f / (1.f + expf(-bx));
+    const float q = s * (1.f - s);
+    const float inv = 1.f / 1.1f;
+    switch (order) {
+      case 0: return x * s * inv;
+      case 1: return (s + bx * q) * inv;
+      case 2: return (2.f * beta * q + beta * bx * q * (1.f - 2.f * s)) * inv;
+      default: return (3.f * beta * beta * q * (1.f - 2.f * s) +
+                       beta * beta * bx * q * (1.f - 6.f * s + 6.f * s * s)) * inv;
+    }
+  }
+}
+
+// d/d(beta) of the order-th x-derivative of LipSwish (beta = softplus(raw beta)).
+__device__ __forceinline__ float lipswish_dbeta(float x, int order, float beta) {
+  const float bx = beta * x;
+  const float s = 1.f / (1.f + expf(-bx));
+  const float q = s * (1.f - s);
+  const float inv = 1.f / 1.1f;
+  const float r1 = 1.f - 2.f * s;
+  const float r2 = 1.f - 6.f * s + 6.f * s * s;
+  switch (order) {
+    case 0: return x * x * q * inv;
+    case 1: return (2.f * x * q + bx * x * q * r1) * inv;
+    default: return (2.f * q + 4.f * bx * q * r1 + bx * bx * q * r2) * inv;
+  }
+}
+
+__device__ __forceinline__ float act_dispatch(int kind, float x, int order, float beta) {
+  switch (kind) {
+    case IMPFLOW_ACT_SIN: return act_eval<IMPFLOW_ACT_SIN>(x, order, beta);
+    case IMPFLOW_ACT_LIPSWISH: return act_eval<IMPFLOW_ACT_LIPSWISH>(x, order, beta);
+    case IMPFLOW_ACT_RELU: return act_eval<IMPFLOW_ACT_RELU>(x, order, beta);
+    default: return act_eval<IMPFLOW_ACT_NONE>(x, order, beta);
+  }
+}
+
+// Fused GEMM / col2im epilogue description (see impflow_gemm_nt in the header).
+struct Epilogue {
+  const float* bias;      // [N] or null
+  float* pre_out;         // [M,ldc] or null
+  float* act_out;         // [M,ldc] or null
+  const float* dmul_pre;  // [M,ldc] or null
+  long long ldc;
+  int act_kind;
+  const float* beta_ptr;  // device scalar softplus(beta) for LipSwish, or null
+  float beta;             // filled in by the kernel from beta_ptr
+};
+
+__device__ __forceinline__ Epilogue resolve_beta(Epilogue e) {
+  e.beta = (e.beta_ptr != nullptr) ? __ldg(e.beta_ptr) : 0.f;
+  return e;
+}
+
+__device__ __forceinline__ void epilogue_store(const Epilogue& e, long long m, int n, float acc) {
+  const long long idx = m * e.ldc + n;
+  if (e.dmul_pre != nullptr) {
+    e.pre_out[idx] = acc * act_dispatch(e.act_kind, e.dmul_pre[idx], 1, e.beta);
+    return;
+  }
+  const float v = acc + (e.bias ? e.bias[n] : 0.f);
+  if (e.pre_out) e.pre_out[idx] = v;
+  if (e.act_out) e.act_out[idx] = act_dispatch(e.act_kind, v, 0, e.beta);
+}
+
+}  // namespace impflow

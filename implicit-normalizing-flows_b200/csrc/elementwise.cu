@@ -1,0 +1,354 @@
+// Elementwise / reduction kernels on the ImpFlow hot path (HBM-bound; coalesced float4 access,
+// grids sized as multiples of the 148 SMs).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace impflow {
+
+static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr int kSMs = 148;
+
+static inline int grid_for(long long work_items, int per_block) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)kSMs * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- act_mul: out = g * act^(order)(x) ---------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_act_mul(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out, long long n,
+          int order, const float* __restrict__ beta_ptr, int vec) {
+  const float beta = (beta_ptr != nullptr) ? __ldg(beta_ptr) : 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (vec) {
+    const long long n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (; i < n4; i += stride) {
+      const float4 xv = x4[i];
+      float4 r;
+      r.x = act_eval<KIND>(xv.x, order, beta);
+      r.y = act_eval<KIND>(xv.y, order, beta);
+      r.z = act_eval<KIND>(xv.z, order, beta);
+      r.w = act_eval<KIND>(xv.w, order, beta);
+      if (g != nullptr) {
+        const float4 gv = g4[i];
+        r.x *= gv.x; r.y *= gv.y; r.z *= gv.z; r.w *= gv.w;
+      }
+      o4[i] = r;
+    }
+    i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  }
+  for (; i < n; i += stride) {
+    float r = act_eval<KIND>(x[i], order, beta);
+    if (g != nullptr) r *= g[i];
+    out[i] = r;
+  }
+}
+
+// ---- beta gradient of LipSwish: two-stage deterministic reduce --------------------------------
+__global__ void __launch_bounds__(256)
+k_beta_grad_stage1(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ partial,
+                   long long n, int order, const float* __restrict__ beta_ptr) {
+  const float beta = __ldg(beta_ptr);
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    acc += (double)(g[i] * lipswish_dbeta(x[i], order, beta));
+  __shared__ double ws[8];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    partial[blockIdx.x] = (float)t;
+  }
+}
+__global__ void k_sum_partials(const float* __restrict__ partial, float* __restrict__ out, int m) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < m; i += 32) acc += (double)partial[i];
+  acc = warp_sum_d(acc);
+  if (threadIdx.x == 0) out[0] = (float)acc;
+}
+
+// ---- lincomb3 -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_lincomb3(const float* __restrict__ a, float ca, const float* __restrict__ b, float cb,
+           const float* __restrict__ c, float cc, float* __restrict__ out, long long n, int vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (; i < n4; i += stride) {
+      const float4 av = reinterpret_cast<const float4*>(a)[i];
+      float4 r = make_float4(av.x * ca, av.y * ca, av.z * ca, av.w * ca);
+      if (b != nullptr) {
+        const float4 bv = reinterpret_cast<const float4*>(b)[i];
+        r.x += bv.x * cb; r.y += bv.y * cb; r.z += bv.z * cb; r.w += bv.w * cb;
+      }
+      if (c != nullptr) {
+        const float4 cv = reinterpret_cast<const float4*>(c)[i];
+        r.x += cv.x * cc; r.y += cv.y * cc; r.z += cv.z * cc; r.w += cv.w * cc;
+      }
+      reinterpret_cast<float4*>(out)[i] = r;
+    }
+    i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  }
+  for (; i < n; i += stride) {
+    float r = a[i] * ca;
+    if (b != nullptr) r += b[i] * cb;
+    if (c != nullptr) r += c[i] * cc;
+    out[i] = r;
+  }
+}
+
+// ---- rowdot: one CTA per sample (large d) or one warp per sample (small d) -----------------------
+__global__ void __launch_bounds__(256)
+k_rowdot_block(const float* __restrict__ a, const float* __restrict__ c, float* __restrict__ out, long long d,
+               float alpha, float beta, int vec) {
+  const long long base = (long long)blockIdx.x * d;
+  float acc = 0.f;
+  if (vec) {
+    const float4* a4 = reinterpret_cast<const float4*>(a + base);
+    const float4* c4 = reinterpret_cast<const float4*>(c + base);
+    for (long long i = threadIdx.x; i < (d >> 2); i += 256) {
+      const float4 x = a4[i], y = c4[i];
+      acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    }
+  } else {
+    for (long long i = threadIdx.x; i < d; i += 256) acc += a[base + i] * c[base + i];
+  }
+  __shared__ float ws[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    out[blockIdx.x] = (beta == 0.f ? 0.f : beta * out[blockIdx.x]) + alpha * t;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_rowdot_warp(const float* __restrict__ a, const float* __restrict__ c, float* __restrict__ out, int B, int d,
+              float alpha, float beta) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int i = lane; i < d; i += 32) acc += a[(long long)b * d + i] * c[(long long)b * d + i];
+  acc = warp_sum(acc);
+  if (lane == 0) out[b] = (beta == 0.f ? 0.f : beta * out[b]) + alpha * acc;
+}
+
+// ---- colsum: out[n] = sum_m a[m,n]; grid over column tiles of 32, 8 row-lanes ------------------
+__global__ void __launch_bounds__(256)
+k_colsum(const float* __restrict__ a, float* __restrict__ out, long long M, int N) {
+  __shared__ float tile[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (col < N)
+    for (long long m = ry; m < M; m += 8) acc += a[m * N + col];
+  tile[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && col < N) {
+    float t = 0.f;
+    for (int r = 0; r < 8; ++r) t += tile[r][threadIdx.x & 31];
+    out[col] = t;
+  }
+}
+
+// ---- transpose ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_transpose(const float* __restrict__ a, float* __restrict__ out, long long M, long long N) {
+  __shared__ float tile[32][33];
+  const long long m0 = (long long)blockIdx.y * 32, n0 = (long long)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (m0 + r < M && n0 + tx < N) tile[r][tx] = a[(m0 + r) * N + n0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (n0 + r < N && m0 + tx < M) out[(n0 + r) * M + m0 + tx] = tile[tx][r];
+}
+
+// ---- im2col / col2im for NHWC 3x3 stride 1 pad 1 -------------------------------------------------
+// col row p=(b,y,x) has 9*C entries ordered (ky,kx,c).
+__global__ void __launch_bounds__(256)
+k_im2col3x3(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C) {
+  const long long total = (long long)B * H * W * 9 * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int tap = (int)(t % 9);
+    const long long p = t / 9;
+    const int xx = (int)(p % W);
+    const int yy = (int)((p / W) % H);
+    const long long b = p / ((long long)W * H);
+    const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+    float v = 0.f;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = x[((b * H + sy) * W + sx) * C + c];
+    col[i] = v;
+  }
+}
+
+// x[p,c] = sum_tap col[p - off(tap), tap, c] followed by the fused epilogue.
+__global__ void __launch_bounds__(256)
+k_col2im3x3(const float* __restrict__ col, int B, int H, int W, int C, Epilogue ep_in) {
+  const Epilogue ep = resolve_beta(ep_in);
+  const long long total = (long long)B * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long p = i / C;
+    const int xx = (int)(p % W);
+    const int yy = (int)((p / W) % H);
+    const long long b = p / ((long long)W * H);
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sy = yy - (tap / 3 - 1), sx = xx - (tap % 3 - 1);
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+        acc += col[(((b * H + sy) * W + sx) * 9 + tap) * C + c];
+    }
+    epilogue_store(ep, p, c, acc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_split_tf32(const float* __restrict__ a, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = a[i];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float hf = __uint_as_float(h);
+    hi[i] = hf;
+    lo[i] = v - hf;
+  }
+}
+
+}  // namespace impflow
+
+using namespace impflow;
+
+extern "C" int impflow_version(void) { return IMPFLOW_ABI_VERSION; }
+extern "C" const char* impflow_last_error(void) { return impflow::g_err; }
+extern "C" long long impflow_launch_count(void) { return impflow::g_launch_count; }
+
+extern "C" int impflow_act_mul(const float* x, const float* g, float* out, long long n, int kind, int order,
+                               const float* beta_sp, void* stream) {
+  IMPFLOW_REQUIRE(kind != IMPFLOW_ACT_LIPSWISH || beta_sp != nullptr, "act_mul: LipSwish needs beta_sp");
+  IMPFLOW_REQUIRE(order >= 0 && order <= 3, "act_mul: order %d not in [0,3]", order);
+  if (n <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int vec = (aligned16(x) && aligned16(out) && (g == nullptr || aligned16(g)) && n >= 4) ? 1 : 0;
+  const int grid = grid_for(vec ? (n >> 2) : n, 256);
+  switch (kind) {
+    case IMPFLOW_ACT_SIN: k_act_mul<IMPFLOW_ACT_SIN><<<grid, 256, 0, s>>>(x, g, out, n, order, beta_sp, vec); break;
+    case IMPFLOW_ACT_LIPSWISH:
+      k_act_mul<IMPFLOW_ACT_LIPSWISH><<<grid, 256, 0, s>>>(x, g, out, n, order, beta_sp, vec);
+      break;
+    case IMPFLOW_ACT_RELU: k_act_mul<IMPFLOW_ACT_RELU><<<grid, 256, 0, s>>>(x, g, out, n, order, beta_sp, vec); break;
+    case IMPFLOW_ACT_NONE: k_act_mul<IMPFLOW_ACT_NONE><<<grid, 256, 0, s>>>(x, g, out, n, order, beta_sp, vec); break;
+    default: set_error("act_mul: unknown activation kind %d", kind); return -3;
+  }
+  return check_launch("k_act_mul");
+}
+
+extern "C" size_t impflow_reduce_workspace_floats(long long n) {
+  (void)n;
+  return (size_t)kSMs * 16;
+}
+
+extern "C" int impflow_act_beta_grad(const float* x, const float* g, float* out, float* partial, long long n,
+                                     int order, const float* beta_sp, void* stream) {
+  IMPFLOW_REQUIRE(beta_sp != nullptr, "act_beta_grad: beta_sp is null");
+  IMPFLOW_REQUIRE(order >= 0 && order <= 2, "act_beta_grad: order %d not in [0,2]", order);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = grid_for(n, 1024);
+  k_beta_grad_stage1<<<grid, 256, 0, s>>>(x, g, partial, n, order, beta_sp);
+  if (check_launch("k_beta_grad_stage1")) return -1;
+  k_sum_partials<<<1, 32, 0, s>>>(partial, out, grid);
+  return check_launch("k_sum_partials");
+}
+
+extern "C" int impflow_lincomb3(const float* a, float ca, const float* b, float cb, const float* c, float cc,
+                                float* out, long long n, void* stream) {
+  if (n <= 0) return 0;
+  const int vec = (aligned16(a) && aligned16(out) && (b == nullptr || aligned16(b)) &&
+                   (c == nullptr || aligned16(c)) && n >= 4) ? 1 : 0;
+  const int grid = grid_for(vec ? (n >> 2) : n, 256);
+  k_lincomb3<<<grid, 256, 0, (cudaStream_t)stream>>>(a, ca, b, cb, c, cc, out, n, vec);
+  return check_launch("k_lincomb3");
+}
+
+extern "C" int impflow_rowdot(const float* a, const float* c, float* out, int B, long long d, float alpha,
+                              float beta, void* stream) {
+  if (B <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d <= 256) {
+    k_rowdot_warp<<<(B + 7) / 8, 256, 0, s>>>(a, c, out, B, (int)d, alpha, beta);
+    return check_launch("k_rowdot_warp");
+  }
+  const int vec = (aligned16(a) && aligned16(c) && (d % 4 == 0)) ? 1 : 0;
+  k_rowdot_block<<<B, 256, 0, s>>>(a, c, out, d, alpha, beta, vec);
+  return check_launch("k_rowdot_block");
+}
+
+extern "C" int impflow_colsum(const float* a, float* out, long long M, int N, void* stream) {
+  if (N <= 0) return 0;
+  k_colsum<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a, out, M, N);
+  return check_launch("k_colsum");
+}
+
+extern "C" int impflow_transpose(const float* a, float* out, long long M, long long N, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + 31) / 32));
+  IMPFLOW_REQUIRE(grid.y <= 65535, "transpose: M=%lld too large for this grid layout", M);
+  k_transpose<<<grid, 256, 0, (cudaStream_t)stream>>>(a, out, M, N);
+  return check_launch("k_transpose");
+}
+
+extern "C" int impflow_im2col3x3(const float* x, float* col, int B, int H, int W, int C, void* stream) {
+  const long long total = (long long)B * H * W * 9 * C;
+  if (total <= 0) return 0;
+  k_im2col3x3<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, col, B, H, W, C);
+  return check_launch("k_im2col3x3");
+}
+
+extern "C" int impflow_col2im3x3(const float* col, int B, int H, int W, int C, const float* bias, float* pre_out,
+                                 float* act_out, const float* dmul_pre, int act_kind, const float* beta_sp,
+                                 void* stream) {
+  const long long total = (long long)B * H * W * C;
+  if (total <= 0) return 0;
+  IMPFLOW_REQUIRE(pre_out != nullptr || act_out != nullptr, "col2im3x3: no output given");
+  IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr, "col2im3x3: dmul_pre needs pre_out");
+  Epilogue ep{bias, pre_out, act_out, dmul_pre, (long long)C, act_kind, beta_sp, 0.f};
+  k_col2im3x3<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(col, B, H, W, C, ep);
+  return check_launch("k_col2im3x3");
+}
+
+extern "C" int impflow_split_tf32(const float* a, float* hi, float* lo, long long n, void* stream) {
+  if (n <= 0) return 0;
+  k_split_tf32<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, hi, lo, n);
+  return check_launch("k_split_tf32");
+}

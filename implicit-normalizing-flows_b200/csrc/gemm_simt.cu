@@ -1,0 +1,119 @@
+// fp32 CUDA-core GEMM  C[M,N] = A[M,K] * B[N,K]^T  with the fused branch epilogue.
+// Exact-fp32 backend of impflow_gemm_nt: used for the small MLP shapes (toy / tabular, K or N
+// down to 2) and as the on-device cross-check of the tcgen05 3xTF32 backend.
+#include "common.cuh"
+
+namespace impflow {
+
+constexpr int BK = 16;
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(256)
+k_gemm_nt(const float* __restrict__ A, long long lda, const float* __restrict__ Bm, long long ldb, long long M,
+          int N, int K, Epilogue ep_in, int vecA, int vecB) {
+  const Epilogue ep = resolve_beta(ep_in);
+  constexpr int TM = BM / 16, TN = BN / 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = (long long)blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // ---- load tiles (K-major rows -> transposed smem) ----
+#pragma unroll
+    for (int it = 0; it < BM / 64; ++it) {
+      const int r = (tid >> 2) + it * 64, q = tid & 3;
+      const long long gm = m0 + r;
+      const int gk = k0 + q * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gm < M) {
+        if (vecA && gk + 3 < K) {
+          const float4 t = *reinterpret_cast<const float4*>(A + gm * lda + gk);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (gk + e < K) v[e] = A[gm * lda + gk + e];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) As[q * 4 + e][r] = v[e];
+    }
+#pragma unroll
+    for (int it = 0; it < BN / 64; ++it) {
+      const int r = (tid >> 2) + it * 64, q = tid & 3;
+      const int gn = n0 + r;
+      const int gk = k0 + q * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gn < N) {
+        if (vecB && gk + 3 < K) {
+          const float4 t = *reinterpret_cast<const float4*>(Bm + (long long)gn * ldb + gk);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (gk + e < K) v[e] = Bm[(long long)gn * ldb + gk + e];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Bs[q * 4 + e][r] = v[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&As[kk][(i / 4) * 64 + ty * 4]);
+        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&Bs[kk][(j / 4) * 64 + tx * 4]);
+        b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // ---- epilogue ----
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const long long m = m0 + (i / 4) * 64 + ty * 4 + (i % 4);
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + (j / 4) * 64 + tx * 4 + (j % 4);
+      if (n < N) epilogue_store(ep, m, n, acc[i][j]);
+    }
+  }
+}
+
+int gemm_nt_simt(const float* A, long long lda, const float* Bm, long long ldb, long long M, int N, int K,
+                 const Epilogue& ep, cudaStream_t s) {
+  const int vecA = ((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (lda % 4) == 0) ? 1 : 0;
+  const int vecB = ((reinterpret_cast<uintptr_t>(Bm) & 15) == 0 && (ldb % 4) == 0) ? 1 : 0;
+  const long long tiles_big = ((M + 127) / 128) * ((N + 127) / 128);
+  if (tiles_big >= 148 && N > 64) {
+    dim3 grid((N + 127) / 128, (unsigned)((M + 127) / 128));
+    IMPFLOW_REQUIRE(grid.y <= 65535, "gemm_nt: M=%lld too large", M);
+    k_gemm_nt<128, 128><<<grid, 256, 0, s>>>(A, lda, Bm, ldb, M, N, K, ep, vecA, vecB);
+  } else {
+    dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64));
+    IMPFLOW_REQUIRE(grid.y <= 65535, "gemm_nt: M=%lld too large", M);
+    k_gemm_nt<64, 64><<<grid, 256, 0, s>>>(A, lda, Bm, ldb, M, N, K, ep, vecA, vecB);
+  }
+  return check_launch("k_gemm_nt");
+}
+
+}  // namespace impflow

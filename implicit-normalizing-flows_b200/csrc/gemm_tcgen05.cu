@@ -1,0 +1,465 @@
+// tcgen05 / TMA / TMEM GEMM for the residual-branch contractions (sm_100a only):
+//
+//     C[M,N] = A[M,K] * B[N,K]^T       fp32 in, fp32 out, "3xTF32" error-compensated:
+//     A = A_hi + A_lo, B = B_hi + B_lo  (tf32-representable planes, see k_split_tf32)
+//     C ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi   accumulated in fp32 in TMEM.
+//
+// Why 3xTF32: the Broyden solves converge to eps*sqrt(B*d) with eps down to 1e-10 — i.e. fp32
+// round-off — so the branch must be evaluated to fp32 accuracy (SURVEY.md §7 hard part 1).
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor.2d, 128B-swizzled K-major tiles, 4 tiles/stage
+//   warp 1   : MMA issuer    — one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8)
+//   warp 2   : TMEM allocator (2 accumulator stages of BN columns)
+//   warps 4-7: epilogue      — tcgen05.ld 32x32b, fused bias / activation / act' product /
+//                              hi-lo split for the next GEMM, direct coalesced-per-row stores
+// smem ring: STAGES x {A_hi, A_lo, B_hi, B_lo}, full/empty mbarriers; TMEM full/empty mbarriers
+// let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace impflow {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;  // 32 fp32 = 128 bytes = one swizzle-128B row
+constexpr int TC_THREADS = 256;
+
+struct TcEpilogue {
+  Epilogue e;
+  float* split_hi;  // optional tf32 hi plane of the "next layer input" value
+  float* split_lo;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=2 (SW128) [61,64)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;           // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32; // SBO: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;           // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = (BN >= 128) ? 3 : 4;
+  static constexpr int kABytes = TC_BM * TC_BK * 4;  // 16 KB per plane
+  static constexpr int kBBytes = BN * TC_BK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+           const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+           long long M, int N, int K, TcEpilogue ep) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = K / TC_BK;
+  const long long m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const long long num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapAhi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapAlo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBhi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBlo)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_idx = (int)(tile / n_tiles) * TC_BM;
+        const int n_idx = (int)(tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          tma_load_2d(&mapAhi, &full[stage], st, kb * TC_BK, m_idx);
+          tma_load_2d(&mapAlo, &full[stage], st + Cfg::kABytes, kb * TC_BK, m_idx);
+          tma_load_2d(&mapBhi, &full[stage], st + 2 * Cfg::kABytes, kb * TC_BK, n_idx);
+          tma_load_2d(&mapBlo, &full[stage], st + 2 * Cfg::kABytes + Cfg::kBBytes, kb * TC_BK, n_idx);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2,
+    // b=TF32 [10,13)=2, K-major both, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(TC_BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a_lo = a_hi + Cfg::kABytes;
+          const uint32_t b_hi = a_hi + 2 * Cfg::kABytes;
+          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint32_t koff = k * 32;  // 8 tf32 = 32 bytes inside the 128B swizzle row
+            const uint64_t dah = make_kmajor_sw128_desc(a_hi + koff);
+            const uint64_t dal = make_kmajor_sw128_desc(a_lo + koff);
+            const uint64_t dbh = make_kmajor_sw128_desc(b_hi + koff);
+            const uint64_t dbl = make_kmajor_sw128_desc(b_lo + koff);
+            umma_tf32(tmem_c, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_c, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_c, dah, dbh, idesc, 1u);
+          }
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&empty[stage]);  // frees the smem stage when the MMAs retire
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);  // accumulator ready for the epilogue
+      __syncwarp();
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp - 4;  // TMEM lane quarter this warp may touch (warp % 4)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const Epilogue e = resolve_beta(ep.e);
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long m = (tile / n_tiles) * TC_BM + q * 32 + lane;
+      const int n_base = (int)(tile % n_tiles) * BN;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        tmem_ld32(taddr, r);
+        const int n0 = n_base + c * 32;
+        if (m < M && n0 < N) {
+          const long long row = m * e.ldc;
+          const bool full_vec = (n0 + 32 <= N) && ((e.ldc & 3) == 0);
+          float v[32];
+          if (e.dmul_pre != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float p[4];
+              if (full_vec) {
+                const float4 t = *reinterpret_cast<const float4*>(e.dmul_pre + row + n0 + j);
+                p[0] = t.x; p[1] = t.y; p[2] = t.z; p[3] = t.w;
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) p[u] = (n0 + j + u < N) ? e.dmul_pre[row + n0 + j + u] : 0.f;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                v[j + u] = __uint_as_float(r[j + u]) * act_dispatch(e.act_kind, p[u], 1, e.beta);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float b = (e.bias != nullptr && n0 + j < N) ? __ldg(e.bias + n0 + j) : 0.f;
+              v[j] = __uint_as_float(r[j]) + b;
+            }
+            if (e.pre_out != nullptr) {
+              if (full_vec) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(e.pre_out + row + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < N) e.pre_out[row + n0 + j] = v[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_dispatch(e.act_kind, v[j], 0, e.beta);
+          }
+          float* main_out = (e.dmul_pre != nullptr) ? e.pre_out : e.act_out;
+          if (main_out != nullptr) {
+            if (full_vec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(main_out + row + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < N) main_out[row + n0 + j] = v[j];
+            }
+          }
+          if (ep.split_hi != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float h[4], l[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint32_t hb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j + u]));
+                h[u] = __uint_as_float(hb);
+                l[u] = v[j + u] - h[u];
+              }
+              if (full_vec) {
+                *reinterpret_cast<float4*>(ep.split_hi + row + n0 + j) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(ep.split_lo + row + n0 + j) = make_float4(l[0], l[1], l[2], l[3]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (n0 + j + u < N) {
+                    ep.split_hi[row + n0 + j + u] = h[u];
+                    ep.split_lo[row + n0 + j + u] = l[u];
+                  }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* base, long long rows, int K, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled entry point not available");
+    return -1;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed with %d (rows=%lld K=%d ld=%lld)", (int)r, rows, K, ld);
+    return -1;
+  }
+  return 0;
+}
+
+template <int BN>
+static int launch_tc(const float* Ahi, const float* Alo, long long lda, const float* Bhi, const float* Blo,
+                     long long ldb, long long M, int N, int K, const TcEpilogue& ep, cudaStream_t s) {
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if (make_map(&mAh, Ahi, M, K, lda, TC_BM) || make_map(&mAl, Alo, M, K, lda, TC_BM) ||
+      make_map(&mBh, Bhi, N, K, ldb, BN) || make_map(&mBl, Blo, N, K, ldb, BN))
+    return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_gemm_tc3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes) !=
+        cudaSuccess) {
+      set_error("gemm_tc: cannot set %d bytes of dynamic shared memory", TcCfg<BN>::kSmemBytes);
+      return -1;
+    }
+    attr_set = true;
+  }
+  const long long tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
+  const int grid = (int)(tiles < 148 ? tiles : 148);
+  k_gemm_tc3<BN><<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, s>>>(mAh, mAl, mBh, mBl, M, N, K, ep);
+  return check_launch("k_gemm_tc3");
+}
+
+int gemm_nt_simt(const float* A, long long lda, const float* Bm, long long ldb, long long M, int N, int K,
+                 const Epilogue& ep, cudaStream_t s);
+
+}  // namespace impflow
+
+using namespace impflow;
+
+extern "C" int impflow_gemm_nt(const float* A, long long lda, const float* Bm, long long ldb, const float* bias,
+                               float* pre_out, float* act_out, const float* dmul_pre, long long ldc, long long M,
+                               int N, int K, int act_kind, const float* beta_sp, void* stream) {
+  IMPFLOW_REQUIRE(M >= 1 && N >= 1 && K >= 1, "gemm_nt: empty problem M=%lld N=%d K=%d", M, N, K);
+  IMPFLOW_REQUIRE(pre_out != nullptr || act_out != nullptr, "gemm_nt: no output given");
+  IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr, "gemm_nt: dmul_pre needs pre_out");
+  Epilogue ep{bias, pre_out, act_out, dmul_pre, ldc, act_kind, beta_sp, 0.f};
+  return gemm_nt_simt(A, lda, Bm, ldb, M, N, K, ep, (cudaStream_t)stream);
+}
+
+extern "C" int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long long lda, const float* B_hi,
+                                  const float* B_lo, long long ldb, const float* bias, float* pre_out,
+                                  float* act_out, const float* dmul_pre, float* split_hi, float* split_lo,
+                                  long long ldc, long long M, int N, int K, int act_kind,
+                                  const float* beta_sp, void* stream) {
+  IMPFLOW_REQUIRE(M >= 1 && N >= 1 && K >= 1, "gemm_nt_tc: empty problem M=%lld N=%d K=%d", M, N, K);
+  IMPFLOW_REQUIRE(pre_out != nullptr || act_out != nullptr || split_hi != nullptr, "gemm_nt_tc: no output given");
+  IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr || split_hi != nullptr,
+                  "gemm_nt_tc: dmul_pre needs pre_out or split planes");
+  IMPFLOW_REQUIRE((split_hi == nullptr) == (split_lo == nullptr), "gemm_nt_tc: split planes come in pairs");
+  if (K % TC_BK != 0 || (lda % 4) != 0 || (ldb % 4) != 0) {
+    set_error("gemm_nt_tc: needs K %% 32 == 0 and 16-byte aligned rows (K=%d lda=%lld ldb=%lld)", K, lda, ldb);
+    return -2;
+  }
+  const uintptr_t al = reinterpret_cast<uintptr_t>(A_hi) | reinterpret_cast<uintptr_t>(A_lo) |
+                       reinterpret_cast<uintptr_t>(B_hi) | reinterpret_cast<uintptr_t>(B_lo);
+  if (al & 15) {
+    set_error("gemm_nt_tc: operand base pointers must be 16-byte aligned");
+    return -2;
+  }
+  TcEpilogue ep{{bias, pre_out, act_out, dmul_pre, ldc, act_kind, beta_sp, 0.f}, split_hi, split_lo};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (N <= 32) return launch_tc<32>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, s);
+  if (N <= 64) return launch_tc<64>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, s);
+  return launch_tc<128>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, s);
+}

@@ -1,0 +1,326 @@
+"""Induced-2-norm constrained Linear / Conv2d — API and state-dict mirror of
+lib/layers/base/mixed_lipschitz.py (InducedNormLinear :12-146, InducedNormConv2d :149-403).
+
+Only domain = codomain = 2 (every shipped config) is implemented; other
+norms raise.  Forward math runs on the impflow CUDA kernels (GEMM / im2col / power iteration);
+there is no CPU execution path except the constructor-time power iteration that the reference
+also performs on the host before the model is moved to the GPU."""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.nn.init as init
+
+from ... import ops
+
+__all__ = ['InducedNormLinear', 'InducedNormConv2d']
+
+
+def _check_norms(domain, codomain):
+    if torch.is_tensor(domain) or torch.is_tensor(codomain):
+        raise NotImplementedError('impflow_b200: learnable induced-norm orders (learn_p) are out of scope')
+    if not (domain == 2 and codomain == 2):
+        raise NotImplementedError('impflow_b200: only domain=codomain=2 is implemented, got %r -> %r'
+                                  % (domain, codomain))
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError('impflow_b200: %s must live on a CUDA device (no CPU fallback)' % what)
+
+
+class _Sigma(torch.autograd.Function):
+    """sigma = u^T W v on the device (mixed_lipschitz.py:125, 320); linear in W."""
+
+    @staticmethod
+    def forward(ctx, W2d, u, v):
+        ctx.save_for_backward(u, v)
+        sigma, _ = ops.sn_power_iter(W2d, u, v, 0, 0.0, 0.0)   # 0 iterations: u, v untouched
+        return sigma
+
+    @staticmethod
+    def backward(ctx, g):
+        u, v = ctx.saved_tensors
+        return g * torch.outer(u, v), None, None
+
+
+def _soft_rescale(weight, sigma, coeff):
+    # soft normalisation: only when sigma is larger than coeff (mixed_lipschitz.py:128-131)
+    factor = torch.max(torch.ones(1, device=weight.device), sigma / coeff)
+    return weight / factor
+
+
+class InducedNormLinear(nn.Module):
+
+    def __init__(self, in_features, out_features, bias=True, coeff=0.97, domain=2, codomain=2, n_iterations=None,
+                 atol=None, rtol=None, zero_init=False, **unused_kwargs):
+        del unused_kwargs
+        super(InducedNormLinear, self).__init__()
+        _check_norms(domain, codomain)
+        self.in_features = in_features
+        self.out_features = out_features
+        self.coeff = coeff
+        self.n_iterations = n_iterations
+        self.atol = atol
+        self.rtol = rtol
+        self.domain = domain
+        self.codomain = codomain
+        self.weight = nn.Parameter(torch.Tensor(out_features, in_features))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(out_features))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters(zero_init)
+        h, w = self.weight.shape
+        self.register_buffer('scale', torch.tensor(0.))
+        self.register_buffer('u', F.normalize(self.weight.new_empty(h).normal_(0, 1), dim=0))
+        self.register_buffer('v', F.normalize(self.weight.new_empty(w).normal_(0, 1), dim=0))
+        self._init_power_iteration_host(200)
+
+    def reset_parameters(self, zero_init=False):
+        # same draws as the reference (mixed_lipschitz.py:58-66)
+        init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if zero_init:
+            self.weight.data.div_(1000)
+        if self.bias is not None:
+            fan_in, _ = init._calculate_fan_in_and_fan_out(self.weight)
+            bound = 1 / math.sqrt(fan_in)
+            init.uniform_(self.bias, -bound, bound)
+
+    def _init_power_iteration_host(self, n):
+        """Constructor-time 200 power iterations (mixed_lipschitz.py:44-46) on the construction
+        device; not part of the hot path."""
+        with torch.no_grad():
+            if self.weight.is_cuda:
+                sigma, _ = ops.sn_power_iter(self.weight, self.u, self.v, n, 0.0, 0.0)
+                self.scale.copy_(sigma[0])
+                return
+            W, u, v = self.weight, self.u, self.v
+            for _ in range(n):
+                u = F.normalize(torch.mv(W, v), dim=0)
+                v = F.normalize(torch.mv(W.t(), u), dim=0)
+            self.u.copy_(u)
+            self.v.copy_(v)
+            self.scale.copy_(torch.dot(u, torch.mv(W, v)))
+
+    def compute_domain_codomain(self):
+        return self.domain, self.codomain
+
+    def compute_one_iter(self):
+        _require_cuda(self.weight, 'InducedNormLinear.weight')
+        u, v = self.u.clone(), self.v.clone()
+        sigma, _ = ops.sn_power_iter(self.weight.detach(), u, v, 1, 0.0, 0.0)
+        return sigma[0]
+
+    def compute_weight(self, update=True, n_iterations=None, atol=None, rtol=None):
+        _require_cuda(self.weight, 'InducedNormLinear.weight')
+        if update:
+            n_iterations = self.n_iterations if n_iterations is None else n_iterations
+            atol = self.atol if atol is None else atol
+            rtol = self.rtol if rtol is None else atol      # reference quirk (mixed_lipschitz.py:94)
+            if n_iterations is None and (atol is None or rtol is None):
+                raise ValueError('Need one of n_iteration or (atol, rtol).')
+            with torch.no_grad():
+                ops.sn_power_iter(self.weight.detach(), self.u, self.v, n_iterations, atol, rtol)
+        sigma = _Sigma.apply(self.weight, self.u, self.v)
+        with torch.no_grad():
+            self.scale.copy_(sigma[0])
+        return _soft_rescale(self.weight, sigma, self.coeff)
+
+    def forward(self, input):
+        weight = self.compute_weight(update=False)
+        shape = input.shape
+        y = ops.linear(input.reshape(-1, shape[-1]), weight, self.bias)
+        return y.view(*shape[:-1], self.out_features)
+
+    def extra_repr(self):
+        return ('in_features={}, out_features={}, bias={}, coeff={}, domain={:.2f}, codomain={:.2f}, n_iters={}, '
+                'atol={}, rtol={}'.format(self.in_features, self.out_features, self.bias is not None, self.coeff,
+                                          self.domain, self.codomain, self.n_iterations, self.atol, self.rtol))
+
+
+def _pair(x):
+    return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+
+def _to_nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _from_nhwc(y):
+    return y.permute(0, 3, 1, 2)
+
+
+class InducedNormConv2d(nn.Module):
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, bias=True, coeff=0.97, domain=2,
+                 codomain=2, n_iterations=None, atol=None, rtol=None, **unused_kwargs):
+        del unused_kwargs
+        super(InducedNormConv2d, self).__init__()
+        _check_norms(domain, codomain)
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride = _pair(stride)
+        self.padding = _pair(padding)
+        if self.kernel_size not in ((1, 1), (3, 3)) or self.stride != (1, 1) or \
+                self.padding != (self.kernel_size[0] // 2,) * 2:
+            raise NotImplementedError('impflow_b200: conv kernels are 1x1 or 3x3, stride 1, same padding '
+                                      '(all shipped configs); got k=%s s=%s p=%s'
+                                      % (self.kernel_size, self.stride, self.padding))
+        self.coeff = coeff
+        self.n_iterations = n_iterations
+        self.domain = domain
+        self.codomain = codomain
+        self.atol = atol
+        self.rtol = rtol
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels, *self.kernel_size))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+        self.register_buffer('initialized', torch.tensor(0))
+        self.register_buffer('spatial_dims', torch.tensor([1., 1.]))
+        self.register_buffer('scale', torch.tensor(0.))
+        self.register_buffer('u', self.weight.new_empty(self.out_channels))
+        self.register_buffer('v', self.weight.new_empty(self.in_channels))
+        self._hw = None
+
+    def compute_domain_codomain(self):
+        return self.domain, self.codomain
+
+    def reset_parameters(self):
+        init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in, _ = init._calculate_fan_in_and_fan_out(self.weight)
+            bound = 1 / math.sqrt(fan_in)
+            init.uniform_(self.bias, -bound, bound)
+
+    # --- helpers -------------------------------------------------------------------------------
+    def _spatial(self):
+        if self._hw is None:
+            self._hw = (int(self.spatial_dims[0].item()), int(self.spatial_dims[1].item()))
+        return self._hw
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._hw = None
+        return super(InducedNormConv2d, self)._load_from_state_dict(*args, **kwargs)
+
+    def _conv_vec(self, vec_chw, weight, transpose=False):
+        """3x3 conv (or its adjoint) applied to one image given/returned as a flat CHW vector."""
+        h, w = self._spatial()
+        if not transpose:
+            x = vec_chw.view(1, self.in_channels, h, w)
+            y = ops.conv3x3_nhwc(_to_nhwc(x), weight)
+        else:
+            x = vec_chw.view(1, self.out_channels, h, w)
+            wt = weight.flip(2, 3).transpose(0, 1)        # conv_transpose2d, stride 1, pad 1
+            y = ops.conv3x3_nhwc(_to_nhwc(x), wt)
+        return _from_nhwc(y).reshape(-1)
+
+    def _initialize_u_v(self):
+        # mixed_lipschitz.py:195-239 (domain = codomain = 2: a single start, no restarts)
+        with torch.no_grad():
+            if self.kernel_size == (1, 1):
+                self.u.resize_(self.out_channels).normal_(0, 1)
+                self.u.copy_(F.normalize(self.u, dim=0))
+                self.v.resize_(self.in_channels).normal_(0, 1)
+                self.v.copy_(F.normalize(self.v, dim=0))
+            else:
+                c = self.in_channels
+                h, w = self._spatial()
+                self.v.resize_(c * h * w).normal_(0, 1)
+                self.v.copy_(F.normalize(self.v, dim=0))
+                self.u.resize_(self.out_channels * h * w).normal_(0, 1)
+                self.u.copy_(F.normalize(self.u, dim=0))
+            self.initialized.fill_(1)
+            self.compute_weight(True)
+            self.u = self.u.clone(memory_format=torch.contiguous_format)
+            self.v = self.v.clone(memory_format=torch.contiguous_format)
+
+    def compute_one_iter(self):
+        if not self.initialized:
+            raise ValueError('Layer needs to be initialized first.')
+        _require_cuda(self.weight, 'InducedNormConv2d.weight')
+        if self.kernel_size == (1, 1):
+            W2 = self.weight.detach().view(self.out_channels, self.in_channels)
+            sigma, _ = ops.sn_power_iter(W2, self.u.clone(), self.v.clone(), 1, 0.0, 0.0)
+            return sigma[0]
+        with torch.no_grad():
+            wt = self.weight.detach()
+            u = F.normalize(self._conv_vec(self.v, wt), dim=0)
+            v = F.normalize(self._conv_vec(u, wt, transpose=True), dim=0)
+            return torch.dot(u, self._conv_vec(v, wt))
+
+    def compute_weight(self, update=True, n_iterations=None, atol=None, rtol=None):
+        _require_cuda(self.weight, 'InducedNormConv2d.weight')
+        if not self.initialized:
+            self._initialize_u_v()
+        n_iterations = self.n_iterations if n_iterations is None else n_iterations
+        atol = self.atol if atol is None else atol
+        rtol = self.rtol if rtol is None else atol          # reference quirk (:279, :331)
+        if n_iterations is None and (atol is None or rtol is None):
+            raise ValueError('Need one of n_iteration or (atol, rtol).')
+        if self.kernel_size == (1, 1):
+            return self._compute_weight_1x1(update, n_iterations, atol, rtol)
+        return self._compute_weight_kxk(update, n_iterations, atol, rtol)
+
+    def _compute_weight_1x1(self, update, n_iterations, atol, rtol):
+        W2 = self.weight.view(self.out_channels, self.in_channels)
+        if update:
+            with torch.no_grad():
+                ops.sn_power_iter(W2.detach(), self.u, self.v, n_iterations, atol, rtol)
+        sigma = _Sigma.apply(W2, self.u, self.v)
+        with torch.no_grad():
+            self.scale.copy_(sigma[0])
+        return _soft_rescale(W2, sigma, self.coeff).view(self.out_channels, self.in_channels, 1, 1)
+
+    def _compute_weight_kxk(self, update, n_iterations, atol, rtol):
+        u, v = self.u, self.v
+        if update:
+            max_itrs = 200 if n_iterations is None else n_iterations
+            with torch.no_grad():
+                wt = self.weight.detach()
+                for _ in range(max_itrs):
+                    old_u, old_v = u, v
+                    u = F.normalize(self._conv_vec(v, wt), dim=0)
+                    v = F.normalize(self._conv_vec(u, wt, transpose=True), dim=0)
+                    if n_iterations is None and atol is not None and rtol is not None:
+                        err_u = torch.norm(u - old_u) / (u.nelement() ** 0.5)
+                        err_v = torch.norm(v - old_v) / (v.nelement() ** 0.5)
+                        tol_u = atol + rtol * torch.max(u)
+                        tol_v = atol + rtol * torch.max(v)
+                        if bool((err_u < tol_u) & (err_v < tol_v)):
+                            break
+                self.u.copy_(u)
+                self.v.copy_(v)
+                u, v = self.u, self.v
+        weight_v = self._conv_vec(v, self.weight)
+        sigma = ops.rowdot_fn(u.view(1, -1), weight_v.view(1, -1))
+        with torch.no_grad():
+            self.scale.copy_(sigma[0])
+        return _soft_rescale(self.weight, sigma, self.coeff)
+
+    def forward(self, input):
+        _require_cuda(input, 'InducedNormConv2d input')
+        if not self.initialized:
+            self.spatial_dims.copy_(torch.tensor(input.shape[2:4]).to(self.spatial_dims))
+            self._hw = None
+        weight = self.compute_weight(update=False)
+        x = _to_nhwc(input)
+        if self.kernel_size == (1, 1):
+            y = ops.conv1x1_nhwc(x, weight, self.bias)
+        else:
+            y = ops.conv3x3_nhwc(x, weight, self.bias)
+        return _from_nhwc(y)
+
+    def extra_repr(self):
+        s = '{}, {}, kernel_size={}, stride={}'.format(self.in_channels, self.out_channels, self.kernel_size,
+                                                       self.stride)
+        if self.bias is None:
+            s += ', bias=False'
+        s += ', coeff={}, domain={:.2f}, codomain={:.2f}, n_iters={}, atol={}, rtol={}'.format(
+            self.coeff, self.domain, self.codomain, self.n_iterations, self.atol, self.rtol)
+        return s

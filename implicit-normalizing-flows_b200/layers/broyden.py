@@ -1,0 +1,111 @@
+"""Batched limited-memory Broyden root solver — API mirror of lib/layers/broyden.py:123-193.
+
+`g_` is any callable on CUDA tensors (one branch evaluation / one vjp per call); all of the
+solver algebra (rank-1 updates, low-rank mat-vecs, norms, best-iterate tracking, break rules)
+runs in the impflow CUDA kernels with the bookkeeping kept on the device.  The host reads a
+600-byte state record per iteration to learn whether the loop continues."""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _cabi
+
+__all__ = ['broyden']
+
+_STATE_DTYPE = np.dtype([('nstep', '<i4'), ('lowest_step', '<i4'), ('active', '<i4'), ('prot_break', '<i4'),
+                         ('converged', '<i4'), ('stagnated', '<i4'), ('do_update', '<i4'), ('new_lowest', '<i4'),
+                         ('threshold', '<i4'), ('counter', '<i4'), ('eps', '<f8'), ('init_objective', '<f8'),
+                         ('lowest', '<f8'), ('objective', '<f8'), ('trace', '<f8', (64,))])
+
+_workspaces = {}
+
+
+class _Workspace(object):
+    """Device buffers of one (B, d, T) problem size, reused across solves."""
+
+    def __init__(self, B, d, T, device):
+        lib = _cabi.load()
+        f32 = dict(device=device, dtype=torch.float32)
+        self.xa = torch.empty(B, d, **f32)
+        self.xb = torch.empty(B, d, **f32)
+        self.low_x = torch.empty(B, d, **f32)
+        self.low_g = torch.empty(B, d, **f32)
+        self.Ut = torch.empty(B, T, d, **f32)
+        self.Vt = torch.empty(B, T, d, **f32)
+        self.sample_sq = torch.empty(B, **f32)
+        self.low_sq = torch.empty(B, **f32)
+        self.partial = torch.empty(max(int(lib.impflow_broyden_workspace_floats(B, d, T)), 1), **f32)
+        nbytes = int(lib.impflow_broyden_state_bytes())
+        assert nbytes == _STATE_DTYPE.itemsize, 'state layout mismatch between header and host'
+        self.state = torch.zeros(nbytes, device=device, dtype=torch.uint8)
+        self.state_host = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+
+    def read_state(self):
+        self.state_host.copy_(self.state, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.state_host.numpy().view(_STATE_DTYPE)[0]
+
+
+def _workspace(B, d, T, device):
+    key = (B, d, T, device.index)
+    ws = _workspaces.get(key)
+    if ws is None:
+        if len(_workspaces) > 16:
+            _workspaces.clear()
+        ws = _workspaces[key] = _Workspace(B, d, T, device)
+    return ws
+
+
+def broyden(g_, x0, threshold, eps, ls=False, name='unknown'):
+    """Find x with g_(x) = 0, starting at x0.  Same return dict as the reference
+    (broyden.py:184-193)."""
+    if ls:
+        raise NotImplementedError('impflow_b200: the Armijo line search is dead code in the reference '
+                                  '(both call sites use ls=False) and is not implemented')
+    if not x0.is_cuda:
+        raise RuntimeError('impflow_b200.broyden: x0 must be a CUDA tensor (no CPU fallback)')
+    lib = _cabi.load()
+    shape = x0.shape
+    B = shape[0]
+    d = x0.numel() // B
+    eps_scaled = eps * np.sqrt(np.prod((B, d)))       # broyden.py:131
+    ws = _workspace(B, d, threshold, x0.device)
+    st = _cabi.stream
+
+    def g(x2d):
+        out = g_(x2d.view(shape))
+        out = out.reshape(B, d)
+        if out.dtype != torch.float32 or not out.is_contiguous():
+            out = out.contiguous().float()
+        return out
+
+    x_old, xn = ws.xa, ws.xb
+    x_old.copy_(x0.reshape(B, d))
+    gx = g(x_old)
+    sp = ctypes.c_void_p(ws.state.data_ptr())
+    _cabi.check(lib.impflow_broyden_begin(_cabi.ptr(x_old), _cabi.ptr(gx), _cabi.ptr(xn), _cabi.ptr(ws.low_x),
+                                          _cabi.ptr(ws.low_g), _cabi.ptr(ws.sample_sq), _cabi.ptr(ws.low_sq),
+                                          _cabi.ptr(ws.partial), sp, B, d, threshold, float(eps_scaled), st()),
+                'broyden_begin')
+    state = ws.read_state()
+    while state['active']:
+        gn = g(xn)
+        _cabi.check(lib.impflow_broyden_step(_cabi.ptr(x_old), _cabi.ptr(gx), _cabi.ptr(xn), _cabi.ptr(gn),
+                                             _cabi.ptr(ws.Ut), _cabi.ptr(ws.Vt), _cabi.ptr(ws.low_x),
+                                             _cabi.ptr(ws.low_g), _cabi.ptr(ws.sample_sq), _cabi.ptr(ws.low_sq),
+                                             _cabi.ptr(ws.partial), sp, B, d, threshold, st()), 'broyden_step')
+        x_old, xn = xn, x_old        # the kernel wrote the next iterate into the old buffer
+        gx = gn
+        state = ws.read_state()
+    nstep = int(state['nstep'])
+    return {'result': ws.low_x.clone().view(shape),
+            'nstep': nstep,
+            'tnstep': nstep,
+            'lowest_step': int(state['lowest_step']),
+            'diff': float(state['lowest']),
+            'diff_detail': torch.sqrt(ws.low_sq),
+            'prot_break': bool(state['prot_break']),
+            'trace': [float(t) for t in state['trace'][:nstep + 1]],
+            'eps': eps_scaled,
+            'threshold': threshold}

@@ -1,0 +1,395 @@
+"""imBlock: the implicit invertible block  z + f(z) = x + g(x)  — API / state-dict mirror of
+lib/layers/implicit_block.py (imBlock :103-355, RootFind :51-100, Backward :165-217, estimators
+:373-450, roulette helpers :457-483).
+
+What runs where:
+  * forward / inverse root solves and the implicit-differentiation solve in backward: the CUDA
+    Broyden kernels (layers/broyden.py) with the residual g assembled by a fused elementwise
+    kernel; g's branch evaluations run on the impflow GEMM / conv / activation kernels;
+  * log-det estimators: vjp chains through the differentiable kernel primitives (ops.py), the
+    Neumann accumulation and Hutchinson dots on fused kernels;
+  * host: the Russian-roulette draw and coefficient table (a handful of Python floats) and, in the
+    default parity mode, the probe draw on the CPU generator exactly as the reference does.
+"""
+import copy
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from .. import ops
+from .broyden import broyden
+
+__all__ = ['imBlock']
+
+# 'reference': n and probes are drawn with the very calls the reference makes (global NumPy RNG,
+# CPU torch generator, implicit_block.py:274,297-298) -> identical draws under identical seeds.
+# 'device': probes come from the CUDA generator (no host->device copy on the hot path).
+PROBE_MODE = {'mode': 'reference'}
+
+
+def find_fixed_point(g, y, threshold=1000, eps=1e-5):
+    """Banach iteration, fallback after a protective break (implicit_block.py:17-28)."""
+    x, x_prev = g(y), y
+    i = 0
+    tol = eps + eps * y.abs()
+    while not torch.all((x - x_prev) ** 2 / tol < 1.):
+        x, x_prev = g(x), x
+        i += 1
+        if i > threshold:
+            break
+    return x
+
+
+class RootFind(Function):
+    """Solve z + nnet_z(z) = x + nnet_x(x) for z without building a graph (implicit_block.py:51-100)."""
+    last_info = None   # result dict of the most recent Broyden solve (read by tests / bench)
+
+    @staticmethod
+    def f(nnet_z, nnet_x, z, x):
+        return nnet_x(x) - nnet_z(z)
+
+    @staticmethod
+    def banach_find_root(nnet_z, nnet_x, z0, x, *args):
+        eps, threshold = args[-2], args[-1]
+        x_embed = nnet_x(x) + x
+        z_est = find_fixed_point(lambda z: x_embed - nnet_z(z), z0, threshold=threshold, eps=eps)
+        return z_est.clone().detach()
+
+    @staticmethod
+    def broyden_find_root(nnet_z, nnet_x, z0, x, *args):
+        eps, threshold = args[-2], args[-1]
+        x_embed = ops.lincomb3(nnet_x(x), 1.0, x, 1.0)
+
+        def g(z):     # x_embed - nnet_z(z) - z in one kernel (implicit_block.py:72)
+            return ops.lincomb3(x_embed, 1.0, nnet_z(z), -1.0, z, -1.0)
+
+        info = broyden(g, torch.zeros_like(z0), threshold=threshold, eps=eps, name='forward')
+        RootFind.last_info = info
+        if info['prot_break']:
+            z_est = RootFind.banach_find_root(nnet_z, nnet_x, z0, x, eps, 1000)
+        else:
+            z_est = info['result']
+        return z_est.clone().detach()
+
+    @staticmethod
+    def forward(ctx, nnet_z, nnet_x, z0, x, method, *args):
+        root_find = RootFind.broyden_find_root if method == 'broyden' else RootFind.banach_find_root
+        ctx.args_len = len(args)
+        with torch.no_grad():
+            return root_find(nnet_z, nnet_x, z0, x, *args)
+
+    @staticmethod
+    def backward(ctx, grad_z):
+        assert 0, 'Cannot backward to this function.'
+
+
+class imBlock(nn.Module):
+
+    def __init__(self, nnet_x, nnet_z, geom_p=0.5, lamb=2., n_power_series=None, exact_trace=False,
+                 brute_force=False, n_samples=1, n_exact_terms=2, n_exact_terms_test=20, n_dist='geometric',
+                 neumann_grad=True, grad_in_forward=True, eps_forward=1e-6, eps_backward=1e-10, eps_sample=1e-5,
+                 threshold=30):
+        super(imBlock, self).__init__()
+        self.nnet_x = nnet_x
+        self.nnet_z = nnet_z
+        # frozen twins used by the implicit backward; kept for state-dict compatibility (:136-141)
+        self.nnet_x_copy = copy.deepcopy(self.nnet_x)
+        self.nnet_z_copy = copy.deepcopy(self.nnet_z)
+        for p in self.nnet_x_copy.parameters():
+            p.requires_grad_(False)
+        for p in self.nnet_z_copy.parameters():
+            p.requires_grad_(False)
+        self.n_dist = n_dist
+        # quirk #12: geom_p ends up a plain fp32 tensor (not in the state dict), lamb a Parameter
+        self.geom_p = nn.Parameter(torch.tensor(np.log(geom_p) - np.log(1. - geom_p))).float()
+        self.lamb = nn.Parameter(torch.tensor(lamb)).float()
+        self.n_samples = n_samples
+        self.n_power_series = n_power_series
+        self.exact_trace = exact_trace
+        self.brute_force = brute_force
+        self.n_exact_terms = n_exact_terms
+        self.n_exact_terms_test = n_exact_terms_test
+        self.grad_in_forward = grad_in_forward
+        self.neumann_grad = neumann_grad
+        self.eps_forward = eps_forward
+        self.eps_backward = eps_backward
+        self.eps_sample = eps_sample
+        self.threshold = threshold
+        self.register_buffer('last_n_samples', torch.zeros(self.n_samples))
+        self.register_buffer('last_firmom', torch.zeros(1))
+        self.register_buffer('last_secmom', torch.zeros(1))
+        # hooks for tests / multi-GPU parity: inject the roulette draw and the probes
+        self._inject_n = None
+        self._inject_probes = None
+        self.solver_stats = {}
+
+    class Backward(Function):
+        """Identity in forward; implicit differentiation in backward (implicit_block.py:165-217):
+        solve v^T (I + J_z) = grad with Broyden, then dl_dx = v^T (I + J_x)."""
+        last_info = None
+
+        @staticmethod
+        def forward(ctx, nnet_z, nnet_x, z, x, *args):
+            ctx.save_for_backward(z, x)
+            ctx.nnet_z = nnet_z
+            ctx.nnet_x = nnet_x
+            ctx.args = args
+            return z
+
+        @staticmethod
+        def backward(ctx, grad):
+            grad = grad.clone()
+            z, x = ctx.saved_tensors
+            args = ctx.args
+            eps, threshold = args[-2:]
+            nnet_z, nnet_x = ctx.nnet_z, ctx.nnet_x
+            z = z.clone().detach().requires_grad_()
+            x = x.clone().detach().requires_grad_()
+            with torch.enable_grad():
+                Fz = nnet_z(z) + z
+
+            def g(v):     # v^T dFz/dz - grad: one vjp through the branch per call (:199-203)
+                (vJ,) = torch.autograd.grad(Fz, z, v, retain_graph=True)
+                return ops.lincomb3(vJ, 1.0, grad, -1.0)
+
+            info = broyden(g, torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
+            imBlock.Backward.last_info = info
+            dl_dh = info['result']
+            del Fz
+            with torch.enable_grad():
+                Fx = nnet_x(x) + x
+            (dl_dx,) = torch.autograd.grad(Fx, x, dl_dh)
+            return (None, None, dl_dh, dl_dx) + (None,) * len(args)
+
+    def forward(self, x, logpx=None, restore=False):
+        z0 = x.clone().detach()
+        if restore:
+            with torch.no_grad():
+                _ = self.nnet_x_copy(z0)
+                _ = self.nnet_z_copy(z0)
+        z = RootFind.apply(self.nnet_z, self.nnet_x, z0, z0, 'broyden', self.eps_forward, self.threshold)
+        self.solver_stats['fwd'] = RootFind.last_info
+        # re-attach: gradients reach the branch parameters through this expression (:227)
+        z = RootFind.f(self.nnet_z, self.nnet_x, z.detach(), z0) + z0
+        self.nnet_x_copy.load_state_dict(self.nnet_x.state_dict())
+        self.nnet_z_copy.load_state_dict(self.nnet_z.state_dict())
+        z = self.Backward.apply(self.nnet_z_copy, self.nnet_x_copy, z, x, 'broyden', self.eps_backward,
+                                self.threshold)
+        if logpx is None:
+            return z
+        return z, logpx - self._logdetgrad(z, x)
+
+    def inverse(self, z, logpy=None):
+        x0 = z.clone().detach()
+        x = RootFind.apply(self.nnet_x, self.nnet_z, x0, z, 'broyden', self.eps_sample, self.threshold)
+        self.solver_stats['inv'] = RootFind.last_info
+        if logpy is None:
+            return x
+        return x, logpy + self._logdetgrad(z, x)
+
+    # --------------------------------------------------------------------------------------
+    def _draw_n(self):
+        if self._inject_n is not None:
+            return np.asarray(self._inject_n)
+        if self.n_dist == 'geometric':
+            return geometric_sample(torch.sigmoid(self.geom_p).item(), self.n_samples)
+        return poisson_sample(self.lamb.item(), self.n_samples)
+
+    def _rcdf(self, k, offset):
+        if self.n_dist == 'geometric':
+            return geometric_1mcdf(torch.sigmoid(self.geom_p).item(), k, offset)
+        return poisson_1mcdf(self.lamb.item(), k, offset)
+
+    def _draw_probes(self, x, z):
+        if self._inject_probes is not None:
+            vx, vz = self._inject_probes
+            return vx.to(x), vz.to(z)
+        if PROBE_MODE['mode'] == 'device':
+            vx = torch.randint(0, 2, x.shape, device=x.device).to(x) * 2 - 1
+            vz = torch.randint(0, 2, z.shape, device=z.device).to(z) * 2 - 1
+            return vx, vz
+        bern = torch.distributions.bernoulli.Bernoulli(torch.Tensor([0.5]))
+        vx = bern.sample(x.shape).reshape(x.shape).to(x) * 2 - 1
+        vz = bern.sample(z.shape).reshape(z.shape).to(z) * 2 - 1
+        return vx, vz
+
+    def _logdetgrad(self, z, x):
+        """logdet |dz/dx| = logdet(I + J_x) - logdet(I + J_z)  (implicit_block.py:245-350)."""
+        with torch.enable_grad():
+            if (self.brute_force or not self.training) and (x.ndimension() == 2 and x.shape[1] <= 10):
+                x = x.requires_grad_(True)
+                z = z.requires_grad_(True)
+                Jx = batch_jacobian(x + self.nnet_x(x), x)
+                Jz = batch_jacobian(z + self.nnet_z(z), z)
+                return (torch.logdet(Jx) - torch.logdet(Jz)).view(-1, 1)
+
+            n_samples = None
+            if self.training and self.n_power_series is not None:
+                n_power_series = self.n_power_series          # truncated (biased) estimation
+                coeff_fn = lambda k: 1.
+            else:
+                n_exact = self.n_exact_terms if self.training else self.n_exact_terms_test
+                n_samples = self._draw_n()
+                n_power_series = int(max(n_samples) + n_exact)
+                coeff_fn = lambda k: 1 / self._rcdf(k, n_exact) * sum(n_samples >= k - n_exact) / len(n_samples)
+
+            if not self.exact_trace:
+                vareps_x, vareps_z = self._draw_probes(x, z)
+                if self.training and self.neumann_grad:
+                    estimator_fn = neumann_logdet_estimator
+                else:
+                    estimator_fn = basic_logdet_estimator
+                if self.training and self.grad_in_forward:
+                    logdet_x = mem_eff_wrapper(estimator_fn, self.nnet_x, x, n_power_series, vareps_x, coeff_fn,
+                                               self.training)
+                    logdet_z = mem_eff_wrapper(estimator_fn, self.nnet_z, z, n_power_series, vareps_z, coeff_fn,
+                                               self.training)
+                else:
+                    x = x.requires_grad_(True)
+                    z = z.requires_grad_(True)
+                    logdet_x = estimator_fn(self.nnet_x(x), x, n_power_series, vareps_x, coeff_fn, self.training)
+                    logdet_z = estimator_fn(self.nnet_z(z), z, n_power_series, vareps_z, coeff_fn, self.training)
+                logdetgrad = logdet_x - logdet_z
+            else:
+                x = x.requires_grad_(True)
+                z = z.requires_grad_(True)
+                logdetgrad = _exact_trace_series(self.nnet_x(x), x, n_power_series, coeff_fn) - \
+                    _exact_trace_series(self.nnet_z(z), z, n_power_series, coeff_fn)
+
+            if self.training and self.n_power_series is None:
+                self.last_n_samples.copy_(torch.tensor(n_samples).to(self.last_n_samples))
+                estimator = logdetgrad.detach()
+                self.last_firmom.copy_(torch.mean(estimator).to(self.last_firmom))
+                self.last_secmom.copy_(torch.mean(estimator ** 2).to(self.last_secmom))
+            return logdetgrad.view(-1, 1)
+
+    def extra_repr(self):
+        return ('dist={}, n_samples={}, n_power_series={}, neumann_grad={}, exact_trace={}, brute_force={}, '
+                'grad_in_forward={}'.format(self.n_dist, self.n_samples, self.n_power_series, self.neumann_grad,
+                                            self.exact_trace, self.brute_force, self.grad_in_forward))
+
+
+def batch_jacobian(g, x, create_graph=True):
+    """(B,d,d) Jacobian from d vjps (implicit_block.py:358-362)."""
+    rows = []
+    for j in range(g.shape[1]):
+        (r,) = torch.autograd.grad(torch.sum(g[:, j]), x, create_graph=create_graph)
+        rows.append(r.view(x.shape[0], 1, x.shape[1]))
+    return torch.cat(rows, 1)
+
+
+def batch_trace(M):
+    return M.view(M.shape[0], -1)[:, ::M.shape[1] + 1].sum(1)
+
+
+def _exact_trace_series(g, x, n_power_series, coeff_fn):
+    J = batch_jacobian(g, x)
+    out = batch_trace(J)
+    Jk = J
+    for k in range(2, n_power_series + 1):
+        Jk = torch.bmm(J, Jk)
+        out = out + (-1) ** (k + 1) / k * coeff_fn(k) * batch_trace(Jk)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# log-det estimators
+# ------------------------------------------------------------------------------------------
+
+class MemoryEfficientLogDetEstimator(torch.autograd.Function):
+    """Back-prop in forward: the gradients of the estimate w.r.t. x and the branch parameters
+    are taken immediately and only scaled in backward (implicit_block.py:373-415)."""
+
+    @staticmethod
+    def forward(ctx, estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training, *g_params):
+        ctx.training = training
+        with torch.enable_grad():
+            x = x.detach().requires_grad_(True)
+            g = gnet(x)
+            logdetgrad = estimator_fn(g, x, n_power_series, vareps, coeff_fn, training)
+            if training:
+                grad_x, *grad_params = torch.autograd.grad(logdetgrad.sum(), (x,) + g_params, retain_graph=False,
+                                                           allow_unused=True)
+                if grad_x is None:
+                    grad_x = torch.zeros_like(x)
+                ctx.none_mask = [gp is None for gp in grad_params]
+                ctx.save_for_backward(grad_x, *[gp if gp is not None else x.new_zeros(()) for gp in grad_params])
+        return safe_detach(logdetgrad)
+
+    @staticmethod
+    def backward(ctx, grad_logdetgrad):
+        if not ctx.training:
+            raise ValueError('Provide training=True if using backward.')
+        grad_x, *grad_params = ctx.saved_tensors
+        dL = grad_logdetgrad[0].detach()      # quirk #13: assumes a uniform upstream gradient
+        with torch.no_grad():
+            grad_x = grad_x * dL
+            grad_params = tuple(None if m else gp * dL for gp, m in zip(grad_params, ctx.none_mask))
+        return (None, None, grad_x, None, None, None, None) + grad_params
+
+
+def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training):
+    """sum_k (-1)^(k+1)/k coeff(k) <v^T J^k, v>  (implicit_block.py:418-426)."""
+    vjp = vareps
+    logdetgrad = torch.tensor(0.).to(x)
+    for k in range(1, n_power_series + 1):
+        vjp = torch.autograd.grad(g, x, vjp, create_graph=training, retain_graph=True)[0]
+        tr = ops.rowdot_fn(vjp, vareps)
+        logdetgrad = logdetgrad + (-1) ** (k + 1) / k * coeff_fn(k) * tr
+    return logdetgrad
+
+
+def neumann_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training):
+    """Neumann-series gradient estimator: a surrogate whose gradient is unbiased for the log-det
+    gradient (implicit_block.py:429-438)."""
+    vjp = vareps
+    neumann_vjp = vareps
+    with torch.no_grad():
+        for k in range(1, n_power_series + 1):
+            vjp = torch.autograd.grad(g, x, vjp, retain_graph=True)[0]
+            neumann_vjp = ops.lincomb3(neumann_vjp, 1.0, vjp, float((-1) ** k * coeff_fn(k)))
+    vjp_jac = torch.autograd.grad(g, x, neumann_vjp, create_graph=training)[0]
+    return ops.rowdot_fn(vjp_jac, vareps)
+
+
+def mem_eff_wrapper(estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training):
+    if not isinstance(gnet, nn.Module):
+        raise ValueError('g is required to be an instance of nn.Module.')
+    return MemoryEfficientLogDetEstimator.apply(estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training,
+                                                *list(gnet.parameters()))
+
+
+# ---- roulette helpers: python floats, global NumPy RNG (implicit_block.py:457-483) -----------
+
+def geometric_sample(p, n_samples):
+    return np.random.geometric(p, n_samples)
+
+
+def geometric_1mcdf(p, k, offset):
+    """P(n >= k - offset)"""
+    if k <= offset:
+        return 1.
+    k = k - offset
+    return (1 - p) ** max(k - 1, 0)
+
+
+def poisson_sample(lamb, n_samples):
+    return np.random.poisson(lamb, n_samples)
+
+
+def poisson_1mcdf(lamb, k, offset):
+    """P(n >= k - offset)"""
+    if k <= offset:
+        return 1.
+    k = k - offset
+    s = 1.
+    for i in range(1, k):
+        s += lamb ** i / math.factorial(i)
+    return 1 - np.exp(-lamb) * s
+
+
+def safe_detach(tensor):
+    return tensor.detach().requires_grad_(tensor.requires_grad)

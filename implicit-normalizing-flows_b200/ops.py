@@ -1,0 +1,365 @@
+"""Python-side operator layer over the C ABI.
+
+Two kinds of entry points:
+  * raw launchers (``act_mul``, ``gemm_nt`` ...): allocate outputs with torch, call the kernel
+    on the current CUDA stream; used directly on the no-grad hot loops (Broyden g evaluations,
+    Neumann vjp chain);
+  * ``torch.autograd.Function`` primitives built from those launchers whose backward passes are
+    expressed with the same primitives, so the graph can be differentiated repeatedly (the
+    log-det estimators differentiate through vjps: implicit_block.py:386-388, 418-438).
+"""
+import torch
+
+from . import _cabi
+
+ACT_NONE, ACT_SIN, ACT_LIPSWISH, ACT_RELU = 0, 1, 2, 3
+
+# GEMM backend policy: 'auto' uses the tcgen05 3xTF32 kernel whenever its layout constraints hold
+# and the problem is big enough to fill tiles; 'simt' forces the exact-fp32 CUDA-core kernel.
+_BACKEND = {'mode': 'auto', 'min_flops_tc': 2 * 128 * 128 * 64}
+
+
+def set_gemm_backend(mode):
+    assert mode in ('auto', 'simt', 'tc')
+    _BACKEND['mode'] = mode
+
+
+def get_gemm_backend():
+    return _BACKEND['mode']
+
+
+def _lib():
+    return _cabi.load()
+
+
+def _dense(t):
+    """A tensor whose memory is one dense block (contiguous in *some* permutation)."""
+    if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
+        return t
+    return t.contiguous()
+
+
+def _match_layout(t, ref):
+    """t laid out in memory exactly like ref (same strides)."""
+    if t.stride() == ref.stride() and t.shape == ref.shape:
+        return t
+    out = torch.empty_like(ref)
+    out.copy_(t)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# raw launchers
+# ------------------------------------------------------------------------------------------
+
+def act_mul(x, g, kind, order, beta_sp=None, out=None):
+    """out = g * act^(order)(x); x dense in any memory order, g (optional) in the same order."""
+    x = _dense(x)
+    if g is not None:
+        g = _match_layout(g, x)
+    if out is None:
+        out = torch.empty_like(x)
+    _cabi.check(_lib().impflow_act_mul(_cabi.ptr(x, 'x'), _cabi.ptr(g, 'g', True), _cabi.ptr(out, 'out'),
+                                       x.numel(), kind, order, _cabi.ptr(beta_sp, 'beta_sp', True),
+                                       _cabi.stream()), 'act_mul')
+    return out
+
+
+def act_beta_grad(x, g, order, beta_sp):
+    x = _dense(x)
+    g = _match_layout(g, x)
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    ws = torch.empty(int(_lib().impflow_reduce_workspace_floats(x.numel())), device=x.device, dtype=torch.float32)
+    _cabi.check(_lib().impflow_act_beta_grad(_cabi.ptr(x), _cabi.ptr(g), _cabi.ptr(out), _cabi.ptr(ws), x.numel(),
+                                             order, _cabi.ptr(beta_sp), _cabi.stream()), 'act_beta_grad')
+    return out
+
+
+def lincomb3(a, ca, b=None, cb=0.0, c=None, cc=0.0, out=None):
+    """out = ca*a + cb*b + cc*c (same shapes; laid out like a)."""
+    a = _dense(a)
+    if b is not None:
+        b = _match_layout(b, a)
+    if c is not None:
+        c = _match_layout(c, a)
+    if out is None:
+        out = torch.empty_like(a)
+    _cabi.check(_lib().impflow_lincomb3(_cabi.ptr(a), ca, _cabi.ptr(b, 'b', True), cb, _cabi.ptr(c, 'c', True), cc,
+                                        _cabi.ptr(out), a.numel(), _cabi.stream()), 'lincomb3')
+    return out
+
+
+def rowdot(a, c, out=None, alpha=1.0, beta=0.0):
+    """out[b] = beta*out[b] + alpha*<a[b], c[b]> over everything but dim 0."""
+    a = _dense(a)
+    c = _match_layout(c, a)
+    B = a.shape[0]
+    if out is None:
+        out = torch.empty(B, device=a.device, dtype=torch.float32)
+        beta = 0.0
+    _cabi.check(_lib().impflow_rowdot(_cabi.ptr(a), _cabi.ptr(c), _cabi.ptr(out), B, a.numel() // max(B, 1), alpha,
+                                      beta, _cabi.stream()), 'rowdot')
+    return out
+
+
+def colsum(a2d):
+    a2d = a2d.contiguous()
+    out = torch.empty(a2d.shape[1], device=a2d.device, dtype=torch.float32)
+    _cabi.check(_lib().impflow_colsum(_cabi.ptr(a2d), _cabi.ptr(out), a2d.shape[0], a2d.shape[1], _cabi.stream()),
+                'colsum')
+    return out
+
+
+def transpose2d(a2d):
+    a2d = a2d.contiguous()
+    out = torch.empty(a2d.shape[1], a2d.shape[0], device=a2d.device, dtype=torch.float32)
+    _cabi.check(_lib().impflow_transpose(_cabi.ptr(a2d), _cabi.ptr(out), a2d.shape[0], a2d.shape[1], _cabi.stream()),
+                'transpose')
+    return out
+
+
+def im2col3x3(x_nhwc):
+    x_nhwc = x_nhwc.contiguous()
+    B, H, W, C = x_nhwc.shape
+    col = torch.empty(B * H * W, 9 * C, device=x_nhwc.device, dtype=torch.float32)
+    _cabi.check(_lib().impflow_im2col3x3(_cabi.ptr(x_nhwc), _cabi.ptr(col), B, H, W, C, _cabi.stream()), 'im2col3x3')
+    return col
+
+
+def col2im3x3(col, B, H, W, C, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, want_act=False,
+              dmul_pre=None):
+    col = col.contiguous()
+    dev = col.device
+    pre = torch.empty(B, H, W, C, device=dev, dtype=torch.float32) if (want_pre or dmul_pre is not None) else None
+    act = torch.empty(B, H, W, C, device=dev, dtype=torch.float32) if want_act else None
+    _cabi.check(_lib().impflow_col2im3x3(_cabi.ptr(col), B, H, W, C, _cabi.ptr(bias, 'bias', True),
+                                         _cabi.ptr(pre, 'pre', True), _cabi.ptr(act, 'act', True),
+                                         _cabi.ptr(dmul_pre, 'dmul', True), act_kind,
+                                         _cabi.ptr(beta_sp, 'beta', True), _cabi.stream()), 'col2im3x3')
+    return pre, act
+
+
+def split_tf32(a):
+    a = a.contiguous()
+    hi = torch.empty_like(a)
+    lo = torch.empty_like(a)
+    _cabi.check(_lib().impflow_split_tf32(_cabi.ptr(a), _cabi.ptr(hi), _cabi.ptr(lo), a.numel(), _cabi.stream()),
+                'split_tf32')
+    return hi, lo
+
+
+def _tc_ok(M, N, K, lda, ldb):
+    mode = _BACKEND['mode']
+    if mode == 'simt':
+        return False
+    ok = (K % 32 == 0) and (lda % 4 == 0) and (ldb % 4 == 0)
+    if mode == 'tc':
+        return ok
+    return ok and (2 * M * N * K >= _BACKEND['min_flops_tc']) and M >= 128 and N >= 16
+
+
+def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, want_act=False, dmul_pre=None,
+            A_split=None, B_split=None, want_split=False):
+    """C = A @ Bm^T (+bias) with the fused epilogue.  A (M,K), Bm (N,K) row-major.
+
+    Returns (pre, act, split) where split is None or the (hi, lo) tf32 planes of the value that
+    feeds the next GEMM (only produced by the tcgen05 backend)."""
+    A = A.contiguous()
+    Bm = Bm.contiguous()
+    M, K = A.shape
+    N = Bm.shape[0]
+    assert Bm.shape[1] == K, 'gemm_nt: inner dimensions differ'
+    dev = A.device
+    need_pre = want_pre or dmul_pre is not None
+    pre = torch.empty(M, N, device=dev, dtype=torch.float32) if need_pre else None
+    act = torch.empty(M, N, device=dev, dtype=torch.float32) if want_act else None
+    if dmul_pre is not None:
+        dmul_pre = dmul_pre.contiguous()
+    lib = _lib()
+    if _tc_ok(M, N, K, K, K):
+        Ah, Al = A_split if A_split is not None else split_tf32(A)
+        Bh, Bl = B_split if B_split is not None else split_tf32(Bm)
+        sh = torch.empty(M, N, device=dev, dtype=torch.float32) if want_split else None
+        sl = torch.empty(M, N, device=dev, dtype=torch.float32) if want_split else None
+        _cabi.check(lib.impflow_gemm_nt_tc(_cabi.ptr(Ah), _cabi.ptr(Al), K, _cabi.ptr(Bh), _cabi.ptr(Bl), K,
+                                           _cabi.ptr(bias, 'bias', True), _cabi.ptr(pre, 'pre', True),
+                                           _cabi.ptr(act, 'act', True), _cabi.ptr(dmul_pre, 'dmul', True),
+                                           _cabi.ptr(sh, 'sh', True), _cabi.ptr(sl, 'sl', True), N, M, N, K,
+                                           act_kind, _cabi.ptr(beta_sp, 'beta', True), _cabi.stream()),
+                    'gemm_nt_tc')
+        return pre, act, ((sh, sl) if want_split else None)
+    _cabi.check(lib.impflow_gemm_nt(_cabi.ptr(A), K, _cabi.ptr(Bm), K, _cabi.ptr(bias, 'bias', True),
+                                    _cabi.ptr(pre, 'pre', True), _cabi.ptr(act, 'act', True),
+                                    _cabi.ptr(dmul_pre, 'dmul', True), N, M, N, K, act_kind,
+                                    _cabi.ptr(beta_sp, 'beta', True), _cabi.stream()), 'gemm_nt')
+    return pre, act, None
+
+
+def sn_power_iter(W2d, u, v, n_iterations, atol, rtol):
+    """In-place power iteration on (u, v); returns (sigma (1,), iters (1,) int32) device tensors."""
+    W2d = W2d.contiguous()
+    sigma = torch.empty(1, device=W2d.device, dtype=torch.float32)
+    iters = torch.zeros(1, device=W2d.device, dtype=torch.int32)
+    n_it = -1 if n_iterations is None else int(n_iterations)
+    _cabi.check(_lib().impflow_sn_power_iter(_cabi.ptr(W2d), _cabi.ptr(u), _cabi.ptr(v), _cabi.ptr(sigma),
+                                             _cabi.iptr(iters), W2d.shape[0], W2d.shape[1], n_it,
+                                             float(atol if atol is not None else 0.0),
+                                             float(rtol if rtol is not None else 0.0), _cabi.stream()),
+                'sn_power_iter')
+    return sigma, iters
+
+
+# ------------------------------------------------------------------------------------------
+# differentiable primitives (closed under differentiation)
+# ------------------------------------------------------------------------------------------
+
+class _ActMul(torch.autograd.Function):
+    """out = g * f^(order)(x; beta).  d/dg = f^(order), d/dx = g f^(order+1), d/dbeta via reduction."""
+
+    @staticmethod
+    def forward(ctx, x, g, beta_sp, kind, order):
+        ctx.kind, ctx.order = kind, order
+        ctx.has_g = g is not None
+        ctx.save_for_backward(x, g if g is not None else x.new_empty(0), beta_sp if beta_sp is not None else x.new_empty(0))
+        return act_mul(x, g, kind, order, beta_sp)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, g, beta_sp = ctx.saved_tensors
+        g = g if ctx.has_g else None
+        beta_sp = beta_sp if beta_sp.numel() else None
+        kind, order = ctx.kind, ctx.order
+        gx = gg = gbeta = None
+        inner = gout if g is None else gout * g
+        if ctx.needs_input_grad[0]:
+            if kind == ACT_RELU and order >= 1:
+                gx = torch.zeros_like(x)
+            elif order + 1 > 3:
+                raise RuntimeError('impflow_b200: activation derivatives above order 3 are not implemented')
+            else:
+                gx = _ActMul.apply(x, inner, beta_sp, kind, order + 1)
+        if g is not None and ctx.needs_input_grad[1]:
+            gg = _ActMul.apply(x, gout, beta_sp, kind, order)
+        if beta_sp is not None and ctx.needs_input_grad[2]:
+            if order > 2:
+                raise RuntimeError('impflow_b200: beta gradient above order 2 is not implemented')
+            gbeta = act_beta_grad(x, inner.detach(), order, beta_sp.detach()).view_as(beta_sp)
+        return gx, gg, gbeta, None, None
+
+
+def activation(x, kind, beta_sp=None):
+    return _ActMul.apply(x, None, beta_sp, kind, 0)
+
+
+class _Transpose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a):
+        return transpose2d(a)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Transpose.apply(g)
+
+
+class _ColSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a):
+        ctx.M = a.shape[0]
+        return colsum(a)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.unsqueeze(0).expand(ctx.M, -1)
+
+
+class _GemmNT(torch.autograd.Function):
+    """C = A B^T + bias;  dA = G B = G (B^T)^T,  dB = G^T A,  dbias = colsum(G)."""
+
+    @staticmethod
+    def forward(ctx, A, Bm, bias):
+        ctx.save_for_backward(A, Bm)
+        ctx.has_bias = bias is not None
+        pre, _, _ = gemm_nt(A, Bm, bias)
+        return pre
+
+    @staticmethod
+    def backward(ctx, G):
+        A, Bm = ctx.saved_tensors
+        gA = gB = gbias = None
+        G = G.contiguous()
+        if ctx.needs_input_grad[0]:
+            gA = _GemmNT.apply(G, _Transpose.apply(Bm), None)
+        if ctx.needs_input_grad[1]:
+            gB = _GemmNT.apply(_Transpose.apply(G), _Transpose.apply(A), None)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gbias = _ColSum.apply(G)
+        return gA, gB, gbias
+
+
+def linear(x2d, W, bias=None):
+    return _GemmNT.apply(x2d, W, bias)
+
+
+class _Im2col(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_nhwc):
+        ctx.shape = tuple(x_nhwc.shape)
+        return im2col3x3(x_nhwc)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, C = ctx.shape
+        return _Col2im.apply(g, B, H, W, C)
+
+
+class _Col2im(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, col, B, H, W, C):
+        pre, _ = col2im3x3(col, B, H, W, C)
+        return pre
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Im2col.apply(g), None, None, None, None
+
+
+def conv3x3_nhwc(x_nhwc, W_oihw, bias=None):
+    """3x3 / stride 1 / pad 1 cross-correlation on an NHWC tensor (F.conv2d semantics,
+    mixed_lipschitz.py:391) as im2col+GEMM (narrow input) or GEMM+col2im (narrow output)."""
+    B, H, Wd, Cin = x_nhwc.shape
+    Cout = W_oihw.shape[0]
+    if Cin <= Cout:
+        Wr = W_oihw.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)           # (co, ky, kx, ci)
+        y = _GemmNT.apply(_Im2col.apply(x_nhwc), Wr, bias)
+        return y.view(B, H, Wd, Cout)
+    W2 = W_oihw.flip(2, 3).permute(2, 3, 0, 1).reshape(9 * Cout, Cin)    # (ky, kx, co) <- flipped taps
+    Y = _GemmNT.apply(x_nhwc.reshape(B * H * Wd, Cin), W2, None)
+    y = _Col2im.apply(Y, B, H, Wd, Cout)
+    if bias is not None:
+        y = y + bias
+    return y
+
+
+def conv1x1_nhwc(x_nhwc, W_oihw, bias=None):
+    B, H, Wd, Cin = x_nhwc.shape
+    Cout = W_oihw.shape[0]
+    y = _GemmNT.apply(x_nhwc.reshape(B * H * Wd, Cin), W_oihw.reshape(Cout, Cin), bias)
+    return y.view(B, H, Wd, Cout)
+
+
+class _RowDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, c):
+        ctx.save_for_backward(a, c)
+        return rowdot(a, c)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, c = ctx.saved_tensors
+        shape = [-1] + [1] * (a.dim() - 1)
+        gv = g.view(*shape)
+        return (gv * c if ctx.needs_input_grad[0] else None), (gv * a if ctx.needs_input_grad[1] else None)
+
+
+def rowdot_fn(a, c):
+    return _RowDot.apply(a, c)

@@ -1,0 +1,156 @@
+/*
+ * impflow_b200.h — C ABI of libimpflow_b200.so (sm_100a).
+ *
+ * The reference (musikisomorphie/implicit-normalizing-flows) has no FFI: its boundary for the
+ * hot path is the Python module API.  This header is the C-ABI layer the
+ * Python host classes in `implicit-normalizing-flows_b200/` bind with ctypes; every entry
+ * point names the reference code it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *  - all tensor arguments are DEVICE pointers to dense fp32 unless stated; the caller
+ *    (PyTorch) owns every buffer including workspaces; nothing here allocates or frees.
+ *  - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it and never
+ *    synchronise unless stated.
+ *  - return 0 on success, negative on error; the message is available through
+ *    impflow_last_error() (thread-local).
+ */
+#ifndef IMPFLOW_B200_H
+#define IMPFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMPFLOW_ABI_VERSION 1
+
+/* activation kinds (lib/layers/base/activations.py:7-12 Sin, :64-71 Swish; torch.nn.ReLU) */
+#define IMPFLOW_ACT_NONE 0
+#define IMPFLOW_ACT_SIN 1
+#define IMPFLOW_ACT_LIPSWISH 2
+#define IMPFLOW_ACT_RELU 3
+
+int impflow_version(void);
+const char* impflow_last_error(void);
+/* number of kernels launched by this library in this process so far (bench.py gpu_launches) */
+long long impflow_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Broyden solver algebra — replaces lib/layers/broyden.py:101-193 (rmatvec, matvec, the
+ * rank-1 update, norms, best-iterate tracking, break rules).  g itself is evaluated by the
+ * caller between calls.  History is kept as U^T (B,T,d) and V^T (B,T,d), row-contiguous.
+ *
+ * Device state (int32/float/double words, see BroydenState in csrc/broyden.cu):
+ *   the caller allocates impflow_broyden_state_bytes(T) bytes and may copy it to the host to
+ *   read nstep / lowest_step / flags / trace.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t nstep;        /* iterations done (broyden.py:155) */
+  int32_t lowest_step;  /* step of the best iterate (:162) */
+  int32_t active;       /* 1 while the while-condition (:153) still holds */
+  int32_t prot_break;   /* protective break fired (:169-172) */
+  int32_t converged;    /* objective < eps (:163) */
+  int32_t stagnated;    /* stagnation rule fired (:165-168) */
+  int32_t do_update;    /* the last step must apply the rank-1 update (:174-181) */
+  int32_t new_lowest;   /* the last step improved the best iterate (:159-162) */
+  int32_t threshold;
+  int32_t counter;      /* internal: last-block election */
+  double eps;           /* eps * sqrt(B*d) (:131) */
+  double init_objective;
+  double lowest;
+  double objective;     /* latest ||g||_F */
+  double trace[64];     /* trace[0..nstep]; threshold <= 63 */
+} impflow_broyden_state;
+
+size_t impflow_broyden_state_bytes(void);
+
+/* After the caller evaluated g0 = g(x0):  init state, low_x=x0, low_g=g0, xn = x0 + (-g0)
+ * (broyden.py:136-151).  sample_sq (B) receives per-sample ||g0||^2, low_sq (B) a copy;
+ * `partial` is a float workspace of impflow_broyden_workspace_floats(B,d,T) elements. */
+int impflow_broyden_begin(const float* x0, const float* g0, float* xn, float* low_x, float* low_g,
+                          float* sample_sq, float* low_sq, float* partial, impflow_broyden_state* state,
+                          int B, long long d, int threshold, double eps_scaled, void* stream);
+
+/* After the caller evaluated gn = g(xn): one loop body of broyden.py:153-181.
+ *  - norms + bookkeeping + break rules on the device (state updated);
+ *  - if the step must update: v^T, u (NaN scrub), store in slot (nstep-1), next direction,
+ *    and x_next = xn + update is written into `x_old`'s buffer (the caller then swaps roles:
+ *    x_old<->xn, g_old<->gn);
+ *  - if the step improved the best iterate: low_x=xn, low_g=gn, low_sq=sample_sq.
+ * `partial` is a float workspace of impflow_broyden_workspace_floats(B,d,T) elements. */
+size_t impflow_broyden_workspace_floats(int B, long long d, int threshold);
+int impflow_broyden_step(float* x_old, const float* g_old, const float* xn, const float* gn, float* Ut,
+                         float* Vt, float* low_x, float* low_g, float* sample_sq, float* low_sq,
+                         float* partial, impflow_broyden_state* state, int B, long long d, int threshold,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Elementwise / reductions on the path
+ * ------------------------------------------------------------------------------------------ */
+/* out = g * act^(order)(x) (g may be NULL -> 1).  order 0..3; beta_sp = DEVICE pointer to the
+ * scalar softplus(beta) for LipSwish (NULL otherwise) — a pointer so that no host sync is needed.  Replaces activations.py:11-12,70-71 and their autograd derivatives. */
+int impflow_act_mul(const float* x, const float* g, float* out, long long n, int kind, int order,
+                    const float* beta_sp, void* stream);
+/* out[0] = sum_i g[i] * d/d(beta_sp) act^(order)(x[i])  (order 0..2); deterministic 2-stage
+ * reduce; `partial` needs impflow_reduce_workspace_floats(n) floats. */
+size_t impflow_reduce_workspace_floats(long long n);
+int impflow_act_beta_grad(const float* x, const float* g, float* out, float* partial, long long n,
+                          int order, const float* beta_sp, void* stream);
+/* out = a*ca + b*cb + c*cc (b, c may be NULL). Solver residuals x_embed - f(z) - z
+ * (implicit_block.py:72) and v J + v - grad (:199-203); Neumann accumulation (:435). */
+int impflow_lincomb3(const float* a, float ca, const float* b, float cb, const float* c, float cc,
+                     float* out, long long n, void* stream);
+/* out[b] = beta*out[b] + alpha * <a[b,:], c[b,:]>  — Hutchinson trace term
+ * (implicit_block.py:423,437). */
+int impflow_rowdot(const float* a, const float* c, float* out, int B, long long d, float alpha, float beta,
+                   void* stream);
+/* out[n] = sum_m a[m,n]  (bias gradient). */
+int impflow_colsum(const float* a, float* out, long long M, int N, void* stream);
+/* out[n,m] = a[m,n] */
+int impflow_transpose(const float* a, float* out, long long M, long long N, void* stream);
+/* NHWC 3x3, stride 1, pad 1 patch gather col[(b,y,x),(ky,kx,c)] = x[b,y+ky-1,x+kx-1,c], and its
+ * adjoint (scatter-sum) with the same fused epilogue as impflow_gemm_nt (N = C, ldc = C). */
+int impflow_im2col3x3(const float* x, float* col, int B, int H, int W, int C, void* stream);
+int impflow_col2im3x3(const float* col, int B, int H, int W, int C, const float* bias, float* pre_out,
+                      float* act_out, const float* dmul_pre, int act_kind, const float* beta_sp, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Residual-branch contractions — replace F.linear / F.conv2d and their vjps
+ * (mixed_lipschitz.py:134-136, 388-391; implicit_block.py:422,434,436).
+ *   C[M,N] = A[M,K] * B[N,K]^T  (+ bias[N])   fp32 in / fp32 accumulate.
+ * Epilogue (all optional, NULL = off):
+ *   pre_out  <- acc + bias                       (pre-activation, kept for the vjp)
+ *   act_out  <- act(acc + bias)                  (input of the next layer)
+ *   dmul_pre : if set, pre_out <- acc * act'(dmul_pre[m,n])   (vjp through the activation)
+ * impflow_gemm_nt     : exact-fp32 CUDA-core tiles (any M,N,K; small MLP shapes, cross-check).
+ * impflow_gemm_nt_tc  : tcgen05 3xTF32 (TMA-fed, TMEM accumulators).  Operands come as tf32 hi/lo
+ *                       planes (a = hi + lo, see impflow_split_tf32); needs K % 32 == 0 and rows that
+ *                       are 16-byte aligned (returns -2 otherwise).  split_hi/split_lo (optional)
+ *                       receive the hi/lo planes of the value that feeds the next GEMM
+ *                       (act_out value, or the act' product in dmul mode).
+ * ------------------------------------------------------------------------------------------ */
+int impflow_gemm_nt(const float* A, long long lda, const float* Bm, long long ldb, const float* bias,
+                    float* pre_out, float* act_out, const float* dmul_pre, long long ldc, long long M,
+                    int N, int K, int act_kind, const float* beta_sp, void* stream);
+int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long long lda, const float* B_hi,
+                       const float* B_lo, long long ldb, const float* bias, float* pre_out, float* act_out,
+                       const float* dmul_pre, float* split_hi, float* split_lo, long long ldc, long long M,
+                       int N, int K, int act_kind, const float* beta_sp, void* stream);
+/* a -> tf32 "hi" (round-to-nearest) and "lo" = a - hi planes used by the 3xTF32 backend. */
+int impflow_split_tf32(const float* a, float* hi, float* lo, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Induced 2-norm power iteration for a dense (out,in) matrix — replaces
+ * mixed_lipschitz.py:85-123 (Linear) and :276-319 (1x1 conv).  One CTA, device-side early
+ * exit with the reference tolerance rule; u, v updated in place; sigma[0] = u^T W v,
+ * iters[0] = iterations used.  n_iterations < 0 means "tolerance mode, cap 200".
+ * ------------------------------------------------------------------------------------------ */
+int impflow_sn_power_iter(const float* W, float* u, float* v, float* sigma, int* iters, int out_f,
+                          int in_f, int n_iterations, float atol, float rtol, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMPFLOW_B200_H */

@@ -1,0 +1,210 @@
+"""GPU parity tests of the individual CUDA kernels, called through the C ABI (ctypes)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import impflow_oracle as orc
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    import impflow_b200
+    return impflow_b200.ops
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (7, 5, 3), (100, 128, 2), (1000, 128, 128), (257, 6, 128),
+                                   (64, 43, 64), (300, 200, 77), (4096, 512, 512)])
+def test_gemm_simt(ops, M, N, K):
+    ops.set_gemm_backend('simt')
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (A.double() @ B.double().t() + bias.double())
+    pre, act, _ = ops.gemm_nt(A.cuda(), B.cuda(), bias.cuda(), act_kind=ops.ACT_SIN, want_pre=True, want_act=True)
+    assert rel_err(pre.cpu(), ref) < 2e-6          # fp32 accumulate
+    assert rel_err(act.cpu(), orc.sin_act(ref.float())) < 1e-5
+    ops.set_gemm_backend('auto')
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 32), (256, 512, 512), (1000, 128, 128), (4096, 512, 512),
+                                   (130, 27, 64), (777, 108, 512), (2048, 432, 96), (128, 16, 32), (65536, 512, 32)])
+def test_gemm_tcgen05_3xtf32(ops, M, N, K):
+    """tolerance: 3xTF32 keeps ~22 mantissa bits per operand -> 1e-5 rel stated by north_star."""
+    ops.set_gemm_backend('tc')
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g) / np.sqrt(K)
+    bias = torch.randn(N, generator=g)
+    ref = (A.double() @ B.double().t() + bias.double())
+    pre, act, split = ops.gemm_nt(A.cuda(), B.cuda(), bias.cuda(), act_kind=ops.ACT_RELU, want_pre=True,
+                                  want_act=True, want_split=True)
+    torch.cuda.synchronize()
+    assert rel_err(pre.cpu(), ref) < 3e-6
+    assert rel_err(act.cpu(), torch.relu(ref)) < 3e-6
+    hi, lo = split
+    assert rel_err((hi + lo).cpu(), act.cpu()) < 1e-7
+    # exact-fp32 CUDA-core kernel agrees as well
+    ops.set_gemm_backend('simt')
+    pre2, _, _ = ops.gemm_nt(A.cuda(), B.cuda(), bias.cuda())
+    assert rel_err(pre.cpu(), pre2.cpu()) < 3e-6
+    ops.set_gemm_backend('auto')
+
+
+def test_gemm_tcgen05_dmul(ops):
+    ops.set_gemm_backend('tc')
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 512, 256, 128
+    A, B, P = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / 11, torch.randn(M, N, generator=g)
+    beta = torch.tensor([0.9])
+    Pd = P.clone().requires_grad_(True)
+    (d1,) = torch.autograd.grad(orc.lipswish(Pd, beta).sum(), Pd)
+    ref = (A.double() @ B.double().t()) * d1.double()
+    pre, _, _ = ops.gemm_nt(A.cuda(), B.cuda(), None, act_kind=ops.ACT_LIPSWISH,
+                            beta_sp=F.softplus(beta).cuda(), dmul_pre=P.cuda())
+    assert rel_err(pre.cpu(), ref) < 5e-6
+    ops.set_gemm_backend('auto')
+
+
+def test_activation_orders_vs_golden(ops, golden):
+    fx = golden('activations')
+    x = torch.from_numpy(fx['x']).cuda()
+    bsp = F.softplus(torch.tensor([0.5])).cuda()
+    for name, kind, b in (('sin', ops.ACT_SIN, None), ('swish', ops.ACT_LIPSWISH, bsp)):
+        for order, key in enumerate(['y', 'd1', 'd2', 'd3']):
+            out = ops.act_mul(x, None, kind, order, b).cpu().numpy()
+            np.testing.assert_allclose(out, fx[name + '_' + key], rtol=2e-5, atol=2e-5)
+    # beta gradient of sum(w * swish(x))
+    beta = torch.tensor([0.5], requires_grad=True, device='cuda')
+    import impflow_b200
+    y = impflow_b200.ops.activation(x, ops.ACT_LIPSWISH, F.softplus(beta))
+    (gb,) = torch.autograd.grad((y * torch.from_numpy(fx['swish_w']).cuda()).sum(), beta)
+    np.testing.assert_allclose(gb.cpu().numpy(), fx['swish_grad_beta'], rtol=1e-4)
+
+
+def test_elementwise_helpers(ops):
+    g = torch.Generator().manual_seed(3)
+    for shape in [(5, 7), (64, 3072), (3, 1001)]:
+        a, b, c = (torch.randn(*shape, generator=g) for _ in range(3))
+        out = ops.lincomb3(a.cuda(), 1.0, b.cuda(), -1.0, c.cuda(), -0.5).cpu()
+        torch.testing.assert_close(out, a - b - 0.5 * c, rtol=1e-6, atol=1e-6)
+        d = ops.rowdot(a.cuda(), b.cuda()).cpu()
+        torch.testing.assert_close(d, (a.double() * b.double()).sum(1).float(), rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(ops.colsum(a.cuda()).cpu(), a.double().sum(0).float(), rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(ops.transpose2d(a.cuda()).cpu(), a.t().contiguous())
+        hi, lo = ops.split_tf32(a.cuda())
+        torch.testing.assert_close((hi + lo).cpu(), a, rtol=0, atol=0)
+        assert int((hi.cpu().view(torch.int32) & 0x1FFF).abs().max()) == 0     # tf32-representable
+
+
+def test_im2col_col2im(ops):
+    g = torch.Generator().manual_seed(4)
+    B, H, W, C = 3, 6, 5, 4
+    x = torch.randn(B, C, H, W, generator=g)
+    col = ops.im2col3x3(x.permute(0, 2, 3, 1).contiguous().cuda()).cpu()
+    ref = F.unfold(x, 3, padding=1).view(B, C, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * C)
+    torch.testing.assert_close(col, ref)
+    # adjoint: <im2col(x), y> == <x, col2im(y)>
+    y = torch.randn(B * H * W, 9 * C, generator=g)
+    back, _ = ops.col2im3x3(y.cuda(), B, H, W, C)
+    lhs = (col.double() * y.double()).sum()
+    rhs = (x.permute(0, 2, 3, 1).double() * back.cpu().double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+@pytest.mark.parametrize('cin,cout', [(3, 16), (16, 3), (8, 8)])
+def test_conv3x3_matches_conv2d(ops, cin, cout):
+    g = torch.Generator().manual_seed(cin * 31 + cout)
+    x = torch.randn(2, cin, 8, 8, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / 5
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), 1, 1)
+    y = ops.conv3x3_nhwc(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), b.cuda()).permute(0, 3, 1, 2)
+    assert rel_err(y.cpu(), ref) < 3e-6
+    # gradients through the kernel primitives
+    xg = x.clone().cuda().requires_grad_(True)
+    wg = w.clone().cuda().requires_grad_(True)
+    y = ops.conv3x3_nhwc(xg.permute(0, 2, 3, 1).contiguous(), wg, b.cuda()).permute(0, 3, 1, 2)
+    t = torch.randn(ref.shape, generator=g)
+    gx, gw = torch.autograd.grad((y * t.cuda()).sum(), (xg, wg))
+    xr, wr = x.clone().double().requires_grad_(True), w.clone().double().requires_grad_(True)
+    gxr, gwr = torch.autograd.grad((F.conv2d(xr, wr, b.double(), 1, 1) * t.double()).sum(), (xr, wr))
+    assert rel_err(gx.cpu(), gxr) < 5e-6
+    assert rel_err(gw.cpu(), gwr) < 5e-6
+
+
+def test_sn_power_iter_vs_golden(ops, golden):
+    fx = golden('induced_norm')
+    W = torch.from_numpy(fx['lin_weight2']).cuda()
+    u, v = torch.from_numpy(fx['lin_init_u']).cuda(), torch.from_numpy(fx['lin_init_v']).cuda()
+    sigma, iters = ops.sn_power_iter(W, u, v, None, 1e-3, 1e-3)
+    np.testing.assert_allclose(u.cpu().numpy(), fx['lin_u_tol'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(v.cpu().numpy(), fx['lin_v_tol'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(sigma.cpu().numpy()[0], fx['lin_scale_tol'], rtol=1e-5)
+    sigma, iters = ops.sn_power_iter(W, u, v, 5, 0.0, 0.0)
+    assert int(iters.item()) == 5
+    np.testing.assert_allclose(u.cpu().numpy(), fx['lin_u_it5'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(sigma.cpu().numpy()[0], fx['lin_scale_it5'], rtol=1e-5)
+    # iteration count of the tolerance rule equals the oracle's
+    W0 = torch.from_numpy(fx['lin_weight2'])
+    _, _, used = orc.power_iterate_matrix(W0, torch.from_numpy(fx['lin_init_u']), torch.from_numpy(fx['lin_init_v']),
+                                          None, 1e-3, 1e-3)
+    u, v = torch.from_numpy(fx['lin_init_u']).cuda(), torch.from_numpy(fx['lin_init_v']).cuda()
+    _, iters = ops.sn_power_iter(W, u, v, None, 1e-3, 1e-3)
+    assert int(iters.item()) == used
+
+
+@pytest.mark.parametrize('tag', ['small', 'wide', 'capped', 'long', 'protbreak'])
+def test_broyden_vs_golden(golden, tag):
+    import impflow_b200
+    fx = golden('broyden_analytic')
+    B, d, T, eps, scale, gain = fx[tag + '_meta']
+    W, c = torch.from_numpy(fx[tag + '_W']).cuda(), torch.from_numpy(fx[tag + '_c']).cuda()
+    if gain < 0:
+        g = lambda x: c - float(scale) * torch.tanh(x @ W) - x
+    else:
+        g = lambda x: c + float(gain) * x
+    res = impflow_b200.layers.broyden.broyden(g, torch.zeros(int(B), int(d), device='cuda'), int(T), float(eps))
+    nstep, lowest_step, prot = fx[tag + '_ints']
+    trace_ref = fx[tag + '_trace']
+    assert int(res['prot_break']) == prot
+    if tag == 'long':
+        # 30 non-converging steps of a chaotic map: fp32 round-off decorrelates the late iterates;
+        # the iteration COUNT is still exact and the early trace agrees.
+        assert res['nstep'] == nstep
+        np.testing.assert_allclose(res['trace'][:6], trace_ref[:6], rtol=1e-3)
+        return
+    assert res['nstep'] == nstep
+    assert res['lowest_step'] == lowest_step
+    np.testing.assert_allclose(res['trace'][:3], trace_ref[:3], rtol=1e-5)
+    assert rel_err(res['result'].cpu(), fx[tag + '_result']) < 1e-5
+    np.testing.assert_allclose(res['diff'], fx[tag + '_diff'], rtol=0.5, atol=1e-6)
+    assert res['diff_detail'].shape == (int(B),)
+
+
+@pytest.mark.parametrize('B,d', [(3, 2), (5, 130), (4, 3072), (2, 16384), (2, 65536), (3, 1026)])
+def test_broyden_shapes_against_oracle(B, d):
+    """Same seeded contraction solved by the CUDA solver and by the CPU oracle at several sizes
+    (warp-per-sample, single-CTA, multi-CTA cluster and non-float4 paths)."""
+    import impflow_b200
+    g = torch.Generator().manual_seed(d)
+    c = torch.randn(B, d, generator=g)
+    a = torch.rand(d, generator=g) * 0.8 + 0.1
+    shift = 7 if d > 7 else 1
+    f_cpu = lambda x: c - 0.6 * torch.sin(x * a + torch.roll(x, shift, 1)) - x
+    cg, ag = c.cuda(), a.cuda()
+    f_gpu = lambda x: cg - 0.6 * torch.sin(x * ag + torch.roll(x, shift, 1)) - x
+    ref = orc.broyden_solve(f_cpu, torch.zeros(B, d), 30, 1e-6)
+    res = impflow_b200.layers.broyden.broyden(f_gpu, torch.zeros(B, d, device='cuda'), 30, 1e-6)
+    assert res['nstep'] == ref['nstep'], (res['trace'], ref['trace'])
+    assert res['lowest_step'] == ref['lowest_step']
+    assert rel_err(res['result'].cpu(), ref['result']) < 1e-5
+    np.testing.assert_allclose(res['trace'][:-1], ref['trace'][:-1], rtol=2e-3)
