@@ -73,14 +73,27 @@ def check(rc, what):
         raise RuntimeError('%s failed (%d): %s' % (what, rc, last_error()))
 
 
+def require_device(t, what='tensor'):
+    """The product has no CPU execution path: every tensor handed to a kernel must be on a GPU."""
+    if not t.is_cuda:
+        raise RuntimeError('impflow_b200: %s must be a CUDA tensor (no CPU fallback exists for this path)' % what)
+
+
+def pinned_bytes(n):
+    return torch.zeros(n, dtype=torch.uint8).pin_memory()
+
+
+def sync_stream():
+    torch.cuda.current_stream().synchronize()
+
+
 def ptr(t, name='tensor', allow_none=False):
     """Device pointer of a dense fp32 CUDA tensor (memory order is the caller's business)."""
     if t is None:
         if allow_none:
             return None
         raise ValueError('%s is None' % name)
-    if not t.is_cuda:
-        raise RuntimeError('impflow_b200: %s must be a CUDA tensor (no CPU fallback exists for this path)' % name)
+    require_device(t, name)
     if t.dtype != torch.float32:
         raise RuntimeError('impflow_b200: %s must be float32, got %s' % (name, t.dtype))
     return ctypes.c_void_p(t.data_ptr())
@@ -89,7 +102,7 @@ def ptr(t, name='tensor', allow_none=False):
 def iptr(t):
     if t is None:
         return None
-    assert t.is_cuda
+    require_device(t, 'int tensor')
     return ctypes.c_void_p(t.data_ptr())
 
 

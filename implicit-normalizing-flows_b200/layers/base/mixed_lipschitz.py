@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torch.nn.init as init
 
-from ... import ops
+from ... import _cabi, ops
 
 __all__ = ['InducedNormLinear', 'InducedNormConv2d']
 
@@ -26,8 +26,7 @@ def _check_norms(domain, codomain):
 
 
 def _require_cuda(t, what):
-    if not t.is_cuda:
-        raise RuntimeError('impflow_b200: %s must live on a CUDA device (no CPU fallback)' % what)
+    _cabi.require_device(t, what)
 
 
 class _Sigma(torch.autograd.Function):

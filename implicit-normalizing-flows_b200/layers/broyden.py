@@ -39,11 +39,11 @@ class _Workspace(object):
         nbytes = int(lib.impflow_broyden_state_bytes())
         assert nbytes == _STATE_DTYPE.itemsize, 'state layout mismatch between header and host'
         self.state = torch.zeros(nbytes, device=device, dtype=torch.uint8)
-        self.state_host = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+        self.state_host = _cabi.pinned_bytes(nbytes)
 
     def read_state(self):
         self.state_host.copy_(self.state, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        _cabi.sync_stream()
         return self.state_host.numpy().view(_STATE_DTYPE)[0]
 
 
@@ -63,8 +63,7 @@ def broyden(g_, x0, threshold, eps, ls=False, name='unknown'):
     if ls:
         raise NotImplementedError('impflow_b200: the Armijo line search is dead code in the reference '
                                   '(both call sites use ls=False) and is not implemented')
-    if not x0.is_cuda:
-        raise RuntimeError('impflow_b200.broyden: x0 must be a CUDA tensor (no CPU fallback)')
+    _cabi.require_device(x0, 'broyden x0')
     lib = _cabi.load()
     shape = x0.shape
     B = shape[0]

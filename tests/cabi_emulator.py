@@ -1,0 +1,365 @@
+"""TEST INFRASTRUCTURE ONLY — a numpy emulation of the C ABI in include/impflow_b200.h.
+
+The CPU test-suite (`-m "not gpu"`) uses it to exercise the *host* logic of the product package
+(autograd wiring of the kernel primitives, weight re-layouts for the conv-as-GEMM paths, the
+Broyden host loop, RNG / coefficient handling, state-dict compatibility) without a GPU.  It
+restates what each kernel computes, with the same formulas as the .cu sources, on host memory
+addressed by the raw pointers the product passes.  It is never importable from the product and
+nothing here is timed or shipped; the GPU tests (`-m gpu`) run the real kernels.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+ACT_NONE, ACT_SIN, ACT_LIPSWISH, ACT_RELU = 0, 1, 2, 3
+
+
+def _addr(p):
+    if p is None:
+        return None
+    if isinstance(p, ctypes.c_void_p):
+        return p.value
+    return int(p)
+
+
+def _f32(p, n):
+    a = _addr(p)
+    if a is None:
+        return None
+    return np.ctypeslib.as_array((ctypes.c_float * int(n)).from_address(a))
+
+
+def _act(kind, x, order, beta):
+    x = x.astype(np.float32)
+    if kind == ACT_NONE:
+        return x if order == 0 else (np.ones_like(x) if order == 1 else np.zeros_like(x))
+    if kind == ACT_SIN:
+        two_pi = np.float32(2 * math.pi)
+        s, c = np.sin(two_pi * x), np.cos(two_pi * x)
+        return [s / np.float32(math.pi) * np.float32(0.5), c, -two_pi * s, -two_pi * two_pi * c][order]
+    if kind == ACT_RELU:
+        return [np.maximum(x, 0), (x > 0).astype(np.float32), np.zeros_like(x), np.zeros_like(x)][order]
+    bx = beta * x
+    s = 1 / (1 + np.exp(-bx))
+    q = s * (1 - s)
+    inv = np.float32(1 / 1.1)
+    if order == 0:
+        return x * s * inv
+    if order == 1:
+        return (s + bx * q) * inv
+    if order == 2:
+        return (2 * beta * q + beta * bx * q * (1 - 2 * s)) * inv
+    return (3 * beta * beta * q * (1 - 2 * s) + beta * beta * bx * q * (1 - 6 * s + 6 * s * s)) * inv
+
+
+def _dbeta(x, order, beta):
+    bx = beta * x
+    s = 1 / (1 + np.exp(-bx))
+    q = s * (1 - s)
+    r1, r2 = 1 - 2 * s, 1 - 6 * s + 6 * s * s
+    inv = 1 / 1.1
+    if order == 0:
+        return x * x * q * inv
+    if order == 1:
+        return (2 * x * q + bx * x * q * r1) * inv
+    return (2 * q + 4 * bx * q * r1 + bx * bx * q * r2) * inv
+
+
+def _beta(p):
+    return None if _addr(p) is None else np.float32(_f32(p, 1)[0])
+
+
+def _epilogue(acc, bias, pre_out, act_out, dmul_pre, act_kind, beta, split_hi=None, split_lo=None):
+    """acc: (M,N) float32; outputs are flat views written in place."""
+    if dmul_pre is not None:
+        nxt = (acc * _act(act_kind, dmul_pre.reshape(acc.shape), 1, beta)).astype(np.float32)
+        if pre_out is not None:
+            pre_out[:] = nxt.ravel()
+    else:
+        v = acc + (bias[None, :] if bias is not None else 0)
+        v = v.astype(np.float32)
+        if pre_out is not None:
+            pre_out[:] = v.ravel()
+        nxt = _act(act_kind, v, 0, beta).astype(np.float32)
+        if act_out is not None:
+            act_out[:] = nxt.ravel()
+    if split_hi is not None:
+        hi = _tf32(nxt)
+        split_hi[:] = hi.ravel()
+        split_lo[:] = (nxt - hi).ravel()
+
+
+def _tf32(a):
+    b = a.astype(np.float32).view(np.uint32).astype(np.uint64)
+    b = (b + 0x1000) & 0xFFFFE000          # round to nearest (ties away), keep 10 mantissa bits
+    return b.astype(np.uint32).view(np.float32)
+
+
+STATE_DTYPE = np.dtype([('nstep', '<i4'), ('lowest_step', '<i4'), ('active', '<i4'), ('prot_break', '<i4'),
+                        ('converged', '<i4'), ('stagnated', '<i4'), ('do_update', '<i4'), ('new_lowest', '<i4'),
+                        ('threshold', '<i4'), ('counter', '<i4'), ('eps', '<f8'), ('init_objective', '<f8'),
+                        ('lowest', '<f8'), ('objective', '<f8'), ('trace', '<f8', (64,))])
+
+
+def _state(p):
+    buf = (ctypes.c_uint8 * STATE_DTYPE.itemsize).from_address(_addr(p))
+    return np.ctypeslib.as_array(buf).view(STATE_DTYPE)
+
+
+class EmulatedLib(object):
+    """Attribute-compatible stand-in for the ctypes CDLL of libimpflow_b200.so."""
+
+    def __init__(self):
+        self.launches = 0
+        self._err = b''
+
+    # ---- misc ----
+    def impflow_version(self):
+        return 1
+
+    def impflow_last_error(self):
+        return self._err
+
+    def impflow_launch_count(self):
+        return self.launches
+
+    def impflow_broyden_state_bytes(self):
+        return STATE_DTYPE.itemsize
+
+    def impflow_broyden_workspace_floats(self, B, d, T):
+        return B * 64
+
+    def impflow_reduce_workspace_floats(self, n):
+        return 148 * 16
+
+    # ---- broyden (csrc/broyden.cu) ----
+    def _decide(self, st, total, init):
+        s = st[0]
+        obj = float(np.float32(np.sqrt(total)))
+        s['objective'] = obj
+        if init:
+            s['nstep'] = 0
+            s['lowest_step'] = 0
+            s['init_objective'] = obj
+            s['lowest'] = obj
+            s['trace'][0] = obj
+            for k in ('prot_break', 'converged', 'stagnated', 'do_update', 'new_lowest'):
+                s[k] = 0
+            s['active'] = int(obj >= s['eps'] and 0 < s['threshold'])
+            return
+        T = int(s['threshold'])
+        nstep = int(s['nstep']) + 1
+        s['nstep'] = nstep
+        s['trace'][nstep] = obj
+        new_low = 0
+        if obj < s['lowest']:
+            s['lowest'] = obj
+            s['lowest_step'] = nstep
+            new_low = 1
+        s['new_lowest'] = new_low
+        conv = int(obj < s['eps'])
+        stag = 0
+        if not conv and obj < 3 * s['eps'] and nstep == T:
+            tr = s['trace'][nstep - T + 1:nstep + 1]
+            stag = int(np.max(tr) / np.min(tr) < 1.3)
+        prot = int((not conv) and (not stag) and obj > s['init_objective'] * 1e6)
+        s['converged'], s['stagnated'], s['prot_break'] = conv, stag, prot
+        upd = 0 if (conv or stag or prot) else 1
+        s['do_update'] = upd
+        s['active'] = int(bool(upd) and obj >= s['eps'] and nstep < T)
+
+    def impflow_broyden_begin(self, x0, g0, xn, low_x, low_g, sample_sq, low_sq, partial, state, B, d, T, eps, stream):
+        n = B * d
+        x0, g0, xn, low_x, low_g = (_f32(p, n) for p in (x0, g0, xn, low_x, low_g))
+        ssq, lsq = _f32(sample_sq, B), _f32(low_sq, B)
+        st = _state(state)
+        st[0]['threshold'] = T
+        st[0]['eps'] = eps
+        st[0]['counter'] = 0
+        low_x[:] = x0
+        low_g[:] = g0
+        xn[:] = x0 + (-g0)
+        ssq[:] = (g0.reshape(B, d) ** 2).sum(1)
+        lsq[:] = ssq
+        self._decide(st, float(ssq.astype(np.float64).sum()), True)
+        self.launches += 2
+        return 0
+
+    def impflow_broyden_step(self, x_old, g_old, xn, gn, Ut, Vt, low_x, low_g, sample_sq, low_sq, partial, state,
+                             B, d, T, stream):
+        n = B * d
+        x_old, g_old, xn, gn, low_x, low_g = (_f32(p, n) for p in (x_old, g_old, xn, gn, low_x, low_g))
+        U, V = _f32(Ut, B * T * d).reshape(B, T, d), _f32(Vt, B * T * d).reshape(B, T, d)
+        ssq, lsq = _f32(sample_sq, B), _f32(low_sq, B)
+        st = _state(state)
+        with np.errstate(all='ignore'):
+            ssq[:] = (gn.reshape(B, d) ** 2).sum(1)
+            self._decide(st, float(ssq.astype(np.float64).sum()), False)
+            s = st[0]
+            if s['new_lowest']:
+                lsq[:] = ssq
+                low_x[:] = xn
+                low_g[:] = gn
+            self.launches += 2
+            if not s['do_update']:
+                return 0
+            k = int(s['nstep']) - 1
+            X, G = xn.reshape(B, d), gn.reshape(B, d)
+            dx, dg = X - x_old.reshape(B, d), G - g_old.reshape(B, d)
+            Uk, Vk = U[:, :k], V[:, :k]
+            a = np.einsum('bi,bji->bj', dx, Uk)
+            bb = np.einsum('bji,bi->bj', Vk, dg)
+            c = np.einsum('bji,bi->bj', Vk, G)
+            vT = -dx + np.einsum('bj,bji->bi', a, Vk)
+            w = -dg + np.einsum('bj,bji->bi', bb, Uk)
+            S = np.einsum('bj,bji->bi', c, Uk)
+            den = (vT * dg).sum(1, keepdims=True)
+            vs = np.where(np.isnan(vT), 0, vT).astype(np.float32)
+            ck = (vs * G).sum(1, keepdims=True)
+            u = (dx - w) / den
+            u = np.where(np.isnan(u), 0, u).astype(np.float32)
+            V[:, k] = vs
+            U[:, k] = u
+            upd = -((-G) + (S + u * ck))
+            x_old.reshape(B, d)[:] = X + upd
+        return 0
+
+    # ---- elementwise (csrc/elementwise.cu) ----
+    def impflow_act_mul(self, x, g, out, n, kind, order, beta_sp, stream):
+        xv, gv, ov = _f32(x, n), _f32(g, n), _f32(out, n)
+        with np.errstate(all='ignore'):
+            r = _act(kind, xv, order, _beta(beta_sp))
+        ov[:] = r if gv is None else r * gv
+        self.launches += 1
+        return 0
+
+    def impflow_act_beta_grad(self, x, g, out, partial, n, order, beta_sp, stream):
+        xv, gv = _f32(x, n).astype(np.float64), _f32(g, n).astype(np.float64)
+        _f32(out, 1)[0] = np.float32((gv * _dbeta(xv, order, float(_beta(beta_sp)))).sum())
+        self.launches += 2
+        return 0
+
+    def impflow_lincomb3(self, a, ca, b, cb, c, cc, out, n, stream):
+        r = _f32(a, n) * np.float32(ca)
+        if _addr(b) is not None:
+            r = r + _f32(b, n) * np.float32(cb)
+        if _addr(c) is not None:
+            r = r + _f32(c, n) * np.float32(cc)
+        _f32(out, n)[:] = r
+        self.launches += 1
+        return 0
+
+    def impflow_rowdot(self, a, c, out, B, d, alpha, beta, stream):
+        av, cv, ov = _f32(a, B * d).reshape(B, d), _f32(c, B * d).reshape(B, d), _f32(out, B)
+        dot = (av * cv).sum(1)
+        ov[:] = (0 if beta == 0 else beta * ov) + alpha * dot
+        self.launches += 1
+        return 0
+
+    def impflow_colsum(self, a, out, M, N, stream):
+        _f32(out, N)[:] = _f32(a, M * N).reshape(M, N).sum(0)
+        self.launches += 1
+        return 0
+
+    def impflow_transpose(self, a, out, M, N, stream):
+        _f32(out, M * N)[:] = _f32(a, M * N).reshape(M, N).T.ravel()
+        self.launches += 1
+        return 0
+
+    def impflow_im2col3x3(self, x, col, B, H, W, C, stream):
+        xv = _f32(x, B * H * W * C).reshape(B, H, W, C)
+        xp = np.zeros((B, H + 2, W + 2, C), np.float32)
+        xp[:, 1:-1, 1:-1] = xv
+        cv = _f32(col, B * H * W * 9 * C).reshape(B, H, W, 9, C)
+        for tap in range(9):
+            ky, kx = tap // 3, tap % 3
+            cv[:, :, :, tap] = xp[:, ky:ky + H, kx:kx + W]
+        self.launches += 1
+        return 0
+
+    def impflow_col2im3x3(self, col, B, H, W, C, bias, pre_out, act_out, dmul_pre, act_kind, beta_sp, stream):
+        cv = _f32(col, B * H * W * 9 * C).reshape(B, H, W, 9, C)
+        acc = np.zeros((B, H + 2, W + 2, C), np.float32)
+        for tap in range(9):
+            ky, kx = tap // 3, tap % 3
+            acc[:, ky:ky + H, kx:kx + W] += cv[:, :, :, tap]
+        acc = acc[:, 1:-1, 1:-1].reshape(B * H * W, C)
+        n = B * H * W * C
+        _epilogue(acc, _f32(bias, C), _f32(pre_out, n), _f32(act_out, n), _f32(dmul_pre, n), act_kind,
+                  _beta(beta_sp))
+        self.launches += 1
+        return 0
+
+    def impflow_split_tf32(self, a, hi, lo, n, stream):
+        av = _f32(a, n)
+        h = _tf32(av)
+        _f32(hi, n)[:] = h
+        _f32(lo, n)[:] = av - h
+        self.launches += 1
+        return 0
+
+    # ---- GEMMs (csrc/gemm_simt.cu, csrc/gemm_tcgen05.cu) ----
+    def impflow_gemm_nt(self, A, lda, Bm, ldb, bias, pre_out, act_out, dmul_pre, ldc, M, N, K, act_kind, beta_sp,
+                        stream):
+        assert lda == K and ldb == K and ldc == N
+        acc = (_f32(A, M * K).reshape(M, K) @ _f32(Bm, N * K).reshape(N, K).T).astype(np.float32)
+        _epilogue(acc, _f32(bias, N), _f32(pre_out, M * N), _f32(act_out, M * N), _f32(dmul_pre, M * N), act_kind,
+                  _beta(beta_sp))
+        self.launches += 1
+        return 0
+
+    def impflow_gemm_nt_tc(self, A_hi, A_lo, lda, B_hi, B_lo, ldb, bias, pre_out, act_out, dmul_pre, split_hi,
+                           split_lo, ldc, M, N, K, act_kind, beta_sp, stream):
+        if K % 32 or lda % 4 or ldb % 4:
+            self._err = b'gemm_nt_tc: layout'
+            return -2
+        ah, al = _f32(A_hi, M * K).reshape(M, K).astype(np.float64), _f32(A_lo, M * K).reshape(M, K).astype(np.float64)
+        bh, bl = _f32(B_hi, N * K).reshape(N, K).astype(np.float64), _f32(B_lo, N * K).reshape(N, K).astype(np.float64)
+        acc = (al @ bh.T + ah @ bl.T + ah @ bh.T).astype(np.float32)
+        _epilogue(acc, _f32(bias, N), _f32(pre_out, M * N), _f32(act_out, M * N), _f32(dmul_pre, M * N), act_kind,
+                  _beta(beta_sp), _f32(split_hi, M * N), _f32(split_lo, M * N))
+        self.launches += 1
+        return 0
+
+    # ---- spectral (csrc/spectral.cu) ----
+    def impflow_sn_power_iter(self, W, u, v, sigma, iters, out_f, in_f, n_iterations, atol, rtol, stream):
+        Wm = _f32(W, out_f * in_f).reshape(out_f, in_f)
+        uv, vv = _f32(u, out_f), _f32(v, in_f)
+        nrm = lambda t: t / max(np.float32(np.sqrt((t * t).sum())), np.float32(1e-12))
+        tol_mode = n_iterations < 0
+        used = 0
+        un, vn = uv.copy(), vv.copy()
+        for _ in range(200 if tol_mode else n_iterations):
+            ou, ov = un, vn
+            un = nrm(Wm @ vn).astype(np.float32)
+            vn = nrm(Wm.T @ un).astype(np.float32)
+            used += 1
+            if tol_mode:
+                err_u = np.sqrt(((un - ou) ** 2).sum()) / np.sqrt(out_f)
+                err_v = np.sqrt(((vn - ov) ** 2).sum()) / np.sqrt(in_f)
+                if err_u < atol + rtol * un.max() and err_v < atol + rtol * vn.max():
+                    break
+        _f32(sigma, 1)[0] = np.float32(un @ (Wm @ vn))
+        if _addr(iters) is not None:
+            np.ctypeslib.as_array((ctypes.c_int32 * 1).from_address(_addr(iters)))[0] = used
+        if used > 0:
+            uv[:] = un
+            vv[:] = vn
+        self.launches += 1
+        return 0
+
+
+def install(monkeypatch):
+    """Route the product's C-ABI calls to the numpy emulation for the duration of one test."""
+    import impflow_b200
+    cabi = impflow_b200._cabi
+    lib = EmulatedLib()
+    monkeypatch.setattr(cabi, '_lib', lib)
+    monkeypatch.setattr(cabi, 'load', lambda: lib)
+    monkeypatch.setattr(cabi, 'require_device', lambda t, what='tensor': None)
+    monkeypatch.setattr(cabi, 'pinned_bytes', lambda n: torch.zeros(n, dtype=torch.uint8))
+    monkeypatch.setattr(cabi, 'sync_stream', lambda: None)
+    monkeypatch.setattr(cabi, 'stream', lambda: None)
+    return lib

@@ -1,243 +1,47 @@
-"""GPU parity of the imBlock / ImplicitFlow module API against fixtures produced by the
-unmodified reference (tests/golden).  State dicts are loaded with the reference's own keys.
-
-Tolerances (BASELINE.json north_star): forward Broyden iteration counts exact; z within 1e-5
-rel; log-det within 1e-4 rel.  Backward-solve counts are asserted only where the reference's
-own trace clears eps with margin — several fixtures sit at fp32 round-off (eps_backward=1e-10,
-SURVEY.md §7 hard part 2) and end on the 30-step cap or a NaN objective."""
-import numpy as np
+"""GPU parity of the imBlock / ImplicitFlow module API against the reference's golden fixtures
+(real kernels, through the C ABI).  The cases live in tests/imblock_cases.py."""
 import pytest
-import torch
 
-from tests.helpers import rel_err, sub_sd
+from tests import imblock_cases as cases
 
 pytestmark = pytest.mark.gpu
 
 
-def _pkg():
-    import impflow_b200
-    return impflow_b200
+@pytest.fixture(autouse=True)
+def _on_gpu():
+    cases.DEV['device'] = 'cuda'
+    yield
 
 
-def build_mlp(layers, dims, coeff, n_iterations, tol, data_dim):
-    mods = []
-    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
-        if i > 0:
-            mods.append(layers.base.Sin())
-        mods.append(layers.base.get_linear(a, b, coeff=coeff, n_iterations=n_iterations, atol=tol, rtol=tol,
-                                           domain=2, codomain=2, zero_init=(b == data_dim)))
-    return torch.nn.Sequential(*mods)
-
-
-def build_conv_branch(layers, c, idim, coeff, tol, leading_act):
-    mods = []
-    if leading_act:
-        mods.append(layers.base.Swish())
-    mk = lambda a, b, k: layers.base.get_conv2d(a, b, k, 1, k // 2, coeff=coeff, n_iterations=None, domain=2,
-                                                codomain=2, atol=tol, rtol=tol)
-    mods += [mk(c, idim, 3), layers.base.Swish(), mk(idim, idim, 1), layers.base.Swish(), mk(idim, c, 3)]
-    return torch.nn.Sequential(*mods)
-
-
-def std_normal_logprob(z):
-    return -0.5 * np.log(2 * np.pi) - z.pow(2) / 2
-
-
-def load_block(blk, fx, tag, x):
-    blk = blk.cuda()
-    with torch.no_grad():
-        blk(x, restore=True)         # lazy u/v shaping before loading (train_img.py:481-500)
-    sd = {k: v.cuda() for k, v in sub_sd(fx, tag + '_sd_').items()}
-    missing, unexpected = blk.load_state_dict(sd, strict=True)
-    assert not missing and not unexpected
-    return blk
-
-
-def run_train(blk, fx, tag, inject=True):
-    blk.train()
-    x = torch.from_numpy(fx[tag + '_x']).cuda().requires_grad_(True)
-    if inject:
-        blk._inject_n = fx[tag + '_n_draws'].astype(np.int64)
-        blk._inject_probes = (torch.from_numpy(fx[tag + '_vareps_x']), torch.from_numpy(fx[tag + '_vareps_z']))
-    else:
-        np.random.seed(int(fx[tag + '_seed']))
-        torch.manual_seed(int(fx[tag + '_seed']))
-    z, dlogp = blk(x, torch.zeros(x.shape[0], 1, device='cuda'))
-    logpz = std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True)
-    loss = -(logpz - dlogp).mean()
-    loss.backward()
-    return x, z, dlogp, loss
-
-
-def check_train(blk, fx, tag, x, z, dlogp, loss, bwd_exact=False, grad_tol=1e-3):
-    pkg = _pkg()
-    assert blk.solver_stats['fwd']['nstep'] == int(fx[tag + '_fwd_nstep'][0])
-    bwd = pkg.layers.imBlock.Backward.last_info['nstep']
-    print('%s: fwd nstep %d  bwd nstep %d (reference %d)' % (tag, blk.solver_stats['fwd']['nstep'], bwd,
-                                                            int(fx[tag + '_bwd_nstep'][0])))
-    if bwd_exact:
-        assert bwd == int(fx[tag + '_bwd_nstep'][0])
-    assert rel_err(z.detach().cpu(), fx[tag + '_z']) < 1e-5
-    assert rel_err(dlogp.detach().cpu(), fx[tag + '_dlogp']) < 1e-4
-    np.testing.assert_allclose(loss.item(), fx[tag + '_loss'], rtol=1e-5)
-    assert rel_err(x.grad.cpu(), fx[tag + '_grad_x']) < grad_tol
-    worst = 0.0
-    for n, p in blk.named_parameters():
-        key = tag + '_grad_' + n
-        if key in fx:
-            assert p.grad is not None, n
-            worst = max(worst, rel_err(p.grad.cpu(), fx[key]))
-    assert worst < grad_tol, worst
-
-
-MLP = {
-    'toy': dict(dims=[2, 32, 32, 2], n_it=20, tol=None, kw=dict(n_dist='geometric', brute_force=True, n_samples=1,
-                                                                neumann_grad=False, grad_in_forward=False)),
-    'tab6': dict(dims=[6, 64, 64, 6], n_it=None, tol=1e-3, kw=dict(n_dist='geometric', n_samples=1, n_exact_terms=2,
-                                                                   neumann_grad=False, grad_in_forward=False,
-                                                                   eps_forward=1e-5)),
-    'tab43': dict(dims=[43, 64, 64, 43], n_it=None, tol=1e-3, kw=dict(n_dist='geometric', n_samples=1,
-                                                                      n_exact_terms=2, neumann_grad=False,
-                                                                      grad_in_forward=False, eps_forward=1e-5)),
-}
-
-
-def make_mlp_block(tag):
-    layers = _pkg().layers
-    c = MLP[tag]
-    d = c['dims'][0]
-    return layers.imBlock(build_mlp(layers, c['dims'], 0.99, c['n_it'], c['tol'], d),
-                          build_mlp(layers, c['dims'], 0.99, c['n_it'], c['tol'], d), **c['kw'])
-
-
-@pytest.mark.parametrize('tag', list(MLP))
+@pytest.mark.parametrize('tag', list(cases.MLP))
 def test_imblock_mlp_train(golden, tag):
-    fx = golden('imblock_mlp')
-    blk = load_block(make_mlp_block(tag), fx, tag, torch.from_numpy(fx[tag + '_x']).cuda())
-    x, z, dlogp, loss = run_train(blk, fx, tag)
-    check_train(blk, fx, tag, x, z, dlogp, loss, bwd_exact=(tag == 'toy'))
+    cases.case_imblock_mlp_train(golden, tag)
 
 
 @pytest.mark.parametrize('tag', ['tab6', 'tab43'])
 def test_imblock_mlp_train_reference_rng(golden, tag):
-    """No injection: the product draws n and the probes with the reference's own RNG calls."""
-    fx = golden('imblock_mlp')
-    blk = load_block(make_mlp_block(tag), fx, tag, torch.from_numpy(fx[tag + '_x']).cuda())
-    x, z, dlogp, loss = run_train(blk, fx, tag, inject=False)
-    np.testing.assert_array_equal(blk.last_n_samples.cpu().numpy(), fx[tag + '_n_draws'])   # term counts exact
-    assert rel_err(dlogp.detach().cpu(), fx[tag + '_dlogp']) < 1e-4
+    cases.case_imblock_mlp_train_reference_rng(golden, tag)
 
 
 @pytest.mark.parametrize('tag', ['tab6', 'tab43'])
 def test_imblock_mlp_eval_and_inverse(golden, tag):
-    fx = golden('imblock_mlp')
-    blk = load_block(make_mlp_block(tag), fx, tag, torch.from_numpy(fx[tag + '_x']).cuda())
-    blk.eval()
-    if tag + 'eval_n_draws' in fx:
-        blk._inject_n = fx[tag + 'eval_n_draws'].astype(np.int64)
-    if tag + 'eval_vareps_x' in fx:
-        blk._inject_probes = (torch.from_numpy(fx[tag + 'eval_vareps_x']), torch.from_numpy(fx[tag + 'eval_vareps_z']))
-    x = torch.from_numpy(fx[tag + '_x']).cuda()
-    z, dlogp = blk(x, torch.zeros(x.shape[0], 1, device='cuda'))
-    assert blk.solver_stats['fwd']['nstep'] == int(fx[tag + 'eval_fwd_nstep'][0])
-    assert rel_err(z.detach().cpu(), fx[tag + 'eval_z']) < 1e-5
-    assert rel_err(dlogp.detach().cpu(), fx[tag + 'eval_dlogp']) < 1e-4
-    with torch.no_grad():
-        x_rec = blk.inverse(torch.from_numpy(fx[tag + '_z']).cuda())
-    assert blk.solver_stats['inv']['nstep'] == int(fx[tag + '_inv_nstep'][0])
-    assert rel_err(x_rec.cpu(), fx[tag + '_x_rec']) < 1e-5
-    assert rel_err(x_rec.cpu(), fx[tag + '_x']) < 1e-3           # round trip
+    cases.case_imblock_mlp_eval_and_inverse(golden, tag)
 
 
-CONV = {
-    'cifar': dict(lead=True, kw=dict(n_dist='poisson', n_samples=1, n_exact_terms=3, neumann_grad=True,
-                                     grad_in_forward=True)),
-    'cifar_basic': dict(lead=False, kw=dict(n_dist='poisson', n_samples=1, n_exact_terms=3, neumann_grad=False,
-                                            grad_in_forward=False)),
-}
-
-
-@pytest.mark.parametrize('tag', list(CONV))
+@pytest.mark.parametrize('tag', list(cases.CONV))
 @pytest.mark.parametrize('backend', ['simt', 'auto'])
 def test_imblock_conv_train(golden, tag, backend):
-    pkg = _pkg()
-    pkg.ops.set_gemm_backend(backend)
-    try:
-        fx = golden('imblock_conv')
-        layers = pkg.layers
-        c = CONV[tag]
-        blk = layers.imBlock(build_conv_branch(layers, 4, 32, 0.9, 1e-3, c['lead']),
-                             build_conv_branch(layers, 4, 32, 0.9, 1e-3, c['lead']), **c['kw'])
-        blk = load_block(blk, fx, tag, torch.from_numpy(fx[tag + '_x']).cuda())
-        x, z, dlogp, loss = run_train(blk, fx, tag)
-        check_train(blk, fx, tag, x, z, dlogp, loss, grad_tol=2e-3)
-    finally:
-        pkg.ops.set_gemm_backend('auto')
+    cases.case_imblock_conv_train(golden, tag, backend)
 
 
 def test_imblock_classifier_block(golden):
-    pkg = _pkg()
-    layers = pkg.layers
-    fx = golden('imblock_conv')
-    mk = lambda a, b: layers.base.get_conv2d(a, b, kernel_size=3, stride=1, padding=1, bias=False, coeff=0.9,
-                                             n_iterations=None, domain=2, codomain=2, atol=1e-3, rtol=1e-3)
-    net = lambda: torch.nn.Sequential(mk(8, 16), torch.nn.ReLU(), mk(16, 8), torch.nn.ReLU())
-    blk = load_block(layers.imBlock(net(), net()), fx, 'cls', torch.from_numpy(fx['cls_x']).cuda())
-    blk.train()
-    x = torch.from_numpy(fx['cls_x']).cuda().requires_grad_(True)
-    z = blk(x)
-    loss = (z ** 2).mean()
-    loss.backward()
-    assert blk.solver_stats['fwd']['nstep'] == int(fx['cls_fwd_nstep'][0])
-    print('cls bwd nstep %d (reference %d)' % (layers.imBlock.Backward.last_info['nstep'], int(fx['cls_bwd_nstep'][0])))
-    assert rel_err(z.detach().cpu(), fx['cls_z']) < 1e-5
-    np.testing.assert_allclose(loss.item(), fx['cls_loss'], rtol=1e-5)
-    assert rel_err(x.grad.cpu(), fx['cls_grad_x']) < 1e-3
-    for n, p in blk.named_parameters():
-        if 'cls_grad_' + n in fx:
-            assert rel_err(p.grad.cpu(), fx['cls_grad_' + n]) < 2e-3, n
+    cases.case_imblock_classifier_block(golden)
 
 
 def test_implicit_flow_density_step(golden):
-    """Whole multiscale model (LogitTransform, ActNorm2d, imBlock, Squeeze) at the reference's
-    CIFAR recipe, scaled down: bits/dim, solver counts, reconstruction (train_img.py:517-549)."""
-    pkg = _pkg()
-    layers = pkg.layers
-    fx = golden('flow_small')
-    B, c, hw = 4, 3, 8
-    model = pkg.ImplicitFlow(
-        (B, c, hw, hw), n_blocks=[1, 1], intermediate_dim=16, factor_out=False, quadratic=False,
-        init_layer=layers.LogitTransform(0.05), actnorm=True, fc_actnorm=False, batchnorm=False, dropout=0.,
-        fc=False, coeff=0.9, vnorms='2222', n_lipschitz_iters=None, sn_atol=1e-3, sn_rtol=1e-3,
-        n_power_series=None, n_dist='poisson', n_samples=1, kernels='3-1-3', activation_fn='swish', fc_end=False,
-        fc_idim=128, n_exact_terms=3, preact=True, neumann_grad=True, grad_in_forward=True, first_resblock=True,
-        learn_p=False, classification=False, classification_hdim=64, n_classes=10).cuda()
-    x = torch.from_numpy(fx['x']).cuda()
-    with torch.no_grad():
-        model(x, restore=True)
-    sd = {k: v.cuda() for k, v in sub_sd(fx, 'sd_').items()}
-    model.load_state_dict(sd, strict=True)
-    model.train()
-    np.random.seed(int(fx['seed']))
-    torch.manual_seed(int(fx['seed']))
-    z, dlogp = model(x, 0)
-    ndim = c * hw * hw
-    logpz = std_normal_logprob(z).view(z.size(0), -1).sum(1, keepdim=True)
-    bpd = -torch.mean(logpz - dlogp - np.log(256) * ndim) / ndim / np.log(2)
-    bpd.backward()
-    blocks = [m for m in model.modules() if isinstance(m, layers.imBlock)]
-    assert [b.solver_stats['fwd']['nstep'] for b in blocks] == fx['fwd_nstep'].tolist()
-    np.testing.assert_array_equal(np.stack([b.last_n_samples.cpu().numpy() for b in blocks]), fx['n_draws'])
-    assert rel_err(z.detach().cpu(), fx['z']) < 1e-5
-    assert rel_err(dlogp.detach().cpu(), fx['dlogp']) < 1e-4
-    np.testing.assert_allclose(bpd.item(), fx['bpd'], rtol=1e-5)
-    worst = 0.0
-    for n, p in model.named_parameters():
-        if 'grad_' + n in fx and p.grad is not None:
-            worst = max(worst, rel_err(p.grad.cpu(), fx['grad_' + n]))
-    assert worst < 5e-3, worst
-    model.eval()
-    with torch.no_grad():
-        x_rec = model(z.detach(), inverse=True)
-    assert rel_err(x_rec.cpu(), fx['x_rec']) < 1e-4
-    assert rel_err(x_rec.cpu(), fx['x']) < 1e-3
+    cases.case_implicit_flow_density_step(golden)
+
+
+def test_smoke_entry():
+    import __graft_entry__
+    __graft_entry__.smoke()

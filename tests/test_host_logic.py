@@ -1,0 +1,138 @@
+"""CPU tests of the product's HOST logic (autograd wiring of the kernel primitives, conv-as-GEMM
+weight layouts, Broyden host loop, RNG / roulette handling, state-dict compatibility) with the
+C ABI replaced by the numpy emulator in tests/cabi_emulator.py.  The same cases run against the
+real kernels in test_gpu_imblock.py."""
+import numpy as np
+import pytest
+import torch
+
+from tests import cabi_emulator
+from tests import imblock_cases as cases
+from tests.helpers import rel_err
+
+
+@pytest.fixture(autouse=True)
+def _emulated(monkeypatch):
+    cases.DEV['device'] = 'cpu'
+    lib = cabi_emulator.install(monkeypatch)
+    yield lib
+    cases.DEV['device'] = 'cuda'
+
+
+@pytest.mark.parametrize('tag', list(cases.MLP))
+def test_imblock_mlp_train(golden, tag):
+    cases.case_imblock_mlp_train(golden, tag)
+
+
+@pytest.mark.parametrize('tag', ['tab6'])
+def test_imblock_mlp_train_reference_rng(golden, tag):
+    cases.case_imblock_mlp_train_reference_rng(golden, tag)
+
+
+@pytest.mark.parametrize('tag', ['tab6', 'tab43'])
+def test_imblock_mlp_eval_and_inverse(golden, tag):
+    cases.case_imblock_mlp_eval_and_inverse(golden, tag)
+
+
+@pytest.mark.parametrize('tag', list(cases.CONV))
+@pytest.mark.parametrize('backend', ['simt', 'tc'])
+def test_imblock_conv_train(golden, tag, backend):
+    cases.case_imblock_conv_train(golden, tag, backend)
+
+
+def test_imblock_classifier_block(golden):
+    cases.case_imblock_classifier_block(golden)
+
+
+def test_implicit_flow_density_step(golden):
+    cases.case_implicit_flow_density_step(golden)
+
+
+@pytest.mark.parametrize('tag', ['small', 'wide', 'capped', 'protbreak'])
+def test_broyden_host_loop(golden, tag):
+    import impflow_b200
+    fx = golden('broyden_analytic')
+    B, d, T, eps, scale, gain = fx[tag + '_meta']
+    W, c = torch.from_numpy(fx[tag + '_W']), torch.from_numpy(fx[tag + '_c'])
+    g = (lambda x: c - float(scale) * torch.tanh(x @ W) - x) if gain < 0 else (lambda x: c + float(gain) * x)
+    res = impflow_b200.layers.broyden.broyden(g, torch.zeros(int(B), int(d)), int(T), float(eps))
+    nstep, lowest_step, prot = fx[tag + '_ints']
+    assert (res['nstep'], res['lowest_step'], int(res['prot_break'])) == (nstep, lowest_step, prot)
+    assert rel_err(res['result'], fx[tag + '_result']) < 1e-5
+    assert len(res['trace']) == nstep + 1
+
+
+def test_state_dict_keys_match_reference(golden):
+    """Key-for-key state-dict compatibility with the reference modules (SURVEY.md §5 checkpoint row)."""
+    import impflow_b200
+    layers = impflow_b200.layers
+    fx = golden('imblock_mlp')
+    blk = cases.make_mlp_block('tab6')
+    ref_keys = sorted(k[len('tab6_sd_'):] for k in fx if k.startswith('tab6_sd_'))
+    assert sorted(blk.state_dict().keys()) == ref_keys
+    fx = golden('imblock_conv')
+    blk = layers.imBlock(cases.build_conv_branch(layers, 4, 32, 0.9, 1e-3, True),
+                         cases.build_conv_branch(layers, 4, 32, 0.9, 1e-3, True))
+    ref_keys = sorted(k[len('cifar_sd_'):] for k in fx if k.startswith('cifar_sd_'))
+    assert sorted(blk.state_dict().keys()) == ref_keys
+    assert 'geom_p' not in blk.state_dict() and 'lamb' in blk.state_dict()       # quirk #12
+
+
+def test_compat_install_registers_reference_import_names():
+    import impflow_b200
+    impflow_b200.compat.install()
+    import lib.layers as L
+    import lib.layers.base as BL
+    from lib.implicit_flow import ImplicitFlow
+    from lib.layers.broyden import broyden
+    assert L.imBlock is impflow_b200.layers.imBlock and BL.get_conv2d is impflow_b200.layers.base.get_conv2d
+    assert ImplicitFlow is impflow_b200.ImplicitFlow and callable(broyden)
+    import sys
+    for k in [k for k in sys.modules if k == 'lib' or k.startswith('lib.')]:
+        del sys.modules[k]
+
+
+def test_induced_norm_layers_vs_golden(golden):
+    import impflow_b200
+    BL = impflow_b200.layers.base
+    fx = golden('induced_norm')
+    lin = BL.InducedNormLinear(6, 16, coeff=0.5, domain=2, codomain=2, atol=1e-3, rtol=1e-3)
+    lin.load_state_dict({k[len('lin_init_'):]: torch.from_numpy(v) for k, v in fx.items() if k.startswith('lin_init_')})
+    with torch.no_grad():
+        lin.weight.copy_(torch.from_numpy(fx['lin_weight2']))
+    W = lin.compute_weight(update=True)
+    np.testing.assert_allclose(W.detach().numpy(), fx['lin_W_tol'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(lin.scale.numpy(), fx['lin_scale_tol'], rtol=1e-5)
+    W = lin.compute_weight(update=True, n_iterations=5)
+    np.testing.assert_allclose(W.detach().numpy(), fx['lin_W_it5'], rtol=1e-5, atol=1e-6)
+    y = lin(torch.from_numpy(fx['lin_x']))
+    np.testing.assert_allclose(y.detach().numpy(), fx['lin_y'], rtol=1e-4, atol=1e-5)
+    lin.zero_grad()
+    lin(torch.from_numpy(fx['lin_x'])).pow(2).sum().backward()
+    np.testing.assert_allclose(lin.weight.grad.numpy(), fx['lin_grad_weight'], rtol=1e-3, atol=1e-5)
+
+    conv = BL.InducedNormConv2d(5, 8, 3, 1, 1, coeff=0.4, domain=2, codomain=2, atol=1e-3, rtol=1e-3)
+    x = torch.from_numpy(fx['conv_x'])
+    with torch.no_grad():
+        conv(x)
+    conv.load_state_dict({k[len('conv_init_'):]: torch.from_numpy(v) for k, v in fx.items() if k.startswith('conv_init_')})
+    np.testing.assert_allclose(conv(x).detach().numpy(), fx['conv_y'], rtol=1e-4, atol=1e-5)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(fx['conv_weight2']))
+    W = conv.compute_weight(update=True)
+    np.testing.assert_allclose(conv.u.numpy(), fx['conv_u_tol'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(W.detach().numpy(), fx['conv_W_tol'], rtol=1e-5, atol=1e-6)
+    conv.zero_grad()
+    conv(x).pow(2).sum().backward()
+    np.testing.assert_allclose(conv.weight.grad.numpy(), fx['conv_grad_weight'], rtol=2e-3, atol=1e-4)
+
+    c1 = BL.InducedNormConv2d(8, 8, 1, 1, 0, coeff=0.3, domain=2, codomain=2, atol=1e-3, rtol=1e-3)
+    x = torch.from_numpy(fx['c1_x'])
+    with torch.no_grad():
+        c1(x)
+    c1.load_state_dict({k[len('c1_init_'):]: torch.from_numpy(v) for k, v in fx.items() if k.startswith('c1_init_')})
+    np.testing.assert_allclose(c1(x).detach().numpy(), fx['c1_y'], rtol=1e-4, atol=1e-5)
+    with torch.no_grad():
+        c1.weight.copy_(torch.from_numpy(fx['c1_weight2']))
+    W = c1.compute_weight(update=True)
+    np.testing.assert_allclose(W.detach().numpy(), fx['c1_W_tol'], rtol=1e-5, atol=1e-6)
