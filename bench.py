@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — ImpFlow hot-path benchmark (contract in the task brief, tier section ④).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference algorithm on host cores
+
+A "step" is one training step of the CIFAR-10-shape ImplicitFlow of run_cifar10.sh
+(train_img.py:591-660): forward (6 imBlocks: Broyden solve + power-series log-det), bits/dim,
+backward (implicit-differentiation Broyden solves), gradient all-reduce (N>1), clip, Adam,
+update_lipschitz — on synthetic U[0,1) images with random-init weights.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'impflow_train_samples_per_sec'
+UNIT = 'samples/s'
+WORKLOADS = {
+    # run_cifar10.sh:1-3 + train_img.py defaults
+    'cifar': dict(input=(3, 32, 32), n_blocks=[2, 2, 2], idim=512, batch=64, n_exact_terms=10, coeff=0.9),
+    # reduced-width debug variant (not a bench line)
+    'cifar-small': dict(input=(3, 32, 32), n_blocks=[1, 1, 1], idim=64, batch=16, n_exact_terms=4, coeff=0.9),
+}
+
+
+def std_normal_logprob(z):
+    return -0.5 * np.log(2 * np.pi) - z.pow(2) / 2
+
+
+def build_model(pkg, wl, batch):
+    layers = pkg.layers
+    c, h, w = wl['input']
+    return pkg.ImplicitFlow(
+        (batch, c, h, w), n_blocks=wl['n_blocks'], intermediate_dim=wl['idim'], factor_out=False, quadratic=False,
+        init_layer=layers.LogitTransform(0.05), actnorm=True, fc_actnorm=False, batchnorm=False, dropout=0.,
+        fc=False, coeff=wl['coeff'], vnorms='2222', n_lipschitz_iters=None, sn_atol=1e-3, sn_rtol=1e-3,
+        n_power_series=None, n_dist='poisson', n_samples=1, kernels='3-1-3', activation_fn='swish', fc_end=False,
+        fc_idim=128, n_exact_terms=wl['n_exact_terms'], preact=True, neumann_grad=True, grad_in_forward=True,
+        first_resblock=True, learn_p=False, classification=False, classification_hdim=256, n_classes=10)
+
+
+def update_lipschitz(pkg, model):
+    """train_img.py:786-792; the frozen *_copy twins are skipped (overwritten at the next forward,
+    SURVEY.md quirk #11)."""
+    BL = pkg.layers.base
+    with torch.no_grad():
+        for name, m in model.named_modules():
+            if '_copy' in name:
+                continue
+            if isinstance(m, (BL.InducedNormConv2d, BL.InducedNormLinear)):
+                m.compute_weight(update=True)
+
+
+class ClockSampler(object):
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
+                                     f[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                   'samples': len(sm)}
+        return out
+
+
+def run_cpu_reference(wl_name, steps, warmup, batch, threads=None):
+    """The reference algorithm (oracle port, PyTorch CPU like the reference itself) on host cores."""
+    from oracle import flow_oracle
+    import impflow_b200 as pkg
+    wl = WORKLOADS[wl_name]
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = build_model(pkg, wl, batch)       # constructor only (CPU): same init path as the product
+    sd = model.state_dict()
+    c, h, w = wl['input']
+    x = torch.rand(batch, c, h, w)
+    # lazily shaped conv u/v buffers + data-dependent ActNorm init, as model(x, restore=True) would do
+    sd = _host_init_lazy_buffers(sd, wl, x)
+    cfg = dict(flow_oracle.CIFAR_CFG, n_exact_terms=wl['n_exact_terms'])
+    flow = flow_oracle.OracleFlow(sd, wl['n_blocks'], cfg, coeff=wl['coeff'])
+    opt = torch.optim.Adam(flow.params, lr=1e-3, betas=(0.9, 0.99))
+    times, stats = [], {}
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        bpd = flow.train_step(x, opt, stats)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = float(np.mean(times) * 1e3)
+    return {'value': batch / (ms / 1e3), 'ms_per_step': ms, 'cores': threads, 'batch': batch, 'bpd': bpd,
+            'fwd_nstep': stats.get('fwd_nstep', [])[-6:], 'bwd_nstep': stats.get('bwd_nstep', [])[-6:]}
+
+
+def _host_init_lazy_buffers(sd, wl, x):
+    """Shape the conv u/v buffers and ActNorm parameters on the host the way the reference's first
+    `model(x, restore=True)` does (mixed_lipschitz.py:195-239, act_norm.py:25-37)."""
+    import torch.nn.functional as F
+    from oracle import impflow_oracle as orc
+    sd = {k: v.clone() for k, v in sd.items()}
+    c, h, w = wl['input']
+    feat = x
+    alpha = 0.05
+    s = alpha + (1 - 2 * alpha) * feat
+    feat = torch.log(s) - torch.log(1 - s)
+    n_scales = len(wl['n_blocks'])
+    for sc, nb in enumerate(wl['n_blocks']):
+        pre = 'transforms.%d.chain.' % sc
+        i = 1 if sc == 0 else 0
+        items = ([('actnorm', i)] if sc == 0 else [])
+        i += len(items)
+        for _ in range(nb):
+            items.append(('imblock', i))
+            items.append(('actnorm', i + 1))
+            i += 2
+        for kind, idx in items:
+            if kind == 'actnorm':
+                wgt, b = orc.actnorm_init(feat)
+                sd['%s%d.weight' % (pre, idx)] = wgt
+                sd['%s%d.bias' % (pre, idx)] = b
+                sd['%s%d.initialized' % (pre, idx)] = torch.tensor(1)
+                feat = (feat + b.view(1, -1, 1, 1)) * torch.exp(wgt.view(1, -1, 1, 1))
+            else:
+                for net in ('nnet_x', 'nnet_z', 'nnet_x_copy', 'nnet_z_copy'):
+                    j = 0
+                    while True:
+                        key = '%s%d.%s.%d.' % (pre, idx, net, j)
+                        if not any(k.startswith('%s%d.%s.' % (pre, idx, net)) and int(k.split('.')[5]) >= j
+                                   for k in sd):
+                            break
+                        if key + 'weight' in sd and sd[key + 'weight'].dim() == 4:
+                            Wt = sd[key + 'weight']
+                            hh, ww = feat.shape[2], feat.shape[3]
+                            sd[key + 'spatial_dims'] = torch.tensor([float(hh), float(ww)])
+                            sd[key + 'initialized'] = torch.tensor(1)
+                            if Wt.shape[-1] == 1:
+                                u = F.normalize(torch.randn(Wt.shape[0]), dim=0)
+                                v = F.normalize(torch.randn(Wt.shape[1]), dim=0)
+                                u, v, _ = orc.power_iterate_matrix(Wt.view(Wt.shape[0], Wt.shape[1]), u, v, None,
+                                                                   1e-3, 1e-3)
+                            else:
+                                v = F.normalize(torch.randn(Wt.shape[1] * hh * ww), dim=0)
+                                u = F.normalize(torch.randn(Wt.shape[0] * hh * ww), dim=0)
+                                u, v, _ = orc.power_iterate_conv(Wt, u, v, (Wt.shape[1], hh, ww), 1, 1, None, 1e-3,
+                                                                 1e-3)
+                            sd[key + 'u'], sd[key + 'v'] = u, v
+                        j += 1
+        if sc < n_scales - 1:
+            feat = orc.squeeze2(feat)
+    return sd
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='cifar', choices=list(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (weak scaling)')
+    ap.add_argument('--cpu-batch', type=int, default=4, help='images per CPU-baseline step (bounded sample)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--probe-mode', default='reference', choices=['reference', 'device'])
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    wl = WORKLOADS[args.workload]
+    batch = args.batch or wl['batch']
+    config = {'workload': ('cifar10-shape ImplicitFlow train step (run_cifar10.sh: nblocks 2-2-2, idim 512, k3-1-3, '
+                           'LipSwish, 10 exact terms, Neumann grad, mem-eff)' if args.workload == 'cifar'
+                           else args.workload),
+              'per_gpu_batch': batch, 'global_batch': batch * world, 'parallelism': 'dp%d' % world,
+              'l2': 'per-step working set (>1 GB of activations) exceeds the 126 MB L2; 256 MB flush between steps',
+              'gemm': '3xTF32 on tcgen05 (fp32-accurate; ceiling = 1/6 of the bf16 peak)',
+              'probe_mode': args.probe_mode}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        cpu_batch = args.cpu_batch
+        res = run_cpu_reference(args.workload, max(args.steps, 1), max(min(args.warmup, 1), 0), cpu_batch)
+        line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': 0,
+                'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': res['ms_per_step'],
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': config,
+                'cpu_baseline': {'value': res['value'], 'unit': UNIT, 'cores': res['cores'], 'kind': 'port',
+                                 'sample': '%d-image steps of the same model (samples/s is per image)' % cpu_batch},
+                'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'solver_iterations': {'fwd': res['fwd_nstep'], 'bwd': res['bwd_nstep']}}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py --impl b200 needs a GPU (there is no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    import impflow_b200 as pkg
+    from impflow_b200.layers import implicit_block
+    implicit_block.PROBE_MODE['mode'] = args.probe_mode
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = build_model(pkg, wl, batch).to(dev)
+    c, h, w = wl['input']
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.rand(batch, c, h, w, generator=gen).pin_memory()
+    x_dev = x_host.to(dev)
+    with torch.no_grad():
+        model(x_dev, restore=True)           # ActNorm data init + lazy u/v shaping (train_img.py:502-507)
+    if world > 1:
+        pkg.parallel.broadcast_module(model, 0)
+    np.random.seed(100 + rank)
+    torch.manual_seed(100 + rank)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    bucket = pkg.parallel.FlatGradBucket(params)
+    opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.99))
+    n_dims = c * h * w
+    flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)
+    blocks = [m for m in model.modules() if isinstance(m, pkg.layers.imBlock)]
+
+    def step(x):
+        bucket.zero()
+        z, dlogp = model(x, 0)
+        logpz = std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True)
+        logpx = logpz - dlogp - np.log(256) * n_dims
+        bpd = -torch.mean(logpx) / n_dims / np.log(2)
+        bpd.backward()
+        bucket.allreduce_mean()
+        torch.nn.utils.clip_grad_norm_(params, 1.)
+        opt.step()
+        update_lipschitz(pkg, model)
+        return bpd
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    sync_all()
+
+    # ---------------- timed region: K steps, inputs resident in HBM ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    pkg.ops.GEMM_PROFILE['on'] = True
+    pkg.ops.GEMM_PROFILE['events'] = []
+    launches0 = pkg._cabi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    solves = 0
+    fwd_its, bwd_its = [], []
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        flush.zero_()
+        step(x_dev)
+        solves += 2 * len(blocks) * batch
+        fwd_its.append([b.solver_stats['fwd']['nstep'] for b in blocks])
+    ev1.record()
+    sync_all()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = pkg._cabi.launch_count() - launches0
+    pkg.ops.GEMM_PROFILE['on'] = False
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = batch * world / (ms_step / 1e3)
+
+    # roofline of the dominant kernel (tcgen05 3xTF32 GEMM) from events recorded inside the timed region
+    gemm_ms, gemm_flop, n_gemm = 0.0, 0.0, 0
+    for e0, e1, flop in pkg.ops.GEMM_PROFILE['events']:
+        gemm_ms += e0.elapsed_time(e1)
+        gemm_flop += flop
+        n_gemm += 1
+    pkg.ops.GEMM_PROFILE['events'] = []
+
+    # ---------------- e2e: same step through the public API from pinned host buffers ----------------
+    sync_all()
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        xb = x_host.to(dev, non_blocking=True)
+        last = step(xb).item()                     # device -> host read of the step's loss
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    te = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF sustained (B200_PROFILING.md)'
+    achieved = (gemm_flop / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else 0.0
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': config, 'clocks': clocks,
+        'e2e': {'value': batch * world / (e2e_ms / 1e3), 'unit': UNIT, 'ms_per_step': e2e_ms,
+                'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': 4, 'last_bpd': last},
+        'gpu_launches': int(launches),
+        'broyden_solves_per_sec': solves * world / (ms_total / 1e3),
+        'solver_iterations_fwd_last_step': fwd_its[-1] if fwd_its else None,
+        'roofline': {'kernel': 'k_gemm_tc3 (tcgen05 3xTF32 residual-branch GEMM)', 'bound': 'tensor',
+                     'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                     'traffic': None, 'peak_source': peak_src, 'launches': n_gemm,
+                     'share_of_step': gemm_ms / ms_total if ms_total > 0 else None,
+                     'note': 'achieved = 2MNK algorithmic fp32 flops / CUDA-event time of every tcgen05 GEMM launch '
+                             'in the timed region; each launch issues 3 tf32 MMAs per product, so the mode ceiling '
+                             'is peak/6'},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            res = run_cpu_reference(args.workload, 2, 1, args.cpu_batch)
+            line['cpu_baseline'] = {'value': res['value'], 'unit': UNIT, 'cores': res['cores'], 'kind': 'port',
+                                    'sample': '2 timed + 1 warm-up steps of %d images of the same model on host '
+                                              'cores' % args.cpu_batch}
+        except Exception as exc:      # the baseline must never hide the GPU number
+            line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                                    'sample': 'failed: %r' % (exc,)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -19,6 +19,11 @@ ACT_NONE, ACT_SIN, ACT_LIPSWISH, ACT_RELU = 0, 1, 2, 3
 _BACKEND = {'mode': 'auto', 'min_flops_tc': 2 * 128 * 128 * 64}
 
 
+# bench.py switches this on inside its timed region to collect (start, end, flop) CUDA events of
+# every tcgen05 GEMM launch for the roofline line.
+GEMM_PROFILE = {'on': False, 'events': []}
+
+
 def set_gemm_backend(mode):
     assert mode in ('auto', 'simt', 'tc')
     _BACKEND['mode'] = mode
@@ -181,12 +186,19 @@ def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, wa
         Bh, Bl = B_split if B_split is not None else split_tf32(Bm)
         sh = torch.empty(M, N, device=dev, dtype=torch.float32) if want_split else None
         sl = torch.empty(M, N, device=dev, dtype=torch.float32) if want_split else None
+        if GEMM_PROFILE['on']:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         _cabi.check(lib.impflow_gemm_nt_tc(_cabi.ptr(Ah), _cabi.ptr(Al), K, _cabi.ptr(Bh), _cabi.ptr(Bl), K,
                                            _cabi.ptr(bias, 'bias', True), _cabi.ptr(pre, 'pre', True),
                                            _cabi.ptr(act, 'act', True), _cabi.ptr(dmul_pre, 'dmul', True),
                                            _cabi.ptr(sh, 'sh', True), _cabi.ptr(sl, 'sl', True), N, M, N, K,
                                            act_kind, _cabi.ptr(beta_sp, 'beta', True), _cabi.stream()),
                     'gemm_nt_tc')
+        if GEMM_PROFILE['on']:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            GEMM_PROFILE['events'].append((e0, e1, 2.0 * M * N * K))
         return pre, act, ((sh, sl) if want_split else None)
     _cabi.check(lib.impflow_gemm_nt(_cabi.ptr(A), K, _cabi.ptr(Bm), K, _cabi.ptr(bias, 'bias', True),
                                     _cabi.ptr(pre, 'pre', True), _cabi.ptr(act, 'act', True),
