@@ -211,6 +211,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=4, help='images per CPU-baseline step (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--probe-mode', default='reference', choices=['reference', 'device'])
+    ap.add_argument('--unfused', action='store_true', help='disable the graph-free branch programs (A/B)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -256,6 +257,7 @@ def main():
     import impflow_b200 as pkg
     from impflow_b200.layers import implicit_block
     implicit_block.PROBE_MODE['mode'] = args.probe_mode
+    implicit_block.FUSED['on'] = not args.unfused
 
     torch.manual_seed(0)
     np.random.seed(0)
@@ -311,6 +313,7 @@ def main():
     solves = 0
     fwd_its, bwd_its = [], []
     sync_all()
+    torch.cuda.nvtx.range_push('timed')      # ncu --nvtx --nvtx-include "timed/" isolates these launches
     ev0.record()
     for _ in range(args.steps):
         flush.zero_()
@@ -319,6 +322,7 @@ def main():
         fwd_its.append([b.solver_stats['fwd']['nstep'] for b in blocks])
     ev1.record()
     sync_all()
+    torch.cuda.nvtx.range_pop()
     ms_total = ev0.elapsed_time(ev1)
     launches = pkg._cabi.launch_count() - launches0
     pkg.ops.GEMM_PROFILE['on'] = False

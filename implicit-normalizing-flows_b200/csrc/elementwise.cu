@@ -192,14 +192,18 @@ k_transpose(const float* __restrict__ a, float* __restrict__ out, long long M, l
 // ---- im2col / col2im for NHWC 3x3 stride 1 pad 1 -------------------------------------------------
 // col row p=(b,y,x) has 9*C entries ordered (ky,kx,c).
 __global__ void __launch_bounds__(256)
-k_im2col3x3(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C) {
-  const long long total = (long long)B * H * W * 9 * C;
+k_im2col3x3(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int ld) {
+  const long long total = (long long)B * H * W * ld;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long t = i / C;
-    const int tap = (int)(t % 9);
-    const long long p = t / 9;
+    const int kcol = (int)(i % ld);
+    const long long p = i / ld;
+    if (kcol >= 9 * C) {
+      col[i] = 0.f;
+      continue;
+    }
+    const int c = kcol % C;
+    const int tap = kcol / C;
     const int xx = (int)(p % W);
     const int yy = (int)((p / W) % H);
     const long long b = p / ((long long)W * H);
@@ -328,10 +332,11 @@ extern "C" int impflow_transpose(const float* a, float* out, long long M, long l
   return check_launch("k_transpose");
 }
 
-extern "C" int impflow_im2col3x3(const float* x, float* col, int B, int H, int W, int C, void* stream) {
-  const long long total = (long long)B * H * W * 9 * C;
+extern "C" int impflow_im2col3x3(const float* x, float* col, int B, int H, int W, int C, int ld, void* stream) {
+  IMPFLOW_REQUIRE(ld >= 9 * C, "im2col3x3: ld=%d < 9*C=%d", ld, 9 * C);
+  const long long total = (long long)B * H * W * ld;
   if (total <= 0) return 0;
-  k_im2col3x3<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, col, B, H, W, C);
+  k_im2col3x3<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, col, B, H, W, C, ld);
   return check_launch("k_im2col3x3");
 }
 

@@ -29,6 +29,31 @@ __all__ = ['imBlock']
 # 'device': probes come from the CUDA generator (no host->device copy on the hot path).
 PROBE_MODE = {'mode': 'reference'}
 
+# Graph-free fused evaluation (branch_program.py) of the no-grad hot loops: Broyden g evaluations,
+# the vjps of the implicit backward solve and of the Neumann / eval-mode power series.  Off = every
+# branch evaluation goes through the module and autograd (same kernels, many more launches).
+FUSED = {'on': True}
+
+
+def _program(nnet):
+    if not FUSED['on']:
+        return None
+    prog = getattr(nnet, '_impflow_program', False)
+    if prog is False:
+        from ..branch_program import compile_branch
+        prog = compile_branch(nnet) if isinstance(nnet, nn.Module) else None
+        try:
+            nnet._impflow_program = prog
+        except Exception:
+            pass
+    return prog
+
+
+def branch_eval(nnet, x):
+    """nnet(x) under no_grad, through the fused program when the branch is compilable."""
+    prog = _program(nnet)
+    return prog.forward(x) if prog is not None else nnet(x)
+
 
 def find_fixed_point(g, y, threshold=1000, eps=1e-5):
     """Banach iteration, fallback after a protective break (implicit_block.py:17-28)."""
@@ -54,17 +79,17 @@ class RootFind(Function):
     @staticmethod
     def banach_find_root(nnet_z, nnet_x, z0, x, *args):
         eps, threshold = args[-2], args[-1]
-        x_embed = nnet_x(x) + x
-        z_est = find_fixed_point(lambda z: x_embed - nnet_z(z), z0, threshold=threshold, eps=eps)
+        x_embed = branch_eval(nnet_x, x) + x
+        z_est = find_fixed_point(lambda z: x_embed - branch_eval(nnet_z, z), z0, threshold=threshold, eps=eps)
         return z_est.clone().detach()
 
     @staticmethod
     def broyden_find_root(nnet_z, nnet_x, z0, x, *args):
         eps, threshold = args[-2], args[-1]
-        x_embed = ops.lincomb3(nnet_x(x), 1.0, x, 1.0)
+        x_embed = ops.lincomb3(branch_eval(nnet_x, x), 1.0, x, 1.0)
 
         def g(z):     # x_embed - nnet_z(z) - z in one kernel (implicit_block.py:72)
-            return ops.lincomb3(x_embed, 1.0, nnet_z(z), -1.0, z, -1.0)
+            return ops.lincomb3(x_embed, 1.0, branch_eval(nnet_z, z), -1.0, z, -1.0)
 
         info = broyden(g, torch.zeros_like(z0), threshold=threshold, eps=eps, name='forward')
         RootFind.last_info = info
@@ -146,6 +171,19 @@ class imBlock(nn.Module):
             args = ctx.args
             eps, threshold = args[-2:]
             nnet_z, nnet_x = ctx.nnet_z, ctx.nnet_x
+            prog_z, prog_x = _program(nnet_z), _program(nnet_x)
+            if prog_z is not None and prog_x is not None:
+                # graph-free: v^T (I + J_z) from the fused vjp kernels
+                with torch.no_grad():
+                    z, x = z.detach(), x.detach()
+                    prog_z.forward(z, save=True)
+                    info = broyden(lambda v: ops.lincomb3(prog_z.vjp(v), 1.0, v, 1.0, grad, -1.0),
+                                   torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
+                    imBlock.Backward.last_info = info
+                    dl_dh = info['result']
+                    prog_x.forward(x, save=True)
+                    dl_dx = ops.lincomb3(prog_x.vjp(dl_dh), 1.0, dl_dh, 1.0)
+                return (None, None, dl_dh, dl_dx) + (None,) * len(args)
             z = z.clone().detach().requires_grad_()
             x = x.clone().detach().requires_grad_()
             with torch.enable_grad():
@@ -176,6 +214,9 @@ class imBlock(nn.Module):
         z = RootFind.f(self.nnet_z, self.nnet_x, z.detach(), z0) + z0
         self.nnet_x_copy.load_state_dict(self.nnet_x.state_dict())
         self.nnet_z_copy.load_state_dict(self.nnet_z.state_dict())
+        if FUSED['on']:      # the frozen twins hold the same weights: share the live nets' programs
+            self.nnet_z_copy._impflow_program = _program(self.nnet_z)
+            self.nnet_x_copy._impflow_program = _program(self.nnet_x)
         z = self.Backward.apply(self.nnet_z_copy, self.nnet_x_copy, z, x, 'broyden', self.eps_backward,
                                 self.threshold)
         if logpx is None:
@@ -250,8 +291,10 @@ class imBlock(nn.Module):
                 else:
                     x = x.requires_grad_(True)
                     z = z.requires_grad_(True)
-                    logdet_x = estimator_fn(self.nnet_x(x), x, n_power_series, vareps_x, coeff_fn, self.training)
-                    logdet_z = estimator_fn(self.nnet_z(z), z, n_power_series, vareps_z, coeff_fn, self.training)
+                    logdet_x = estimator_fn(self.nnet_x(x), x, n_power_series, vareps_x, coeff_fn, self.training,
+                                            _program(self.nnet_x))
+                    logdet_z = estimator_fn(self.nnet_z(z), z, n_power_series, vareps_z, coeff_fn, self.training,
+                                            _program(self.nnet_z))
                 logdetgrad = logdet_x - logdet_z
             else:
                 x = x.requires_grad_(True)
@@ -331,9 +374,19 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
         return (None, None, grad_x, None, None, None, None) + grad_params
 
 
-def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training):
+def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, program=None):
     """sum_k (-1)^(k+1)/k coeff(k) <v^T J^k, v>  (implicit_block.py:418-426)."""
     vjp = vareps
+    if not training and program is not None:
+        # eval mode builds no graph: the whole chain runs on the fused vjp kernels, the Hutchinson
+        # dots accumulate in place
+        with torch.no_grad():
+            program.forward(x.detach(), save=True)
+            out = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+            for k in range(1, n_power_series + 1):
+                vjp = program.vjp(vjp)
+                ops.rowdot(vjp, vareps, out=out, alpha=float((-1) ** (k + 1) / k * coeff_fn(k)), beta=1.0)
+        return out
     logdetgrad = torch.tensor(0.).to(x)
     for k in range(1, n_power_series + 1):
         vjp = torch.autograd.grad(g, x, vjp, create_graph=training, retain_graph=True)[0]
@@ -342,14 +395,19 @@ def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training):
     return logdetgrad
 
 
-def neumann_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training):
+def neumann_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, program=None):
     """Neumann-series gradient estimator: a surrogate whose gradient is unbiased for the log-det
     gradient (implicit_block.py:429-438)."""
     vjp = vareps
     neumann_vjp = vareps
     with torch.no_grad():
+        if program is not None:
+            program.forward(x.detach(), save=True)
         for k in range(1, n_power_series + 1):
-            vjp = torch.autograd.grad(g, x, vjp, retain_graph=True)[0]
+            if program is not None:
+                vjp = program.vjp(vjp)
+            else:
+                vjp = torch.autograd.grad(g, x, vjp, retain_graph=True)[0]
             neumann_vjp = ops.lincomb3(neumann_vjp, 1.0, vjp, float((-1) ** k * coeff_fn(k)))
     vjp_jac = torch.autograd.grad(g, x, neumann_vjp, create_graph=training)[0]
     return ops.rowdot_fn(vjp_jac, vareps)

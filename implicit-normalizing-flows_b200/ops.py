@@ -123,11 +123,14 @@ def transpose2d(a2d):
     return out
 
 
-def im2col3x3(x_nhwc):
+def im2col3x3(x_nhwc, ld=None):
+    """(B,H,W,C) -> (B*H*W, ld) patch matrix, ld >= 9*C (tail zero-filled)."""
     x_nhwc = x_nhwc.contiguous()
     B, H, W, C = x_nhwc.shape
-    col = torch.empty(B * H * W, 9 * C, device=x_nhwc.device, dtype=torch.float32)
-    _cabi.check(_lib().impflow_im2col3x3(_cabi.ptr(x_nhwc), _cabi.ptr(col), B, H, W, C, _cabi.stream()), 'im2col3x3')
+    ld = 9 * C if ld is None else ld
+    col = torch.empty(B * H * W, ld, device=x_nhwc.device, dtype=torch.float32)
+    _cabi.check(_lib().impflow_im2col3x3(_cabi.ptr(x_nhwc), _cabi.ptr(col), B, H, W, C, ld, _cabi.stream()),
+                'im2col3x3')
     return col
 
 

@@ -110,9 +110,10 @@ int impflow_rowdot(const float* a, const float* c, float* out, int B, long long 
 int impflow_colsum(const float* a, float* out, long long M, int N, void* stream);
 /* out[n,m] = a[m,n] */
 int impflow_transpose(const float* a, float* out, long long M, long long N, void* stream);
-/* NHWC 3x3, stride 1, pad 1 patch gather col[(b,y,x),(ky,kx,c)] = x[b,y+ky-1,x+kx-1,c], and its
+/* NHWC 3x3, stride 1, pad 1 patch gather col[(b,y,x),(ky,kx,c)] = x[b,y+ky-1,x+kx-1,c] (rows of
+ * `ld` >= 9*C floats, the tail zero-filled so that K can be padded to a multiple of 32), and its
  * adjoint (scatter-sum) with the same fused epilogue as impflow_gemm_nt (N = C, ldc = C). */
-int impflow_im2col3x3(const float* x, float* col, int B, int H, int W, int C, void* stream);
+int impflow_im2col3x3(const float* x, float* col, int B, int H, int W, int C, int ld, void* stream);
 int impflow_col2im3x3(const float* col, int B, int H, int W, int C, const float* bias, float* pre_out,
                       float* act_out, const float* dmul_pre, int act_kind, const float* beta_sp, void* stream);
 

@@ -20,10 +20,11 @@ ref)
 ncu)
   CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --probe-mode device"
   timeout -s KILL 900 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
-  timeout -s KILL 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
-      --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+  timeout -s KILL 1500 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "timed/" \
+      -c 15000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit $?"; wc -l gpurun_out/launches.csv
-  timeout -s KILL 1500 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc3 -s 40 -c 3 \
+  timeout -s KILL 1500 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "timed/" \
+      -k regex:k_gemm_tc3 -s 10 -c 4 \
       -o gpurun_out/prof_gemm_tc3 -f $CMD > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?"; ls -la gpurun_out/*.ncu-rep ;;
 esac

@@ -268,14 +268,15 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
-    def impflow_im2col3x3(self, x, col, B, H, W, C, stream):
+    def impflow_im2col3x3(self, x, col, B, H, W, C, ld, stream):
         xv = _f32(x, B * H * W * C).reshape(B, H, W, C)
         xp = np.zeros((B, H + 2, W + 2, C), np.float32)
         xp[:, 1:-1, 1:-1] = xv
-        cv = _f32(col, B * H * W * 9 * C).reshape(B, H, W, 9, C)
+        full = _f32(col, B * H * W * ld).reshape(B, H, W, ld)
+        full[...] = 0
         for tap in range(9):
             ky, kx = tap // 3, tap % 3
-            cv[:, :, :, tap] = xp[:, ky:ky + H, kx:kx + W]
+            full[:, :, :, tap * C:(tap + 1) * C] = xp[:, ky:ky + H, kx:kx + W]
         self.launches += 1
         return 0
 

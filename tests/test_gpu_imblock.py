@@ -38,6 +38,16 @@ def test_imblock_classifier_block(golden):
     cases.case_imblock_classifier_block(golden)
 
 
+def test_imblock_unfused_path(golden):
+    from impflow_b200.layers import implicit_block
+    implicit_block.FUSED['on'] = False
+    try:
+        cases.case_imblock_conv_train(golden, 'cifar', 'auto')
+        cases.case_imblock_mlp_train(golden, 'tab6')
+    finally:
+        implicit_block.FUSED['on'] = True
+
+
 def test_implicit_flow_density_step(golden):
     cases.case_implicit_flow_density_step(golden)
 

@@ -44,6 +44,17 @@ def test_imblock_classifier_block(golden):
     cases.case_imblock_classifier_block(golden)
 
 
+def test_imblock_conv_train_unfused(golden):
+    """Same parity through the module / autograd path (graph-free branch programs switched off)."""
+    from impflow_b200.layers import implicit_block
+    implicit_block.FUSED['on'] = False
+    try:
+        cases.case_imblock_conv_train(golden, 'cifar', 'simt')
+        cases.case_imblock_classifier_block(golden)
+    finally:
+        implicit_block.FUSED['on'] = True
+
+
 def test_implicit_flow_density_step(golden):
     cases.case_implicit_flow_density_step(golden)
 
@@ -136,3 +147,62 @@ def test_induced_norm_layers_vs_golden(golden):
         c1.weight.copy_(torch.from_numpy(fx['c1_weight2']))
     W = c1.compute_weight(update=True)
     np.testing.assert_allclose(W.detach().numpy(), fx['c1_W_tol'], rtol=1e-5, atol=1e-6)
+
+
+def _branch_cases():
+    import impflow_b200
+    L = impflow_b200.layers
+    torch.manual_seed(0)
+    mk = lambda a, b, k, bias=True: L.base.get_conv2d(a, b, k, 1, k // 2, bias=bias, coeff=0.9, n_iterations=None,
+                                                      domain=2, codomain=2, atol=1e-3, rtol=1e-3)
+    lin = lambda a, b: L.base.get_linear(a, b, coeff=0.9, n_iterations=None, atol=1e-3, rtol=1e-3, domain=2, codomain=2)
+    return {
+        'cifar_lead': (torch.nn.Sequential(L.base.Swish(), mk(4, 32, 3), L.base.Swish(), mk(32, 32, 1), L.base.Swish(),
+                                           mk(32, 4, 3)), (2, 4, 8, 8)),
+        'cifar_nolead': (torch.nn.Sequential(mk(3, 32, 3), L.base.Swish(), mk(32, 32, 1), L.base.Swish(), mk(32, 3, 3)),
+                         (2, 3, 8, 8)),
+        'cls_relu': (torch.nn.Sequential(mk(8, 16, 3, False), torch.nn.ReLU(), mk(16, 8, 3, False), torch.nn.ReLU()),
+                     (2, 8, 8, 8)),
+        'mlp_sin': (torch.nn.Sequential(lin(6, 64), L.base.Sin(), lin(64, 64), L.base.Sin(), lin(64, 6)), (9, 6)),
+        'wide_both': (torch.nn.Sequential(mk(32, 64, 3), L.base.Swish(), mk(64, 32, 3)), (1, 32, 4, 4)),
+    }
+
+
+@pytest.mark.parametrize('name', ['cifar_lead', 'cifar_nolead', 'cls_relu', 'mlp_sin', 'wide_both'])
+@pytest.mark.parametrize('backend', ['simt', 'tc'])
+def test_branch_program_matches_module_autograd(name, backend):
+    """The fused graph-free forward / vjp equals the module's autograd forward / vjp."""
+    import impflow_b200
+    from impflow_b200.branch_program import compile_branch
+    impflow_b200.ops.set_gemm_backend(backend)
+    try:
+        net, shape = _branch_cases()[name]
+        x = torch.randn(*shape)
+        with torch.no_grad():
+            net(x)                                  # lazy u/v shaping
+            for p in net.parameters():
+                if p.dim() > 1:
+                    p.mul_(3.0)                     # make the spectral rescale active
+        prog = compile_branch(net)
+        assert prog is not None
+        xr = x.clone().requires_grad_(True)
+        y_ref = net(xr)
+        v = torch.randn_like(y_ref)
+        (vjp_ref,) = torch.autograd.grad(y_ref, xr, v)
+        with torch.no_grad():
+            y = prog.forward(x)
+            y2 = prog.forward(x, save=True)
+            vjp = prog.vjp(v)
+            vjp_again = prog.vjp(v)
+        assert rel_err(y, y_ref.detach()) < 2e-6
+        assert rel_err(y2, y_ref.detach()) < 2e-6
+        assert rel_err(vjp, vjp_ref) < 5e-6
+        assert rel_err(vjp_again, vjp_ref) < 5e-6
+    finally:
+        impflow_b200.ops.set_gemm_backend('auto')
+
+
+def test_branch_program_rejects_unknown_modules():
+    from impflow_b200.branch_program import compile_branch
+    assert compile_branch(torch.nn.Sequential(torch.nn.Linear(3, 3))) is None
+    assert compile_branch(torch.nn.Tanh()) is None
