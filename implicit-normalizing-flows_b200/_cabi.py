@@ -30,13 +30,15 @@ SIGNATURES = {
     'impflow_act_beta_grad': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _ll, _i, _c_fp, _c_fp]),
     'impflow_lincomb3': (_i, [_c_fp, _f, _c_fp, _f, _c_fp, _f, _c_fp, _ll, _c_fp]),
     'impflow_rowdot': (_i, [_c_fp, _c_fp, _c_fp, _i, _ll, _f, _f, _c_fp]),
-    'impflow_colsum': (_i, [_c_fp, _c_fp, _ll, _i, _c_fp]),
+    'impflow_colsum_chunks': (_i, [_ll, _i]),
+    'impflow_colsum': (_i, [_c_fp, _c_fp, _c_fp, _ll, _i, _c_fp]),
     'impflow_transpose': (_i, [_c_fp, _c_fp, _ll, _ll, _c_fp]),
     'impflow_im2col3x3': (_i, [_c_fp, _c_fp, _i, _i, _i, _i, _i, _c_fp]),
     'impflow_col2im3x3': (_i, [_c_fp, _i, _i, _i, _i, _c_fp, _c_fp, _c_fp, _c_fp, _i, _c_fp, _c_fp]),
     'impflow_gemm_nt': (_i, [_c_fp, _ll, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
     'impflow_gemm_nt_tc': (_i, [_c_fp, _c_fp, _ll, _c_fp, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp,
-                                _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
+                                _ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
+    'impflow_gemm_tc_splits': (_i, [_ll, _i, _i]),
     'impflow_split_tf32': (_i, [_c_fp, _c_fp, _c_fp, _ll, _c_fp]),
     'impflow_sn_power_iter': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _i, _i, _i, _f, _f, _c_fp]),
 }
@@ -107,7 +109,9 @@ def iptr(t):
 
 
 def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw cudaStream_t of torch's current stream (the C-level getter: ~0.3 us instead of the
+    ~15 us of torch.cuda.current_stream(), which matters at thousands of launches per step)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def launch_count():

@@ -32,11 +32,18 @@ class _Act(object):
     def __init__(self, kind, module=None):
         self.kind = kind
         self.module = module       # Swish module (for beta) or None
+        self._beta = None          # softplus(beta) device scalar, refreshed by BranchProgram._prep
+
+    def refresh(self):
+        if self.kind == ops.ACT_LIPSWISH:
+            self._beta = F.softplus(self.module.beta.detach())
 
     def beta_sp(self):
         if self.kind != ops.ACT_LIPSWISH:
             return None
-        return F.softplus(self.module.beta.detach())
+        if self._beta is None:
+            self.refresh()
+        return self._beta
 
 
 class _Weights(object):
@@ -99,6 +106,9 @@ class BranchProgram(object):
         for act, m in self.stages:
             key += [m.weight._version, m.u._version, m.v._version, m.weight.data_ptr(),
                     (m.bias._version if m.bias is not None else -1)]
+        for act in [a for a, _ in self.stages] + [self.post_act]:
+            if act is not None and act.module is not None:
+                key += [act.module.beta._version, act.module.beta.data_ptr()]
         return tuple(key)
 
     def _use_tc(self, M, N, K):
@@ -107,7 +117,7 @@ class BranchProgram(object):
             return False
         if mode == 'tc':
             return True
-        return M >= 128 and N >= 16 and K >= 32
+        return M >= 64 and N >= 8 and K >= 32
 
     def _prep(self, M, meta=None):
         """(Re)build the cached effective weights; M = rows of the activation matrices."""
@@ -116,6 +126,9 @@ class BranchProgram(object):
             return self._weights
         ws = []
         with torch.no_grad():
+            for act in [a for a, _ in self.stages] + [self.post_act]:
+                if act is not None:
+                    act.refresh()
             for act, m in self.stages:
                 w = _Weights()
                 if isinstance(m, InducedNormConv2d) and not m.initialized and meta is not None:
@@ -199,7 +212,7 @@ class BranchProgram(object):
                 _cabi.ptr(A_split[0]), _cabi.ptr(A_split[1]), Wk, _cabi.ptr(W_split[0]), _cabi.ptr(W_split[1]), Wk,
                 _cabi.ptr(bias, 'bias', True), _cabi.ptr(pre, 'pre', True), _cabi.ptr(out_act, 'act', True),
                 _cabi.ptr(dmul_pre, 'dmul', True), _cabi.ptr(sh, 'sh', True), _cabi.ptr(sl, 'sl', True), N, M, N, Wk,
-                kind, _cabi.ptr(beta, 'beta', True), _cabi.stream()), 'gemm_nt_tc')
+                kind, _cabi.ptr(beta, 'beta', True), None, _cabi.stream()), 'gemm_nt_tc')
             if ops.GEMM_PROFILE['on']:
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record()

@@ -158,21 +158,23 @@ k_rowdot_warp(const float* __restrict__ a, const float* __restrict__ c, float* _
   if (lane == 0) out[b] = (beta == 0.f ? 0.f : beta * out[b]) + alpha * acc;
 }
 
-// ---- colsum: out[n] = sum_m a[m,n]; grid over column tiles of 32, 8 row-lanes ------------------
+// ---- colsum: out[n] = sum_m a[m,n]; grid (column tiles of 32, row chunks), two deterministic stages ----
 __global__ void __launch_bounds__(256)
-k_colsum(const float* __restrict__ a, float* __restrict__ out, long long M, int N) {
+k_colsum(const float* __restrict__ a, float* __restrict__ out, long long M, int N, long long rows_per_chunk) {
   __shared__ float tile[8][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
+  const long long m0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long m1 = m0 + rows_per_chunk < M ? m0 + rows_per_chunk : M;
   float acc = 0.f;
   if (col < N)
-    for (long long m = ry; m < M; m += 8) acc += a[m * N + col];
+    for (long long m = m0 + ry; m < m1; m += 8) acc += a[m * N + col];
   tile[ry][threadIdx.x & 31] = acc;
   __syncthreads();
   if (ry == 0 && col < N) {
     float t = 0.f;
     for (int r = 0; r < 8; ++r) t += tile[r][threadIdx.x & 31];
-    out[col] = t;
+    out[(long long)blockIdx.y * N + col] = t;
   }
 }
 
@@ -318,10 +320,28 @@ extern "C" int impflow_rowdot(const float* a, const float* c, float* out, int B,
   return check_launch("k_rowdot_block");
 }
 
-extern "C" int impflow_colsum(const float* a, float* out, long long M, int N, void* stream) {
+extern "C" int impflow_colsum_chunks(long long M, int N) {
+  const int col_tiles = (N + 31) / 32;
+  long long chunks = (296 + col_tiles - 1) / col_tiles;
+  if (chunks > (M + 63) / 64) chunks = (M + 63) / 64;
+  return chunks < 1 ? 1 : (int)chunks;
+}
+
+extern "C" int impflow_colsum(const float* a, float* out, float* partial, long long M, int N, void* stream) {
   if (N <= 0) return 0;
-  k_colsum<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a, out, M, N);
-  return check_launch("k_colsum");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int chunks = impflow_colsum_chunks(M, N);
+  const long long rows = (M + chunks - 1) / chunks;
+  dim3 grid((N + 31) / 32, chunks);
+  if (chunks == 1) {
+    k_colsum<<<grid, 256, 0, s>>>(a, out, M, N, rows);
+    return check_launch("k_colsum");
+  }
+  IMPFLOW_REQUIRE(partial != nullptr, "colsum: needs a partial workspace of chunks*N floats");
+  k_colsum<<<grid, 256, 0, s>>>(a, partial, M, N, rows);
+  if (check_launch("k_colsum")) return -1;
+  k_colsum<<<dim3((N + 31) / 32, 1), 256, 0, s>>>(partial, out, chunks, N, chunks);
+  return check_launch("k_colsum(stage2)");
 }
 
 extern "C" int impflow_transpose(const float* a, float* out, long long M, long long N, void* stream) {

@@ -128,7 +128,7 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
            const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-           long long M, int N, int K, TcEpilogue ep) {
+           long long M, int N, int K, TcEpilogue ep, int splits, float* __restrict__ splitk_ws) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -144,7 +144,10 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
   const int num_kb = K / TC_BK;
   const long long m_tiles = (M + TC_BM - 1) / TC_BM;
   const int n_tiles = (N + BN - 1) / BN;
-  const long long num_tiles = m_tiles * n_tiles;
+  // split-K (weight-gradient shapes: small M x N, K = all pixels): work item = (tile, k-slice);
+  // raw partial accumulators go to splitk_ws[slice][M][N] and k_splitk_reduce finishes the job.
+  const long long num_tiles = m_tiles * n_tiles * splits;
+  const int kb_per = (num_kb + splits - 1) / splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapAhi)) : "memory");
@@ -180,9 +183,12 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_idx = (int)(tile / n_tiles) * TC_BM;
-        const int n_idx = (int)(tile % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const long long mn = tile / splits;
+        const int ks = (int)(tile % splits);
+        const int m_idx = (int)(mn / n_tiles) * TC_BM;
+        const int n_idx = (int)(mn % n_tiles) * BN;
+        const int kb_end = min(num_kb, (ks + 1) * kb_per);
+        for (int kb = ks * kb_per; kb < kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -211,7 +217,10 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int ks = (int)(tile % splits);
+      const int kb_begin = ks * kb_per;
+      const int kb_end = min(num_kb, kb_begin + kb_per);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -226,7 +235,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
             const uint64_t dal = make_kmajor_sw128_desc(a_lo + koff);
             const uint64_t dbh = make_kmajor_sw128_desc(b_hi + koff);
             const uint64_t dbl = make_kmajor_sw128_desc(b_lo + koff);
-            umma_tf32(tmem_c, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_c, dal, dbh, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
             umma_tf32(tmem_c, dah, dbl, idesc, 1u);
             umma_tf32(tmem_c, dah, dbh, idesc, 1u);
           }
@@ -253,8 +262,10 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
     uint32_t acc_phase = 0;
     const Epilogue e = resolve_beta(ep.e);
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long m = (tile / n_tiles) * TC_BM + q * 32 + lane;
-      const int n_base = (int)(tile % n_tiles) * BN;
+      const long long mn = tile / splits;
+      const int ks = (int)(tile % splits);
+      const long long m = (mn / n_tiles) * TC_BM + q * 32 + lane;
+      const int n_base = (int)(mn % n_tiles) * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -263,6 +274,15 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
         tmem_ld32(taddr, r);
         const int n0 = n_base + c * 32;
+        if (splits > 1) {
+          if (m < M && n0 < N) {
+            float* dst = splitk_ws + ((long long)ks * M + m) * N + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < N) dst[j] = __uint_as_float(r[j]);
+          }
+          continue;
+        }
         if (m < M && n0 < N) {
           const long long row = m * e.ldc;
           const bool full_vec = (n0 + 32 <= N) && ((e.ldc & 3) == 0);
@@ -398,9 +418,34 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, int K, 
   return 0;
 }
 
+__global__ void __launch_bounds__(256)
+k_splitk_reduce(const float* __restrict__ ws, const float* __restrict__ bias, float* __restrict__ out,
+                long long M, int N, long long ldc, int splits) {
+  const long long total = M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + i];   // fixed order: deterministic
+    const long long m = i / N;
+    const int n = (int)(i % N);
+    out[m * ldc + n] = acc + (bias != nullptr ? bias[n] : 0.f);
+  }
+}
+
+static int pick_splits(long long M, int N, int K, int BN) {
+  const long long tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
+  const int num_kb = K / TC_BK;
+  if (tiles >= 96 || num_kb < 64) return 1;
+  long long s = (296 + tiles - 1) / tiles;
+  if (s > num_kb / 16) s = num_kb / 16;
+  if (s > 64) s = 64;
+  return s < 2 ? 1 : (int)s;
+}
+
 template <int BN>
 static int launch_tc(const float* Ahi, const float* Alo, long long lda, const float* Bhi, const float* Blo,
-                     long long ldb, long long M, int N, int K, const TcEpilogue& ep, cudaStream_t s) {
+                     long long ldb, long long M, int N, int K, const TcEpilogue& ep, int splits, float* ws,
+                     cudaStream_t s) {
   CUtensorMap mAh, mAl, mBh, mBl;
   if (make_map(&mAh, Ahi, M, K, lda, TC_BM) || make_map(&mAl, Alo, M, K, lda, TC_BM) ||
       make_map(&mBh, Bhi, N, K, ldb, BN) || make_map(&mBl, Blo, N, K, ldb, BN))
@@ -414,10 +459,17 @@ static int launch_tc(const float* Ahi, const float* Alo, long long lda, const fl
     }
     attr_set = true;
   }
-  const long long tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
+  const long long tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN) * splits;
   const int grid = (int)(tiles < 148 ? tiles : 148);
-  k_gemm_tc3<BN><<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, s>>>(mAh, mAl, mBh, mBl, M, N, K, ep);
-  return check_launch("k_gemm_tc3");
+  k_gemm_tc3<BN><<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, s>>>(mAh, mAl, mBh, mBl, M, N, K, ep, splits, ws);
+  if (check_launch("k_gemm_tc3")) return -1;
+  if (splits > 1) {
+    long long blocks = (M * N + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_splitk_reduce<<<(int)blocks, 256, 0, s>>>(ws, ep.e.bias, ep.e.pre_out, M, N, ep.e.ldc, splits);
+    return check_launch("k_splitk_reduce");
+  }
+  return 0;
 }
 
 int gemm_nt_simt(const float* A, long long lda, const float* Bm, long long ldb, long long M, int N, int K,
@@ -437,11 +489,18 @@ extern "C" int impflow_gemm_nt(const float* A, long long lda, const float* Bm, l
   return gemm_nt_simt(A, lda, Bm, ldb, M, N, K, ep, (cudaStream_t)stream);
 }
 
+static int tc_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
+
+extern "C" int impflow_gemm_tc_splits(long long M, int N, int K) {
+  if (K % TC_BK != 0) return 1;
+  return pick_splits(M, N, K, tc_bn(N));
+}
+
 extern "C" int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long long lda, const float* B_hi,
                                   const float* B_lo, long long ldb, const float* bias, float* pre_out,
                                   float* act_out, const float* dmul_pre, float* split_hi, float* split_lo,
                                   long long ldc, long long M, int N, int K, int act_kind,
-                                  const float* beta_sp, void* stream) {
+                                  const float* beta_sp, float* splitk_ws, void* stream) {
   IMPFLOW_REQUIRE(M >= 1 && N >= 1 && K >= 1, "gemm_nt_tc: empty problem M=%lld N=%d K=%d", M, N, K);
   IMPFLOW_REQUIRE(pre_out != nullptr || act_out != nullptr || split_hi != nullptr, "gemm_nt_tc: no output given");
   IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr || split_hi != nullptr,
@@ -459,7 +518,11 @@ extern "C" int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long lon
   }
   TcEpilogue ep{{bias, pre_out, act_out, dmul_pre, ldc, act_kind, beta_sp, 0.f}, split_hi, split_lo};
   cudaStream_t s = (cudaStream_t)stream;
-  if (N <= 32) return launch_tc<32>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, s);
-  if (N <= 64) return launch_tc<64>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, s);
-  return launch_tc<128>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, s);
+  // split-K only for the plain epilogue (weight-gradient GEMMs) and only if the caller gave a workspace
+  int splits = 1;
+  if (splitk_ws != nullptr && act_out == nullptr && dmul_pre == nullptr && split_hi == nullptr && pre_out != nullptr)
+    splits = pick_splits(M, N, K, tc_bn(N));
+  if (N <= 32) return launch_tc<32>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
+  if (N <= 64) return launch_tc<64>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
+  return launch_tc<128>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
 }

@@ -55,6 +55,23 @@ def branch_eval(nnet, x):
     return prog.forward(x) if prog is not None else nnet(x)
 
 
+_pinned = {}
+
+
+def _upload(host_t, like):
+    """Host tensor -> device of `like` through a reusable pinned staging buffer (async H2D)."""
+    if not like.is_cuda:
+        return host_t.to(like)
+    slots = _pinned.setdefault(host_t.numel(), [])
+    # two alternating buffers per size: the previous upload of the same size may still be in flight
+    if len(slots) < 4:
+        slots.append(torch.empty(host_t.numel(), dtype=torch.float32).pin_memory())
+    buf = slots.pop(0)
+    slots.append(buf)
+    buf.copy_(host_t.reshape(-1))
+    return buf.to(like.device, non_blocking=True).view(host_t.shape)
+
+
 def find_fixed_point(g, y, threshold=1000, eps=1e-5):
     """Banach iteration, fallback after a protective break (implicit_block.py:17-28)."""
     x, x_prev = g(y), y
@@ -232,17 +249,28 @@ class imBlock(nn.Module):
         return x, logpy + self._logdetgrad(z, x)
 
     # --------------------------------------------------------------------------------------
+    def _rate(self):
+        """geom p / poisson lambda as a python float: one device read per change of the tensor
+        (the reference reads it with .item() once per _logdetgrad call, :264-269)."""
+        t = self.geom_p if self.n_dist == 'geometric' else self.lamb
+        key = (self.n_dist, t._version, t.data_ptr())
+        cached = getattr(self, '_rate_cache', None)
+        if cached is None or cached[0] != key:
+            val = torch.sigmoid(t).item() if self.n_dist == 'geometric' else t.item()
+            cached = self._rate_cache = (key, val)
+        return cached[1]
+
     def _draw_n(self):
         if self._inject_n is not None:
             return np.asarray(self._inject_n)
         if self.n_dist == 'geometric':
-            return geometric_sample(torch.sigmoid(self.geom_p).item(), self.n_samples)
-        return poisson_sample(self.lamb.item(), self.n_samples)
+            return geometric_sample(self._rate(), self.n_samples)
+        return poisson_sample(self._rate(), self.n_samples)
 
     def _rcdf(self, k, offset):
         if self.n_dist == 'geometric':
-            return geometric_1mcdf(torch.sigmoid(self.geom_p).item(), k, offset)
-        return poisson_1mcdf(self.lamb.item(), k, offset)
+            return geometric_1mcdf(self._rate(), k, offset)
+        return poisson_1mcdf(self._rate(), k, offset)
 
     def _draw_probes(self, x, z):
         if self._inject_probes is not None:
@@ -252,9 +280,11 @@ class imBlock(nn.Module):
             vx = torch.randint(0, 2, x.shape, device=x.device).to(x) * 2 - 1
             vz = torch.randint(0, 2, z.shape, device=z.device).to(z) * 2 - 1
             return vx, vz
+        # same draws as the reference (CPU generator, vareps_x before vareps_z, :297-298); the
+        # +-1 values are staged in pinned memory so the upload does not synchronise the stream
         bern = torch.distributions.bernoulli.Bernoulli(torch.Tensor([0.5]))
-        vx = bern.sample(x.shape).reshape(x.shape).to(x) * 2 - 1
-        vz = bern.sample(z.shape).reshape(z.shape).to(z) * 2 - 1
+        vx = _upload(bern.sample(x.shape).reshape(x.shape) * 2 - 1, x)
+        vz = _upload(bern.sample(z.shape).reshape(z.shape) * 2 - 1, z)
         return vx, vz
 
     def _logdetgrad(self, z, x):

@@ -109,9 +109,12 @@ def rowdot(a, c, out=None, alpha=1.0, beta=0.0):
 
 def colsum(a2d):
     a2d = a2d.contiguous()
-    out = torch.empty(a2d.shape[1], device=a2d.device, dtype=torch.float32)
-    _cabi.check(_lib().impflow_colsum(_cabi.ptr(a2d), _cabi.ptr(out), a2d.shape[0], a2d.shape[1], _cabi.stream()),
-                'colsum')
+    M, N = a2d.shape
+    out = torch.empty(N, device=a2d.device, dtype=torch.float32)
+    chunks = int(_lib().impflow_colsum_chunks(M, N))
+    partial = torch.empty(chunks * N, device=a2d.device, dtype=torch.float32) if chunks > 1 else None
+    _cabi.check(_lib().impflow_colsum(_cabi.ptr(a2d), _cabi.ptr(out), _cabi.ptr(partial, 'partial', True), M, N,
+                                      _cabi.stream()), 'colsum')
     return out
 
 
@@ -163,7 +166,7 @@ def _tc_ok(M, N, K, lda, ldb):
     ok = (K % 32 == 0) and (lda % 4 == 0) and (ldb % 4 == 0)
     if mode == 'tc':
         return ok
-    return ok and (2 * M * N * K >= _BACKEND['min_flops_tc']) and M >= 128 and N >= 16
+    return ok and (2 * M * N * K >= _BACKEND['min_flops_tc']) and N >= 8
 
 
 def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, want_act=False, dmul_pre=None,
@@ -189,6 +192,11 @@ def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, wa
         Bh, Bl = B_split if B_split is not None else split_tf32(Bm)
         sh = torch.empty(M, N, device=dev, dtype=torch.float32) if want_split else None
         sl = torch.empty(M, N, device=dev, dtype=torch.float32) if want_split else None
+        ws = None
+        if act is None and dmul_pre is None and not want_split:
+            splits = int(lib.impflow_gemm_tc_splits(M, N, K))
+            if splits > 1:
+                ws = torch.empty(splits * M * N, device=dev, dtype=torch.float32)
         if GEMM_PROFILE['on']:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -196,7 +204,8 @@ def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, wa
                                            _cabi.ptr(bias, 'bias', True), _cabi.ptr(pre, 'pre', True),
                                            _cabi.ptr(act, 'act', True), _cabi.ptr(dmul_pre, 'dmul', True),
                                            _cabi.ptr(sh, 'sh', True), _cabi.ptr(sl, 'sl', True), N, M, N, K,
-                                           act_kind, _cabi.ptr(beta_sp, 'beta', True), _cabi.stream()),
+                                           act_kind, _cabi.ptr(beta_sp, 'beta', True),
+                                           _cabi.ptr(ws, 'ws', True), _cabi.stream()),
                     'gemm_nt_tc')
         if GEMM_PROFILE['on']:
             e1 = torch.cuda.Event(enable_timing=True)

@@ -106,8 +106,10 @@ int impflow_lincomb3(const float* a, float ca, const float* b, float cb, const f
  * (implicit_block.py:423,437). */
 int impflow_rowdot(const float* a, const float* c, float* out, int B, long long d, float alpha, float beta,
                    void* stream);
-/* out[n] = sum_m a[m,n]  (bias gradient). */
-int impflow_colsum(const float* a, float* out, long long M, int N, void* stream);
+/* out[n] = sum_m a[m,n]  (bias gradient); two deterministic stages over row chunks, `partial`
+ * holds impflow_colsum_chunks(M,N) * N floats (may be NULL when that is 1). */
+int impflow_colsum_chunks(long long M, int N);
+int impflow_colsum(const float* a, float* out, float* partial, long long M, int N, void* stream);
 /* out[n,m] = a[m,n] */
 int impflow_transpose(const float* a, float* out, long long M, long long N, void* stream);
 /* NHWC 3x3, stride 1, pad 1 patch gather col[(b,y,x),(ky,kx,c)] = x[b,y+ky-1,x+kx-1,c] (rows of
@@ -138,7 +140,11 @@ int impflow_gemm_nt(const float* A, long long lda, const float* Bm, long long ld
 int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long long lda, const float* B_hi,
                        const float* B_lo, long long ldb, const float* bias, float* pre_out, float* act_out,
                        const float* dmul_pre, float* split_hi, float* split_lo, long long ldc, long long M,
-                       int N, int K, int act_kind, const float* beta_sp, void* stream);
+                       int N, int K, int act_kind, const float* beta_sp, float* splitk_ws, void* stream);
+/* Weight-gradient shapes (small M x N, K = all pixels) are split along K over the SMs: with the plain
+ * epilogue (pre_out (+bias) only) and a workspace of impflow_gemm_tc_splits(M,N,K) * M * N floats the
+ * kernel writes per-slice partials and a fixed-order reduce finishes; splitk_ws = NULL disables it. */
+int impflow_gemm_tc_splits(long long M, int N, int K);
 /* a -> tf32 "hi" (round-to-nearest) and "lo" = a - hi planes used by the 3xTF32 backend. */
 int impflow_split_tf32(const float* a, float* hi, float* lo, long long n, void* stream);
 

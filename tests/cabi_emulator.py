@@ -258,7 +258,13 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
-    def impflow_colsum(self, a, out, M, N, stream):
+    def impflow_colsum_chunks(self, M, N):
+        return 1
+
+    def impflow_gemm_tc_splits(self, M, N, K):
+        return 1
+
+    def impflow_colsum(self, a, out, partial, M, N, stream):
         _f32(out, N)[:] = _f32(a, M * N).reshape(M, N).sum(0)
         self.launches += 1
         return 0
@@ -312,7 +318,7 @@ class EmulatedLib(object):
         return 0
 
     def impflow_gemm_nt_tc(self, A_hi, A_lo, lda, B_hi, B_lo, ldb, bias, pre_out, act_out, dmul_pre, split_hi,
-                           split_lo, ldc, M, N, K, act_kind, beta_sp, stream):
+                           split_lo, ldc, M, N, K, act_kind, beta_sp, splitk_ws, stream):
         if K % 32 or lda % 4 or ldb % 4:
             self._err = b'gemm_nt_tc: layout'
             return -2

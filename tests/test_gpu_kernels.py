@@ -59,6 +59,33 @@ def test_gemm_tcgen05_3xtf32(ops, M, N, K):
     ops.set_gemm_backend('auto')
 
 
+@pytest.mark.parametrize('M,N,K', [(27, 512, 65536), (512, 512, 16384), (512, 27, 4096), (130, 70, 8192)])
+def test_gemm_tcgen05_split_k(ops, M, N, K):
+    """Weight-gradient shapes: small M x N, long K -> split-K partials + fixed-order reduce."""
+    import impflow_b200
+    ops.set_gemm_backend('tc')
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g) / np.sqrt(K)
+    bias = torch.randn(N, generator=g)
+    assert impflow_b200._cabi.load().impflow_gemm_tc_splits(M, N, K) > 1
+    pre, _, _ = ops.gemm_nt(A.cuda(), B.cuda(), bias.cuda())
+    pre_again, _, _ = ops.gemm_nt(A.cuda(), B.cuda(), bias.cuda())
+    ref = A.double() @ B.double().t() + bias.double()
+    assert rel_err(pre.cpu(), ref) < 3e-6
+    assert torch.equal(pre, pre_again)            # deterministic reduce order
+    ops.set_gemm_backend('auto')
+
+
+def test_colsum_large(ops):
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(65536, 512, generator=g)
+    out = ops.colsum(a.cuda()).cpu()
+    torch.testing.assert_close(out, a.double().sum(0).float(), rtol=1e-4, atol=1e-2)
+    a = torch.randn(70, 5, generator=g)
+    torch.testing.assert_close(ops.colsum(a.cuda()).cpu(), a.double().sum(0).float(), rtol=1e-5, atol=1e-5)
+
+
 def test_gemm_tcgen05_dmul(ops):
     ops.set_gemm_backend('tc')
     g = torch.Generator().manual_seed(5)
