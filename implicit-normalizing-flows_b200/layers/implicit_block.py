@@ -207,7 +207,8 @@ class imBlock(nn.Module):
                 Fz = nnet_z(z) + z
 
             def g(v):     # v^T dFz/dz - grad: one vjp through the branch per call (:199-203)
-                (vJ,) = torch.autograd.grad(Fz, z, v, retain_graph=True)
+                with ops.activations_only():
+                    (vJ,) = torch.autograd.grad(Fz, z, v, retain_graph=True)
                 return ops.lincomb3(vJ, 1.0, grad, -1.0)
 
             info = broyden(g, torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
@@ -216,7 +217,8 @@ class imBlock(nn.Module):
             del Fz
             with torch.enable_grad():
                 Fx = nnet_x(x) + x
-            (dl_dx,) = torch.autograd.grad(Fx, x, dl_dh)
+            with ops.activations_only():
+                (dl_dx,) = torch.autograd.grad(Fx, x, dl_dh)
             return (None, None, dl_dh, dl_dx) + (None,) * len(args)
 
     def forward(self, x, logpx=None, restore=False):
@@ -349,7 +351,8 @@ def batch_jacobian(g, x, create_graph=True):
     """(B,d,d) Jacobian from d vjps (implicit_block.py:358-362)."""
     rows = []
     for j in range(g.shape[1]):
-        (r,) = torch.autograd.grad(torch.sum(g[:, j]), x, create_graph=create_graph)
+        with ops.activations_only():
+            (r,) = torch.autograd.grad(torch.sum(g[:, j]), x, create_graph=create_graph)
         rows.append(r.view(x.shape[0], 1, x.shape[1]))
     return torch.cat(rows, 1)
 
@@ -419,7 +422,8 @@ def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, pro
         return out
     logdetgrad = torch.tensor(0.).to(x)
     for k in range(1, n_power_series + 1):
-        vjp = torch.autograd.grad(g, x, vjp, create_graph=training, retain_graph=True)[0]
+        with ops.activations_only():
+            vjp = torch.autograd.grad(g, x, vjp, create_graph=training, retain_graph=True)[0]
         tr = ops.rowdot_fn(vjp, vareps)
         logdetgrad = logdetgrad + (-1) ** (k + 1) / k * coeff_fn(k) * tr
     return logdetgrad
@@ -437,9 +441,11 @@ def neumann_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, p
             if program is not None:
                 vjp = program.vjp(vjp)
             else:
-                vjp = torch.autograd.grad(g, x, vjp, retain_graph=True)[0]
+                with ops.activations_only():
+                    vjp = torch.autograd.grad(g, x, vjp, retain_graph=True)[0]
             neumann_vjp = ops.lincomb3(neumann_vjp, 1.0, vjp, float((-1) ** k * coeff_fn(k)))
-    vjp_jac = torch.autograd.grad(g, x, neumann_vjp, create_graph=training)[0]
+    with ops.activations_only():
+        vjp_jac = torch.autograd.grad(g, x, neumann_vjp, create_graph=training)[0]
     return ops.rowdot_fn(vjp_jac, vareps)
 
 

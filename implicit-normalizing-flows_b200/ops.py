@@ -24,6 +24,25 @@ _BACKEND = {'mode': 'auto', 'min_flops_tc': 2 * 128 * 128 * 64}
 GEMM_PROFILE = {'on': False, 'events': []}
 
 
+# While a caller differentiates w.r.t. ACTIVATIONS only (the vjp chains of the log-det estimators,
+# implicit_block.py:422,434,436), the parameter-gradient branches of the primitives' backward
+# passes (weight-gradient GEMMs with their transposes, bias column sums, LipSwish beta reductions)
+# are dead work: ctx.needs_input_grad is fixed at forward time and cannot tell.  The estimators
+# switch this flag on around those torch.autograd.grad calls.
+_ACT_ONLY = {'on': False}
+
+
+class activations_only(object):
+    """Context manager: backward passes of the kernel primitives skip parameter gradients."""
+
+    def __enter__(self):
+        self._prev = _ACT_ONLY['on']
+        _ACT_ONLY['on'] = True
+
+    def __exit__(self, *exc):
+        _ACT_ONLY['on'] = self._prev
+
+
 def set_gemm_backend(mode):
     assert mode in ('auto', 'simt', 'tc')
     _BACKEND['mode'] = mode
@@ -264,7 +283,7 @@ class _ActMul(torch.autograd.Function):
                 gx = _ActMul.apply(x, inner, beta_sp, kind, order + 1)
         if g is not None and ctx.needs_input_grad[1]:
             gg = _ActMul.apply(x, gout, beta_sp, kind, order)
-        if beta_sp is not None and ctx.needs_input_grad[2]:
+        if beta_sp is not None and ctx.needs_input_grad[2] and not _ACT_ONLY['on']:
             if order > 2:
                 raise RuntimeError('impflow_b200: beta gradient above order 2 is not implemented')
             gbeta = act_beta_grad(x, inner.detach(), order, beta_sp.detach()).view_as(beta_sp)
@@ -313,9 +332,9 @@ class _GemmNT(torch.autograd.Function):
         G = G.contiguous()
         if ctx.needs_input_grad[0]:
             gA = _GemmNT.apply(G, _Transpose.apply(Bm), None)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and not _ACT_ONLY['on']:
             gB = _GemmNT.apply(_Transpose.apply(G), _Transpose.apply(A), None)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[2] and not _ACT_ONLY['on']:
             gbias = _ColSum.apply(G)
         return gA, gB, gbias
 
@@ -325,26 +344,32 @@ def linear(x2d, W, bias=None):
 
 
 class _Im2col(torch.autograd.Function):
+    """(B,H,W,C) -> (B*H*W, ld) patches, ld >= 9C zero padded; adjoint = _Col2im on the first 9C columns."""
+
     @staticmethod
-    def forward(ctx, x_nhwc):
+    def forward(ctx, x_nhwc, ld):
         ctx.shape = tuple(x_nhwc.shape)
-        return im2col3x3(x_nhwc)
+        ctx.ld = ld
+        return im2col3x3(x_nhwc, ld)
 
     @staticmethod
     def backward(ctx, g):
         B, H, W, C = ctx.shape
-        return _Col2im.apply(g, B, H, W, C)
+        if ctx.ld != 9 * C:
+            g = g[:, :9 * C]           # the zero-padded tail carries no gradient
+        return _Col2im.apply(g, B, H, W, C), None
 
 
 class _Col2im(torch.autograd.Function):
     @staticmethod
     def forward(ctx, col, B, H, W, C):
+        ctx.C = C
         pre, _ = col2im3x3(col, B, H, W, C)
         return pre
 
     @staticmethod
     def backward(ctx, g):
-        return _Im2col.apply(g), None, None, None, None
+        return _Im2col.apply(g, 9 * ctx.C), None, None, None, None
 
 
 def conv3x3_nhwc(x_nhwc, W_oihw, bias=None):
@@ -353,8 +378,12 @@ def conv3x3_nhwc(x_nhwc, W_oihw, bias=None):
     B, H, Wd, Cin = x_nhwc.shape
     Cout = W_oihw.shape[0]
     if Cin <= Cout:
-        Wr = W_oihw.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)           # (co, ky, kx, ci)
-        y = _GemmNT.apply(_Im2col.apply(x_nhwc), Wr, bias)
+        K = 9 * Cin
+        Kp = (K + 31) // 32 * 32 if _BACKEND['mode'] != 'simt' else K    # K % 32 == 0 -> tcgen05 kernel
+        Wr = W_oihw.permute(0, 2, 3, 1).reshape(Cout, K)                 # (co, ky, kx, ci)
+        if Kp != K:
+            Wr = torch.nn.functional.pad(Wr, (0, Kp - K))
+        y = _GemmNT.apply(_Im2col.apply(x_nhwc, Kp), Wr, bias)
         return y.view(B, H, Wd, Cout)
     W2 = W_oihw.flip(2, 3).permute(2, 3, 0, 1).reshape(9 * Cout, Cin)    # (ky, kx, co) <- flipped taps
     Y = _GemmNT.apply(x_nhwc.reshape(B * H * Wd, Cin), W2, None)

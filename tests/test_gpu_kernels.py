@@ -72,7 +72,7 @@ def test_gemm_tcgen05_split_k(ops, M, N, K):
     pre, _, _ = ops.gemm_nt(A.cuda(), B.cuda(), bias.cuda())
     pre_again, _, _ = ops.gemm_nt(A.cuda(), B.cuda(), bias.cuda())
     ref = A.double() @ B.double().t() + bias.double()
-    assert rel_err(pre.cpu(), ref) < 3e-6
+    assert rel_err(pre.cpu(), ref) < 1e-5         # fp32 accumulation over up to 65 536 terms
     assert torch.equal(pre, pre_again)            # deterministic reduce order
     ops.set_gemm_backend('auto')
 
