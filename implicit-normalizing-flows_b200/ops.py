@@ -199,6 +199,14 @@ def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, wa
     M, K = A.shape
     N = Bm.shape[0]
     assert Bm.shape[1] == K, 'gemm_nt: inner dimensions differ'
+    if K % 32 != 0 and _BACKEND['mode'] != 'simt' and N >= 8 and 2 * M * N * K >= 64 * _BACKEND['min_flops_tc'] \
+            and A_split is None and B_split is None:
+        # a large GEMM with an odd inner dimension (e.g. K = 9*3 = 27): zero-pad K so that it runs on
+        # the tcgen05 kernel instead of CUDA cores
+        pad = (K + 31) // 32 * 32 - K
+        A = torch.nn.functional.pad(A, (0, pad))
+        Bm = torch.nn.functional.pad(Bm, (0, pad))
+        K += pad
     dev = A.device
     need_pre = want_pre or dmul_pre is not None
     pre = torch.empty(M, N, device=dev, dtype=torch.float32) if need_pre else None
