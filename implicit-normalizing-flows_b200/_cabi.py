@@ -27,7 +27,8 @@ SIGNATURES = {
     'impflow_broyden_step': (_i, [_c_fp] * 12 + [_i, _ll, _i, _c_fp]),
     'impflow_act_mul': (_i, [_c_fp, _c_fp, _c_fp, _ll, _i, _i, _c_fp, _c_fp]),
     'impflow_reduce_workspace_floats': (ctypes.c_size_t, [_ll]),
-    'impflow_act_beta_grad': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _ll, _i, _c_fp, _c_fp]),
+    'impflow_act_beta_grad': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _i, _c_fp, _c_fp]),
+    'impflow_act_second': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _i, _c_fp, _c_fp]),
     'impflow_lincomb3': (_i, [_c_fp, _f, _c_fp, _f, _c_fp, _f, _c_fp, _ll, _c_fp]),
     'impflow_rowdot': (_i, [_c_fp, _c_fp, _c_fp, _i, _ll, _f, _f, _c_fp]),
     'impflow_colsum_chunks': (_i, [_ll, _i]),

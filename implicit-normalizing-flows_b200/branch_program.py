@@ -1,17 +1,35 @@
-"""Fused, graph-free evaluation of a residual branch for the no-grad hot loops.
+"""Graph-free evaluation of a residual branch: forward, vjp, first-order backward and the
+hand-derived gradient of the Neumann log-det estimator — all as short sequences of impflow
+kernel launches, with no autograd graph.
 
-The three loops that dominate an ImpFlow step never need an autograd graph:
-  * the (nstep+1) branch evaluations of a forward / inverse Broyden solve (implicit_block.py:68-80),
-  * the vjps of the implicit-differentiation solve in backward (implicit_block.py:199-207),
-  * the n_power_series vjps of the Neumann estimator (implicit_block.py:432-435).
-A BranchProgram compiles an nn.Sequential of [act] layer act layer ... [act] (InducedNormLinear /
-InducedNormConv2d 1x1 / 3x3 + Sin / Swish / ReLU — every branch the shipped configs build) into a
-short list of kernel launches per evaluation:
-  forward : [act] -> (im2col) GEMM{bias, act, hi/lo split} -> ... -> GEMM (col2im{bias})
-  vjp     : GEMM^T{act', hi/lo split} ... with the pre-activations saved by forward(save=True)
-with the spectrally rescaled weights (compute_weight(update=False), hoisted out of the loops —
-they are constant within a solve), their conv-as-GEMM re-layouts and tf32 hi/lo planes cached until
-a parameter or u/v buffer changes version.
+Why: an ImpFlow step evaluates each branch ~60 times (Broyden g evaluations, implicit-backward
+vjps, the n-term vjp chain of the power series, the estimator's double backward).  Driving every
+one of them through nn.Module.__call__ + autograd costs thousands of tiny launches; the arithmetic
+is a handful of GEMMs.  A BranchProgram compiles an nn.Sequential of
+    [act] layer act layer ... layer [act]
+(InducedNormLinear / InducedNormConv2d 1x1 / 3x3 + Sin / Swish / ReLU: every branch the shipped
+configs build — train_toy.py:146-171, train_tabular.py:292-311, implicit_flow.py:359-398,
+train_classification.py:152-167) into:
+
+  forward(x)            nnet(x)                                      (implicit_block.py:68-80)
+  vjp(v)                v^T J                                        (:199-203, :432-435)
+  backward_full(g)      (g^T J, dL/dtheta)  for z = f_x(z0) - f_z(z*) + z0   (:227)
+  neumann(w, v)         S = <w^T J, v>, dS/dx, dS/dtheta             (:386-388, :429-438)
+
+Layer forms (rows = pixels or samples, channels contiguous):
+  mm   : linear / 1x1 conv          y = A W^T
+  c3 A : 3x3, cin <= cout           y = im2col(A) Wr^T        transpose: col2im(G W2t^T)
+  c3 B : 3x3, cin >  cout           y = col2im(A W2^T)        transpose: im2col(G) Wrt^T
+The spectrally rescaled weights (compute_weight(update=False)), their GEMM re-layouts and tf32
+hi/lo planes are cached until a parameter / u / v / beta changes version.
+
+neumann() differentiates S = sum_b <w_b, J_b v_b> by hand: S is the forward-mode tangent of the
+branch in direction v contracted with w, so one tangent sweep (t_{l} = W phi'(p) t_{l-1}) plus one
+reverse sweep carrying two adjoints per layer (of the tangent and of the primal) replaces
+autograd's double backward:
+    tbar_a = W^T tbar_y                abar = W^T ybar
+    Wbar  += tbar_y (x) t_a + ybar (x) a          bbar += sum ybar
+    tbar_p = phi'(p) tbar_a            pbar = phi''(p) t_p tbar_a + phi'(p) abar
 """
 import torch
 import torch.nn as nn
@@ -51,6 +69,23 @@ class _Weights(object):
     __slots__ = ('fwd', 'fwd_split', 'bwd', 'bwd_split', 'bias', 'kind', 'cin', 'cout', 'fwd_k', 'bwd_k', 'a_type')
 
 
+class _T(object):
+    """A rows-space activation: fp32 tensor and/or its tf32 hi/lo planes."""
+    __slots__ = ('f', 's')
+
+    def __init__(self, f=None, s=None):
+        self.f, self.s = f, s
+
+    def f32(self):
+        if self.f is None:
+            self.f = ops.lincomb3(self.s[0], 1.0, self.s[1], 1.0)
+        return self.f
+
+
+class _Saved(object):
+    __slots__ = ('rows', 'meta', 'M', 'pres', 'ains')
+
+
 def _act_of(m):
     if isinstance(m, Sin):
         return _Act(ops.ACT_SIN)
@@ -86,27 +121,31 @@ def compile_branch(nnet):
     kinds = {isinstance(m, InducedNormLinear) for _, m in stages}
     if len(kinds) != 1:
         return None
-    return BranchProgram(stages, pending, flatten)
+    return BranchProgram(stages, pending, flatten, list(nnet.parameters()))
 
 
 class BranchProgram(object):
 
-    def __init__(self, stages, post_act, flatten):
+    def __init__(self, stages, post_act, flatten, params):
         self.stages = stages            # [(pre_act or None, layer module)]
         self.post_act = post_act
         self.flatten = flatten
+        self.params = params            # nnet.parameters() order: the order gradients are returned in
         self.is_linear = isinstance(stages[0][1], InducedNormLinear)
         self._key = None
         self._weights = None
         self._saved = None
 
     # ---------------------------------------------------------------- weights
+    def _acts(self):
+        return [a for a, _ in self.stages] + [self.post_act]
+
     def _version_key(self):
         key = []
         for act, m in self.stages:
             key += [m.weight._version, m.u._version, m.v._version, m.weight.data_ptr(),
                     (m.bias._version if m.bias is not None else -1)]
-        for act in [a for a, _ in self.stages] + [self.post_act]:
+        for act in self._acts():
             if act is not None and act.module is not None:
                 key += [act.module.beta._version, act.module.beta.data_ptr()]
         return tuple(key)
@@ -126,7 +165,7 @@ class BranchProgram(object):
             return self._weights
         ws = []
         with torch.no_grad():
-            for act in [a for a, _ in self.stages] + [self.post_act]:
+            for act in self._acts():
                 if act is not None:
                     act.refresh()
             for act, m in self.stages:
@@ -189,15 +228,18 @@ class BranchProgram(object):
         return y.view(B, H, W, y.shape[-1]).permute(0, 3, 1, 2)
 
     def _gemm(self, A, A_split, Wm, Wk, W_split, bias, act, want_pre, want_act, dmul_pre, want_split):
-        """One fused GEMM launch; A is (M, Wk) fp32 and/or its planes."""
+        """One fused GEMM launch; A is (M, Wk) fp32 and/or its planes.  Epilogue as in the header:
+        normal: pre = acc+bias, act = act(pre); dmul: pre = acc*act'(dmul_pre), act = acc (raw)."""
         lib = _cabi.load()
         M = (A if A is not None else A_split[0]).shape[0]
         N = Wm.shape[0]
         dev = Wm.device
         kind = act.kind if act is not None else ops.ACT_NONE
         beta = act.beta_sp() if act is not None else None
-        if W_split is None and not want_act:
-            want_pre = True            # the CUDA-core kernel has no plane outputs
+        if W_split is None:
+            want_split = False
+            if not want_act and not want_pre:
+                want_pre = True
         pre = torch.empty(M, N, device=dev, dtype=torch.float32) if want_pre else None
         out_act = torch.empty(M, N, device=dev, dtype=torch.float32) if want_act else None
         if W_split is not None:
@@ -234,113 +276,280 @@ class BranchProgram(object):
         out[:, :A.shape[1]] = A
         return out
 
+    @staticmethod
+    def _im2col_first(w, transpose):
+        """True when (this direction of) the layer is im2col + GEMM; False for GEMM (+ col2im)."""
+        return w.kind == 'c3' and (w.a_type != transpose)
+
+    def _wants_planes(self, w, transpose, channels):
+        """Can the layer (in this direction) consume hi/lo planes of a `channels`-wide input directly?"""
+        if w.kind == 'c3' and self._im2col_first(w, transpose):
+            return False
+        Wk, Wsp = (w.bwd_k, w.bwd_split) if transpose else (w.fwd_k, w.fwd_split)
+        return Wsp is not None and Wk == channels
+
+    def _apply(self, w, X, meta, transpose, bias=None, act=None, want_pre=True, want_act=False, dmul_pre=None,
+               want_split=False):
+        """Apply layer `w` (or its transpose) to the rows-space handle X with the fused epilogue.
+        Returns (pre, act_out, split)."""
+        Wm, Wk, Wsp = (w.bwd, w.bwd_k, w.bwd_split) if transpose else (w.fwd, w.fwd_k, w.fwd_split)
+        cin = w.cout if transpose else w.cin
+        cout = w.cin if transpose else w.cout
+        M = (X.f if X.f is not None else X.s[0]).shape[0]
+        next_is_pre = dmul_pre is not None or act is None      # which output feeds the next layer
+        if w.kind == 'mm' or self._im2col_first(w, transpose):
+            if w.kind == 'c3':
+                B, H, Wd = meta[1]
+                A, A_split = ops.im2col3x3(X.f32().view(B, H, Wd, cin), ld=Wk), None
+            else:
+                A_split = X.s if (X.s is not None and Wsp is not None and X.s[0].shape[1] == Wk) else None
+                A = self._pad_cols(X.f32(), Wk) if A_split is None else None
+            if want_split and Wsp is None:          # CUDA-core GEMM: planes come from the split kernel below
+                want_pre, want_act = (True, want_act) if next_is_pre else (want_pre, True)
+            pre, a_out, split = self._gemm(A, A_split, Wm, Wk, Wsp, bias, act, want_pre, want_act, dmul_pre,
+                                           want_split)
+        else:
+            B, H, Wd = meta[1]
+            A_split = X.s if (X.s is not None and Wsp is not None and X.s[0].shape[1] == Wk) else None
+            A = self._pad_cols(X.f32(), Wk) if A_split is None else None
+            Y, _, _ = self._gemm(A, A_split, Wm, Wk, Wsp, None, None, True, False, None, False)
+            if want_split:
+                want_pre, want_act = (True, want_act) if next_is_pre else (want_pre, True)
+            pre, a_out = ops.col2im3x3(Y, B, H, Wd, cout, bias, act.kind if act is not None else ops.ACT_NONE,
+                                       act.beta_sp() if act is not None else None, want_pre=want_pre,
+                                       want_act=want_act,
+                                       dmul_pre=dmul_pre.view(B, H, Wd, cout) if dmul_pre is not None else None)
+            pre = pre.view(M, cout) if pre is not None else None
+            a_out = a_out.view(M, cout) if a_out is not None else None
+            split = None
+        if want_split and split is None:
+            split = ops.split_tf32(pre if next_is_pre else a_out)
+        return pre, a_out, split
+
     # ---------------------------------------------------------------- forward
-    def forward(self, x, save=False):
-        """nnet(x) without a graph.  save=True keeps the pre-activations for vjp()."""
+    def forward_saved(self, x, save=True):
+        """(nnet(x), saved) without a graph; saved feeds vjp / backward_full / neumann."""
         rows, meta = self._to_rows(x)
         M = rows.shape[0]
         ws = self._prep(M, meta)
-        saved = []                    # saved[i] = input of the activation in front of layer i (or None)
         n = len(self.stages)
-        h, h_split = rows, None
+        pres = [None] * (n + 1)       # pres[i] = input of the activation in front of layer i (pres[n]: post act)
+        ains = [None] * n             # ains[i] = input handle of layer i (after its activation)
+        X = _T(f=rows)
         act0 = self.stages[0][0]
         if act0 is not None:
-            saved.append(rows if save else None)
-            h = ops.act_mul(rows, None, act0.kind, 0, act0.beta_sp())
-        else:
-            saved.append(None)
-        out = None
-        for i, (_, m) in enumerate(self.stages):
+            pres[0] = rows
+            X = _T(f=ops.act_mul(rows, None, act0.kind, 0, act0.beta_sp()))
+        for i in range(n):
             w = ws[i]
             last = i == n - 1
             nxt = self.post_act if last else self.stages[i + 1][0]
-            need_pre = (nxt is None) or (save and nxt is not None)
-            if w.kind == 'mm' or w.a_type:
-                if w.kind == 'c3':
-                    B, H, Wd = meta[1]
-                    A = ops.im2col3x3(h.view(B, H, Wd, w.cin), ld=w.fwd_k)
-                    A_split = None
-                else:
-                    A_split = h_split if (h_split is not None and h_split[0].shape[1] == w.fwd_k) else None
-                    A = self._pad_cols(h, w.fwd_k) if (A_split is None or w.fwd_split is None) else None
-                nxt_tc = (not last) and ws[i + 1].fwd_split is not None and \
-                    (ws[i + 1].kind == 'mm' or not ws[i + 1].a_type) and ws[i + 1].fwd_k == w.cout
-                emit_split = nxt_tc and w.fwd_split is not None
-                want_act = nxt is not None and (last or not emit_split or ws[i + 1].fwd_split is None)
-                pre, a_out, split = self._gemm(A, A_split, w.fwd, w.fwd_k, w.fwd_split, w.bias, nxt,
-                                               want_pre=need_pre, want_act=want_act, dmul_pre=None,
-                                               want_split=emit_split)
-                if nxt_tc and not emit_split:     # this GEMM ran on CUDA cores: planes by the split kernel
-                    split = ops.split_tf32(a_out if nxt is not None else pre)
-            else:   # narrow-output 3x3: GEMM to (M, 9*cout) then col2im with the fused epilogue
-                B, H, Wd = meta[1]
-                A_split = h_split if (h_split is not None and h_split[0].shape[1] == w.fwd_k) else None
-                A = self._pad_cols(h, w.fwd_k) if (A_split is None or w.fwd_split is None) else None
-                Y, _, _ = self._gemm(A, A_split, w.fwd, w.fwd_k, w.fwd_split, None, None, True, False, None, False)
-                pre, a_out = ops.col2im3x3(Y, B, H, Wd, w.cout, w.bias, nxt.kind if nxt is not None else ops.ACT_NONE,
-                                           nxt.beta_sp() if nxt is not None else None,
-                                           want_pre=need_pre, want_act=nxt is not None)
-                pre = pre.view(M, w.cout) if pre is not None else None
-                a_out = a_out.view(M, w.cout) if a_out is not None else None
-                split = None
+            ains[i] = X
+            want_split = (not last) and self._wants_planes(ws[i + 1], False, w.cout)
+            need_pre = (nxt is None) or save
+            want_act = nxt is not None and (last or not want_split)
+            pre, a_out, split = self._apply(w, X, meta, False, bias=w.bias, act=nxt, want_pre=need_pre,
+                                            want_act=want_act, want_split=want_split)
             if nxt is not None:
-                saved.append(pre if save else None)
-            else:
-                saved.append(None)
-            if last:
-                out = a_out if nxt is not None else pre
-            else:
-                h, h_split = (a_out if nxt is not None else pre), split
-                if h is None and h_split is None:
-                    raise RuntimeError('BranchProgram: lost the activation of layer %d' % i)
-                if h is None and not (ws[i + 1].fwd_split is not None and h_split[0].shape[1] == ws[i + 1].fwd_k):
-                    h = ops.lincomb3(h_split[0], 1.0, h_split[1], 1.0)
+                pres[i + 1] = pre
+            X = _T(f=(a_out if nxt is not None else pre), s=split)
+        out = X.f32()
+        saved = None
         if save:
-            self._saved = (saved, meta, M)
-        return self._from_rows(out, meta)
+            saved = _Saved()
+            saved.rows, saved.meta, saved.M, saved.pres, saved.ains = rows, meta, M, pres, ains
+        return self._from_rows(out, meta), saved
+
+    def forward(self, x, save=False):
+        y, saved = self.forward_saved(x, save)
+        if save:
+            self._saved = saved
+        return y
 
     # ---------------------------------------------------------------- vjp
-    def vjp(self, v):
-        """v^T J at the point of the last forward(save=True)."""
-        if self._saved is None:
+    def vjp(self, v, saved=None):
+        """v^T J at the point of `saved` (default: the last forward(save=True))."""
+        saved = saved if saved is not None else self._saved
+        if saved is None:
             raise RuntimeError('BranchProgram.vjp: call forward(save=True) first')
-        saved, meta, M = self._saved
+        meta, M, pres = saved.meta, saved.M, saved.pres
         ws = self._prep(M)
-        t, _ = self._to_rows(v)
-        t_split = None
         n = len(self.stages)
+        t, _ = self._to_rows(v)
+        T = _T(f=t)
         if self.post_act is not None:
-            t = ops.act_mul(saved[n], t, self.post_act.kind, 1, self.post_act.beta_sp())
+            T = _T(f=ops.act_mul(pres[n], t, self.post_act.kind, 1, self.post_act.beta_sp()))
         for i in range(n - 1, -1, -1):
             w = ws[i]
-            act = self.stages[i][0]            # activation in front of layer i: multiply by act'(saved[i])
-            dm = saved[i] if act is not None else None
-            if w.kind == 'mm' or not w.a_type:
-                # transpose is "wide K": plain GEMM (mm) or im2col + GEMM (narrow-output conv)
-                if w.kind == 'c3':
-                    B, H, Wd = meta[1]
-                    A = ops.im2col3x3(t.view(B, H, Wd, w.cout), ld=w.bwd_k)
-                    A_split = None
-                else:
-                    A_split = t_split if (t_split is not None and t_split[0].shape[1] == w.bwd_k) else None
-                    A = self._pad_cols(t, w.bwd_k) if (A_split is None or w.bwd_split is None) else None
-                nxt_tc = i > 0 and ws[i - 1].bwd_split is not None and \
-                    (ws[i - 1].kind == 'mm' or ws[i - 1].a_type) and ws[i - 1].bwd_k == w.cin
-                emit_split = nxt_tc and w.bwd_split is not None
-                pre, _, split = self._gemm(A, A_split, w.bwd, w.bwd_k, w.bwd_split, None, act, want_pre=not emit_split,
-                                           want_act=False, dmul_pre=dm, want_split=emit_split)
-                if nxt_tc and not emit_split:
-                    split = ops.split_tf32(pre)
-                t, t_split = pre, split
+            act = self.stages[i][0]            # activation in front of layer i: multiply by act'(pres[i])
+            dm = pres[i] if act is not None else None
+            want_split = i > 0 and self._wants_planes(ws[i - 1], True, w.cin)
+            pre, _, split = self._apply(w, T, meta, True, act=act, want_pre=not want_split, dmul_pre=dm,
+                                        want_split=want_split)
+            T = _T(f=pre, s=split)
+        return self._from_rows(T.f32(), meta)
+
+    # ---------------------------------------------------------------- parameter gradients
+    def _wgrad_gemm_layout(self, w, meta, G, Xin):
+        """dL/d(w.fwd) (N, Kpad) from the output adjoint G (M, cout) and the layer input handle."""
+        if w.kind == 'c3':
+            B, H, Wd = meta[1]
+            if w.a_type:
+                Gm, Am = G, ops.im2col3x3(Xin.f32().view(B, H, Wd, w.cin), ld=w.fwd_k)
             else:
-                B, H, Wd = meta[1]
-                A_split = t_split if (t_split is not None and t_split[0].shape[1] == w.bwd_k) else None
-                A = self._pad_cols(t, w.bwd_k) if (A_split is None or w.bwd_split is None) else None
-                Y, _, _ = self._gemm(A, A_split, w.bwd, w.bwd_k, w.bwd_split, None, None, True, False, None, False)
-                pre, _ = ops.col2im3x3(Y, B, H, Wd, w.cin, None, act.kind if act is not None else ops.ACT_NONE,
-                                       act.beta_sp() if act is not None else None, want_pre=True, want_act=False,
-                                       dmul_pre=dm.view(B, H, Wd, w.cin) if dm is not None else None)
-                t, t_split = pre.view(M, w.cin), None
-        if t is None:
-            t = ops.lincomb3(t_split[0], 1.0, t_split[1], 1.0)
-        return self._from_rows(t, meta)
+                Gm, Am = ops.im2col3x3(G.view(B, H, Wd, w.cout), ld=9 * w.cout), self._pad_cols(Xin.f32(), w.fwd_k)
+        else:
+            Gm, Am = G, self._pad_cols(Xin.f32(), w.fwd_k)
+        out, _, _ = ops.gemm_nt(ops.transpose2d(Gm), ops.transpose2d(Am))
+        return out
+
+    @staticmethod
+    def _to_weight_layout(w, Wbar):
+        """GEMM-layout gradient -> gradient of the effective weight in the module's weight layout."""
+        if w.kind == 'mm':
+            return Wbar[:, :w.cin]
+        if w.a_type:
+            return Wbar[:, :9 * w.cin].reshape(w.cout, 3, 3, w.cin).permute(0, 3, 1, 2)
+        return Wbar[:, :w.cin].reshape(3, 3, w.cout, w.cin).flip(0, 1).permute(2, 3, 0, 1)
+
+    def _finish_param_grads(self, ws, wbars, bbars, betabars):
+        """Chain the effective-weight gradients through the spectral rescale W / max(1, sigma/coeff)
+        (mixed_lipschitz.py:125-131: differentiable through sigma with u, v constant) and order
+        everything like nnet.parameters()."""
+        by_id = {}
+        for i, (act, m) in enumerate(self.stages):
+            if wbars[i] is not None:
+                g_eff = self._to_weight_layout(ws[i], wbars[i]).reshape(m.weight.shape).contiguous()
+                with torch.enable_grad():
+                    W_eff = m.compute_weight(update=False)
+                    (gw,) = torch.autograd.grad(W_eff, m.weight, g_eff)
+                by_id[id(m.weight)] = gw
+            if m.bias is not None and bbars[i] is not None:
+                by_id[id(m.bias)] = bbars[i]
+        for act, gb in zip(self._acts(), betabars):
+            if act is not None and act.module is not None and gb is not None:
+                # d/d(raw beta) = d/d softplus(beta) * sigmoid(beta)
+                by_id[id(act.module.beta)] = gb * torch.sigmoid(act.module.beta.detach())
+        return [by_id.get(id(p)) for p in self.params]
+
+    @staticmethod
+    def _add(a, b):
+        if a is None:
+            return b
+        if b is None:
+            return a
+        return ops.lincomb3(a, 1.0, b, 1.0)
+
+    def backward_full(self, saved, gout, need_input_grad=True):
+        """First-order backward of y = nnet(x): returns (g^T J or None, [dL/dp for p in parameters()])."""
+        meta, M, pres, ains = saved.meta, saved.M, saved.pres, saved.ains
+        ws = self._prep(M)
+        n = len(self.stages)
+        acts = self._acts()
+        wbars, bbars, betabars = [None] * n, [None] * n, [None] * (n + 1)
+        g, _ = self._to_rows(gout)
+        if self.post_act is not None:
+            pa = self.post_act
+            if pa.module is not None:
+                betabars[n] = ops.act_beta_grad(pres[n], g, 0, pa.beta_sp())
+            g = ops.act_mul(pres[n], g, pa.kind, 1, pa.beta_sp())
+        G = _T(f=g)
+        for i in range(n - 1, -1, -1):
+            w = ws[i]
+            act = acts[i]
+            Gf = G.f32()
+            wbars[i] = self._wgrad_gemm_layout(w, meta, Gf, ains[i])
+            if w.bias is not None:
+                bbars[i] = ops.colsum(Gf)
+            if i == 0 and not need_input_grad and (act is None or act.module is None):
+                break
+            if act is not None:
+                want_raw = act.module is not None
+                pbar, abar, _ = self._apply(w, G, meta, True, act=act, want_pre=True, want_act=want_raw,
+                                            dmul_pre=pres[i])
+                if want_raw:
+                    betabars[i] = ops.act_beta_grad(pres[i], abar, 0, act.beta_sp())
+            else:
+                pbar, _, _ = self._apply(w, G, meta, True, want_pre=True)
+            G = _T(f=pbar)
+        gx = self._from_rows(G.f32(), meta) if need_input_grad else None
+        return gx, self._finish_param_grads(ws, wbars, bbars, betabars)
+
+    # ---------------------------------------------------------------- Neumann estimator gradient
+    def neumann(self, saved, w_vec, v_vec, seed_scale=None):
+        """S_b = <w_b^T J_b, v_b> together with dS/dx and dS/dtheta of S = sum_b c_b S_b
+        (c = seed_scale or 1), by one tangent sweep and one two-adjoint reverse sweep."""
+        meta, M, pres, ains = saved.meta, saved.M, saved.pres, saved.ains
+        ws = self._prep(M)
+        n = len(self.stages)
+        acts = self._acts()
+        Bsz = v_vec.shape[0]
+        # ---- tangent sweep: t_p (tangent of every activation input), t_a (tangent of every layer input)
+        tps = [None] * (n + 1)
+        tas = [None] * n
+        tp0, _ = self._to_rows(v_vec)
+        TA = _T(f=tp0)
+        if acts[0] is not None:
+            tps[0] = tp0
+            TA = _T(f=ops.act_mul(pres[0], tp0, acts[0].kind, 1, acts[0].beta_sp()))
+        for i in range(n):
+            w = ws[i]
+            last = i == n - 1
+            nxt = acts[i + 1]
+            tas[i] = TA
+            want_split = (not last) and self._wants_planes(ws[i + 1], False, w.cout)
+            if nxt is not None:
+                prod, raw, split = self._apply(w, TA, meta, False, act=nxt, want_pre=(last or not want_split),
+                                               want_act=True, dmul_pre=pres[i + 1], want_split=want_split)
+                tps[i + 1] = raw
+                TA = _T(f=prod, s=split)
+            else:
+                pre, _, split = self._apply(w, TA, meta, False, want_pre=True, want_split=want_split)
+                TA = _T(f=pre, s=split)
+        tout = TA.f32()
+        wrows, _ = self._to_rows(w_vec)
+        S = ops.rowdot(tout.view(Bsz, -1), wrows.view(Bsz, -1))
+        if seed_scale is not None:
+            wrows = (wrows.view(Bsz, -1) * seed_scale.view(Bsz, 1)).view_as(wrows)
+        # ---- reverse sweep with two adjoints: Tbar (of the tangent) and Ybar (of the primal)
+        wbars, bbars, betabars = [None] * n, [None] * n, [None] * (n + 1)
+        Tbar, Ybar = _T(f=wrows), None
+        if self.post_act is not None:
+            pa = self.post_act
+            if pa.module is not None:
+                betabars[n] = ops.act_beta_grad(pres[n], wrows, 1, pa.beta_sp(), g2=tps[n])
+            Ybar = _T(f=ops.act_second(pres[n], tps[n], wrows, None, pa.kind, pa.beta_sp()))
+            Tbar = _T(f=ops.act_mul(pres[n], wrows, pa.kind, 1, pa.beta_sp()))
+        for i in range(n - 1, -1, -1):
+            w = ws[i]
+            act = acts[i]
+            wb = self._wgrad_gemm_layout(w, meta, Tbar.f32(), tas[i])
+            if Ybar is not None:
+                wb = self._add(wb, self._wgrad_gemm_layout(w, meta, Ybar.f32(), ains[i]))
+                if w.bias is not None:
+                    bbars[i] = ops.colsum(Ybar.f32())
+            wbars[i] = wb
+            abar = None
+            if Ybar is not None:
+                abar, _, _ = self._apply(w, Ybar, meta, True, want_pre=True)
+            if act is not None:
+                # one launch: tbar_p = phi'(p) * (W^T Tbar) in `prod`, the raw W^T Tbar in `raw`
+                prod, tabar, _ = self._apply(w, Tbar, meta, True, act=act, want_pre=(i > 0), want_act=True,
+                                             dmul_pre=pres[i])
+                if act.module is not None:
+                    gb = ops.act_beta_grad(pres[i], tabar, 1, act.beta_sp(), g2=tps[i])
+                    if abar is not None:
+                        gb = gb + ops.act_beta_grad(pres[i], abar, 0, act.beta_sp())
+                    betabars[i] = gb
+                Ybar = _T(f=ops.act_second(pres[i], tps[i], tabar, abar, act.kind, act.beta_sp()))
+                Tbar = _T(f=prod)
+            else:
+                if i > 0:
+                    tabar, _, _ = self._apply(w, Tbar, meta, True, want_pre=True)
+                    Tbar = _T(f=tabar)
+                Ybar = _T(f=abar) if abar is not None else None
+        if Ybar is not None:
+            gx = self._from_rows(Ybar.f32(), meta)
+        else:
+            gx = torch.zeros_like(v_vec)
+        return S, gx, self._finish_param_grads(ws, wbars, bbars, betabars)

@@ -124,7 +124,8 @@ __device__ __forceinline__ Epilogue resolve_beta(Epilogue e) {
 __device__ __forceinline__ void epilogue_store(const Epilogue& e, long long m, int n, float acc) {
   const long long idx = m * e.ldc + n;
   if (e.dmul_pre != nullptr) {
-    e.pre_out[idx] = acc * act_dispatch(e.act_kind, e.dmul_pre[idx], 1, e.beta);
+    if (e.pre_out) e.pre_out[idx] = acc * act_dispatch(e.act_kind, e.dmul_pre[idx], 1, e.beta);
+    if (e.act_out) e.act_out[idx] = acc;   // dmul mode: act_out receives the raw accumulator
     return;
   }
   const float v = acc + (e.bias ? e.bias[n] : 0.f);

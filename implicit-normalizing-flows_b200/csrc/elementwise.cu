@@ -65,13 +65,16 @@ k_act_mul(const float* __restrict__ x, const float* __restrict__ g, float* __res
 
 // ---- beta gradient of LipSwish: two-stage deterministic reduce --------------------------------
 __global__ void __launch_bounds__(256)
-k_beta_grad_stage1(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ partial,
-                   long long n, int order, const float* __restrict__ beta_ptr) {
+k_beta_grad_stage1(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ g2,
+                   float* __restrict__ partial, long long n, int order, const float* __restrict__ beta_ptr) {
   const float beta = __ldg(beta_ptr);
   double acc = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    acc += (double)(g[i] * lipswish_dbeta(x[i], order, beta));
+       i += (long long)gridDim.x * blockDim.x) {
+    float w = g[i];
+    if (g2 != nullptr) w *= g2[i];
+    acc += (double)(w * lipswish_dbeta(x[i], order, beta));
+  }
   __shared__ double ws[8];
   acc = warp_sum_d(acc);
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
@@ -87,6 +90,22 @@ __global__ void k_sum_partials(const float* __restrict__ partial, float* __restr
   for (int i = threadIdx.x; i < m; i += 32) acc += (double)partial[i];
   acc = warp_sum_d(acc);
   if (threadIdx.x == 0) out[0] = (float)acc;
+}
+
+// ---- second-order activation term of the Neumann-gradient reverse pass:
+//      out = act''(p) * t * ga + act'(p) * gb     (gb may be null)
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_act_second(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ ga,
+             const float* __restrict__ gb, float* __restrict__ out, long long n, const float* __restrict__ beta_ptr) {
+  const float beta = (beta_ptr != nullptr) ? __ldg(beta_ptr) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    float r = act_eval<KIND>(pv, 2, beta) * t[i] * ga[i];
+    if (gb != nullptr) r += act_eval<KIND>(pv, 1, beta) * gb[i];
+    out[i] = r;
+  }
 }
 
 // ---- lincomb3 -----------------------------------------------------------------------------------
@@ -285,13 +304,29 @@ extern "C" size_t impflow_reduce_workspace_floats(long long n) {
   return (size_t)kSMs * 16;
 }
 
-extern "C" int impflow_act_beta_grad(const float* x, const float* g, float* out, float* partial, long long n,
-                                     int order, const float* beta_sp, void* stream) {
+extern "C" int impflow_act_second(const float* p, const float* t, const float* ga, const float* gb, float* out,
+                                  long long n, int kind, const float* beta_sp, void* stream) {
+  if (n <= 0) return 0;
+  IMPFLOW_REQUIRE(kind != IMPFLOW_ACT_LIPSWISH || beta_sp != nullptr, "act_second: LipSwish needs beta_sp");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = grid_for(n, 256);
+  switch (kind) {
+    case IMPFLOW_ACT_SIN: k_act_second<IMPFLOW_ACT_SIN><<<grid, 256, 0, s>>>(p, t, ga, gb, out, n, beta_sp); break;
+    case IMPFLOW_ACT_LIPSWISH: k_act_second<IMPFLOW_ACT_LIPSWISH><<<grid, 256, 0, s>>>(p, t, ga, gb, out, n, beta_sp); break;
+    case IMPFLOW_ACT_RELU: k_act_second<IMPFLOW_ACT_RELU><<<grid, 256, 0, s>>>(p, t, ga, gb, out, n, beta_sp); break;
+    case IMPFLOW_ACT_NONE: k_act_second<IMPFLOW_ACT_NONE><<<grid, 256, 0, s>>>(p, t, ga, gb, out, n, beta_sp); break;
+    default: set_error("act_second: unknown activation kind %d", kind); return -3;
+  }
+  return check_launch("k_act_second");
+}
+
+extern "C" int impflow_act_beta_grad(const float* x, const float* g, const float* g2, float* out, float* partial,
+                                     long long n, int order, const float* beta_sp, void* stream) {
   IMPFLOW_REQUIRE(beta_sp != nullptr, "act_beta_grad: beta_sp is null");
   IMPFLOW_REQUIRE(order >= 0 && order <= 2, "act_beta_grad: order %d not in [0,2]", order);
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = grid_for(n, 1024);
-  k_beta_grad_stage1<<<grid, 256, 0, s>>>(x, g, partial, n, order, beta_sp);
+  k_beta_grad_stage1<<<grid, 256, 0, s>>>(x, g, g2, partial, n, order, beta_sp);
   if (check_launch("k_beta_grad_stage1")) return -1;
   k_sum_partials<<<1, 32, 0, s>>>(partial, out, grid);
   return check_launch("k_sum_partials");
@@ -366,7 +401,8 @@ extern "C" int impflow_col2im3x3(const float* col, int B, int H, int W, int C, c
   const long long total = (long long)B * H * W * C;
   if (total <= 0) return 0;
   IMPFLOW_REQUIRE(pre_out != nullptr || act_out != nullptr, "col2im3x3: no output given");
-  IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr, "col2im3x3: dmul_pre needs pre_out");
+  IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr || act_out != nullptr,
+                  "col2im3x3: dmul_pre needs pre_out or act_out");
   Epilogue ep{bias, pre_out, act_out, dmul_pre, (long long)C, act_kind, beta_sp, 0.f};
   k_col2im3x3<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(col, B, H, W, C, ep);
   return check_launch("k_col2im3x3");

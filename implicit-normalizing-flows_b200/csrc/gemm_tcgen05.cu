@@ -288,6 +288,19 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
           const bool full_vec = (n0 + 32 <= N) && ((e.ldc & 3) == 0);
           float v[32];
           if (e.dmul_pre != nullptr) {
+            if (e.act_out != nullptr) {      // dmul mode: act_out receives the raw accumulator
+              if (full_vec) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(e.act_out + row + n0 + j) =
+                      make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                  __uint_as_float(r[j + 3]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < N) e.act_out[row + n0 + j] = __uint_as_float(r[j]);
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float p[4];
@@ -484,7 +497,8 @@ extern "C" int impflow_gemm_nt(const float* A, long long lda, const float* Bm, l
                                int N, int K, int act_kind, const float* beta_sp, void* stream) {
   IMPFLOW_REQUIRE(M >= 1 && N >= 1 && K >= 1, "gemm_nt: empty problem M=%lld N=%d K=%d", M, N, K);
   IMPFLOW_REQUIRE(pre_out != nullptr || act_out != nullptr, "gemm_nt: no output given");
-  IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr, "gemm_nt: dmul_pre needs pre_out");
+  IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr || act_out != nullptr,
+                  "gemm_nt: dmul_pre needs pre_out or act_out");
   Epilogue ep{bias, pre_out, act_out, dmul_pre, ldc, act_kind, beta_sp, 0.f};
   return gemm_nt_simt(A, lda, Bm, ldb, M, N, K, ep, (cudaStream_t)stream);
 }
@@ -503,8 +517,8 @@ extern "C" int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long lon
                                   const float* beta_sp, float* splitk_ws, void* stream) {
   IMPFLOW_REQUIRE(M >= 1 && N >= 1 && K >= 1, "gemm_nt_tc: empty problem M=%lld N=%d K=%d", M, N, K);
   IMPFLOW_REQUIRE(pre_out != nullptr || act_out != nullptr || split_hi != nullptr, "gemm_nt_tc: no output given");
-  IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr || split_hi != nullptr,
-                  "gemm_nt_tc: dmul_pre needs pre_out or split planes");
+  IMPFLOW_REQUIRE(dmul_pre == nullptr || pre_out != nullptr || split_hi != nullptr || act_out != nullptr,
+                  "gemm_nt_tc: dmul_pre needs pre_out, act_out or split planes");
   IMPFLOW_REQUIRE((split_hi == nullptr) == (split_lo == nullptr), "gemm_nt_tc: split planes come in pairs");
   if (K % TC_BK != 0 || (lda % 4) != 0 || (ldb % 4) != 0) {
     set_error("gemm_nt_tc: needs K %% 32 == 0 and 16-byte aligned rows (K=%d lda=%lld ldb=%lld)", K, lda, ldb);

@@ -55,6 +55,33 @@ def branch_eval(nnet, x):
     return prog.forward(x) if prog is not None else nnet(x)
 
 
+class _BranchApply(Function):
+    """y = nnet(x) evaluated and differentiated (first order) by the graph-free branch program:
+    one fused forward, one fused backward sweep with the weight gradients (implicit_block.py:227)."""
+
+    @staticmethod
+    def forward(ctx, x, prog, *params):
+        y, saved = prog.forward_saved(x.detach())
+        ctx.prog, ctx.saved_state = prog, saved
+        ctx.need_x = x.requires_grad
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        gx, pgrads = ctx.prog.backward_full(ctx.saved_state, gout, need_input_grad=ctx.need_x)
+        ctx.saved_state = None
+        return (gx, None) + tuple(pgrads)
+
+
+def branch_apply(nnet, x):
+    """nnet(x) with gradients to the branch parameters; fused when the branch is compilable."""
+    prog = _program(nnet)
+    if prog is None or not torch.is_grad_enabled():
+        return nnet(x) if prog is None else prog.forward(x)
+    return _BranchApply.apply(x, prog, *prog.params)
+
+
 _pinned = {}
 
 
@@ -230,7 +257,7 @@ class imBlock(nn.Module):
         z = RootFind.apply(self.nnet_z, self.nnet_x, z0, z0, 'broyden', self.eps_forward, self.threshold)
         self.solver_stats['fwd'] = RootFind.last_info
         # re-attach: gradients reach the branch parameters through this expression (:227)
-        z = RootFind.f(self.nnet_z, self.nnet_x, z.detach(), z0) + z0
+        z = branch_apply(self.nnet_x, z0) - branch_apply(self.nnet_z, z.detach()) + z0
         self.nnet_x_copy.load_state_dict(self.nnet_x.state_dict())
         self.nnet_z_copy.load_state_dict(self.nnet_z.state_dict())
         if FUSED['on']:      # the frozen twins hold the same weights: share the live nets' programs

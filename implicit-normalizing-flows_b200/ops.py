@@ -89,13 +89,30 @@ def act_mul(x, g, kind, order, beta_sp=None, out=None):
     return out
 
 
-def act_beta_grad(x, g, order, beta_sp):
+def act_beta_grad(x, g, order, beta_sp, g2=None):
+    """sum(g * g2 * d/dbeta act^(order)(x)) as a 1-element tensor."""
     x = _dense(x)
     g = _match_layout(g, x)
+    if g2 is not None:
+        g2 = _match_layout(g2, x)
     out = torch.empty(1, device=x.device, dtype=torch.float32)
     ws = torch.empty(int(_lib().impflow_reduce_workspace_floats(x.numel())), device=x.device, dtype=torch.float32)
-    _cabi.check(_lib().impflow_act_beta_grad(_cabi.ptr(x), _cabi.ptr(g), _cabi.ptr(out), _cabi.ptr(ws), x.numel(),
-                                             order, _cabi.ptr(beta_sp), _cabi.stream()), 'act_beta_grad')
+    _cabi.check(_lib().impflow_act_beta_grad(_cabi.ptr(x), _cabi.ptr(g), _cabi.ptr(g2, 'g2', True), _cabi.ptr(out),
+                                             _cabi.ptr(ws), x.numel(), order, _cabi.ptr(beta_sp), _cabi.stream()),
+                'act_beta_grad')
+    return out
+
+
+def act_second(p, t, ga, gb, kind, beta_sp=None):
+    """act''(p) * t * ga + act'(p) * gb  (gb optional)."""
+    p = _dense(p)
+    t, ga = _match_layout(t, p), _match_layout(ga, p)
+    if gb is not None:
+        gb = _match_layout(gb, p)
+    out = torch.empty_like(p)
+    _cabi.check(_lib().impflow_act_second(_cabi.ptr(p), _cabi.ptr(t), _cabi.ptr(ga), _cabi.ptr(gb, 'gb', True),
+                                          _cabi.ptr(out), p.numel(), kind, _cabi.ptr(beta_sp, 'beta', True),
+                                          _cabi.stream()), 'act_second')
     return out
 
 

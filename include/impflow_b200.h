@@ -93,11 +93,15 @@ int impflow_broyden_step(float* x_old, const float* g_old, const float* xn, cons
  * scalar softplus(beta) for LipSwish (NULL otherwise) — a pointer so that no host sync is needed.  Replaces activations.py:11-12,70-71 and their autograd derivatives. */
 int impflow_act_mul(const float* x, const float* g, float* out, long long n, int kind, int order,
                     const float* beta_sp, void* stream);
-/* out[0] = sum_i g[i] * d/d(beta_sp) act^(order)(x[i])  (order 0..2); deterministic 2-stage
- * reduce; `partial` needs impflow_reduce_workspace_floats(n) floats. */
+/* out[0] = sum_i g[i] * g2[i] * d/d(beta_sp) act^(order)(x[i])  (order 0..2; g2 may be NULL);
+ * deterministic 2-stage reduce; `partial` needs impflow_reduce_workspace_floats(n) floats. */
 size_t impflow_reduce_workspace_floats(long long n);
-int impflow_act_beta_grad(const float* x, const float* g, float* out, float* partial, long long n,
-                          int order, const float* beta_sp, void* stream);
+int impflow_act_beta_grad(const float* x, const float* g, const float* g2, float* out, float* partial,
+                          long long n, int order, const float* beta_sp, void* stream);
+/* out = act''(p) * t * ga + act'(p) * gb (gb may be NULL): the activation step of the hand-derived
+ * reverse pass of the Neumann gradient estimator (implicit_block.py:386-388, 429-438). */
+int impflow_act_second(const float* p, const float* t, const float* ga, const float* gb, float* out,
+                       long long n, int kind, const float* beta_sp, void* stream);
 /* out = a*ca + b*cb + c*cc (b, c may be NULL). Solver residuals x_embed - f(z) - z
  * (implicit_block.py:72) and v J + v - grad (:199-203); Neumann accumulation (:435). */
 int impflow_lincomb3(const float* a, float ca, const float* b, float cb, const float* c, float cc,
@@ -126,7 +130,8 @@ int impflow_col2im3x3(const float* col, int B, int H, int W, int C, const float*
  * Epilogue (all optional, NULL = off):
  *   pre_out  <- acc + bias                       (pre-activation, kept for the vjp)
  *   act_out  <- act(acc + bias)                  (input of the next layer)
- *   dmul_pre : if set, pre_out <- acc * act'(dmul_pre[m,n])   (vjp through the activation)
+ *   dmul_pre : if set, pre_out <- acc * act'(dmul_pre[m,n])   (vjp / tangent through the activation)
+ *              and act_out (if given) <- acc, the raw product
  * impflow_gemm_nt     : exact-fp32 CUDA-core tiles (any M,N,K; small MLP shapes, cross-check).
  * impflow_gemm_nt_tc  : tcgen05 3xTF32 (TMA-fed, TMEM accumulators).  Operands come as tf32 hi/lo
  *                       planes (a = hi + lo, see impflow_split_tf32); needs K % 32 == 0 and rows that

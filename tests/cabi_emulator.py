@@ -77,6 +77,8 @@ def _epilogue(acc, bias, pre_out, act_out, dmul_pre, act_kind, beta, split_hi=No
         nxt = (acc * _act(act_kind, dmul_pre.reshape(acc.shape), 1, beta)).astype(np.float32)
         if pre_out is not None:
             pre_out[:] = nxt.ravel()
+        if act_out is not None:
+            act_out[:] = acc.astype(np.float32).ravel()
     else:
         v = acc + (bias[None, :] if bias is not None else 0)
         v = v.astype(np.float32)
@@ -235,10 +237,23 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
-    def impflow_act_beta_grad(self, x, g, out, partial, n, order, beta_sp, stream):
+    def impflow_act_beta_grad(self, x, g, g2, out, partial, n, order, beta_sp, stream):
         xv, gv = _f32(x, n).astype(np.float64), _f32(g, n).astype(np.float64)
+        if _addr(g2) is not None:
+            gv = gv * _f32(g2, n).astype(np.float64)
         _f32(out, 1)[0] = np.float32((gv * _dbeta(xv, order, float(_beta(beta_sp)))).sum())
         self.launches += 2
+        return 0
+
+    def impflow_act_second(self, p, t, ga, gb, out, n, kind, beta_sp, stream):
+        pv = _f32(p, n)
+        beta = _beta(beta_sp)
+        with np.errstate(all='ignore'):
+            r = _act(kind, pv, 2, beta) * _f32(t, n) * _f32(ga, n)
+            if _addr(gb) is not None:
+                r = r + _act(kind, pv, 1, beta) * _f32(gb, n)
+        _f32(out, n)[:] = r
+        self.launches += 1
         return 0
 
     def impflow_lincomb3(self, a, ca, b, cb, c, cc, out, n, stream):
