@@ -409,10 +409,24 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
     @staticmethod
     def forward(ctx, estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training, *g_params):
         ctx.training = training
+        prog = _program(gnet)
+        if training and prog is not None and estimator_fn is neumann_logdet_estimator:
+            # graph-free: fused forward, n fused vjps, then the hand-derived tangent / reverse sweeps
+            with torch.no_grad():
+                xd = x.detach()
+                _, saved = prog.forward_saved(xd)
+                vjp = neumann_vjp = vareps
+                for k in range(1, n_power_series + 1):
+                    vjp = prog.vjp(vjp, saved)
+                    neumann_vjp = ops.lincomb3(neumann_vjp, 1.0, vjp, float((-1) ** k * coeff_fn(k)))
+                logdetgrad, grad_x, grad_params = prog.neumann(saved, neumann_vjp, vareps)
+            ctx.none_mask = [gp is None for gp in grad_params]
+            ctx.save_for_backward(grad_x, *[gp if gp is not None else xd.new_zeros(()) for gp in grad_params])
+            return logdetgrad
         with torch.enable_grad():
             x = x.detach().requires_grad_(True)
             g = gnet(x)
-            logdetgrad = estimator_fn(g, x, n_power_series, vareps, coeff_fn, training)
+            logdetgrad = estimator_fn(g, x, n_power_series, vareps, coeff_fn, training, prog)
             if training:
                 grad_x, *grad_params = torch.autograd.grad(logdetgrad.sum(), (x,) + g_params, retain_graph=False,
                                                            allow_unused=True)

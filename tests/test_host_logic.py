@@ -261,3 +261,41 @@ def test_branch_program_gradients_match_autograd(name, backend):
                 assert rel_err(g, r) < 5e-5, tuple(p.shape)
     finally:
         impflow_b200.ops.set_gemm_backend('auto')
+
+
+def test_fused_paths_are_taken(golden, monkeypatch):
+    """Guards against silently falling back to the module/autograd path: one CIFAR-style training
+    forward+backward must run the Neumann gradient, the attach backward and all vjps on the
+    graph-free branch programs and never build an autograd graph through the branch."""
+    import impflow_b200
+    from impflow_b200 import branch_program as bp
+    from impflow_b200.layers import implicit_block as ib
+    counts = {'neumann': 0, 'backward_full': 0, 'vjp': 0, 'autograd_estimator': 0, 'module_calls': 0}
+
+    def wrap(cls, name, key):
+        orig = getattr(cls, name)
+
+        def f(self, *a, **k):
+            counts[key] += 1
+            return orig(self, *a, **k)
+        monkeypatch.setattr(cls, name, f)
+    wrap(bp.BranchProgram, 'neumann', 'neumann')
+    wrap(bp.BranchProgram, 'backward_full', 'backward_full')
+    wrap(bp.BranchProgram, 'vjp', 'vjp')
+    orig_est = ib.neumann_logdet_estimator
+    monkeypatch.setattr(ib, 'neumann_logdet_estimator',
+                        lambda *a, **k: (counts.__setitem__('autograd_estimator', counts['autograd_estimator'] + 1),
+                                         orig_est(*a, **k))[1])
+    fx = golden('imblock_conv')
+    layers = impflow_b200.layers
+    blk = layers.imBlock(cases.build_conv_branch(layers, 4, 32, 0.9, 1e-3, True),
+                         cases.build_conv_branch(layers, 4, 32, 0.9, 1e-3, True), **cases.CONV['cifar']['kw'])
+    blk = cases.load_block(blk, fx, 'cifar', torch.from_numpy(fx['cifar_x']))
+    hook = lambda m, i: counts.__setitem__('module_calls', counts['module_calls'] + 1)
+    hs = [blk.nnet_x.register_forward_pre_hook(hook), blk.nnet_z.register_forward_pre_hook(hook)]
+    cases.run_train(blk, fx, 'cifar')
+    for h in hs:
+        h.remove()
+    assert counts['neumann'] == 2 and counts['backward_full'] == 2
+    assert counts['autograd_estimator'] == 0 and counts['module_calls'] == 0
+    assert counts['vjp'] > 2 * 3
