@@ -210,7 +210,7 @@ def main():
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (weak scaling)')
     ap.add_argument('--cpu-batch', type=int, default=4, help='images per CPU-baseline step (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--probe-mode', default='reference', choices=['reference', 'device'])
+    ap.add_argument('--probe-mode', default='device', choices=['reference', 'device'])
     ap.add_argument('--unfused', action='store_true', help='disable the graph-free branch programs (A/B)')
     args = ap.parse_args()
 

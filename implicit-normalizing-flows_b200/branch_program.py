@@ -170,7 +170,7 @@ class BranchProgram(object):
                     act.refresh()
             for act, m in self.stages:
                 w = _Weights()
-                if isinstance(m, InducedNormConv2d) and not m.initialized and meta is not None:
+                if isinstance(m, InducedNormConv2d) and not m.is_initialized() and meta is not None:
                     # first use: record the spatial dims like InducedNormConv2d.forward does
                     m.spatial_dims.copy_(torch.tensor([float(meta[1][1]), float(meta[1][2])]).to(m.spatial_dims))
                     m._hw = None

@@ -186,6 +186,7 @@ class InducedNormConv2d(nn.Module):
         self.register_buffer('u', self.weight.new_empty(self.out_channels))
         self.register_buffer('v', self.weight.new_empty(self.in_channels))
         self._hw = None
+        self._init_known = None     # python mirror of the `initialized` buffer (reading it syncs the stream)
 
     def compute_domain_codomain(self):
         return self.domain, self.codomain
@@ -198,6 +199,12 @@ class InducedNormConv2d(nn.Module):
             init.uniform_(self.bias, -bound, bound)
 
     # --- helpers -------------------------------------------------------------------------------
+    def is_initialized(self):
+        """`bool(self.initialized)` without a device->host read on every call."""
+        if self._init_known is None or not self._init_known:
+            self._init_known = bool(self.initialized)
+        return self._init_known
+
     def _spatial(self):
         if self._hw is None:
             self._hw = (int(self.spatial_dims[0].item()), int(self.spatial_dims[1].item()))
@@ -205,6 +212,7 @@ class InducedNormConv2d(nn.Module):
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._hw = None
+        self._init_known = None
         return super(InducedNormConv2d, self)._load_from_state_dict(*args, **kwargs)
 
     def _conv_vec(self, vec_chw, weight, transpose=False):
@@ -235,12 +243,13 @@ class InducedNormConv2d(nn.Module):
                 self.u.resize_(self.out_channels * h * w).normal_(0, 1)
                 self.u.copy_(F.normalize(self.u, dim=0))
             self.initialized.fill_(1)
+            self._init_known = True
             self.compute_weight(True)
             self.u = self.u.clone(memory_format=torch.contiguous_format)
             self.v = self.v.clone(memory_format=torch.contiguous_format)
 
     def compute_one_iter(self):
-        if not self.initialized:
+        if not self.is_initialized():
             raise ValueError('Layer needs to be initialized first.')
         _require_cuda(self.weight, 'InducedNormConv2d.weight')
         if self.kernel_size == (1, 1):
@@ -255,7 +264,7 @@ class InducedNormConv2d(nn.Module):
 
     def compute_weight(self, update=True, n_iterations=None, atol=None, rtol=None):
         _require_cuda(self.weight, 'InducedNormConv2d.weight')
-        if not self.initialized:
+        if not self.is_initialized():
             self._initialize_u_v()
         n_iterations = self.n_iterations if n_iterations is None else n_iterations
         atol = self.atol if atol is None else atol
@@ -304,7 +313,7 @@ class InducedNormConv2d(nn.Module):
 
     def forward(self, input):
         _require_cuda(input, 'InducedNormConv2d input')
-        if not self.initialized:
+        if not self.is_initialized():
             self.spatial_dims.copy_(torch.tensor(input.shape[2:4]).to(self.spatial_dims))
             self._hw = None
         weight = self.compute_weight(update=False)

@@ -21,13 +21,20 @@ class ActNormNd(nn.Module):
         self.weight = Parameter(torch.Tensor(num_features))
         self.bias = Parameter(torch.Tensor(num_features))
         self.register_buffer('initialized', torch.tensor(0))
+        self._init_known = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._init_known = None
+        return super(ActNormNd, self)._load_from_state_dict(*args, **kwargs)
 
     @property
     def shape(self):
         raise NotImplementedError
 
     def _maybe_init(self, x):
-        if self.initialized:
+        if self._init_known is None or not self._init_known:
+            self._init_known = bool(self.initialized)     # one device read until initialised
+        if self._init_known:
             return
         with torch.no_grad():      # data-dependent init (act_norm.py:25-37)
             c = x.size(1)
@@ -37,6 +44,7 @@ class ActNormNd(nn.Module):
             self.bias.data.copy_(-batch_mean)
             self.weight.data.copy_(-0.5 * torch.log(batch_var))
             self.initialized.fill_(1)
+            self._init_known = True
 
     def forward(self, x, logpx=None, restore=None):
         self._maybe_init(x)
@@ -46,7 +54,6 @@ class ActNormNd(nn.Module):
         return y, logpx - self._logdetgrad(x)
 
     def inverse(self, y, logpy=None):
-        assert self.initialized
         x = y * torch.exp(-self.weight.view(*self.shape)) - self.bias.view(*self.shape)
         if logpy is None:
             return x
