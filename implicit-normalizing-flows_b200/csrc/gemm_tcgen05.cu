@@ -115,7 +115,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = (BN >= 128) ? 3 : 4;
+  static constexpr int kStages = (BN >= 256) ? 2 : (BN >= 128) ? 3 : 4;
   static constexpr int kABytes = TC_BM * TC_BK * 4;  // 16 KB per plane
   static constexpr int kBBytes = BN * TC_BK * 4;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
@@ -503,7 +503,14 @@ extern "C" int impflow_gemm_nt(const float* A, long long lda, const float* Bm, l
   return gemm_nt_simt(A, lda, Bm, ldb, M, N, K, ep, (cudaStream_t)stream);
 }
 
-static int tc_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
+static int g_wide_tiles = 1;   // BN = 256 tiles for N >= 256 (halves the A-operand re-reads through L2)
+static int tc_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : ((N >= 256 && g_wide_tiles) ? 256 : 128)); }
+
+extern "C" int impflow_gemm_tc_set_wide_tiles(int on) {
+  const int prev = g_wide_tiles;
+  g_wide_tiles = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" int impflow_gemm_tc_splits(long long M, int N, int K) {
   if (K % TC_BK != 0) return 1;
@@ -536,7 +543,9 @@ extern "C" int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long lon
   int splits = 1;
   if (splitk_ws != nullptr && act_out == nullptr && dmul_pre == nullptr && split_hi == nullptr && pre_out != nullptr)
     splits = pick_splits(M, N, K, tc_bn(N));
-  if (N <= 32) return launch_tc<32>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
-  if (N <= 64) return launch_tc<64>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
+  const int bn = tc_bn(N);
+  if (bn == 32) return launch_tc<32>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
+  if (bn == 64) return launch_tc<64>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
+  if (bn == 256) return launch_tc<256>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
   return launch_tc<128>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
 }

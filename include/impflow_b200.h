@@ -150,6 +150,9 @@ int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long long lda, cons
  * epilogue (pre_out (+bias) only) and a workspace of impflow_gemm_tc_splits(M,N,K) * M * N floats the
  * kernel writes per-slice partials and a fixed-order reduce finishes; splitk_ws = NULL disables it. */
 int impflow_gemm_tc_splits(long long M, int N, int K);
+/* Tile-shape switch for A/B measurements: 1 (default) = 128x256 tiles when N >= 256, 0 = 128x128.
+ * Returns the previous setting. */
+int impflow_gemm_tc_set_wide_tiles(int on);
 /* a -> tf32 "hi" (round-to-nearest) and "lo" = a - hi planes used by the 3xTF32 backend. */
 int impflow_split_tf32(const float* a, float* hi, float* lo, long long n, void* stream);
 

@@ -279,6 +279,9 @@ class EmulatedLib(object):
     def impflow_gemm_tc_splits(self, M, N, K):
         return 1
 
+    def impflow_gemm_tc_set_wide_tiles(self, on):
+        return 1
+
     def impflow_colsum(self, a, out, partial, M, N, stream):
         _f32(out, N)[:] = _f32(a, M * N).reshape(M, N).sum(0)
         self.launches += 1
