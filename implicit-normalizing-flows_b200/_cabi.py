@@ -25,6 +25,9 @@ SIGNATURES = {
     'impflow_broyden_workspace_floats': (ctypes.c_size_t, [_i, _ll, _i]),
     'impflow_broyden_begin': (_i, [_c_fp] * 9 + [_i, _ll, _i, _d, _c_fp]),
     'impflow_broyden_step': (_i, [_c_fp] * 12 + [_i, _ll, _i, _c_fp]),
+    'impflow_mlp_solver_limits': (_i, [_c_fp, _c_fp, _c_fp]),
+    'impflow_mlp_solver_partial_doubles': (ctypes.c_size_t, []),
+    'impflow_mlp_broyden_solve': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _i, _i, _c_fp] + [_c_fp] * 12 + [_i, _i, _d, _c_fp]),
     'impflow_act_mul': (_i, [_c_fp, _c_fp, _c_fp, _ll, _i, _i, _c_fp, _c_fp]),
     'impflow_reduce_workspace_floats': (ctypes.c_size_t, [_ll]),
     'impflow_act_beta_grad': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _i, _c_fp, _c_fp]),

@@ -210,6 +210,28 @@ class BranchProgram(object):
             return Wp, Kp, ops.split_tf32(Wp)
         return Wm.contiguous(), K, None
 
+    def mlp_solver_spec(self, x):
+        """Arguments of the persistent small-d solver (csrc/mlp_solver.cu) or None if this branch does not
+        qualify: plain Linear/act/.../Linear MLP, one activation kind, d <= 128, widths <= 256."""
+        if not self.is_linear or self.post_act is not None or self.stages[0][0] is not None:
+            return None
+        kinds = {a.kind for a, _ in self.stages[1:]}
+        if len(kinds) > 1 or any(a is None for a, _ in self.stages[1:]):
+            return None
+        rows, meta = self._to_rows(x)
+        ws = self._prep(rows.shape[0], meta)
+        dims = [ws[0].cin] + [w.cout for w in ws]
+        if dims[0] != dims[-1] or dims[0] > 128 or max(dims) > 256 or len(ws) > 8:
+            return None
+        key = ('mlp', self._key)
+        cached = getattr(self, '_mlp_spec', None)
+        if cached is None or cached[0] != key:
+            Wt = [w.fwd[:, :w.cin].t().contiguous() for w in ws]
+            cached = self._mlp_spec = (key, Wt)
+        act = self.stages[1][0] if len(self.stages) > 1 else None
+        return (cached[1], [w.bias for w in ws], dims, act.kind if act is not None else ops.ACT_NONE,
+                act.beta_sp() if act is not None else None)
+
     # ---------------------------------------------------------------- plumbing
     def _to_rows(self, x):
         """Module-level tensor -> (rows matrix, meta)."""
@@ -247,18 +269,14 @@ class BranchProgram(object):
                 A_split = ops.split_tf32(A)
             sh = torch.empty(M, N, device=dev, dtype=torch.float32) if want_split else None
             sl = torch.empty(M, N, device=dev, dtype=torch.float32) if want_split else None
-            if ops.GEMM_PROFILE['on']:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e0.record()
             _cabi.check(lib.impflow_gemm_nt_tc(
                 _cabi.ptr(A_split[0]), _cabi.ptr(A_split[1]), Wk, _cabi.ptr(W_split[0]), _cabi.ptr(W_split[1]), Wk,
                 _cabi.ptr(bias, 'bias', True), _cabi.ptr(pre, 'pre', True), _cabi.ptr(out_act, 'act', True),
                 _cabi.ptr(dmul_pre, 'dmul', True), _cabi.ptr(sh, 'sh', True), _cabi.ptr(sl, 'sl', True), N, M, N, Wk,
                 kind, _cabi.ptr(beta, 'beta', True), None, _cabi.stream()), 'gemm_nt_tc')
             if ops.GEMM_PROFILE['on']:
-                e1 = torch.cuda.Event(enable_timing=True)
-                e1.record()
-                ops.GEMM_PROFILE['events'].append((e0, e1, 2.0 * M * N * Wk))
+                ops.record_gemm(M, N, Wk, pre is not None, out_act is not None, dmul_pre is not None, want_split,
+                                False)
             return pre, out_act, ((sh, sl) if want_split else None)
         if A is None:
             A = ops.lincomb3(A_split[0], 1.0, A_split[1], 1.0)

@@ -1,0 +1,368 @@
+// Persistent Broyden root solver for small-d MLP branches (toy d=2, tabular d=6/43/63, hidden 128):
+// ONE cooperative launch performs the whole solve of
+//        g(z) = x_embed - f(z) - z = 0          (implicit_block.py:68-80, broyden.py:123-193)
+// including every branch evaluation f(z) (fused fp32 MLP with the activation in registers), the
+// batch-global residual norm (one grid.sync per iteration), the reference's break rules and
+// best-iterate tracking, and the per-sample rank-1 updates (one warp per sample, history U^T/V^T in
+// global memory that stays L2-resident: B*T*d*8 bytes = 15 MB at B=1000, d=63, T=30).
+// The host reads back the 600-byte state once, after the solve — the reference synchronises the host
+// on every iteration (broyden.py:145,157).
+//
+// Work split: a CTA owns tiles of kTile samples.  The MLP is evaluated per tile with activations in
+// shared memory and weights (stored transposed, [in][out], so a warp reads consecutive neurons)
+// streamed through L1/L2; each thread accumulates 4 samples x 1 neuron.  The decision logic is
+// replicated in every CTA from the same partial sums in the same order, so all CTAs take identical
+// branches without a second grid barrier.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace impflow {
+
+constexpr int kMlpThreads = 256;
+constexpr int kMlpWarps = kMlpThreads / 32;
+constexpr int kTile = 16;        // samples per tile
+constexpr int kMaxLayers = 8;
+constexpr int kMaxWidth = 256;   // widest layer (incl. d)
+
+struct MlpDesc {
+  int L;                       // number of linear layers
+  int dims[kMaxLayers + 1];    // dims[0] = d, ..., dims[L] = d
+  const float* Wt[kMaxLayers]; // [in][out]
+  const float* bias[kMaxLayers];
+  int act_kind;
+  const float* beta;
+};
+
+// out[s][n] = act?( bias[n] + sum_k in[s][k] * Wt[k][n] ) for the kTile samples of one tile.
+__device__ void mlp_layer(const float* __restrict__ Wt, const float* __restrict__ bias, const float* in, float* out,
+                          int K, int N, int act_kind, float beta, bool apply_act) {
+  // thread -> (neuron n, group of 4 samples)
+  for (int idx = threadIdx.x; idx < N * (kTile / 4); idx += kMlpThreads) {
+    const int n = idx % N;
+    const int sg = idx / N;
+    float acc[4];
+    const float b = bias != nullptr ? __ldg(bias + n) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = b;
+    const float* i0 = in + (sg * 4 + 0) * kMaxWidth;
+    int k = 0;
+    for (; k + 3 < K; k += 4) {
+      const float w0 = __ldg(Wt + (long long)(k + 0) * N + n);
+      const float w1 = __ldg(Wt + (long long)(k + 1) * N + n);
+      const float w2 = __ldg(Wt + (long long)(k + 2) * N + n);
+      const float w3 = __ldg(Wt + (long long)(k + 3) * N + n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 h = *reinterpret_cast<const float4*>(i0 + j * kMaxWidth + k);
+        acc[j] = fmaf(h.x, w0, acc[j]);
+        acc[j] = fmaf(h.y, w1, acc[j]);
+        acc[j] = fmaf(h.z, w2, acc[j]);
+        acc[j] = fmaf(h.w, w3, acc[j]);
+      }
+    }
+    for (; k < K; ++k) {
+      const float w0 = __ldg(Wt + (long long)k * N + n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(i0[j * kMaxWidth + k], w0, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      out[(sg * 4 + j) * kMaxWidth + n] = apply_act ? act_dispatch(act_kind, acc[j], 0, beta) : acc[j];
+  }
+}
+
+// f(zin) for the tile's samples; result left in the returned smem buffer ([kTile][kMaxWidth], first d cols).
+__device__ float* mlp_eval(const MlpDesc& net, const float* __restrict__ zin, int s0, int B, float* bufA, float* bufB,
+                           float beta) {
+  const int d = net.dims[0];
+  for (int i = threadIdx.x; i < kTile * d; i += kMlpThreads) {
+    const int s = i / d, c = i % d;
+    bufA[s * kMaxWidth + c] = (s0 + s < B) ? zin[(long long)(s0 + s) * d + c] : 0.f;
+  }
+  __syncthreads();
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int l = 0; l < net.L; ++l) {
+    mlp_layer(net.Wt[l], net.bias[l], cur, nxt, net.dims[l], net.dims[l + 1], net.act_kind, beta, l + 1 < net.L);
+    __syncthreads();
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  return cur;
+}
+
+struct LocalState {   // replica of impflow_broyden_state kept in shared memory by every CTA
+  int nstep, lowest_step, active, prot_break, converged, stagnated, do_update, new_lowest, threshold;
+  double eps, init_objective, lowest, objective;
+  double trace[64];
+};
+
+__device__ void local_decide(LocalState* st, double total, bool init) {
+  const double obj = (double)(float)sqrt(total);
+  st->objective = obj;
+  if (init) {
+    st->nstep = 0; st->lowest_step = 0; st->init_objective = obj; st->lowest = obj; st->trace[0] = obj;
+    st->prot_break = st->converged = st->stagnated = st->do_update = st->new_lowest = 0;
+    st->active = (obj >= st->eps && 0 < st->threshold) ? 1 : 0;
+    return;
+  }
+  const int T = st->threshold;
+  const int nstep = ++st->nstep;
+  st->trace[nstep] = obj;
+  int new_low = 0;
+  if (obj < st->lowest) { st->lowest = obj; st->lowest_step = nstep; new_low = 1; }
+  st->new_lowest = new_low;
+  const int conv = obj < st->eps ? 1 : 0;
+  int stag = 0;
+  if (!conv && obj < 3.0 * st->eps && nstep == T) {
+    double mx = st->trace[nstep - T + 1], mn = mx;
+    for (int i = nstep - T + 1; i <= nstep; ++i) { mx = fmax(mx, st->trace[i]); mn = fmin(mn, st->trace[i]); }
+    stag = (mx / mn < 1.3) ? 1 : 0;
+  }
+  const int prot = (!conv && !stag && obj > st->init_objective * 1e6) ? 1 : 0;
+  st->converged = conv; st->stagnated = stag; st->prot_break = prot;
+  const int upd = (conv || stag || prot) ? 0 : 1;
+  st->do_update = upd;
+  st->active = (upd && obj >= st->eps && nstep < T) ? 1 : 0;
+}
+
+// rank-1 update of one sample by one warp (d <= 128), same algebra as k_update_small (broyden.cu).
+__device__ void warp_update(float* x_old, const float* g_old, const float* xn, const float* gn, float* Ut, float* Vt,
+                            int d, int T, int k, int lane) {
+  float dx[4], dg[4], gg[4], xv[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = lane + 32 * e;
+    if (i < d) {
+      xv[e] = xn[i]; gg[e] = gn[i]; dx[e] = xv[e] - x_old[i]; dg[e] = gg[e] - g_old[i];
+    } else {
+      xv[e] = gg[e] = dx[e] = dg[e] = 0.f;
+    }
+  }
+  float vT[4], w[4], S[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { vT[e] = -dx[e]; w[e] = -dg[e]; S[e] = 0.f; }
+  for (int j = 0; j < k; ++j) {
+    float u1[4], v1[4], a = 0.f, bb = 0.f, c = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = lane + 32 * e;
+      u1[e] = i < d ? Ut[(long long)j * d + i] : 0.f;
+      v1[e] = i < d ? Vt[(long long)j * d + i] : 0.f;
+      a += dx[e] * u1[e]; bb += v1[e] * dg[e]; c += v1[e] * gg[e];
+    }
+    a = warp_sum(a); bb = warp_sum(bb); c = warp_sum(c);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { vT[e] += a * v1[e]; w[e] += bb * u1[e]; S[e] += c * u1[e]; }
+  }
+  float den = 0.f, ck = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    den += vT[e] * dg[e];
+    vT[e] = (vT[e] != vT[e]) ? 0.f : vT[e];
+    ck += vT[e] * gg[e];
+  }
+  den = warp_sum(den);
+  ck = warp_sum(ck);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = lane + 32 * e;
+    if (i < d) {
+      float u = (dx[e] - w[e]) / den;
+      u = (u != u) ? 0.f : u;
+      Ut[(long long)k * d + i] = u;
+      Vt[(long long)k * d + i] = vT[e];
+      x_old[i] = xv[e] + (-((-gg[e]) + (S[e] + u * ck)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMlpThreads)
+k_mlp_broyden(MlpDesc net, const float* __restrict__ x_embed, float* za, float* ga, float* zb, float* gb,
+              float* __restrict__ low_z, float* __restrict__ low_g, float* __restrict__ Ut, float* __restrict__ Vt,
+              float* __restrict__ sample_sq, float* __restrict__ low_sq, double* __restrict__ partial,
+              impflow_broyden_state* state, int B, int T, double eps) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ __align__(16) float bufA[kTile * kMaxWidth];
+  __shared__ __align__(16) float bufB[kTile * kMaxWidth];
+  __shared__ LocalState st;
+  __shared__ double red[kMlpWarps];
+  __shared__ float tile_sq[kTile];
+  const int d = net.dims[0];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float beta = net.beta != nullptr ? __ldg(net.beta) : 0.f;
+  const int n_tiles = (B + kTile - 1) / kTile;
+  float *z_old = za, *g_old = ga, *zn = zb, *gn = gb;
+
+  if (tid == 0) { st.threshold = T; st.eps = eps; }
+
+  // evaluates g(zin) -> gout for this CTA's tiles, per-sample ||g||^2 -> sample_sq, returns the CTA partial
+  auto eval_residual = [&](const float* zin, float* gout) -> double {
+    double cta_sum = 0.0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int s0 = tile * kTile;
+      float* f = mlp_eval(net, zin, s0, B, bufA, bufB, beta);
+      if (tid < kTile) tile_sq[tid] = 0.f;
+      __syncthreads();
+      // g = x_embed - f(z) - z, one warp handles samples warp, warp+8
+      for (int s = warp; s < kTile; s += kMlpWarps) {
+        const int b = s0 + s;
+        if (b >= B) continue;
+        float sq = 0.f;
+        for (int c = lane; c < d; c += 32) {
+          const long long i = (long long)b * d + c;
+          const float gv = x_embed[i] - f[s * kMaxWidth + c] - zin[i];
+          gout[i] = gv;
+          sq += gv * gv;
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) { tile_sq[s] = sq; sample_sq[b] = sq; }
+      }
+      __syncthreads();
+      if (tid == 0)
+        for (int s = 0; s < kTile; ++s) cta_sum += (double)tile_sq[s];
+      __syncthreads();
+    }
+    return cta_sum;
+  };
+  // all CTAs: identical fixed-order sum of the per-CTA partials of parity `p`
+  auto total_of = [&](int p) -> double {
+    double acc = 0.0;
+    for (int i = tid; i < (int)gridDim.x; i += kMlpThreads) acc += partial[p * gridDim.x + i];
+    acc = warp_sum_d(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < kMlpWarps; ++w) t += red[w];
+    __syncthreads();
+    return t;
+  };
+
+  // ---- g0 = g(z0), init bookkeeping, zn = z0 - g0 (broyden.py:136-151) ----
+  {
+    const double s = eval_residual(z_old, g_old);
+    if (tid == 0) partial[blockIdx.x] = s;
+  }
+  grid.sync();
+  {
+    const double tot = total_of(0);
+    if (tid == 0) local_decide(&st, tot, true);
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int i = tid; i < kTile * d; i += kMlpThreads) {
+        const int b = tile * kTile + i / d;
+        if (b < B) {
+          const long long idx = (long long)b * d + i % d;
+          const float x = z_old[idx], g = g_old[idx];
+          low_z[idx] = x; low_g[idx] = g; zn[idx] = x + (-g);
+          if (i % d == 0) low_sq[b] = sample_sq[b];
+        }
+      }
+    __syncthreads();
+  }
+  int parity = 1;
+  while (st.active) {
+    const double s = eval_residual(zn, gn);
+    if (tid == 0) partial[parity * gridDim.x + blockIdx.x] = s;
+    grid.sync();
+    const double tot = total_of(parity);
+    if (tid == 0) local_decide(&st, tot, false);
+    __syncthreads();
+    const int k = st.nstep - 1;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int s = warp; s < kTile; s += kMlpWarps) {
+        const int b = tile * kTile + s;
+        if (b >= B) continue;
+        const long long base = (long long)b * d;
+        if (st.new_lowest) {
+          for (int c = lane; c < d; c += 32) { low_z[base + c] = zn[base + c]; low_g[base + c] = gn[base + c]; }
+          if (lane == 0) low_sq[b] = sample_sq[b];
+        }
+        if (st.do_update)
+          warp_update(z_old + base, g_old + base, zn + base, gn + base, Ut + (long long)b * T * d,
+                      Vt + (long long)b * T * d, d, T, k, lane);
+      }
+    }
+    __syncthreads();
+    // the next iterate was written into z_old's buffer: swap roles (uniform over the grid)
+    float* t = z_old; z_old = zn; zn = t;
+    t = g_old; g_old = gn; gn = t;
+    parity ^= 1;
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    state->nstep = st.nstep; state->lowest_step = st.lowest_step; state->active = 0;
+    state->prot_break = st.prot_break; state->converged = st.converged; state->stagnated = st.stagnated;
+    state->do_update = st.do_update; state->new_lowest = st.new_lowest; state->threshold = T; state->counter = 0;
+    state->eps = st.eps; state->init_objective = st.init_objective; state->lowest = st.lowest;
+    state->objective = st.objective;
+    for (int i = 0; i <= st.nstep; ++i) state->trace[i] = st.trace[i];
+  }
+}
+
+}  // namespace impflow
+
+using namespace impflow;
+
+extern "C" int impflow_mlp_solver_limits(int* max_layers, int* max_width, int* max_d) {
+  if (max_layers) *max_layers = kMaxLayers;
+  if (max_width) *max_width = kMaxWidth;
+  if (max_d) *max_d = 128;
+  return 0;
+}
+
+extern "C" size_t impflow_mlp_solver_partial_doubles(void) { return 2 * 148 * 8; }
+
+// params: L transposed weight matrices Wt_l [dims[l]][dims[l+1]] and L bias vectors (pointers on the HOST,
+// pointing to device memory); biases may be NULL.
+extern "C" int impflow_mlp_broyden_solve(const float* x_embed, const float* const* Wt, const float* const* bias,
+                                         const int* dims, int L, int act_kind, const float* beta_sp, float* za,
+                                         float* ga, float* zb, float* gb, float* low_z, float* low_g, float* Ut,
+                                         float* Vt, float* sample_sq, float* low_sq, double* partial,
+                                         impflow_broyden_state* state, int B, int threshold, double eps_scaled,
+                                         void* stream) {
+  IMPFLOW_REQUIRE(L >= 1 && L <= kMaxLayers, "mlp_broyden_solve: %d layers not in [1,%d]", L, kMaxLayers);
+  IMPFLOW_REQUIRE(threshold >= 1 && threshold <= 63, "mlp_broyden_solve: threshold %d not in [1,63]", threshold);
+  IMPFLOW_REQUIRE(dims[0] == dims[L] && dims[0] <= 128, "mlp_broyden_solve: needs d_in == d_out <= 128");
+  IMPFLOW_REQUIRE(act_kind != IMPFLOW_ACT_LIPSWISH || beta_sp != nullptr, "mlp_broyden_solve: LipSwish needs beta");
+  MlpDesc net;
+  memset(&net, 0, sizeof(net));
+  net.L = L;
+  for (int l = 0; l <= L; ++l) {
+    IMPFLOW_REQUIRE(dims[l] >= 1 && dims[l] <= kMaxWidth, "mlp_broyden_solve: width %d not in [1,%d]", dims[l],
+                    kMaxWidth);
+    net.dims[l] = dims[l];
+  }
+  for (int l = 0; l < L; ++l) {
+    net.Wt[l] = Wt[l];
+    net.bias[l] = bias ? bias[l] : nullptr;
+  }
+  net.act_kind = act_kind;
+  net.beta = beta_sp;
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mlp_broyden, kMlpThreads, 0) != cudaSuccess ||
+      per_sm < 1) {
+    set_error("mlp_broyden_solve: occupancy query failed");
+    return -1;
+  }
+  const int n_tiles = (B + kTile - 1) / kTile;
+  int grid = sms * (per_sm > 8 ? 8 : per_sm);
+  if (grid > n_tiles) grid = n_tiles;
+  if (grid > 148 * 8) grid = 148 * 8;
+  int T = threshold;
+  double eps = eps_scaled;
+  void* args[] = {&net, &x_embed, &za, &ga, &zb, &gb, &low_z, &low_g, &Ut, &Vt, &sample_sq, &low_sq,
+                  &partial, &state, &B, &T, &eps};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)k_mlp_broyden, dim3(grid), dim3(kMlpThreads), args, 0,
+                                              (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("mlp_broyden_solve: cooperative launch failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return check_launch("k_mlp_broyden");
+}

@@ -11,7 +11,7 @@ import torch
 
 from .. import _cabi
 
-__all__ = ['broyden']
+__all__ = ['broyden', 'broyden_mlp']
 
 _STATE_DTYPE = np.dtype([('nstep', '<i4'), ('lowest_step', '<i4'), ('active', '<i4'), ('prot_break', '<i4'),
                          ('converged', '<i4'), ('stagnated', '<i4'), ('do_update', '<i4'), ('new_lowest', '<i4'),
@@ -57,6 +57,55 @@ def _workspace(B, d, T, device):
     return ws
 
 
+def _result_dict(ws, state, shape, eps_scaled, threshold):
+    """The reference's return dict (broyden.py:184-193)."""
+    nstep = int(state['nstep'])
+    return {'result': ws.low_x.clone().view(shape),
+            'nstep': nstep,
+            'tnstep': nstep,
+            'lowest_step': int(state['lowest_step']),
+            'diff': float(state['lowest']),
+            'diff_detail': torch.sqrt(ws.low_sq),
+            'prot_break': bool(state['prot_break']),
+            'trace': [float(t) for t in state['trace'][:nstep + 1]],
+            'eps': eps_scaled,
+            'threshold': threshold}
+
+
+def broyden_mlp(spec, x_embed, z0, threshold, eps):
+    """Whole forward/inverse solve of x_embed - f(z) - z = 0 in ONE persistent cooperative kernel
+    (csrc/mlp_solver.cu) for small-d MLP branches.  `spec` comes from BranchProgram.mlp_solver_spec():
+    (Wt list, bias list, dims, act_kind, beta_sp).  Same return dict as broyden()."""
+    _cabi.require_device(z0, 'broyden_mlp z0')
+    lib = _cabi.load()
+    Wt, bias, dims, act_kind, beta_sp = spec
+    shape = z0.shape
+    B = shape[0]
+    d = z0.numel() // B
+    assert d == dims[0] == dims[-1]
+    eps_scaled = eps * np.sqrt(np.prod((B, d)))
+    ws = _workspace(B, d, threshold, z0.device)
+    if not hasattr(ws, 'gb'):
+        ws.ga = torch.empty(B, d, device=z0.device, dtype=torch.float32)
+        ws.gb = torch.empty(B, d, device=z0.device, dtype=torch.float32)
+        ws.partial_d = torch.empty(int(lib.impflow_mlp_solver_partial_doubles()), device=z0.device,
+                                   dtype=torch.float64)
+    ws.xa.copy_(z0.reshape(B, d))
+    L = len(Wt)
+    wt_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in Wt])
+    b_arr = (ctypes.c_void_p * L)(*[(b.data_ptr() if b is not None else None) for b in bias])
+    dims_arr = (ctypes.c_int * (L + 1))(*dims)
+    xe = x_embed.reshape(B, d).contiguous()
+    _cabi.check(lib.impflow_mlp_broyden_solve(
+        _cabi.ptr(xe), wt_arr, b_arr, dims_arr, L, act_kind, _cabi.ptr(beta_sp, 'beta', True), _cabi.ptr(ws.xa),
+        _cabi.ptr(ws.ga), _cabi.ptr(ws.xb), _cabi.ptr(ws.gb), _cabi.ptr(ws.low_x), _cabi.ptr(ws.low_g),
+        _cabi.ptr(ws.Ut), _cabi.ptr(ws.Vt), _cabi.ptr(ws.sample_sq), _cabi.ptr(ws.low_sq),
+        ctypes.c_void_p(ws.partial_d.data_ptr()), ctypes.c_void_p(ws.state.data_ptr()), B, threshold,
+        float(eps_scaled), _cabi.stream()), 'mlp_broyden_solve')
+    state = ws.read_state()
+    return _result_dict(ws, state, shape, eps_scaled, threshold)
+
+
 def broyden(g_, x0, threshold, eps, ls=False, name='unknown'):
     """Find x with g_(x) = 0, starting at x0.  Same return dict as the reference
     (broyden.py:184-193)."""
@@ -97,14 +146,4 @@ def broyden(g_, x0, threshold, eps, ls=False, name='unknown'):
         x_old, xn = xn, x_old        # the kernel wrote the next iterate into the old buffer
         gx = gn
         state = ws.read_state()
-    nstep = int(state['nstep'])
-    return {'result': ws.low_x.clone().view(shape),
-            'nstep': nstep,
-            'tnstep': nstep,
-            'lowest_step': int(state['lowest_step']),
-            'diff': float(state['lowest']),
-            'diff_detail': torch.sqrt(ws.low_sq),
-            'prot_break': bool(state['prot_break']),
-            'trace': [float(t) for t in state['trace'][:nstep + 1]],
-            'eps': eps_scaled,
-            'threshold': threshold}
+    return _result_dict(ws, state, shape, eps_scaled, threshold)

@@ -20,7 +20,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from .. import ops
-from .broyden import broyden
+from .broyden import broyden, broyden_mlp
 
 __all__ = ['imBlock']
 
@@ -33,6 +33,8 @@ PROBE_MODE = {'mode': 'reference'}
 # the vjps of the implicit backward solve and of the Neumann / eval-mode power series.  Off = every
 # branch evaluation goes through the module and autograd (same kernels, many more launches).
 FUSED = {'on': True}
+# One-launch persistent solver for small-d MLP branches (csrc/mlp_solver.cu); off = host-driven loop.
+PERSISTENT_MLP = {'on': True}
 
 
 def _program(nnet):
@@ -131,11 +133,16 @@ class RootFind(Function):
     def broyden_find_root(nnet_z, nnet_x, z0, x, *args):
         eps, threshold = args[-2], args[-1]
         x_embed = ops.lincomb3(branch_eval(nnet_x, x), 1.0, x, 1.0)
+        prog_z = _program(nnet_z)
+        spec = prog_z.mlp_solver_spec(z0) if (prog_z is not None and PERSISTENT_MLP['on']) else None
+        if spec is not None:
+            # small-d MLP branch: the whole solve (branch evaluations included) in one persistent kernel
+            info = broyden_mlp(spec, x_embed, torch.zeros_like(z0), threshold, eps)
+        else:
+            def g(z):     # x_embed - nnet_z(z) - z in one kernel (implicit_block.py:72)
+                return ops.lincomb3(x_embed, 1.0, branch_eval(nnet_z, z), -1.0, z, -1.0)
 
-        def g(z):     # x_embed - nnet_z(z) - z in one kernel (implicit_block.py:72)
-            return ops.lincomb3(x_embed, 1.0, branch_eval(nnet_z, z), -1.0, z, -1.0)
-
-        info = broyden(g, torch.zeros_like(z0), threshold=threshold, eps=eps, name='forward')
+            info = broyden(g, torch.zeros_like(z0), threshold=threshold, eps=eps, name='forward')
         RootFind.last_info = info
         if info['prot_break']:
             z_est = RootFind.banach_find_root(nnet_z, nnet_x, z0, x, eps, 1000)

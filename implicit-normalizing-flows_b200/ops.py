@@ -21,7 +21,43 @@ _BACKEND = {'mode': 'auto', 'min_flops_tc': 2 * 128 * 128 * 64}
 
 # bench.py switches this on inside its timed region to collect (start, end, flop) CUDA events of
 # every tcgen05 GEMM launch for the roofline line.
-GEMM_PROFILE = {'on': False, 'events': []}
+GEMM_PROFILE = {'on': False, 'shapes': {}}
+
+
+def record_gemm(M, N, K, has_pre, has_act, has_dmul, has_split, split_k):
+    key = (int(M), int(N), int(K), bool(has_pre), bool(has_act), bool(has_dmul), bool(has_split), bool(split_k))
+    GEMM_PROFILE['shapes'][key] = GEMM_PROFILE['shapes'].get(key, 0) + 1
+
+
+def time_gemm_shape(key, reps=5, flush=None):
+    """Median CUDA-event duration (ms) of one tcgen05 GEMM launch of the recorded shape `key`, with the
+    L2 flushed by a 256 MB memset that also keeps the stream busy while the launch is enqueued (so the
+    event pair brackets the kernel alone, not host latency)."""
+    M, N, K, has_pre, has_act, has_dmul, has_split, split_k = key
+    dev = torch.device('cuda', torch.cuda.current_device())
+    A = torch.randn(M, K, device=dev)
+    Bm = torch.randn(N, K, device=dev) / max(K, 1) ** 0.5
+    As, Bs = split_tf32(A), split_tf32(Bm)
+    dm = torch.randn(M, N, device=dev) if has_dmul else None
+    beta = torch.full((1,), 0.97, device=dev)
+    if flush is None:
+        flush = torch.empty(64 * 1024 * 1024, device=dev)
+    times = []
+    was = GEMM_PROFILE['on']
+    GEMM_PROFILE['on'] = False
+    for i in range(reps + 1):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gemm_nt(A, Bm, None, act_kind=ACT_LIPSWISH if (has_act or has_dmul) else ACT_NONE, beta_sp=beta,
+                want_pre=has_pre and not has_dmul, want_act=has_act, dmul_pre=dm, A_split=As, B_split=Bs,
+                want_split=has_split)
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            times.append(e0.elapsed_time(e1))
+    GEMM_PROFILE['on'] = was
+    return sorted(times)[len(times) // 2]
 
 
 # While a caller differentiates w.r.t. ACTIVATIONS only (the vjp chains of the log-det estimators,
@@ -241,9 +277,6 @@ def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, wa
             splits = int(lib.impflow_gemm_tc_splits(M, N, K))
             if splits > 1:
                 ws = torch.empty(splits * M * N, device=dev, dtype=torch.float32)
-        if GEMM_PROFILE['on']:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e0.record()
         _cabi.check(lib.impflow_gemm_nt_tc(_cabi.ptr(Ah), _cabi.ptr(Al), K, _cabi.ptr(Bh), _cabi.ptr(Bl), K,
                                            _cabi.ptr(bias, 'bias', True), _cabi.ptr(pre, 'pre', True),
                                            _cabi.ptr(act, 'act', True), _cabi.ptr(dmul_pre, 'dmul', True),
@@ -252,9 +285,7 @@ def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, wa
                                            _cabi.ptr(ws, 'ws', True), _cabi.stream()),
                     'gemm_nt_tc')
         if GEMM_PROFILE['on']:
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record()
-            GEMM_PROFILE['events'].append((e0, e1, 2.0 * M * N * K))
+            record_gemm(M, N, K, pre is not None, act is not None, dmul_pre is not None, want_split, ws is not None)
         return pre, act, ((sh, sl) if want_split else None)
     _cabi.check(lib.impflow_gemm_nt(_cabi.ptr(A), K, _cabi.ptr(Bm), K, _cabi.ptr(bias, 'bias', True),
                                     _cabi.ptr(pre, 'pre', True), _cabi.ptr(act, 'act', True),

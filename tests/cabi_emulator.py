@@ -228,6 +228,47 @@ class EmulatedLib(object):
             x_old.reshape(B, d)[:] = X + upd
         return 0
 
+    # ---- persistent MLP solver (csrc/mlp_solver.cu) ----
+    def impflow_mlp_solver_limits(self, a, b, c):
+        return 0
+
+    def impflow_mlp_solver_partial_doubles(self):
+        return 2 * 148 * 8
+
+    def impflow_mlp_broyden_solve(self, x_embed, Wt, bias, dims, L, act_kind, beta_sp, za, ga, zb, gb, low_z, low_g,
+                                  Ut, Vt, sample_sq, low_sq, partial, state, B, T, eps, stream):
+        dims = [int(v) for v in dims]
+        d = dims[0]
+        beta = _beta(beta_sp)
+        Ws = [_f32(Wt[l], dims[l] * dims[l + 1]).reshape(dims[l], dims[l + 1]) for l in range(L)]
+        bs = [(_f32(bias[l], dims[l + 1]) if bias[l] else None) for l in range(L)]
+        xe = _f32(x_embed, B * d).reshape(B, d)
+
+        def f(z):
+            h = z
+            for l in range(L):
+                h = (h @ Ws[l]).astype(np.float32)
+                if bs[l] is not None:
+                    h = h + bs[l]
+                if l + 1 < L:
+                    h = _act(act_kind, h, 0, beta).astype(np.float32)
+            return h
+
+        bufs = {'x': za, 'g': ga, 'xn': zb, 'gn': gb}
+        x0 = _f32(za, B * d).reshape(B, d)
+        _f32(ga, B * d)[:] = (xe - f(x0) - x0).ravel()
+        self.impflow_broyden_begin(za, ga, zb, low_z, low_g, sample_sq, low_sq, None, state, B, d, T, eps, None)
+        st = _state(state)
+        while st[0]['active']:
+            xn = _f32(bufs['xn'], B * d).reshape(B, d)
+            _f32(bufs['gn'], B * d)[:] = (xe - f(xn) - xn).ravel()
+            self.impflow_broyden_step(bufs['x'], bufs['g'], bufs['xn'], bufs['gn'], Ut, Vt, low_z, low_g, sample_sq,
+                                      low_sq, None, state, B, d, T, None)
+            bufs['x'], bufs['xn'] = bufs['xn'], bufs['x']
+            bufs['g'], bufs['gn'] = bufs['gn'], bufs['g']
+        self.launches += 1
+        return 0
+
     # ---- elementwise (csrc/elementwise.cu) ----
     def impflow_act_mul(self, x, g, out, n, kind, order, beta_sp, stream):
         xv, gv, ov = _f32(x, n), _f32(g, n), _f32(out, n)

@@ -235,3 +235,59 @@ def test_broyden_shapes_against_oracle(B, d):
     assert res['lowest_step'] == ref['lowest_step']
     assert rel_err(res['result'].cpu(), ref['result']) < 1e-5
     np.testing.assert_allclose(res['trace'][:-1], ref['trace'][:-1], rtol=2e-3)
+
+
+@pytest.mark.parametrize('B,d,hidden,nh,act', [(5000, 2, 128, 2, 'sin'), (1000, 6, 128, 4, 'sin'), (1000, 63, 128, 4, 'sin'),
+                                              (37, 43, 64, 2, 'swish'), (1, 5, 16, 1, 'relu')])
+def test_persistent_mlp_solver(B, d, hidden, nh, act):
+    """One-launch persistent solver (csrc/mlp_solver.cu) == host-driven kernel loop == CPU oracle."""
+    import impflow_b200
+    from impflow_b200.branch_program import compile_branch
+    from impflow_b200.layers import broyden as bmod
+    L = impflow_b200.layers
+    torch.manual_seed(B + d)
+    acts = {'sin': L.base.Sin, 'swish': L.base.Swish, 'relu': L.base.ReLU}
+    dims = [d] + [hidden] * nh + [d]
+    mods = []
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        if i > 0:
+            mods.append(acts[act]())
+        mods.append(L.base.get_linear(a, b, coeff=0.9, n_iterations=None, atol=1e-3, rtol=1e-3, domain=2, codomain=2))
+    net = torch.nn.Sequential(*mods)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() > 1:
+                p.mul_(4.0)
+    net = net.cuda()
+    prog = compile_branch(net)
+    x_embed = torch.randn(B, d, device='cuda')
+    z0 = torch.zeros(B, d, device='cuda')
+    with torch.no_grad():
+        spec = prog.mlp_solver_spec(z0)
+        assert spec is not None
+        res_p = bmod.broyden_mlp(spec, x_embed, z0, 30, 1e-6)
+        low_p = res_p['result'].clone()
+        g = lambda z: impflow_b200.ops.lincomb3(x_embed, 1.0, prog.forward(z), -1.0, z, -1.0)
+        res_h = bmod.broyden(g, z0, 30, 1e-6)
+        # CPU oracle on the same effective weights
+        ws = prog._prep(B)
+        Ws = [w.fwd[:, :w.cin].cpu() for w in ws]
+        bs = [w.bias.cpu() for w in ws]
+        beta = torch.nn.functional.softplus(torch.tensor([0.5]))
+
+        def f_cpu(z):
+            h = z
+            for i, (W, b) in enumerate(zip(Ws, bs)):
+                h = h @ W.t() + b
+                if i + 1 < len(Ws):
+                    h = orc.sin_act(h) if act == 'sin' else (orc.lipswish(h, torch.tensor([0.5])) if act == 'swish'
+                                                             else torch.relu(h))
+            return h
+        xe = x_embed.cpu()
+        ref = orc.broyden_solve(lambda z: xe - f_cpu(z) - z, torch.zeros(B, d), 30, 1e-6)
+    assert res_p['nstep'] == res_h['nstep'] == ref['nstep'], (res_p['trace'], res_h['trace'], ref['trace'])
+    assert res_p['lowest_step'] == ref['lowest_step']
+    assert rel_err(low_p.cpu(), ref['result']) < 1e-5
+    assert rel_err(low_p.cpu(), res_h['result'].cpu()) < 1e-5
+    np.testing.assert_allclose(res_p['trace'][:-1], ref['trace'][:-1], rtol=5e-3)
+    assert res_p['diff_detail'].shape == (B,)
