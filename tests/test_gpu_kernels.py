@@ -289,5 +289,7 @@ def test_persistent_mlp_solver(B, d, hidden, nh, act):
     assert res_p['lowest_step'] == ref['lowest_step']
     assert rel_err(low_p.cpu(), ref['result']) < 1e-5
     assert rel_err(low_p.cpu(), res_h['result'].cpu()) < 1e-5
-    np.testing.assert_allclose(res_p['trace'][:-1], ref['trace'][:-1], rtol=5e-3)
+    tp, tr = np.array(res_p['trace']), np.array(ref['trace'])
+    big = tr > 1e-3 * tr[0]                  # below that the residual is fp32 round-off of the branch
+    np.testing.assert_allclose(tp[big], tr[big], rtol=5e-3)
     assert res_p['diff_detail'].shape == (B,)
