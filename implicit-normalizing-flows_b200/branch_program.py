@@ -66,7 +66,8 @@ class _Act(object):
 
 class _Weights(object):
     """Effective weights of one layer in the layouts the fused path needs (fp32 + optional planes)."""
-    __slots__ = ('fwd', 'fwd_split', 'bwd', 'bwd_split', 'bias', 'kind', 'cin', 'cout', 'fwd_k', 'bwd_k', 'a_type')
+    __slots__ = ('fwd', 'fwd_split', 'bwd', 'bwd_split', 'bias', 'kind', 'cin', 'cout', 'fwd_k', 'bwd_k', 'a_type',
+                 'sigma')
 
 
 class _T(object):
@@ -174,7 +175,11 @@ class BranchProgram(object):
                     # first use: record the spatial dims like InducedNormConv2d.forward does
                     m.spatial_dims.copy_(torch.tensor([float(meta[1][1]), float(meta[1][2])]).to(m.spatial_dims))
                     m._hw = None
-                W = m.compute_weight(update=False).detach()
+                if isinstance(m, InducedNormConv2d) and not m.is_initialized():
+                    m.compute_weight(update=False)                      # lazy u/v init (first use only)
+                # effective weight W / max(1, sigma/coeff) with sigma = <W, D> on the device
+                W, sigma = ops.sn_scale(m.weight.detach(), m.sigma_gradient(), m.coeff, scale_out=m.scale)
+                w.sigma = sigma
                 w.bias = m.bias.detach() if m.bias is not None else None
                 if isinstance(m, InducedNormLinear) or m.kernel_size == (1, 1):
                     cout, cin = W.shape[0], W.shape[1]
@@ -438,10 +443,8 @@ class BranchProgram(object):
         for i, (act, m) in enumerate(self.stages):
             if wbars[i] is not None:
                 g_eff = self._to_weight_layout(ws[i], wbars[i]).reshape(m.weight.shape).contiguous()
-                with torch.enable_grad():
-                    W_eff = m.compute_weight(update=False)
-                    (gw,) = torch.autograd.grad(W_eff, m.weight, g_eff)
-                by_id[id(m.weight)] = gw
+                by_id[id(m.weight)] = ops.sn_scale_grad(g_eff, m.weight.detach(), m.sigma_gradient(), ws[i].sigma,
+                                                        m.coeff)
             if m.bias is not None and bbars[i] is not None:
                 by_id[id(m.bias)] = bbars[i]
         for act, gb in zip(self._acts(), betabars):

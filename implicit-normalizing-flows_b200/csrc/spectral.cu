@@ -117,9 +117,52 @@ k_sn_power_iter(const float* __restrict__ W, float* __restrict__ u_g, float* __r
   }
 }
 
+// W / max(1, sigma/coeff) with sigma read from the device (mixed_lipschitz.py:128-131), and its
+// gradient chain  dL/dW = s*G + <G,W> * ds/dsigma * D,  D = dsigma/dW (sigma = <W, D> is linear in W).
+__global__ void __launch_bounds__(256)
+k_sn_scale(const float* __restrict__ W, const float* __restrict__ sigma, float coeff, float* __restrict__ out,
+           float* __restrict__ scale_out, long long n) {
+  const float sg = __ldg(sigma);
+  const float factor = fmaxf(1.f, sg / coeff);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && scale_out != nullptr) scale_out[0] = sg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = W[i] / factor;
+}
+__global__ void __launch_bounds__(256)
+k_sn_scale_grad(const float* __restrict__ G, const float* __restrict__ D, const float* __restrict__ sigma,
+                const float* __restrict__ gw_dot, float coeff, float* __restrict__ out, long long n) {
+  const float sg = __ldg(sigma);
+  const float ratio = sg / coeff;
+  const float s = ratio > 1.f ? 1.f / ratio : 1.f;
+  const float ds = ratio > 1.f ? -coeff / (sg * sg) : 0.f;
+  const float c2 = ds * __ldg(gw_dot);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = s * G[i] + c2 * D[i];
+}
+
 }  // namespace impflow
 
 using namespace impflow;
+
+extern "C" int impflow_sn_scale(const float* W, const float* sigma, float coeff, float* out, float* scale_out,
+                                long long n, void* stream) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  k_sn_scale<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(W, sigma, coeff, out, scale_out, n);
+  return check_launch("k_sn_scale");
+}
+
+extern "C" int impflow_sn_scale_grad(const float* G, const float* D, const float* sigma, const float* gw_dot,
+                                     float coeff, float* out, long long n, void* stream) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  k_sn_scale_grad<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(G, D, sigma, gw_dot, coeff, out, n);
+  return check_launch("k_sn_scale_grad");
+}
 
 extern "C" int impflow_sn_power_iter(const float* W, float* u, float* v, float* sigma, int* iters, int out_f,
                                      int in_f, int n_iterations, float atol, float rtol, void* stream) {

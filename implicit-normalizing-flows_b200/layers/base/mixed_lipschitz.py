@@ -106,6 +106,15 @@ class InducedNormLinear(nn.Module):
     def compute_domain_codomain(self):
         return self.domain, self.codomain
 
+    def sigma_gradient(self):
+        """D = d sigma / d W = u v^T (sigma = u^T W v is linear in W), cached until u or v change."""
+        key = (self.u._version, self.v._version, self.u.data_ptr(), self.v.data_ptr())
+        cached = getattr(self, '_sigma_grad', None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                cached = self._sigma_grad = (key, torch.outer(self.u, self.v).contiguous())
+        return cached[1]
+
     def compute_one_iter(self):
         _require_cuda(self.weight, 'InducedNormLinear.weight')
         u, v = self.u.clone(), self.v.clone()
@@ -226,6 +235,26 @@ class InducedNormConv2d(nn.Module):
             wt = weight.flip(2, 3).transpose(0, 1)        # conv_transpose2d, stride 1, pad 1
             y = ops.conv3x3_nhwc(_to_nhwc(x), wt)
         return _from_nhwc(y).reshape(-1)
+
+    def sigma_gradient(self):
+        """D = d sigma / d W in the weight's layout; sigma = <u, conv(v; W)> is linear in W, so D
+        depends on u and v only (the correlation of u with the patches of v) and is cached until they
+        change (once per update_lipschitz)."""
+        key = (self.u._version, self.v._version, self.u.data_ptr(), self.v.data_ptr())
+        cached = getattr(self, '_sigma_grad', None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                if self.kernel_size == (1, 1):
+                    D = torch.outer(self.u, self.v).view(self.out_channels, self.in_channels, 1, 1).contiguous()
+                else:
+                    h, w = self._spatial()
+                    co, ci = self.out_channels, self.in_channels
+                    v_nhwc = self.v.view(1, ci, h, w).permute(0, 2, 3, 1).contiguous()
+                    col_t = ops.transpose2d(ops.im2col3x3(v_nhwc))                 # (9ci, hw)
+                    Dr, _, _ = ops.gemm_nt(self.u.view(co, h * w), col_t)          # (co, (ky,kx,ci))
+                    D = Dr.view(co, 3, 3, ci).permute(0, 3, 1, 2).contiguous()
+                cached = self._sigma_grad = (key, D)
+        return cached[1]
 
     def _initialize_u_v(self):
         # mixed_lipschitz.py:195-239 (domain = codomain = 2: a single start, no restarts)

@@ -182,6 +182,14 @@ int impflow_split_tf32(const float* a, float* hi, float* lo, long long n, void* 
 int impflow_sn_power_iter(const float* W, float* u, float* v, float* sigma, int* iters, int out_f,
                           int in_f, int n_iterations, float atol, float rtol, void* stream);
 
+/* Soft spectral rescale with sigma on the device: out = W / max(1, sigma[0]/coeff), scale_out[0] =
+ * sigma[0] (mixed_lipschitz.py:125-131), and its gradient chain with D = d sigma / d W (sigma = <W,D>
+ * is linear in W; u, v constant):  out = s*G + gw_dot[0] * ds/dsigma * D,  gw_dot = <G, W>. */
+int impflow_sn_scale(const float* W, const float* sigma, float coeff, float* out, float* scale_out, long long n,
+                     void* stream);
+int impflow_sn_scale_grad(const float* G, const float* D, const float* sigma, const float* gw_dot, float coeff,
+                          float* out, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -390,6 +390,23 @@ class EmulatedLib(object):
         return 0
 
     # ---- spectral (csrc/spectral.cu) ----
+    def impflow_sn_scale(self, W, sigma, coeff, out, scale_out, n, stream):
+        sg = _f32(sigma, 1)[0]
+        _f32(out, n)[:] = _f32(W, n) / max(np.float32(1), sg / np.float32(coeff))
+        if _addr(scale_out) is not None:
+            _f32(scale_out, 1)[0] = sg
+        self.launches += 1
+        return 0
+
+    def impflow_sn_scale_grad(self, G, D, sigma, gw_dot, coeff, out, n, stream):
+        sg = float(_f32(sigma, 1)[0])
+        ratio = sg / coeff
+        s_ = 1.0 / ratio if ratio > 1 else 1.0
+        ds = -coeff / (sg * sg) if ratio > 1 else 0.0
+        _f32(out, n)[:] = np.float32(s_) * _f32(G, n) + np.float32(ds * float(_f32(gw_dot, 1)[0])) * _f32(D, n)
+        self.launches += 1
+        return 0
+
     def impflow_sn_power_iter(self, W, u, v, sigma, iters, out_f, in_f, n_iterations, atol, rtol, stream):
         Wm = _f32(W, out_f * in_f).reshape(out_f, in_f)
         uv, vv = _f32(u, out_f), _f32(v, in_f)
