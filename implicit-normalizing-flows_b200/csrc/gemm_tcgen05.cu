@@ -121,7 +121,8 @@ struct TcCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    4 * 32 * 36 * 4 /*epilogue staging tiles*/;
 };
 
 template <int BN>
@@ -261,6 +262,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     const Epilogue e = resolve_beta(ep.e);
+    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + q * (32 * 36);
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long mn = tile / splits;
       const int ks = (int)(tile % splits);
@@ -283,9 +285,76 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
           }
           continue;
         }
-        if (m < M && n0 < N) {
+        if (n0 >= N) continue;                                   // warp-uniform
+        const bool full_vec = (n0 + 32 <= N) && ((e.ldc & 3) == 0);   // warp-uniform
+        if (full_vec) {
+          // ---- coalesced path: every global load/store of the warp covers 4 rows x 128 contiguous
+          // bytes, staged through a per-warp 32x36 shared-memory tile (lane = row on the register
+          // side, lane = 16-byte column group on the global side) ----
+          const long long m_base = (mn / n_tiles) * TC_BM + q * 32;
+          auto stage_store = [&](float* __restrict__ out, const float* vals) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(vals[j], vals[j + 1], vals[j + 2], vals[j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3), cc = (lane & 7) * 4;
+              const float4 t = *reinterpret_cast<const float4*>(stg + rr * 36 + cc);
+              if (m_base + rr < M) *reinterpret_cast<float4*>(out + (m_base + rr) * e.ldc + n0 + cc) = t;
+            }
+            __syncwarp();
+          };
+          auto stage_load = [&](const float* __restrict__ in, float* vals) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3), cc = (lane & 7) * 4;
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (m_base + rr < M) t = *reinterpret_cast<const float4*>(in + (m_base + rr) * e.ldc + n0 + cc);
+              *reinterpret_cast<float4*>(stg + rr * 36 + cc) = t;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(stg + lane * 36 + j);
+              vals[j] = t.x; vals[j + 1] = t.y; vals[j + 2] = t.z; vals[j + 3] = t.w;
+            }
+            __syncwarp();
+          };
+          float v[32], tmp[32];
+          if (e.dmul_pre != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (e.act_out != nullptr) stage_store(e.act_out, v);   // dmul mode: act_out = raw accumulator
+            stage_load(e.dmul_pre, tmp);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= act_dispatch(e.act_kind, tmp[j], 1, e.beta);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = __uint_as_float(r[j]) + (e.bias != nullptr ? __ldg(e.bias + n0 + j) : 0.f);
+            if (e.pre_out != nullptr) stage_store(e.pre_out, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_dispatch(e.act_kind, v[j], 0, e.beta);
+          }
+          float* main_out = (e.dmul_pre != nullptr) ? e.pre_out : e.act_out;
+          if (main_out != nullptr) stage_store(main_out, v);
+          if (ep.split_hi != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              uint32_t hb;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j]));
+              tmp[j] = __uint_as_float(hb);
+            }
+            stage_store(ep.split_hi, tmp);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tmp[j] = v[j] - tmp[j];
+            stage_store(ep.split_lo, tmp);
+          }
+          continue;
+        }
+        if (m < M) {   // ragged tail chunk: per-lane scalar path
           const long long row = m * e.ldc;
-          const bool full_vec = (n0 + 32 <= N) && ((e.ldc & 3) == 0);
           float v[32];
           if (e.dmul_pre != nullptr) {
             if (e.act_out != nullptr) {      // dmul mode: act_out receives the raw accumulator
