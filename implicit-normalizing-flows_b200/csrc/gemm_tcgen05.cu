@@ -23,7 +23,8 @@ namespace impflow {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // 32 fp32 = 128 bytes = one swizzle-128B row
-constexpr int TC_THREADS = 256;
+constexpr int TC_EPI_WARPS = 8;   // two warps per TMEM lane quarter, interleaved over the 32-column chunks
+constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;
 
 struct TcEpilogue {
   Epilogue e;
@@ -113,6 +114,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per thread and instruction, so the
+// row-per-thread epilogue issues half as many L2 transactions as with 128-bit accesses.
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+
 template <int BN>
 struct TcCfg {
   static constexpr int kStages = (BN >= 256) ? 2 : (BN >= 128) ? 3 : 4;
@@ -121,8 +135,7 @@ struct TcCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    4 * 32 * 36 * 4 /*epilogue staging tiles*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -163,7 +176,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[s], TC_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -258,11 +271,11 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
-    const int q = warp - 4;  // TMEM lane quarter this warp may touch (warp % 4)
+    const int q = warp & 3;           // TMEM lane quarter this warp may touch (warp % 4)
+    const int chunk0 = (warp - 4) >> 2;  // first 32-column chunk of this warp; stride TC_EPI_WARPS / 4
     int acc = 0;
     uint32_t acc_phase = 0;
     const Epilogue e = resolve_beta(ep.e);
-    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + q * (32 * 36);
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long mn = tile / splits;
       const int ks = (int)(tile % splits);
@@ -271,7 +284,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chunk0; c < BN / 32; c += TC_EPI_WARPS / 4) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
         tmem_ld32(taddr, r);
@@ -285,85 +298,20 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
           }
           continue;
         }
-        if (n0 >= N) continue;                                   // warp-uniform
-        const bool full_vec = (n0 + 32 <= N) && ((e.ldc & 3) == 0);   // warp-uniform
-        if (full_vec) {
-          // ---- coalesced path: every global load/store of the warp covers 4 rows x 128 contiguous
-          // bytes, staged through a per-warp 32x36 shared-memory tile (lane = row on the register
-          // side, lane = 16-byte column group on the global side) ----
-          const long long m_base = (mn / n_tiles) * TC_BM + q * 32;
-          auto stage_store = [&](float* __restrict__ out, const float* vals) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(vals[j], vals[j + 1], vals[j + 2], vals[j + 3]);
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + (lane >> 3), cc = (lane & 7) * 4;
-              const float4 t = *reinterpret_cast<const float4*>(stg + rr * 36 + cc);
-              if (m_base + rr < M) *reinterpret_cast<float4*>(out + (m_base + rr) * e.ldc + n0 + cc) = t;
-            }
-            __syncwarp();
-          };
-          auto stage_load = [&](const float* __restrict__ in, float* vals) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + (lane >> 3), cc = (lane & 7) * 4;
-              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (m_base + rr < M) t = *reinterpret_cast<const float4*>(in + (m_base + rr) * e.ldc + n0 + cc);
-              *reinterpret_cast<float4*>(stg + rr * 36 + cc) = t;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(stg + lane * 36 + j);
-              vals[j] = t.x; vals[j + 1] = t.y; vals[j + 2] = t.z; vals[j + 3] = t.w;
-            }
-            __syncwarp();
-          };
-          float v[32], tmp[32];
-          if (e.dmul_pre != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (e.act_out != nullptr) stage_store(e.act_out, v);   // dmul mode: act_out = raw accumulator
-            stage_load(e.dmul_pre, tmp);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= act_dispatch(e.act_kind, tmp[j], 1, e.beta);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = __uint_as_float(r[j]) + (e.bias != nullptr ? __ldg(e.bias + n0 + j) : 0.f);
-            if (e.pre_out != nullptr) stage_store(e.pre_out, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_dispatch(e.act_kind, v[j], 0, e.beta);
-          }
-          float* main_out = (e.dmul_pre != nullptr) ? e.pre_out : e.act_out;
-          if (main_out != nullptr) stage_store(main_out, v);
-          if (ep.split_hi != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              uint32_t hb;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j]));
-              tmp[j] = __uint_as_float(hb);
-            }
-            stage_store(ep.split_hi, tmp);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tmp[j] = v[j] - tmp[j];
-            stage_store(ep.split_lo, tmp);
-          }
-          continue;
-        }
-        if (m < M) {   // ragged tail chunk: per-lane scalar path
+        if (m < M && n0 < N) {
           const long long row = m * e.ldc;
+          const bool full_vec = (n0 + 32 <= N) && ((e.ldc & 7) == 0);   // 32-byte aligned row chunks
           float v[32];
           if (e.dmul_pre != nullptr) {
             if (e.act_out != nullptr) {      // dmul mode: act_out receives the raw accumulator
               if (full_vec) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(e.act_out + row + n0 + j) =
-                      make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                  __uint_as_float(r[j + 3]));
+                for (int j = 0; j < 32; j += 8) {
+                  float t8[8];
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) t8[u] = __uint_as_float(r[j + u]);
+                  st_global_v8(e.act_out + row + n0 + j, t8);
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -371,17 +319,16 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
               }
             }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float p[4];
+            for (int j = 0; j < 32; j += 8) {
+              float p[8];
               if (full_vec) {
-                const float4 t = *reinterpret_cast<const float4*>(e.dmul_pre + row + n0 + j);
-                p[0] = t.x; p[1] = t.y; p[2] = t.z; p[3] = t.w;
+                ld_global_v8(e.dmul_pre + row + n0 + j, p);
               } else {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) p[u] = (n0 + j + u < N) ? e.dmul_pre[row + n0 + j + u] : 0.f;
+                for (int u = 0; u < 8; ++u) p[u] = (n0 + j + u < N) ? e.dmul_pre[row + n0 + j + u] : 0.f;
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
+              for (int u = 0; u < 8; ++u)
                 v[j + u] = __uint_as_float(r[j + u]) * act_dispatch(e.act_kind, p[u], 1, e.beta);
             }
           } else {
@@ -393,8 +340,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
             if (e.pre_out != nullptr) {
               if (full_vec) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(e.pre_out + row + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 8) st_global_v8(e.pre_out + row + n0 + j, v + j);
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -408,8 +354,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
           if (main_out != nullptr) {
             if (full_vec) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(main_out + row + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 32; j += 8) st_global_v8(main_out + row + n0 + j, v + j);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -418,21 +363,21 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
           }
           if (ep.split_hi != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float h[4], l[4];
+            for (int j = 0; j < 32; j += 8) {
+              float h[8], l[8];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < 8; ++u) {
                 uint32_t hb;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j + u]));
                 h[u] = __uint_as_float(hb);
                 l[u] = v[j + u] - h[u];
               }
               if (full_vec) {
-                *reinterpret_cast<float4*>(ep.split_hi + row + n0 + j) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(ep.split_lo + row + n0 + j) = make_float4(l[0], l[1], l[2], l[3]);
+                st_global_v8(ep.split_hi + row + n0 + j, h);
+                st_global_v8(ep.split_lo + row + n0 + j, l);
               } else {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 8; ++u)
                   if (n0 + j + u < N) {
                     ep.split_hi[row + n0 + j + u] = h[u];
                     ep.split_lo[row + n0 + j + u] = l[u];
