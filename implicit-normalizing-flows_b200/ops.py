@@ -308,10 +308,19 @@ def sn_power_iter(W2d, u, v, n_iterations, atol, rtol):
     return sigma, iters
 
 
+def _flat_dot(a, b):
+    """<a, b> over all elements as a 1-element device tensor.  Large operands are viewed as 256 rows so
+    that the row-dot kernel spreads over the SMs (one CTA per row), then the 256 partials are summed."""
+    n = a.numel()
+    if n >= 65536 and n % 256 == 0:
+        return rowdot(a.view(256, -1), b.view(256, -1)).sum().view(1)
+    return rowdot(a.view(1, -1), b.view(1, -1))
+
+
 def sn_scale(W, D, coeff, scale_out=None):
     """(W / max(1, sigma/coeff), sigma) with sigma = <W, D> computed and consumed on the device."""
     W = W.contiguous()
-    sigma = rowdot(W.view(1, -1), D.view(1, -1))
+    sigma = _flat_dot(W, D)
     out = torch.empty_like(W)
     _cabi.check(_lib().impflow_sn_scale(_cabi.ptr(W), _cabi.ptr(sigma), float(coeff), _cabi.ptr(out),
                                         _cabi.ptr(scale_out, 'scale', True), W.numel(), _cabi.stream()), 'sn_scale')
@@ -322,7 +331,7 @@ def sn_scale_grad(G, W, D, sigma, coeff):
     """Gradient of <G, W / max(1, sigma(W)/coeff)> w.r.t. W (sigma linear in W with gradient D)."""
     G = G.contiguous()
     W = W.contiguous()
-    t = rowdot(G.view(1, -1), W.view(1, -1))
+    t = _flat_dot(G, W)
     out = torch.empty_like(W)
     _cabi.check(_lib().impflow_sn_scale_grad(_cabi.ptr(G), _cabi.ptr(D), _cabi.ptr(sigma), _cabi.ptr(t),
                                              float(coeff), _cabi.ptr(out), W.numel(), _cabi.stream()),
