@@ -30,6 +30,15 @@ WORKLOADS = {
     'cifar': dict(input=(3, 32, 32), n_blocks=[2, 2, 2], idim=512, batch=64, n_exact_terms=10, coeff=0.9),
     # reduced-width debug variant (not a bench line)
     'cifar-small': dict(input=(3, 32, 32), n_blocks=[1, 1, 1], idim=64, batch=16, n_exact_terms=4, coeff=0.9),
+    # run_tabular.sh / run_toy.sh shapes (parity-test configs; selectable, never the default bench line)
+    'tabular-power': dict(kind='mlp', d=6, hidden=[128] * 4, n_blocks=20, batch=1000, coeff=0.99, sn_tol=1e-3,
+                          n_lipschitz_iters=None, brute_force=False, eps_forward=1e-5),
+    'tabular-miniboone': dict(kind='mlp', d=43, hidden=[128] * 4, n_blocks=20, batch=1000, coeff=0.99, sn_tol=1e-3,
+                              n_lipschitz_iters=None, brute_force=False, eps_forward=1e-5),
+    'tabular-bsds300': dict(kind='mlp', d=63, hidden=[128] * 4, n_blocks=20, batch=1000, coeff=0.99, sn_tol=1e-3,
+                            n_lipschitz_iters=None, brute_force=False, eps_forward=1e-5),
+    'toy': dict(kind='mlp', d=2, hidden=[128] * 2, n_blocks=6, batch=5000, coeff=0.99, sn_tol=None,
+                n_lipschitz_iters=20, brute_force=True, eps_forward=1e-6),
 }
 
 
@@ -37,7 +46,30 @@ def std_normal_logprob(z):
     return -0.5 * np.log(2 * np.pi) - z.pow(2) / 2
 
 
+def build_mlp_flow(pkg, wl):
+    """train_tabular.py:292-336 / train_toy.py:146-171,224-242: n imBlocks over Sin MLP branches."""
+    layers = pkg.layers
+    d = wl['d']
+    dims = [d] + list(wl['hidden']) + [d]
+
+    def net():
+        mods = []
+        for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+            if i > 0:
+                mods.append(layers.base.Sin())
+            mods.append(layers.base.get_linear(a, b, coeff=wl['coeff'], n_iterations=wl['n_lipschitz_iters'],
+                                               atol=wl['sn_tol'], rtol=wl['sn_tol'], domain=2, codomain=2,
+                                               zero_init=(b == d)))
+        return torch.nn.Sequential(*mods)
+    blocks = [layers.imBlock(net(), net(), n_dist='geometric', n_power_series=None, exact_trace=False,
+                             brute_force=wl['brute_force'], n_samples=1, n_exact_terms=2, neumann_grad=False,
+                             grad_in_forward=False, eps_forward=wl['eps_forward']) for _ in range(wl['n_blocks'])]
+    return layers.SequentialFlow(blocks)
+
+
 def build_model(pkg, wl, batch):
+    if wl.get('kind') == 'mlp':
+        return build_mlp_flow(pkg, wl)
     layers = pkg.layers
     c, h, w = wl['input']
     return pkg.ImplicitFlow(
@@ -49,16 +81,16 @@ def build_model(pkg, wl, batch):
         first_resblock=True, learn_p=False, classification=False, classification_hdim=256, n_classes=10)
 
 
-def update_lipschitz(pkg, model):
-    """train_img.py:786-792; the frozen *_copy twins are skipped (overwritten at the next forward,
-    SURVEY.md quirk #11)."""
+def update_lipschitz(pkg, model, n_iterations=None):
+    """train_img.py:786-792 (train_toy.py:174-179 with n_iterations); the frozen *_copy twins are skipped
+    (overwritten at the next forward, SURVEY.md quirk #11)."""
     BL = pkg.layers.base
     with torch.no_grad():
         for name, m in model.named_modules():
             if '_copy' in name:
                 continue
             if isinstance(m, (BL.InducedNormConv2d, BL.InducedNormLinear)):
-                m.compute_weight(update=True)
+                m.compute_weight(update=True, n_iterations=n_iterations)
 
 
 class ClockSampler(object):
@@ -117,6 +149,8 @@ def run_cpu_reference(wl_name, steps, warmup, batch, threads=None):
     from oracle import flow_oracle
     import impflow_b200 as pkg
     wl = WORKLOADS[wl_name]
+    if wl.get('kind') == 'mlp':
+        return run_cpu_reference_mlp(pkg, wl, steps, warmup, batch, threads)
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     torch.manual_seed(0)
@@ -139,6 +173,49 @@ def run_cpu_reference(wl_name, steps, warmup, batch, threads=None):
             times.append(dt)
     ms = float(np.mean(times) * 1e3)
     return {'value': batch / (ms / 1e3), 'ms_per_step': ms, 'cores': threads, 'batch': batch, 'bpd': bpd,
+            'fwd_nstep': stats.get('fwd_nstep', [])[-6:], 'bwd_nstep': stats.get('bwd_nstep', [])[-6:]}
+
+
+def run_cpu_reference_mlp(pkg, wl, steps, warmup, batch, threads=None):
+    """Oracle port of the tabular / toy training step on host cores."""
+    from oracle import impflow_oracle as orc
+    from tests.helpers import oracle_branch
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = build_mlp_flow(pkg, wl)
+    sd = model.state_dict()
+    d = wl['d']
+    blocks, params = [], []
+    for i in range(wl['n_blocks']):
+        sub = lambda pre: {k[len(pre):]: v.clone() for k, v in sd.items() if k.startswith(pre)}
+        bx = oracle_branch(sub('chain.%d.nnet_x.' % i), 'sin', wl['coeff'], wl['sn_tol'], wl['n_lipschitz_iters'])
+        bz = oracle_branch(sub('chain.%d.nnet_z.' % i), 'sin', wl['coeff'], wl['sn_tol'], wl['n_lipschitz_iters'])
+        blocks.append((bx, bz))
+        params += bx.parameters() + bz.parameters()
+    cfg = dict(orc.DEFAULT_CFG, neumann_grad=False, grad_in_forward=False, eps_forward=wl['eps_forward'],
+               brute_force=wl['brute_force'])
+    opt = torch.optim.Adam(params, lr=1e-3)
+    x = torch.randn(batch, d)
+    times, stats = [], {}
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        h, logp = x, torch.zeros(batch, 1)
+        for bx, bz in blocks:
+            h, logp = orc.imblock_forward(bx, bz, h, logp, cfg, True, stats=stats)
+        logpz = (-0.5 * np.log(2 * np.pi) - h.pow(2) / 2).sum(1, keepdim=True)
+        loss = -(logpz - logp).mean()
+        loss.backward()
+        opt.step()
+        for bx, bz in blocks:
+            bx.update_lipschitz(wl['n_lipschitz_iters'])
+            bz.update_lipschitz(wl['n_lipschitz_iters'])
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    ms = float(np.mean(times) * 1e3)
+    return {'value': batch / (ms / 1e3), 'ms_per_step': ms, 'cores': threads, 'batch': batch, 'bpd': float(loss),
             'fwd_nstep': stats.get('fwd_nstep', [])[-6:], 'bwd_nstep': stats.get('bwd_nstep', [])[-6:]}
 
 
@@ -262,9 +339,18 @@ def main():
     torch.manual_seed(0)
     np.random.seed(0)
     model = build_model(pkg, wl, batch).to(dev)
-    c, h, w = wl['input']
+    is_mlp = wl.get('kind') == 'mlp'
     gen = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.rand(batch, c, h, w, generator=gen).pin_memory()
+    if is_mlp:
+        c, h, w = wl['d'], 1, 1
+        x_host = torch.randn(batch, wl['d'], generator=gen).pin_memory()     # z-scored tabular data
+        with torch.no_grad():        # move the near-zero last layers so the solves do real work
+            for n_, p_ in model.named_parameters():
+                if n_.endswith('weight') and p_.dim() == 2 and p_.requires_grad:
+                    p_.mul_(30.0 if p_.shape[0] == wl['d'] else 1.0)
+    else:
+        c, h, w = wl['input']
+        x_host = torch.rand(batch, c, h, w, generator=gen).pin_memory()
     x_dev = x_host.to(dev)
     with torch.no_grad():
         model(x_dev, restore=True)           # ActNorm data init + lazy u/v shaping (train_img.py:502-507)
@@ -282,15 +368,21 @@ def main():
 
     def step(x):
         bucket.zero()
-        z, dlogp = model(x, 0)
-        logpz = std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True)
-        logpx = logpz - dlogp - np.log(256) * n_dims
-        bpd = -torch.mean(logpx) / n_dims / np.log(2)
+        if is_mlp:          # train_tabular.py:398-407 / train_toy.py:108-116
+            z, dlogp = model(x, torch.zeros(x.shape[0], 1, device=x.device))
+            logpz = std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True)
+            bpd = -(logpz - dlogp).mean()
+        else:
+            z, dlogp = model(x, 0)
+            logpz = std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True)
+            logpx = logpz - dlogp - np.log(256) * n_dims
+            bpd = -torch.mean(logpx) / n_dims / np.log(2)
         bpd.backward()
         bucket.allreduce_mean()
-        torch.nn.utils.clip_grad_norm_(params, 1.)
+        if not is_mlp:
+            torch.nn.utils.clip_grad_norm_(params, 1.)
         opt.step()
-        update_lipschitz(pkg, model)
+        update_lipschitz(pkg, model, wl.get('n_lipschitz_iters'))
         return bpd
 
     def sync_all():
