@@ -431,17 +431,26 @@ def main():
     # busy so the events bracket the kernel alone) and weighted by its launch count.
     gemm_shapes = dict(pkg.ops.GEMM_PROFILE['shapes'])
     pkg.ops.GEMM_PROFILE['shapes'] = {}
-    gemm_ms, gemm_flop, n_gemm, top_shapes = 0.0, 0.0, 0, []
+    kern = {}      # kernel name -> dict(ms, flop, launches, shapes)
     if rank == 0:
         for key, cnt in gemm_shapes.items():
-            t = pkg.ops.time_gemm_shape(key, reps=3, flush=flush)
-            fl = 2.0 * key[0] * key[1] * key[2]
-            gemm_ms += t * cnt
-            gemm_flop += fl * cnt
-            n_gemm += cnt
-            top_shapes.append((t * cnt, {'M': key[0], 'N': key[1], 'K': key[2], 'launches_per_step': cnt / args.steps,
-                                         'us': t * 1e3, 'tflops': fl / t / 1e9}))
-        top_shapes = [d for _, d in sorted(top_shapes, key=lambda x: -x[0])[:4]]
+            if key[0] == 'branch3':
+                _, M_, C_, N3_, is_vjp, save_pre = key
+                name = 'k_branch3'
+                t = pkg.ops.time_branch3_shape(key, reps=3, flush=flush)
+                fl = 2.0 * M_ * (N3_ * C_ + C_ * C_ + C_ * N3_)      # algorithmic: unpadded 9c tap columns
+                desc = {'M': M_, 'C': C_, 'taps': N3_, 'mode': 'vjp' if is_vjp else ('fwd+save' if save_pre else 'fwd')}
+            else:
+                name = 'k_gemm_tc3'
+                t = pkg.ops.time_gemm_shape(key, reps=3, flush=flush)
+                fl = 2.0 * key[0] * key[1] * key[2]
+                desc = {'M': key[0], 'N': key[1], 'K': key[2]}
+            k = kern.setdefault(name, {'ms': 0.0, 'flop': 0.0, 'launches': 0, 'shapes': []})
+            k['ms'] += t * cnt
+            k['flop'] += fl * cnt
+            k['launches'] += cnt
+            desc.update({'launches_per_step': cnt / args.steps, 'us': t * 1e3, 'tflops': fl / t / 1e9})
+            k['shapes'].append((t * cnt, desc))
 
     # ---------------- e2e: same step through the public API from pinned host buffers ----------------
     sync_all()
@@ -469,7 +478,23 @@ def main():
         pass
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF sustained (B200_PROFILING.md)'
-    achieved = (gemm_flop / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else 0.0
+    KNAMES = {'k_branch3': 'k_branch3 (fused 3-layer residual-branch tile kernel, tcgen05 3xTF32, operands in TMEM)',
+              'k_gemm_tc3': 'k_gemm_tc3 (tcgen05 3xTF32 residual-branch GEMM)'}
+
+    def roof(name):
+        k = kern[name]
+        ach = k['flop'] / (k['ms'] / 1e3) / 1e12 if k['ms'] > 0 else 0.0
+        return {'kernel': KNAMES[name], 'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': ach / peak_tf, 'traffic': None, 'peak_source': peak_src, 'launches': k['launches'],
+                'share_of_step': k['ms'] / ms_total if ms_total > 0 else None,
+                'top_shapes': [d for _, d in sorted(k['shapes'], key=lambda x: -x[0])[:4]],
+                'frac_of_3xtf32_ceiling': ach / (peak_tf / 6.0),
+                'note': 'achieved = sum(algorithmic flops) / sum(kernel time) over every launch of this kernel in '
+                        'the timed region; per-shape kernel times measured live with CUDA events (L2 flushed). '
+                        'Each product is 3 tf32 MMAs (fp32-accurate 3xTF32), so the mode ceiling is peak/6 = '
+                        '%.0f TFLOP/s' % (peak_tf / 6.0)}
+
+    order = sorted(kern, key=lambda n: -kern[n]['ms'])
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -479,17 +504,10 @@ def main():
         'gpu_launches': int(launches),
         'broyden_solves_per_sec': solves * world / (ms_total / 1e3),
         'solver_iterations_fwd_last_step': fwd_its[-1] if fwd_its else None,
-        'roofline': {'kernel': 'k_gemm_tc3 (tcgen05 3xTF32 residual-branch GEMM)', 'bound': 'tensor',
-                     'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                     'traffic': None, 'peak_source': peak_src, 'launches': n_gemm,
-                     'share_of_step': gemm_ms / ms_total if ms_total > 0 else None,
-                     'top_shapes': top_shapes,
-                     'frac_of_3xtf32_ceiling': achieved / (peak_tf / 6.0),
-                     'note': 'achieved = sum(2MNK) / sum(kernel time) over every tcgen05 GEMM launch of the timed '
-                             'region; per-shape kernel times measured live with CUDA events (L2 flushed). Each '
-                             'launch issues 3 tf32 MMAs per product (fp32-accurate 3xTF32), so the mode ceiling is '
-                             'peak/6 = %.0f TFLOP/s' % (peak_tf / 6.0)},
+        'roofline': roof(order[0]) if order else None,
     }
+    if len(order) > 1:
+        line['roofline_secondary'] = roof(order[1])
     if world == 1 and not args.no_cpu_baseline:
         try:
             res = run_cpu_reference(args.workload, 2, 1, args.cpu_batch)

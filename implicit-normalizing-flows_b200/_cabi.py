@@ -42,6 +42,7 @@ SIGNATURES = {
     'impflow_gemm_nt': (_i, [_c_fp, _ll, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
     'impflow_gemm_nt_tc': (_i, [_c_fp, _c_fp, _ll, _c_fp, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp,
                                 _ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
+    'impflow_branch3_tc': (_i, [_c_fp, _ll] + [_c_fp] * 13 + [_ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
     'impflow_gemm_tc_splits': (_i, [_ll, _i, _i]),
     'impflow_gemm_tc_set_wide_tiles': (_i, [_i]),
     'impflow_split_tf32': (_i, [_c_fp, _c_fp, _c_fp, _ll, _c_fp]),

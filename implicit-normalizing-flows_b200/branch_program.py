@@ -39,7 +39,10 @@ from . import _cabi, ops
 from .layers.base.activations import ReLU, Sin, Swish
 from .layers.base.mixed_lipschitz import InducedNormConv2d, InducedNormLinear
 
-__all__ = ['BranchProgram', 'compile_branch']
+__all__ = ['BranchProgram', 'compile_branch', 'FUSED3']
+
+# One-launch tile kernel for the 3-layer conv branch (csrc/branch_fused.cu); off = three GEMM launches.
+FUSED3 = {'on': True}
 
 
 def _round_up(n, m):
@@ -84,7 +87,7 @@ class _T(object):
 
 
 class _Saved(object):
-    __slots__ = ('rows', 'meta', 'M', 'pres', 'ains')
+    __slots__ = ('rows', 'meta', 'M', 'pres', 'ains', 'derivs')
 
 
 def _act_of(m):
@@ -349,12 +352,92 @@ class BranchProgram(object):
             split = ops.split_tf32(pre if next_is_pre else a_out)
         return pre, a_out, split
 
+
+    # ---------------------------------------------------------------- fused 3-layer tile kernel
+    def _fused3_ok(self, ws, meta):
+        """True when the whole branch is one impflow_branch3_tc launch (csrc/branch_fused.cu): the
+        3x3(c->C) / 1x1(C->C) / 3x3(C->c) conv stack with 9c <= 32 tap columns and C a multiple of 256
+        (the first-scale blocks of the image flows, implicit_flow.py:359-398)."""
+        if not FUSED3['on'] or self.is_linear or len(ws) != 3 or self.post_act is not None or meta[0] != 'conv':
+            return False
+        w0, w1, w2 = ws
+        a1, a2 = self.stages[1][0], self.stages[2][0]
+        if a1 is None or a2 is None or a1.kind != a2.kind:
+            return False
+        C = w1.cout
+        return (w0.kind == 'c3' and w0.a_type and w0.fwd_k == 32 and w0.cout == C and w0.fwd_split is not None
+                and w0.bwd_split is not None and w1.kind == 'mm' and w1.cin == C and C % 256 == 0
+                and w1.fwd_split is not None and w1.bwd_split is not None
+                and w2.kind == 'c3' and not w2.a_type and w2.cin == C and w2.bwd_k == 32 and 9 * w2.cout <= 32
+                and w2.fwd_split is not None and w2.bwd_split is not None)
+
+    def _forward_fused3(self, rows, meta, ws, save):
+        B, H, Wd = meta[1]
+        M = rows.shape[0]
+        w0, w1, w2 = ws
+        a1, a2 = self.stages[1][0], self.stages[2][0]
+        pres = [None] * 4
+        act0 = self.stages[0][0]
+        xin = rows
+        if act0 is not None:
+            pres[0] = rows
+            xin = ops.act_mul(rows, None, act0.kind, 0, act0.beta_sp())
+        x0 = ops.im2col3x3(xin.view(B, H, Wd, w0.cin), ld=32)
+        Y, pres[1], pres[2] = ops.branch3_tc(x0, w0.fwd_split, w1.fwd_split, w2.fwd_split, 9 * w2.cout,
+                                             bias1=w0.bias, bias2=w1.bias, act_kind=a1.kind, beta1=a1.beta_sp(),
+                                             beta2=a2.beta_sp(), save_pre=save)
+        out, _ = ops.col2im3x3(Y, B, H, Wd, w2.cout, w2.bias)
+        saved = None
+        if save:
+            saved = _Saved()
+            saved.rows, saved.meta, saved.M, saved.pres, saved.derivs = rows, meta, M, pres, {}
+            # layer inputs are not kept: backward_full / neumann re-evaluate them from the pre-activations
+            saved.ains = None
+        return self._from_rows(out.view(M, w2.cout), meta), saved
+
+    def _ains(self, saved):
+        """Layer-input handles of a saved forward (the fused forward keeps only the pre-activations)."""
+        if saved.ains is None:
+            acts = self._acts()
+            ains = []
+            for i in range(len(self.stages)):
+                src = saved.rows if i == 0 else saved.pres[i]
+                a = acts[i]
+                ains.append(_T(f=src if a is None else ops.act_mul(src, None, a.kind, 0, a.beta_sp())))
+            saved.ains = ains
+        return saved.ains
+
+    def _deriv(self, saved, i):
+        """act'(pres[i]) of the activation in front of layer i, evaluated once per saved forward."""
+        d = saved.derivs.get(i)
+        if d is None:
+            a = self.stages[i][0]
+            d = saved.derivs[i] = ops.act_mul(saved.pres[i], None, a.kind, 1, a.beta_sp())
+        return d
+
+    def _vjp_fused3(self, v, saved, ws):
+        B, H, Wd = saved.meta[1]
+        w0, w1, w2 = ws
+        t, _ = self._to_rows(v)
+        x0 = ops.im2col3x3(t.view(B, H, Wd, w2.cout), ld=32)
+        Y, _, _ = ops.branch3_tc(x0, w2.bwd_split, w1.bwd_split, w0.bwd_split, 9 * w0.cin,
+                                 mul1=self._deriv(saved, 2), mul2=self._deriv(saved, 1))
+        act0 = self.stages[0][0]
+        if act0 is not None:
+            out, _ = ops.col2im3x3(Y, B, H, Wd, w0.cin, None, act0.kind, act0.beta_sp(),
+                                   dmul_pre=saved.pres[0].view(B, H, Wd, w0.cin))
+        else:
+            out, _ = ops.col2im3x3(Y, B, H, Wd, w0.cin, None)
+        return self._from_rows(out.view(saved.M, w0.cin), saved.meta)
+
     # ---------------------------------------------------------------- forward
     def forward_saved(self, x, save=True):
         """(nnet(x), saved) without a graph; saved feeds vjp / backward_full / neumann."""
         rows, meta = self._to_rows(x)
         M = rows.shape[0]
         ws = self._prep(M, meta)
+        if self._fused3_ok(ws, meta):
+            return self._forward_fused3(rows, meta, ws, save)
         n = len(self.stages)
         pres = [None] * (n + 1)       # pres[i] = input of the activation in front of layer i (pres[n]: post act)
         ains = [None] * n             # ains[i] = input handle of layer i (after its activation)
@@ -380,7 +463,7 @@ class BranchProgram(object):
         saved = None
         if save:
             saved = _Saved()
-            saved.rows, saved.meta, saved.M, saved.pres, saved.ains = rows, meta, M, pres, ains
+            saved.rows, saved.meta, saved.M, saved.pres, saved.ains, saved.derivs = rows, meta, M, pres, ains, {}
         return self._from_rows(out, meta), saved
 
     def forward(self, x, save=False):
@@ -397,6 +480,8 @@ class BranchProgram(object):
             raise RuntimeError('BranchProgram.vjp: call forward(save=True) first')
         meta, M, pres = saved.meta, saved.M, saved.pres
         ws = self._prep(M)
+        if self._fused3_ok(ws, meta):
+            return self._vjp_fused3(v, saved, ws)
         n = len(self.stages)
         t, _ = self._to_rows(v)
         T = _T(f=t)
@@ -463,7 +548,7 @@ class BranchProgram(object):
 
     def backward_full(self, saved, gout, need_input_grad=True):
         """First-order backward of y = nnet(x): returns (g^T J or None, [dL/dp for p in parameters()])."""
-        meta, M, pres, ains = saved.meta, saved.M, saved.pres, saved.ains
+        meta, M, pres, ains = saved.meta, saved.M, saved.pres, self._ains(saved)
         ws = self._prep(M)
         n = len(self.stages)
         acts = self._acts()
@@ -500,7 +585,7 @@ class BranchProgram(object):
     def neumann(self, saved, w_vec, v_vec, seed_scale=None):
         """S_b = <w_b^T J_b, v_b> together with dS/dx and dS/dtheta of S = sum_b c_b S_b
         (c = seed_scale or 1), by one tangent sweep and one two-adjoint reverse sweep."""
-        meta, M, pres, ains = saved.meta, saved.M, saved.pres, saved.ains
+        meta, M, pres, ains = saved.meta, saved.M, saved.pres, self._ains(saved)
         ws = self._prep(M)
         n = len(self.stages)
         acts = self._acts()

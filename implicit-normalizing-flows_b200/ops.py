@@ -60,6 +60,41 @@ def time_gemm_shape(key, reps=5, flush=None):
     return sorted(times)[len(times) // 2]
 
 
+def time_branch3_shape(key, reps=5, flush=None):
+    """Median CUDA-event duration (ms) of one fused branch tile-kernel launch of the recorded shape."""
+    _, M, C, N3, is_vjp, save_pre = key
+    dev = torch.device('cuda', torch.cuda.current_device())
+    x0 = torch.zeros(M, 32, device=dev)
+    x0[:, :N3] = torch.randn(M, N3, device=dev)
+    W1 = split_tf32(torch.randn(C, 32, device=dev) / 5)
+    W2 = split_tf32(torch.randn(C, C, device=dev) / C ** 0.5)
+    W3 = split_tf32(torch.randn(N3, C, device=dev) / C ** 0.5)
+    b1, b2 = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    beta = torch.full((1,), 0.97, device=dev)
+    m1 = torch.randn(M, C, device=dev) if is_vjp else None
+    m2 = torch.randn(M, C, device=dev) if is_vjp else None
+    if flush is None:
+        flush = torch.empty(64 * 1024 * 1024, device=dev)
+    was = GEMM_PROFILE['on']
+    GEMM_PROFILE['on'] = False
+    times = []
+    for i in range(reps + 1):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if is_vjp:
+            branch3_tc(x0, W1, W2, W3, N3, mul1=m1, mul2=m2)
+        else:
+            branch3_tc(x0, W1, W2, W3, N3, bias1=b1, bias2=b2, act_kind=ACT_LIPSWISH, beta1=beta, beta2=beta,
+                       save_pre=save_pre)
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            times.append(e0.elapsed_time(e1))
+    GEMM_PROFILE['on'] = was
+    return sorted(times)[len(times) // 2]
+
+
 # While a caller differentiates w.r.t. ACTIVATIONS only (the vjp chains of the log-det estimators,
 # implicit_block.py:422,434,436), the parameter-gradient branches of the primitives' backward
 # passes (weight-gradient GEMMs with their transposes, bias column sums, LipSwish beta reductions)
@@ -292,6 +327,36 @@ def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, wa
                                     _cabi.ptr(dmul_pre, 'dmul', True), N, M, N, K, act_kind,
                                     _cabi.ptr(beta_sp, 'beta', True), _cabi.stream()), 'gemm_nt')
     return pre, act, None
+
+
+def branch3_tc(x0, W1s, W2s, W3s, N3, bias1=None, bias2=None, mul1=None, mul2=None, act_kind=ACT_NONE, beta1=None,
+               beta2=None, save_pre=False):
+    """Fused narrow -> C -> C -> narrow chain (csrc/branch_fused.cu): returns (Y (M,N3), pre1, pre2).
+
+    x0 (M, >=32) fp32; W1s/W2s/W3s = (hi, lo) tf32 planes of (C,32), (C,C), (N3,C) K-major weights.
+    mul_l given: psi_l(t) = t * mul_l (vjp through the activation); else psi_l(t) = act(t + bias_l)."""
+    x0 = x0.contiguous()
+    M, ldx = x0.shape
+    C = W2s[0].shape[0]
+    dev = x0.device
+    pre1 = torch.empty(M, C, device=dev, dtype=torch.float32) if save_pre else None
+    pre2 = torch.empty(M, C, device=dev, dtype=torch.float32) if save_pre else None
+    out = torch.zeros(M, N3, device=dev, dtype=torch.float32) if C > 256 else \
+        torch.empty(M, N3, device=dev, dtype=torch.float32)
+    _cabi.check(_lib().impflow_branch3_tc(
+        _cabi.ptr(x0), ldx, _cabi.ptr(W1s[0]), _cabi.ptr(W1s[1]), _cabi.ptr(W2s[0]), _cabi.ptr(W2s[1]),
+        _cabi.ptr(W3s[0]), _cabi.ptr(W3s[1]), _cabi.ptr(bias1, 'bias1', True), _cabi.ptr(bias2, 'bias2', True),
+        _cabi.ptr(mul1, 'mul1', True), _cabi.ptr(mul2, 'mul2', True), _cabi.ptr(pre1, 'pre1', True),
+        _cabi.ptr(pre2, 'pre2', True), _cabi.ptr(out), N3, M, C, N3, act_kind, _cabi.ptr(beta1, 'beta1', True),
+        _cabi.ptr(beta2, 'beta2', True), _cabi.stream()), 'branch3_tc')
+    if GEMM_PROFILE['on']:
+        record_branch3(M, C, N3, mul1 is not None, save_pre)
+    return out, pre1, pre2
+
+
+def record_branch3(M, C, N3, is_vjp, save_pre):
+    key = ('branch3', int(M), int(C), int(N3), bool(is_vjp), bool(save_pre))
+    GEMM_PROFILE['shapes'][key] = GEMM_PROFILE['shapes'].get(key, 0) + 1
 
 
 def sn_power_iter(W2d, u, v, n_iterations, atol, rtol):

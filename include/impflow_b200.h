@@ -173,6 +173,22 @@ int impflow_gemm_tc_set_wide_tiles(int on);
 /* a -> tf32 "hi" (round-to-nearest) and "lo" = a - hi planes used by the 3xTF32 backend. */
 int impflow_split_tf32(const float* a, float* hi, float* lo, long long n, void* stream);
 
+/* Fused residual-branch tile kernel for the 3x3 / 1x1 / 3x3 conv branch whose narrow side has 9*c <= 32
+ * tap columns (implicit_flow.py:359-398 at the first CIFAR scale), forward or transposed (vjp), one launch:
+ *     Y[M,N3] (+)= psi2( psi1( X0[M,32] W1[C,32]^T ) W2[C,C]^T ) W3[N3,C]^T
+ *   psi_l(t) = act(t + bias_l)  with pre_l_out <- t + bias_l (optional)     when mul_l == NULL   (forward)
+ *   psi_l(t) = t * mul_l[m,n]   (mul_l = act'(pre), evaluated once per saved forward)             (vjp)
+ * The C-wide intermediates stay in tensor memory; weights come as tf32 hi/lo planes (K-major rows);
+ * X0 is plain fp32 (im2col of the narrow tensor, ldx >= 32, columns >= 9c zero).  Needs C % 256 == 0 and
+ * N3 <= 32 (returns -2 otherwise).  When C > 256 the two 256-channel halves are summed into `out` with
+ * atomics: the caller zero-fills `out` (two addends on zero: order-independent, deterministic).
+ * Replaces three impflow_gemm_nt_tc launches + the plane traffic between them. */
+int impflow_branch3_tc(const float* x0, long long ldx, const float* W1_hi, const float* W1_lo, const float* W2_hi,
+                       const float* W2_lo, const float* W3_hi, const float* W3_lo, const float* bias1,
+                       const float* bias2, const float* mul1, const float* mul2, float* pre1_out, float* pre2_out,
+                       float* out, long long ldo, long long M, int C, int N3, int act_kind, const float* beta1,
+                       const float* beta2, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Induced 2-norm power iteration for a dense (out,in) matrix — replaces
  * mixed_lipschitz.py:85-123 (Linear) and :276-319 (1x1 conv).  One CTA, device-side early

@@ -389,6 +389,39 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_branch3_tc(self, x0, ldx, W1_hi, W1_lo, W2_hi, W2_lo, W3_hi, W3_lo, bias1, bias2, mul1, mul2, pre1_out,
+                           pre2_out, out, ldo, M, C, N3, act_kind, beta1, beta2, stream):
+        if C % 256 or N3 > 32 or ldx < 32 or ldx % 4 or ldo < N3:
+            self._err = b'branch3_tc: layout'
+            return -2
+        pl = lambda p, r, c: _f32(p, r * c).reshape(r, c).astype(np.float64)
+        x = _f32(x0, M * ldx).reshape(M, ldx)[:, :32]
+        xh = _tf32(x)
+        xl = (x - xh).astype(np.float32)
+
+        def mm(ah, al, bh, bl):
+            return (al.astype(np.float64) @ bh.T + ah.astype(np.float64) @ bl.T + ah.astype(np.float64) @ bh.T
+                    ).astype(np.float32)
+
+        def psi(acc, bias, mul, pre_out, beta):
+            if mul is not None:
+                return acc * _f32(mul, M * C).reshape(M, C)
+            v = acc + (_f32(bias, C) if _addr(bias) is not None else np.float32(0))
+            if _addr(pre_out) is not None:
+                _f32(pre_out, M * C).reshape(M, C)[:] = v
+            return _act(act_kind, v, 0, beta)
+
+        a1 = psi(mm(xh, xl, pl(W1_hi, C, 32), pl(W1_lo, C, 32)), bias1, mul1 if _addr(mul1) else None, pre1_out,
+                 _beta(beta1)).astype(np.float32)
+        a1h = _tf32(a1)
+        a2 = psi(mm(a1h, a1 - a1h, pl(W2_hi, C, C), pl(W2_lo, C, C)), bias2, mul2 if _addr(mul2) else None, pre2_out,
+                 _beta(beta2)).astype(np.float32)
+        a2h = _tf32(a2)
+        y = mm(a2h, a2 - a2h, pl(W3_hi, N3, C), pl(W3_lo, N3, C))
+        _f32(out, M * ldo).reshape(M, ldo)[:, :N3] = y
+        self.launches += 1
+        return 0
+
     # ---- spectral (csrc/spectral.cu) ----
     def impflow_sn_scale(self, W, sigma, coeff, out, scale_out, n, stream):
         sg = _f32(sigma, 1)[0]

@@ -101,6 +101,41 @@ def test_gemm_tcgen05_dmul(ops):
     ops.set_gemm_backend('auto')
 
 
+@pytest.mark.parametrize('M,C,N3,mode', [(128, 256, 27, 'fwd'), (300, 512, 27, 'fwd'), (1024, 512, 27, 'vjp'),
+                                         (128 * 160, 512, 32, 'fwd'), (128 * 301, 512, 27, 'vjp'),
+                                         (640, 256, 9, 'vjp')])
+def test_branch3_fused_chain(ops, M, C, N3, mode):
+    """Fused narrow->C->C->narrow tile kernel against the same chain in fp64 (forward with saved
+    pre-activations, and the vjp form with act' multipliers), incl. ragged M and multi-item CTAs."""
+    g = torch.Generator().manual_seed(M + C + N3)
+    x0 = torch.zeros(M, 32)
+    x0[:, :27] = torch.randn(M, 27, generator=g)
+    W1 = torch.randn(C, 32, generator=g) / 27 ** 0.5
+    W1[:, 27:] = 0
+    W2 = torch.randn(C, C, generator=g) / C ** 0.5
+    W3 = torch.randn(N3, C, generator=g) / C ** 0.5
+    b1, b2 = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    beta1, beta2 = torch.tensor([0.9]), torch.tensor([1.3])
+    dev = _dev()
+    sp = lambda t: ops.split_tf32(t.to(dev))
+    if mode == 'fwd':
+        y, p1, p2 = ops.branch3_tc(x0.to(dev), sp(W1), sp(W2), sp(W3), N3, bias1=b1.to(dev), bias2=b2.to(dev),
+                                   act_kind=ops.ACT_LIPSWISH, beta1=beta1.to(dev), beta2=beta2.to(dev), save_pre=True)
+        sw = lambda t, b: t * torch.sigmoid(t * b.double()) / 1.1
+        r1 = x0.double() @ W1.double().t() + b1.double()
+        r2 = sw(r1, beta1) @ W2.double().t() + b2.double()
+        ry = sw(r2, beta2) @ W3.double().t()
+        assert rel_err(p1.cpu(), r1) < 3e-6       # one 3xTF32 GEMM (same bound as test_gemm_tcgen05_3xtf32)
+        assert rel_err(p2.cpu(), r2) < 6e-6       # two chained
+    else:
+        m1 = torch.randn(M, C, generator=g)
+        m2 = torch.randn(M, C, generator=g)
+        y, _, _ = ops.branch3_tc(x0.to(dev), sp(W1), sp(W2), sp(W3), N3, mul1=m1.to(dev), mul2=m2.to(dev))
+        ry = (((x0.double() @ W1.double().t()) * m1.double()) @ W2.double().t() * m2.double()) @ W3.double().t()
+    assert y.shape == (M, N3)
+    assert rel_err(y.cpu(), ry) < 1e-5            # three chained: the north_star bound
+
+
 def test_activation_orders_vs_golden(ops, golden):
     fx = golden('activations')
     x = torch.from_numpy(fx['x']).cuda()

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests import cabi_emulator
+from tests import branch_cases, cabi_emulator
 from tests import imblock_cases as cases
 from tests.helpers import rel_err
 
@@ -149,57 +149,10 @@ def test_induced_norm_layers_vs_golden(golden):
     np.testing.assert_allclose(W.detach().numpy(), fx['c1_W_tol'], rtol=1e-5, atol=1e-6)
 
 
-def _branch_cases():
-    import impflow_b200
-    L = impflow_b200.layers
-    torch.manual_seed(0)
-    mk = lambda a, b, k, bias=True: L.base.get_conv2d(a, b, k, 1, k // 2, bias=bias, coeff=0.9, n_iterations=None,
-                                                      domain=2, codomain=2, atol=1e-3, rtol=1e-3)
-    lin = lambda a, b: L.base.get_linear(a, b, coeff=0.9, n_iterations=None, atol=1e-3, rtol=1e-3, domain=2, codomain=2)
-    return {
-        'cifar_lead': (torch.nn.Sequential(L.base.Swish(), mk(4, 32, 3), L.base.Swish(), mk(32, 32, 1), L.base.Swish(),
-                                           mk(32, 4, 3)), (2, 4, 8, 8)),
-        'cifar_nolead': (torch.nn.Sequential(mk(3, 32, 3), L.base.Swish(), mk(32, 32, 1), L.base.Swish(), mk(32, 3, 3)),
-                         (2, 3, 8, 8)),
-        'cls_relu': (torch.nn.Sequential(mk(8, 16, 3, False), torch.nn.ReLU(), mk(16, 8, 3, False), torch.nn.ReLU()),
-                     (2, 8, 8, 8)),
-        'mlp_sin': (torch.nn.Sequential(lin(6, 64), L.base.Sin(), lin(64, 64), L.base.Sin(), lin(64, 6)), (9, 6)),
-        'wide_both': (torch.nn.Sequential(mk(32, 64, 3), L.base.Swish(), mk(64, 32, 3)), (1, 32, 4, 4)),
-    }
-
-
-@pytest.mark.parametrize('name', ['cifar_lead', 'cifar_nolead', 'cls_relu', 'mlp_sin', 'wide_both'])
+@pytest.mark.parametrize('name', branch_cases.NAMES)
 @pytest.mark.parametrize('backend', ['simt', 'tc'])
 def test_branch_program_matches_module_autograd(name, backend):
-    """The fused graph-free forward / vjp equals the module's autograd forward / vjp."""
-    import impflow_b200
-    from impflow_b200.branch_program import compile_branch
-    impflow_b200.ops.set_gemm_backend(backend)
-    try:
-        net, shape = _branch_cases()[name]
-        x = torch.randn(*shape)
-        with torch.no_grad():
-            net(x)                                  # lazy u/v shaping
-            for p in net.parameters():
-                if p.dim() > 1:
-                    p.mul_(3.0)                     # make the spectral rescale active
-        prog = compile_branch(net)
-        assert prog is not None
-        xr = x.clone().requires_grad_(True)
-        y_ref = net(xr)
-        v = torch.randn_like(y_ref)
-        (vjp_ref,) = torch.autograd.grad(y_ref, xr, v)
-        with torch.no_grad():
-            y = prog.forward(x)
-            y2 = prog.forward(x, save=True)
-            vjp = prog.vjp(v)
-            vjp_again = prog.vjp(v)
-        assert rel_err(y, y_ref.detach()) < 2e-6
-        assert rel_err(y2, y_ref.detach()) < 2e-6
-        assert rel_err(vjp, vjp_ref) < 5e-6
-        assert rel_err(vjp_again, vjp_ref) < 5e-6
-    finally:
-        impflow_b200.ops.set_gemm_backend('auto')
+    branch_cases.case_matches_module_autograd(name, backend)
 
 
 def test_branch_program_rejects_unknown_modules():
@@ -208,59 +161,16 @@ def test_branch_program_rejects_unknown_modules():
     assert compile_branch(torch.nn.Tanh()) is None
 
 
-@pytest.mark.parametrize('name', ['cifar_lead', 'cifar_nolead', 'cls_relu', 'mlp_sin', 'wide_both'])
+@pytest.mark.parametrize('name', branch_cases.NAMES)
 @pytest.mark.parametrize('backend', ['simt', 'tc'])
 def test_branch_program_gradients_match_autograd(name, backend):
-    """backward_full (first order) and neumann (hand-derived double backward) against autograd through
-    the differentiable kernel primitives."""
-    import impflow_b200
-    from impflow_b200.branch_program import compile_branch
-    impflow_b200.ops.set_gemm_backend(backend)
-    try:
-        net, shape = _branch_cases()[name]
-        x = torch.randn(*shape)
-        with torch.no_grad():
-            net(x)
-            for p in net.parameters():
-                if p.dim() > 1:
-                    p.mul_(3.0)
-        prog = compile_branch(net)
-        params = list(net.parameters())
-        # ---- first-order backward
-        xr = x.clone().requires_grad_(True)
-        y = net(xr)
-        gout = torch.randn_like(y)
-        ref = torch.autograd.grad(y, [xr] + params, gout, allow_unused=True)
-        with torch.no_grad():
-            _, saved = prog.forward_saved(x)
-            gx, pg = prog.backward_full(saved, gout)
-        assert rel_err(gx, ref[0]) < 1e-5
-        for p, g, r in zip(params, pg, ref[1:]):
-            assert (g is None) == (r is None)
-            if r is not None:
-                assert rel_err(g, r) < 2e-5, tuple(p.shape)
-        # ---- Neumann estimator: S = <w^T J, v>, dS/dx, dS/dtheta
-        w, v = torch.randn_like(y), torch.randn_like(x)
-        xr = x.clone().requires_grad_(True)
-        y = net(xr)
-        (wJ,) = torch.autograd.grad(y, xr, w, create_graph=True)
-        S_ref = (wJ.reshape(x.shape[0], -1) * v.reshape(x.shape[0], -1)).sum(1)
-        ref = torch.autograd.grad(S_ref.sum(), [xr] + params, allow_unused=True)
-        with torch.no_grad():
-            _, saved = prog.forward_saved(x)
-            S, gx, pg = prog.neumann(saved, w, v)
-        assert rel_err(S, S_ref.detach()) < 1e-5
-        if ref[0] is not None and float(ref[0].norm()) > 0:
-            assert rel_err(gx, ref[0]) < 2e-5
-        else:
-            assert float(gx.norm()) < 1e-6
-        for p, g, r in zip(params, pg, ref[1:]):
-            if r is None or float(r.norm()) == 0:
-                assert g is None or float(g.norm()) < 1e-6
-            else:
-                assert rel_err(g, r) < 5e-5, tuple(p.shape)
-    finally:
-        impflow_b200.ops.set_gemm_backend('auto')
+    branch_cases.case_gradients_match_autograd(name, backend)
+
+
+def test_fused3_tile_kernel_is_taken():
+    assert branch_cases.case_fused3_is_taken('fused3_lead') == 2       # forward + vjp
+    assert branch_cases.case_fused3_is_taken('fused3_512') == 2
+    assert branch_cases.case_fused3_is_taken('cifar_lead') == 0        # width 32: three GEMMs
 
 
 def test_fused_paths_are_taken(golden, monkeypatch):
