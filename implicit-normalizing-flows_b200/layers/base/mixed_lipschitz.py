@@ -130,7 +130,9 @@ class InducedNormLinear(nn.Module):
             if n_iterations is None and (atol is None or rtol is None):
                 raise ValueError('Need one of n_iteration or (atol, rtol).')
             with torch.no_grad():
-                ops.sn_power_iter(self.weight.detach(), self.u, self.v, n_iterations, atol, rtol)
+                sig, _ = ops.sn_power_iter(self.weight.detach(), self.u, self.v, n_iterations, atol, rtol)
+            if not torch.is_grad_enabled():
+                return ops.sn_rescale(self.weight.detach(), sig, self.coeff, scale_out=self.scale)
         sigma = _Sigma.apply(self.weight, self.u, self.v)
         with torch.no_grad():
             self.scale.copy_(sigma[0])
@@ -308,7 +310,10 @@ class InducedNormConv2d(nn.Module):
         W2 = self.weight.view(self.out_channels, self.in_channels)
         if update:
             with torch.no_grad():
-                ops.sn_power_iter(W2.detach(), self.u, self.v, n_iterations, atol, rtol)
+                sig, _ = ops.sn_power_iter(W2.detach(), self.u, self.v, n_iterations, atol, rtol)
+            if not torch.is_grad_enabled():
+                return ops.sn_rescale(W2.detach(), sig, self.coeff, scale_out=self.scale).view(
+                    self.out_channels, self.in_channels, 1, 1)
         sigma = _Sigma.apply(W2, self.u, self.v)
         with torch.no_grad():
             self.scale.copy_(sigma[0])
@@ -316,6 +321,19 @@ class InducedNormConv2d(nn.Module):
 
     def _compute_weight_kxk(self, update, n_iterations, atol, rtol):
         u, v = self.u, self.v
+        if update and self.kernel_size == (3, 3):
+            # the whole iteration (and sigma) in one cooperative launch; no host synchronisation
+            h, w = self._spatial()
+            tol_mode = n_iterations is None and atol is not None and rtol is not None
+            res = None
+            if tol_mode or n_iterations is not None:
+                with torch.no_grad():
+                    res = ops.sn_power_iter_conv(self.weight.detach(), self.u, self.v, h, w,
+                                                 None if tol_mode else n_iterations, atol, rtol)
+            if res is not None:
+                update = False
+                if not torch.is_grad_enabled():      # update_lipschitz: nothing differentiates this result
+                    return ops.sn_rescale(self.weight.detach(), res[0], self.coeff, scale_out=self.scale)
         if update:
             max_itrs = 200 if n_iterations is None else n_iterations
             with torch.no_grad():

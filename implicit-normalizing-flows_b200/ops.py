@@ -373,6 +373,35 @@ def sn_power_iter(W2d, u, v, n_iterations, atol, rtol):
     return sigma, iters
 
 
+def sn_power_iter_conv(W, u, v, h, w, n_iterations, atol, rtol):
+    """In-place power iteration of the 3x3 conv W (Cout,Cin,3,3) on one h x w image: one cooperative launch.
+    Returns (sigma (1,), iters (1,) int32) device tensors, or None when the shape is not supported by the
+    kernel (narrow side too large for shared memory) and the caller has to iterate itself."""
+    W = W.contiguous()
+    co, ci = W.shape[0], W.shape[1]
+    n_ws = int(_lib().impflow_sn_conv_workspace_floats(co, ci, h, w))
+    if n_ws == 0:
+        return None
+    ws = torch.empty(n_ws, device=W.device, dtype=torch.float32)
+    sigma = torch.empty(1, device=W.device, dtype=torch.float32)
+    iters = torch.zeros(1, device=W.device, dtype=torch.int32)
+    n_it = -1 if n_iterations is None else int(n_iterations)
+    _cabi.check(_lib().impflow_sn_power_iter_conv3x3(
+        _cabi.ptr(W), _cabi.ptr(u), _cabi.ptr(v), _cabi.ptr(sigma), _cabi.iptr(iters), co, ci, h, w, n_it,
+        float(atol if atol is not None else 0.0), float(rtol if rtol is not None else 0.0), _cabi.ptr(ws),
+        _cabi.stream()), 'sn_power_iter_conv3x3')
+    return sigma, iters
+
+
+def sn_rescale(W, sigma, coeff, scale_out=None):
+    """W / max(1, sigma/coeff) with sigma a device scalar (no graph)."""
+    W = W.contiguous()
+    out = torch.empty_like(W)
+    _cabi.check(_lib().impflow_sn_scale(_cabi.ptr(W), _cabi.ptr(sigma), float(coeff), _cabi.ptr(out),
+                                        _cabi.ptr(scale_out, 'scale', True), W.numel(), _cabi.stream()), 'sn_scale')
+    return out
+
+
 def _flat_dot(a, b):
     """<a, b> over all elements as a 1-element device tensor.  Large operands are viewed as 256 rows so
     that the row-dot kernel spreads over the SMs (one CTA per row), then the 256 partials are summed."""

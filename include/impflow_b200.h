@@ -198,6 +198,17 @@ int impflow_branch3_tc(const float* x0, long long ldx, const float* W1_hi, const
 int impflow_sn_power_iter(const float* W, float* u, float* v, float* sigma, int* iters, int out_f,
                           int in_f, int n_iterations, float atol, float rtol, void* stream);
 
+/* The same power iteration for a 3x3 / stride 1 / pad 1 convolution acting on ONE H x W image — replaces the
+ * host loop of mixed_lipschitz.py:328-386 (_compute_weight_kxk: 1-sample conv2d / conv_transpose2d,
+ * normalisations and a host-synchronising tolerance test per iteration) with ONE cooperative launch.
+ * W is [Cout][Cin][3][3]; u (Cout*H*W) and v (Cin*H*W) are flat CHW vectors updated in place;
+ * sigma[0] = <u, conv(v)>; iters[0] = iterations used; n_iterations < 0 = tolerance mode (cap 200).
+ * `ws` holds impflow_sn_conv_workspace_floats() floats; that function returns 0 (and the solver -2) when the
+ * narrow side of the layer does not fit in shared memory (the caller then keeps its own loop). */
+size_t impflow_sn_conv_workspace_floats(int Cout, int Cin, int H, int W);
+int impflow_sn_power_iter_conv3x3(const float* W, float* u, float* v, float* sigma, int* iters, int Cout, int Cin,
+                                  int H, int Wd, int n_iterations, float atol, float rtol, float* ws, void* stream);
+
 /* Soft spectral rescale with sigma on the device: out = W / max(1, sigma[0]/coeff), scale_out[0] =
  * sigma[0] (mixed_lipschitz.py:125-131), and its gradient chain with D = d sigma / d W (sigma = <W,D>
  * is linear in W; u, v constant):  out = s*G + gw_dot[0] * ds/dsigma * D,  gw_dot = <G, W>. */

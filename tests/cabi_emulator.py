@@ -466,6 +466,40 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_sn_conv_workspace_floats(self, Cout, Cin, H, W):
+        narrow = min(Cout, Cin) * H * W
+        return 0 if 2 * narrow * 4 > 160 * 1024 else 128 * narrow + narrow + 5 * 128
+
+    def impflow_sn_power_iter_conv3x3(self, W, u, v, sigma, iters, Cout, Cin, H, Wd, n_iterations, atol, rtol, ws,
+                                      stream):
+        import torch.nn.functional as F
+        Wt = torch.from_numpy(_f32(W, Cout * Cin * 9).reshape(Cout, Cin, 3, 3).copy())
+        uv, vv = _f32(u, Cout * H * Wd), _f32(v, Cin * H * Wd)
+        un, vn = torch.from_numpy(uv.copy()), torch.from_numpy(vv.copy())
+        nrm = lambda t: t / max(float(t.norm()), 1e-12)
+        conv = lambda t: F.conv2d(t.view(1, Cin, H, Wd), Wt, padding=1).reshape(-1)
+        convT = lambda t: F.conv_transpose2d(t.view(1, Cout, H, Wd), Wt, padding=1).reshape(-1)
+        tol_mode = n_iterations < 0
+        used = 0
+        for _ in range(200 if tol_mode else n_iterations):
+            ou, ov = un, vn
+            un = nrm(conv(vn))
+            vn = nrm(convT(un))
+            used += 1
+            if tol_mode:
+                err_u = float((un - ou).norm()) / un.numel() ** 0.5
+                err_v = float((vn - ov).norm()) / vn.numel() ** 0.5
+                if err_u < atol + rtol * float(un.max()) and err_v < atol + rtol * float(vn.max()):
+                    break
+        _f32(sigma, 1)[0] = np.float32(float(torch.dot(un, conv(vn))))
+        if _addr(iters) is not None:
+            np.ctypeslib.as_array((ctypes.c_int32 * 1).from_address(_addr(iters)))[0] = used
+        if used > 0:
+            uv[:] = un.numpy()
+            vv[:] = vn.numpy()
+        self.launches += 1
+        return 0
+
 
 def install(monkeypatch):
     """Route the product's C-ABI calls to the numpy emulation for the duration of one test."""

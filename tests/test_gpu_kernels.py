@@ -224,6 +224,37 @@ def test_sn_power_iter_vs_golden(ops, golden):
     assert int(iters.item()) == used
 
 
+@pytest.mark.parametrize('co,ci,h,w,n_it', [(512, 3, 32, 32, None), (3, 512, 32, 32, None), (512, 12, 16, 16, 3),
+                                            (48, 512, 8, 8, None), (32, 4, 8, 8, 5), (5, 40, 6, 7, None),
+                                            (16, 16, 8, 8, None), (512, 3, 32, 32, 0)])
+def test_sn_power_iter_conv_vs_oracle(ops, co, ci, h, w, n_it):
+    """One-launch cooperative conv power iteration against the oracle's loop (mixed_lipschitz.py:328-386):
+    both layer orientations (wide output / wide input), tolerance and fixed-count modes, odd image shapes."""
+    g = torch.Generator().manual_seed(co * 7 + ci)
+    W = torch.randn(co, ci, 3, 3, generator=g) / (3.0 * ci ** 0.5)
+    u0 = F.normalize(torch.randn(co * h * w, generator=g), dim=0)
+    v0 = F.normalize(torch.randn(ci * h * w, generator=g), dim=0)
+    tol = 1e-3 if n_it is None else None
+    if n_it == 0:
+        u_ref, v_ref, used = u0, v0, 0
+    else:
+        u_ref, v_ref, used = orc.power_iterate_conv(W, u0.clone(), v0.clone(), (ci, h, w), 1, 1, n_it, tol, tol)
+    s_ref = orc.sigma_conv(W, u_ref, v_ref, (ci, h, w), 1, 1)
+    u, v = u0.clone().cuda(), v0.clone().cuda()
+    res = ops.sn_power_iter_conv(W.cuda(), u, v, h, w, n_it, tol, tol)
+    assert res is not None
+    sigma, iters = res
+    assert int(iters.item()) == used
+    assert rel_err(u.cpu(), u_ref) < 1e-5
+    assert rel_err(v.cpu(), v_ref) < 1e-5
+    assert abs(float(sigma.item()) - float(s_ref)) < 1e-5 * max(1.0, abs(float(s_ref)))
+
+
+def test_sn_power_iter_conv_unsupported_shape(ops):
+    assert ops.sn_power_iter_conv(torch.randn(64, 64, 3, 3).cuda(), torch.randn(64 * 1024).cuda(),
+                                  torch.randn(64 * 1024).cuda(), 32, 32, None, 1e-3, 1e-3) is None
+
+
 @pytest.mark.parametrize('tag', ['small', 'wide', 'capped', 'long', 'protbreak'])
 def test_broyden_vs_golden(golden, tag):
     import impflow_b200
