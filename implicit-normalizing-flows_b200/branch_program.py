@@ -67,6 +67,10 @@ class _Act(object):
         return self._beta
 
 
+# epilogue stub: the dmul operand already holds act'(pre) (see BranchProgram._deriv)
+_MULT = _Act(ops.ACT_MULTIPLIER)
+
+
 class _Weights(object):
     """Effective weights of one layer in the layouts the fused path needs (fp32 + optional planes)."""
     __slots__ = ('fwd', 'fwd_split', 'bwd', 'bwd_split', 'bias', 'kind', 'cin', 'cout', 'fwd_k', 'bwd_k', 'a_type',
@@ -411,7 +415,7 @@ class BranchProgram(object):
         """act'(pres[i]) of the activation in front of layer i, evaluated once per saved forward."""
         d = saved.derivs.get(i)
         if d is None:
-            a = self.stages[i][0]
+            a = self._acts()[i]
             d = saved.derivs[i] = ops.act_mul(saved.pres[i], None, a.kind, 1, a.beta_sp())
         return d
 
@@ -490,10 +494,10 @@ class BranchProgram(object):
         for i in range(n - 1, -1, -1):
             w = ws[i]
             act = self.stages[i][0]            # activation in front of layer i: multiply by act'(pres[i])
-            dm = pres[i] if act is not None else None
+            dm = self._deriv(saved, i) if act is not None else None      # evaluated once per saved forward
             want_split = i > 0 and self._wants_planes(ws[i - 1], True, w.cin)
-            pre, _, split = self._apply(w, T, meta, True, act=act, want_pre=not want_split, dmul_pre=dm,
-                                        want_split=want_split)
+            pre, _, split = self._apply(w, T, meta, True, act=(_MULT if act is not None else None),
+                                        want_pre=not want_split, dmul_pre=dm, want_split=want_split)
             T = _T(f=pre, s=split)
         return self._from_rows(T.f32(), meta)
 
@@ -571,8 +575,8 @@ class BranchProgram(object):
                 break
             if act is not None:
                 want_raw = act.module is not None
-                pbar, abar, _ = self._apply(w, G, meta, True, act=act, want_pre=True, want_act=want_raw,
-                                            dmul_pre=pres[i])
+                pbar, abar, _ = self._apply(w, G, meta, True, act=_MULT, want_pre=True, want_act=want_raw,
+                                            dmul_pre=self._deriv(saved, i))
                 if want_raw:
                     betabars[i] = ops.act_beta_grad(pres[i], abar, 0, act.beta_sp())
             else:
@@ -605,8 +609,9 @@ class BranchProgram(object):
             tas[i] = TA
             want_split = (not last) and self._wants_planes(ws[i + 1], False, w.cout)
             if nxt is not None:
-                prod, raw, split = self._apply(w, TA, meta, False, act=nxt, want_pre=(last or not want_split),
-                                               want_act=True, dmul_pre=pres[i + 1], want_split=want_split)
+                prod, raw, split = self._apply(w, TA, meta, False, act=_MULT, want_pre=(last or not want_split),
+                                               want_act=True, dmul_pre=self._deriv(saved, i + 1),
+                                               want_split=want_split)
                 tps[i + 1] = raw
                 TA = _T(f=prod, s=split)
             else:
@@ -640,8 +645,8 @@ class BranchProgram(object):
                 abar, _, _ = self._apply(w, Ybar, meta, True, want_pre=True)
             if act is not None:
                 # one launch: tbar_p = phi'(p) * (W^T Tbar) in `prod`, the raw W^T Tbar in `raw`
-                prod, tabar, _ = self._apply(w, Tbar, meta, True, act=act, want_pre=(i > 0), want_act=True,
-                                             dmul_pre=pres[i])
+                prod, tabar, _ = self._apply(w, Tbar, meta, True, act=_MULT, want_pre=(i > 0), want_act=True,
+                                             dmul_pre=self._deriv(saved, i))
                 if act.module is not None:
                     gb = ops.act_beta_grad(pres[i], tabar, 1, act.beta_sp(), g2=tps[i])
                     if abar is not None:

@@ -103,16 +103,6 @@ __device__ __forceinline__ void st16(float* p, const float* v) {
   for (int j = 0; j < 4; ++j) p4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-// LipSwish x*sigmoid(beta*x)/1.1 on the SFU fast paths (ex2.approx + rcp.approx: ~3 ulp, the same order
-// as the fp32 accumulation error of the GEMMs around it); this is the inner loop of the transform warps.
-__device__ __forceinline__ float lipswish_fast(float x, float beta) {
-  float e, s;
-  const float t = fminf(-1.4426950408889634f * beta * x, 126.f);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.f + e));
-  return x * s * (1.f / 1.1f);
-}
-
 // psi: 16 accumulator values of one row -> the next layer's operand values.
 template <int ACT>
 __device__ __forceinline__ void psi16(const uint32_t* r, float* a, const float* bias, const float* mul, bool has_mul,

@@ -80,6 +80,16 @@ __device__ __forceinline__ float act_eval(float x, int order, float beta) {
   }
 }
 
+// LipSwish x*sigmoid(beta*x)/1.1 on the SFU fast paths (ex2.approx + rcp.approx: ~3 ulp, the same order
+// as the fp32 accumulation error of the GEMMs around it); used by the GEMM / tile-kernel epilogues.
+__device__ __forceinline__ float lipswish_fast(float x, float beta) {
+  float e, s;
+  const float t = fminf(-1.4426950408889634f * beta * x, 126.f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.f + e));
+  return x * s * (1.f / 1.1f);
+}
+
 // d/d(beta) of the order-th x-derivative of LipSwish (beta = softplus(raw beta)).
 __device__ __forceinline__ float lipswish_dbeta(float x, int order, float beta) {
   const float bx = beta * x;
@@ -100,6 +110,7 @@ __device__ __forceinline__ float act_dispatch(int kind, float x, int order, floa
     case IMPFLOW_ACT_SIN: return act_eval<IMPFLOW_ACT_SIN>(x, order, beta);
     case IMPFLOW_ACT_LIPSWISH: return act_eval<IMPFLOW_ACT_LIPSWISH>(x, order, beta);
     case IMPFLOW_ACT_RELU: return act_eval<IMPFLOW_ACT_RELU>(x, order, beta);
+    case IMPFLOW_ACT_MULTIPLIER: return x;      // the stored value IS the derivative factor
     default: return act_eval<IMPFLOW_ACT_NONE>(x, order, beta);
   }
 }

@@ -188,8 +188,15 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
       for (int c = chunk0; c < BN / 32; c += TC_EPI_WARPS / 4) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-        tmem_ld32(taddr, r);
         const int n0 = n_base + c * 32;
+        // the act' operand is requested before the accumulator read so that its latency hides behind it
+        float dm[32];
+        const bool dm_vec = e.dmul_pre != nullptr && splits == 1 && m < M && (n0 + 32 <= N) && ((e.ldc & 7) == 0);
+        if (dm_vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) ld_global_v8(e.dmul_pre + m * e.ldc + n0 + j, dm + j);
+        }
+        tmem_ld32(taddr, r);
         if (splits > 1) {
           if (m < M && n0 < N) {
             float* dst = splitk_ws + ((long long)ks * M + m) * N + n0;
@@ -223,7 +230,8 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
             for (int j = 0; j < 32; j += 8) {
               float p[8];
               if (full_vec) {
-                ld_global_v8(e.dmul_pre + row + n0 + j, p);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) p[u] = dm[j + u];
               } else {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) p[u] = (n0 + j + u < N) ? e.dmul_pre[row + n0 + j + u] : 0.f;
@@ -249,7 +257,13 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
               }
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_dispatch(e.act_kind, v[j], 0, e.beta);
+            if (e.act_kind == IMPFLOW_ACT_LIPSWISH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = lipswish_fast(v[j], e.beta);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_dispatch(e.act_kind, v[j], 0, e.beta);
+            }
           }
           float* main_out = (e.dmul_pre != nullptr) ? e.pre_out : e.act_out;
           if (main_out != nullptr) {

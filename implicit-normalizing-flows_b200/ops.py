@@ -13,6 +13,7 @@ import torch
 from . import _cabi
 
 ACT_NONE, ACT_SIN, ACT_LIPSWISH, ACT_RELU = 0, 1, 2, 3
+ACT_MULTIPLIER = 4      # dmul epilogues only: the dmul operand already holds act'(pre)
 
 # GEMM backend policy: 'auto' uses the tcgen05 3xTF32 kernel whenever its layout constraints hold
 # and the problem is big enough to fill tiles; 'simt' forces the exact-fp32 CUDA-core kernel.

@@ -31,6 +31,9 @@ extern "C" {
 #define IMPFLOW_ACT_SIN 1
 #define IMPFLOW_ACT_LIPSWISH 2
 #define IMPFLOW_ACT_RELU 3
+/* pseudo kind for the dmul_pre epilogues: dmul_pre already holds the multiplier act'(pre) (evaluated once per
+ * saved forward by impflow_act_mul order 1), so the epilogue is one multiply instead of an exp + divide */
+#define IMPFLOW_ACT_MULTIPLIER 4
 
 int impflow_version(void);
 const char* impflow_last_error(void);

@@ -16,6 +16,14 @@ for key in [(65536, 512, 512, False, True, False, False, False),   # act only
             (65536, 512, 32, False, False, True, True, False),
             (65536, 32, 512, True, False, False, False, False),    # conv3 (N=27 padded)
             (16384, 512, 512, False, False, False, True, False),
+            (16384, 512, 512, False, False, True, True, False),
+            (16384, 512, 512, True, False, False, False, False),
+            (16384, 512, 128, False, False, False, True, False),
+            (16384, 512, 128, False, False, True, True, False),
+            (16384, 512, 128, True, False, False, False, False),
+            (16384, 128, 512, True, False, False, False, False),
+            (4096, 512, 448, False, False, True, True, False),
+            (4096, 448, 512, True, False, False, False, False),
             (4096, 512, 512, False, False, False, True, False),
             (512, 512, 65536, True, False, False, False, True),    # conv2 weight gradient (split-K)
             (32, 512, 65536, True, False, False, False, True)]:

@@ -13,7 +13,7 @@ import math
 import numpy as np
 import torch
 
-ACT_NONE, ACT_SIN, ACT_LIPSWISH, ACT_RELU = 0, 1, 2, 3
+ACT_NONE, ACT_SIN, ACT_LIPSWISH, ACT_RELU, ACT_MULTIPLIER = 0, 1, 2, 3, 4
 
 
 def _addr(p):
@@ -39,6 +39,9 @@ def _act(kind, x, order, beta):
         two_pi = np.float32(2 * math.pi)
         s, c = np.sin(two_pi * x), np.cos(two_pi * x)
         return [s / np.float32(math.pi) * np.float32(0.5), c, -two_pi * s, -two_pi * two_pi * c][order]
+    if kind == ACT_MULTIPLIER:
+        assert order == 1
+        return x
     if kind == ACT_RELU:
         return [np.maximum(x, 0), (x > 0).astype(np.float32), np.zeros_like(x), np.zeros_like(x)][order]
     bx = beta * x
