@@ -38,6 +38,8 @@ SIGNATURES = {
     'impflow_colsum': (_i, [_c_fp, _c_fp, _c_fp, _ll, _i, _c_fp]),
     'impflow_transpose': (_i, [_c_fp, _c_fp, _ll, _ll, _c_fp]),
     'impflow_im2col3x3': (_i, [_c_fp, _c_fp, _i, _i, _i, _i, _i, _c_fp]),
+    'impflow_im2col3x3_split': (_i, [_c_fp, _c_fp, _c_fp, _i, _i, _i, _i, _i, _c_fp]),
+    'impflow_transpose_split': (_i, [_c_fp, _c_fp, _c_fp, _ll, _ll, _c_fp]),
     'impflow_col2im3x3': (_i, [_c_fp, _i, _i, _i, _i, _c_fp, _c_fp, _c_fp, _c_fp, _i, _c_fp, _c_fp]),
     'impflow_gemm_nt': (_i, [_c_fp, _ll, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
     'impflow_gemm_nt_tc': (_i, [_c_fp, _c_fp, _ll, _c_fp, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp,

@@ -330,7 +330,10 @@ class BranchProgram(object):
         if w.kind == 'mm' or self._im2col_first(w, transpose):
             if w.kind == 'c3':
                 B, H, Wd = meta[1]
-                A, A_split = ops.im2col3x3(X.f32().view(B, H, Wd, cin), ld=Wk), None
+                if Wsp is not None:      # patches written directly as the GEMM's tf32 planes
+                    A, A_split = None, ops.im2col3x3_split(X.f32().view(B, H, Wd, cin), ld=Wk)
+                else:
+                    A, A_split = ops.im2col3x3(X.f32().view(B, H, Wd, cin), ld=Wk), None
             else:
                 A_split = X.s if (X.s is not None and Wsp is not None and X.s[0].shape[1] == Wk) else None
                 A = self._pad_cols(X.f32(), Wk) if A_split is None else None
@@ -512,8 +515,7 @@ class BranchProgram(object):
                 Gm, Am = ops.im2col3x3(G.view(B, H, Wd, w.cout), ld=9 * w.cout), self._pad_cols(Xin.f32(), w.fwd_k)
         else:
             Gm, Am = G, self._pad_cols(Xin.f32(), w.fwd_k)
-        out, _, _ = ops.gemm_nt(ops.transpose2d(Gm), ops.transpose2d(Am))
-        return out
+        return ops.wgrad_gemm(Gm, Am)
 
     @staticmethod
     def _to_weight_layout(w, Wbar):

@@ -211,29 +211,7 @@ k_transpose(const float* __restrict__ a, float* __restrict__ out, long long M, l
 }
 
 // ---- im2col / col2im for NHWC 3x3 stride 1 pad 1 -------------------------------------------------
-// col row p=(b,y,x) has 9*C entries ordered (ky,kx,c).
-__global__ void __launch_bounds__(256)
-k_im2col3x3(const float* __restrict__ x, float* __restrict__ col, int B, int H, int W, int C, int ld) {
-  const long long total = (long long)B * H * W * ld;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int kcol = (int)(i % ld);
-    const long long p = i / ld;
-    if (kcol >= 9 * C) {
-      col[i] = 0.f;
-      continue;
-    }
-    const int c = kcol % C;
-    const int tap = kcol / C;
-    const int xx = (int)(p % W);
-    const int yy = (int)((p / W) % H);
-    const long long b = p / ((long long)W * H);
-    const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
-    float v = 0.f;
-    if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = x[((b * H + sy) * W + sx) * C + c];
-    col[i] = v;
-  }
-}
+// col row p=(b,y,x) has 9*C entries ordered (ky,kx,c): see k_im2col3x3_rows below.
 
 // x[p,c] = sum_tap col[p - off(tap), tap, c] followed by the fused epilogue.
 __global__ void __launch_bounds__(256)
@@ -268,6 +246,90 @@ k_split_tf32(const float* __restrict__ a, float* __restrict__ hi, float* __restr
     const float hf = __uint_as_float(h);
     hi[i] = hf;
     lo[i] = v - hf;
+  }
+}
+__device__ __forceinline__ void split1(float v, float& h, float& l) {
+  uint32_t hb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+  h = __uint_as_float(hb);
+  l = v - h;
+}
+__global__ void __launch_bounds__(256)
+k_split_tf32_v4(const float4* __restrict__ a, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = a[i];
+    float4 h, l;
+    split1(v.x, h.x, l.x);
+    split1(v.y, h.y, l.y);
+    split1(v.z, h.z, l.z);
+    split1(v.w, h.w, l.w);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// out_hi/out_lo[n,m] = tf32 split of a[m,n]: the transposed operand planes of the weight-gradient GEMMs
+// in one pass (instead of transpose, then split).  64 x 32 tiles, 128-byte segments on both sides.
+__global__ void __launch_bounds__(256)
+k_transpose_split(const float* __restrict__ a, float* __restrict__ out_hi, float* __restrict__ out_lo, long long M,
+                  int N) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long m_tiles = (M + 63) / 64;
+  const int n_tiles = (N + 31) / 32;
+  for (long long t = blockIdx.x; t < m_tiles * n_tiles; t += gridDim.x) {
+    const long long m0 = (t / n_tiles) * 64;
+    const int n0 = (int)(t % n_tiles) * 32;
+    for (int r = ty; r < 64; r += 8)
+      tile[r][tx] = (m0 + r < M && n0 + tx < N) ? a[(m0 + r) * N + n0 + tx] : 0.f;
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      if (n0 + r < N) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const long long m = m0 + half * 32 + tx;
+          if (m < M) {
+            float h, l;
+            split1(tile[half * 32 + tx][r], h, l);
+            out_hi[(long long)(n0 + r) * M + m] = h;
+            out_lo[(long long)(n0 + r) * M + m] = l;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// im2col, one warp per pixel row: the 9 taps of a pixel are 9 contiguous C-float segments of the image
+// and one contiguous ld-float row of the patch matrix; optional tf32 hi/lo planes instead of fp32.
+__global__ void __launch_bounds__(256)
+k_im2col3x3_rows(const float* __restrict__ x, float* __restrict__ col, float* __restrict__ col_lo, int B, int H,
+                 int W, int C, int ld) {
+  const int lane = threadIdx.x & 31;
+  const long long n_pix = (long long)B * H * W;
+  const int K = 9 * C;
+  for (long long p = blockIdx.x * 8LL + (threadIdx.x >> 5); p < n_pix; p += (long long)gridDim.x * 8) {
+    const int xx = (int)(p % W);
+    const int yy = (int)((p / W) % H);
+    const long long img = p - (long long)yy * W - xx;          // pixel index of (b, 0, 0)
+    for (int k = lane; k < ld; k += 32) {
+      float v = 0.f;
+      if (k < K) {
+        const int tap = k / C, c = k - tap * C;
+        const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = x[(img + (long long)sy * W + sx) * C + c];
+      }
+      if (col_lo != nullptr) {
+        float h, l;
+        split1(v, h, l);
+        col[p * ld + k] = h;
+        col_lo[p * ld + k] = l;
+      } else {
+        col[p * ld + k] = v;
+      }
+    }
   }
 }
 
@@ -387,12 +449,32 @@ extern "C" int impflow_transpose(const float* a, float* out, long long M, long l
   return check_launch("k_transpose");
 }
 
-extern "C" int impflow_im2col3x3(const float* x, float* col, int B, int H, int W, int C, int ld, void* stream) {
+static int launch_im2col(const float* x, float* col, float* col_lo, int B, int H, int W, int C, int ld,
+                         void* stream) {
   IMPFLOW_REQUIRE(ld >= 9 * C, "im2col3x3: ld=%d < 9*C=%d", ld, 9 * C);
-  const long long total = (long long)B * H * W * ld;
-  if (total <= 0) return 0;
-  k_im2col3x3<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, col, B, H, W, C, ld);
-  return check_launch("k_im2col3x3");
+  const long long n_pix = (long long)B * H * W;
+  if (n_pix <= 0) return 0;
+  k_im2col3x3_rows<<<grid_for(n_pix, 8), 256, 0, (cudaStream_t)stream>>>(x, col, col_lo, B, H, W, C, ld);
+  return check_launch("k_im2col3x3_rows");
+}
+
+extern "C" int impflow_im2col3x3(const float* x, float* col, int B, int H, int W, int C, int ld, void* stream) {
+  return launch_im2col(x, col, nullptr, B, H, W, C, ld, stream);
+}
+
+extern "C" int impflow_im2col3x3_split(const float* x, float* col_hi, float* col_lo, int B, int H, int W, int C,
+                                       int ld, void* stream) {
+  IMPFLOW_REQUIRE(col_hi != nullptr && col_lo != nullptr, "im2col3x3_split: both planes are required");
+  return launch_im2col(x, col_hi, col_lo, B, H, W, C, ld, stream);
+}
+
+extern "C" int impflow_transpose_split(const float* a, float* out_hi, float* out_lo, long long M, long long N,
+                                       void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  IMPFLOW_REQUIRE(N < (1LL << 31), "transpose_split: N=%lld too large", N);
+  const long long tiles = ((M + 63) / 64) * ((N + 31) / 32);
+  k_transpose_split<<<grid_for(tiles, 1), 256, 0, (cudaStream_t)stream>>>(a, out_hi, out_lo, M, (int)N);
+  return check_launch("k_transpose_split");
 }
 
 extern "C" int impflow_col2im3x3(const float* col, int B, int H, int W, int C, const float* bias, float* pre_out,
@@ -410,6 +492,11 @@ extern "C" int impflow_col2im3x3(const float* col, int B, int H, int W, int C, c
 
 extern "C" int impflow_split_tf32(const float* a, float* hi, float* lo, long long n, void* stream) {
   if (n <= 0) return 0;
+  if (aligned16(a) && aligned16(hi) && aligned16(lo) && (n % 4 == 0)) {
+    k_split_tf32_v4<<<grid_for(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(a), reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n >> 2);
+    return check_launch("k_split_tf32_v4");
+  }
   k_split_tf32<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, hi, lo, n);
   return check_launch("k_split_tf32");
 }

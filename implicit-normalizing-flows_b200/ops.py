@@ -245,6 +245,39 @@ def im2col3x3(x_nhwc, ld=None):
     return col
 
 
+def im2col3x3_split(x_nhwc, ld=None):
+    """im2col3x3 written directly as the tf32 (hi, lo) planes the tcgen05 GEMM consumes."""
+    x_nhwc = x_nhwc.contiguous()
+    B, H, W, C = x_nhwc.shape
+    ld = 9 * C if ld is None else ld
+    hi = torch.empty(B * H * W, ld, device=x_nhwc.device, dtype=torch.float32)
+    lo = torch.empty_like(hi)
+    _cabi.check(_lib().impflow_im2col3x3_split(_cabi.ptr(x_nhwc), _cabi.ptr(hi), _cabi.ptr(lo), B, H, W, C, ld,
+                                               _cabi.stream()), 'im2col3x3_split')
+    return hi, lo
+
+
+def transpose_split(a2d):
+    """tf32 (hi, lo) planes of a2d^T in one pass."""
+    a2d = a2d.contiguous()
+    M, N = a2d.shape
+    hi = torch.empty(N, M, device=a2d.device, dtype=torch.float32)
+    lo = torch.empty_like(hi)
+    _cabi.check(_lib().impflow_transpose_split(_cabi.ptr(a2d), _cabi.ptr(hi), _cabi.ptr(lo), M, N, _cabi.stream()),
+                'transpose_split')
+    return hi, lo
+
+
+def wgrad_gemm(G, A):
+    """dW (N1, N2) = G^T A for G (M, N1), A (M, N2): the weight-gradient contraction over all rows (pixels).
+    tcgen05 path: both operands go through one transpose+split pass, then a split-K GEMM."""
+    M, N1 = G.shape
+    N2 = A.shape[1]
+    if _tc_ok(N1, N2, M, M, M):
+        return gemm_nt(None, None, A_split=transpose_split(G), B_split=transpose_split(A))[0]
+    return gemm_nt(transpose2d(G), transpose2d(A))[0]
+
+
 def col2im3x3(col, B, H, W, C, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, want_act=False,
               dmul_pre=None):
     col = col.contiguous()
@@ -283,11 +316,17 @@ def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, wa
 
     Returns (pre, act, split) where split is None or the (hi, lo) tf32 planes of the value that
     feeds the next GEMM (only produced by the tcgen05 backend)."""
-    A = A.contiguous()
-    Bm = Bm.contiguous()
-    M, K = A.shape
-    N = Bm.shape[0]
-    assert Bm.shape[1] == K, 'gemm_nt: inner dimensions differ'
+    if A is None or Bm is None:      # operands given as planes only
+        assert A_split is not None and B_split is not None, 'gemm_nt: planes missing'
+        M, K = A_split[0].shape
+        N = B_split[0].shape[0]
+        assert B_split[0].shape[1] == K, 'gemm_nt: inner dimensions differ'
+    else:
+        A = A.contiguous()
+        Bm = Bm.contiguous()
+        M, K = A.shape
+        N = Bm.shape[0]
+        assert Bm.shape[1] == K, 'gemm_nt: inner dimensions differ'
     if K % 32 != 0 and _BACKEND['mode'] != 'simt' and N >= 8 and 2 * M * N * K >= 64 * _BACKEND['min_flops_tc'] \
             and A_split is None and B_split is None:
         # a large GEMM with an odd inner dimension (e.g. K = 9*3 = 27): zero-pad K so that it runs on
@@ -296,7 +335,7 @@ def gemm_nt(A, Bm, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, wa
         A = torch.nn.functional.pad(A, (0, pad))
         Bm = torch.nn.functional.pad(Bm, (0, pad))
         K += pad
-    dev = A.device
+    dev = (A if A is not None else A_split[0]).device
     need_pre = want_pre or dmul_pre is not None
     pre = torch.empty(M, N, device=dev, dtype=torch.float32) if need_pre else None
     act = torch.empty(M, N, device=dev, dtype=torch.float32) if want_act else None

@@ -140,6 +140,9 @@ int impflow_transpose(const float* a, float* out, long long M, long long N, void
  * `ld` >= 9*C floats, the tail zero-filled so that K can be padded to a multiple of 32), and its
  * adjoint (scatter-sum) with the same fused epilogue as impflow_gemm_nt (N = C, ldc = C). */
 int impflow_im2col3x3(const float* x, float* col, int B, int H, int W, int C, int ld, void* stream);
+/* the same gather written directly as tf32 hi/lo planes (the A operand of impflow_gemm_nt_tc) */
+int impflow_im2col3x3_split(const float* x, float* col_hi, float* col_lo, int B, int H, int W, int C, int ld,
+                            void* stream);
 int impflow_col2im3x3(const float* col, int B, int H, int W, int C, const float* bias, float* pre_out,
                       float* act_out, const float* dmul_pre, int act_kind, const float* beta_sp, void* stream);
 
@@ -175,6 +178,9 @@ int impflow_gemm_tc_splits(long long M, int N, int K);
 int impflow_gemm_tc_set_wide_tiles(int on);
 /* a -> tf32 "hi" (round-to-nearest) and "lo" = a - hi planes used by the 3xTF32 backend. */
 int impflow_split_tf32(const float* a, float* hi, float* lo, long long n, void* stream);
+/* out_hi/out_lo[n,m] = tf32 split of a[m,n] (a is M x N row-major): the K-major operand planes of the
+ * weight-gradient GEMMs dW = G^T A (K = all pixels) in one pass. */
+int impflow_transpose_split(const float* a, float* out_hi, float* out_lo, long long M, long long N, void* stream);
 
 /* Fused residual-branch tile kernel for the 3x3 / 1x1 / 3x3 conv branch whose narrow side has 9*c <= 32
  * tap columns (implicit_flow.py:359-398 at the first CIFAR scale), forward or transposed (vjp), one launch:

@@ -110,3 +110,23 @@ print('synced wall per step: %.1f ms' % (tot / N * 1e3))
 for k, v in sorted(ACC.items(), key=lambda kv: -kv[1]):
     print('  %-58s %7.2f ms  %5.1f%%  calls/step %5.1f  own launches/step %6.1f' %
           (k, v / N * 1e3, 100 * v / tot, CNT[k] / N, LCH[k] / N))
+
+if os.environ.get('CPROF'):
+    import cProfile
+    import io
+    import pstats
+    ON['on'] = False
+    step()
+    torch.cuda.synchronize()
+    pr = cProfile.Profile()
+    t0 = time.perf_counter()
+    pr.enable()
+    step()
+    pr.disable()
+    t_host = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    print('host issue time of one step under cProfile: %.1f ms' % (t_host * 1e3))
+    for key in ('tottime', 'cumulative'):
+        sio = io.StringIO()
+        pstats.Stats(pr, stream=sio).sort_stats(key).print_stats(40)
+        print(sio.getvalue()[:7000])

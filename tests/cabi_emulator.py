@@ -348,6 +348,22 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_im2col3x3_split(self, x, col_hi, col_lo, B, H, W, C, ld, stream):
+        full = np.zeros((B * H * W, ld), dtype=np.float32)
+        self.impflow_im2col3x3(x, ctypes.c_void_p(full.ctypes.data), B, H, W, C, ld, stream)
+        h = _tf32(full.reshape(-1))
+        _f32(col_hi, full.size)[:] = h
+        _f32(col_lo, full.size)[:] = full.reshape(-1) - h
+        return 0
+
+    def impflow_transpose_split(self, a, out_hi, out_lo, M, N, stream):
+        t = np.ascontiguousarray(_f32(a, M * N).reshape(M, N).T).reshape(-1)
+        h = _tf32(t)
+        _f32(out_hi, M * N)[:] = h
+        _f32(out_lo, M * N)[:] = t - h
+        self.launches += 1
+        return 0
+
     def impflow_col2im3x3(self, col, B, H, W, C, bias, pre_out, act_out, dmul_pre, act_kind, beta_sp, stream):
         cv = _f32(col, B * H * W * 9 * C).reshape(B, H, W, 9, C)
         acc = np.zeros((B, H + 2, W + 2, C), np.float32)

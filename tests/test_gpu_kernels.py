@@ -182,6 +182,34 @@ def test_im2col_col2im(ops):
     assert abs(lhs - rhs) / abs(lhs) < 1e-5
 
 
+@pytest.mark.parametrize('M,N', [(64, 32), (65536, 27), (1000, 77), (4096, 512), (130, 513)])
+def test_transpose_split(ops, M, N):
+    a = torch.randn(M, N, generator=torch.Generator().manual_seed(M + N)).cuda()
+    hi, lo = ops.transpose_split(a)
+    assert hi.shape == (N, M)
+    assert torch.equal(hi + lo, a.t())                               # exact: lo is the rounding residual
+    assert torch.equal(hi, ops.split_tf32(a.t().contiguous())[0])    # same rounding as the plain split kernel
+
+
+@pytest.mark.parametrize('B,H,W,C,ld', [(2, 8, 8, 3, 32), (3, 5, 7, 12, 128), (1, 4, 4, 48, 448), (2, 6, 6, 3, 27)])
+def test_im2col_split_planes(ops, B, H, W, C, ld):
+    x = torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(C)).cuda()
+    col = ops.im2col3x3(x, ld=ld)
+    ref = F.unfold(x.permute(0, 3, 1, 2), 3, padding=1).view(B, C, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * C)
+    assert torch.equal(col[:, :9 * C], ref) and float(col[:, 9 * C:].abs().sum()) == 0.0
+    hi, lo = ops.im2col3x3_split(x, ld=ld)
+    assert torch.equal(hi + lo, col)
+    assert torch.equal(hi, ops.split_tf32(col)[0])
+
+
+def test_split_tf32_vectorised_and_tail(ops):
+    for n in (4096, 4099, 3):
+        a = torch.randn(n).cuda()
+        hi, lo = ops.split_tf32(a)
+        assert torch.equal(hi + lo, a)
+        assert int((hi.view(torch.int32) & 0x1FFF).abs().sum()) == 0       # tf32: low 13 mantissa bits clear
+
+
 @pytest.mark.parametrize('cin,cout', [(3, 16), (16, 3), (8, 8)])
 def test_conv3x3_matches_conv2d(ops, cin, cout):
     g = torch.Generator().manual_seed(cin * 31 + cout)
