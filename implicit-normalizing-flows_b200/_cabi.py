@@ -45,6 +45,12 @@ SIGNATURES = {
     'impflow_gemm_nt_tc': (_i, [_c_fp, _c_fp, _ll, _c_fp, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp,
                                 _ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
     'impflow_branch3_tc': (_i, [_c_fp, _ll] + [_c_fp] * 13 + [_ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
+    'impflow_conv3_workspace_floats': (ctypes.c_size_t, [_i] * 6),
+    'impflow_conv3_forward': (_i, [_c_fp] * 6),
+    'impflow_conv3_prepare_vjp': (_i, [_c_fp] * 6),
+    'impflow_conv3_vjp': (_i, [_c_fp] * 7),
+    'impflow_conv3_power_series': (_i, [_c_fp] * 6 + [_i, _c_fp, _c_fp]),
+    'impflow_conv3_broyden': (_i, [_c_fp, _i] + [_c_fp] * 17 + [_i, _d, _c_fp]),
     'impflow_gemm_tc_splits': (_i, [_ll, _i, _i]),
     'impflow_gemm_tc_set_wide_tiles': (_i, [_i]),
     'impflow_split_tf32': (_i, [_c_fp, _c_fp, _c_fp, _ll, _c_fp]),
@@ -54,6 +60,17 @@ SIGNATURES = {
     'impflow_sn_power_iter_conv3x3': (_i, [_c_fp] * 5 + [_i, _i, _i, _i, _i, _f, _f, _c_fp, _c_fp]),
     'impflow_sn_power_iter': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _i, _i, _i, _f, _f, _c_fp]),
 }
+
+
+
+class Conv3Plan(ctypes.Structure):
+    """impflow_conv3_plan of include/impflow_b200.h."""
+    _fields_ = ([(n, ctypes.c_int32) for n in ('B', 'H', 'W', 'c', 'C', 'k0', 'act_kind', 'act0_kind', 'allow_fused',
+                                               'reserved')] +
+                [(n, ctypes.c_void_p) for n in ('beta0', 'beta1', 'beta2', 'W1f_hi', 'W1f_lo', 'W2f_hi', 'W2f_lo',
+                                                'W3f_hi', 'W3f_lo', 'b1', 'b2', 'b3', 'W3b_hi', 'W3b_lo', 'W2b_hi',
+                                                'W2b_lo', 'W1b_hi', 'W1b_lo', 'ws')])
+
 
 _lib = None
 

@@ -31,6 +31,8 @@ autograd's double backward:
     Wbar  += tbar_y (x) t_a + ybar (x) a          bbar += sum ybar
     tbar_p = phi'(p) tbar_a            pbar = phi''(p) t_p tbar_a + phi'(p) abar
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -39,10 +41,22 @@ from . import _cabi, ops
 from .layers.base.activations import ReLU, Sin, Swish
 from .layers.base.mixed_lipschitz import InducedNormConv2d, InducedNormLinear
 
-__all__ = ['BranchProgram', 'compile_branch', 'FUSED3']
+__all__ = ['BranchProgram', 'compile_branch', 'FUSED3', 'CONV3_NATIVE']
 
 # One-launch tile kernel for the 3-layer conv branch (csrc/branch_fused.cu); off = three GEMM launches.
 FUSED3 = {'on': True}
+# Native host runtime for the 3-layer conv branch (csrc/conv3_plan.cu): one C call per evaluation / power
+# series / Broyden solve; off = the Python-driven launch sequences below.
+CONV3_NATIVE = {'on': True}
+
+_conv3_ws = {}      # device index -> workspace tensor shared by every plan (grown on demand)
+
+
+def _conv3_workspace(n_floats, device):
+    t = _conv3_ws.get(device.index)
+    if t is None or t.numel() < n_floats:
+        t = _conv3_ws[device.index] = torch.empty(int(n_floats), device=device, dtype=torch.float32)
+    return t
 
 
 def _round_up(n, m):
@@ -360,47 +374,163 @@ class BranchProgram(object):
         return pre, a_out, split
 
 
-    # ---------------------------------------------------------------- fused 3-layer tile kernel
-    def _fused3_ok(self, ws, meta):
-        """True when the whole branch is one impflow_branch3_tc launch (csrc/branch_fused.cu): the
-        3x3(c->C) / 1x1(C->C) / 3x3(C->c) conv stack with 9c <= 32 tap columns and C a multiple of 256
-        (the first-scale blocks of the image flows, implicit_flow.py:359-398)."""
-        if not FUSED3['on'] or self.is_linear or len(ws) != 3 or self.post_act is not None or meta[0] != 'conv':
-            return False
+    # ---------------------------------------------------------------- native 3-layer conv runtime
+    def _conv3(self, ws, meta):
+        """impflow_conv3_plan (ctypes) for this branch, or None when it is not the
+        [act] 3x3(c->C) act 1x1(C->C) act 3x3(C->c) stack of the image flows (implicit_flow.py:359-398)
+        with every layer on the tcgen05 path."""
+        if not CONV3_NATIVE['on'] or self.is_linear or len(ws) != 3 or self.post_act is not None or meta[0] != 'conv':
+            return None
         w0, w1, w2 = ws
         a1, a2 = self.stages[1][0], self.stages[2][0]
         if a1 is None or a2 is None or a1.kind != a2.kind:
-            return False
-        C = w1.cout
-        return (w0.kind == 'c3' and w0.a_type and w0.fwd_k == 32 and w0.cout == C and w0.fwd_split is not None
-                and w0.bwd_split is not None and w1.kind == 'mm' and w1.cin == C and C % 256 == 0
-                and w1.fwd_split is not None and w1.bwd_split is not None
-                and w2.kind == 'c3' and not w2.a_type and w2.cin == C and w2.bwd_k == 32 and 9 * w2.cout <= 32
-                and w2.fwd_split is not None and w2.bwd_split is not None)
-
-    def _forward_fused3(self, rows, meta, ws, save):
+            return None
+        C, c = w1.cout, w0.cin
+        ok = (w0.kind == 'c3' and w0.a_type and w0.cout == C and w1.kind == 'mm' and w1.cin == C
+              and w2.kind == 'c3' and not w2.a_type and w2.cin == C and w2.cout == c
+              and w0.fwd_k == w2.bwd_k and w0.fwd_k % 32 == 0 and C % 32 == 0
+              and w1.fwd_k == C and w1.bwd_k == C and w2.fwd_k == C and w0.bwd_k == C
+              and all(w.fwd_split is not None and w.bwd_split is not None for w in ws))
+        if not ok:
+            return None
         B, H, Wd = meta[1]
-        M = rows.shape[0]
-        w0, w1, w2 = ws
-        a1, a2 = self.stages[1][0], self.stages[2][0]
-        pres = [None] * 4
+        k0 = w0.fwd_k
+        lib = _cabi.load()
+        wsp = _conv3_workspace(lib.impflow_conv3_workspace_floats(B, H, Wd, c, C, k0), w0.fwd.device)
+        key = (self._key, meta[1], FUSED3['on'], wsp.data_ptr())
+        cached = getattr(self, '_conv3_cache', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
         act0 = self.stages[0][0]
-        xin = rows
-        if act0 is not None:
-            pres[0] = rows
-            xin = ops.act_mul(rows, None, act0.kind, 0, act0.beta_sp())
-        x0 = ops.im2col3x3(xin.view(B, H, Wd, w0.cin), ld=32)
-        Y, pres[1], pres[2] = ops.branch3_tc(x0, w0.fwd_split, w1.fwd_split, w2.fwd_split, 9 * w2.cout,
-                                             bias1=w0.bias, bias2=w1.bias, act_kind=a1.kind, beta1=a1.beta_sp(),
-                                             beta2=a2.beta_sp(), save_pre=save)
-        out, _ = ops.col2im3x3(Y, B, H, Wd, w2.cout, w2.bias)
+        P = _cabi.Conv3Plan()
+        P.B, P.H, P.W, P.c, P.C, P.k0 = B, H, Wd, c, C, k0
+        P.act_kind = a1.kind
+        P.act0_kind = act0.kind if act0 is not None else ops.ACT_NONE
+        P.allow_fused = 1 if FUSED3['on'] else 0
+        dp = lambda t: (t.data_ptr() if t is not None else None)
+        P.beta0 = dp(act0.beta_sp()) if act0 is not None else None
+        P.beta1, P.beta2 = dp(a1.beta_sp()), dp(a2.beta_sp())
+        P.W1f_hi, P.W1f_lo = dp(w0.fwd_split[0]), dp(w0.fwd_split[1])
+        P.W2f_hi, P.W2f_lo = dp(w1.fwd_split[0]), dp(w1.fwd_split[1])
+        P.W3f_hi, P.W3f_lo = dp(w2.fwd_split[0]), dp(w2.fwd_split[1])
+        P.b1, P.b2, P.b3 = dp(w0.bias), dp(w1.bias), dp(w2.bias)
+        P.W3b_hi, P.W3b_lo = dp(w2.bwd_split[0]), dp(w2.bwd_split[1])
+        P.W2b_hi, P.W2b_lo = dp(w1.bwd_split[0]), dp(w1.bwd_split[1])
+        P.W1b_hi, P.W1b_lo = dp(w0.bwd_split[0]), dp(w0.bwd_split[1])
+        P.ws = wsp.data_ptr()
+        # the weights / betas stay alive in self._weights and the _Act objects; the plan only borrows them
+        self._conv3_cache = (key, P, (ws, wsp, [a.beta_sp() for a in self._acts() if a is not None]))
+        return P
+
+    @staticmethod
+    def _plan_ptr(P):
+        return ctypes.c_void_p(ctypes.addressof(P))
+
+    def _record_conv3(self, P, is_vjp, save, count=1):
+        """bench.py roofline bookkeeping: which tensor-core launches one native evaluation makes."""
+        M = P.B * P.H * P.W
+        tile = P.allow_fused and P.k0 == 32 and P.C % 256 == 0 and 9 * P.c <= 32
+        for _ in range(count):
+            if tile:
+                ops.record_branch3(M, P.C, 9 * P.c, is_vjp, save)
+            else:
+                ops.record_gemm(M, P.C, P.k0, save, False, is_vjp, True, False)
+                ops.record_gemm(M, P.C, P.C, save, False, is_vjp, True, False)
+                ops.record_gemm(M, 9 * P.c, P.C, True, False, False, False, False)
+
+    def _native_forward(self, P, rows, meta, save):
+        M = rows.shape[0]
+        dev = rows.device
+        y = torch.empty(M, P.c, device=dev, dtype=torch.float32)
+        pre1 = torch.empty(M, P.C, device=dev, dtype=torch.float32) if save else None
+        pre2 = torch.empty(M, P.C, device=dev, dtype=torch.float32) if save else None
+        _cabi.check(_cabi.load().impflow_conv3_forward(self._plan_ptr(P), _cabi.ptr(rows), _cabi.ptr(y),
+                                                       _cabi.ptr(pre1, 'pre1', True), _cabi.ptr(pre2, 'pre2', True),
+                                                       _cabi.stream()), 'conv3_forward')
+        if ops.GEMM_PROFILE['on']:
+            self._record_conv3(P, False, save)
         saved = None
         if save:
             saved = _Saved()
-            saved.rows, saved.meta, saved.M, saved.pres, saved.derivs = rows, meta, M, pres, {}
-            # layer inputs are not kept: backward_full / neumann re-evaluate them from the pre-activations
-            saved.ains = None
-        return self._from_rows(out.view(M, w2.cout), meta), saved
+            saved.rows, saved.meta, saved.M, saved.derivs = rows, meta, M, {}
+            saved.pres = [rows if self.stages[0][0] is not None else None, pre1, pre2, None]
+            saved.ains = None       # backward_full / neumann re-evaluate the layer inputs from the pre-activations
+        return self._from_rows(y, meta), saved
+
+    def _vjp_operands(self, saved):
+        return (_cabi.ptr(saved.pres[0], 'pre0', True), _cabi.ptr(self._deriv(saved, 1)),
+                _cabi.ptr(self._deriv(saved, 2)))
+
+    def _native_vjp(self, P, v, saved):
+        t, _ = self._to_rows(v)
+        out = torch.empty_like(t)
+        pre0, d1, d2 = self._vjp_operands(saved)
+        _cabi.check(_cabi.load().impflow_conv3_vjp(self._plan_ptr(P), pre0, d1, d2, _cabi.ptr(t), _cabi.ptr(out),
+                                                   _cabi.stream()), 'conv3_vjp')
+        if ops.GEMM_PROFILE['on']:
+            self._record_conv3(P, True, False)
+        return self._from_rows(out, saved.meta)
+
+    def native_plan(self, x):
+        """The native plan for inputs shaped like x (module layout), or None."""
+        if self.is_linear or x.dim() != 4:
+            return None
+        meta = ('conv', (x.shape[0], x.shape[2], x.shape[3]))
+        return self._conv3(self._prep(x.shape[0] * x.shape[2] * x.shape[3], meta), meta)
+
+    def neumann_chain(self, saved, vareps, coeffs):
+        """w = v + sum_k coeffs[k-1] v^T J^k in one C call (implicit_block.py:431-435), or None if this
+        branch has no native plan."""
+        P = self._conv3(self._prep(saved.M), saved.meta)
+        if P is None:
+            return None
+        t, _ = self._to_rows(vareps)
+        w_rows = torch.empty_like(t)
+        n = len(coeffs)
+        arr = (ctypes.c_double * max(n, 1))(*[float(c) for c in coeffs])
+        pre0, d1, d2 = self._vjp_operands(saved)
+        _cabi.check(_cabi.load().impflow_conv3_power_series(self._plan_ptr(P), pre0, d1, d2, _cabi.ptr(t), arr, n,
+                                                            _cabi.ptr(w_rows), _cabi.stream()), 'conv3_power_series')
+        if ops.GEMM_PROFILE['on']:
+            self._record_conv3(P, True, False, n)
+        return self._from_rows(w_rows, saved.meta)
+
+    def broyden_solve(self, mode, rhs, saved, threshold, eps):
+        """Whole Broyden solve in one C call (mode 0: rhs - nnet(z) - z = 0 from z = 0; mode 1:
+        v^T J + v - rhs = 0 at `saved`).  Returns the reference's result dict, or None without a plan."""
+        from .layers import broyden as _b
+        B = rhs.shape[0]
+        meta = ('conv', (B, rhs.shape[2], rhs.shape[3])) if rhs.dim() == 4 else None
+        if meta is None:
+            return None
+        M = B * rhs.shape[2] * rhs.shape[3]
+        P = self._conv3(self._prep(M, meta), meta)
+        if P is None:
+            return None
+        lib = _cabi.load()
+        rows, _ = self._to_rows(rhs)
+        d = rows.numel() // B
+        eps_scaled = eps * (B * d) ** 0.5
+        wk = _b._workspace(B, d, threshold, rows.device)
+        if not hasattr(wk, 'ga'):
+            wk.ga = torch.empty(B, d, device=rows.device, dtype=torch.float32)
+            wk.gb = torch.empty(B, d, device=rows.device, dtype=torch.float32)
+        wk.xa.zero_()
+        if mode == 1:
+            pre0, d1, d2 = self._vjp_operands(saved)
+        else:
+            pre0 = d1 = d2 = None
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        _cabi.check(lib.impflow_conv3_broyden(
+            self._plan_ptr(P), mode, _cabi.ptr(rows), pre0, d1, d2, vp(wk.xa), vp(wk.xb), vp(wk.ga), vp(wk.gb),
+            vp(wk.low_x), vp(wk.low_g), vp(wk.Ut), vp(wk.Vt), vp(wk.sample_sq), vp(wk.low_sq), vp(wk.partial),
+            vp(wk.state), vp(wk.state_host), threshold, float(eps_scaled), _cabi.stream()), 'conv3_broyden')
+        state = wk.state_host.numpy().view(_b._STATE_DTYPE)[0]
+        info = _b._result_dict(wk, state, (B, d), eps_scaled, threshold)
+        info['result'] = self._from_rows(info['result'].view(M, P.c), meta)
+        if ops.GEMM_PROFILE['on']:
+            self._record_conv3(P, mode == 1, False, info['nstep'] + 1)
+        return info
 
     def _ains(self, saved):
         """Layer-input handles of a saved forward (the fused forward keeps only the pre-activations)."""
@@ -422,29 +552,15 @@ class BranchProgram(object):
             d = saved.derivs[i] = ops.act_mul(saved.pres[i], None, a.kind, 1, a.beta_sp())
         return d
 
-    def _vjp_fused3(self, v, saved, ws):
-        B, H, Wd = saved.meta[1]
-        w0, w1, w2 = ws
-        t, _ = self._to_rows(v)
-        x0 = ops.im2col3x3(t.view(B, H, Wd, w2.cout), ld=32)
-        Y, _, _ = ops.branch3_tc(x0, w2.bwd_split, w1.bwd_split, w0.bwd_split, 9 * w0.cin,
-                                 mul1=self._deriv(saved, 2), mul2=self._deriv(saved, 1))
-        act0 = self.stages[0][0]
-        if act0 is not None:
-            out, _ = ops.col2im3x3(Y, B, H, Wd, w0.cin, None, act0.kind, act0.beta_sp(),
-                                   dmul_pre=saved.pres[0].view(B, H, Wd, w0.cin))
-        else:
-            out, _ = ops.col2im3x3(Y, B, H, Wd, w0.cin, None)
-        return self._from_rows(out.view(saved.M, w0.cin), saved.meta)
-
     # ---------------------------------------------------------------- forward
     def forward_saved(self, x, save=True):
         """(nnet(x), saved) without a graph; saved feeds vjp / backward_full / neumann."""
         rows, meta = self._to_rows(x)
         M = rows.shape[0]
         ws = self._prep(M, meta)
-        if self._fused3_ok(ws, meta):
-            return self._forward_fused3(rows, meta, ws, save)
+        P = self._conv3(ws, meta)
+        if P is not None:
+            return self._native_forward(P, rows, meta, save)
         n = len(self.stages)
         pres = [None] * (n + 1)       # pres[i] = input of the activation in front of layer i (pres[n]: post act)
         ains = [None] * n             # ains[i] = input handle of layer i (after its activation)
@@ -487,8 +603,9 @@ class BranchProgram(object):
             raise RuntimeError('BranchProgram.vjp: call forward(save=True) first')
         meta, M, pres = saved.meta, saved.M, saved.pres
         ws = self._prep(M)
-        if self._fused3_ok(ws, meta):
-            return self._vjp_fused3(v, saved, ws)
+        P = self._conv3(ws, meta)
+        if P is not None:
+            return self._native_vjp(P, v, saved)
         n = len(self.stages)
         t, _ = self._to_rows(v)
         T = _T(f=t)

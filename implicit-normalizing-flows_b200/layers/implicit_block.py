@@ -135,10 +135,14 @@ class RootFind(Function):
         x_embed = ops.lincomb3(branch_eval(nnet_x, x), 1.0, x, 1.0)
         prog_z = _program(nnet_z)
         spec = prog_z.mlp_solver_spec(z0) if (prog_z is not None and PERSISTENT_MLP['on']) else None
+        info = None
         if spec is not None:
             # small-d MLP branch: the whole solve (branch evaluations included) in one persistent kernel
             info = broyden_mlp(spec, x_embed, torch.zeros_like(z0), threshold, eps)
-        else:
+        elif prog_z is not None:
+            # conv branch: the whole solve in one call of the native runtime (csrc/conv3_plan.cu)
+            info = prog_z.broyden_solve(0, x_embed, None, threshold, eps)
+        if info is None:
             def g(z):     # x_embed - nnet_z(z) - z in one kernel (implicit_block.py:72)
                 return ops.lincomb3(x_embed, 1.0, branch_eval(nnet_z, z), -1.0, z, -1.0)
 
@@ -227,9 +231,11 @@ class imBlock(nn.Module):
                 # graph-free: v^T (I + J_z) from the fused vjp kernels
                 with torch.no_grad():
                     z, x = z.detach(), x.detach()
-                    prog_z.forward(z, save=True)
-                    info = broyden(lambda v: ops.lincomb3(prog_z.vjp(v), 1.0, v, 1.0, grad, -1.0),
-                                   torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
+                    _, saved_z = prog_z.forward_saved(z)
+                    info = prog_z.broyden_solve(1, grad, saved_z, threshold, eps)
+                    if info is None:
+                        info = broyden(lambda v: ops.lincomb3(prog_z.vjp(v, saved_z), 1.0, v, 1.0, grad, -1.0),
+                                       torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
                     imBlock.Backward.last_info = info
                     dl_dh = info['result']
                     prog_x.forward(x, save=True)
@@ -422,10 +428,13 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
             with torch.no_grad():
                 xd = x.detach()
                 _, saved = prog.forward_saved(xd)
-                vjp = neumann_vjp = vareps
-                for k in range(1, n_power_series + 1):
-                    vjp = prog.vjp(vjp, saved)
-                    neumann_vjp = ops.lincomb3(neumann_vjp, 1.0, vjp, float((-1) ** k * coeff_fn(k)))
+                coeffs = [float((-1) ** k * coeff_fn(k)) for k in range(1, n_power_series + 1)]
+                neumann_vjp = prog.neumann_chain(saved, vareps, coeffs)       # one C call when native
+                if neumann_vjp is None:
+                    vjp = neumann_vjp = vareps
+                    for k in range(1, n_power_series + 1):
+                        vjp = prog.vjp(vjp, saved)
+                        neumann_vjp = ops.lincomb3(neumann_vjp, 1.0, vjp, coeffs[k - 1])
                 logdetgrad, grad_x, grad_params = prog.neumann(saved, neumann_vjp, vareps)
             ctx.none_mask = [gp is None for gp in grad_params]
             ctx.save_for_backward(grad_x, *[gp if gp is not None else xd.new_zeros(()) for gp in grad_params])

@@ -50,7 +50,8 @@ def time_gemm_shape(key, reps=5, flush=None):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        gemm_nt(A, Bm, None, act_kind=ACT_LIPSWISH if (has_act or has_dmul) else ACT_NONE, beta_sp=beta,
+        gemm_nt(A, Bm, None, act_kind=ACT_MULTIPLIER if has_dmul else (ACT_LIPSWISH if has_act or has_split else ACT_NONE),
+                beta_sp=beta,
                 want_pre=has_pre and not has_dmul, want_act=has_act, dmul_pre=dm, A_split=As, B_split=Bs,
                 want_split=has_split)
         e1.record()

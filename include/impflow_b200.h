@@ -199,6 +199,60 @@ int impflow_branch3_tc(const float* x0, long long ldx, const float* W1_hi, const
                        const float* beta2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Native host runtime of the 3x3 / 1x1 / 3x3 conv residual branch (implicit_flow.py:359-398): one C call per
+ * branch evaluation, per Neumann power-series chain and per Broyden solve (csrc/conv3_plan.cu).  All
+ * tensors are NHWC "rows": M = B*H*W rows of c floats; a sample is a contiguous block of H*W*c floats.
+ * Shapes with 9c <= 32 and C % 256 == 0 run on impflow_branch3_tc, the others on im2col planes + three
+ * impflow_gemm_nt_tc + col2im.  The caller owns every buffer; `ws` holds
+ * impflow_conv3_workspace_floats(B,H,W,c,C,k0) floats and may be shared by all plans used on one stream.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t B, H, W;       /* images and their spatial size */
+  int32_t c, C;          /* narrow (input = output) channels, hidden width */
+  int32_t k0;            /* 9c rounded up to a multiple of 32: row length of the patch matrices */
+  int32_t act_kind;      /* activation between the layers (one kind for both) */
+  int32_t act0_kind;     /* leading activation, IMPFLOW_ACT_NONE if the branch starts with the conv */
+  int32_t allow_fused;   /* 0 = never use the one-launch tile kernel (A/B switch) */
+  int32_t reserved;
+  const float *beta0, *beta1, *beta2; /* device scalars softplus(beta) of the three LipSwish modules or NULL */
+  const float *W1f_hi, *W1f_lo;       /* (C, k0)  layer 1, rows (ky,kx,ci) zero-padded to k0 */
+  const float *W2f_hi, *W2f_lo;       /* (C, C)   layer 2 */
+  const float *W3f_hi, *W3f_lo;       /* (9c, C)  layer 3 in tap-major GEMM form (col2im follows) */
+  const float *b1, *b2, *b3;          /* biases (C), (C), (c) or NULL */
+  const float *W3b_hi, *W3b_lo;       /* (C, k0)  transposed layer 3 */
+  const float *W2b_hi, *W2b_lo;       /* (C, C)   transposed layer 2 */
+  const float *W1b_hi, *W1b_lo;       /* (9c, C)  transposed layer 1 */
+  float* ws;
+} impflow_conv3_plan;
+
+size_t impflow_conv3_workspace_floats(int B, int H, int W, int c, int C, int k0);
+/* y_rows = nnet(x_rows); pre1 / pre2 (M,C; optional) receive the hidden pre-activations kept for the vjp */
+int impflow_conv3_forward(const impflow_conv3_plan* plan, const float* x_rows, float* y_rows, float* pre1,
+                          float* pre2, void* stream);
+/* d_l = act'(pre_l): the multipliers of the transposed sweep, evaluated once per saved forward */
+int impflow_conv3_prepare_vjp(const impflow_conv3_plan* plan, const float* pre1, const float* pre2, float* d1,
+                              float* d2, void* stream);
+/* out_rows = v^T J at the saved point; pre0 = the branch input rows (needed when act0_kind != NONE) */
+int impflow_conv3_vjp(const impflow_conv3_plan* plan, const float* pre0, const float* d1, const float* d2,
+                      const float* v_rows, float* out_rows, void* stream);
+/* w = v + sum_{k=1..n} coeffs[k-1] * v^T J^k  — the no-grad chain of the Neumann gradient estimator
+ * (implicit_block.py:431-435); coeffs is a HOST array */
+int impflow_conv3_power_series(const impflow_conv3_plan* plan, const float* pre0, const float* d1, const float* d2,
+                               const float* v_rows, const double* coeffs, int n, float* w_rows, void* stream);
+/* Whole Broyden solve (broyden.py:123-193) with the residual evaluated by this branch:
+ *   mode 0: g(z) = rhs - nnet(z) - z        (forward / inverse solve, implicit_block.py:68-80; rhs = x_embed)
+ *   mode 1: g(v) = v^T J + v - rhs          (implicit backward, :199-207; rhs = incoming gradient)
+ * xa holds the start point; xa/xb/ga/gb are (B,d) scratch; the other buffers are those of
+ * impflow_broyden_step.  state_host is PINNED host memory: the routine copies the device state there and
+ * synchronises the stream once per iteration (the only host decision of the loop); on return it holds the
+ * final state and low_x the best iterate. */
+int impflow_conv3_broyden(const impflow_conv3_plan* plan, int mode, const float* rhs_rows, const float* pre0,
+                          const float* d1, const float* d2, float* xa, float* xb, float* ga, float* gb, float* low_x,
+                          float* low_g, float* Ut, float* Vt, float* sample_sq, float* low_sq, float* partial,
+                          impflow_broyden_state* state_dev, impflow_broyden_state* state_host, int threshold,
+                          double eps_scaled, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Induced 2-norm power iteration for a dense (out,in) matrix — replaces
  * mixed_lipschitz.py:85-123 (Linear) and :276-319 (1x1 conv).  One CTA, device-side early
  * exit with the reference tolerance rule; u, v updated in place; sigma[0] = u^T W v,

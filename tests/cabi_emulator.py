@@ -441,6 +441,116 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    # ---- native conv3 runtime (csrc/conv3_plan.cu): the same orchestration over the emulated kernels ----
+    @staticmethod
+    def _plan(p):
+        from impflow_b200._cabi import Conv3Plan
+        return Conv3Plan.from_address(_addr(p))
+
+    @staticmethod
+    def _tmp(*shape):
+        a = np.zeros(shape, dtype=np.float32)
+        return a, ctypes.c_void_p(a.ctypes.data)
+
+    def impflow_conv3_workspace_floats(self, B, H, W, c, C, k0):
+        return 64
+
+    def _conv3_chain(self, P, xin_ptr, W1, W2, W3, b1, b2, mul1, mul2, pre1, pre2, act_kind, beta1, beta2):
+        M, N3 = P.B * P.H * P.W, 9 * P.c
+        Y, Yp = self._tmp(M, N3)
+        if P.allow_fused and P.k0 == 32 and P.C % 256 == 0 and N3 <= 32:
+            x0, x0p = self._tmp(M, 32)
+            assert self.impflow_im2col3x3(xin_ptr, x0p, P.B, P.H, P.W, P.c, 32, None) == 0
+            assert self.impflow_branch3_tc(x0p, 32, W1[0], W1[1], W2[0], W2[1], W3[0], W3[1], b1, b2, mul1, mul2, pre1,
+                                           pre2, Yp, N3, M, P.C, N3, act_kind, beta1, beta2, None) == 0
+            return Y, Yp
+        xh, xhp = self._tmp(M, P.k0)
+        xl, xlp = self._tmp(M, P.k0)
+        h1h, h1hp = self._tmp(M, P.C)
+        h1l, h1lp = self._tmp(M, P.C)
+        h2h, h2hp = self._tmp(M, P.C)
+        h2l, h2lp = self._tmp(M, P.C)
+        assert self.impflow_im2col3x3_split(xin_ptr, xhp, xlp, P.B, P.H, P.W, P.c, P.k0, None) == 0
+        k1 = ACT_MULTIPLIER if mul1 is not None else act_kind
+        assert self.impflow_gemm_nt_tc(xhp, xlp, P.k0, W1[0], W1[1], P.k0, b1, pre1, None, mul1, h1hp, h1lp, P.C, M, P.C,
+                                       P.k0, k1, beta1, None, None) == 0
+        assert self.impflow_gemm_nt_tc(h1hp, h1lp, P.C, W2[0], W2[1], P.C, b2, pre2, None, mul2, h2hp, h2lp, P.C, M, P.C,
+                                       P.C, k1, beta2, None, None) == 0
+        assert self.impflow_gemm_nt_tc(h2hp, h2lp, P.C, W3[0], W3[1], P.C, None, Yp, None, None, None, None, N3, M, N3,
+                                       P.C, ACT_NONE, None, None, None) == 0
+        return Y, Yp
+
+    def impflow_conv3_forward(self, plan, x_rows, y_rows, pre1, pre2, stream):
+        P = self._plan(plan)
+        M = P.B * P.H * P.W
+        xin = x_rows
+        if P.act0_kind != ACT_NONE:
+            t, tp = self._tmp(M, P.c)
+            self.impflow_act_mul(x_rows, None, tp, M * P.c, P.act0_kind, 0, P.beta0, None)
+            xin = tp
+        none = lambda v: v if _addr(v) is not None else None
+        Y, Yp = self._conv3_chain(P, xin, (P.W1f_hi, P.W1f_lo), (P.W2f_hi, P.W2f_lo), (P.W3f_hi, P.W3f_lo), none(P.b1),
+                                  none(P.b2), None, None, none(pre1), none(pre2), P.act_kind, none(P.beta1),
+                                  none(P.beta2))
+        return self.impflow_col2im3x3(Yp, P.B, P.H, P.W, P.c, none(P.b3), y_rows, None, None, ACT_NONE, None, None)
+
+    def impflow_conv3_prepare_vjp(self, plan, pre1, pre2, d1, d2, stream):
+        P = self._plan(plan)
+        n = P.B * P.H * P.W * P.C
+        self.impflow_act_mul(pre1, None, d1, n, P.act_kind, 1, P.beta1, None)
+        return self.impflow_act_mul(pre2, None, d2, n, P.act_kind, 1, P.beta2, None)
+
+    def impflow_conv3_vjp(self, plan, pre0, d1, d2, v_rows, out_rows, stream):
+        P = self._plan(plan)
+        Y, Yp = self._conv3_chain(P, v_rows, (P.W3b_hi, P.W3b_lo), (P.W2b_hi, P.W2b_lo), (P.W1b_hi, P.W1b_lo), None, None,
+                                  d2, d1, None, None, ACT_NONE, None, None)
+        if P.act0_kind != ACT_NONE:
+            return self.impflow_col2im3x3(Yp, P.B, P.H, P.W, P.c, None, out_rows, None, pre0, P.act0_kind, P.beta0, None)
+        return self.impflow_col2im3x3(Yp, P.B, P.H, P.W, P.c, None, out_rows, None, None, ACT_NONE, None, None)
+
+    def impflow_conv3_power_series(self, plan, pre0, d1, d2, v_rows, coeffs, n, w_rows, stream):
+        P = self._plan(plan)
+        nel = P.B * P.H * P.W * P.c
+        w = _f32(w_rows, nel)
+        w[:] = _f32(v_rows, nel)
+        cur, curp = self._tmp(nel)
+        cur[:] = w
+        for k in range(n):
+            nxt, nxtp = self._tmp(nel)
+            assert self.impflow_conv3_vjp(plan, pre0, d1, d2, curp, nxtp, None) == 0
+            w += np.float32(coeffs[k]) * nxt
+            cur, curp = nxt, nxtp
+        return 0
+
+    def impflow_conv3_broyden(self, plan, mode, rhs_rows, pre0, d1, d2, xa, xb, ga, gb, low_x, low_g, Ut, Vt, sample_sq,
+                              low_sq, partial, state_dev, state_host, threshold, eps_scaled, stream):
+        P = self._plan(plan)
+        nel = P.B * P.H * P.W * P.c
+        d = P.H * P.W * P.c
+        rhs = _f32(rhs_rows, nel)
+
+        def eval_g(xp, gp):
+            t, tp = self._tmp(nel)
+            if mode == 0:
+                assert self.impflow_conv3_forward(plan, xp, tp, None, None, None) == 0
+                _f32(gp, nel)[:] = rhs - t - _f32(xp, nel)
+            else:
+                assert self.impflow_conv3_vjp(plan, pre0, d1, d2, xp, tp, None) == 0
+                _f32(gp, nel)[:] = t + _f32(xp, nel) - rhs
+
+        x_old, xn, g_old, gn = xa, xb, ga, gb
+        eval_g(x_old, g_old)
+        self.impflow_broyden_begin(x_old, g_old, xn, low_x, low_g, sample_sq, low_sq, partial, state_dev, P.B, d,
+                                   threshold, eps_scaled, None)
+        while _state(state_dev)[0]['active']:
+            eval_g(xn, gn)
+            self.impflow_broyden_step(x_old, g_old, xn, gn, Ut, Vt, low_x, low_g, sample_sq, low_sq, partial, state_dev,
+                                      P.B, d, threshold, None)
+            x_old, xn = xn, x_old
+            g_old, gn = gn, g_old
+        ctypes.memmove(_addr(state_host), _addr(state_dev), STATE_DTYPE.itemsize)
+        return 0
+
     # ---- spectral (csrc/spectral.cu) ----
     def impflow_sn_scale(self, W, sigma, coeff, out, scale_out, n, stream):
         sg = _f32(sigma, 1)[0]
