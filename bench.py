@@ -82,15 +82,10 @@ def build_model(pkg, wl, batch):
 
 
 def update_lipschitz(pkg, model, n_iterations=None):
-    """train_img.py:786-792 (train_toy.py:174-179 with n_iterations); the frozen *_copy twins are skipped
-    (overwritten at the next forward, SURVEY.md quirk #11)."""
-    BL = pkg.layers.base
-    with torch.no_grad():
-        for name, m in model.named_modules():
-            if '_copy' in name:
-                continue
-            if isinstance(m, (BL.InducedNormConv2d, BL.InducedNormLinear)):
-                m.compute_weight(update=True, n_iterations=n_iterations)
+    """train_img.py:786-792 (train_toy.py:174-179 with n_iterations): power-iteration refresh of every
+    induced-norm layer after the optimiser step; the package fans the independent layers out over side
+    streams (the frozen *_copy twins are skipped, SURVEY.md quirk #11)."""
+    pkg.layers.base.update_lipschitz(model, n_iterations)
 
 
 class ClockSampler(object):

@@ -182,6 +182,18 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
       const int ks = (int)(tile % splits);
       const long long m = (mn / n_tiles) * TC_BM + q * 32 + lane;
       const int n_base = (int)(mn % n_tiles) * BN;
+      // The act' / multiplier operand of a chunk is requested one chunk ahead (the first one before the
+      // accumulator is even complete), so its global-memory latency hides behind the MMAs / the previous chunk.
+      float dm[32], dm_next[32];
+      const bool dm_rows = e.dmul_pre != nullptr && splits == 1 && m < M && ((e.ldc & 7) == 0);
+      auto dm_fetch = [&](int c) {
+        const int n0f = n_base + c * 32;
+        if (dm_rows && c < BN / 32 && n0f + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) ld_global_v8(e.dmul_pre + m * e.ldc + n0f + j, dm_next + j);
+        }
+      };
+      dm_fetch(chunk0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -189,13 +201,9 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
         const int n0 = n_base + c * 32;
-        // the act' operand is requested before the accumulator read so that its latency hides behind it
-        float dm[32];
-        const bool dm_vec = e.dmul_pre != nullptr && splits == 1 && m < M && (n0 + 32 <= N) && ((e.ldc & 7) == 0);
-        if (dm_vec) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) ld_global_v8(e.dmul_pre + m * e.ldc + n0 + j, dm + j);
-        }
+        for (int j = 0; j < 32; ++j) dm[j] = dm_next[j];
+        dm_fetch(c + TC_EPI_WARPS / 4);
         tmem_ld32(taddr, r);
         if (splits > 1) {
           if (m < M && n0 < N) {

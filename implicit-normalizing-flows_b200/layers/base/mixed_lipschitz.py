@@ -14,7 +14,7 @@ import torch.nn.init as init
 
 from ... import _cabi, ops
 
-__all__ = ['InducedNormLinear', 'InducedNormConv2d']
+__all__ = ['InducedNormLinear', 'InducedNormConv2d', 'update_lipschitz']
 
 
 def _check_norms(domain, codomain):
@@ -379,3 +379,43 @@ class InducedNormConv2d(nn.Module):
         s += ', coeff={}, domain={:.2f}, codomain={:.2f}, n_iters={}, atol={}, rtol={}'.format(
             self.coeff, self.domain, self.codomain, self.n_iterations, self.atol, self.rtol)
         return s
+
+
+_side_streams = {}
+
+
+def update_lipschitz(model, n_iterations=None, n_streams=8):
+    """The per-step power-iteration refresh of every induced-norm layer (train_img.py:786-792,
+    train_toy.py:174-179 with n_iterations): `compute_weight(update=True)` under no_grad.
+
+    The layers are independent and each refresh is one or two latency-bound launches (a single-CTA matrix
+    power iteration or the cooperative conv one), so they are fanned out over side streams and joined
+    back into the current stream.  The frozen `*_copy` twins are skipped: imBlock.forward overwrites
+    them from the live nets before their next use (SURVEY.md quirk #11)."""
+    mods = [m for name, m in model.named_modules()
+            if '_copy' not in name and isinstance(m, (InducedNormConv2d, InducedNormLinear))]
+    if not mods:
+        return
+    dev = mods[0].weight.device
+    with torch.no_grad():
+        ready = all((not isinstance(m, InducedNormConv2d)) or m.is_initialized() for m in mods)
+        if dev.type != 'cuda' or n_streams <= 1 or len(mods) < 2 or not ready:
+            for m in mods:
+                m.compute_weight(update=True, n_iterations=n_iterations)
+            return
+        pool = _side_streams.setdefault(dev.index, [])
+        while len(pool) < n_streams:
+            pool.append(torch.cuda.Stream(device=dev))
+        used = pool[:min(n_streams, len(mods))]
+        main = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        for s in used:
+            s.wait_event(start)
+        for i, m in enumerate(mods):
+            with torch.cuda.stream(used[i % len(used)]):
+                m.compute_weight(update=True, n_iterations=n_iterations)
+        for s in used:
+            done = torch.cuda.Event()
+            done.record(s)
+            main.wait_event(done)
