@@ -214,6 +214,47 @@ def run_cpu_reference_mlp(pkg, wl, steps, warmup, batch, threads=None):
             'fwd_nstep': stats.get('fwd_nstep', [])[-6:], 'bwd_nstep': stats.get('bwd_nstep', [])[-6:]}
 
 
+def solver_roofline(pkg, B, d, T, n_iter, flush, hbm_gbs, peak_src):
+    """HBM roofline of the Broyden solver algebra (k_norm_decide + k_update, csrc/broyden.cu) at one (B, d):
+    n_iter iterations of impflow_broyden_step on random residuals, each timed alone with CUDA events (L2
+    flushed).  Algorithmic bytes of iteration i (history rank i-1): (6 + 2i) * d * 4 per sample
+    (SURVEY.md section 8d)."""
+    import ctypes
+    from impflow_b200.layers import broyden as _b
+    cabi = pkg._cabi
+    lib = cabi.load()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    wk = _b._workspace(B, d, T, dev)
+    g = [torch.randn(B, d, device=dev) for _ in range(2)]
+    wk.xa.normal_()
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    cabi.check(lib.impflow_broyden_begin(vp(wk.xa), vp(g[0]), vp(wk.xb), vp(wk.low_x), vp(wk.low_g), vp(wk.sample_sq),
+                                         vp(wk.low_sq), vp(wk.partial), vp(wk.state), B, d, T, 1e-30, cabi.stream()),
+               'broyden_begin')
+    x_old, xn, g_old, gn = wk.xa, wk.xb, g[0], g[1]
+    t_ms, bytes_alg = 0.0, 0.0
+    for i in range(1, n_iter + 1):
+        gn.normal_()
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cabi.check(lib.impflow_broyden_step(vp(x_old), vp(g_old), vp(xn), vp(gn), vp(wk.Ut), vp(wk.Vt), vp(wk.low_x),
+                                            vp(wk.low_g), vp(wk.sample_sq), vp(wk.low_sq), vp(wk.partial),
+                                            vp(wk.state), B, d, T, cabi.stream()), 'broyden_step')
+        e1.record()
+        torch.cuda.synchronize()
+        t_ms += e0.elapsed_time(e1)
+        bytes_alg += (6 + 2 * i) * d * 4.0 * B
+        x_old, xn, g_old, gn = xn, x_old, gn, g_old
+    ach = bytes_alg / (t_ms / 1e3) / 1e9
+    return {'kernel': 'k_norm_decide + k_update (Broyden rank-1 update and break rules, csrc/broyden.cu)',
+            'bound': 'hbm', 'achieved': ach, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach / hbm_gbs, 'traffic': None,
+            'peak_source': peak_src, 'shape': {'B': B, 'd': d, 'iterations': n_iter},
+            'us_per_iteration': t_ms * 1e3 / n_iter,
+            'note': 'algorithmic bytes (6+2i)*d*4 per sample for iteration i; the kernel re-reads the rank-(i-1) '
+                    'history once more than the minimum (see DESIGN.md section 4)'}
+
+
 def _host_init_lazy_buffers(sd, wl, x):
     """Shape the conv u/v buffers and ActNorm parameters on the host the way the reference's first
     `model(x, restore=True)` does (mixed_lipschitz.py:195-239, act_norm.py:25-37)."""
@@ -503,6 +544,16 @@ def main():
     }
     if len(order) > 1:
         line['roofline_secondary'] = roof(order[1])
+    if not is_mlp:
+        # the solver-algebra phase against the HBM roofline: the bench shape (latency-bound: 0.8 MB per
+        # vector) and the classifier shape of SURVEY.md section 8 (B=128, d=65536: 2 GB of history)
+        hbm = peaks.get('hbm_gbs', 6650.0)
+        hsrc = 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
+        try:
+            line['roofline_solver'] = [solver_roofline(pkg, batch, n_dims, 30, 6, flush, hbm, hsrc),
+                                       solver_roofline(pkg, 128, 65536, 30, 8, flush, hbm, hsrc)]
+        except Exception as exc:
+            line['roofline_solver'] = 'failed: %r' % (exc,)
     if world == 1 and not args.no_cpu_baseline:
         try:
             res = run_cpu_reference(args.workload, 2, 1, args.cpu_batch)
