@@ -18,7 +18,8 @@
 //     [384,448)  A ring slot 1                       [448,512) X0 hi | lo
 // Warps: 0 = TMA producer (weight chunks: W2 256x32 + W1 32x32 per K chunk, then W3 32x32 chunks;
 // 3-stage ring of 72 KB), 1 = MMA issuer (tcgen05.mma kind::tf32, A from TMEM, B from smem),
-// 2 = TMEM allocator, 4..11 = transform warps (tcgen05.ld -> psi -> tf32 split -> tcgen05.st).
+// 2 = TMEM allocator, 4..19 = transform warps (4 per TMEM lane quarter, 8 columns of a chunk each:
+// tcgen05.ld -> psi -> tf32 split -> tcgen05.st).
 #include "tc_common.cuh"
 
 namespace impflow {
@@ -28,7 +29,8 @@ constexpr int BF_W2_BYTES = 256 * TC_BK * 4;   // 32 KB per plane
 constexpr int BF_W1_BYTES = 32 * TC_BK * 4;    // 4 KB per plane
 constexpr int BF_STAGE_BYTES = 2 * BF_W2_BYTES + 2 * BF_W1_BYTES;   // 72 KB
 constexpr int BF_SMEM_BYTES = BF_NS * BF_STAGE_BYTES + 1024 + 256;
-constexpr int BF_XF_WARPS = 8;
+constexpr int BF_XF_WARPS = 16;                // transform warps: 4 per TMEM lane quarter
+constexpr int BF_CW = 32 / (BF_XF_WARPS / 4);  // columns of a 32-column chunk per transform warp
 constexpr int BF_THREADS = 128 + 32 * BF_XF_WARPS;
 constexpr uint32_t BF_COL_ACC = 0, BF_COL_S = 256, BF_COL_A = 320, BF_COL_X0 = 448;
 
@@ -61,71 +63,78 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void split16(const float* v, uint32_t* hi, uint32_t* lo) {
+// tf32 hi/lo split: round-to-nearest, ties away from zero (what cvt.rna.tf32.f32 does for finite values),
+// written as two integer ops so that the transform loop stays short
+__device__ __forceinline__ void split8(const float* v, uint32_t* hi, uint32_t* lo) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j]));
+  for (int j = 0; j < BF_CW; ++j) {
+    const uint32_t hb = (__float_as_uint(v[j]) + 0x1000u) & 0xffffe000u;
     hi[j] = hb;
     lo[j] = __float_as_uint(v[j] - __uint_as_float(hb));
   }
 }
-__device__ __forceinline__ void ld16(const float* p, float* v) {
+__device__ __forceinline__ void ld8(const float* p, float* v) {
   const float4* p4 = reinterpret_cast<const float4*>(p);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < BF_CW / 4; ++j) {
     const float4 t = __ldg(p4 + j);
     v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
   }
 }
-__device__ __forceinline__ void st16(float* p, const float* v) {
+__device__ __forceinline__ void st8(float* p, const float* v) {
   float4* p4 = reinterpret_cast<float4*>(p);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) p4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  for (int j = 0; j < BF_CW / 4; ++j) p4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-// psi: 16 accumulator values of one row -> the next layer's operand values.
+// psi: the accumulator values of one row segment -> the next layer's operand values.
+//   multiplier mode: a = acc * mul;   activation mode: v = acc + bias (optionally stored), a = act(v).
+// LipSwish x*sigmoid(beta*x)/1.1 runs on the SFU fast paths with the constants folded:
+//   e = 2^(x * (-beta*log2 e)),  a = x * rcp(1.1 + 1.1 e)       (5 instructions per element)
 template <int ACT>
-__device__ __forceinline__ void psi16(const uint32_t* r, float* a, const float* bias, const float* mul, bool has_mul,
-                                      float* pre_out, bool store_pre, float beta) {
+__device__ __forceinline__ void psi8(const uint32_t* r, float* a, const float* bias, const float* mul, bool has_mul,
+                                     float* pre_out, bool store_pre, float beta, float neg_beta_log2e) {
   if (has_mul) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = __uint_as_float(r[j]) * mul[j];
+    for (int j = 0; j < BF_CW; ++j) a[j] = __uint_as_float(r[j]) * mul[j];
     return;
   }
-  float v[16];
+  float v[BF_CW];
   if (bias != nullptr) {
-    float b[16];
-    ld16(bias, b);
+    float b[BF_CW];
+    ld8(bias, b);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + b[j];
+    for (int j = 0; j < BF_CW; ++j) v[j] = __uint_as_float(r[j]) + b[j];
   } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    for (int j = 0; j < BF_CW; ++j) v[j] = __uint_as_float(r[j]);
   }
-  if (store_pre) st16(pre_out, v);
+  if (store_pre) st8(pre_out, v);
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    a[j] = (ACT == IMPFLOW_ACT_LIPSWISH) ? lipswish_fast(v[j], beta) : act_eval<ACT>(v[j], 0, beta);
+  for (int j = 0; j < BF_CW; ++j) {
+    if (ACT == IMPFLOW_ACT_LIPSWISH) {
+      float e, s;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[j] * neg_beta_log2e));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(fmaf(e, 1.1f, 1.1f)));
+      a[j] = v[j] * s;
+    } else {
+      a[j] = act_eval<ACT>(v[j], 0, beta);
+    }
+  }
 }
 
 template <int ACT>
@@ -313,94 +322,99 @@ k_branch3(const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ C
     }
   } else if (warp >= 4) {
     // ================= transform warps =================
-    const int q = warp & 3;               // TMEM lane quarter
-    const int h = (warp - 4) >> 2;        // which 16 of a chunk's 32 columns
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int cw0 = ((warp - 4) >> 2) * BF_CW; // first of this warp's columns inside a 32-column chunk
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float beta1 = args.beta1 != nullptr ? __ldg(args.beta1) : 0.f;
     const float beta2 = args.beta2 != nullptr ? __ldg(args.beta2) : 0.f;
+    const float nbl1 = -1.4426950408889634f * beta1, nbl2 = -1.4426950408889634f * beta2;
     const bool has_mul1 = args.mul1 != nullptr, has_mul2 = args.mul2 != nullptr;
     const int C = args.C;
     uint32_t ga = 0, gs = 0, it = 0;
+    // the im2col row segment of the NEXT item is fetched while the current item's tail is processed
+    float x0_next[BF_CW];
+    auto fetch_x0 = [&](long long item) {
+      const long long mm = (item / n_halves) * TC_BM + q * 32 + lane;
+      if (item < num_items && mm < args.M) {
+        ld8(args.x0 + mm * args.ldx + cw0, x0_next);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BF_CW; ++j) x0_next[j] = 0.f;
+      }
+    };
+    fetch_x0(blockIdx.x);
     for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int nh = (int)(item % n_halves);
       const long long m = (item / n_halves) * TC_BM + q * 32 + lane;
       const bool valid = m < args.M;
-      uint32_t hi[16], lo[16];
-      float a[16];
-      float mul[16], mul_next[16];      // multiplier rows are fetched one chunk ahead of their use
-      if (has_mul1 && valid) ld16(args.mul1 + m * C + h * 16, mul_next);
+      uint32_t hi[BF_CW], lo[BF_CW];
+      float a[BF_CW];
+      float mul[BF_CW], mul_next[BF_CW];      // multiplier rows are fetched one chunk ahead of their use
+      if (has_mul1 && valid) ld8(args.mul1 + m * C + cw0, mul_next);
       // ---- X0 row -> TMEM (hi | lo)
-      {
-        float v[16];
-        if (valid) {
-          ld16(args.x0 + m * args.ldx + h * 16, v);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-        split16(v, hi, lo);
-        mbar_wait(x0_empty, (it & 1) ^ 1);
-        tc_fence_after();
-        tmem_st16(tmem_base + lane_base + BF_COL_X0 + h * 16, hi);
-        tmem_st16(tmem_base + lane_base + BF_COL_X0 + 32 + h * 16, lo);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(x0_full);
-      }
+      split8(x0_next, hi, lo);
+      mbar_wait(x0_empty, (it & 1) ^ 1);
+      tc_fence_after();
+      tmem_st8(tmem_base + lane_base + BF_COL_X0 + cw0, hi);
+      tmem_st8(tmem_base + lane_base + BF_COL_X0 + 32 + cw0, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x0_full);
       // ---- layer 1 chunks: S -> psi1 -> A ring
       for (int kc = 0; kc < NC; ++kc) {
-        const int n0 = kc * TC_BK + h * 16;
+        const int n0 = kc * TC_BK + cw0;
         if (has_mul1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mul[j] = valid ? mul_next[j] : 0.f;
-          if (valid && kc + 1 < NC) ld16(args.mul1 + m * C + n0 + TC_BK, mul_next);
+          for (int j = 0; j < BF_CW; ++j) mul[j] = valid ? mul_next[j] : 0.f;
+          if (valid && kc + 1 < NC) ld8(args.mul1 + m * C + n0 + TC_BK, mul_next);
         }
-        if (kc == NC - 1 && has_mul2 && valid) ld16(args.mul2 + m * C + nh * 256 + h * 16, mul_next);
+        if (kc == NC - 1 && has_mul2 && valid) ld8(args.mul2 + m * C + nh * 256 + cw0, mul_next);
         const uint32_t sc = gs + kc, buf = sc & 1;
         mbar_wait(&s_full[buf], (sc >> 1) & 1);
         tc_fence_after();
-        uint32_t r[16];
-        tmem_ld16(tmem_base + lane_base + BF_COL_S + buf * 32 + h * 16, r);
+        uint32_t r[BF_CW];
+        tmem_ld8(tmem_base + lane_base + BF_COL_S + buf * 32 + cw0, r);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[buf]);
-        psi16<ACT>(r, a, args.bias1 != nullptr ? args.bias1 + n0 : nullptr, mul, has_mul1,
-                   args.pre1_out != nullptr ? args.pre1_out + m * C + n0 : nullptr,
-                   args.pre1_out != nullptr && valid && nh == 0, beta1);
-        split16(a, hi, lo);
+        psi8<ACT>(r, a, args.bias1 != nullptr ? args.bias1 + n0 : nullptr, mul, has_mul1,
+                  args.pre1_out != nullptr ? args.pre1_out + m * C + n0 : nullptr,
+                  args.pre1_out != nullptr && valid && nh == 0, beta1, nbl1);
+        split8(a, hi, lo);
         const uint32_t ac = ga + kc, slot = ac & 1;
         mbar_wait(&a_empty[slot], ((ac >> 1) & 1) ^ 1);
         tc_fence_after();
-        tmem_st16(tmem_base + lane_base + BF_COL_A + slot * 64 + h * 16, hi);
-        tmem_st16(tmem_base + lane_base + BF_COL_A + slot * 64 + 32 + h * 16, lo);
+        tmem_st8(tmem_base + lane_base + BF_COL_A + slot * 64 + cw0, hi);
+        tmem_st8(tmem_base + lane_base + BF_COL_A + slot * 64 + 32 + cw0, lo);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[slot]);
       }
       ga += NC, gs += NC;
+      fetch_x0(item + gridDim.x);
       // ---- layer 2 accumulator: ACC -> psi2 -> A ring (layer-3 operand)
       mbar_wait(acc_full, it & 1);
       tc_fence_after();
       for (int c2 = 0; c2 < NC3; ++c2) {
-        const int n0 = nh * 256 + c2 * TC_BK + h * 16;
+        const int n0 = nh * 256 + c2 * TC_BK + cw0;
         if (has_mul2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mul[j] = valid ? mul_next[j] : 0.f;
-          if (valid && c2 + 1 < NC3) ld16(args.mul2 + m * C + n0 + TC_BK, mul_next);
+          for (int j = 0; j < BF_CW; ++j) mul[j] = valid ? mul_next[j] : 0.f;
+          if (valid && c2 + 1 < NC3) ld8(args.mul2 + m * C + n0 + TC_BK, mul_next);
         }
-        uint32_t r[16];
-        tmem_ld16(tmem_base + lane_base + BF_COL_ACC + c2 * TC_BK + h * 16, r);
-        psi16<ACT>(r, a, args.bias2 != nullptr ? args.bias2 + n0 : nullptr, mul, has_mul2,
-                   args.pre2_out != nullptr ? args.pre2_out + m * C + n0 : nullptr,
-                   args.pre2_out != nullptr && valid, beta2);
-        split16(a, hi, lo);
+        uint32_t r[BF_CW];
+        tmem_ld8(tmem_base + lane_base + BF_COL_ACC + c2 * TC_BK + cw0, r);
+        psi8<ACT>(r, a, args.bias2 != nullptr ? args.bias2 + n0 : nullptr, mul, has_mul2,
+                  args.pre2_out != nullptr ? args.pre2_out + m * C + n0 : nullptr,
+                  args.pre2_out != nullptr && valid, beta2, nbl2);
+        split8(a, hi, lo);
         const uint32_t ac = ga + c2, slot = ac & 1;
         mbar_wait(&a_empty[slot], ((ac >> 1) & 1) ^ 1);
         tc_fence_after();
-        tmem_st16(tmem_base + lane_base + BF_COL_A + slot * 64 + h * 16, hi);
-        tmem_st16(tmem_base + lane_base + BF_COL_A + slot * 64 + 32 + h * 16, lo);
+        tmem_st8(tmem_base + lane_base + BF_COL_A + slot * 64 + cw0, hi);
+        tmem_st8(tmem_base + lane_base + BF_COL_A + slot * 64 + 32 + cw0, lo);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -411,16 +425,16 @@ k_branch3(const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ C
       mbar_wait(acc3_full, it & 1);
       tc_fence_after();
       {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + lane_base + BF_COL_S + 32 + h * 16, r);
+        uint32_t r[BF_CW];
+        tmem_ld8(tmem_base + lane_base + BF_COL_S + 32 + cw0, r);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc3_empty);
         if (valid) {
-          float* dst = args.out + m * args.ldo + h * 16;
+          float* dst = args.out + m * args.ldo + cw0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (h * 16 + j < args.N3) {
+          for (int j = 0; j < BF_CW; ++j) {
+            if (cw0 + j < args.N3) {
               if (n_halves > 1) {
                 atomicAdd(dst + j, __uint_as_float(r[j]));    // exactly two addends on zeros: order-independent
               } else {

@@ -83,11 +83,11 @@ __device__ __forceinline__ float act_eval(float x, int order, float beta) {
 // LipSwish x*sigmoid(beta*x)/1.1 on the SFU fast paths (ex2.approx + rcp.approx: ~3 ulp, the same order
 // as the fp32 accumulation error of the GEMMs around it); used by the GEMM / tile-kernel epilogues.
 __device__ __forceinline__ float lipswish_fast(float x, float beta) {
+  // e = 2^(-beta x log2 e);  x / (1.1 (1 + e)): e = +inf gives rcp(inf) = 0 and x * 0 = 0 for finite x
   float e, s;
-  const float t = fminf(-1.4426950408889634f * beta * x, 126.f);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.f + e));
-  return x * s * (1.f / 1.1f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (-1.4426950408889634f * beta)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(fmaf(e, 1.1f, 1.1f)));
+  return x * s;
 }
 
 // d/d(beta) of the order-th x-derivative of LipSwish (beta = softplus(raw beta)).

@@ -290,8 +290,8 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
               float h[8], l[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                uint32_t hb;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j + u]));
+                // round to nearest, ties away (= cvt.rna.tf32.f32 for finite values) in two integer ops
+                const uint32_t hb = (__float_as_uint(v[j + u]) + 0x1000u) & 0xffffe000u;
                 h[u] = __uint_as_float(hb);
                 l[u] = v[j + u] - h[u];
               }
