@@ -49,13 +49,14 @@ FUSED3 = {'on': True}
 # series / Broyden solve; off = the Python-driven launch sequences below.
 CONV3_NATIVE = {'on': True}
 
-_conv3_ws = {}      # device index -> workspace tensor shared by every plan (grown on demand)
+_conv3_ws = {}      # (device index, stream) -> workspace tensor shared by every plan used on that stream
 
 
 def _conv3_workspace(n_floats, device):
-    t = _conv3_ws.get(device.index)
+    key = (device.index, torch._C._cuda_getCurrentRawStream(device.index) if device.type == 'cuda' else 0)
+    t = _conv3_ws.get(key)
     if t is None or t.numel() < n_floats:
-        t = _conv3_ws[device.index] = torch.empty(int(n_floats), device=device, dtype=torch.float32)
+        t = _conv3_ws[key] = torch.empty(int(n_floats), device=device, dtype=torch.float32)
     return t
 
 
@@ -398,9 +399,11 @@ class BranchProgram(object):
         lib = _cabi.load()
         wsp = _conv3_workspace(lib.impflow_conv3_workspace_floats(B, H, Wd, c, C, k0), w0.fwd.device)
         key = (self._key, meta[1], FUSED3['on'], wsp.data_ptr())
-        cached = getattr(self, '_conv3_cache', None)
-        if cached is not None and cached[0] == key:
-            return cached[1]
+        cache = getattr(self, '_conv3_cache', None)
+        if cache is None or cache.get('weights') != self._key:
+            cache = self._conv3_cache = {'weights': self._key}       # plans of older weights are dropped
+        if key in cache:
+            return cache[key][0]
         act0 = self.stages[0][0]
         P = _cabi.Conv3Plan()
         P.B, P.H, P.W, P.c, P.C, P.k0 = B, H, Wd, c, C, k0
@@ -419,7 +422,7 @@ class BranchProgram(object):
         P.W1b_hi, P.W1b_lo = dp(w0.bwd_split[0]), dp(w0.bwd_split[1])
         P.ws = wsp.data_ptr()
         # the weights / betas stay alive in self._weights and the _Act objects; the plan only borrows them
-        self._conv3_cache = (key, P, (ws, wsp, [a.beta_sp() for a in self._acts() if a is not None]))
+        cache[key] = (P, (ws, wsp, [a.beta_sp() for a in self._acts() if a is not None]))
         return P
 
     @staticmethod

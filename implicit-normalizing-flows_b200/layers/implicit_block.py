@@ -84,6 +84,56 @@ def branch_apply(nnet, x):
     return _BranchApply.apply(x, prog, *prog.params)
 
 
+# Independent halves of a block's work (the log-det estimates of the x- and z-branch) on two streams.
+OVERLAP = {'on': True}
+_side = {}
+
+
+class _overlap(object):
+    """`with _overlap(t) as side: with side: <work A>; <work B>` runs A on a side stream that forks from and
+    joins back into the current stream of t's device; a no-op (A then B in order) off the GPU."""
+
+    def __init__(self, like):
+        self.dev = like.device if (like.is_cuda and OVERLAP['on']) else None
+
+    def __enter__(self):
+        if self.dev is None:
+            import contextlib
+            return contextlib.nullcontext()
+        self.main = torch.cuda.current_stream(self.dev)
+        self.side = _side.get(self.dev.index)
+        if self.side is None:
+            self.side = _side[self.dev.index] = torch.cuda.Stream(device=self.dev)
+        fork = torch.cuda.Event()
+        fork.record(self.main)
+        self.side.wait_event(fork)
+        return torch.cuda.stream(self.side)
+
+    def __exit__(self, *exc):
+        if self.dev is not None:
+            join = torch.cuda.Event()
+            join.record(self.side)
+            self.main.wait_event(join)
+        return False
+
+
+def _sync_twin(dst, src):
+    """dst.load_state_dict(src.state_dict()) for two structurally identical nets, as one multi-tensor copy
+    (the reference refreshes the frozen twins after every forward, implicit_block.py:228-229).  Falls back
+    to load_state_dict whenever a shape differs (lazily shaped u / v before their first use)."""
+    with torch.no_grad():
+        d = list(dst.parameters()) + list(dst.buffers())
+        s = list(src.parameters()) + list(src.buffers())
+        if len(d) == len(s) and all(a.shape == b.shape and a.dtype == b.dtype for a, b in zip(d, s)):
+            torch._foreach_copy_(d, [t.detach() for t in s])
+            for m in dst.modules():           # python mirrors of buffers that load_state_dict would reset
+                if hasattr(m, '_hw'):
+                    m._hw = None
+                    m._init_known = None
+            return
+    dst.load_state_dict(src.state_dict())
+
+
 _pinned = {}
 
 
@@ -271,8 +321,8 @@ class imBlock(nn.Module):
         self.solver_stats['fwd'] = RootFind.last_info
         # re-attach: gradients reach the branch parameters through this expression (:227)
         z = branch_apply(self.nnet_x, z0) - branch_apply(self.nnet_z, z.detach()) + z0
-        self.nnet_x_copy.load_state_dict(self.nnet_x.state_dict())
-        self.nnet_z_copy.load_state_dict(self.nnet_z.state_dict())
+        _sync_twin(self.nnet_x_copy, self.nnet_x)         # == load_state_dict(state_dict()) (:228-229)
+        _sync_twin(self.nnet_z_copy, self.nnet_z)
         if FUSED['on']:      # the frozen twins hold the same weights: share the live nets' programs
             self.nnet_z_copy._impflow_program = _program(self.nnet_z)
             self.nnet_x_copy._impflow_program = _program(self.nnet_x)
@@ -356,10 +406,18 @@ class imBlock(nn.Module):
                 else:
                     estimator_fn = basic_logdet_estimator
                 if self.training and self.grad_in_forward:
+                    # the two estimates are independent: the z-branch runs on a side stream so that kernels
+                    # that cannot fill the GPU on their own (the deeper, smaller scales) overlap
+                    # (only the graph-free evaluations: the autograd nodes are created on the current stream)
+                    est = MemoryEfficientLogDetEstimator
+                    with _overlap(x) as side:
+                        with side:
+                            pz = est.payload(estimator_fn, self.nnet_z, z, n_power_series, vareps_z, coeff_fn, True)
+                        px = est.payload(estimator_fn, self.nnet_x, x, n_power_series, vareps_x, coeff_fn, True)
                     logdet_x = mem_eff_wrapper(estimator_fn, self.nnet_x, x, n_power_series, vareps_x, coeff_fn,
-                                               self.training)
+                                               self.training, px)
                     logdet_z = mem_eff_wrapper(estimator_fn, self.nnet_z, z, n_power_series, vareps_z, coeff_fn,
-                                               self.training)
+                                               self.training, pz)
                 else:
                     x = x.requires_grad_(True)
                     z = z.requires_grad_(True)
@@ -420,25 +478,37 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
     are taken immediately and only scaled in backward (implicit_block.py:373-415)."""
 
     @staticmethod
-    def forward(ctx, estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training, *g_params):
-        ctx.training = training
+    def payload(estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training):
+        """The graph-free evaluation (estimate, d/dx, d/dtheta) of the Neumann estimator: fused forward, the
+        n-term vjp chain, then the hand-derived tangent / reverse sweeps.  Plain tensors in and out, so it can
+        run on a side stream; None when this branch / estimator has no graph-free form."""
         prog = _program(gnet)
-        if training and prog is not None and estimator_fn is neumann_logdet_estimator:
-            # graph-free: fused forward, n fused vjps, then the hand-derived tangent / reverse sweeps
-            with torch.no_grad():
-                xd = x.detach()
-                _, saved = prog.forward_saved(xd)
-                coeffs = [float((-1) ** k * coeff_fn(k)) for k in range(1, n_power_series + 1)]
-                neumann_vjp = prog.neumann_chain(saved, vareps, coeffs)       # one C call when native
-                if neumann_vjp is None:
-                    vjp = neumann_vjp = vareps
-                    for k in range(1, n_power_series + 1):
-                        vjp = prog.vjp(vjp, saved)
-                        neumann_vjp = ops.lincomb3(neumann_vjp, 1.0, vjp, coeffs[k - 1])
-                logdetgrad, grad_x, grad_params = prog.neumann(saved, neumann_vjp, vareps)
+        if not (training and prog is not None and estimator_fn is neumann_logdet_estimator):
+            return None
+        with torch.no_grad():
+            xd = x.detach()
+            _, saved = prog.forward_saved(xd)
+            coeffs = [float((-1) ** k * coeff_fn(k)) for k in range(1, n_power_series + 1)]
+            neumann_vjp = prog.neumann_chain(saved, vareps, coeffs)       # one C call when native
+            if neumann_vjp is None:
+                vjp = neumann_vjp = vareps
+                for k in range(1, n_power_series + 1):
+                    vjp = prog.vjp(vjp, saved)
+                    neumann_vjp = ops.lincomb3(neumann_vjp, 1.0, vjp, coeffs[k - 1])
+            return prog.neumann(saved, neumann_vjp, vareps)
+
+    @staticmethod
+    def forward(ctx, estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training, payload, *g_params):
+        ctx.training = training
+        if payload is None:
+            payload = MemoryEfficientLogDetEstimator.payload(estimator_fn, gnet, x, n_power_series, vareps, coeff_fn,
+                                                             training)
+        if payload is not None:
+            logdetgrad, grad_x, grad_params = payload
             ctx.none_mask = [gp is None for gp in grad_params]
-            ctx.save_for_backward(grad_x, *[gp if gp is not None else xd.new_zeros(()) for gp in grad_params])
+            ctx.save_for_backward(grad_x, *[gp if gp is not None else grad_x.new_zeros(()) for gp in grad_params])
             return logdetgrad
+        prog = _program(gnet)
         with torch.enable_grad():
             x = x.detach().requires_grad_(True)
             g = gnet(x)
@@ -461,7 +531,7 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
         with torch.no_grad():
             grad_x = grad_x * dL
             grad_params = tuple(None if m else gp * dL for gp, m in zip(grad_params, ctx.none_mask))
-        return (None, None, grad_x, None, None, None, None) + grad_params
+        return (None, None, grad_x, None, None, None, None, None) + grad_params
 
 
 def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, program=None):
@@ -506,11 +576,11 @@ def neumann_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, p
     return ops.rowdot_fn(vjp_jac, vareps)
 
 
-def mem_eff_wrapper(estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training):
+def mem_eff_wrapper(estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training, payload=None):
     if not isinstance(gnet, nn.Module):
         raise ValueError('g is required to be an instance of nn.Module.')
     return MemoryEfficientLogDetEstimator.apply(estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training,
-                                                *list(gnet.parameters()))
+                                                payload, *list(gnet.parameters()))
 
 
 # ---- roulette helpers: python floats, global NumPy RNG (implicit_block.py:457-483) -----------

@@ -62,8 +62,8 @@ def timed(name, fn):
 
 ib.RootFind.broyden_find_root = staticmethod(timed('fwd solve (RootFind)', ib.RootFind.broyden_find_root))
 ib.branch_apply = timed('re-attach branch_apply', ib.branch_apply)
-ib.MemoryEfficientLogDetEstimator.forward = staticmethod(
-    timed('logdet estimator fwd (chain + neumann)', ib.MemoryEfficientLogDetEstimator.forward))
+ib.MemoryEfficientLogDetEstimator.payload = staticmethod(
+    timed('logdet estimator fwd (chain + neumann)', ib.MemoryEfficientLogDetEstimator.payload))
 ib.imBlock.Backward.backward = staticmethod(timed('implicit backward solve', ib.imBlock.Backward.backward))
 ib._BranchApply.backward = staticmethod(timed('re-attach backward_full', ib._BranchApply.backward))
 bp.BranchProgram.neumann = timed('  of which neumann sweeps', bp.BranchProgram.neumann)
