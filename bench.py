@@ -356,6 +356,8 @@ def main():
         print(json.dumps(line))
         return
 
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+        os.environ['NCCL_DEBUG'] = 'WARN'        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     import torch.distributed as dist
     assert torch.cuda.is_available(), 'bench.py --impl b200 needs a GPU (there is no CPU fallback)'
     torch.cuda.set_device(local_rank)

@@ -402,7 +402,17 @@ extern "C" int impflow_gemm_nt(const float* A, long long lda, const float* Bm, l
 }
 
 static int g_wide_tiles = 1;   // BN = 256 tiles for N >= 256 (halves the A-operand re-reads through L2)
-static int tc_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : ((N >= 256 && g_wide_tiles) ? 256 : 128)); }
+// Tile width: 256 halves the A-operand re-reads, but a problem with few row tiles fills more SMs (and
+// finishes in fewer, cheaper rounds) with 128-wide tiles: compare rounds x relative tile cost.
+static int tc_bn(int N, long long M = 1LL << 40) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N < 256 || !g_wide_tiles) return 128;
+  const long long m_tiles = (M + TC_BM - 1) / TC_BM;
+  const long long r256 = (m_tiles * ((N + 255) / 256) + 147) / 148;
+  const long long r128 = (m_tiles * ((N + 127) / 128) + 147) / 148;
+  return (r128 * 55 < r256 * 100) ? 128 : 256;
+}
 
 extern "C" int impflow_gemm_tc_set_wide_tiles(int on) {
   const int prev = g_wide_tiles;
@@ -412,7 +422,7 @@ extern "C" int impflow_gemm_tc_set_wide_tiles(int on) {
 
 extern "C" int impflow_gemm_tc_splits(long long M, int N, int K) {
   if (K % TC_BK != 0) return 1;
-  return pick_splits(M, N, K, tc_bn(N));
+  return pick_splits(M, N, K, tc_bn(N, M));
 }
 
 extern "C" int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long long lda, const float* B_hi,
@@ -440,8 +450,8 @@ extern "C" int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long lon
   // split-K only for the plain epilogue (weight-gradient GEMMs) and only if the caller gave a workspace
   int splits = 1;
   if (splitk_ws != nullptr && act_out == nullptr && dmul_pre == nullptr && split_hi == nullptr && pre_out != nullptr)
-    splits = pick_splits(M, N, K, tc_bn(N));
-  const int bn = tc_bn(N);
+    splits = pick_splits(M, N, K, tc_bn(N, M));
+  const int bn = tc_bn(N, M);
   if (bn == 32) return launch_tc<32>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
   if (bn == 64) return launch_tc<64>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
   if (bn == 256) return launch_tc<256>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
