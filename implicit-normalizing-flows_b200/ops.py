@@ -400,6 +400,12 @@ def record_branch3(M, C, N3, is_vjp, save_pre):
     GEMM_PROFILE['shapes'][key] = GEMM_PROFILE['shapes'].get(key, 0) + 1
 
 
+def _mark_written(*tensors):
+    """Kernels that update a caller's tensor in place through its raw pointer must bump its autograd version:
+    the host caches (effective weights, d sigma / d W) are keyed on `_version`."""
+    torch.autograd.graph.increment_version(tensors)
+
+
 def sn_power_iter(W2d, u, v, n_iterations, atol, rtol):
     """In-place power iteration on (u, v); returns (sigma (1,), iters (1,) int32) device tensors."""
     W2d = W2d.contiguous()
@@ -411,6 +417,8 @@ def sn_power_iter(W2d, u, v, n_iterations, atol, rtol):
                                              float(atol if atol is not None else 0.0),
                                              float(rtol if rtol is not None else 0.0), _cabi.stream()),
                 'sn_power_iter')
+    if n_it != 0:
+        _mark_written(u, v)
     return sigma, iters
 
 
@@ -431,6 +439,8 @@ def sn_power_iter_conv(W, u, v, h, w, n_iterations, atol, rtol):
         _cabi.ptr(W), _cabi.ptr(u), _cabi.ptr(v), _cabi.ptr(sigma), _cabi.iptr(iters), co, ci, h, w, n_it,
         float(atol if atol is not None else 0.0), float(rtol if rtol is not None else 0.0), _cabi.ptr(ws),
         _cabi.stream()), 'sn_power_iter_conv3x3')
+    if n_it != 0:
+        _mark_written(u, v)
     return sigma, iters
 
 

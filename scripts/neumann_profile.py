@@ -66,3 +66,18 @@ torch.cuda.synchronize()
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats('tottime').print_stats(25)
 print(s.getvalue()[:6000])
+
+import collections
+for name, fn in [('backward_full', lambda: prog.backward_full(saved, w)), ('neumann', lambda: prog.neumann(saved, w, v))]:
+    with torch.no_grad():
+        fn()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+    rows = sorted(prof.key_averages(), key=lambda e: -e.self_device_time_total)
+    tot = sum(e.self_device_time_total for e in rows)
+    print('---- %s: %.2f ms GPU' % (name, tot / 1e3))
+    for e in rows[:16]:
+        print('  %8.0f us %5.1f%% n=%3d  %s' % (e.self_device_time_total, 100 * e.self_device_time_total / tot, e.count,
+                                                e.key[:70]))

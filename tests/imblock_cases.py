@@ -256,3 +256,40 @@ def case_implicit_flow_density_step(golden):
         x_rec = model(z.detach(), inverse=True)
     assert rel_err(x_rec.cpu(), fx['x_rec']) < 1e-4
     assert rel_err(x_rec.cpu(), fx['x']) < 1e-3
+
+
+def case_sigma_cache_follows_power_iteration():
+    """u / v are updated in place by the power-iteration kernels: every host cache keyed on them (d sigma/d W,
+    the effective weights of the branch programs) must see the change (regression: stale sigma after
+    update_lipschitz)."""
+    import impflow_b200
+    from impflow_b200.branch_program import compile_branch
+    L = impflow_b200.layers
+    dev = DEV['device']
+    torch.manual_seed(3)
+    mk = lambda a, b, k: L.base.get_conv2d(a, b, k, 1, k // 2, coeff=0.9, n_iterations=None, domain=2, codomain=2,
+                                           atol=1e-3, rtol=1e-3)
+    net = torch.nn.Sequential(mk(3, 32, 3), L.base.Swish(), mk(32, 32, 1), L.base.Swish(), mk(32, 3, 3)).to(dev)
+    lin = L.base.get_linear(8, 16, coeff=0.9, n_iterations=None, atol=1e-3, rtol=1e-3, domain=2, codomain=2).to(dev)
+    x = torch.randn(2, 3, 8, 8, device=dev)
+    with torch.no_grad():
+        net(x)
+        prog = compile_branch(net)
+        prog.forward(x)
+        for m in list(net) + [lin]:
+            if hasattr(m, 'sigma_gradient'):
+                m.sigma_gradient()                    # fill the caches
+        for p in list(net.parameters()) + list(lin.parameters()):
+            if p.dim() > 1:
+                p.copy_(torch.randn_like(p))          # a big "optimiser step": the singular vectors move
+        L.base.update_lipschitz(net)
+        lin.compute_weight(update=True)
+        for m in list(net) + [lin]:
+            if not hasattr(m, 'sigma_gradient'):
+                continue
+            D = m.sigma_gradient()
+            sigma_cached = float((m.weight * D).sum())
+            assert abs(sigma_cached - float(m.scale)) < 1e-4 * max(1.0, abs(float(m.scale))), type(m).__name__
+        y_prog = prog.forward(x)
+        y_mod = net(x)
+    assert float((y_prog - y_mod).abs().max()) < 1e-5 * max(1.0, float(y_mod.abs().max()))

@@ -55,3 +55,7 @@ def test_implicit_flow_density_step(golden):
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_sigma_cache_follows_power_iteration():
+    cases.case_sigma_cache_follows_power_iteration()

@@ -213,3 +213,7 @@ def test_fused_paths_are_taken(golden, monkeypatch):
     assert counts['autograd_estimator'] == 0 and counts['module_calls'] == 0
     # the vjp chains and both solves run inside the native runtime (one C call each): csrc/conv3_plan.cu
     assert counts['chain'] == 2 and counts['solve'] >= 2 and counts['vjp'] == 1      # 1: dl_dx = v^T (I + J_x)
+
+
+def test_sigma_cache_follows_power_iteration():
+    cases.case_sigma_cache_follows_power_iteration()
