@@ -293,3 +293,57 @@ def case_sigma_cache_follows_power_iteration():
         y_prog = prog.forward(x)
         y_mod = net(x)
     assert float((y_prog - y_mod).abs().max()) < 1e-5 * max(1.0, float(y_mod.abs().max()))
+
+
+def case_training_trajectory_matches_oracle(golden, n_steps=3):
+    """Several full training steps (forward, bits/dim, backward, clip, Adam, update_lipschitz:
+    train_img.py:591-660, 786-792) of the small multiscale flow, product vs the oracle port, same seeds and
+    therefore the same roulette draws and probes: loss per step and forward solver iteration counts."""
+    from oracle import flow_oracle
+    pkg = _pkg()
+    layers = pkg.layers
+    fx = golden('flow_small')
+    B, c, hw = 4, 3, 8
+    model = pkg.ImplicitFlow(
+        (B, c, hw, hw), n_blocks=[1, 1], intermediate_dim=16, factor_out=False, quadratic=False,
+        init_layer=layers.LogitTransform(0.05), actnorm=True, fc_actnorm=False, batchnorm=False, dropout=0.,
+        fc=False, coeff=0.9, vnorms='2222', n_lipschitz_iters=None, sn_atol=1e-3, sn_rtol=1e-3,
+        n_power_series=None, n_dist='poisson', n_samples=1, kernels='3-1-3', activation_fn='swish', fc_end=False,
+        fc_idim=128, n_exact_terms=3, preact=True, neumann_grad=True, grad_in_forward=True, first_resblock=True,
+        learn_p=False, classification=False, classification_hdim=64, n_classes=10).to(DEV["device"])
+    x = torch.from_numpy(fx['x']).to(DEV["device"])
+    with torch.no_grad():
+        model(x, restore=True)
+    sd = {k: v.to(DEV["device"]) for k, v in sub_sd(fx, 'sd_').items()}
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    seed = int(fx['seed'])
+    ndim = c * hw * hw
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.99))
+    blocks = [m for m in model.modules() if isinstance(m, layers.imBlock)]
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    got, got_steps = [], []
+    for _ in range(n_steps):
+        opt.zero_grad()
+        z, dlogp = model(x, 0)
+        logpz = std_normal_logprob(z).view(z.size(0), -1).sum(1, keepdim=True)
+        bpd = -torch.mean(logpz - dlogp - np.log(256) * ndim) / ndim / np.log(2)
+        bpd.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.)
+        opt.step()
+        layers.base.update_lipschitz(model)
+        got.append(float(bpd))
+        got_steps.append([b.solver_stats['fwd']['nstep'] for b in blocks])
+    # oracle trajectory from the same state dict
+    cfg = dict(flow_oracle.CIFAR_CFG, n_exact_terms=3)
+    flow = flow_oracle.OracleFlow({k: v.clone() for k, v in sub_sd(fx, 'sd_').items()}, [1, 1], cfg, coeff=0.9)
+    oopt = torch.optim.Adam(flow.params, lr=1e-3, betas=(0.9, 0.99))
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    stats = {}
+    want = [flow.train_step(torch.from_numpy(fx['x']), oopt, stats) for _ in range(n_steps)]
+    np.testing.assert_allclose(got[0], want[0], rtol=1e-5)
+    np.testing.assert_allclose(got, want, rtol=2e-3)          # later steps inherit the 5e-3 gradient tolerance
+    assert sum(got_steps, []) == [int(v) for v in stats['fwd_nstep']]

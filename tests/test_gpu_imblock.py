@@ -59,3 +59,7 @@ def test_smoke_entry():
 
 def test_sigma_cache_follows_power_iteration():
     cases.case_sigma_cache_follows_power_iteration()
+
+
+def test_training_trajectory_matches_oracle(golden):
+    cases.case_training_trajectory_matches_oracle(golden)

@@ -217,3 +217,7 @@ def test_fused_paths_are_taken(golden, monkeypatch):
 
 def test_sigma_cache_follows_power_iteration():
     cases.case_sigma_cache_follows_power_iteration()
+
+
+def test_training_trajectory_matches_oracle(golden):
+    cases.case_training_trajectory_matches_oracle(golden)
