@@ -399,7 +399,9 @@ def main():
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     bucket = pkg.parallel.FlatGradBucket(params)
-    opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.99))
+    # step tail of train_img.py:652-658 in one fused pass: clip_grad_norm_(1.) + the vendored Adam + parameter EMA
+    opt = pkg.optim.FusedAdam(params, lr=1e-3, betas=(0.9, 0.99), bucket=bucket,
+                              max_grad_norm=None if is_mlp else 1., ema_decay=None if is_mlp else 0.999)
     n_dims = c * h * w
     flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)
     blocks = [m for m in model.modules() if isinstance(m, pkg.layers.imBlock)]
@@ -417,8 +419,6 @@ def main():
             bpd = -torch.mean(logpx) / n_dims / np.log(2)
         bpd.backward()
         bucket.allreduce_mean()
-        if not is_mlp:
-            torch.nn.utils.clip_grad_norm_(params, 1.)
         opt.step()
         update_lipschitz(pkg, model, wl.get('n_lipschitz_iters'))
         return bpd
@@ -504,6 +504,30 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
 
+    # ---------------- generation path: forward-only Broyden solves (model.inverse, train_img.py:756-761) ----------
+    inv = None
+    if not is_mlp:
+        model.eval()
+        with torch.no_grad():
+            zs = torch.randn(batch, n_dims, device=dev)
+            for _ in range(2):
+                model(zs, inverse=True)
+            sync_all()
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_inv = max(2, min(args.steps, 5))
+            i0.record()
+            for _ in range(n_inv):
+                model(zs, inverse=True)
+            i1.record()
+            sync_all()
+        ti = torch.tensor([i0.elapsed_time(i1) / n_inv], device=dev)
+        if world > 1:
+            dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+        inv = {'ms_per_batch': float(ti.item()), 'samples_per_sec': batch * world / (float(ti.item()) / 1e3),
+               'broyden_solves_per_sec': len(blocks) * batch * world / (float(ti.item()) / 1e3),
+               'solver_iterations': [b.solver_stats['inv']['nstep'] for b in blocks if 'inv' in b.solver_stats]}
+        model.train()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -542,6 +566,7 @@ def main():
         'gpu_launches': int(launches),
         'broyden_solves_per_sec': solves * world / (ms_total / 1e3),
         'solver_iterations_fwd_last_step': fwd_its[-1] if fwd_its else None,
+        'inverse_sampling': inv,
         'roofline': roof(order[0]) if order else None,
     }
     if len(order) > 1:

@@ -11,6 +11,7 @@ from . import ops  # noqa: F401
 from . import layers  # noqa: F401
 from . import implicit_flow  # noqa: F401
 from . import parallel  # noqa: F401
+from . import optim  # noqa: F401
 from . import compat  # noqa: F401
 from .implicit_flow import ImplicitFlow  # noqa: F401
 

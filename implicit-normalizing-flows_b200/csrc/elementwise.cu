@@ -333,9 +333,42 @@ k_im2col3x3_rows(const float* __restrict__ x, float* __restrict__ col, float* __
   }
 }
 
+// Step tail in one pass over the flat parameter / gradient buffers (train_img.py:652-658): gradient clipping
+// (clip_grad_norm_: g *= min(1, max_norm / (||g|| + 1e-6)), the norm read from the device), the vendored Adam
+// update (lib/optimizers.py:86-103: denom = sqrt(v) + eps, step = lr * sqrt(1-b2^t) / (1-b1^t)) and the
+// exponential moving average of the parameters (lib/utils.py:140-146).
+__global__ void __launch_bounds__(256)
+k_clip_adam_ema(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                float* __restrict__ ema, long long n, const float* __restrict__ gnorm_sq, float max_norm,
+                float step_size, float beta1, float beta2, float eps, float ema_decay) {
+  float coef = 1.f;
+  if (gnorm_sq != nullptr && max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(__ldg(gnorm_sq)) + 1e-6f));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const float pi = p[i] - step_size * mi / (sqrtf(vi) + eps);
+    g[i] = gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi;
+    if (ema != nullptr) ema[i] = ema_decay * ema[i] + (1.f - ema_decay) * pi;
+  }
+}
+
 }  // namespace impflow
 
 using namespace impflow;
+
+extern "C" int impflow_clip_adam_ema(float* p, float* g, float* m, float* v, float* ema, long long n,
+                                     const float* gnorm_sq, float max_norm, float step_size, float beta1,
+                                     float beta2, float eps, float ema_decay, void* stream) {
+  if (n <= 0) return 0;
+  k_clip_adam_ema<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, gnorm_sq, max_norm, step_size,
+                                                                     beta1, beta2, eps, ema_decay);
+  return check_launch("k_clip_adam_ema");
+}
 
 extern "C" int impflow_version(void) { return IMPFLOW_ABI_VERSION; }
 extern "C" const char* impflow_last_error(void) { return impflow::g_err; }

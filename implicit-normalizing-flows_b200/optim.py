@@ -1,0 +1,83 @@
+"""Step tail of the training loop as one fused pass: gradient clipping, the
+Adam update of the reference's vendored optimiser (lib/optimizers.py:47-107) and the parameter EMA
+(lib/utils.py:140-146) over flat buffers, with the clip norm kept on the device (no host sync).
+
+    bucket = parallel.FlatGradBucket(params)            # gradients live in one flat buffer
+    opt = optim.FusedAdam(params, lr=1e-3, betas=(0.9, 0.99), bucket=bucket, max_grad_norm=1.)
+    loss.backward(); bucket.allreduce_mean(); opt.step()
+
+`step()` = clip_grad_norm_(params, max_grad_norm) + Adam.step() (+ ema.apply()) of train_img.py:652-658."""
+import math
+
+import torch
+
+from . import _cabi, ops
+from .parallel import FlatGradBucket
+
+__all__ = ['FusedAdam']
+
+
+class FusedAdam(torch.optim.Optimizer):
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, bucket=None,
+                 max_grad_norm=None, ema_decay=None):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        if amsgrad:
+            raise NotImplementedError('impflow_b200.optim.FusedAdam: amsgrad is not used by any shipped config')
+        # weight_decay is accepted and ignored like in the reference, whose decay line is a no-op
+        # (`p.data.add(...)` without the underscore, lib/optimizers.py:105-106)
+        params = [p for p in params if p.requires_grad]
+        super(FusedAdam, self).__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.bucket = bucket if bucket is not None else FlatGradBucket(params)
+        if [id(p) for p in self.bucket.params] != [id(p) for p in params]:
+            raise ValueError('FusedAdam: the gradient bucket must hold exactly the optimised parameters, in order')
+        self.max_grad_norm = max_grad_norm
+        self.ema_decay = ema_decay
+        n = self.bucket.flat.numel()
+        dev = self.bucket.flat.device
+        # parameters re-pointed at one flat buffer (values preserved)
+        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, off in zip(params, self.bucket.offsets):        # same (aligned) layout as the gradients
+                v = self.flat_p[off:off + p.numel()].view_as(p)
+                v.copy_(p.data)
+                p.data = v
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.ema = self.flat_p.clone() if ema_decay is not None else None
+        self.step_count = 0
+        self.last_grad_norm_sq = None        # device scalar of the latest step (sqrt it to log the norm)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self.bucket.gather_strays()
+        g = self.bucket.flat
+        self.step_count += 1
+        group = self.param_groups[0]
+        beta1, beta2 = group['betas']
+        t = self.step_count
+        step_size = group['lr'] * math.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
+        gsq = None
+        if self.max_grad_norm is not None:
+            gsq = ops._flat_dot(g, g) if g.numel() % 256 == 0 else ops.rowdot(g.view(1, -1), g.view(1, -1))
+            self.last_grad_norm_sq = gsq
+        _cabi.check(_cabi.load().impflow_clip_adam_ema(
+            _cabi.ptr(self.flat_p), _cabi.ptr(g), _cabi.ptr(self.exp_avg), _cabi.ptr(self.exp_avg_sq),
+            _cabi.ptr(self.ema, 'ema', True), g.numel(), _cabi.ptr(gsq, 'gnorm_sq', True),
+            float(self.max_grad_norm or 0.0), float(step_size), float(beta1), float(beta2), float(group['eps']),
+            float(self.ema_decay or 0.0), _cabi.stream()), 'clip_adam_ema')
+        # the kernel wrote through raw pointers: the host caches are keyed on the tensors' versions
+        torch.autograd.graph.increment_version([p for p in self.bucket.params])
+        return loss
+
+    def grad_norm(self):
+        """||g|| before clipping of the latest step, as a device scalar (what clip_grad_norm_ returns)."""
+        return torch.sqrt(self.last_grad_norm_sq) if self.last_grad_norm_sq is not None else None

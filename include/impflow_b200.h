@@ -146,6 +146,15 @@ int impflow_im2col3x3_split(const float* x, float* col_hi, float* col_lo, int B,
 int impflow_col2im3x3(const float* col, int B, int H, int W, int C, const float* bias, float* pre_out,
                       float* act_out, const float* dmul_pre, int act_kind, const float* beta_sp, void* stream);
 
+/* Step tail over FLAT parameter / gradient / moment buffers in one pass — replaces clip_grad_norm_
+ * (train_img.py:652), the vendored Adam update (lib/optimizers.py:47-107: denom = sqrt(v) + eps) and the EMA
+ * of the parameters (lib/utils.py:140-146, train_img.py:658).  gnorm_sq: DEVICE scalar sum(g^2) (e.g. from
+ * impflow_rowdot), NULL or max_norm <= 0 = no clipping; g is overwritten with the clipped gradient; ema may
+ * be NULL; step_size = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the host. */
+int impflow_clip_adam_ema(float* p, float* g, float* m, float* v, float* ema, long long n, const float* gnorm_sq,
+                          float max_norm, float step_size, float beta1, float beta2, float eps, float ema_decay,
+                          void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Residual-branch contractions — replace F.linear / F.conv2d and their vjps
  * (mixed_lipschitz.py:134-136, 388-391; implicit_block.py:422,434,436).

@@ -592,3 +592,28 @@ def bits_per_dim(z, delta_logp, n_dims, nvals=256):
     logpz = (-0.5 * math.log(2 * math.pi) - z.pow(2) / 2).view(z.size(0), -1).sum(1, keepdim=True)
     logpx = logpz - delta_logp - np.log(nvals) * n_dims
     return -torch.mean(logpx) / n_dims / np.log(2)
+
+
+# --------------------------------------------------------------------------------------
+# step tail (lib/optimizers.py:47-107, torch.nn.utils.clip_grad_norm_, lib/utils.py:140-146)
+# --------------------------------------------------------------------------------------
+
+def clip_adam_ema_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas, eps, max_norm=None, ema=None,
+                       ema_decay=None):
+    """One step of train_img.py:652-658 on lists of tensors (updated in place): clip_grad_norm_ over all
+    gradients, the vendored Adam (denom = sqrt(v) + eps; step = lr * sqrt(1-b2^t) / (1-b1^t); its weight-decay
+    line is a no-op) and ExponentialMovingAverage.apply (shadow += (1 - decay) * (param - shadow))."""
+    with torch.no_grad():
+        if max_norm is not None:
+            total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+            coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+            for g in grads:
+                g.mul_(coef)
+        b1, b2 = betas
+        step_size = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+        for i, (p, g, m, v) in enumerate(zip(params, grads, exp_avg, exp_avg_sq)):
+            m.mul_(b1).add_(g, alpha=1 - b1)
+            v.mul_(b2).addcmul_(g, g, value=1 - b2)
+            p.addcdiv_(m, v.sqrt().add_(eps), value=-step_size)
+            if ema is not None:
+                ema[i].add_((1 - ema_decay) * (p - ema[i]))

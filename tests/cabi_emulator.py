@@ -300,6 +300,23 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_clip_adam_ema(self, p, g, m, v, ema, n, gnorm_sq, max_norm, step_size, beta1, beta2, eps, ema_decay,
+                              stream):
+        f = np.float32
+        P, G, M, V = _f32(p, n), _f32(g, n), _f32(m, n), _f32(v, n)
+        coef = f(1)
+        if _addr(gnorm_sq) is not None and max_norm > 0:
+            coef = min(f(1), f(max_norm) / (np.sqrt(_f32(gnorm_sq, 1)[0]) + f(1e-6)))
+        G[:] = G * coef
+        M[:] = f(beta1) * M + f(1 - beta1) * G
+        V[:] = f(beta2) * V + f(1 - beta2) * G * G
+        P[:] = P - f(step_size) * M / (np.sqrt(V) + f(eps))
+        if _addr(ema) is not None:
+            E = _f32(ema, n)
+            E[:] = f(ema_decay) * E + f(1 - ema_decay) * P
+        self.launches += 1
+        return 0
+
     def impflow_lincomb3(self, a, ca, b, cb, c, cc, out, n, stream):
         r = _f32(a, n) * np.float32(ca)
         if _addr(b) is not None:

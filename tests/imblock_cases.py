@@ -347,3 +347,35 @@ def case_training_trajectory_matches_oracle(golden, n_steps=3):
     np.testing.assert_allclose(got[0], want[0], rtol=1e-5)
     np.testing.assert_allclose(got, want, rtol=2e-3)          # later steps inherit the 5e-3 gradient tolerance
     assert sum(got_steps, []) == [int(v) for v in stats['fwd_nstep']]
+
+
+def case_fused_adam_matches_reference_step():
+    """optim.FusedAdam.step() == clip_grad_norm_ + the vendored Adam + EMA (train_img.py:652-658), several steps."""
+    from oracle import impflow_oracle as orc
+    pkg = _pkg()
+    dev = DEV['device']
+    torch.manual_seed(11)
+    shapes = [(32, 3, 3, 3), (32,), (7, 5), (1,), (64, 32, 1, 1)]
+    params = [torch.nn.Parameter(torch.randn(*s, device=dev)) for s in shapes]
+    ref_p = [p.detach().cpu().clone() for p in params]
+    ref_m = [torch.zeros_like(p) for p in ref_p]
+    ref_v = [torch.zeros_like(p) for p in ref_p]
+    ref_e = [p.clone() for p in ref_p]
+    bucket = pkg.parallel.FlatGradBucket(params)
+    opt = pkg.optim.FusedAdam(params, lr=1e-2, betas=(0.9, 0.99), bucket=bucket, max_grad_norm=1.0, ema_decay=0.9)
+    versions = [p._version for p in params]
+    for t in range(1, 5):
+        grads = [torch.randn(*s) * (3.0 if t % 2 else 0.01) for s in shapes]     # clipped and unclipped steps
+        bucket.zero()
+        for p, g in zip(params, grads):
+            p.grad.copy_(g.to(dev))
+        opt.step()
+        orc.clip_adam_ema_step(ref_p, [g.clone() for g in grads], ref_m, ref_v, t, 1e-2, (0.9, 0.99), 1e-8, 1.0, ref_e,
+                               0.9)
+        total = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads)))
+        assert abs(float(opt.grad_norm()) - total) < 1e-4 * total
+        for p, r in zip(params, ref_p):
+            assert rel_err(p.detach().cpu(), r) < 2e-6
+    for r, off in zip(ref_e, bucket.offsets):
+        assert rel_err(opt.ema[off:off + r.numel()].cpu().view_as(r), r) < 2e-6
+    assert all(p._version > v for p, v in zip(params, versions))      # host caches are keyed on versions

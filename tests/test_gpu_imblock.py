@@ -63,3 +63,7 @@ def test_sigma_cache_follows_power_iteration():
 
 def test_training_trajectory_matches_oracle(golden):
     cases.case_training_trajectory_matches_oracle(golden)
+
+
+def test_fused_adam_matches_reference_step():
+    cases.case_fused_adam_matches_reference_step()

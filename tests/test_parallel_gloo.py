@@ -34,7 +34,9 @@ def _worker(rank, world, port, q):
     bucket = par.FlatGradBucket(model.parameters())
     bucket.zero()
     model(xs).pow(2).mean().backward()
-    flat = bucket.allreduce_mean().clone()
+    bucket.allreduce_mean()
+    flat = torch.cat([v.reshape(-1) for v in bucket.views]).clone()    # the bucket pads every tensor to 256 B
+    assert float(bucket.flat.sum()) == float(flat.sum()) or abs(float(bucket.flat.sum()) - float(flat.sum())) < 1e-5
     for p in model.parameters():                      # grads are views into the bucket
         assert p.grad.data_ptr() >= bucket.flat.data_ptr()
     w0 = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
