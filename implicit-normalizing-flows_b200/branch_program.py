@@ -104,6 +104,13 @@ class _T(object):
             self.f = ops.lincomb3(self.s[0], 1.0, self.s[1], 1.0)
         return self.f
 
+    def planes(self):
+        """tf32 hi/lo planes, split at most once per tensor (they feed both the next GEMM as its K-major A
+        operand and the weight-gradient contraction as an MN-major operand)."""
+        if self.s is None:
+            self.s = ops.split_tf32(self.f)
+        return self.s
+
 
 class _Saved(object):
     __slots__ = ('rows', 'meta', 'M', 'pres', 'ains', 'derivs')
@@ -350,7 +357,7 @@ class BranchProgram(object):
                 else:
                     A, A_split = ops.im2col3x3(X.f32().view(B, H, Wd, cin), ld=Wk), None
             else:
-                A_split = X.s if (X.s is not None and Wsp is not None and X.s[0].shape[1] == Wk) else None
+                A_split = X.planes() if (Wsp is not None and cin == Wk) else None
                 A = self._pad_cols(X.f32(), Wk) if A_split is None else None
             if want_split and Wsp is None:          # CUDA-core GEMM: planes come from the split kernel below
                 want_pre, want_act = (True, want_act) if next_is_pre else (want_pre, True)
@@ -358,7 +365,7 @@ class BranchProgram(object):
                                            want_split)
         else:
             B, H, Wd = meta[1]
-            A_split = X.s if (X.s is not None and Wsp is not None and X.s[0].shape[1] == Wk) else None
+            A_split = X.planes() if (Wsp is not None and cin == Wk) else None
             A = self._pad_cols(X.f32(), Wk) if A_split is None else None
             Y, _, _ = self._gemm(A, A_split, Wm, Wk, Wsp, None, None, True, False, None, False)
             if want_split:
@@ -626,15 +633,28 @@ class BranchProgram(object):
 
     # ---------------------------------------------------------------- parameter gradients
     def _wgrad_gemm_layout(self, w, meta, G, Xin):
-        """dL/d(w.fwd) (N, Kpad) from the output adjoint G (M, cout) and the layer input handle."""
+        """dL/d(w.fwd) (N, Kpad) from the output adjoint G (M, cout) (tensor or handle) and the layer input
+        handle.  Wide operands go in as their cached hi/lo planes."""
+        Gh = G if isinstance(G, _T) else _T(f=G)
+        tc = w.fwd_split is not None and ops.WGRAD_MN_MAJOR['on']
         if w.kind == 'c3':
             B, H, Wd = meta[1]
             if w.a_type:
-                Gm, Am = G, ops.im2col3x3(Xin.f32().view(B, H, Wd, w.cin), ld=w.fwd_k)
+                Am = ops.im2col3x3(Xin.f32().view(B, H, Wd, w.cin), ld=w.fwd_k)
+                if tc and w.cout % 4 == 0:
+                    return ops.wgrad_gemm(None, Am, G_split=Gh.planes())
+                Gm = Gh.f32()
             else:
-                Gm, Am = ops.im2col3x3(G.view(B, H, Wd, w.cout), ld=9 * w.cout), self._pad_cols(Xin.f32(), w.fwd_k)
+                # patch rows padded to a multiple of 4 floats (16-byte rows for TMA); the extra output rows are cut
+                Gm = ops.im2col3x3(Gh.f32().view(B, H, Wd, w.cout), ld=_round_up(9 * w.cout, 4))
+                if tc and w.cin == w.fwd_k:
+                    return ops.wgrad_gemm(Gm, None, A_split=Xin.planes())[:9 * w.cout]
+                Am = self._pad_cols(Xin.f32(), w.fwd_k)
+                return ops.wgrad_gemm(Gm, Am)[:9 * w.cout]
         else:
-            Gm, Am = G, self._pad_cols(Xin.f32(), w.fwd_k)
+            if tc and w.cin == w.fwd_k and w.cout % 4 == 0:
+                return ops.wgrad_gemm(None, None, G_split=Gh.planes(), A_split=Xin.planes())
+            Gm, Am = Gh.f32(), self._pad_cols(Xin.f32(), w.fwd_k)
         return ops.wgrad_gemm(Gm, Am)
 
     @staticmethod
@@ -690,7 +710,7 @@ class BranchProgram(object):
             w = ws[i]
             act = acts[i]
             Gf = G.f32()
-            wbars[i] = self._wgrad_gemm_layout(w, meta, Gf, ains[i])
+            wbars[i] = self._wgrad_gemm_layout(w, meta, G, ains[i])
             if w.bias is not None:
                 bbars[i] = ops.colsum(Gf)
             if i == 0 and not need_input_grad and (act is None or act.module is None):
@@ -756,9 +776,9 @@ class BranchProgram(object):
         for i in range(n - 1, -1, -1):
             w = ws[i]
             act = acts[i]
-            wb = self._wgrad_gemm_layout(w, meta, Tbar.f32(), tas[i])
+            wb = self._wgrad_gemm_layout(w, meta, Tbar, tas[i])
             if Ybar is not None:
-                wb = self._add(wb, self._wgrad_gemm_layout(w, meta, Ybar.f32(), ains[i]))
+                wb = self._add(wb, self._wgrad_gemm_layout(w, meta, Ybar, ains[i]))
                 if w.bias is not None:
                     bbars[i] = ops.colsum(Ybar.f32())
             wbars[i] = wb

@@ -264,7 +264,6 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
                   if (n0 + j < N) e.pre_out[row + n0 + j] = v[j];
               }
             }
-#pragma unroll
             if (e.act_kind == IMPFLOW_ACT_LIPSWISH) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = lipswish_fast(v[j], e.beta);

@@ -123,7 +123,8 @@ inline PFN_encodeTiled get_encode() {
   return fn;
 }
 
-inline int make_map(CUtensorMap* map, const float* base, long long rows, int K, long long ld, int box_rows) {
+inline int make_map(CUtensorMap* map, const float* base, long long rows, int K, long long ld, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode();
   if (enc == nullptr) {
     set_error("gemm_tc: cuTensorMapEncodeTiled entry point not available");
@@ -134,7 +135,7 @@ inline int make_map(CUtensorMap* map, const float* base, long long rows, int K, 
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm_tc: cuTensorMapEncodeTiled failed with %d (rows=%lld K=%d ld=%lld)", (int)r, rows, K, ld);

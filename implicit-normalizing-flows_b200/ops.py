@@ -269,11 +269,36 @@ def transpose_split(a2d):
     return hi, lo
 
 
-def wgrad_gemm(G, A):
+WGRAD_MN_MAJOR = {'on': True}      # A/B switch: False = transposed copies + the K-major GEMM
+
+
+def wgrad_gemm(G, A, G_split=None, A_split=None):
     """dW (N1, N2) = G^T A for G (M, N1), A (M, N2): the weight-gradient contraction over all rows (pixels).
-    tcgen05 path: both operands go through one transpose+split pass, then a split-K GEMM."""
-    M, N1 = G.shape
-    N2 = A.shape[1]
+    tcgen05 path: the row-major hi/lo planes of both operands go to the tensor core as MN-major tiles
+    (csrc/wgrad_tcgen05.cu); planes that already exist (they also feed the neighbouring GEMMs) are reused."""
+    M, N1 = G.shape if G is not None else G_split[0].shape
+    N2 = A.shape[1] if A is not None else A_split[0].shape[1]
+    dev = (G if G is not None else G_split[0]).device
+    if _tc_ok(N1, N2, M, M, M) and WGRAD_MN_MAJOR['on'] and N1 % 4 == 0 and N2 % 4 == 0:
+        lib = _lib()
+        Gs = G_split if G_split is not None else split_tf32(G)
+        As = A_split if A_split is not None else split_tf32(A)
+        assert Gs[0].is_contiguous() and As[0].is_contiguous()
+        out = torch.empty(N1, N2, device=dev, dtype=torch.float32)
+        # the wider operand becomes the 128-row (M) side of the MMA tiles
+        swap = N1 < N2 and N1 < 128
+        (Xs, n_x), (Ys, n_y) = ((As, N2), (Gs, N1)) if swap else ((Gs, N1), (As, N2))
+        ws = torch.empty(int(lib.impflow_wgrad_tc_workspace_floats(M, n_x, n_y)), device=dev, dtype=torch.float32)
+        _cabi.check(lib.impflow_wgrad_tc(_cabi.ptr(Xs[0]), _cabi.ptr(Xs[1]), n_x, _cabi.ptr(Ys[0]), _cabi.ptr(Ys[1]),
+                                         n_y, _cabi.ptr(out), N2, 1 if swap else 0, M, n_x, n_y, _cabi.ptr(ws),
+                                         _cabi.stream()), 'wgrad_tc')
+        if GEMM_PROFILE['on']:
+            record_gemm(n_x, n_y, M, True, False, False, False, True)
+        return out
+    if G is None:
+        G = lincomb3(G_split[0], 1.0, G_split[1], 1.0)
+    if A is None:
+        A = lincomb3(A_split[0], 1.0, A_split[1], 1.0)
     if _tc_ok(N1, N2, M, M, M):
         return gemm_nt(None, None, A_split=transpose_split(G), B_split=transpose_split(A))[0]
     return gemm_nt(transpose2d(G), transpose2d(A))[0]

@@ -185,6 +185,16 @@ int impflow_gemm_tc_splits(long long M, int N, int K);
 /* Tile-shape switch for A/B measurements: 1 (default) = 128x256 tiles when N >= 256, 0 = 128x128.
  * Returns the previous setting. */
 int impflow_gemm_tc_set_wide_tiles(int on);
+/* Weight-gradient contraction dW[N1,N2] = G[Mpix,N1]^T A[Mpix,N2] (K = all pixels) straight from the row-major
+ * hi/lo planes: both operands are fed to tcgen05 as MN-major tiles (TMA boxes of 32 pixels x 32 channels), so
+ * no transposed copies are made (replaces the autograd weight gradients of F.conv2d / F.linear,
+ * mixed_lipschitz.py:134-136,388-391).  Needs Mpix % 32 == 0 and 16-byte aligned rows (-2 otherwise);
+ * out[n1*ldo + n2] (or out[n2*ldo + n1] when transpose_out) receives the fixed-order sum of the split-K
+ * partials; ws holds impflow_wgrad_tc_workspace_floats() floats. */
+size_t impflow_wgrad_tc_workspace_floats(long long Mpix, int N1, int N2);
+int impflow_wgrad_tc(const float* G_hi, const float* G_lo, long long ldg, const float* A_hi, const float* A_lo,
+                     long long lda, float* out, long long ldo, int transpose_out, long long Mpix, int N1, int N2,
+                     float* ws, void* stream);
 /* a -> tf32 "hi" (round-to-nearest) and "lo" = a - hi planes used by the 3xTF32 backend. */
 int impflow_split_tf32(const float* a, float* hi, float* lo, long long n, void* stream);
 /* out_hi/out_lo[n,m] = tf32 split of a[m,n] (a is M x N row-major): the K-major operand planes of the

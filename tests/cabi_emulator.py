@@ -458,6 +458,25 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_wgrad_tc_workspace_floats(self, Mpix, N1, N2):
+        return 16
+
+    def impflow_wgrad_tc(self, G_hi, G_lo, ldg, A_hi, A_lo, lda, out, ldo, transpose_out, Mpix, N1, N2, ws, stream):
+        if Mpix % 32 or ldg % 4 or lda % 4:
+            self._err = b'wgrad_tc: layout'
+            return -2
+        gh = _f32(G_hi, Mpix * ldg).reshape(Mpix, ldg)[:, :N1].astype(np.float64)
+        gl = _f32(G_lo, Mpix * ldg).reshape(Mpix, ldg)[:, :N1].astype(np.float64)
+        ah = _f32(A_hi, Mpix * lda).reshape(Mpix, lda)[:, :N2].astype(np.float64)
+        al = _f32(A_lo, Mpix * lda).reshape(Mpix, lda)[:, :N2].astype(np.float64)
+        c = (gl.T @ ah + gh.T @ al + gh.T @ ah).astype(np.float32)
+        if transpose_out:
+            _f32(out, N2 * ldo).reshape(N2, ldo)[:, :N1] = c.T
+        else:
+            _f32(out, N1 * ldo).reshape(N1, ldo)[:, :N2] = c
+        self.launches += 1
+        return 0
+
     # ---- native conv3 runtime (csrc/conv3_plan.cu): the same orchestration over the emulated kernels ----
     @staticmethod
     def _plan(p):

@@ -182,6 +182,28 @@ def test_im2col_col2im(ops):
     assert abs(lhs - rhs) / abs(lhs) < 1e-5
 
 
+@pytest.mark.parametrize('M,N1,N2', [(4096, 512, 512), (65536, 512, 32), (16384, 28, 512), (2048, 128, 128),
+                                     (1024, 512, 448), (8192, 108, 512), (640, 256, 64)])
+def test_wgrad_mn_major(ops, M, N1, N2):
+    """dW = G^T A straight from the row-major planes (MN-major tcgen05 operands, csrc/wgrad_tcgen05.cu) against
+    fp64, the transposed-copy path, and with planes supplied by the caller."""
+    g = torch.Generator().manual_seed(M + N1 + N2)
+    G = torch.randn(M, N1, generator=g).cuda()
+    A = torch.randn(M, N2, generator=g).cuda()
+    ref = G.double().t() @ A.double()
+    out = ops.wgrad_gemm(G, A)
+    assert out.shape == (N1, N2)
+    assert rel_err(out.cpu(), ref.cpu()) < 1e-5      # fp32 accumulation over up to 65536 terms per split
+    out2 = ops.wgrad_gemm(None, None, G_split=ops.split_tf32(G), A_split=ops.split_tf32(A))
+    assert torch.equal(out, out2)
+    ops.WGRAD_MN_MAJOR['on'] = False
+    try:
+        old = ops.wgrad_gemm(G, A)
+    finally:
+        ops.WGRAD_MN_MAJOR['on'] = True
+    assert rel_err(out.cpu(), old.cpu()) < 1e-5
+
+
 @pytest.mark.parametrize('M,N', [(64, 32), (65536, 27), (1000, 77), (4096, 512), (130, 513)])
 def test_transpose_split(ops, M, N):
     a = torch.randn(M, N, generator=torch.Generator().manual_seed(M + N)).cuda()
