@@ -302,33 +302,51 @@ k_transpose_split(const float* __restrict__ a, float* __restrict__ out_hi, float
   }
 }
 
-// im2col, one warp per pixel row: the 9 taps of a pixel are 9 contiguous C-float segments of the image
-// and one contiguous ld-float row of the patch matrix; optional tf32 hi/lo planes instead of fp32.
+// im2col: one thread per 4 consecutive patch columns of one pixel (ld % 4 == 0) or per column (otherwise):
+// the stores of a warp are one contiguous 512-byte run, the gathers hit the (small, cached) image; optional
+// tf32 hi/lo planes instead of fp32.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 k_im2col3x3_rows(const float* __restrict__ x, float* __restrict__ col, float* __restrict__ col_lo, int B, int H,
                  int W, int C, int ld) {
-  const int lane = threadIdx.x & 31;
-  const long long n_pix = (long long)B * H * W;
+  const int groups = ld / VEC;
+  const long long total = (long long)B * H * W * groups;
   const int K = 9 * C;
-  for (long long p = blockIdx.x * 8LL + (threadIdx.x >> 5); p < n_pix; p += (long long)gridDim.x * 8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / groups;
+    const int k0 = (int)(i - p * groups) * VEC;
     const int xx = (int)(p % W);
     const int yy = (int)((p / W) % H);
     const long long img = p - (long long)yy * W - xx;          // pixel index of (b, 0, 0)
-    for (int k = lane; k < ld; k += 32) {
-      float v = 0.f;
+    float v[VEC];
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) {
+      const int k = k0 + u;
+      v[u] = 0.f;
       if (k < K) {
         const int tap = k / C, c = k - tap * C;
         const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = x[(img + (long long)sy * W + sx) * C + c];
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) v[u] = __ldg(x + (img + (long long)sy * W + sx) * C + c);
       }
-      if (col_lo != nullptr) {
-        float h, l;
-        split1(v, h, l);
-        col[p * ld + k] = h;
-        col_lo[p * ld + k] = l;
+    }
+    float* dst = col + p * ld + k0;
+    if (col_lo != nullptr) {
+      float h[VEC], l[VEC];
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) split1(v[u], h[u], l[u]);
+      float* dst_lo = col_lo + p * ld + k0;
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(dst_lo) = make_float4(l[0], l[1], l[2], l[3]);
       } else {
-        col[p * ld + k] = v;
+        dst[0] = h[0];
+        dst_lo[0] = l[0];
       }
+    } else if (VEC == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      dst[0] = v[0];
     }
   }
 }
@@ -487,7 +505,13 @@ static int launch_im2col(const float* x, float* col, float* col_lo, int B, int H
   IMPFLOW_REQUIRE(ld >= 9 * C, "im2col3x3: ld=%d < 9*C=%d", ld, 9 * C);
   const long long n_pix = (long long)B * H * W;
   if (n_pix <= 0) return 0;
-  k_im2col3x3_rows<<<grid_for(n_pix, 8), 256, 0, (cudaStream_t)stream>>>(x, col, col_lo, B, H, W, C, ld);
+  const bool vec = (ld % 4 == 0) && aligned16(col) && (col_lo == nullptr || aligned16(col_lo));
+  if (vec) {
+    k_im2col3x3_rows<4><<<grid_for(n_pix * (ld / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, col, col_lo, B, H, W, C,
+                                                                                           ld);
+  } else {
+    k_im2col3x3_rows<1><<<grid_for(n_pix * ld, 256), 256, 0, (cudaStream_t)stream>>>(x, col, col_lo, B, H, W, C, ld);
+  }
   return check_launch("k_im2col3x3_rows");
 }
 
