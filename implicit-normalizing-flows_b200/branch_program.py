@@ -41,13 +41,18 @@ from . import _cabi, ops
 from .layers.base.activations import ReLU, Sin, Swish
 from .layers.base.mixed_lipschitz import InducedNormConv2d, InducedNormLinear
 
-__all__ = ['BranchProgram', 'compile_branch', 'FUSED3', 'CONV3_NATIVE']
+__all__ = ['BranchProgram', 'compile_branch', 'FUSED3', 'CONV3_NATIVE', 'MEMO']
 
 # One-launch tile kernel for the 3-layer conv branch (csrc/branch_fused.cu); off = three GEMM launches.
 FUSED3 = {'on': True}
 # Native host runtime for the 3-layer conv branch (csrc/conv3_plan.cu): one C call per evaluation / power
 # series / Broyden solve; off = the Python-driven launch sequences below.
 CONV3_NATIVE = {'on': True}
+
+# The same branch is evaluated at the same point several times per step (nnet_x(x) for x_embed, for the
+# re-attach and for the log-det estimate; nnet_z(z) for the estimate and again in the implicit backward).  The
+# last saved forward of a program is kept and handed out again while input storage, version and weights match.
+MEMO = {'on': True}
 
 _conv3_ws = {}      # (device index, stream) -> workspace tensor shared by every plan used on that stream
 
@@ -568,6 +573,20 @@ class BranchProgram(object):
         rows, meta = self._to_rows(x)
         M = rows.shape[0]
         ws = self._prep(M, meta)
+        memo_key = None
+        if save and MEMO['on']:
+            # the memo keeps `x` alive, so an equal (data_ptr, shape, strides) can only be the same storage, and
+            # an unchanged version counter means unchanged contents
+            memo_key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x._version, self._key)
+            m = getattr(self, '_memo', None)
+            if m is not None and m[0] == memo_key:
+                return m[2], m[3]
+        out = self._forward_saved_impl(rows, meta, M, ws, save)
+        if memo_key is not None:
+            self._memo = (memo_key, x, out[0], out[1])
+        return out
+
+    def _forward_saved_impl(self, rows, meta, M, ws, save):
         P = self._conv3(ws, meta)
         if P is not None:
             return self._native_forward(P, rows, meta, save)

@@ -51,10 +51,14 @@ def _program(nnet):
     return prog
 
 
-def branch_eval(nnet, x):
-    """nnet(x) under no_grad, through the fused program when the branch is compilable."""
+def branch_eval(nnet, x, keep=False):
+    """nnet(x) under no_grad, through the fused program when the branch is compilable.  keep=True also keeps
+    the pre-activations: the program hands the same saved forward to the re-attach and to the log-det
+    estimate, which evaluate the branch at the same point (branch_program.MEMO)."""
     prog = _program(nnet)
-    return prog.forward(x) if prog is not None else nnet(x)
+    if prog is None:
+        return nnet(x)
+    return prog.forward_saved(x)[0] if keep else prog.forward(x)
 
 
 class _BranchApply(Function):
@@ -182,7 +186,7 @@ class RootFind(Function):
     @staticmethod
     def broyden_find_root(nnet_z, nnet_x, z0, x, *args):
         eps, threshold = args[-2], args[-1]
-        x_embed = ops.lincomb3(branch_eval(nnet_x, x), 1.0, x, 1.0)
+        x_embed = ops.lincomb3(branch_eval(nnet_x, x, keep=getattr(nnet_x, 'training', False)), 1.0, x, 1.0)
         prog_z = _program(nnet_z)
         spec = prog_z.mlp_solver_spec(z0) if (prog_z is not None and PERSISTENT_MLP['on']) else None
         info = None
@@ -260,6 +264,7 @@ class imBlock(nn.Module):
         """Identity in forward; implicit differentiation in backward (implicit_block.py:165-217):
         solve v^T (I + J_z) = grad with Broyden, then dl_dx = v^T (I + J_x)."""
         last_info = None
+        x_alias = None
 
         @staticmethod
         def forward(ctx, nnet_z, nnet_x, z, x, *args):
@@ -267,6 +272,8 @@ class imBlock(nn.Module):
             ctx.nnet_z = nnet_z
             ctx.nnet_x = nnet_x
             ctx.args = args
+            # a detached tensor with x's values whose saved forward the x-branch program may still hold
+            ctx.x_alias, imBlock.Backward.x_alias = imBlock.Backward.x_alias, None
             return z
 
         @staticmethod
@@ -288,8 +295,9 @@ class imBlock(nn.Module):
                                        torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
                     imBlock.Backward.last_info = info
                     dl_dh = info['result']
-                    prog_x.forward(x, save=True)
-                    dl_dx = ops.lincomb3(prog_x.vjp(dl_dh), 1.0, dl_dh, 1.0)
+                    xa = ctx.x_alias if (ctx.x_alias is not None and ctx.x_alias.shape == x.shape) else x
+                    _, saved_x = prog_x.forward_saved(xa)
+                    dl_dx = ops.lincomb3(prog_x.vjp(dl_dh, saved_x), 1.0, dl_dh, 1.0)
                 return (None, None, dl_dh, dl_dx) + (None,) * len(args)
             z = z.clone().detach().requires_grad_()
             x = x.clone().detach().requires_grad_()
@@ -313,6 +321,7 @@ class imBlock(nn.Module):
 
     def forward(self, x, logpx=None, restore=False):
         z0 = x.clone().detach()
+        self._z0 = z0          # same values as x: lets the x-branch estimate reuse the saved forward at z0
         if restore:
             with torch.no_grad():
                 _ = self.nnet_x_copy(z0)
@@ -326,11 +335,14 @@ class imBlock(nn.Module):
         if FUSED['on']:      # the frozen twins hold the same weights: share the live nets' programs
             self.nnet_z_copy._impflow_program = _program(self.nnet_z)
             self.nnet_x_copy._impflow_program = _program(self.nnet_x)
+        imBlock.Backward.x_alias = z0
         z = self.Backward.apply(self.nnet_z_copy, self.nnet_x_copy, z, x, 'broyden', self.eps_backward,
                                 self.threshold)
         if logpx is None:
             return z
-        return z, logpx - self._logdetgrad(z, x)
+        out = z, logpx - self._logdetgrad(z, x)
+        self._z0 = None
+        return out
 
     def inverse(self, z, logpy=None):
         x0 = z.clone().detach()
@@ -413,7 +425,9 @@ class imBlock(nn.Module):
                     with _overlap(x) as side:
                         with side:
                             pz = est.payload(estimator_fn, self.nnet_z, z, n_power_series, vareps_z, coeff_fn, True)
-                        px = est.payload(estimator_fn, self.nnet_x, x, n_power_series, vareps_x, coeff_fn, True)
+                        z0 = getattr(self, '_z0', None)
+                        x_at = z0 if (z0 is not None and z0.shape == x.shape and z0.device == x.device) else x
+                        px = est.payload(estimator_fn, self.nnet_x, x_at, n_power_series, vareps_x, coeff_fn, True)
                     logdet_x = mem_eff_wrapper(estimator_fn, self.nnet_x, x, n_power_series, vareps_x, coeff_fn,
                                                self.training, px)
                     logdet_z = mem_eff_wrapper(estimator_fn, self.nnet_z, z, n_power_series, vareps_z, coeff_fn,

@@ -67,3 +67,36 @@ def test_training_trajectory_matches_oracle(golden):
 
 def test_fused_adam_matches_reference_step():
     cases.case_fused_adam_matches_reference_step()
+
+
+def test_imblock_without_saved_forward_memo(golden):
+    """Same goldens with the saved-forward memo switched off (every use re-evaluates the branch)."""
+    from impflow_b200 import branch_program
+    branch_program.MEMO['on'] = False
+    try:
+        cases.case_imblock_conv_train(golden, 'cifar', 'auto')
+    finally:
+        branch_program.MEMO['on'] = True
+
+
+def test_saved_forward_memo_is_hit(golden, monkeypatch):
+    """One training forward+backward of a conv imBlock evaluates each branch's saved forward once per distinct
+    point: nnet_x at x (x_embed, re-attach, estimate share it), nnet_z at z* and at z (estimate and implicit
+    backward share it)."""
+    from impflow_b200 import branch_program as bp
+    calls = []
+    orig = bp.BranchProgram._forward_saved_impl
+
+    def counted(self, rows, meta, M, ws, save):
+        calls.append(save)
+        return orig(self, rows, meta, M, ws, save)
+    monkeypatch.setattr(bp.BranchProgram, '_forward_saved_impl', counted)
+    cases.case_imblock_conv_train(golden, 'cifar', 'auto')
+    n_saved = sum(1 for s in calls if s)
+    bp.MEMO['on'] = False
+    try:
+        del calls[:]
+        cases.case_imblock_conv_train(golden, 'cifar', 'auto')
+    finally:
+        bp.MEMO['on'] = True
+    assert n_saved < sum(1 for s in calls if s)
