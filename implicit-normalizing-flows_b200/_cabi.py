@@ -57,10 +57,12 @@ SIGNATURES = {
     'impflow_gemm_tc_splits': (_i, [_ll, _i, _i]),
     'impflow_gemm_tc_set_wide_tiles': (_i, [_i]),
     'impflow_split_tf32': (_i, [_c_fp, _c_fp, _c_fp, _ll, _c_fp]),
+    'impflow_prep_weights': (_i, [_c_fp, _c_fp, _f, _i, _i, _i, _c_fp, _c_fp, _c_fp, _i, _i, _c_fp, _c_fp, _c_fp, _i, _i,
+                                  _c_fp]),
     'impflow_sn_scale': (_i, [_c_fp, _c_fp, _f, _c_fp, _c_fp, _ll, _c_fp]),
     'impflow_sn_scale_grad': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _f, _c_fp, _ll, _c_fp]),
     'impflow_sn_conv_workspace_floats': (ctypes.c_size_t, [_i, _i, _i, _i]),
-    'impflow_sn_power_iter_conv3x3': (_i, [_c_fp] * 5 + [_i, _i, _i, _i, _i, _f, _f, _c_fp, _c_fp]),
+    'impflow_sn_power_iter_conv3x3': (_i, [_c_fp] * 5 + [_i, _i, _i, _i, _i, _f, _f, _c_fp, _c_fp, _c_fp]),
     'impflow_sn_power_iter': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _i, _i, _i, _f, _f, _c_fp]),
 }
 

@@ -39,7 +39,7 @@ import torch.nn.functional as F
 
 from . import _cabi, ops
 from .layers.base.activations import ReLU, Sin, Swish
-from .layers.base.mixed_lipschitz import InducedNormConv2d, InducedNormLinear
+from .layers.base.mixed_lipschitz import InducedNormConv2d, InducedNormLinear, sigma_of
 
 __all__ = ['BranchProgram', 'compile_branch', 'FUSED3', 'CONV3_NATIVE', 'MEMO']
 
@@ -211,43 +211,31 @@ class BranchProgram(object):
                     m._hw = None
                 if isinstance(m, InducedNormConv2d) and not m.is_initialized():
                     m.compute_weight(update=False)                      # lazy u/v init (first use only)
-                # effective weight W / max(1, sigma/coeff) with sigma = <W, D> on the device
-                W, sigma = ops.sn_scale(m.weight.detach(), m.sigma_gradient(), m.coeff, scale_out=m.scale)
-                w.sigma = sigma
+                # effective weight W / max(1, sigma/coeff) in every layout the kernels consume: one launch
+                Wt = m.weight.detach()
+                w.sigma = sigma_of(m)
                 w.bias = m.bias.detach() if m.bias is not None else None
+                cout, cin = Wt.shape[0], Wt.shape[1]
                 if isinstance(m, InducedNormLinear) or m.kernel_size == (1, 1):
-                    cout, cin = W.shape[0], W.shape[1]
-                    W2 = W.reshape(cout, cin)
-                    w.kind, w.cin, w.cout, w.a_type = 'mm', cin, cout, True
-                    fwd, bwd = W2, W2.t()
+                    w.kind, w.cin, w.cout, w.a_type, kind = 'mm', cin, cout, True, 0
+                    fshape, bshape = (cout, cin), (cin, cout)
                 else:
-                    cout, cin = W.shape[0], W.shape[1]
                     w.kind, w.cin, w.cout = 'c3', cin, cout
                     w.a_type = cin <= cout
                     if w.a_type:     # forward: im2col + GEMM(K=9cin); transpose: GEMM(N=9cin) + col2im
-                        fwd = W.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
-                        bwd = W.permute(2, 3, 1, 0).reshape(9 * cin, cout)
+                        kind, fshape, bshape = 1, (cout, 9 * cin), (9 * cin, cout)
                     else:            # forward: GEMM(N=9cout) + col2im; transpose: im2col + GEMM(K=9cout)
-                        fwd = W.flip(2, 3).permute(2, 3, 0, 1).reshape(9 * cout, cin)
-                        bwd = W.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, 9 * cout)
-                w.fwd, w.fwd_k, w.fwd_split = self._finish(fwd, M)
-                w.bwd, w.bwd_k, w.bwd_split = self._finish(bwd, M)
+                        kind, fshape, bshape = 2, (9 * cout, cin), (cin, 9 * cout)
+                tc_f = self._use_tc(M, fshape[0], _round_up(fshape[1], 32))
+                tc_b = self._use_tc(M, bshape[0], _round_up(bshape[1], 32))
+                fshape = (fshape[0], _round_up(fshape[1], 32) if tc_f else fshape[1])
+                bshape = (bshape[0], _round_up(bshape[1], 32) if tc_b else bshape[1])
+                w.fwd, w.fwd_split, w.bwd, w.bwd_split = ops.prep_weights(Wt, w.sigma, m.coeff, kind, fshape, tc_f,
+                                                                          bshape, tc_b)
+                w.fwd_k, w.bwd_k = fshape[1], bshape[1]
                 ws.append(w)
         self._key, self._weights = key, ws
         return ws
-
-    def _finish(self, Wm, M):
-        """Contiguous (N, Kpad) weight matrix, its padded K and (if the tcgen05 path applies) planes."""
-        N, K = Wm.shape
-        if self._use_tc(M, N, _round_up(K, 32)):
-            Kp = _round_up(K, 32)
-            if Kp != K:
-                Wp = Wm.new_zeros(N, Kp)
-                Wp[:, :K] = Wm
-            else:
-                Wp = Wm.contiguous()
-            return Wp, Kp, ops.split_tf32(Wp)
-        return Wm.contiguous(), K, None
 
     def mlp_solver_spec(self, x):
         """Arguments of the persistent small-d solver (csrc/mlp_solver.cu) or None if this branch does not

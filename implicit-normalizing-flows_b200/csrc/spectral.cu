@@ -142,9 +142,69 @@ k_sn_scale_grad(const float* __restrict__ G, const float* __restrict__ D, const 
     out[i] = s * G[i] + c2 * D[i];
 }
 
+// Effective weight of one layer in every layout the branch kernels consume, in ONE launch: the soft spectral
+// rescale W / max(1, sigma/coeff) (mixed_lipschitz.py:128-131), the GEMM re-layouts of both directions
+// (K zero-padded) and their tf32 hi/lo planes.  Replaces ~12 permute / pad / split launches per layer and step.
+//   kind 0 (linear, 1x1):            fwd[co][ci]                   bwd[ci][co]
+//   kind 1 (3x3, cin <= cout):       fwd[co][(ky,kx,ci)]           bwd[(ky,kx,ci)][co]
+//   kind 2 (3x3, cin >  cout):       fwd[(ky',kx',co)][ci]         bwd[ci][(ky',kx',co)]     taps flipped: ky' = 2-ky
+struct PrepOut {
+  float* f32;
+  float* hi;   // may be null (CUDA-core path: no planes)
+  float* lo;
+  int N, Kp;   // rows, padded row length
+};
+__global__ void __launch_bounds__(256)
+k_prep_weights(const float* __restrict__ W, const float* __restrict__ sigma, float coeff, int kind, int cout,
+               int cin, PrepOut fwd, PrepOut bwd) {
+  const float factor = fmaxf(1.f, __ldg(sigma) / coeff);
+  const int nf = fwd.N * fwd.Kp, nb = bwd.N * bwd.Kp;
+  const int taps = kind == 0 ? 1 : 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += gridDim.x * blockDim.x) {
+    const bool is_fwd = i < nf;
+    const PrepOut& o = is_fwd ? fwd : bwd;
+    const int j = is_fwd ? i : i - nf;
+    const int r = j / o.Kp, k = j - r * o.Kp;
+    int co = -1, ci = 0, tap = 0;       // source element W[co][ci][tap]; co = -1: zero padding
+    if (kind == 0) {
+      if (is_fwd) { if (k < cin) co = r, ci = k; } else { if (k < cout) co = k, ci = r; }
+    } else if (kind == 1) {
+      if (is_fwd) { if (k < 9 * cin) co = r, tap = k / cin, ci = k - tap * cin; }
+      else { if (k < cout) co = k, tap = r / cin, ci = r - tap * cin; }
+    } else {
+      if (is_fwd) { if (k < cin) { const int t = r / cout; co = r - t * cout, ci = k, tap = 8 - t; } }
+      else { if (k < 9 * cout) { const int t = k / cout; co = k - t * cout, ci = r, tap = 8 - t; } }
+    }
+    const float v = co >= 0 ? W[((long long)co * cin + ci) * taps + tap] / factor : 0.f;
+    o.f32[j] = v;
+    if (o.hi != nullptr) {
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      o.hi[j] = __uint_as_float(hb);
+      o.lo[j] = v - __uint_as_float(hb);
+    }
+  }
+}
+
 }  // namespace impflow
 
 using namespace impflow;
+
+extern "C" int impflow_prep_weights(const float* W, const float* sigma, float coeff, int kind, int cout, int cin,
+                                    float* fwd, float* fwd_hi, float* fwd_lo, int fwd_rows, int fwd_k, float* bwd,
+                                    float* bwd_hi, float* bwd_lo, int bwd_rows, int bwd_k, void* stream) {
+  IMPFLOW_REQUIRE(kind >= 0 && kind <= 2 && cout >= 1 && cin >= 1, "prep_weights: bad layer (kind=%d)", kind);
+  IMPFLOW_REQUIRE(fwd != nullptr && bwd != nullptr, "prep_weights: outputs missing");
+  IMPFLOW_REQUIRE((fwd_hi == nullptr) == (fwd_lo == nullptr) && (bwd_hi == nullptr) == (bwd_lo == nullptr),
+                  "prep_weights: planes come in pairs");
+  const long long total = (long long)fwd_rows * fwd_k + (long long)bwd_rows * bwd_k;
+  IMPFLOW_REQUIRE(total < (1LL << 31), "prep_weights: layer too large");
+  PrepOut f{fwd, fwd_hi, fwd_lo, fwd_rows, fwd_k}, b{bwd, bwd_hi, bwd_lo, bwd_rows, bwd_k};
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_prep_weights<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(W, sigma, coeff, kind, cout, cin, f, b);
+  return check_launch("k_prep_weights");
+}
 
 extern "C" int impflow_sn_scale(const float* W, const float* sigma, float coeff, float* out, float* scale_out,
                                 long long n, void* stream) {

@@ -36,6 +36,7 @@ struct PcArgs {
   float atol, rtol;
   float* ws;
   int chans;        // wide channels per CTA
+  float* D;         // optional [Cout][Cin][3][3]: d sigma / d W at the final (u, v)
 };
 
 __device__ __forceinline__ float pc_block_sum(float v, float* scratch) {
@@ -307,6 +308,33 @@ k_sn_power_iter_conv3x3(const PcArgs a) {
     grid.sync();
     sigma = pc_grid_sum(ws_dot, G, scratch);
   }
+  if (a.D != nullptr) {
+    // d sigma / d W[co][ci][ky][kx] = sum_{y,x} u[co,y,x] v[ci,y+ky-1,x+kx-1]  (sigma = <u, conv(v)> is linear in W):
+    // one warp per (wide channel of this CTA, narrow channel, tap), lanes over the pixels
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int e = warp; e < nch * Cn * 9; e += kPcWarps) {
+      const int cl = e / (Cn * 9), r = e % (Cn * 9), cn = r / 9, k = r % 9;
+      const int dy = k / 3 - 1, dx = k % 3 - 1;
+      const float* wsl = wa + cl * HW;
+      const float* nsl = nb + cn * HW;
+      float acc = 0.f;
+      for (int p = lane; p < HW; p += 32) {
+        const int y = p / Wd, x = p % Wd;
+        // u is indexed at the output pixel, v at the shifted input pixel
+        const int uy = wide_is_out ? y : y - dy, ux = wide_is_out ? x : x - dx;
+        const int vy = wide_is_out ? y + dy : y, vx = wide_is_out ? x + dx : x;
+        if (uy < 0 || uy >= H || ux < 0 || ux >= Wd || vy < 0 || vy >= H || vx < 0 || vx >= Wd) continue;
+        const float uu = wide_is_out ? wsl[uy * Wd + ux] : nsl[uy * Wd + ux];
+        const float vv = wide_is_out ? nsl[vy * Wd + vx] : wsl[vy * Wd + vx];
+        acc += uu * vv;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const long long co = wide_is_out ? (cw0 + cl) : cn, ci = wide_is_out ? cn : (cw0 + cl);
+        a.D[(co * a.Cin + ci) * 9 + k] = acc;
+      }
+    }
+  }
   if (it > 0) {
     for (int i = tid; i < Ls; i += kPcThreads) wide_g[(long long)cw0 * HW + i] = wa[i];
     if (cta == 0)
@@ -344,7 +372,7 @@ extern "C" size_t impflow_sn_conv_workspace_floats(int Cout, int Cin, int H, int
 
 extern "C" int impflow_sn_power_iter_conv3x3(const float* W, float* u, float* v, float* sigma, int* iters, int Cout,
                                              int Cin, int H, int Wd, int n_iterations, float atol, float rtol,
-                                             float* ws, void* stream) {
+                                             float* ws, float* D, void* stream) {
   IMPFLOW_REQUIRE(Cout >= 1 && Cin >= 1 && H >= 1 && Wd >= 1, "sn_power_iter_conv3x3: empty problem");
   int chans, grid;
   size_t smem;
@@ -363,7 +391,7 @@ extern "C" int impflow_sn_power_iter_conv3x3(const float* W, float* u, float* v,
     }
     smem_set = smem;
   }
-  PcArgs a{W, u, v, sigma, iters, Cout, Cin, H, Wd, n_iterations, atol, rtol, ws, chans};
+  PcArgs a{W, u, v, sigma, iters, Cout, Cin, H, Wd, n_iterations, atol, rtol, ws, chans, D};
   void* args[] = {&a};
   cudaError_t e = cudaLaunchCooperativeKernel((void*)k_sn_power_iter_conv3x3, dim3(grid), dim3(kPcThreads), args, smem,
                                               (cudaStream_t)stream);

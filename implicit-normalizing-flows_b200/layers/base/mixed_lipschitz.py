@@ -14,7 +14,7 @@ import torch.nn.init as init
 
 from ... import _cabi, ops
 
-__all__ = ['InducedNormLinear', 'InducedNormConv2d', 'update_lipschitz']
+__all__ = ['InducedNormLinear', 'InducedNormConv2d', 'update_lipschitz', 'sigma_of']
 
 
 def _check_norms(domain, codomain):
@@ -27,6 +27,11 @@ def _check_norms(domain, codomain):
 
 def _require_cuda(t, what):
     _cabi.require_device(t, what)
+
+
+def _state_key(m):
+    """Identifies the (weight, u, v) contents a cached sigma / d sigma/dW belongs to."""
+    return (m.weight._version, m.u._version, m.v._version, m.weight.data_ptr(), m.u.data_ptr(), m.v.data_ptr())
 
 
 class _Sigma(torch.autograd.Function):
@@ -132,7 +137,9 @@ class InducedNormLinear(nn.Module):
             with torch.no_grad():
                 sig, _ = ops.sn_power_iter(self.weight.detach(), self.u, self.v, n_iterations, atol, rtol)
             if not torch.is_grad_enabled():
-                return ops.sn_rescale(self.weight.detach(), sig, self.coeff, scale_out=self.scale)
+                out = ops.sn_rescale(self.weight.detach(), sig, self.coeff, scale_out=self.scale)
+                self._scale_for = _state_key(self)
+                return out
         sigma = _Sigma.apply(self.weight, self.u, self.v)
         with torch.no_grad():
             self.scale.copy_(sigma[0])
@@ -312,8 +319,10 @@ class InducedNormConv2d(nn.Module):
             with torch.no_grad():
                 sig, _ = ops.sn_power_iter(W2.detach(), self.u, self.v, n_iterations, atol, rtol)
             if not torch.is_grad_enabled():
-                return ops.sn_rescale(W2.detach(), sig, self.coeff, scale_out=self.scale).view(
+                out = ops.sn_rescale(W2.detach(), sig, self.coeff, scale_out=self.scale).view(
                     self.out_channels, self.in_channels, 1, 1)
+                self._scale_for = _state_key(self)
+                return out
         sigma = _Sigma.apply(W2, self.u, self.v)
         with torch.no_grad():
             self.scale.copy_(sigma[0])
@@ -329,11 +338,15 @@ class InducedNormConv2d(nn.Module):
             if tol_mode or n_iterations is not None:
                 with torch.no_grad():
                     res = ops.sn_power_iter_conv(self.weight.detach(), self.u, self.v, h, w,
-                                                 None if tol_mode else n_iterations, atol, rtol)
+                                                 None if tol_mode else n_iterations, atol, rtol, want_D=True)
             if res is not None:
                 update = False
+                # the kernel also leaves d sigma / d W for the new (u, v): what sigma_gradient() would recompute
+                self._sigma_grad = ((self.u._version, self.v._version, self.u.data_ptr(), self.v.data_ptr()), res[2])
                 if not torch.is_grad_enabled():      # update_lipschitz: nothing differentiates this result
-                    return ops.sn_rescale(self.weight.detach(), res[0], self.coeff, scale_out=self.scale)
+                    out = ops.sn_rescale(self.weight.detach(), res[0], self.coeff, scale_out=self.scale)
+                    self._scale_for = _state_key(self)      # `scale` now holds sigma of exactly this state
+                    return out
         if update:
             max_itrs = 200 if n_iterations is None else n_iterations
             with torch.no_grad():
@@ -419,3 +432,15 @@ def update_lipschitz(model, n_iterations=None, n_streams=8):
             done = torch.cuda.Event()
             done.record(s)
             main.wait_event(done)
+
+
+def sigma_of(m):
+    """Device scalar sigma = <W, d sigma/dW> of the layer's CURRENT weight (what compute_weight(update=False)
+    uses).  When the weight, u and v are untouched since the last power iteration the value the kernel left in
+    `m.scale` is that number and nothing is launched."""
+    if getattr(m, '_scale_for', None) == _state_key(m):
+        return m.scale
+    with torch.no_grad():
+        sigma = ops._flat_dot(m.weight.detach().contiguous(), m.sigma_gradient())
+        m.scale.copy_(sigma[0])
+    return sigma

@@ -447,10 +447,10 @@ def sn_power_iter(W2d, u, v, n_iterations, atol, rtol):
     return sigma, iters
 
 
-def sn_power_iter_conv(W, u, v, h, w, n_iterations, atol, rtol):
+def sn_power_iter_conv(W, u, v, h, w, n_iterations, atol, rtol, want_D=False):
     """In-place power iteration of the 3x3 conv W (Cout,Cin,3,3) on one h x w image: one cooperative launch.
-    Returns (sigma (1,), iters (1,) int32) device tensors, or None when the shape is not supported by the
-    kernel (narrow side too large for shared memory) and the caller has to iterate itself."""
+    Returns (sigma (1,), iters (1,) int32[, D = d sigma / d W]) device tensors, or None when the shape is not
+    supported by the kernel (narrow side too large for shared memory) and the caller has to iterate itself."""
     W = W.contiguous()
     co, ci = W.shape[0], W.shape[1]
     n_ws = int(_lib().impflow_sn_conv_workspace_floats(co, ci, h, w))
@@ -460,13 +460,14 @@ def sn_power_iter_conv(W, u, v, h, w, n_iterations, atol, rtol):
     sigma = torch.empty(1, device=W.device, dtype=torch.float32)
     iters = torch.zeros(1, device=W.device, dtype=torch.int32)
     n_it = -1 if n_iterations is None else int(n_iterations)
+    D = torch.empty_like(W) if want_D else None
     _cabi.check(_lib().impflow_sn_power_iter_conv3x3(
         _cabi.ptr(W), _cabi.ptr(u), _cabi.ptr(v), _cabi.ptr(sigma), _cabi.iptr(iters), co, ci, h, w, n_it,
         float(atol if atol is not None else 0.0), float(rtol if rtol is not None else 0.0), _cabi.ptr(ws),
-        _cabi.stream()), 'sn_power_iter_conv3x3')
+        _cabi.ptr(D, 'D', True), _cabi.stream()), 'sn_power_iter_conv3x3')
     if n_it != 0:
         _mark_written(u, v)
-    return sigma, iters
+    return (sigma, iters, D) if want_D else (sigma, iters)
 
 
 def sn_rescale(W, sigma, coeff, scale_out=None):
@@ -476,6 +477,23 @@ def sn_rescale(W, sigma, coeff, scale_out=None):
     _cabi.check(_lib().impflow_sn_scale(_cabi.ptr(W), _cabi.ptr(sigma), float(coeff), _cabi.ptr(out),
                                         _cabi.ptr(scale_out, 'scale', True), W.numel(), _cabi.stream()), 'sn_scale')
     return out
+
+
+def prep_weights(W, sigma, coeff, kind, fwd_shape, fwd_planes, bwd_shape, bwd_planes):
+    """Rescaled weight in the forward / transposed GEMM layouts (+ hi/lo planes) in one launch; see
+    impflow_prep_weights.  *_shape = (rows, padded K)."""
+    W = W.contiguous()
+    dev = W.device
+    mk = lambda shp: torch.empty(shp[0], shp[1], device=dev, dtype=torch.float32)
+    f, b = mk(fwd_shape), mk(bwd_shape)
+    fs = (mk(fwd_shape), mk(fwd_shape)) if fwd_planes else None
+    bs = (mk(bwd_shape), mk(bwd_shape)) if bwd_planes else None
+    _cabi.check(_lib().impflow_prep_weights(
+        _cabi.ptr(W), _cabi.ptr(sigma), float(coeff), kind, W.shape[0], W.shape[1], _cabi.ptr(f),
+        _cabi.ptr(fs[0] if fs else None, 'fh', True), _cabi.ptr(fs[1] if fs else None, 'fl', True), fwd_shape[0],
+        fwd_shape[1], _cabi.ptr(b), _cabi.ptr(bs[0] if bs else None, 'bh', True),
+        _cabi.ptr(bs[1] if bs else None, 'bl', True), bwd_shape[0], bwd_shape[1], _cabi.stream()), 'prep_weights')
+    return f, fs, b, bs
 
 
 def _flat_dot(a, b):

@@ -285,15 +285,27 @@ int impflow_sn_power_iter(const float* W, float* u, float* v, float* sigma, int*
  * normalisations and a host-synchronising tolerance test per iteration) with ONE cooperative launch.
  * W is [Cout][Cin][3][3]; u (Cout*H*W) and v (Cin*H*W) are flat CHW vectors updated in place;
  * sigma[0] = <u, conv(v)>; iters[0] = iterations used; n_iterations < 0 = tolerance mode (cap 200).
+ * D (optional, W's shape) receives d sigma / d W at the final (u, v) — the correlation of u with the patches
+ * of v that the gradient of the rescaled weight needs.
  * `ws` holds impflow_sn_conv_workspace_floats() floats; that function returns 0 (and the solver -2) when the
  * narrow side of the layer does not fit in shared memory (the caller then keeps its own loop). */
 size_t impflow_sn_conv_workspace_floats(int Cout, int Cin, int H, int W);
 int impflow_sn_power_iter_conv3x3(const float* W, float* u, float* v, float* sigma, int* iters, int Cout, int Cin,
-                                  int H, int Wd, int n_iterations, float atol, float rtol, float* ws, void* stream);
+                                  int H, int Wd, int n_iterations, float atol, float rtol, float* ws, float* D,
+                                  void* stream);
 
 /* Soft spectral rescale with sigma on the device: out = W / max(1, sigma[0]/coeff), scale_out[0] =
  * sigma[0] (mixed_lipschitz.py:125-131), and its gradient chain with D = d sigma / d W (sigma = <W,D>
  * is linear in W; u, v constant):  out = s*G + gw_dot[0] * ds/dsigma * D,  gw_dot = <G, W>. */
+/* One launch per layer and optimiser step: the rescaled weight W / max(1, sigma[0]/coeff) written in every
+ * layout the branch kernels consume — forward and transposed GEMM forms (K zero-padded to fwd_k / bwd_k) as
+ * fp32 and, when the plane pointers are given, tf32 hi/lo planes.  kind 0: linear / 1x1 (fwd (cout, fwd_k),
+ * bwd (cin, bwd_k)); kind 1: 3x3 with cin <= cout (fwd (cout, 9cin->fwd_k), bwd (9cin, bwd_k));
+ * kind 2: 3x3 with cin > cout (fwd (9cout, fwd_k), bwd (cin, 9cout->bwd_k), taps flipped).  Replaces the
+ * permute / flip / pad / split sequence of the host (branch_program._prep). */
+int impflow_prep_weights(const float* W, const float* sigma, float coeff, int kind, int cout, int cin, float* fwd,
+                         float* fwd_hi, float* fwd_lo, int fwd_rows, int fwd_k, float* bwd, float* bwd_hi,
+                         float* bwd_lo, int bwd_rows, int bwd_k, void* stream);
 int impflow_sn_scale(const float* W, const float* sigma, float coeff, float* out, float* scale_out, long long n,
                      void* stream);
 int impflow_sn_scale_grad(const float* G, const float* D, const float* sigma, const float* gw_dot, float coeff,

@@ -588,6 +588,31 @@ class EmulatedLib(object):
         return 0
 
     # ---- spectral (csrc/spectral.cu) ----
+    def impflow_prep_weights(self, W, sigma, coeff, kind, cout, cin, fwd, fwd_hi, fwd_lo, fwd_rows, fwd_k, bwd, bwd_hi,
+                             bwd_lo, bwd_rows, bwd_k, stream):
+        taps = 1 if kind == 0 else 9
+        Wt = torch.from_numpy(_f32(W, cout * cin * taps).copy()).view(cout, cin, *((1, 1) if kind == 0 else (3, 3)))
+        Wt = Wt / max(np.float32(1), _f32(sigma, 1)[0] / np.float32(coeff))
+        if kind == 0:
+            f, b = Wt.reshape(cout, cin), Wt.reshape(cout, cin).t()
+        elif kind == 1:
+            f = Wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+            b = Wt.permute(2, 3, 1, 0).reshape(9 * cin, cout)
+        else:
+            f = Wt.flip(2, 3).permute(2, 3, 0, 1).reshape(9 * cout, cin)
+            b = Wt.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, 9 * cout)
+        for m, out, hi, lo, rows, kp in ((f, fwd, fwd_hi, fwd_lo, fwd_rows, fwd_k), (b, bwd, bwd_hi, bwd_lo, bwd_rows, bwd_k)):
+            assert m.shape[0] == rows and m.shape[1] <= kp
+            full = np.zeros((rows, kp), dtype=np.float32)
+            full[:, :m.shape[1]] = m.numpy()
+            _f32(out, rows * kp)[:] = full.reshape(-1)
+            if _addr(hi) is not None:
+                h = _tf32(full.reshape(-1))
+                _f32(hi, rows * kp)[:] = h
+                _f32(lo, rows * kp)[:] = full.reshape(-1) - h
+        self.launches += 1
+        return 0
+
     def impflow_sn_scale(self, W, sigma, coeff, out, scale_out, n, stream):
         sg = _f32(sigma, 1)[0]
         _f32(out, n)[:] = _f32(W, n) / max(np.float32(1), sg / np.float32(coeff))
@@ -635,7 +660,7 @@ class EmulatedLib(object):
         narrow = min(Cout, Cin) * H * W
         return 0 if 2 * narrow * 4 > 160 * 1024 else 128 * narrow + narrow + 5 * 128
 
-    def impflow_sn_power_iter_conv3x3(self, W, u, v, sigma, iters, Cout, Cin, H, Wd, n_iterations, atol, rtol, ws,
+    def impflow_sn_power_iter_conv3x3(self, W, u, v, sigma, iters, Cout, Cin, H, Wd, n_iterations, atol, rtol, ws, D,
                                       stream):
         import torch.nn.functional as F
         Wt = torch.from_numpy(_f32(W, Cout * Cin * 9).reshape(Cout, Cin, 3, 3).copy())
@@ -657,6 +682,11 @@ class EmulatedLib(object):
                 if err_u < atol + rtol * float(un.max()) and err_v < atol + rtol * float(vn.max()):
                     break
         _f32(sigma, 1)[0] = np.float32(float(torch.dot(un, conv(vn))))
+        if _addr(D) is not None:      # d <u, conv(v; W)> / dW
+            with torch.enable_grad():
+                Wg = Wt.clone().requires_grad_(True)
+                s_ = torch.dot(un, F.conv2d(vn.view(1, Cin, H, Wd), Wg, padding=1).reshape(-1))
+                _f32(D, Cout * Cin * 9)[:] = torch.autograd.grad(s_, Wg)[0].reshape(-1).numpy()
         if _addr(iters) is not None:
             np.ctypeslib.as_array((ctypes.c_int32 * 1).from_address(_addr(iters)))[0] = used
         if used > 0:

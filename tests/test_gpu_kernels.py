@@ -274,6 +274,37 @@ def test_sn_power_iter_vs_golden(ops, golden):
     assert int(iters.item()) == used
 
 
+@pytest.mark.parametrize('kind,cout,cin', [(0, 512, 512), (0, 6, 128), (1, 512, 3), (1, 32, 4), (2, 3, 512), (2, 12, 512),
+                                           (2, 4, 32)])
+def test_prep_weights_layouts(ops, kind, cout, cin):
+    """One-launch weight preparation (rescale + GEMM layouts of both directions + hi/lo planes) against the
+    permute / flip / pad expressions it replaces."""
+    g = torch.Generator().manual_seed(kind * 100 + cout + cin)
+    shape = (cout, cin) + ((1, 1) if kind == 0 else (3, 3))
+    W = torch.randn(*shape, generator=g).cuda()
+    sigma = torch.tensor([1.7], device='cuda')
+    coeff = 0.9
+    Ws = W / max(1.0, 1.7 / coeff)
+    if kind == 0:
+        f, b = Ws.reshape(cout, cin), Ws.reshape(cout, cin).t()
+    elif kind == 1:
+        f, b = Ws.permute(0, 2, 3, 1).reshape(cout, 9 * cin), Ws.permute(2, 3, 1, 0).reshape(9 * cin, cout)
+    else:
+        f = Ws.flip(2, 3).permute(2, 3, 0, 1).reshape(9 * cout, cin)
+        b = Ws.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, 9 * cout)
+    pad = lambda k: (k + 31) // 32 * 32
+    for planes in (True, False):
+        fs = (f.shape[0], pad(f.shape[1]) if planes else f.shape[1])
+        bs = (b.shape[0], pad(b.shape[1]) if planes else b.shape[1])
+        of, ofs, ob, obs = ops.prep_weights(W, sigma, coeff, kind, fs, planes, bs, planes)
+        for ref, out, sp in ((f, of, ofs), (b, ob, obs)):
+            assert torch.allclose(out[:, :ref.shape[1]], ref, rtol=1e-6, atol=0)
+            assert float(out[:, ref.shape[1]:].abs().sum()) == 0.0
+            assert (sp is not None) == planes
+            if planes:
+                assert torch.equal(sp[0] + sp[1], out) and torch.equal(sp[0], ops.split_tf32(out)[0])
+
+
 @pytest.mark.parametrize('co,ci,h,w,n_it', [(512, 3, 32, 32, None), (3, 512, 32, 32, None), (512, 12, 16, 16, 3),
                                             (48, 512, 8, 8, None), (32, 4, 8, 8, 5), (5, 40, 6, 7, None),
                                             (16, 16, 8, 8, None), (512, 3, 32, 32, 0)])
@@ -291,9 +322,13 @@ def test_sn_power_iter_conv_vs_oracle(ops, co, ci, h, w, n_it):
         u_ref, v_ref, used = orc.power_iterate_conv(W, u0.clone(), v0.clone(), (ci, h, w), 1, 1, n_it, tol, tol)
     s_ref = orc.sigma_conv(W, u_ref, v_ref, (ci, h, w), 1, 1)
     u, v = u0.clone().cuda(), v0.clone().cuda()
-    res = ops.sn_power_iter_conv(W.cuda(), u, v, h, w, n_it, tol, tol)
+    res = ops.sn_power_iter_conv(W.cuda(), u, v, h, w, n_it, tol, tol, want_D=True)
     assert res is not None
-    sigma, iters = res
+    sigma, iters, D = res
+    Wg = W.clone().requires_grad_(True)       # d <u, conv(v; W)> / dW at the final (u, v)
+    (D_ref,) = torch.autograd.grad(torch.dot(u.cpu(), F.conv2d(v.cpu().view(1, ci, h, w), Wg, padding=1).reshape(-1)),
+                                   Wg)
+    assert rel_err(D.cpu(), D_ref) < 1e-5
     assert int(iters.item()) == used
     assert rel_err(u.cpu(), u_ref) < 1e-5
     assert rel_err(v.cpu(), v_ref) < 1e-5
