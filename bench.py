@@ -316,7 +316,7 @@ def _host_init_lazy_buffers(sd, wl, x):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cifar', choices=list(WORKLOADS))
@@ -431,6 +431,13 @@ def main():
     for _ in range(args.warmup):
         step(x_dev)
     sync_all()
+    if os.environ.get('IMPFLOW_BENCH_GC', '') == 'freeze':      # diagnostic: cost of Python's cyclic GC in the loop
+        import gc
+        gc.collect()
+        gc.freeze()
+    elif os.environ.get('IMPFLOW_BENCH_GC', '') == 'off':
+        import gc
+        gc.disable()
 
     # ---------------- timed region: K steps, inputs resident in HBM ----------------
     sampler = ClockSampler(local_rank)

@@ -21,6 +21,7 @@ dev = torch.device('cuda:0')
 torch.manual_seed(0)
 np.random.seed(0)
 ib.PROBE_MODE['mode'] = 'device'
+ib.OVERLAP['on'] = os.environ.get('OVERLAP', '0') == '1'      # one stream: the per-phase timers sync the device
 model = bench.build_model(pkg, wl, batch).to(dev)
 c, h, w = wl['input']
 x = torch.rand(batch, c, h, w, device=dev)

@@ -379,3 +379,70 @@ def case_fused_adam_matches_reference_step():
     for r, off in zip(ref_e, bucket.offsets):
         assert rel_err(opt.ema[off:off + r.numel()].cpu().view_as(r), r) < 2e-6
     assert all(p._version > v for p, v in zip(params, versions))      # host caches are keyed on versions
+
+
+def case_wide_conv_block_vs_oracle(width=256, c=3, hw=8, batch=2, verbose=False):
+    """A CIFAR-recipe conv imBlock at a width the one-launch tile kernel and the native runtime take
+    (9c <= 32, width % 256 == 0): one training step (Broyden solve, re-attach, Neumann estimator with the
+    memory-efficient backward, implicit backward) against the CPU oracle on the same weights, roulette draw and
+    probes.  Returns the error summary (used by __graft_entry__.smoke)."""
+    from oracle import impflow_oracle as orc
+    from tests.helpers import oracle_branch
+    pkg = _pkg()
+    layers = pkg.layers
+    dev = DEV['device']
+    torch.manual_seed(5)
+    np.random.seed(5)
+    kw = dict(n_dist='poisson', n_samples=1, n_exact_terms=3, neumann_grad=True, grad_in_forward=True)
+    blk = layers.imBlock(build_conv_branch(layers, c, width, 0.9, 1e-3, True),
+                         build_conv_branch(layers, c, width, 0.9, 1e-3, True), **kw).to(dev)
+    x0 = torch.randn(batch, c, hw, hw)
+    with torch.no_grad():
+        blk(x0.to(dev), restore=True)                 # lazy u / v shaping
+        for n, p in blk.named_parameters():           # make the branches (and the spectral rescale) do real work
+            if n.endswith('weight') and p.requires_grad:
+                p.mul_(3.0)
+        layers.base.update_lipschitz(blk)
+    sd = {k: v.detach().cpu().clone() for k, v in blk.state_dict().items()}
+    blk.train()
+    n_draws = np.array([2])
+    vx = (torch.randint(0, 2, x0.shape) * 2 - 1).float()
+    vz = (torch.randint(0, 2, x0.shape) * 2 - 1).float()
+    blk._inject_n, blk._inject_probes = n_draws, (vx, vz)
+    pkg.ops.GEMM_PROFILE['on'], pkg.ops.GEMM_PROFILE['shapes'] = True, {}
+    try:
+        xg = x0.clone().to(dev).requires_grad_(True)
+        z, dlogp = blk(xg, torch.zeros(batch, 1, device=dev))
+        loss = -(std_normal_logprob(z).reshape(batch, -1).sum(1, keepdim=True) - dlogp).mean()
+        loss.backward()
+        fused = sum(v for k, v in pkg.ops.GEMM_PROFILE['shapes'].items() if k[0] == 'branch3')
+    finally:
+        pkg.ops.GEMM_PROFILE['on'], pkg.ops.GEMM_PROFILE['shapes'] = False, {}
+    sub = lambda pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    bx = oracle_branch(sub('nnet_x.'), 'swish', 0.9, 1e-3)
+    bz = oracle_branch(sub('nnet_z.'), 'swish', 0.9, 1e-3)
+    cfg = dict(orc.DEFAULT_CFG, n_dist='poisson', n_exact_terms=3, neumann_grad=True, grad_in_forward=True)
+    xo = x0.detach().clone().requires_grad_(True)
+    stats = {}
+    zo, dlo = orc.imblock_forward(bx, bz, xo, torch.zeros(batch, 1), cfg, True, n_draws=n_draws, probes=(vx, vz),
+                                  stats=stats)
+    lo = -(std_normal_logprob(zo).reshape(batch, -1).sum(1, keepdim=True) - dlo).mean()
+    lo.backward()
+    res = {'z': rel_err(z.detach().cpu(), zo.detach()), 'logdet': rel_err(dlogp.detach().cpu(), dlo.detach()),
+           'loss': abs(float(loss) - float(lo)) / abs(float(lo)), 'grad_x': rel_err(xg.grad.cpu(), xo.grad),
+           'fwd_nstep': (blk.solver_stats['fwd']['nstep'], stats['fwd_nstep'][0]), 'fused_launches': fused}
+    worst = 0.0
+    names = [n for n, _ in blk.named_parameters() if n.startswith('nnet_x.') or n.startswith('nnet_z.')]
+    oparams = dict(zip([n for n in names if n.startswith('nnet_x.')], bx.parameters()))
+    oparams.update(zip([n for n in names if n.startswith('nnet_z.')], bz.parameters()))
+    for n, p in blk.named_parameters():
+        if n in oparams and p.grad is not None and oparams[n].grad is not None and float(oparams[n].grad.norm()) > 1e-6:
+            worst = max(worst, rel_err(p.grad.cpu(), oparams[n].grad))
+    res['grad_params'] = worst
+    if verbose:
+        print('wide conv imBlock vs oracle:', res)
+    assert res['fwd_nstep'][0] == res['fwd_nstep'][1]
+    assert res['z'] < 1e-5 and res['logdet'] < 1e-4 and res['loss'] < 1e-5
+    assert res['grad_x'] < 2e-3 and res['grad_params'] < 5e-3
+    assert fused > 0, 'the fused tile kernel was not used'
+    return res

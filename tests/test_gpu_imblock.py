@@ -100,3 +100,7 @@ def test_saved_forward_memo_is_hit(golden, monkeypatch):
     finally:
         bp.MEMO['on'] = True
     assert n_saved < sum(1 for s in calls if s)
+
+
+def test_wide_conv_block_vs_oracle():
+    cases.case_wide_conv_block_vs_oracle(verbose=True)
