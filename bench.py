@@ -356,14 +356,23 @@ def main():
         print(json.dumps(line))
         return
 
-    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-        os.environ['NCCL_DEBUG'] = 'WARN'        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     import torch.distributed as dist
     assert torch.cuda.is_available(), 'bench.py --impl b200 needs a GPU (there is no CPU fallback)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on stdout while the communicator is created; rank 0's stdout is ONE JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     import __graft_entry__
     if rank == 0:
         __graft_entry__.build()

@@ -318,8 +318,13 @@ k_sn_power_iter_conv3x3(const PcArgs a) {
       const float* wsl = wa + cl * HW;
       const float* nsl = nb + cn * HW;
       float acc = 0.f;
-      for (int p = lane; p < HW; p += 32) {
-        const int y = p / Wd, x = p % Wd;
+      int y = lane / Wd, x = lane % Wd;          // pixel of this lane, advanced by 32 per step without divisions
+      const int step_y = 32 / Wd, step_x = 32 % Wd;
+      for (int p = lane; p < HW; p += 32, y += step_y, x += step_x) {
+        if (x >= Wd) {
+          x -= Wd;
+          ++y;
+        }
         // u is indexed at the output pixel, v at the shifted input pixel
         const int uy = wide_is_out ? y : y - dy, ux = wide_is_out ? x : x - dx;
         const int vy = wide_is_out ? y + dy : y, vx = wide_is_out ? x + dx : x;
