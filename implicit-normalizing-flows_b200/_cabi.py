@@ -32,6 +32,8 @@ SIGNATURES = {
     'impflow_reduce_workspace_floats': (ctypes.c_size_t, [_ll]),
     'impflow_act_beta_grad': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _i, _c_fp, _c_fp]),
     'impflow_act_second': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _i, _c_fp, _c_fp]),
+    'impflow_neumann_act_bwd_workspace_floats': (ctypes.c_size_t, [_ll, _i]),
+    'impflow_neumann_act_bwd': (_i, [_c_fp] * 9 + [_ll, _i, _c_fp, _c_fp]),
     'impflow_lincomb3': (_i, [_c_fp, _f, _c_fp, _f, _c_fp, _f, _c_fp, _ll, _c_fp]),
     'impflow_clip_adam_ema': (_i, [_c_fp] * 5 + [_ll, _c_fp, _f, _f, _f, _f, _f, _f, _c_fp]),
     'impflow_rowdot': (_i, [_c_fp, _c_fp, _c_fp, _i, _ll, _f, _f, _c_fp]),

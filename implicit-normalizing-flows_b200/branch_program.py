@@ -49,6 +49,10 @@ FUSED3 = {'on': True}
 # series / Broyden solve; off = the Python-driven launch sequences below.
 CONV3_NATIVE = {'on': True}
 
+# One-pass activation step of the Neumann reverse sweep (csrc/elementwise.cu: k_neumann_act_bwd); off = act_second +
+# two act_beta_grad + colsum + split.
+NEUMANN_FUSED = {'on': True}
+
 # The same branch is evaluated at the same point several times per step (nnet_x(x) for x_embed, for the
 # re-attach and for the log-det estimate; nnet_z(z) for the estimate and again in the implicit backward).  The
 # last saved forward of a program is kept and handed out again while input storage, version and weights match.
@@ -99,10 +103,10 @@ class _Weights(object):
 
 class _T(object):
     """A rows-space activation: fp32 tensor and/or its tf32 hi/lo planes."""
-    __slots__ = ('f', 's')
+    __slots__ = ('f', 's', 'colsum')
 
     def __init__(self, f=None, s=None):
-        self.f, self.s = f, s
+        self.f, self.s, self.colsum = f, s, None
 
     def f32(self):
         if self.f is None:
@@ -787,7 +791,7 @@ class BranchProgram(object):
             if Ybar is not None:
                 wb = self._add(wb, self._wgrad_gemm_layout(w, meta, Ybar, ains[i]))
                 if w.bias is not None:
-                    bbars[i] = ops.colsum(Ybar.f32())
+                    bbars[i] = Ybar.colsum if Ybar.colsum is not None else ops.colsum(Ybar.f32())
             wbars[i] = wb
             abar = None
             if Ybar is not None:
@@ -796,12 +800,21 @@ class BranchProgram(object):
                 # one launch: tbar_p = phi'(p) * (W^T Tbar) in `prod`, the raw W^T Tbar in `raw`
                 prod, tabar, _ = self._apply(w, Tbar, meta, True, act=_MULT, want_pre=(i > 0), want_act=True,
                                              dmul_pre=self._deriv(saved, i))
-                if act.module is not None:
-                    gb = ops.act_beta_grad(pres[i], tabar, 1, act.beta_sp(), g2=tps[i])
-                    if abar is not None:
-                        gb = gb + ops.act_beta_grad(pres[i], abar, 0, act.beta_sp())
-                    betabars[i] = gb
-                Ybar = _T(f=ops.act_second(pres[i], tps[i], tabar, abar, act.kind, act.beta_sp()))
+                fuse = (NEUMANN_FUSED['on'] and act.module is not None and act.kind == ops.ACT_LIPSWISH and i > 0
+                        and tabar.dim() == 2 and tabar.shape[1] >= 64 and ws[i - 1].fwd_split is not None)
+                if fuse:
+                    # one pass: ybar planes, their column sums (bias gradient of layer i-1) and d/dbeta
+                    planes, ybar_colsum, betabars[i] = ops.neumann_act_bwd(pres[i], tps[i], tabar, abar,
+                                                                          act.beta_sp())
+                    Ybar = _T(s=planes)
+                    Ybar.colsum = ybar_colsum
+                else:
+                    if act.module is not None:
+                        gb = ops.act_beta_grad(pres[i], tabar, 1, act.beta_sp(), g2=tps[i])
+                        if abar is not None:
+                            gb = gb + ops.act_beta_grad(pres[i], abar, 0, act.beta_sp())
+                        betabars[i] = gb
+                    Ybar = _T(f=ops.act_second(pres[i], tps[i], tabar, abar, act.kind, act.beta_sp()))
                 Tbar = _T(f=prod)
             else:
                 if i > 0:

@@ -108,6 +108,68 @@ k_act_second(const float* __restrict__ p, const float* __restrict__ t, const flo
   }
 }
 
+__device__ __forceinline__ void split1(float v, float& h, float& l) {
+  uint32_t hb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+  h = __uint_as_float(hb);
+  l = v - h;
+}
+// ---- fused activation step of the Neumann reverse sweep for one LipSwish layer (wide tensors, N columns):
+//   ybar = act''(p) * t * ta + act'(p) * ab                (adjoint of the pre-activation; tf32 hi/lo planes)
+//   colsum[n]  += sum_rows ybar                           (bias gradient of the layer below)
+//   beta_grad  += sum ta * t * d/dbeta act'(p) + ab * d/dbeta act(p)
+// One pass over p, t, ta, ab instead of act_second + two act_beta_grad + colsum + split (14 tensor passes -> 6).
+// Block b owns a contiguous row chunk and every column: per-block partials, summed by a second stage in
+// fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+k_neumann_act_bwd(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ ta,
+                  const float* __restrict__ ab, float* __restrict__ y_hi, float* __restrict__ y_lo,
+                  float* __restrict__ col_partial, float* __restrict__ beta_partial, long long M, int N,
+                  long long rows_per_block, const float* __restrict__ beta_ptr) {
+  const float beta = __ldg(beta_ptr);
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  double bacc = 0.0;
+  for (int c = threadIdx.x; c < N; c += 256) {
+    float cacc = 0.f;
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+      const long long i = r * N + c;
+      const float pv = p[i], tv = t[i], tav = ta[i];
+      const float abv = ab != nullptr ? ab[i] : 0.f;
+      const float y = act_eval<IMPFLOW_ACT_LIPSWISH>(pv, 2, beta) * tv * tav +
+                      act_eval<IMPFLOW_ACT_LIPSWISH>(pv, 1, beta) * abv;
+      float h, l;
+      split1(y, h, l);
+      y_hi[i] = h;
+      y_lo[i] = l;
+      cacc += y;
+      float bg = tav * tv * lipswish_dbeta(pv, 1, beta);
+      if (ab != nullptr) bg += abv * lipswish_dbeta(pv, 0, beta);
+      bacc += (double)bg;
+    }
+    col_partial[(long long)blockIdx.x * N + c] = cacc;
+  }
+  __shared__ double ws[8];
+  bacc = warp_sum_d(bacc);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = bacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tt = 0.0;
+    for (int w = 0; w < 8; ++w) tt += ws[w];
+    beta_partial[blockIdx.x] = (float)tt;
+  }
+}
+// second stage: colsum[n] = sum_b col_partial[b][n] (fixed order)
+__global__ void __launch_bounds__(256)
+k_sum_col_partials(const float* __restrict__ part, float* __restrict__ out, int nblk, int N) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblk; ++b) acc += part[(long long)b * N + c];
+  out[c] = acc;
+}
+
 // ---- lincomb3 -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_lincomb3(const float* __restrict__ a, float ca, const float* __restrict__ b, float cb,
@@ -247,12 +309,6 @@ k_split_tf32(const float* __restrict__ a, float* __restrict__ hi, float* __restr
     hi[i] = hf;
     lo[i] = v - hf;
   }
-}
-__device__ __forceinline__ void split1(float v, float& h, float& l) {
-  uint32_t hb;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-  h = __uint_as_float(hb);
-  l = v - h;
 }
 __global__ void __launch_bounds__(256)
 k_split_tf32_v4(const float4* __restrict__ a, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
@@ -442,6 +498,34 @@ extern "C" int impflow_act_beta_grad(const float* x, const float* g, const float
   k_beta_grad_stage1<<<grid, 256, 0, s>>>(x, g, g2, partial, n, order, beta_sp);
   if (check_launch("k_beta_grad_stage1")) return -1;
   k_sum_partials<<<1, 32, 0, s>>>(partial, out, grid);
+  return check_launch("k_sum_partials");
+}
+
+static int neumann_blocks(long long M) {
+  long long b = (M + 15) / 16;
+  if (b > 148 * 4) b = 148 * 4;
+  return b < 1 ? 1 : (int)b;
+}
+
+extern "C" size_t impflow_neumann_act_bwd_workspace_floats(long long M, int N) {
+  return (size_t)neumann_blocks(M) * ((size_t)N + 1);
+}
+
+extern "C" int impflow_neumann_act_bwd(const float* p, const float* t, const float* ta, const float* ab, float* y_hi,
+                                       float* y_lo, float* colsum, float* beta_grad, float* ws, long long M, int N,
+                                       const float* beta_sp, void* stream) {
+  IMPFLOW_REQUIRE(M >= 1 && N >= 1, "neumann_act_bwd: empty problem");
+  IMPFLOW_REQUIRE(beta_sp != nullptr && ws != nullptr, "neumann_act_bwd: beta / workspace missing");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nblk = neumann_blocks(M);
+  const long long rows = (M + nblk - 1) / nblk;
+  float* col_partial = ws;
+  float* beta_partial = ws + (size_t)nblk * N;
+  k_neumann_act_bwd<<<nblk, 256, 0, s>>>(p, t, ta, ab, y_hi, y_lo, col_partial, beta_partial, M, N, rows, beta_sp);
+  if (check_launch("k_neumann_act_bwd")) return -1;
+  k_sum_col_partials<<<(N + 255) / 256, 256, 0, s>>>(col_partial, colsum, nblk, N);
+  if (check_launch("k_sum_col_partials")) return -1;
+  k_sum_partials<<<1, 32, 0, s>>>(beta_partial, beta_grad, nblk);
   return check_launch("k_sum_partials");
 }
 

@@ -189,6 +189,27 @@ def act_second(p, t, ga, gb, kind, beta_sp=None):
     return out
 
 
+def neumann_act_bwd(p, t, ta, ab, beta_sp):
+    """Fused activation step of the Neumann reverse sweep (LipSwish): returns ((ybar_hi, ybar_lo), colsum (N,),
+    beta_grad (1,)) for ybar = act''(p) t ta + act'(p) ab; see impflow_neumann_act_bwd."""
+    p = p.contiguous()
+    M, N = p.shape
+    t, ta = _match_layout(t, p), _match_layout(ta, p)
+    if ab is not None:
+        ab = _match_layout(ab, p)
+    dev = p.device
+    hi, lo = torch.empty_like(p), torch.empty_like(p)
+    colsum_out = torch.empty(N, device=dev, dtype=torch.float32)
+    bg = torch.empty(1, device=dev, dtype=torch.float32)
+    lib = _lib()
+    ws = torch.empty(int(lib.impflow_neumann_act_bwd_workspace_floats(M, N)), device=dev, dtype=torch.float32)
+    _cabi.check(lib.impflow_neumann_act_bwd(_cabi.ptr(p), _cabi.ptr(t), _cabi.ptr(ta), _cabi.ptr(ab, 'ab', True),
+                                            _cabi.ptr(hi), _cabi.ptr(lo), _cabi.ptr(colsum_out), _cabi.ptr(bg),
+                                            _cabi.ptr(ws), M, N, _cabi.ptr(beta_sp), _cabi.stream()),
+                'neumann_act_bwd')
+    return (hi, lo), colsum_out, bg
+
+
 def lincomb3(a, ca, b=None, cb=0.0, c=None, cc=0.0, out=None):
     """out = ca*a + cb*b + cc*c (same shapes; laid out like a)."""
     a = _dense(a)

@@ -122,6 +122,14 @@ int impflow_act_beta_grad(const float* x, const float* g, const float* g2, float
  * reverse pass of the Neumann gradient estimator (implicit_block.py:386-388, 429-438). */
 int impflow_act_second(const float* p, const float* t, const float* ga, const float* gb, float* out,
                        long long n, int kind, const float* beta_sp, void* stream);
+/* The activation step of that reverse sweep for one LipSwish layer in ONE pass over (M,N) tensors:
+ *   ybar = act''(p) t ta + act'(p) ab   written as tf32 hi/lo planes (they feed the next transposed GEMM and the
+ *   weight gradient), colsum[n] = sum_m ybar (bias gradient of the layer below), beta_grad[0] = sum ta t
+ *   d/dbeta act'(p) + ab d/dbeta act(p).  ab may be NULL.  ws: impflow_neumann_act_bwd_workspace_floats(M,N). */
+size_t impflow_neumann_act_bwd_workspace_floats(long long M, int N);
+int impflow_neumann_act_bwd(const float* p, const float* t, const float* ta, const float* ab, float* y_hi, float* y_lo,
+                            float* colsum, float* beta_grad, float* ws, long long M, int N, const float* beta_sp,
+                            void* stream);
 /* out = a*ca + b*cb + c*cc (b, c may be NULL). Solver residuals x_embed - f(z) - z
  * (implicit_block.py:72) and v J + v - grad (:199-203); Neumann accumulation (:435). */
 int impflow_lincomb3(const float* a, float ca, const float* b, float cb, const float* c, float cc,

@@ -317,6 +317,26 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_neumann_act_bwd_workspace_floats(self, M, N):
+        return 8
+
+    def impflow_neumann_act_bwd(self, p, t, ta, ab, y_hi, y_lo, colsum, beta_grad, ws, M, N, beta_sp, stream):
+        n = M * N
+        beta = _beta(beta_sp)
+        P, T, TA = _f32(p, n), _f32(t, n), _f32(ta, n)
+        AB = _f32(ab, n) if _addr(ab) is not None else np.zeros(n, dtype=np.float32)
+        y = (_act(ACT_LIPSWISH, P, 2, beta) * T * TA + _act(ACT_LIPSWISH, P, 1, beta) * AB).astype(np.float32)
+        h = _tf32(y)
+        _f32(y_hi, n)[:] = h
+        _f32(y_lo, n)[:] = y - h
+        _f32(colsum, N)[:] = y.reshape(M, N).astype(np.float64).sum(0).astype(np.float32)
+        bg = (TA * T * _dbeta(P, 1, beta)).astype(np.float64).sum()
+        if _addr(ab) is not None:
+            bg += (AB * _dbeta(P, 0, beta)).astype(np.float64).sum()
+        _f32(beta_grad, 1)[0] = np.float32(bg)
+        self.launches += 3
+        return 0
+
     def impflow_lincomb3(self, a, ca, b, cb, c, cc, out, n, stream):
         r = _f32(a, n) * np.float32(ca)
         if _addr(b) is not None:

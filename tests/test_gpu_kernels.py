@@ -204,6 +204,24 @@ def test_wgrad_mn_major(ops, M, N1, N2):
     assert rel_err(out.cpu(), old.cpu()) < 1e-5
 
 
+@pytest.mark.parametrize('M,N,with_ab', [(4096, 512, True), (1000, 256, True), (65536, 512, False), (77, 64, True)])
+def test_neumann_act_bwd_fused(ops, M, N, with_ab):
+    """One-pass activation step of the Neumann reverse sweep against the separate kernels / fp64."""
+    g = torch.Generator().manual_seed(M + N)
+    p, t, ta, ab = [torch.randn(M, N, generator=g).cuda() for _ in range(4)]
+    beta = torch.tensor([0.83], device='cuda')
+    planes, colsum, bg = ops.neumann_act_bwd(p, t, ta, ab if with_ab else None, beta)
+    y_ref = ops.act_second(p, t, ta, ab if with_ab else None, ops.ACT_LIPSWISH, beta)
+    y = planes[0] + planes[1]
+    assert rel_err(y.cpu(), y_ref.cpu()) < 1e-6
+    assert torch.equal(planes[0], ops.split_tf32(y)[0])
+    assert rel_err(colsum.cpu(), y_ref.double().sum(0).cpu()) < 1e-5
+    bg_ref = ops.act_beta_grad(p, ta, 1, beta, g2=t)
+    if with_ab:
+        bg_ref = bg_ref + ops.act_beta_grad(p, ab, 0, beta)
+    assert abs(float(bg) - float(bg_ref)) < 1e-4 * max(1.0, abs(float(bg_ref)))
+
+
 @pytest.mark.parametrize('M,N', [(64, 32), (65536, 27), (1000, 77), (4096, 512), (130, 513)])
 def test_transpose_split(ops, M, N):
     a = torch.randn(M, N, generator=torch.Generator().manual_seed(M + N)).cuda()
