@@ -166,7 +166,8 @@ k_sum_col_partials(const float* __restrict__ part, float* __restrict__ out, int 
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
   float acc = 0.f;
-  for (int b = 0; b < nblk; ++b) acc += part[(long long)b * N + c];
+#pragma unroll 8
+  for (int b = 0; b < nblk; ++b) acc += part[(long long)b * N + c];      // independent loads, fixed summation order
   out[c] = acc;
 }
 
