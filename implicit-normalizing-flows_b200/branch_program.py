@@ -464,14 +464,21 @@ class BranchProgram(object):
             saved.ains = None       # backward_full / neumann re-evaluate the layer inputs from the pre-activations
         return self._from_rows(y, meta), saved
 
-    def _vjp_operands(self, saved):
+    def _vjp_operands(self, saved, P=None):
+        if P is not None and 1 not in saved.derivs and 2 not in saved.derivs:
+            # both act' multipliers of this saved forward in one call of the native runtime
+            d1, d2 = torch.empty_like(saved.pres[1]), torch.empty_like(saved.pres[2])
+            _cabi.check(_cabi.load().impflow_conv3_prepare_vjp(self._plan_ptr(P), _cabi.ptr(saved.pres[1]),
+                                                               _cabi.ptr(saved.pres[2]), _cabi.ptr(d1), _cabi.ptr(d2),
+                                                               _cabi.stream()), 'conv3_prepare_vjp')
+            saved.derivs[1], saved.derivs[2] = d1, d2
         return (_cabi.ptr(saved.pres[0], 'pre0', True), _cabi.ptr(self._deriv(saved, 1)),
                 _cabi.ptr(self._deriv(saved, 2)))
 
     def _native_vjp(self, P, v, saved):
         t, _ = self._to_rows(v)
         out = torch.empty_like(t)
-        pre0, d1, d2 = self._vjp_operands(saved)
+        pre0, d1, d2 = self._vjp_operands(saved, P)
         _cabi.check(_cabi.load().impflow_conv3_vjp(self._plan_ptr(P), pre0, d1, d2, _cabi.ptr(t), _cabi.ptr(out),
                                                    _cabi.stream()), 'conv3_vjp')
         if ops.GEMM_PROFILE['on']:
@@ -495,7 +502,7 @@ class BranchProgram(object):
         w_rows = torch.empty_like(t)
         n = len(coeffs)
         arr = (ctypes.c_double * max(n, 1))(*[float(c) for c in coeffs])
-        pre0, d1, d2 = self._vjp_operands(saved)
+        pre0, d1, d2 = self._vjp_operands(saved, P)
         _cabi.check(_cabi.load().impflow_conv3_power_series(self._plan_ptr(P), pre0, d1, d2, _cabi.ptr(t), arr, n,
                                                             _cabi.ptr(w_rows), _cabi.stream()), 'conv3_power_series')
         if ops.GEMM_PROFILE['on']:
@@ -524,7 +531,7 @@ class BranchProgram(object):
             wk.gb = torch.empty(B, d, device=rows.device, dtype=torch.float32)
         wk.xa.zero_()
         if mode == 1:
-            pre0, d1, d2 = self._vjp_operands(saved)
+            pre0, d1, d2 = self._vjp_operands(saved, P)
         else:
             pre0 = d1 = d2 = None
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
