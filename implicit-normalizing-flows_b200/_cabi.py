@@ -125,16 +125,23 @@ def sync_stream():
     torch.cuda.current_stream().synchronize()
 
 
+_F32 = torch.float32
+_CHECK_DEVICE = [True]      # the CPU test-suite's C-ABI emulator switches the device check off (tests/cabi_emulator.py)
+
+
 def ptr(t, name='tensor', allow_none=False):
-    """Device pointer of a dense fp32 CUDA tensor (memory order is the caller's business)."""
+    """Device pointer (int) of a dense fp32 CUDA tensor (memory order is the caller's business).  This sits on
+    every kernel launch (~10 arguments each, thousands of launches per step), so it is kept to two attribute
+    checks."""
     if t is None:
         if allow_none:
             return None
         raise ValueError('%s is None' % name)
-    require_device(t, name)
-    if t.dtype != torch.float32:
+    if t.dtype is not _F32:
         raise RuntimeError('impflow_b200: %s must be float32, got %s' % (name, t.dtype))
-    return ctypes.c_void_p(t.data_ptr())
+    if _CHECK_DEVICE[0] and not t.is_cuda:
+        require_device(t, name)
+    return t.data_ptr()
 
 
 def iptr(t):

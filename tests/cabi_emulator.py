@@ -724,6 +724,7 @@ def install(monkeypatch):
     monkeypatch.setattr(cabi, '_lib', lib)
     monkeypatch.setattr(cabi, 'load', lambda: lib)
     monkeypatch.setattr(cabi, 'require_device', lambda t, what='tensor': None)
+    monkeypatch.setattr(cabi, '_CHECK_DEVICE', [False])
     monkeypatch.setattr(cabi, 'pinned_bytes', lambda n: torch.zeros(n, dtype=torch.uint8))
     monkeypatch.setattr(cabi, 'sync_stream', lambda: None)
     monkeypatch.setattr(cabi, 'stream', lambda: None)
