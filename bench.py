@@ -382,6 +382,8 @@ def main():
     from impflow_b200.layers import implicit_block
     implicit_block.PROBE_MODE['mode'] = args.probe_mode
     implicit_block.FUSED['on'] = not args.unfused
+    if os.environ.get('IMPFLOW_TMA_STORE', '') == '0':       # A/B: per-thread stores instead of bulk tensor stores
+        pkg._cabi.load().impflow_gemm_tc_set_tma_store(0)
 
     torch.manual_seed(0)
     np.random.seed(0)
@@ -494,6 +496,12 @@ def main():
                 t = pkg.ops.time_branch3_shape(key, reps=3, flush=flush)
                 fl = 2.0 * M_ * (N3_ * C_ + C_ * C_ + C_ * N3_)      # algorithmic: unpadded 9c tap columns
                 desc = {'M': M_, 'C': C_, 'taps': N3_, 'mode': 'vjp' if is_vjp else ('fwd+save' if save_pre else 'fwd')}
+            elif key[0] == 'wgrad':
+                _, M_, N1_, N2_ = key
+                name = 'k_wgrad_tc3'
+                t = pkg.ops.time_wgrad_shape(key, reps=3, flush=flush)
+                fl = 2.0 * M_ * N1_ * N2_
+                desc = {'pixels': M_, 'N1': N1_, 'N2': N2_}
             else:
                 name = 'k_gemm_tc3'
                 t = pkg.ops.time_gemm_shape(key, reps=3, flush=flush)
@@ -557,7 +565,8 @@ def main():
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF sustained (B200_PROFILING.md)'
     KNAMES = {'k_branch3': 'k_branch3 (fused 3-layer residual-branch tile kernel, tcgen05 3xTF32, operands in TMEM)',
-              'k_gemm_tc3': 'k_gemm_tc3 (tcgen05 3xTF32 residual-branch GEMM)'}
+              'k_gemm_tc3': 'k_gemm_tc3 (tcgen05 3xTF32 residual-branch GEMM)',
+              'k_wgrad_tc3': 'k_wgrad_tc3 (tcgen05 3xTF32 weight gradient, MN-major operands)'}
 
     def roof(name):
         k = kern[name]
@@ -587,6 +596,8 @@ def main():
     }
     if len(order) > 1:
         line['roofline_secondary'] = roof(order[1])
+    if len(order) > 2:
+        line['roofline_tertiary'] = roof(order[2])
     if not is_mlp:
         # the solver-algebra phase against the HBM roofline: the bench shape (latency-bound: 0.8 MB per
         # vector) and the classifier shape of SURVEY.md section 8 (B=128, d=65536: 2 GB of history)

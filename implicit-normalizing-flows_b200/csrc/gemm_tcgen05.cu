@@ -36,18 +36,22 @@ struct TcCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = TC_EPI_WARPS * 4096;   // one 32x32 fp32 tile per epilogue warp (TMA stores)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
            const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+           const __grid_constant__ CUtensorMap mapPre, const __grid_constant__ CUtensorMap mapAct,
+           const __grid_constant__ CUtensorMap mapShi, const __grid_constant__ CUtensorMap mapSlo, int tma_store,
            long long M, int N, int K, TcEpilogue ep, int splits, float* __restrict__ splitk_ws) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;        // 1024-byte aligned 4 KB tiles, one per epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
@@ -177,6 +181,43 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     const Epilogue e = resolve_beta(ep.e);
+    // Output path.  tma_store: every 32x32 chunk is staged in this warp's shared-memory tile (128-byte rows,
+    // SWIZZLE_128B, conflict-free row-per-thread writes) and leaves through ONE bulk tensor store, which also
+    // clips ragged M / N; the per-thread 32-byte global stores of the fallback touch 32 different lines per
+    // instruction and are limited by the L1 request rate.
+    const bool use_tma = tma_store != 0 && splits == 1;
+    uint8_t* const my_stage = staging + (warp - 4) * 4096;
+    auto emit = [&](const CUtensorMap* map, float* out, const float* vals, long long row, int n0, long long m0w,
+                    bool full_vec) {
+      if (use_tma) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read the tile
+        __syncwarp();
+        const uint32_t sbase = smem_u32(my_stage) + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)((j ^ (lane & 7)) << 4)),
+                       "f"(vals[4 * j]), "f"(vals[4 * j + 1]), "f"(vals[4 * j + 2]), "f"(vals[4 * j + 3])
+                       : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(map)),
+                       "r"(smem_u32(my_stage)), "r"(n0), "r"((int)m0w)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        return;
+      }
+      if (full_vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) st_global_v8(out + row + n0 + j, vals + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < N) out[row + n0 + j] = vals[j];
+      }
+    };
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long mn = tile / splits;
       const int ks = (int)(tile % splits);
@@ -214,35 +255,27 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
           }
           continue;
         }
-        if (m < M && n0 < N) {
+        const long long m0w = (mn / n_tiles) * TC_BM + q * 32;          // first row of this warp's chunk
+        if (use_tma ? (m0w < M && n0 < N) : (m < M && n0 < N)) {
           const long long row = m * e.ldc;
           const bool full_vec = (n0 + 32 <= N) && ((e.ldc & 7) == 0);   // 32-byte aligned row chunks
           float v[32];
           if (e.dmul_pre != nullptr) {
             if (e.act_out != nullptr) {      // dmul mode: act_out receives the raw accumulator
-              if (full_vec) {
+              float raw[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  float t8[8];
-#pragma unroll
-                  for (int u = 0; u < 8; ++u) t8[u] = __uint_as_float(r[j + u]);
-                  st_global_v8(e.act_out + row + n0 + j, t8);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (n0 + j < N) e.act_out[row + n0 + j] = __uint_as_float(r[j]);
-              }
+              for (int j = 0; j < 32; ++j) raw[j] = __uint_as_float(r[j]);
+              emit(&mapAct, e.act_out, raw, row, n0, m0w, full_vec);
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float p[8];
-              if (full_vec) {
+              if (full_vec && m < M) {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) p[u] = dm[j + u];
               } else {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) p[u] = (n0 + j + u < N) ? e.dmul_pre[row + n0 + j + u] : 0.f;
+                for (int u = 0; u < 8; ++u) p[u] = (m < M && n0 + j + u < N) ? e.dmul_pre[row + n0 + j + u] : 0.f;
               }
 #pragma unroll
               for (int u = 0; u < 8; ++u)
@@ -254,16 +287,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
               const float b = (e.bias != nullptr && n0 + j < N) ? __ldg(e.bias + n0 + j) : 0.f;
               v[j] = __uint_as_float(r[j]) + b;
             }
-            if (e.pre_out != nullptr) {
-              if (full_vec) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) st_global_v8(e.pre_out + row + n0 + j, v + j);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (n0 + j < N) e.pre_out[row + n0 + j] = v[j];
-              }
-            }
+            if (e.pre_out != nullptr) emit(&mapPre, e.pre_out, v, row, n0, m0w, full_vec);
             if (e.act_kind == IMPFLOW_ACT_LIPSWISH) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = lipswish_fast(v[j], e.beta);
@@ -272,40 +296,22 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
               for (int j = 0; j < 32; ++j) v[j] = act_dispatch(e.act_kind, v[j], 0, e.beta);
             }
           }
-          float* main_out = (e.dmul_pre != nullptr) ? e.pre_out : e.act_out;
-          if (main_out != nullptr) {
-            if (full_vec) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) st_global_v8(main_out + row + n0 + j, v + j);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < N) main_out[row + n0 + j] = v[j];
-            }
+          if (e.dmul_pre != nullptr) {
+            if (e.pre_out != nullptr) emit(&mapPre, e.pre_out, v, row, n0, m0w, full_vec);
+          } else if (e.act_out != nullptr) {
+            emit(&mapAct, e.act_out, v, row, n0, m0w, full_vec);
           }
           if (ep.split_hi != nullptr) {
+            float h[32], l[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float h[8], l[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                // round to nearest, ties away (= cvt.rna.tf32.f32 for finite values) in two integer ops
-                const uint32_t hb = (__float_as_uint(v[j + u]) + 0x1000u) & 0xffffe000u;
-                h[u] = __uint_as_float(hb);
-                l[u] = v[j + u] - h[u];
-              }
-              if (full_vec) {
-                st_global_v8(ep.split_hi + row + n0 + j, h);
-                st_global_v8(ep.split_lo + row + n0 + j, l);
-              } else {
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (n0 + j + u < N) {
-                    ep.split_hi[row + n0 + j + u] = h[u];
-                    ep.split_lo[row + n0 + j + u] = l[u];
-                  }
-              }
+            for (int j = 0; j < 32; ++j) {
+              // round to nearest, ties away (= cvt.rna.tf32.f32 for finite values) in two integer ops
+              const uint32_t hb = (__float_as_uint(v[j]) + 0x1000u) & 0xffffe000u;
+              h[j] = __uint_as_float(hb);
+              l[j] = v[j] - h[j];
             }
+            emit(&mapShi, ep.split_hi, h, row, n0, m0w, full_vec);
+            emit(&mapSlo, ep.split_lo, l, row, n0, m0w, full_vec);
           }
         }
       }
@@ -317,6 +323,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
         acc_phase ^= 1;
       }
     }
+    if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
   }
   tc_fence_before();
   __syncthreads();
@@ -342,6 +349,8 @@ k_splitk_reduce(const float* __restrict__ ws, const float* __restrict__ bias, fl
   }
 }
 
+static int g_tma_store = 1;   // A/B switch (impflow_gemm_tc_set_tma_store)
+
 static int pick_splits(long long M, int N, int K, int BN) {
   const long long tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
   const int num_kb = K / TC_BK;
@@ -360,6 +369,16 @@ static int launch_tc(const float* Ahi, const float* Alo, long long lda, const fl
   if (make_map(&mAh, Ahi, M, K, lda, TC_BM) || make_map(&mAl, Alo, M, K, lda, TC_BM) ||
       make_map(&mBh, Bhi, N, K, ldb, BN) || make_map(&mBl, Blo, N, K, ldb, BN))
     return -1;
+  // outputs leave through bulk tensor stores when every output plane can be described by a tensor map
+  // (16-byte aligned base and row stride); split-K partials keep the plain stores
+  CUtensorMap mo[4];
+  memset(mo, 0, sizeof(mo));
+  float* outs[4] = {ep.e.pre_out, ep.e.act_out, ep.split_hi, ep.split_lo};
+  int tma_store = (g_tma_store && splits == 1 && (ep.e.ldc % 4) == 0) ? 1 : 0;
+  for (int i = 0; i < 4 && tma_store; ++i)
+    if (outs[i] != nullptr && (reinterpret_cast<uintptr_t>(outs[i]) & 15) != 0) tma_store = 0;
+  for (int i = 0; i < 4 && tma_store; ++i)
+    if (outs[i] != nullptr && make_map(&mo[i], outs[i], M, N, ep.e.ldc, 32)) return -1;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_gemm_tc3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes) !=
@@ -371,7 +390,8 @@ static int launch_tc(const float* Ahi, const float* Alo, long long lda, const fl
   }
   const long long tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN) * splits;
   const int grid = (int)(tiles < 148 ? tiles : 148);
-  k_gemm_tc3<BN><<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, s>>>(mAh, mAl, mBh, mBl, M, N, K, ep, splits, ws);
+  k_gemm_tc3<BN><<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, s>>>(mAh, mAl, mBh, mBl, mo[0], mo[1], mo[2], mo[3], tma_store,
+                                                                  M, N, K, ep, splits, ws);
   if (check_launch("k_gemm_tc3")) return -1;
   if (splits > 1) {
     long long blocks = (M * N + 255) / 256;
@@ -416,6 +436,12 @@ static int tc_bn(int N, long long M = 1LL << 40) {
 extern "C" int impflow_gemm_tc_set_wide_tiles(int on) {
   const int prev = g_wide_tiles;
   g_wide_tiles = on ? 1 : 0;
+  return prev;
+}
+
+extern "C" int impflow_gemm_tc_set_tma_store(int on) {
+  const int prev = g_tma_store;
+  g_tma_store = on ? 1 : 0;
   return prev;
 }
 

@@ -97,6 +97,30 @@ def time_branch3_shape(key, reps=5, flush=None):
     return sorted(times)[len(times) // 2]
 
 
+def time_wgrad_shape(key, reps=5, flush=None):
+    """Median CUDA-event duration (ms) of one MN-major weight-gradient launch (kernel + fixed-order reduce)."""
+    _, M, N1, N2 = key
+    dev = torch.device('cuda', torch.cuda.current_device())
+    Gs = split_tf32(torch.randn(M, N1, device=dev))
+    As = split_tf32(torch.randn(M, N2, device=dev))
+    if flush is None:
+        flush = torch.empty(64 * 1024 * 1024, device=dev)
+    was = GEMM_PROFILE['on']
+    GEMM_PROFILE['on'] = False
+    times = []
+    for i in range(reps + 1):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        wgrad_gemm(None, None, G_split=Gs, A_split=As)
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            times.append(e0.elapsed_time(e1))
+    GEMM_PROFILE['on'] = was
+    return sorted(times)[len(times) // 2]
+
+
 # While a caller differentiates w.r.t. ACTIVATIONS only (the vjp chains of the log-det estimators,
 # implicit_block.py:422,434,436), the parameter-gradient branches of the primitives' backward
 # passes (weight-gradient GEMMs with their transposes, bias column sums, LipSwish beta reductions)
@@ -314,7 +338,8 @@ def wgrad_gemm(G, A, G_split=None, A_split=None):
                                          n_y, _cabi.ptr(out), N2, 1 if swap else 0, M, n_x, n_y, _cabi.ptr(ws),
                                          _cabi.stream()), 'wgrad_tc')
         if GEMM_PROFILE['on']:
-            record_gemm(n_x, n_y, M, True, False, False, False, True)
+            key = ('wgrad', int(M), int(n_x), int(n_y))
+            GEMM_PROFILE['shapes'][key] = GEMM_PROFILE['shapes'].get(key, 0) + 1
         return out
     if G is None:
         G = lincomb3(G_split[0], 1.0, G_split[1], 1.0)

@@ -360,6 +360,9 @@ class EmulatedLib(object):
     def impflow_gemm_tc_splits(self, M, N, K):
         return 1
 
+    def impflow_gemm_tc_set_tma_store(self, on):
+        return 1
+
     def impflow_gemm_tc_set_wide_tiles(self, on):
         return 1
 
