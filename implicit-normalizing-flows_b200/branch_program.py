@@ -733,15 +733,18 @@ class BranchProgram(object):
                 bbars[i] = ops.colsum(Gf)
             if i == 0 and not need_input_grad and (act is None or act.module is None):
                 break
+            # the adjoint handed to layer i-1 also leaves the GEMM as hi/lo planes when that layer consumes planes
+            # (its transposed GEMM and its weight gradient): no separate split pass
+            planes = i > 0 and self._wants_planes(ws[i - 1], True, w.cin)
             if act is not None:
                 want_raw = act.module is not None
-                pbar, abar, _ = self._apply(w, G, meta, True, act=_MULT, want_pre=True, want_act=want_raw,
-                                            dmul_pre=self._deriv(saved, i))
+                pbar, abar, split = self._apply(w, G, meta, True, act=_MULT, want_pre=True, want_act=want_raw,
+                                                dmul_pre=self._deriv(saved, i), want_split=planes)
                 if want_raw:
                     betabars[i] = ops.act_beta_grad(pres[i], abar, 0, act.beta_sp())
             else:
-                pbar, _, _ = self._apply(w, G, meta, True, want_pre=True)
-            G = _T(f=pbar)
+                pbar, _, split = self._apply(w, G, meta, True, want_pre=True, want_split=planes)
+            G = _T(f=pbar, s=split)
         gx = self._from_rows(G.f32(), meta) if need_input_grad else None
         return gx, self._finish_param_grads(ws, wbars, bbars, betabars)
 
@@ -805,8 +808,9 @@ class BranchProgram(object):
                 abar, _, _ = self._apply(w, Ybar, meta, True, want_pre=True)
             if act is not None:
                 # one launch: tbar_p = phi'(p) * (W^T Tbar) in `prod`, the raw W^T Tbar in `raw`
-                prod, tabar, _ = self._apply(w, Tbar, meta, True, act=_MULT, want_pre=(i > 0), want_act=True,
-                                             dmul_pre=self._deriv(saved, i))
+                planes = i > 0 and self._wants_planes(ws[i - 1], True, w.cin)
+                prod, tabar, tsplit = self._apply(w, Tbar, meta, True, act=_MULT, want_pre=(i > 0 and not planes),
+                                                  want_act=True, dmul_pre=self._deriv(saved, i), want_split=planes)
                 fuse = (NEUMANN_FUSED['on'] and act.module is not None and act.kind == ops.ACT_LIPSWISH and i > 0
                         and tabar.dim() == 2 and tabar.shape[1] >= 64 and ws[i - 1].fwd_split is not None)
                 if fuse:
@@ -822,7 +826,7 @@ class BranchProgram(object):
                             gb = gb + ops.act_beta_grad(pres[i], abar, 0, act.beta_sp())
                         betabars[i] = gb
                     Ybar = _T(f=ops.act_second(pres[i], tps[i], tabar, abar, act.kind, act.beta_sp()))
-                Tbar = _T(f=prod)
+                Tbar = _T(f=prod, s=tsplit)
             else:
                 if i > 0:
                     tabar, _, _ = self._apply(w, Tbar, meta, True, want_pre=True)
