@@ -550,11 +550,19 @@ class BranchProgram(object):
         """Layer-input handles of a saved forward (the fused forward keeps only the pre-activations)."""
         if saved.ains is None:
             acts = self._acts()
+            ws = self._weights
             ains = []
             for i in range(len(self.stages)):
                 src = saved.rows if i == 0 else saved.pres[i]
                 a = acts[i]
-                ains.append(_T(f=src if a is None else ops.act_mul(src, None, a.kind, 0, a.beta_sp())))
+                w = ws[i] if ws is not None and i < len(ws) else None
+                # a wide input that the weight gradient reads as planes is produced as planes straight away
+                as_planes = (a is not None and w is not None and w.fwd_split is not None and ops.WGRAD_MN_MAJOR['on']
+                             and w.cin == w.fwd_k and (w.kind == 'mm' or not w.a_type))
+                if as_planes:
+                    ains.append(_T(s=ops.act_split(src, a.kind, 0, a.beta_sp())))
+                else:
+                    ains.append(_T(f=src if a is None else ops.act_mul(src, None, a.kind, 0, a.beta_sp())))
             saved.ains = ains
         return saved.ains
 

@@ -114,6 +114,22 @@ __device__ __forceinline__ void split1(float v, float& h, float& l) {
   h = __uint_as_float(hb);
   l = v - h;
 }
+// ---- act^(order)(x) written directly as tf32 hi/lo planes (layer inputs re-evaluated from saved pre-activations
+// for the weight gradients: no fp32 round trip, no separate split pass)
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_act_split(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n, int order,
+            const float* __restrict__ beta_ptr) {
+  const float beta = (beta_ptr != nullptr) ? __ldg(beta_ptr) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float h, l;
+    split1(act_eval<KIND>(x[i], order, beta), h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
 // ---- fused activation step of the Neumann reverse sweep for one LipSwish layer (wide tensors, N columns):
 //   ybar = act''(p) * t * ta + act'(p) * ab                (adjoint of the pre-activation; tf32 hi/lo planes)
 //   colsum[n]  += sum_rows ybar                           (bias gradient of the layer below)
@@ -500,6 +516,22 @@ extern "C" int impflow_act_beta_grad(const float* x, const float* g, const float
   if (check_launch("k_beta_grad_stage1")) return -1;
   k_sum_partials<<<1, 32, 0, s>>>(partial, out, grid);
   return check_launch("k_sum_partials");
+}
+
+extern "C" int impflow_act_split(const float* x, float* hi, float* lo, long long n, int kind, int order,
+                                 const float* beta_sp, void* stream) {
+  if (n <= 0) return 0;
+  IMPFLOW_REQUIRE(order >= 0 && order <= 3, "act_split: order %d not in [0,3]", order);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = grid_for(n, 256);
+  switch (kind) {
+    case IMPFLOW_ACT_SIN: k_act_split<IMPFLOW_ACT_SIN><<<grid, 256, 0, s>>>(x, hi, lo, n, order, beta_sp); break;
+    case IMPFLOW_ACT_LIPSWISH: k_act_split<IMPFLOW_ACT_LIPSWISH><<<grid, 256, 0, s>>>(x, hi, lo, n, order, beta_sp); break;
+    case IMPFLOW_ACT_RELU: k_act_split<IMPFLOW_ACT_RELU><<<grid, 256, 0, s>>>(x, hi, lo, n, order, beta_sp); break;
+    case IMPFLOW_ACT_NONE: k_act_split<IMPFLOW_ACT_NONE><<<grid, 256, 0, s>>>(x, hi, lo, n, order, beta_sp); break;
+    default: set_error("act_split: unknown activation kind %d", kind); return -3;
+  }
+  return check_launch("k_act_split");
 }
 
 static int neumann_blocks(long long M) {

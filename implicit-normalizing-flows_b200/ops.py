@@ -186,6 +186,15 @@ def act_mul(x, g, kind, order, beta_sp=None, out=None):
     return out
 
 
+def act_split(x, kind, order, beta_sp=None):
+    """(hi, lo) tf32 planes of act^(order)(x) in one pass."""
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    _cabi.check(_lib().impflow_act_split(_cabi.ptr(x), _cabi.ptr(hi), _cabi.ptr(lo), x.numel(), kind, order,
+                                         _cabi.ptr(beta_sp, 'beta_sp', True), _cabi.stream()), 'act_split')
+    return hi, lo
+
+
 def act_beta_grad(x, g, order, beta_sp, g2=None):
     """sum(g * g2 * d/dbeta act^(order)(x)) as a 1-element tensor."""
     x = _dense(x)

@@ -113,6 +113,9 @@ int impflow_mlp_broyden_solve(const float* x_embed, const float* const* Wt, cons
  * scalar softplus(beta) for LipSwish (NULL otherwise) — a pointer so that no host sync is needed.  Replaces activations.py:11-12,70-71 and their autograd derivatives. */
 int impflow_act_mul(const float* x, const float* g, float* out, long long n, int kind, int order,
                     const float* beta_sp, void* stream);
+/* hi + lo = act^(order)(x) as tf32 planes (the K-major / MN-major operand form of the tensor-core kernels). */
+int impflow_act_split(const float* x, float* hi, float* lo, long long n, int kind, int order, const float* beta_sp,
+                      void* stream);
 /* out[0] = sum_i g[i] * g2[i] * d/d(beta_sp) act^(order)(x[i])  (order 0..2; g2 may be NULL);
  * deterministic 2-stage reduce; `partial` needs impflow_reduce_workspace_floats(n) floats. */
 size_t impflow_reduce_workspace_floats(long long n);

@@ -281,6 +281,14 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_act_split(self, x, hi, lo, n, kind, order, beta_sp, stream):
+        v = _act(kind, _f32(x, n), order, _beta(beta_sp)).astype(np.float32)
+        h = _tf32(v)
+        _f32(hi, n)[:] = h
+        _f32(lo, n)[:] = v - h
+        self.launches += 1
+        return 0
+
     def impflow_act_beta_grad(self, x, g, g2, out, partial, n, order, beta_sp, stream):
         xv, gv = _f32(x, n).astype(np.float64), _f32(g, n).astype(np.float64)
         if _addr(g2) is not None:
