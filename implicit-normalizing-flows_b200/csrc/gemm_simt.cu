@@ -99,6 +99,86 @@ k_gemm_nt(const float* __restrict__ A, long long lda, const float* __restrict__ 
   }
 }
 
+// General-stride variant for the autograd primitives of the small MLP / classifier shapes:
+//   C[m,n] = sum_k A[m*sAm + k*sAk] * B[n*sBn + k*sBk] (+ bias[n])
+// so that A B, A^T B, A B^T and A^T B^T all run without materialising a transpose (the derivative of a GEMM
+// is a GEMM with transposed operands; with double backward the transposes used to be 25 % of all launches).
+template <int BM>      // rows per CTA: 64, or 32 / 16 when the problem has few row tiles (more CTAs in flight)
+__global__ void __launch_bounds__(256)
+k_gemm_strided(const float* __restrict__ A, long long sAm, long long sAk, const float* __restrict__ Bm, long long sBn,
+               long long sBk, const float* __restrict__ bias, float* __restrict__ out, long long ldc, long long M,
+               int N, int K) {
+  constexpr int BN = 64, TM = BM / 16, TN = 4;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = (long long)blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  // element e of the tile = (row r, k): consecutive threads follow the contiguous dimension of the operand
+  const bool a_m_contig = sAm == 1, b_n_contig = sBn == 1;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int e = tid; e < BM * BK; e += 256) {
+      const int r = a_m_contig ? (e % BM) : (e / BK), kk = a_m_contig ? (e / BM) : (e % BK);
+      const long long gm = m0 + r;
+      const int gk = k0 + kk;
+      As[kk][r] = (gm < M && gk < K) ? A[gm * sAm + (long long)gk * sAk] : 0.f;
+    }
+#pragma unroll
+    for (int e = tid; e < BN * BK; e += 256) {
+      const int r = b_n_contig ? (e % BN) : (e / BK), kk = b_n_contig ? (e / BN) : (e % BK);
+      const int gn = n0 + r;
+      const int gk = k0 + kk;
+      Bs[kk][r] = (gn < N && gk < K) ? Bm[(long long)gn * sBn + (long long)gk * sBk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+      const float4 tb = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float b[4] = {tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const long long m = m0 + ty * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) out[m * ldc + n] = acc[i][j] + (bias != nullptr ? bias[n] : 0.f);
+    }
+  }
+}
+
+int gemm_strided_simt(const float* A, long long sAm, long long sAk, const float* Bm, long long sBn, long long sBk,
+                      const float* bias, float* out, long long ldc, long long M, int N, int K, cudaStream_t s) {
+  const long long col_tiles = (N + 63) / 64;
+  // enough CTAs to cover the SMs: shrink the row tile while the grid is below ~2 CTAs per SM
+  int bm = 64;
+  if (((M + 63) / 64) * col_tiles < 296) bm = 32;
+  if (((M + 31) / 32) * col_tiles < 296) bm = 16;
+  dim3 grid((unsigned)col_tiles, (unsigned)((M + bm - 1) / bm));
+  IMPFLOW_REQUIRE(grid.y <= 65535, "gemm_strided: M=%lld too large", M);
+  if (bm == 64) k_gemm_strided<64><<<grid, 256, 0, s>>>(A, sAm, sAk, Bm, sBn, sBk, bias, out, ldc, M, N, K);
+  else if (bm == 32) k_gemm_strided<32><<<grid, 256, 0, s>>>(A, sAm, sAk, Bm, sBn, sBk, bias, out, ldc, M, N, K);
+  else k_gemm_strided<16><<<grid, 256, 0, s>>>(A, sAm, sAk, Bm, sBn, sBk, bias, out, ldc, M, N, K);
+  return check_launch("k_gemm_strided");
+}
+
 int gemm_nt_simt(const float* A, long long lda, const float* Bm, long long ldb, long long M, int N, int K,
                  const Epilogue& ep, cudaStream_t s) {
   const int vecA = ((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (lda % 4) == 0) ? 1 : 0;

@@ -404,6 +404,8 @@ static int launch_tc(const float* Ahi, const float* Alo, long long lda, const fl
 
 int gemm_nt_simt(const float* A, long long lda, const float* Bm, long long ldb, long long M, int N, int K,
                  const Epilogue& ep, cudaStream_t s);
+int gemm_strided_simt(const float* A, long long sAm, long long sAk, const float* Bm, long long sBn, long long sBk,
+                      const float* bias, float* out, long long ldc, long long M, int N, int K, cudaStream_t s);
 
 }  // namespace impflow
 
@@ -418,6 +420,14 @@ extern "C" int impflow_gemm_nt(const float* A, long long lda, const float* Bm, l
                   "gemm_nt: dmul_pre needs pre_out or act_out");
   Epilogue ep{bias, pre_out, act_out, dmul_pre, ldc, act_kind, beta_sp, 0.f};
   return gemm_nt_simt(A, lda, Bm, ldb, M, N, K, ep, (cudaStream_t)stream);
+}
+
+extern "C" int impflow_gemm_strided(const float* A, long long sAm, long long sAk, const float* Bm, long long sBn,
+                                    long long sBk, const float* bias, float* out, long long ldc, long long M, int N,
+                                    int K, void* stream) {
+  IMPFLOW_REQUIRE(M >= 1 && N >= 1 && K >= 1, "gemm_strided: empty problem M=%lld N=%d K=%d", M, N, K);
+  IMPFLOW_REQUIRE(out != nullptr, "gemm_strided: no output given");
+  return gemm_strided_simt(A, sAm, sAk, Bm, sBn, sBk, bias, out, ldc, M, N, K, (cudaStream_t)stream);
 }
 
 static int g_wide_tiles = 1;   // BN = 256 tiles for N >= 256 (halves the A-operand re-reads through L2)

@@ -17,7 +17,9 @@ ACT_MULTIPLIER = 4      # dmul epilogues only: the dmul operand already holds ac
 
 # GEMM backend policy: 'auto' uses the tcgen05 3xTF32 kernel whenever its layout constraints hold
 # and the problem is big enough to fill tiles; 'simt' forces the exact-fp32 CUDA-core kernel.
-_BACKEND = {'mode': 'auto', 'min_flops_tc': 2 * 128 * 128 * 64}
+# min_flops_tc_autograd: below this the autograd primitive stays on the CUDA cores (one launch instead of two plane
+# splits + the tensor-core launch; the MLP layers of the toy / tabular flows are 33 MFLOP)
+_BACKEND = {'mode': 'auto', 'min_flops_tc': 2 * 128 * 128 * 64, 'min_flops_tc_autograd': 1.0e9}
 
 
 # bench.py switches this on inside its timed region to collect (start, end, flop) CUDA events of
@@ -645,13 +647,60 @@ class _ColSum(torch.autograd.Function):
         return g.unsqueeze(0).expand(ctx.M, -1)
 
 
+def gemm_strided(A, ta, Bm, tb, bias=None):
+    """op(A) op(B) (+ bias) on the CUDA cores without transposed copies: op(X) = X^T if its flag is set.
+    A is (M,K) or (K,M) when ta; Bm is (K,N) or (N,K) when tb."""
+    A, Bm = A.contiguous(), Bm.contiguous()
+    M, K = (A.shape[1], A.shape[0]) if ta else (A.shape[0], A.shape[1])
+    N = Bm.shape[0] if tb else Bm.shape[1]
+    assert (Bm.shape[1] if tb else Bm.shape[0]) == K, 'gemm_strided: inner dimensions differ'
+    lda, ldb = A.shape[1], Bm.shape[1]
+    out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+    sA = (1, lda) if ta else (lda, 1)
+    sB = (ldb, 1) if tb else (1, ldb)
+    _cabi.check(_lib().impflow_gemm_strided(_cabi.ptr(A), sA[0], sA[1], _cabi.ptr(Bm), sB[0], sB[1],
+                                            _cabi.ptr(bias, 'bias', True), _cabi.ptr(out), N, M, N, K, _cabi.stream()),
+                'gemm_strided')
+    return out
+
+
+class _MM(torch.autograd.Function):
+    """C = op(A) op(B) with transpose flags; closed under differentiation (the derivative of a GEMM is a GEMM with
+    other flags), so the small-shape autograd paths (toy / tabular / classifier, incl. the double backward of the
+    log-det estimators) never materialise a transpose."""
+
+    @staticmethod
+    def forward(ctx, A, Bm, ta, tb):
+        ctx.save_for_backward(A, Bm)
+        ctx.ta, ctx.tb = ta, tb
+        return gemm_strided(A, ta, Bm, tb)
+
+    @staticmethod
+    def backward(ctx, G):
+        A, Bm = ctx.saved_tensors
+        ta, tb = ctx.ta, ctx.tb
+        gA = gB = None
+        if ctx.needs_input_grad[0]:
+            gA = _MM.apply(Bm, G, tb, True) if ta else _MM.apply(G, Bm, False, not tb)
+        if ctx.needs_input_grad[1]:
+            gB = _MM.apply(G, A, True, ta) if tb else _MM.apply(A, G, not ta, False)
+        return gA, gB, None, None
+
+
 class _GemmNT(torch.autograd.Function):
-    """C = A B^T + bias;  dA = G B = G (B^T)^T,  dB = G^T A,  dbias = colsum(G)."""
+    """C = A B^T + bias;  dA = G B,  dB = G^T A,  dbias = colsum(G).  Large shapes run on the tcgen05 kernel
+    (transposed copies + planes); small ones on the CUDA-core strided kernel via _MM."""
 
     @staticmethod
     def forward(ctx, A, Bm, bias):
         ctx.save_for_backward(A, Bm)
         ctx.has_bias = bias is not None
+        M, K = A.shape
+        N = Bm.shape[0]
+        ctx.small = not _tc_ok(M, N, (K + 31) // 32 * 32, 4, 4) or (
+            _BACKEND['mode'] == 'auto' and 2.0 * M * N * K < _BACKEND['min_flops_tc_autograd'])
+        if ctx.small:
+            return gemm_strided(A, False, Bm, True, bias)
         pre, _, _ = gemm_nt(A, Bm, bias)
         return pre
 
@@ -660,10 +709,16 @@ class _GemmNT(torch.autograd.Function):
         A, Bm = ctx.saved_tensors
         gA = gB = gbias = None
         G = G.contiguous()
-        if ctx.needs_input_grad[0]:
-            gA = _GemmNT.apply(G, _Transpose.apply(Bm), None)
-        if ctx.needs_input_grad[1] and not _ACT_ONLY['on']:
-            gB = _GemmNT.apply(_Transpose.apply(G), _Transpose.apply(A), None)
+        if ctx.small:
+            if ctx.needs_input_grad[0]:
+                gA = _MM.apply(G, Bm, False, False)
+            if ctx.needs_input_grad[1] and not _ACT_ONLY['on']:
+                gB = _MM.apply(G, A, True, False)
+        else:
+            if ctx.needs_input_grad[0]:
+                gA = _GemmNT.apply(G, _Transpose.apply(Bm), None)
+            if ctx.needs_input_grad[1] and not _ACT_ONLY['on']:
+                gB = _GemmNT.apply(_Transpose.apply(G), _Transpose.apply(A), None)
         if ctx.has_bias and ctx.needs_input_grad[2] and not _ACT_ONLY['on']:
             gbias = _ColSum.apply(G)
         return gA, gB, gbias

@@ -185,6 +185,10 @@ int impflow_clip_adam_ema(float* p, float* g, float* m, float* v, float* ema, lo
 int impflow_gemm_nt(const float* A, long long lda, const float* Bm, long long ldb, const float* bias,
                     float* pre_out, float* act_out, const float* dmul_pre, long long ldc, long long M,
                     int N, int K, int act_kind, const float* beta_sp, void* stream);
+/* Exact-fp32 CUDA-core GEMM with element strides, C[m,n] = sum_k A[m*sAm + k*sAk] * B[n*sBn + k*sBk] (+ bias[n]):
+ * the autograd primitives of the small shapes use it for A B, A^T B, A B^T, A^T B^T without transposed copies. */
+int impflow_gemm_strided(const float* A, long long sAm, long long sAk, const float* Bm, long long sBn, long long sBk,
+                         const float* bias, float* out, long long ldc, long long M, int N, int K, void* stream);
 int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long long lda, const float* B_hi,
                        const float* B_lo, long long ldb, const float* bias, float* pre_out, float* act_out,
                        const float* dmul_pre, float* split_hi, float* split_lo, long long ldc, long long M,

@@ -65,10 +65,11 @@ def case_matches_module_autograd(name, backend, device='cpu'):
             y2 = prog.forward(x, save=True)
             vjp = prog.vjp(v)
             vjp_again = prog.vjp(v)
-        assert rel_err(y.cpu(), y_ref.detach().cpu()) < 3e-6
-        assert rel_err(y2.cpu(), y_ref.detach().cpu()) < 3e-6
-        assert rel_err(vjp.cpu(), vjp_ref.cpu()) < 5e-6
-        assert rel_err(vjp_again.cpu(), vjp_ref.cpu()) < 5e-6
+        # three chained 3xTF32 GEMMs against the module path (exact fp32 on the CUDA cores at these sizes)
+        assert rel_err(y.cpu(), y_ref.detach().cpu()) < 1e-5
+        assert rel_err(y2.cpu(), y_ref.detach().cpu()) < 1e-5
+        assert rel_err(vjp.cpu(), vjp_ref.cpu()) < 1e-5
+        assert rel_err(vjp_again.cpu(), vjp_ref.cpu()) < 1e-5
         return prog
     finally:
         impflow_b200.ops.set_gemm_backend('auto')

@@ -443,6 +443,18 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_gemm_strided(self, A, sAm, sAk, Bm, sBn, sBk, bias, out, ldc, M, N, K, stream):
+        na = (M - 1) * sAm + (K - 1) * sAk + 1
+        nb = (N - 1) * sBn + (K - 1) * sBk + 1
+        a = np.lib.stride_tricks.as_strided(_f32(A, na), shape=(M, K), strides=(4 * sAm, 4 * sAk))
+        b = np.lib.stride_tricks.as_strided(_f32(Bm, nb), shape=(N, K), strides=(4 * sBn, 4 * sBk))
+        c = (a @ b.T).astype(np.float32)
+        if _addr(bias) is not None:
+            c = c + _f32(bias, N)
+        _f32(out, M * ldc).reshape(M, ldc)[:, :N] = c
+        self.launches += 1
+        return 0
+
     def impflow_gemm_nt_tc(self, A_hi, A_lo, lda, B_hi, B_lo, ldb, bias, pre_out, act_out, dmul_pre, split_hi,
                            split_lo, ldc, M, N, K, act_kind, beta_sp, splitk_ws, stream):
         if K % 32 or lda % 4 or ldb % 4:

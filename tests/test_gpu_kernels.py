@@ -35,6 +35,37 @@ def test_gemm_simt(ops, M, N, K):
     ops.set_gemm_backend('auto')
 
 
+@pytest.mark.parametrize('M,N,K', [(1000, 128, 6), (1000, 128, 128), (64, 43, 77), (5, 3, 2), (300, 200, 129)])
+def test_gemm_strided_all_transposes(ops, M, N, K):
+    """CUDA-core GEMM with element strides: op(A) op(B) for all four transpose combinations, and the autograd
+    primitive built on it (first and second derivatives against torch.matmul)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = torch.randn(K, N, generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = A.double() @ B.double()
+    for ta in (False, True):
+        for tb in (False, True):
+            Ax = A.t().contiguous() if ta else A
+            Bx = B.t().contiguous() if tb else B
+            out = ops.gemm_strided(Ax, ta, Bx, tb)
+            assert rel_err(out.cpu(), ref.cpu()) < 2e-6, (ta, tb)
+    out = ops.gemm_strided(A, False, B.t().contiguous(), True, bias)
+    assert rel_err(out.cpu(), (ref + bias.double()).cpu()) < 2e-6
+    # autograd: d/dA and d/dB of <C, R>, and a second derivative through them
+    Ar, Br = A.clone().requires_grad_(True), B.t().contiguous().clone().requires_grad_(True)
+    R = torch.randn(M, N, generator=g).cuda()
+    C = ops.linear(Ar, Br, bias)
+    gA, gB = torch.autograd.grad((C * R).sum(), [Ar, Br], create_graph=True)
+    At, Bt = A.clone().double().requires_grad_(True), B.t().contiguous().clone().double().requires_grad_(True)
+    Ct = At @ Bt.t() + bias.double()
+    gAt, gBt = torch.autograd.grad((Ct * R.double()).sum(), [At, Bt], create_graph=True)
+    assert rel_err(gA.detach().cpu(), gAt.detach().cpu()) < 2e-6 and rel_err(gB.detach().cpu(), gBt.detach().cpu()) < 2e-6
+    (hA,) = torch.autograd.grad((gB * gB).sum(), Ar)
+    (hAt,) = torch.autograd.grad((gBt * gBt).sum(), At)
+    assert rel_err(hA.cpu(), hAt.cpu()) < 5e-6
+
+
 @pytest.mark.parametrize('M,N,K', [(128, 128, 32), (256, 512, 512), (1000, 128, 128), (4096, 512, 512),
                                    (130, 27, 64), (777, 108, 512), (2048, 432, 96), (128, 16, 32), (65536, 512, 32)])
 def test_gemm_tcgen05_3xtf32(ops, M, N, K):
