@@ -384,6 +384,8 @@ def main():
     implicit_block.FUSED['on'] = not args.unfused
     if os.environ.get('IMPFLOW_TMA_STORE', '') == '0':       # A/B: per-thread stores instead of bulk tensor stores
         pkg._cabi.load().impflow_gemm_tc_set_tma_store(0)
+    if os.environ.get('IMPFLOW_PAIR', '') == '0':            # A/B: single-CTA GEMM tiles only (no cta_group::2)
+        pkg._cabi.load().impflow_gemm_tc_set_pair(0)
 
     torch.manual_seed(0)
     np.random.seed(0)

@@ -28,26 +28,74 @@ struct TcEpilogue {
   float* split_lo;
 };
 
-template <int BN>
+// PAIR: two CTAs of a cluster (one TPC) work on one 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA
+// stages its own 128 rows of A and HALF of the B tile, so the operand bytes a CTA pulls through L2 per MMA
+// drop from 96 KB to 64 KB per K chunk (BN = 256): the single-CTA kernel is bound by exactly that stream.
+template <int BN, bool PAIR = false>
 struct TcCfg {
-  static constexpr int kStages = (BN >= 256) ? 2 : (BN >= 128) ? 3 : 4;
+  static constexpr int kStages = PAIR ? 3 : (BN >= 256) ? 2 : (BN >= 128) ? 3 : 4;
   static constexpr int kABytes = TC_BM * TC_BK * 4;  // 16 KB per plane
-  static constexpr int kBBytes = BN * TC_BK * 4;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;  // B rows this CTA stages
+  static constexpr int kBBytes = kBRows * TC_BK * 4;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kTxBytes = PAIR ? 2 * kStageBytes : kStageBytes;   // bytes landing per stage, both CTAs
+  static constexpr int kTileM = PAIR ? 2 * TC_BM : TC_BM;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStagingBytes = TC_EPI_WARPS * 4096;   // one 32x32 fp32 tile per epilogue warp (TMA stores)
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's CTA 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of a pair; the bytes are counted on CTA 0's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
+
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
            const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
            const __grid_constant__ CUtensorMap mapPre, const __grid_constant__ CUtensorMap mapAct,
            const __grid_constant__ CUtensorMap mapShi, const __grid_constant__ CUtensorMap mapSlo, int tma_store,
            long long M, int N, int K, TcEpilogue ep, int splits, float* __restrict__ splitk_ws) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;        // 1024-byte aligned 4 KB tiles, one per epilogue warp
@@ -61,8 +109,12 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = K / TC_BK;
-  const long long m_tiles = (M + TC_BM - 1) / TC_BM;
+  const long long m_tiles = (M + Cfg::kTileM - 1) / Cfg::kTileM;
   const int n_tiles = (N + BN - 1) / BN;
+  // a work stream is one CTA, or one CTA pair (both CTAs walk the same tile sequence)
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const long long stream0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const long long n_streams = PAIR ? (gridDim.x >> 1) : gridDim.x;
   // split-K (weight-gradient shapes: small M x N, K = all pixels): work item = (tile, k-slice);
   // raw partial accumulators go to splitk_ws[slice][M][N] and k_splitk_reduce finishes the job.
   const long long num_tiles = m_tiles * n_tiles * splits;
@@ -81,18 +133,26 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], TC_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tempty[s], PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)Cfg::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {   // the same warp of both CTAs allocates the pair's columns
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)Cfg::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)Cfg::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -101,20 +161,41 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (long long tile = stream0; tile < num_tiles; tile += n_streams) {
         const long long mn = tile / splits;
         const int ks = (int)(tile % splits);
-        const int m_idx = (int)(mn / n_tiles) * TC_BM;
-        const int n_idx = (int)(mn % n_tiles) * BN;
+        const int m_idx = (int)(mn / n_tiles) * Cfg::kTileM + (int)cta_rank * TC_BM;
+        const int n_idx = (int)(mn % n_tiles) * BN + (int)cta_rank * (PAIR ? Cfg::kBRows : 0);
         const int kb_end = min(num_kb, (ks + 1) * kb_per);
         for (int kb = ks * kb_per; kb < kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          tma_load_2d(&mapAhi, &full[stage], st, kb * TC_BK, m_idx);
-          tma_load_2d(&mapAlo, &full[stage], st + Cfg::kABytes, kb * TC_BK, m_idx);
-          tma_load_2d(&mapBhi, &full[stage], st + 2 * Cfg::kABytes, kb * TC_BK, n_idx);
-          tma_load_2d(&mapBlo, &full[stage], st + 2 * Cfg::kABytes + Cfg::kBBytes, kb * TC_BK, n_idx);
+          if (PAIR) {
+            // CTA 0's barrier counts the bytes of both CTAs (the peer's may land before the expect: the
+            // phase cannot complete without CTA 0's own arrival)
+            if (cta_rank == 0) mbar_expect_tx(&full[stage], Cfg::kTxBytes);
+            tma_load_2d_pair(&mapAhi, &full[stage], st, kb * TC_BK, m_idx);
+            tma_load_2d_pair(&mapAlo, &full[stage], st + Cfg::kABytes, kb * TC_BK, m_idx);
+            tma_load_2d_pair(&mapBhi, &full[stage], st + 2 * Cfg::kABytes, kb * TC_BK, n_idx);
+            tma_load_2d_pair(&mapBlo, &full[stage], st + 2 * Cfg::kABytes + Cfg::kBBytes, kb * TC_BK, n_idx);
+          } else {
+            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+            tma_load_2d(&mapAhi, &full[stage], st, kb * TC_BK, m_idx);
+            tma_load_2d(&mapAlo, &full[stage], st + Cfg::kABytes, kb * TC_BK, m_idx);
+            tma_load_2d(&mapBhi, &full[stage], st + 2 * Cfg::kABytes, kb * TC_BK, n_idx);
+            tma_load_2d(&mapBlo, &full[stage], st + 2 * Cfg::kABytes + Cfg::kBBytes, kb * TC_BK, n_idx);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      if (PAIR) {
+        // tail: every stage released (CTA 0's commits also arrive on the peer's barriers — nobody may exit
+        // while such an arrive is in flight)
+        for (int i = 0; i < Cfg::kStages; ++i) {
+          mbar_wait(&empty[stage], phase ^ 1);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -122,17 +203,17 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp == 1 && cta_rank == 0) {
+    // ================= MMA issuer (CTA 0 of a pair issues for both) =================
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2,
     // b=TF32 [10,13)=2, K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                           ((uint32_t)(TC_BM >> 4) << 24);
+                           ((uint32_t)(Cfg::kTileM >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (long long tile = stream0; tile < num_tiles; tile += n_streams) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
@@ -154,20 +235,32 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
             const uint64_t dal = make_kmajor_sw128_desc(a_lo + koff);
             const uint64_t dbh = make_kmajor_sw128_desc(b_hi + koff);
             const uint64_t dbl = make_kmajor_sw128_desc(b_lo + koff);
-            umma_tf32(tmem_c, dal, dbh, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
-            umma_tf32(tmem_c, dah, dbl, idesc, 1u);
-            umma_tf32(tmem_c, dah, dbh, idesc, 1u);
+            if (PAIR) {
+              umma_tf32_pair(tmem_c, dal, dbh, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
+              umma_tf32_pair(tmem_c, dah, dbl, idesc, 1u);
+              umma_tf32_pair(tmem_c, dah, dbh, idesc, 1u);
+            } else {
+              umma_tf32(tmem_c, dal, dbh, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
+              umma_tf32(tmem_c, dah, dbl, idesc, 1u);
+              umma_tf32(tmem_c, dah, dbh, idesc, 1u);
+            }
           }
         }
         __syncwarp();
-        if (elect_one()) umma_commit(&empty[stage]);  // frees the smem stage when the MMAs retire
+        if (elect_one()) {   // frees the smem stage (of both CTAs) when the MMAs retire
+          if (PAIR) umma_commit_pair(&empty[stage]);
+          else umma_commit(&empty[stage]);
+        }
         __syncwarp();
         if (++stage == Cfg::kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&tfull[acc]);  // accumulator ready for the epilogue
+      if (elect_one()) {   // accumulator ready for the epilogue
+        if (PAIR) umma_commit_pair(&tfull[acc]);
+        else umma_commit(&tfull[acc]);
+      }
       __syncwarp();
       if (++acc == 2) {
         acc = 0;
@@ -218,10 +311,11 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
           if (n0 + j < N) out[row + n0 + j] = vals[j];
       }
     };
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (long long tile = stream0; tile < num_tiles; tile += n_streams) {
       const long long mn = tile / splits;
       const int ks = (int)(tile % splits);
-      const long long m = (mn / n_tiles) * TC_BM + q * 32 + lane;
+      const long long m_cta = (mn / n_tiles) * Cfg::kTileM + (long long)cta_rank * TC_BM;   // first row of this CTA
+      const long long m = m_cta + q * 32 + lane;
       const int n_base = (int)(mn % n_tiles) * BN;
       // The act' / multiplier operand of a chunk is requested one chunk ahead (the first one before the
       // accumulator is even complete), so its global-memory latency hides behind the MMAs / the previous chunk.
@@ -255,7 +349,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
           }
           continue;
         }
-        const long long m0w = (mn / n_tiles) * TC_BM + q * 32;          // first row of this warp's chunk
+        const long long m0w = m_cta + q * 32;          // first row of this warp's chunk
         if (use_tma ? (m0w < M && n0 < N) : (m < M && n0 < N)) {
           const long long row = m * e.ldc;
           const bool full_vec = (n0 + 32 <= N) && ((e.ldc & 7) == 0);   // 32-byte aligned row chunks
@@ -317,7 +411,10 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cta0(&tempty[acc]);
+        else mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -327,11 +424,17 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)Cfg::kTmemCols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)Cfg::kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)Cfg::kTmemCols)
+                   : "memory");
   }
 }
 
@@ -361,13 +464,13 @@ static int pick_splits(long long M, int N, int K, int BN) {
   return s < 2 ? 1 : (int)s;
 }
 
-template <int BN>
+template <int BN, bool PAIR = false>
 static int launch_tc(const float* Ahi, const float* Alo, long long lda, const float* Bhi, const float* Blo,
                      long long ldb, long long M, int N, int K, const TcEpilogue& ep, int splits, float* ws,
                      cudaStream_t s) {
   CUtensorMap mAh, mAl, mBh, mBl;
   if (make_map(&mAh, Ahi, M, K, lda, TC_BM) || make_map(&mAl, Alo, M, K, lda, TC_BM) ||
-      make_map(&mBh, Bhi, N, K, ldb, BN) || make_map(&mBl, Blo, N, K, ldb, BN))
+      make_map(&mBh, Bhi, N, K, ldb, TcCfg<BN, PAIR>::kBRows) || make_map(&mBl, Blo, N, K, ldb, TcCfg<BN, PAIR>::kBRows))
     return -1;
   // outputs leave through bulk tensor stores when every output plane can be described by a tensor map
   // (16-byte aligned base and row stride); split-K partials keep the plain stores
@@ -381,17 +484,42 @@ static int launch_tc(const float* Ahi, const float* Alo, long long lda, const fl
     if (outs[i] != nullptr && make_map(&mo[i], outs[i], M, N, ep.e.ldc, 32)) return -1;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_gemm_tc3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes) !=
-        cudaSuccess) {
-      set_error("gemm_tc: cannot set %d bytes of dynamic shared memory", TcCfg<BN>::kSmemBytes);
+    if (cudaFuncSetAttribute(k_gemm_tc3<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TcCfg<BN, PAIR>::kSmemBytes) != cudaSuccess) {
+      set_error("gemm_tc: cannot set %d bytes of dynamic shared memory", TcCfg<BN, PAIR>::kSmemBytes);
       return -1;
     }
     attr_set = true;
   }
-  const long long tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN) * splits;
+  constexpr int kTileM = TcCfg<BN, PAIR>::kTileM;
+  const long long tiles = ((M + kTileM - 1) / kTileM) * ((N + BN - 1) / BN) * splits;
+  if (PAIR) {
+    // one cluster of two CTAs (a TPC's two SMs) per work stream
+    const int pairs = (int)(tiles < 74 ? tiles : 74);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TcCfg<BN, PAIR>::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_tc3<BN, PAIR>, mAh, mAl, mBh, mBl, mo[0], mo[1], mo[2], mo[3],
+                                               tma_store, M, N, K, ep, splits, ws);
+    if (err != cudaSuccess) {
+      set_error("k_gemm_tc3 (pair): launch failed: %s", cudaGetErrorString(err));
+      return -1;
+    }
+    return check_launch("k_gemm_tc3<pair>");
+  }
   const int grid = (int)(tiles < 148 ? tiles : 148);
-  k_gemm_tc3<BN><<<grid, TC_THREADS, TcCfg<BN>::kSmemBytes, s>>>(mAh, mAl, mBh, mBl, mo[0], mo[1], mo[2], mo[3], tma_store,
-                                                                  M, N, K, ep, splits, ws);
+  k_gemm_tc3<BN, PAIR><<<grid, TC_THREADS, TcCfg<BN, PAIR>::kSmemBytes, s>>>(mAh, mAl, mBh, mBl, mo[0], mo[1], mo[2], mo[3],
+                                                                              tma_store, M, N, K, ep, splits, ws);
   if (check_launch("k_gemm_tc3")) return -1;
   if (splits > 1) {
     long long blocks = (M * N + 255) / 256;
@@ -449,6 +577,26 @@ extern "C" int impflow_gemm_tc_set_wide_tiles(int on) {
   return prev;
 }
 
+static int g_pair = 1;   // A/B switch (impflow_gemm_tc_set_pair)
+// CTA pairs (cta_group::2, 256 x 256 tiles) when they finish the problem in fewer cost-weighted rounds than
+// single CTAs: a pair tile streams 64 KB per CTA and K chunk (MMA-paced), a single 128 x 256 tile 96 KB
+// (about 1.5x the MMA time at the L2 -> SM rate), a 128 x 128 tile 64 KB for half the columns.
+static bool tc_use_pair(long long M, int N) {
+  if (!g_pair || !g_wide_tiles || N < 256) return false;
+  const long long n256 = (N + 255) / 256;
+  const long long r_pair = (((M + 255) / 256) * n256 + 73) / 74;
+  const long long m_tiles = (M + TC_BM - 1) / TC_BM;
+  const long long r256 = (m_tiles * n256 + 147) / 148;
+  const long long r128 = (m_tiles * ((N + 127) / 128) + 147) / 148;
+  return r_pair * 100 < r256 * 140 && r_pair * 100 < r128 * 95;
+}
+
+extern "C" int impflow_gemm_tc_set_pair(int on) {
+  const int prev = g_pair;
+  g_pair = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" int impflow_gemm_tc_set_tma_store(int on) {
   const int prev = g_tma_store;
   g_tma_store = on ? 1 : 0;
@@ -487,6 +635,8 @@ extern "C" int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long lon
   if (splitk_ws != nullptr && act_out == nullptr && dmul_pre == nullptr && split_hi == nullptr && pre_out != nullptr)
     splits = pick_splits(M, N, K, tc_bn(N, M));
   const int bn = tc_bn(N, M);
+  if (splits == 1 && tc_use_pair(M, N))
+    return launch_tc<256, true>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, 1, splitk_ws, s);
   if (bn == 32) return launch_tc<32>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
   if (bn == 64) return launch_tc<64>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);
   if (bn == 256) return launch_tc<256>(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, ep, splits, splitk_ws, s);

@@ -203,6 +203,10 @@ int impflow_gemm_tc_set_wide_tiles(int on);
 /* Epilogue switch for A/B measurements: 1 (default) = outputs staged in shared memory and written by bulk tensor
  * (TMA) stores, 0 = per-thread 32-byte global stores.  Returns the previous setting. */
 int impflow_gemm_tc_set_tma_store(int on);
+/* CTA-pair switch for A/B measurements: 1 (default) = problems with N >= 256 that fill the 74 TPCs run on
+ * clusters of two CTAs (tcgen05.mma.cta_group::2, 256x256 tiles, each CTA stages half of the weight tile),
+ * 0 = single-CTA tiles only.  Returns the previous setting. */
+int impflow_gemm_tc_set_pair(int on);
 /* Weight-gradient contraction dW[N1,N2] = G[Mpix,N1]^T A[Mpix,N2] (K = all pixels) straight from the row-major
  * hi/lo planes: both operands are fed to tcgen05 as MN-major tiles (TMA boxes of 32 pixels x 32 channels), so
  * no transposed copies are made (replaces the autograd weight gradients of F.conv2d / F.linear,

@@ -371,6 +371,9 @@ class EmulatedLib(object):
     def impflow_gemm_tc_set_tma_store(self, on):
         return 1
 
+    def impflow_gemm_tc_set_pair(self, on):
+        return 1
+
     def impflow_gemm_tc_set_wide_tiles(self, on):
         return 1
 

@@ -108,6 +108,49 @@ def test_gemm_tcgen05_split_k(ops, M, N, K):
     ops.set_gemm_backend('auto')
 
 
+@pytest.mark.parametrize('M,N,K', [(16384, 512, 512), (16384 + 77, 432, 128), (65536, 256, 64), (20000, 512, 96),
+                                   (256 * 74 * 3 + 130, 300, 32)])
+def test_gemm_tcgen05_cta_pair(ops, M, N, K):
+    """CTA-pair tiles (tcgen05.mma.cta_group::2, 256x256 per cluster): every epilogue mode against fp64 and against
+    the single-CTA kernel, incl. ragged M (second CTA of the last pair partly / fully out of range) and ragged N."""
+    import impflow_b200
+    lib = impflow_b200._cabi.load()
+    ops.set_gemm_backend('tc')
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    P = torch.randn(M, N, generator=g).cuda()
+    beta = F.softplus(torch.tensor([0.9])).cuda()
+    ref = (A.double() @ B.double().t()).cpu()
+    bias_c = bias.double().cpu()
+
+    def run():
+        pre, act, split = ops.gemm_nt(A, B, bias, act_kind=ops.ACT_RELU, want_pre=True, want_act=True, want_split=True)
+        dm, raw, dsplit = ops.gemm_nt(A, B, None, act_kind=ops.ACT_LIPSWISH, beta_sp=beta, dmul_pre=P, want_act=True,
+                                      want_split=True)
+        torch.cuda.synchronize()
+        return [None if t is None else t.cpu() for t in (pre, act, split[0], split[1], dm, raw, dsplit[0], dsplit[1])]
+    assert lib.impflow_gemm_tc_set_pair(1) == 1
+    outs = run()
+    lib.impflow_gemm_tc_set_pair(0)
+    try:
+        outs1 = run()
+    finally:
+        lib.impflow_gemm_tc_set_pair(1)
+    pre, act, s_hi, s_lo, dm, raw = outs[:6]
+    assert rel_err(pre, ref + bias_c) < 3e-6
+    assert rel_err(act, torch.relu(ref + bias_c)) < 3e-6
+    assert rel_err(s_hi + s_lo, act) < 1e-7
+    assert rel_err(raw, ref) < 5e-6
+    for a, b in zip(outs, outs1):
+        if a is None:
+            assert b is None
+            continue
+        assert rel_err(a, b) < 1e-6
+    ops.set_gemm_backend('auto')
+
+
 def test_colsum_large(ops):
     g = torch.Generator().manual_seed(9)
     a = torch.randn(65536, 512, generator=g)
