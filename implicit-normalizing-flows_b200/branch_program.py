@@ -704,10 +704,13 @@ class BranchProgram(object):
                                                         m.coeff)
             if m.bias is not None and bbars[i] is not None:
                 by_id[id(m.bias)] = bbars[i]
-        for act, gb in zip(self._acts(), betabars):
-            if act is not None and act.module is not None and gb is not None:
-                # d/d(raw beta) = d/d softplus(beta) * sigmoid(beta)
-                by_id[id(act.module.beta)] = gb * torch.sigmoid(act.module.beta.detach())
+        # d/d(raw beta) = d/d softplus(beta) * sigmoid(beta): two multi-tensor launches for all activations
+        live = [(act.module.beta, gb) for act, gb in zip(self._acts(), betabars)
+                if act is not None and act.module is not None and gb is not None]
+        if live:
+            sig = torch._foreach_sigmoid([b.detach() for b, _ in live])
+            for (b, _), g in zip(live, torch._foreach_mul([gb for _, gb in live], sig)):
+                by_id[id(b)] = g
         return [by_id.get(id(p)) for p in self.params]
 
     @staticmethod

@@ -381,8 +381,11 @@ class imBlock(nn.Module):
             vx, vz = self._inject_probes
             return vx.to(x), vz.to(z)
         if PROBE_MODE['mode'] == 'device':
-            vx = torch.randint(0, 2, x.shape, device=x.device).to(x) * 2 - 1
-            vz = torch.randint(0, 2, z.shape, device=z.device).to(z) * 2 - 1
+            if x.shape == z.shape and x.dtype == z.dtype and x.device == z.device:
+                v = torch.randint(0, 2, (2,) + tuple(x.shape), device=x.device, dtype=x.dtype).mul_(2).sub_(1)
+                return v[0], v[1]
+            vx = torch.randint(0, 2, x.shape, device=x.device, dtype=x.dtype).mul_(2).sub_(1)
+            vz = torch.randint(0, 2, z.shape, device=z.device, dtype=z.dtype).mul_(2).sub_(1)
             return vx, vz
         # same draws as the reference (CPU generator, vareps_x before vareps_z, :297-298); the
         # +-1 values are staged in pinned memory so the upload does not synchronise the stream
@@ -543,8 +546,11 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
         grad_x, *grad_params = ctx.saved_tensors
         dL = grad_logdetgrad[0].detach()      # quirk #13: assumes a uniform upstream gradient
         with torch.no_grad():
-            grad_x = grad_x * dL
-            grad_params = tuple(None if m else gp * dL for gp, m in zip(grad_params, ctx.none_mask))
+            # one multi-tensor launch for the whole list instead of one small kernel per parameter
+            live = [grad_x] + [gp for gp, m in zip(grad_params, ctx.none_mask) if not m]
+            scaled = iter(torch._foreach_mul(live, dL.reshape(())))
+            grad_x = next(scaled)
+            grad_params = tuple(None if m else next(scaled) for m in ctx.none_mask)
         return (None, None, grad_x, None, None, None, None, None) + grad_params
 
 

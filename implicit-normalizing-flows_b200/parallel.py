@@ -52,20 +52,26 @@ class FlatGradBucket(object):
             self.views.append(v)
 
     def zero(self):
+        """Start of a step.  The .grad slots are emptied rather than pointed at the (zeroed) views: autograd then
+        keeps each parameter's gradient tensor as it arrives (no accumulate kernel per parameter) and
+        gather_strays() moves all of them into the flat buffer with one multi-tensor copy."""
         self.flat.zero_()
-        for p, v in zip(self.params, self.views):
-            if p.grad is not v:     # somebody replaced .grad (e.g. zero_grad(set_to_none=True))
-                p.grad = v
+        for p in self.params:
+            p.grad = None
 
     def gather_strays(self):
-        """Copy gradients that autograd allocated outside the bucket back into it."""
+        """Copy the gradients autograd produced outside the bucket into it (one multi-tensor launch) and point
+        every .grad at its view; parameters without a gradient keep the zeros."""
+        dst, src = [], []
         for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                v.zero_()
-                p.grad = v
-            elif p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
-                p.grad = v
+            g = p.grad
+            if g is not None and g.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(g.detach() if g.shape == v.shape else g.detach().reshape(v.shape))
+            p.grad = v
+        if dst:
+            with torch.no_grad():
+                torch._foreach_copy_(dst, src)
 
     def allreduce_mean(self, group=None):
         self.gather_strays()

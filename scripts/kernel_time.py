@@ -13,6 +13,8 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import impflow_b200 as pkg  # noqa: E402
 
+from impflow_b200.layers import implicit_block  # noqa: E402
+implicit_block.PROBE_MODE['mode'] = os.environ.get('PROBE_MODE', 'device')     # what bench.py times
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else 'cifar']
 batch = wl['batch']
 dev = torch.device('cuda:0')
@@ -26,7 +28,7 @@ with torch.no_grad():
 model.train()
 params = [p for p in model.parameters() if p.requires_grad]
 bucket = pkg.parallel.FlatGradBucket(params)
-opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.99))
+opt = pkg.optim.FusedAdam(params, lr=1e-3, betas=(0.9, 0.99), bucket=bucket, max_grad_norm=1., ema_decay=0.999)
 n_dims = c * h * w
 
 
@@ -37,12 +39,11 @@ def step():
     bpd = -torch.mean(logpz - dlogp - np.log(256) * n_dims) / n_dims / np.log(2)
     bpd.backward()
     bucket.allreduce_mean()
-    torch.nn.utils.clip_grad_norm_(params, 1.)
     opt.step()
     bench.update_lipschitz(pkg, model)
 
 
-for _ in range(2):
+for _ in range(4):
     step()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
@@ -63,3 +64,37 @@ T = sum(tot.values())
 print('GPU kernel time per step: %.1f ms over %d kernels' % (T / 1e3, sum(cnt.values())))
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:25]:
     print('%9.0f us %5.1f%% n=%5d avg=%8.1f  %s' % (v, 100 * v / T, cnt[k], v / cnt[k], k))
+# GPU busy time = union of the kernel intervals over all streams; idle = first start .. last end minus busy
+iv = sorted((ev.time_range.start, ev.time_range.end, ev.name.split('(')[0][:50]) for ev in prof.events()
+            if ev.device_type == torch.autograd.DeviceType.CUDA)
+busy, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
+gaps = []
+late = collections.defaultdict(float)      # idle time by the kernel that ends the gap ("who was late")
+late_n = collections.Counter()
+prev_name = iv[0][2]
+after = collections.defaultdict(float)     # ... and by the kernel that ran before the gap
+for s, e, nm in iv[1:]:
+    if s > cur_e:
+        busy += cur_e - cur_s
+        gaps.append(s - cur_e)
+        late[nm] += s - cur_e
+        late_n[nm] += 1
+        after[prev_name] += s - cur_e
+        cur_s, cur_e = s, e
+        prev_name = nm
+    else:
+        if e > cur_e:
+            prev_name = nm
+        cur_e = max(cur_e, e)
+busy += cur_e - cur_s
+span = iv[-1][1] - iv[0][0]
+gaps = np.array(gaps) if gaps else np.zeros(1)
+print('GPU span %.1f ms, busy (union) %.1f ms, idle %.1f ms in %d gaps (median gap %.1f us, gaps > 20 us: %d totalling %.1f ms)' % (
+    span / 1e3, busy / 1e3, (span - busy) / 1e3, len(gaps), float(np.median(gaps)), int((gaps > 20).sum()),
+    float(gaps[gaps > 20].sum()) / 1e3))
+print('idle time by the kernel that follows the gap:')
+for k, v in sorted(late.items(), key=lambda kv: -kv[1])[:16]:
+    print('   %8.0f us in %4d gaps (avg %6.1f us) before %s' % (v, late_n[k], v / late_n[k], k))
+print('idle time by the kernel that precedes the gap:')
+for k, v in sorted(after.items(), key=lambda kv: -kv[1])[:10]:
+    print('   %8.0f us after %s' % (v, k))

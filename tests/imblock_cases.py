@@ -368,7 +368,7 @@ def case_fused_adam_matches_reference_step():
         grads = [torch.randn(*s) * (3.0 if t % 2 else 0.01) for s in shapes]     # clipped and unclipped steps
         bucket.zero()
         for p, g in zip(params, grads):
-            p.grad.copy_(g.to(dev))
+            p.grad = g.to(dev)       # outside the bucket, as autograd leaves them: step() gathers
         opt.step()
         orc.clip_adam_ema_step(ref_p, [g.clone() for g in grads], ref_m, ref_v, t, 1e-2, (0.9, 0.99), 1e-8, 1.0, ref_e,
                                0.9)
