@@ -37,6 +37,9 @@ SIGNATURES = {
     'impflow_neumann_act_bwd': (_i, [_c_fp] * 9 + [_ll, _i, _c_fp, _c_fp]),
     'impflow_lincomb3': (_i, [_c_fp, _f, _c_fp, _f, _c_fp, _f, _c_fp, _ll, _c_fp]),
     'impflow_clip_adam_ema': (_i, [_c_fp] * 5 + [_ll, _c_fp, _f, _f, _f, _f, _f, _f, _c_fp]),
+    'impflow_actnorm_forward': (_i, [_c_fp] * 6 + [_ll, _i, _ll, _i, _c_fp]),
+    'impflow_actnorm_workspace_floats': (ctypes.c_size_t, [_i]),
+    'impflow_actnorm_backward': (_i, [_c_fp] * 8 + [_ll, _i, _ll, _i, _c_fp]),
     'impflow_rowdot': (_i, [_c_fp, _c_fp, _c_fp, _i, _ll, _f, _f, _c_fp]),
     'impflow_colsum_chunks': (_i, [_ll, _i]),
     'impflow_colsum': (_i, [_c_fp, _c_fp, _c_fp, _ll, _i, _c_fp]),
@@ -67,6 +70,7 @@ SIGNATURES = {
                                   _c_fp]),
     'impflow_sn_scale': (_i, [_c_fp, _c_fp, _f, _c_fp, _c_fp, _ll, _c_fp]),
     'impflow_sn_scale_grad': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _f, _c_fp, _ll, _c_fp]),
+    'impflow_sn_scale_grad_layout': (_i, [_c_fp, _ll, _c_fp, _c_fp, _c_fp, _f, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
     'impflow_sn_conv_workspace_floats': (ctypes.c_size_t, [_i, _i, _i, _i]),
     'impflow_sn_power_iter_conv3x3': (_i, [_c_fp] * 5 + [_i, _i, _i, _i, _i, _f, _f, _c_fp, _c_fp, _c_fp]),
     'impflow_sn_power_iter': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _i, _i, _i, _f, _f, _c_fp]),

@@ -51,6 +51,7 @@ CONV3_NATIVE = {'on': True}
 
 # One-pass activation step of the Neumann reverse sweep (csrc/elementwise.cu: k_neumann_act_bwd); off = act_second +
 # two act_beta_grad + colsum + split.
+FUSED_SN_GRAD = {'on': True}     # weight-layout gradient + spectral chain in one C call
 NEUMANN_FUSED = {'on': True}
 
 # The same branch is evaluated at the same point several times per step (nnet_x(x) for x_embed, for the
@@ -204,9 +205,14 @@ class BranchProgram(object):
             return self._weights
         ws = []
         with torch.no_grad():
-            for act in self._acts():
-                if act is not None:
-                    act.refresh()
+            # softplus(beta) of every LipSwish of the branch in one launch (views of one small tensor)
+            swish = [a for a in self._acts() if a is not None and a.kind == ops.ACT_LIPSWISH]
+            if len(swish) > 1:
+                sp = F.softplus(torch.cat([a.module.beta.detach().reshape(1) for a in swish]))
+                for i, a in enumerate(swish):
+                    a._beta = sp[i:i + 1]
+            elif swish:
+                swish[0].refresh()
             for act, m in self.stages:
                 w = _Weights()
                 if isinstance(m, InducedNormConv2d) and not m.is_initialized() and meta is not None:
@@ -699,9 +705,16 @@ class BranchProgram(object):
         by_id = {}
         for i, (act, m) in enumerate(self.stages):
             if wbars[i] is not None:
-                g_eff = self._to_weight_layout(ws[i], wbars[i]).reshape(m.weight.shape).contiguous()
-                by_id[id(m.weight)] = ops.sn_scale_grad(g_eff, m.weight.detach(), m.sigma_gradient(), ws[i].sigma,
-                                                        m.coeff)
+                w, Wbar = ws[i], wbars[i]
+                W = m.weight.detach()
+                D = m.sigma_gradient()
+                if FUSED_SN_GRAD['on'] and Wbar.dim() == 2 and Wbar.stride(1) == 1 and W.is_contiguous() \
+                        and D.is_contiguous() and D.shape == W.shape:
+                    kind = 0 if w.kind == 'mm' else (1 if w.a_type else 2)
+                    by_id[id(m.weight)] = ops.sn_scale_grad_layout(Wbar, kind, w.cout, w.cin, W, D, w.sigma, m.coeff)
+                else:
+                    g_eff = self._to_weight_layout(w, Wbar).reshape(m.weight.shape).contiguous()
+                    by_id[id(m.weight)] = ops.sn_scale_grad(g_eff, W, D, w.sigma, m.coeff)
             if m.bias is not None and bbars[i] is not None:
                 by_id[id(m.bias)] = bbars[i]
         # d/d(raw beta) = d/d softplus(beta) * sigmoid(beta): two multi-tensor launches for all activations

@@ -450,6 +450,97 @@ k_clip_adam_ema(float* __restrict__ p, float* __restrict__ g, float* __restrict_
 
 }  // namespace impflow
 
+namespace impflow {
+
+// ---- ActNorm (act_norm.py:39-62): y = (x + bias_c) exp(w_c), logpx' = logpx - HW sum_c w_c ------------------------
+// x is (B, C, HW) contiguous (HW = 1 for ActNorm1d) or, channels_last, (B, HW, C) — the memory order the branch
+// kernels leave their outputs in.  One launch forward; the backward is a per-(channel, slice)
+// pass that writes gx and the partial sums of gbias / gweight, and a per-channel finish in fixed order.
+constexpr int kActNormSlices = 32;
+
+__global__ void __launch_bounds__(256)
+k_actnorm_fwd(const float* __restrict__ x, const float* __restrict__ bias, const float* __restrict__ w,
+              float* __restrict__ y, const float* __restrict__ logpx, float* __restrict__ logpx_out, long long B, int C,
+              long long HW, int channels_last) {
+  const long long n = B * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = channels_last ? (int)(i % C) : (int)((i / HW) % C);
+    y[i] = (x[i] + __ldg(bias + c)) * expf(__ldg(w + c));
+  }
+  if (logpx_out != nullptr && blockIdx.x == 0) {
+    __shared__ float ld;
+    if (threadIdx.x == 0) {
+      float sacc = 0.f;
+      for (int c = 0; c < C; ++c) sacc += w[c];          // fixed order
+      ld = sacc * (float)HW;
+    }
+    __syncthreads();
+    for (long long b = threadIdx.x; b < B; b += blockDim.x) logpx_out[b] = logpx[b] - ld;
+  }
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// grid (kActNormSlices, C): slice of the B*HW positions of channel c
+__global__ void __launch_bounds__(256)
+k_actnorm_bwd_partial(const float* __restrict__ gy, const float* __restrict__ y, const float* __restrict__ w,
+                      float* __restrict__ gx, float* __restrict__ partial, long long B, int C, long long HW,
+                      int channels_last) {
+  __shared__ float red[256];
+  const int c = blockIdx.y;
+  const float e = expf(__ldg(w + c));
+  const long long per = B * HW;
+  const long long chunk = (per + kActNormSlices - 1) / kActNormSlices;
+  const long long j0 = blockIdx.x * chunk, j1 = min(per, j0 + chunk);
+  float sb = 0.f, sw = 0.f;
+  for (long long j = j0 + threadIdx.x; j < j1; j += 256) {
+    const long long i = channels_last ? j * C + c : ((j / HW) * C + c) * HW + (j % HW);
+    const float g = gy[i];
+    gx[i] = g * e;
+    sb = fmaf(g, e, sb);
+    sw = fmaf(g, y[i], sw);
+  }
+  sb = block_sum_256(sb, red);
+  sw = block_sum_256(sw, red);
+  if (threadIdx.x == 0) {
+    partial[((long long)c * kActNormSlices + blockIdx.x) * 2] = sb;
+    partial[((long long)c * kActNormSlices + blockIdx.x) * 2 + 1] = sw;
+  }
+}
+
+// one block per channel: gbias_c, gweight_c = sum gy*y - HW * sum_b g_logpx[b]
+__global__ void __launch_bounds__(256)
+k_actnorm_bwd_finish(const float* __restrict__ partial, const float* __restrict__ g_logpx, float* __restrict__ gbias,
+                     float* __restrict__ gw, long long B, long long HW) {
+  __shared__ float red[256];
+  const int c = blockIdx.x;
+  float gl = 0.f;
+  if (g_logpx != nullptr)
+    for (long long b = threadIdx.x; b < B; b += 256) gl += g_logpx[b];
+  gl = block_sum_256(gl, red);
+  if (threadIdx.x == 0) {
+    float sb = 0.f, sw = 0.f;
+    for (int s = 0; s < kActNormSlices; ++s) {
+      sb += partial[((long long)c * kActNormSlices + s) * 2];
+      sw += partial[((long long)c * kActNormSlices + s) * 2 + 1];
+    }
+    gbias[c] = sb;
+    gw[c] = sw - (float)HW * gl;
+  }
+}
+
+}  // namespace impflow
+
 using namespace impflow;
 
 extern "C" int impflow_clip_adam_ema(float* p, float* g, float* m, float* v, float* ema, long long n,
@@ -459,6 +550,31 @@ extern "C" int impflow_clip_adam_ema(float* p, float* g, float* m, float* v, flo
   k_clip_adam_ema<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, gnorm_sq, max_norm, step_size,
                                                                      beta1, beta2, eps, ema_decay);
   return check_launch("k_clip_adam_ema");
+}
+
+extern "C" int impflow_actnorm_forward(const float* x, const float* bias, const float* weight, float* y,
+                                       const float* logpx, float* logpx_out, long long B, int C, long long HW,
+                                       int channels_last, void* stream) {
+  IMPFLOW_REQUIRE(B >= 1 && C >= 1 && HW >= 1, "actnorm_forward: empty input");
+  IMPFLOW_REQUIRE((logpx == nullptr) == (logpx_out == nullptr), "actnorm_forward: logpx and logpx_out come together");
+  k_actnorm_fwd<<<grid_for(B * C * HW, 256), 256, 0, (cudaStream_t)stream>>>(x, bias, weight, y, logpx, logpx_out, B, C,
+                                                                             HW, channels_last);
+  return check_launch("k_actnorm_fwd");
+}
+
+extern "C" size_t impflow_actnorm_workspace_floats(int C) { return (size_t)C * kActNormSlices * 2; }
+
+extern "C" int impflow_actnorm_backward(const float* gy, const float* y, const float* weight, const float* g_logpx,
+                                        float* gx, float* gbias, float* gweight, float* ws, long long B, int C,
+                                        long long HW, int channels_last, void* stream) {
+  IMPFLOW_REQUIRE(B >= 1 && C >= 1 && HW >= 1, "actnorm_backward: empty input");
+  IMPFLOW_REQUIRE(C <= 65535, "actnorm_backward: C=%d too large", C);
+  IMPFLOW_REQUIRE(ws != nullptr, "actnorm_backward: workspace missing");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_actnorm_bwd_partial<<<dim3(kActNormSlices, C), 256, 0, s>>>(gy, y, weight, gx, ws, B, C, HW, channels_last);
+  if (check_launch("k_actnorm_bwd_partial")) return -1;
+  k_actnorm_bwd_finish<<<C, 256, 0, s>>>(ws, g_logpx, gbias, gweight, B, HW);
+  return check_launch("k_actnorm_bwd_finish");
 }
 
 extern "C" int impflow_version(void) { return IMPFLOW_ABI_VERSION; }

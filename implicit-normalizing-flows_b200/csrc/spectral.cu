@@ -142,6 +142,52 @@ k_sn_scale_grad(const float* __restrict__ G, const float* __restrict__ D, const 
     out[i] = s * G[i] + c2 * D[i];
 }
 
+// ---- gradient of the effective weight, straight from the GEMM-layout weight gradient --------------------------
+// The weight-gradient GEMMs produce dL/dW_eff in the layout the forward GEMM consumes (k_prep_weights, fwd side);
+// the chain through the soft rescale needs t = <G, W> first.  Two launches (partial dots, then the combination)
+// read the GEMM layout through the index map below instead of materialising flip / permute / contiguous copies.
+__device__ __forceinline__ long long wbar_index(int kind, int cout, int cin, long long ldw, long long i) {
+  if (kind == 0) return (i / cin) * ldw + (i % cin);
+  const int co = (int)(i / (cin * 9)), r = (int)(i % (cin * 9)), ci = r / 9, t = r % 9;
+  if (kind == 1) return (long long)co * ldw + t * cin + ci;          // fwd[co][(ky,kx,ci)]
+  return ((long long)(8 - t) * cout + co) * ldw + ci;                // fwd[(2-ky,2-kx,co)][ci]
+}
+__global__ void __launch_bounds__(256)
+k_sn_grad_dot(const float* __restrict__ Wbar, long long ldw, const float* __restrict__ W, int kind, int cout, int cin,
+              long long n, float* __restrict__ partial) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc = fmaf(Wbar[wbar_index(kind, cout, cin, ldw, i)], W[i], acc);
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(256)
+k_sn_scale_grad_layout(const float* __restrict__ Wbar, long long ldw, const float* __restrict__ D,
+                       const float* __restrict__ sigma, const float* __restrict__ partial, int n_partial, float coeff,
+                       int kind, int cout, int cin, long long n, float* __restrict__ out) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < n_partial; j += 256) acc += partial[j];     // same order in every block
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const float sg = __ldg(sigma);
+  const float ratio = sg / coeff;
+  const float sc = ratio > 1.f ? 1.f / ratio : 1.f;
+  const float c2 = (ratio > 1.f ? -coeff / (sg * sg) : 0.f) * red[0];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = sc * Wbar[wbar_index(kind, cout, cin, ldw, i)] + c2 * D[i];
+}
+
 // Effective weight of one layer in every layout the branch kernels consume, in ONE launch: the soft spectral
 // rescale W / max(1, sigma/coeff) (mixed_lipschitz.py:128-131), the GEMM re-layouts of both directions
 // (K zero-padded) and their tf32 hi/lo planes.  Replaces ~12 permute / pad / split launches per layer and step.
@@ -222,6 +268,21 @@ extern "C" int impflow_sn_scale_grad(const float* G, const float* D, const float
   if (blocks > 148 * 4) blocks = 148 * 4;
   k_sn_scale_grad<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(G, D, sigma, gw_dot, coeff, out, n);
   return check_launch("k_sn_scale_grad");
+}
+
+extern "C" int impflow_sn_scale_grad_layout(const float* Wbar, long long ldw, const float* W, const float* D,
+                                            const float* sigma, float coeff, int kind, int cout, int cin, float* out,
+                                            float* ws, void* stream) {
+  IMPFLOW_REQUIRE(kind >= 0 && kind <= 2 && cout >= 1 && cin >= 1, "sn_scale_grad_layout: bad layer description");
+  IMPFLOW_REQUIRE(ws != nullptr, "sn_scale_grad_layout: workspace of 1024 floats missing");
+  const long long n = (long long)cout * cin * (kind == 0 ? 1 : 9);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  k_sn_grad_dot<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(Wbar, ldw, W, kind, cout, cin, n, ws);
+  if (check_launch("k_sn_grad_dot")) return -1;
+  k_sn_scale_grad_layout<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(Wbar, ldw, D, sigma, ws, (int)blocks, coeff, kind,
+                                                                        cout, cin, n, out);
+  return check_launch("k_sn_scale_grad_layout");
 }
 
 extern "C" int impflow_sn_power_iter(const float* W, float* u, float* v, float* sigma, int* iters, int out_f,

@@ -1,13 +1,18 @@
 """Elementwise invertible layers chained around imBlock: ActNorm1d/2d (act_norm.py:9-79),
 SqueezeLayer (squeeze.py:7-45), LogitTransform (elemwise.py:58-88).
 
-These are the "next" rows of SURVEY.md §8(f): plain PyTorch tensor expressions on the GPU for
-now (glue either side of the hot path), kept API- and state-dict-compatible."""
+These are the "next" rows of SURVEY.md §8(f), kept API- and state-dict-compatible.  ActNorm's training forward
+and backward run as fused kernels through the C ABI (ops.actnorm); its data-dependent init, the inverses, Squeeze
+(a pure permutation) and the one-off LogitTransform are plain tensor expressions on the GPU."""
 import math
 
 import torch
 import torch.nn as nn
 from torch.nn import Parameter
+
+from .. import ops
+
+FUSED_ACTNORM = {'on': True}     # A/B switch: fused kernels against the plain tensor expressions
 
 __all__ = ['ActNorm1d', 'ActNorm2d', 'SqueezeLayer', 'LogitTransform']
 
@@ -48,6 +53,11 @@ class ActNormNd(nn.Module):
 
     def forward(self, x, logpx=None, restore=None):
         self._maybe_init(x)
+        if FUSED_ACTNORM['on'] and x.dtype == torch.float32 and (
+                logpx is None or (torch.is_tensor(logpx) and logpx.dtype == torch.float32
+                                  and logpx.numel() == x.size(0))):
+            # one kernel forward (y and the log-density update), one C call backward (csrc/elementwise.cu)
+            return ops.actnorm(x, self.bias, self.weight, logpx)
         y = (x + self.bias.view(*self.shape)) * torch.exp(self.weight.view(*self.shape))
         if logpx is None:
             return y

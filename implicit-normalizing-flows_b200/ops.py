@@ -584,6 +584,80 @@ def sn_scale_grad(G, W, D, sigma, coeff):
     return out
 
 
+def sn_scale_grad_layout(Wbar, kind, cout, cin, W, D, sigma, coeff):
+    """sn_scale_grad reading dL/dW_eff from the GEMM layout of the weight-gradient kernels (kind 0 / 1 / 2 as in
+    prep_weights, rows may be longer than the payload) and returning the module's weight layout; two launches
+    from one C call instead of flip / permute / contiguous / dot / scale."""
+    assert Wbar.stride(-1) == 1 and W.is_contiguous() and D.is_contiguous()
+    out = torch.empty_like(W)
+    ws = torch.empty(1024, device=W.device, dtype=torch.float32)
+    _cabi.check(_lib().impflow_sn_scale_grad_layout(_cabi.ptr(Wbar), Wbar.stride(0), _cabi.ptr(W), _cabi.ptr(D),
+                                                    _cabi.ptr(sigma), float(coeff), kind, cout, cin, _cabi.ptr(out),
+                                                    _cabi.ptr(ws), _cabi.stream()), 'sn_scale_grad_layout')
+    return out
+
+
+def _dense_layout(x):
+    """0 = (B, C, ...) contiguous, 1 = channels-last dense (the memory order of the rows-space kernels), None = other."""
+    if x.is_contiguous():
+        return 0
+    if x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous():
+        return 1
+    return None
+
+
+class _ActNorm(torch.autograd.Function):
+    """y = (x + bias_c) exp(weight_c), logpx' = logpx - HW sum(weight): one launch forward, one C call backward
+    (act_norm.py:39-62).  Keeps the input's memory order (NCHW or channels-last)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, weight, logpx):
+        cl = _dense_layout(x)
+        if cl is None:
+            x, cl = x.contiguous(), 0
+        B, C = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * C)
+        y = torch.empty_like(x)          # same strides
+        out_lp = None
+        if logpx is not None:
+            logpx = logpx.contiguous()
+            assert logpx.numel() == B and logpx.dtype == torch.float32, 'actnorm: logpx must hold one float per sample'
+            out_lp = torch.empty_like(logpx)
+        _cabi.check(_lib().impflow_actnorm_forward(_cabi.ptr(x), _cabi.ptr(bias), _cabi.ptr(weight), _cabi.ptr(y),
+                                                   _cabi.ptr(logpx, 'logpx', True), _cabi.ptr(out_lp, 'logpx_out', True),
+                                                   B, C, HW, cl, _cabi.stream()), 'actnorm_forward')
+        ctx.save_for_backward(y, weight)
+        ctx.dims = (B, C, HW, cl)
+        if logpx is None:
+            return y
+        return y, out_lp
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy, g_lp=None):
+        y, weight = ctx.saved_tensors
+        B, C, HW, cl = ctx.dims
+        if gy is None:
+            gy = torch.zeros_like(y)
+        elif gy.stride() != y.stride():
+            gy = torch.empty_like(y).copy_(gy)
+        g_lp = g_lp.contiguous() if g_lp is not None else None
+        gx = torch.empty_like(y)
+        gb, gw = torch.empty_like(weight), torch.empty_like(weight)
+        lib = _lib()
+        ws = torch.empty(int(lib.impflow_actnorm_workspace_floats(C)), device=y.device, dtype=torch.float32)
+        _cabi.check(lib.impflow_actnorm_backward(_cabi.ptr(gy), _cabi.ptr(y), _cabi.ptr(weight),
+                                                 _cabi.ptr(g_lp, 'g_logpx', True), _cabi.ptr(gx), _cabi.ptr(gb),
+                                                 _cabi.ptr(gw), _cabi.ptr(ws), B, C, HW, cl, _cabi.stream()),
+                    'actnorm_backward')
+        return gx, gb, gw, g_lp
+
+
+def actnorm(x, bias, weight, logpx=None):
+    """Fused ActNorm forward (+ log-density update) with its hand-written backward."""
+    return _ActNorm.apply(x, bias, weight, logpx)
+
+
 # ------------------------------------------------------------------------------------------
 # differentiable primitives (closed under differentiation)
 # ------------------------------------------------------------------------------------------

@@ -166,6 +166,20 @@ int impflow_clip_adam_ema(float* p, float* g, float* m, float* v, float* ema, lo
                           float max_norm, float step_size, float beta1, float beta2, float eps, float ema_decay,
                           void* stream);
 
+/* ActNorm1d / ActNorm2d (lib/layers/act_norm.py:39-62), the layer in front of every imBlock
+ * (implicit_flow.py:411-428).  x, y, gy, gx: (B, C, HW) contiguous (HW = 1 for the 1d
+ * case) or, with channels_last = 1, (B, HW, C) — the order the branch kernels leave their outputs in.
+ *   forward : y = (x + bias_c) * exp(weight_c);  logpx_out[b] = logpx[b] - HW * sum_c weight_c  (both NULL: y only)
+ *   backward: gx = gy * exp(weight_c);  gbias_c = sum gy * exp(weight_c);
+ *             gweight_c = sum gy * y - HW * sum_b g_logpx[b]   (g_logpx may be NULL); fixed-order reductions.
+ * ws: impflow_actnorm_workspace_floats(C) floats. */
+int impflow_actnorm_forward(const float* x, const float* bias, const float* weight, float* y, const float* logpx,
+                            float* logpx_out, long long B, int C, long long HW, int channels_last, void* stream);
+size_t impflow_actnorm_workspace_floats(int C);
+int impflow_actnorm_backward(const float* gy, const float* y, const float* weight, const float* g_logpx, float* gx,
+                             float* gbias, float* gweight, float* ws, long long B, int C, long long HW,
+                             int channels_last, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Residual-branch contractions — replace F.linear / F.conv2d and their vjps
  * (mixed_lipschitz.py:134-136, 388-391; implicit_block.py:422,434,436).
@@ -332,6 +346,12 @@ int impflow_sn_scale(const float* W, const float* sigma, float coeff, float* out
                      void* stream);
 int impflow_sn_scale_grad(const float* G, const float* D, const float* sigma, const float* gw_dot, float coeff,
                           float* out, long long n, void* stream);
+/* Same chain, reading dL/dW_eff straight from the GEMM layout the weight-gradient kernels produce (the fwd side of
+ * impflow_prep_weights: kind 0 [cout][cin], 1 [cout][(ky,kx,cin)], 2 [(2-ky,2-kx,cout)][cin]; row stride ldw) and
+ * writing the module's weight layout [cout][cin][3][3]: replaces the flip / permute / contiguous copies and the
+ * separate <G, W> reduction (mixed_lipschitz.py:125-131 backward).  ws: 1024 floats. */
+int impflow_sn_scale_grad_layout(const float* Wbar, long long ldw, const float* W, const float* D, const float* sigma,
+                                 float coeff, int kind, int cout, int cin, float* out, float* ws, void* stream);
 
 #ifdef __cplusplus
 }

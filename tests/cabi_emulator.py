@@ -676,6 +676,61 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_sn_scale_grad_layout(self, Wbar, ldw, W, D, sigma, coeff, kind, cout, cin, out, ws, stream):
+        taps = 1 if kind == 0 else 9
+        n = cout * cin * taps
+        rows = 9 * cout if kind == 2 else cout
+        Wb = _f32(Wbar, (rows - 1) * ldw + (cin if kind != 1 else 9 * cin))
+        i = np.arange(n)
+        if kind == 0:
+            idx = (i // cin) * ldw + (i % cin)
+        else:
+            co, r = i // (cin * 9), i % (cin * 9)
+            ci, t = r // 9, r % 9
+            idx = co * ldw + t * cin + ci if kind == 1 else ((8 - t) * cout + co) * ldw + ci
+        G = Wb[idx]
+        Wv, Dv = _f32(W, n), _f32(D, n)
+        sg = float(_f32(sigma, 1)[0])
+        ratio = sg / coeff
+        s_ = 1.0 / ratio if ratio > 1 else 1.0
+        ds = -coeff / (sg * sg) if ratio > 1 else 0.0
+        t_ = float((G.astype(np.float64) * Wv).sum())
+        _f32(out, n)[:] = np.float32(s_) * G + np.float32(ds * t_) * Dv
+        self.launches += 2
+        return 0
+
+    @staticmethod
+    def _actnorm_view(ptr, B, C, HW, channels_last):
+        """(B, C, HW)-indexed numpy view of either memory order."""
+        if channels_last:
+            return _f32(ptr, B * C * HW).reshape(B, HW, C).transpose(0, 2, 1)
+        return _f32(ptr, B * C * HW).reshape(B, C, HW)
+
+    def impflow_actnorm_forward(self, x, bias, weight, y, logpx, logpx_out, B, C, HW, channels_last, stream):
+        xv = self._actnorm_view(x, B, C, HW, channels_last)
+        b, w = _f32(bias, C), _f32(weight, C)
+        self._actnorm_view(y, B, C, HW, channels_last)[:] = (xv + b[None, :, None]) * np.exp(w)[None, :, None]
+        if _addr(logpx_out) is not None:
+            _f32(logpx_out, B)[:] = _f32(logpx, B) - np.float32(w.sum() * HW)
+        self.launches += 1
+        return 0
+
+    def impflow_actnorm_workspace_floats(self, C):
+        return 64 * C
+
+    def impflow_actnorm_backward(self, gy, y, weight, g_logpx, gx, gbias, gweight, ws, B, C, HW, channels_last,
+                                 stream):
+        g = self._actnorm_view(gy, B, C, HW, channels_last)
+        yv = self._actnorm_view(y, B, C, HW, channels_last)
+        w = _f32(weight, C)
+        e = np.exp(w)
+        self._actnorm_view(gx, B, C, HW, channels_last)[:] = g * e[None, :, None]
+        _f32(gbias, C)[:] = (g.astype(np.float64) * e[None, :, None]).sum((0, 2))
+        gl = float(_f32(g_logpx, B).astype(np.float64).sum()) if _addr(g_logpx) is not None else 0.0
+        _f32(gweight, C)[:] = (g.astype(np.float64) * yv).sum((0, 2)) - HW * gl
+        self.launches += 2
+        return 0
+
     def impflow_sn_power_iter(self, W, u, v, sigma, iters, out_f, in_f, n_iterations, atol, rtol, stream):
         Wm = _f32(W, out_f * in_f).reshape(out_f, in_f)
         uv, vv = _f32(u, out_f), _f32(v, in_f)

@@ -446,3 +446,50 @@ def case_wide_conv_block_vs_oracle(width=256, c=3, hw=8, batch=2, verbose=False)
     assert res['grad_x'] < 2e-3 and res['grad_params'] < 5e-3
     assert fused > 0, 'the fused tile kernel was not used'
     return res
+
+
+def case_actnorm_fused_matches_expression():
+    """ops.actnorm (fused kernels through the C ABI) == the tensor expression of act_norm.py:39-62: y, the log-density
+    update and all four gradients, 2d and 1d, with and without logpx."""
+    pkg = _pkg()
+    from impflow_b200.layers import glue
+    dev = DEV['device']
+    torch.manual_seed(3)
+    for shape, cls, cl in [((5, 12, 16, 16), glue.ActNorm2d, False), ((64, 3, 32, 32), glue.ActNorm2d, False),
+                           ((6, 48, 8, 8), glue.ActNorm2d, True), ((37, 6), glue.ActNorm1d, False)]:
+        layer = cls(shape[1]).to(dev)
+        x0 = torch.randn(*shape, device=dev) * 2 + 0.3
+        if cl:      # channels-last memory order, as the branch kernels leave their outputs
+            x0 = x0.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        with torch.no_grad():
+            layer(x0)                                  # data-dependent init
+            layer.weight.add_(0.1 * torch.randn_like(layer.weight))
+        lp0 = torch.randn(shape[0], 1, device=dev)
+        r = torch.randn(*shape, device=dev)
+        wts = torch.arange(1, shape[0] + 1, device=dev, dtype=torch.float32).view(-1, 1)
+        for with_lp in (True, False):
+            outs = []
+            for fused in (True, False):
+                glue.FUSED_ACTNORM['on'] = fused
+                try:
+                    x = x0.clone().requires_grad_(True)
+                    lp = lp0.clone().requires_grad_(True) if with_lp else None
+                    for p in layer.parameters():
+                        p.grad = None
+                    res = layer(x, lp) if with_lp else layer(x)
+                    y, lp_out = res if with_lp else (res, None)
+                    loss = (y * r).sum()
+                    if with_lp:
+                        loss = loss + (lp_out * wts).sum()
+                    loss.backward()
+                    outs.append([y.detach(), lp_out.detach() if with_lp else None, x.grad, lp.grad if with_lp else None,
+                                 layer.bias.grad.clone(), layer.weight.grad.clone()])
+                finally:
+                    glue.FUSED_ACTNORM['on'] = True
+            a, b = outs
+            for u, v in zip(a, b):
+                if u is None:
+                    assert v is None
+                    continue
+                scale = max(float(v.abs().max()), 1e-30)
+                assert float((u - v).abs().max()) / scale < 5e-6

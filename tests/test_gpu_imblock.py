@@ -104,3 +104,7 @@ def test_saved_forward_memo_is_hit(golden, monkeypatch):
 
 def test_wide_conv_block_vs_oracle():
     cases.case_wide_conv_block_vs_oracle(verbose=True)
+
+
+def test_actnorm_fused_matches_expression():
+    cases.case_actnorm_fused_matches_expression()

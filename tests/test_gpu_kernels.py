@@ -151,6 +151,35 @@ def test_gemm_tcgen05_cta_pair(ops, M, N, K):
     ops.set_gemm_backend('auto')
 
 
+@pytest.mark.parametrize('kind,cout,cin,ld', [(0, 512, 512, 512), (0, 128, 6, 32), (1, 512, 3, 32), (1, 512, 12, 128),
+                                              (2, 12, 512, 512), (2, 48, 512, 512)])
+def test_sn_scale_grad_layout(ops, kind, cout, cin, ld):
+    """GEMM-layout weight gradient -> module layout + spectral chain in one call == permute / flip / dot / scale."""
+    g = torch.Generator().manual_seed(kind * 1000 + cout + cin)
+    rows = 9 * cout if kind == 2 else cout
+    Wbar = torch.randn(rows + (3 if kind == 2 else 0), ld, generator=g).cuda()[:rows]
+    shape = (cout, cin) if kind == 0 else (cout, cin, 3, 3)
+    W, D = torch.randn(*shape, generator=g).cuda(), torch.randn(*shape, generator=g).cuda()
+    for sg in (0.5, 2.0):          # below and above the coeff: rescale inactive / active
+        sigma = torch.tensor([sg]).cuda()
+        if kind == 0:
+            G = Wbar[:, :cin]
+        elif kind == 1:
+            G = Wbar[:, :9 * cin].reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+        else:
+            G = Wbar[:, :cin].reshape(3, 3, cout, cin).flip(0, 1).permute(2, 3, 0, 1)
+        Gc = G.reshape(shape).contiguous()
+        old = ops.sn_scale_grad(Gc, W, D, sigma, 0.9)
+        got = ops.sn_scale_grad_layout(Wbar, kind, cout, cin, W, D, sigma, 0.9)
+        assert got.shape == W.shape
+        # fp64 statement of the chain; the two kernels differ only in the summation order of <G, W>
+        ratio = sg / 0.9
+        sc, ds = (1.0 / ratio, -0.9 / (sg * sg)) if ratio > 1 else (1.0, 0.0)
+        ref = sc * Gc.double() + ds * (Gc.double() * W.double()).sum() * D.double()
+        assert rel_err(got.cpu(), ref.cpu()) < 1e-5
+        assert rel_err(old.cpu(), ref.cpu()) < 1e-5
+
+
 def test_colsum_large(ops):
     g = torch.Generator().manual_seed(9)
     a = torch.randn(65536, 512, generator=g)

@@ -262,3 +262,8 @@ def test_saved_forward_memo_is_hit(golden, monkeypatch):
 
 def test_wide_conv_block_vs_oracle():
     cases.case_wide_conv_block_vs_oracle(verbose=True)
+
+
+def test_actnorm_fused_matches_expression():
+    from tests import imblock_cases
+    imblock_cases.case_actnorm_fused_matches_expression()
