@@ -450,7 +450,10 @@ class imBlock(nn.Module):
                     _exact_trace_series(self.nnet_z(z), z, n_power_series, coeff_fn)
 
             if self.training and self.n_power_series is None:
-                self.last_n_samples.copy_(torch.tensor(n_samples).to(self.last_n_samples))
+                # pinned staging: a pageable H2D copy would wait for every kernel queued so far (a device sync
+                # per imBlock and step)
+                self.last_n_samples.copy_(_upload(torch.as_tensor(np.asarray(n_samples), dtype=torch.float32),
+                                                  self.last_n_samples))
                 estimator = logdetgrad.detach()
                 self.last_firmom.copy_(torch.mean(estimator).to(self.last_firmom))
                 self.last_secmom.copy_(torch.mean(estimator ** 2).to(self.last_secmom))
@@ -567,7 +570,7 @@ def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, pro
                 vjp = program.vjp(vjp)
                 ops.rowdot(vjp, vareps, out=out, alpha=float((-1) ** (k + 1) / k * coeff_fn(k)), beta=1.0)
         return out
-    logdetgrad = torch.tensor(0.).to(x)
+    logdetgrad = torch.zeros((), device=x.device, dtype=x.dtype)
     for k in range(1, n_power_series + 1):
         with ops.activations_only():
             vjp = torch.autograd.grad(g, x, vjp, create_graph=training, retain_graph=True)[0]

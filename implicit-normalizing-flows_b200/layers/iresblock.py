@@ -106,7 +106,8 @@ class iResBlock(nn.Module):
                 logdetgrad = ib._exact_trace_series(g, x, n_power_series, coeff_fn)
 
             if self.training and self.n_power_series is None:
-                self.last_n_samples.copy_(torch.tensor(n_samples).to(self.last_n_samples))
+                self.last_n_samples.copy_(ib._upload(torch.as_tensor(np.asarray(n_samples), dtype=torch.float32),
+                                                     self.last_n_samples))
                 estimator = logdetgrad.detach()
                 self.last_firmom.copy_(torch.mean(estimator).to(self.last_firmom))
                 self.last_secmom.copy_(torch.mean(estimator ** 2).to(self.last_secmom))

@@ -30,7 +30,7 @@ with torch.no_grad():
 model.train()
 params = [p for p in model.parameters() if p.requires_grad]
 bucket = pkg.parallel.FlatGradBucket(params)
-opt = torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.99))
+opt = pkg.optim.FusedAdam(params, lr=1e-3, betas=(0.9, 0.99), bucket=bucket, max_grad_norm=1., ema_decay=0.999)
 n_dims = c * h * w
 
 ACC = collections.OrderedDict()
@@ -89,7 +89,6 @@ def step():
     bpd = -torch.mean(logpz - dlogp - np.log(256) * n_dims) / n_dims / np.log(2)
     bpd.backward()
     bucket.allreduce_mean()
-    torch.nn.utils.clip_grad_norm_(params, 1.)
     opt.step()
     bench.update_lipschitz(pkg, model)
 
