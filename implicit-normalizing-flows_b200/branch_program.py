@@ -51,6 +51,7 @@ CONV3_NATIVE = {'on': True}
 
 # One-pass activation step of the Neumann reverse sweep (csrc/elementwise.cu: k_neumann_act_bwd); off = act_second +
 # two act_beta_grad + colsum + split.
+MLP_VJP_SOLVER = {'on': True}    # implicit backward of small MLP branches in the persistent solver kernel
 FUSED_SN_GRAD = {'on': True}     # weight-layout gradient + spectral chain in one C call
 NEUMANN_FUSED = {'on': True}
 
@@ -268,6 +269,25 @@ class BranchProgram(object):
         act = self.stages[1][0] if len(self.stages) > 1 else None
         return (cached[1], [w.bias for w in ws], dims, act.kind if act is not None else ops.ACT_NONE,
                 act.beta_sp() if act is not None else None)
+
+    def mlp_vjp_spec(self, saved):
+        """Arguments of the persistent solver's implicit-backward mode (impflow_mlp_broyden_solve_vjp) at the point
+        of `saved`, or None if the branch does not qualify (same conditions as mlp_solver_spec)."""
+        if not MLP_VJP_SOLVER['on'] or not self.is_linear or self.post_act is not None \
+                or self.stages[0][0] is not None:
+            return None
+        if any(a is None for a, _ in self.stages[1:]):
+            return None
+        ws = self._prep(saved.M)
+        dims = [ws[0].cin] + [w.cout for w in ws]
+        if dims[0] != dims[-1] or dims[0] > 128 or max(dims) > 256 or len(ws) > 8:
+            return None
+        if any(w.fwd is None or w.fwd.stride(1) != 1 for w in ws):
+            return None
+        dmul = [None] + [self._deriv(saved, i).contiguous() for i in range(1, len(ws))]
+        if any(t.shape != (saved.M, dims[i]) for i, t in enumerate(dmul) if t is not None):
+            return None
+        return [w.fwd for w in ws], [w.fwd.stride(0) for w in ws], dmul, dims
 
     # ---------------------------------------------------------------- plumbing
     def _to_rows(self, x):

@@ -30,15 +30,20 @@ constexpr int kMaxWidth = 256;   // widest layer (incl. d)
 struct MlpDesc {
   int L;                       // number of linear layers
   int dims[kMaxLayers + 1];    // dims[0] = d, ..., dims[L] = d
-  const float* Wt[kMaxLayers]; // [in][out]
+  const float* Wt[kMaxLayers]; // [in][out], row stride ld
+  int ld[kMaxLayers];
   const float* bias[kMaxLayers];
+  const float* dmul[kMaxLayers];   // vjp mode: per-sample multiplier (B, dims[l+1]) on the output of layer l, or null
   int act_kind;
   const float* beta;
+  int mode;                    // 0: g(z) = x_embed - f(z) - z (forward / inverse solve)
+                               // 1: g(v) = v^T J + v - rhs   (implicit backward; f is the transposed linear chain)
 };
 
 // out[s][n] = act?( bias[n] + sum_k in[s][k] * Wt[k][n] ) for the kTile samples of one tile.
-__device__ void mlp_layer(const float* __restrict__ Wt, const float* __restrict__ bias, const float* in, float* out,
-                          int K, int N, int act_kind, float beta, bool apply_act) {
+__device__ void mlp_layer(const float* __restrict__ Wt, int ld, const float* __restrict__ bias, const float* in,
+                          float* out, int K, int N, int act_kind, float beta, bool apply_act,
+                          const float* __restrict__ dmul, int s0, int B) {
   // thread -> (neuron n, group of 4 samples)
   for (int idx = threadIdx.x; idx < N * (kTile / 4); idx += kMlpThreads) {
     const int n = idx % N;
@@ -50,10 +55,10 @@ __device__ void mlp_layer(const float* __restrict__ Wt, const float* __restrict_
     const float* i0 = in + (sg * 4 + 0) * kMaxWidth;
     int k = 0;
     for (; k + 3 < K; k += 4) {
-      const float w0 = __ldg(Wt + (long long)(k + 0) * N + n);
-      const float w1 = __ldg(Wt + (long long)(k + 1) * N + n);
-      const float w2 = __ldg(Wt + (long long)(k + 2) * N + n);
-      const float w3 = __ldg(Wt + (long long)(k + 3) * N + n);
+      const float w0 = __ldg(Wt + (long long)(k + 0) * ld + n);
+      const float w1 = __ldg(Wt + (long long)(k + 1) * ld + n);
+      const float w2 = __ldg(Wt + (long long)(k + 2) * ld + n);
+      const float w3 = __ldg(Wt + (long long)(k + 3) * ld + n);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 h = *reinterpret_cast<const float4*>(i0 + j * kMaxWidth + k);
@@ -64,13 +69,19 @@ __device__ void mlp_layer(const float* __restrict__ Wt, const float* __restrict_
       }
     }
     for (; k < K; ++k) {
-      const float w0 = __ldg(Wt + (long long)k * N + n);
+      const float w0 = __ldg(Wt + (long long)k * ld + n);
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j] = fmaf(i0[j * kMaxWidth + k], w0, acc[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      out[(sg * 4 + j) * kMaxWidth + n] = apply_act ? act_dispatch(act_kind, acc[j], 0, beta) : acc[j];
+    for (int j = 0; j < 4; ++j) {
+      float v = apply_act ? act_dispatch(act_kind, acc[j], 0, beta) : acc[j];
+      if (dmul != nullptr) {
+        const int b = s0 + sg * 4 + j;
+        v = b < B ? v * __ldg(dmul + (long long)b * N + n) : 0.f;
+      }
+      out[(sg * 4 + j) * kMaxWidth + n] = v;
+    }
   }
 }
 
@@ -86,7 +97,8 @@ __device__ float* mlp_eval(const MlpDesc& net, const float* __restrict__ zin, in
   float* cur = bufA;
   float* nxt = bufB;
   for (int l = 0; l < net.L; ++l) {
-    mlp_layer(net.Wt[l], net.bias[l], cur, nxt, net.dims[l], net.dims[l + 1], net.act_kind, beta, l + 1 < net.L);
+    mlp_layer(net.Wt[l], net.ld[l], net.bias[l], cur, nxt, net.dims[l], net.dims[l + 1], net.act_kind, beta,
+              net.mode == 0 && l + 1 < net.L, net.dmul[l], s0, B);
     __syncthreads();
     float* t = cur;
     cur = nxt;
@@ -208,14 +220,15 @@ k_mlp_broyden(MlpDesc net, const float* __restrict__ x_embed, float* za, float* 
       float* f = mlp_eval(net, zin, s0, B, bufA, bufB, beta);
       if (tid < kTile) tile_sq[tid] = 0.f;
       __syncthreads();
-      // g = x_embed - f(z) - z, one warp handles samples warp, warp+8
+      // g = x_embed - f(z) - z (mode 0) or f(v) + v - rhs (mode 1), one warp handles samples warp, warp+8
       for (int s = warp; s < kTile; s += kMlpWarps) {
         const int b = s0 + s;
         if (b >= B) continue;
         float sq = 0.f;
         for (int c = lane; c < d; c += 32) {
           const long long i = (long long)b * d + c;
-          const float gv = x_embed[i] - f[s * kMaxWidth + c] - zin[i];
+          const float fv = f[s * kMaxWidth + c];
+          const float gv = net.mode == 0 ? x_embed[i] - fv - zin[i] : fv + zin[i] - x_embed[i];
           gout[i] = gv;
           sq += gv * gv;
         }
@@ -305,6 +318,11 @@ k_mlp_broyden(MlpDesc net, const float* __restrict__ x_embed, float* za, float* 
 
 }  // namespace impflow
 
+namespace impflow {
+int launch_mlp_solver(MlpDesc net, const float* x_embed, float* za, float* ga, float* zb, float* gb, float* low_z,
+                      float* low_g, float* Ut, float* Vt, float* sample_sq, float* low_sq, double* partial,
+                      impflow_broyden_state* state, int B, int threshold, double eps_scaled, void* stream);
+}
 using namespace impflow;
 
 extern "C" int impflow_mlp_solver_limits(int* max_layers, int* max_width, int* max_d) {
@@ -340,8 +358,54 @@ extern "C" int impflow_mlp_broyden_solve(const float* x_embed, const float* cons
     net.Wt[l] = Wt[l];
     net.bias[l] = bias ? bias[l] : nullptr;
   }
+  for (int l = 0; l < L; ++l) net.ld[l] = dims[l + 1];
   net.act_kind = act_kind;
   net.beta = beta_sp;
+  net.mode = 0;
+  return launch_mlp_solver(net, x_embed, za, ga, zb, gb, low_z, low_g, Ut, Vt, sample_sq, low_sq, partial, state, B,
+                           threshold, eps_scaled, stream);
+}
+
+/* Implicit-backward solve of v^T (I + J) = rhs for the same MLP (implicit_block.py:199-207) in the same persistent
+ * kernel: f becomes the transposed linear chain v -> (((v W_{L-1}) * D_{L-1}) W_{L-2} * D_{L-2}) ... W_0 with the
+ * saved act' multipliers D_l = act'(pre-activation in front of layer l), (B, dims[l]) each.
+ *   W[l]   : DEVICE pointer to the effective weight of layer l, [dims[l+1]][ldw[l]] (HOST array of L)
+ *   dmul[l]: DEVICE pointer to D_l or NULL (HOST array of L; dmul[0] must be NULL) */
+extern "C" int impflow_mlp_broyden_solve_vjp(const float* rhs, const float* const* W, const int* ldw,
+                                             const float* const* dmul, const int* dims, int L, float* za, float* ga,
+                                             float* zb, float* gb, float* low_z, float* low_g, float* Ut, float* Vt,
+                                             float* sample_sq, float* low_sq, double* partial,
+                                             impflow_broyden_state* state, int B, int threshold, double eps_scaled,
+                                             void* stream) {
+  IMPFLOW_REQUIRE(L >= 1 && L <= kMaxLayers, "mlp_broyden_solve_vjp: %d layers not in [1,%d]", L, kMaxLayers);
+  IMPFLOW_REQUIRE(threshold >= 1 && threshold <= 63, "mlp_broyden_solve_vjp: threshold %d not in [1,63]", threshold);
+  IMPFLOW_REQUIRE(dims[0] == dims[L] && dims[0] <= 128, "mlp_broyden_solve_vjp: needs d_in == d_out <= 128");
+  IMPFLOW_REQUIRE(dmul[0] == nullptr, "mlp_broyden_solve_vjp: no activation in front of the first layer");
+  MlpDesc net;
+  memset(&net, 0, sizeof(net));
+  net.L = L;
+  for (int l = 0; l <= L; ++l) {
+    IMPFLOW_REQUIRE(dims[l] >= 1 && dims[l] <= kMaxWidth, "mlp_broyden_solve_vjp: width %d not in [1,%d]", dims[l],
+                    kMaxWidth);
+    net.dims[l] = dims[L - l];          // the chain runs from the output side
+  }
+  for (int j = 0; j < L; ++j) {
+    const int l = L - 1 - j;            // forward layer applied transposed at step j: [out][in] is [K][N] here
+    IMPFLOW_REQUIRE(ldw[l] >= dims[l], "mlp_broyden_solve_vjp: row stride %d < %d", ldw[l], dims[l]);
+    net.Wt[j] = W[l];
+    net.ld[j] = ldw[l];
+    net.dmul[j] = dmul[l];
+  }
+  net.act_kind = IMPFLOW_ACT_NONE;
+  net.mode = 1;
+  return launch_mlp_solver(net, rhs, za, ga, zb, gb, low_z, low_g, Ut, Vt, sample_sq, low_sq, partial, state, B,
+                           threshold, eps_scaled, stream);
+}
+
+namespace impflow {
+int launch_mlp_solver(MlpDesc net, const float* x_embed, float* za, float* ga, float* zb, float* gb, float* low_z,
+                      float* low_g, float* Ut, float* Vt, float* sample_sq, float* low_sq, double* partial,
+                      impflow_broyden_state* state, int B, int threshold, double eps_scaled, void* stream) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -366,3 +430,4 @@ extern "C" int impflow_mlp_broyden_solve(const float* x_embed, const float* cons
   }
   return check_launch("k_mlp_broyden");
 }
+}  // namespace impflow

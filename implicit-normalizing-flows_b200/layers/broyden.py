@@ -11,7 +11,7 @@ import torch
 
 from .. import _cabi
 
-__all__ = ['broyden', 'broyden_mlp']
+__all__ = ['broyden_mlp_vjp', 'broyden', 'broyden_mlp']
 
 _STATE_DTYPE = np.dtype([('nstep', '<i4'), ('lowest_step', '<i4'), ('active', '<i4'), ('prot_break', '<i4'),
                          ('converged', '<i4'), ('stagnated', '<i4'), ('do_update', '<i4'), ('new_lowest', '<i4'),
@@ -102,6 +102,41 @@ def broyden_mlp(spec, x_embed, z0, threshold, eps):
         _cabi.ptr(ws.Ut), _cabi.ptr(ws.Vt), _cabi.ptr(ws.sample_sq), _cabi.ptr(ws.low_sq),
         ctypes.c_void_p(ws.partial_d.data_ptr()), ctypes.c_void_p(ws.state.data_ptr()), B, threshold,
         float(eps_scaled), _cabi.stream()), 'mlp_broyden_solve')
+    state = ws.read_state()
+    return _result_dict(ws, state, shape, eps_scaled, threshold)
+
+
+def broyden_mlp_vjp(spec, rhs, threshold, eps):
+    """Whole implicit-backward solve v^T (I + J) = rhs (implicit_block.py:199-207) from zeros in ONE persistent
+    cooperative kernel for small-d MLP branches.  `spec` comes from BranchProgram.mlp_vjp_spec(saved):
+    (effective weights [out][ld], row strides, act' multipliers (None for layer 0), dims).  Same return dict as
+    broyden()."""
+    _cabi.require_device(rhs, 'broyden_mlp_vjp rhs')
+    lib = _cabi.load()
+    W, ldw, dmul, dims = spec
+    shape = rhs.shape
+    B = shape[0]
+    d = rhs.numel() // B
+    assert d == dims[0] == dims[-1]
+    eps_scaled = eps * np.sqrt(np.prod((B, d)))
+    ws = _workspace(B, d, threshold, rhs.device)
+    if not hasattr(ws, 'gb'):
+        ws.ga = torch.empty(B, d, device=rhs.device, dtype=torch.float32)
+        ws.gb = torch.empty(B, d, device=rhs.device, dtype=torch.float32)
+        ws.partial_d = torch.empty(int(lib.impflow_mlp_solver_partial_doubles()), device=rhs.device,
+                                   dtype=torch.float64)
+    ws.xa.zero_()
+    L = len(W)
+    w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in W])
+    ld_arr = (ctypes.c_int * L)(*[int(v) for v in ldw])
+    dm_arr = (ctypes.c_void_p * L)(*[(t.data_ptr() if t is not None else None) for t in dmul])
+    dims_arr = (ctypes.c_int * (L + 1))(*dims)
+    r = rhs.reshape(B, d).contiguous()
+    _cabi.check(lib.impflow_mlp_broyden_solve_vjp(
+        _cabi.ptr(r), w_arr, ld_arr, dm_arr, dims_arr, L, _cabi.ptr(ws.xa), _cabi.ptr(ws.ga), _cabi.ptr(ws.xb),
+        _cabi.ptr(ws.gb), _cabi.ptr(ws.low_x), _cabi.ptr(ws.low_g), _cabi.ptr(ws.Ut), _cabi.ptr(ws.Vt),
+        _cabi.ptr(ws.sample_sq), _cabi.ptr(ws.low_sq), ctypes.c_void_p(ws.partial_d.data_ptr()),
+        ctypes.c_void_p(ws.state.data_ptr()), B, threshold, float(eps_scaled), _cabi.stream()), 'mlp_broyden_solve_vjp')
     state = ws.read_state()
     return _result_dict(ws, state, shape, eps_scaled, threshold)
 

@@ -20,7 +20,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from .. import ops
-from .broyden import broyden, broyden_mlp
+from .broyden import broyden, broyden_mlp, broyden_mlp_vjp
 
 __all__ = ['imBlock']
 
@@ -290,6 +290,10 @@ class imBlock(nn.Module):
                     z, x = z.detach(), x.detach()
                     _, saved_z = prog_z.forward_saved(z)
                     info = prog_z.broyden_solve(1, grad, saved_z, threshold, eps)
+                    if info is None:
+                        spec = prog_z.mlp_vjp_spec(saved_z)
+                        if spec is not None:       # small-d MLP: the whole solve in one persistent kernel
+                            info = broyden_mlp_vjp(spec, grad, threshold, eps)
                     if info is None:
                         info = broyden(lambda v: ops.lincomb3(prog_z.vjp(v, saved_z), 1.0, v, 1.0, grad, -1.0),
                                        torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')

@@ -55,6 +55,9 @@ class FusedAdam(torch.optim.Optimizer):
         self.step_count = 0
         self.last_grad_norm_sq = None        # device scalar of the latest step (sqrt it to log the norm)
 
+    def zero_grad(self, set_to_none=True):
+        self.bucket.zero()
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
@@ -74,8 +77,11 @@ class FusedAdam(torch.optim.Optimizer):
             _cabi.ptr(self.ema, 'ema', True), g.numel(), _cabi.ptr(gsq, 'gnorm_sq', True),
             float(self.max_grad_norm or 0.0), float(step_size), float(beta1), float(beta2), float(group['eps']),
             float(self.ema_decay or 0.0), _cabi.stream()), 'clip_adam_ema')
-        # the kernel wrote through raw pointers: the host caches are keyed on the tensors' versions
-        torch.autograd.graph.increment_version([p for p in self.bucket.params])
+        # the kernel wrote through raw pointers: the host caches are keyed on the tensors' versions.  Parameters
+        # that received no gradient (the roulette rates geom_p / lamb: the vendored Adam skips them,
+        # lib/optimizers.py:70-72) keep value and version — a zero gradient leaves them bit-identical here too —
+        # so caches of their host copies (imBlock._rate) stay valid and nothing re-reads them from the device
+        torch.autograd.graph.increment_version([p for p, h in zip(self.bucket.params, self.bucket.had_grad) if h])
         return loss
 
     def grad_norm(self):

@@ -46,6 +46,7 @@ class FlatGradBucket(object):
         dev = self.params[0].device if self.params else torch.device('cpu')
         self.flat = torch.zeros(off, device=dev, dtype=torch.float32)
         self.views = []
+        self.had_grad = [True] * len(self.params)      # of the latest gather_strays()
         for p, o in zip(self.params, self.offsets):
             v = self.flat[o:o + p.numel()].view_as(p)
             p.grad = v
@@ -62,15 +63,22 @@ class FlatGradBucket(object):
     def gather_strays(self):
         """Copy the gradients autograd produced outside the bucket into it (one multi-tensor launch) and point
         every .grad at its view; parameters without a gradient keep the zeros."""
-        dst, src = [], []
+        if all(p.grad is v for p, v in zip(self.params, self.views)):
+            return      # nothing outside the bucket (e.g. the optimiser's call after allreduce_mean's)
+        dst, src, empty = [], [], []
+        self.had_grad = [p.grad is not None for p in self.params]
         for p, v in zip(self.params, self.views):
             g = p.grad
-            if g is not None and g.data_ptr() != v.data_ptr():
+            if g is None:
+                empty.append(v)        # stays zero also when the caller used zero_grad() instead of zero()
+            elif g.data_ptr() != v.data_ptr():
                 dst.append(v)
                 src.append(g.detach() if g.shape == v.shape else g.detach().reshape(v.shape))
             p.grad = v
-        if dst:
-            with torch.no_grad():
+        with torch.no_grad():
+            if empty:
+                torch._foreach_zero_(empty)
+            if dst:
                 torch._foreach_copy_(dst, src)
 
     def allreduce_mean(self, group=None):

@@ -106,6 +106,17 @@ int impflow_mlp_broyden_solve(const float* x_embed, const float* const* Wt, cons
                               float* sample_sq, float* low_sq, double* partial, impflow_broyden_state* state,
                               int B, int threshold, double eps_scaled, void* stream);
 
+/* Implicit-backward solve v^T (I + J_f(z)) = rhs of the same MLP branch (imBlock.Backward,
+ * implicit_block.py:199-207) in the same persistent kernel: the residual is g(v) = v^T J + v - rhs with
+ * v^T J = (((v W_{L-1}) * D_{L-1}) W_{L-2} * D_{L-2}) ... W_0, D_l = act'(pre-activation in front of layer l).
+ *   W[l]   : DEVICE pointer to the effective weight of layer l, [dims[l+1]][ldw[l]] row-major (HOST array of L)
+ *   dmul[l]: DEVICE pointer to D_l, (B, dims[l]) contiguous, or NULL (HOST array of L; dmul[0] must be NULL)
+ *   za     : start point (zeros in the reference) on entry; other buffers / state as in impflow_mlp_broyden_solve */
+int impflow_mlp_broyden_solve_vjp(const float* rhs, const float* const* W, const int* ldw, const float* const* dmul,
+                                  const int* dims, int L, float* za, float* ga, float* zb, float* gb, float* low_z,
+                                  float* low_g, float* Ut, float* Vt, float* sample_sq, float* low_sq, double* partial,
+                                  impflow_broyden_state* state, int B, int threshold, double eps_scaled, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Elementwise / reductions on the path
  * ------------------------------------------------------------------------------------------ */

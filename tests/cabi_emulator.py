@@ -272,6 +272,43 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_mlp_broyden_solve_vjp(self, rhs, W, ldw, dmul, dims, L, za, ga, zb, gb, low_z, low_g, Ut, Vt,
+                                      sample_sq, low_sq, partial, state, B, T, eps, stream):
+        dims = [int(v) for v in dims]
+        d = dims[0]
+        Ws = []
+        for l in range(L):
+            ld = int(ldw[l])
+            Ws.append(_f32(W[l], (dims[l + 1] - 1) * ld + dims[l]).copy() if ld == dims[l] else None)
+            full = np.lib.stride_tricks.as_strided(_f32(W[l], (dims[l + 1] - 1) * ld + dims[l]),
+                                                   shape=(dims[l + 1], dims[l]), strides=(4 * ld, 4))
+            Ws[-1] = np.array(full)
+        Ds = [(_f32(dmul[l], B * dims[l]).reshape(B, dims[l]) if dmul[l] else None) for l in range(L)]
+        r = _f32(rhs, B * d).reshape(B, d)
+
+        def f(v):
+            h = v
+            for l in range(L - 1, -1, -1):
+                h = (h @ Ws[l]).astype(np.float32)
+                if Ds[l] is not None:
+                    h = h * Ds[l]
+            return h
+
+        bufs = {'x': za, 'g': ga, 'xn': zb, 'gn': gb}
+        x0 = _f32(za, B * d).reshape(B, d)
+        _f32(ga, B * d)[:] = (f(x0) + x0 - r).ravel()
+        self.impflow_broyden_begin(za, ga, zb, low_z, low_g, sample_sq, low_sq, None, state, B, d, T, eps, None)
+        st = _state(state)
+        while st[0]['active']:
+            xn = _f32(bufs['xn'], B * d).reshape(B, d)
+            _f32(bufs['gn'], B * d)[:] = (f(xn) + xn - r).ravel()
+            self.impflow_broyden_step(bufs['x'], bufs['g'], bufs['xn'], bufs['gn'], Ut, Vt, low_z, low_g, sample_sq,
+                                      low_sq, None, state, B, d, T, None)
+            bufs['x'], bufs['xn'] = bufs['xn'], bufs['x']
+            bufs['g'], bufs['gn'] = bufs['gn'], bufs['g']
+        self.launches += 1
+        return 0
+
     # ---- elementwise (csrc/elementwise.cu) ----
     def impflow_act_mul(self, x, g, out, n, kind, order, beta_sp, stream):
         xv, gv, ov = _f32(x, n), _f32(g, n), _f32(out, n)
