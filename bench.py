@@ -570,11 +570,19 @@ def main():
               'k_gemm_tc3': 'k_gemm_tc3 (tcgen05 3xTF32 residual-branch GEMM)',
               'k_wgrad_tc3': 'k_wgrad_tc3 (tcgen05 3xTF32 weight gradient, MN-major operands)'}
 
+    # DRAM bytes per launch of each kernel from the committed `ncu --set full` captures (profiles/)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+    except Exception:
+        traffic = {}
+
     def roof(name):
         k = kern[name]
         ach = k['flop'] / (k['ms'] / 1e3) / 1e12 if k['ms'] > 0 else 0.0
+        tr = traffic.get(name)
         return {'kernel': KNAMES[name], 'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': ach / peak_tf, 'traffic': None, 'peak_source': peak_src, 'launches': k['launches'],
+                'frac': ach / peak_tf, 'traffic': tr['dram_bytes_per_launch'] if tr else None,
+                'traffic_detail': tr, 'peak_source': peak_src, 'launches': k['launches'],
                 'share_of_step': k['ms'] / ms_total if ms_total > 0 else None,
                 'top_shapes': [d for _, d in sorted(k['shapes'], key=lambda x: -x[0])[:4]],
                 'frac_of_3xtf32_ceiling': ach / (peak_tf / 6.0),
