@@ -176,15 +176,27 @@ k_neumann_act_bwd(const float* __restrict__ p, const float* __restrict__ t, cons
     beta_partial[blockIdx.x] = (float)tt;
   }
 }
-// second stage: colsum[n] = sum_b col_partial[b][n] (fixed order)
+// second stage: colsum[n] = sum_b col_partial[b][n].  One block per 32 columns; 8 row groups sum every 8th partial
+// row (coalesced 128-byte reads) and are combined in fixed order: deterministic, and 8x shorter dependent chains
+// than one thread per column.
 __global__ void __launch_bounds__(256)
 k_sum_col_partials(const float* __restrict__ part, float* __restrict__ out, int nblk, int N) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
-#pragma unroll 8
-  for (int b = 0; b < nblk; ++b) acc += part[(long long)b * N + c];      // independent loads, fixed summation order
-  out[c] = acc;
+  if (c < N) {
+#pragma unroll 4
+    for (int b = grp; b < nblk; b += 8) acc += part[(long long)b * N + c];
+  }
+  red[grp][lane] = acc;
+  __syncthreads();
+  if (grp == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][lane];
+    out[c] = t;
+  }
 }
 
 // ---- lincomb3 -----------------------------------------------------------------------------------
@@ -672,7 +684,7 @@ extern "C" int impflow_neumann_act_bwd(const float* p, const float* t, const flo
   float* beta_partial = ws + (size_t)nblk * N;
   k_neumann_act_bwd<<<nblk, 256, 0, s>>>(p, t, ta, ab, y_hi, y_lo, col_partial, beta_partial, M, N, rows, beta_sp);
   if (check_launch("k_neumann_act_bwd")) return -1;
-  k_sum_col_partials<<<(N + 255) / 256, 256, 0, s>>>(col_partial, colsum, nblk, N);
+  k_sum_col_partials<<<(N + 31) / 32, 256, 0, s>>>(col_partial, colsum, nblk, N);
   if (check_launch("k_sum_col_partials")) return -1;
   k_sum_partials<<<1, 32, 0, s>>>(beta_partial, beta_grad, nblk);
   return check_launch("k_sum_partials");

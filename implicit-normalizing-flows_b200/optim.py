@@ -70,7 +70,7 @@ class FusedAdam(torch.optim.Optimizer):
         step_size = group['lr'] * math.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
         gsq = None
         if self.max_grad_norm is not None:
-            gsq = ops._flat_dot(g, g) if g.numel() % 256 == 0 else ops.rowdot(g.view(1, -1), g.view(1, -1))
+            gsq = ops._flat_dot(g, g)        # 256 CTAs + a 256-element sum (the bucket length is a multiple of 1024)
             self.last_grad_norm_sq = gsq
         _cabi.check(_cabi.load().impflow_clip_adam_ema(
             _cabi.ptr(self.flat_p), _cabi.ptr(g), _cabi.ptr(self.exp_avg), _cabi.ptr(self.exp_avg_sq),

@@ -43,6 +43,8 @@ class FlatGradBucket(object):
         for p in self.params:
             self.offsets.append(off)
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        # total length a multiple of 1024 floats: whole-buffer reductions (the clip norm) split evenly over 256 CTAs
+        off = (off + 1023) // 1024 * 1024
         dev = self.params[0].device if self.params else torch.device('cpu')
         self.flat = torch.zeros(off, device=dev, dtype=torch.float32)
         self.views = []
