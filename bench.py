@@ -386,6 +386,8 @@ def main():
         pkg._cabi.load().impflow_gemm_tc_set_tma_store(0)
     if os.environ.get('IMPFLOW_PAIR', '') == '0':            # A/B: single-CTA GEMM tiles only (no cta_group::2)
         pkg._cabi.load().impflow_gemm_tc_set_pair(0)
+    if os.environ.get('IMPFLOW_PDL', '') == '0':             # A/B: ordinary launches of the tile kernels
+        pkg._cabi.load().impflow_set_pdl(0)
 
     torch.manual_seed(0)
     np.random.seed(0)

@@ -66,6 +66,7 @@ SIGNATURES = {
     'impflow_gemm_tc_set_wide_tiles': (_i, [_i]),
     'impflow_gemm_tc_set_tma_store': (_i, [_i]),
     'impflow_gemm_tc_set_pair': (_i, [_i]),
+    'impflow_set_pdl': (_i, [_i]),
     'impflow_split_tf32': (_i, [_c_fp, _c_fp, _c_fp, _ll, _c_fp]),
     'impflow_prep_weights': (_i, [_c_fp, _c_fp, _f, _i, _i, _i, _c_fp, _c_fp, _c_fp, _i, _i, _c_fp, _c_fp, _c_fp, _i, _i,
                                   _c_fp]),

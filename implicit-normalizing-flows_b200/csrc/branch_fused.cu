@@ -167,6 +167,7 @@ k_branch3(const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ C
   const long long m_tiles = (args.M + TC_BM - 1) / TC_BM;
   const long long num_items = m_tiles * n_halves;
 
+  pdl_trigger();     // col2im behind this kernel may be scheduled as its CTAs retire
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapW1hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapW1lo)) : "memory");
@@ -203,6 +204,7 @@ k_branch3(const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // the set-up above overlapped the predecessor (im2col); no global memory was touched yet
 
   if (warp == 0) {
     // ================= TMA producer: weight chunks =================
@@ -467,7 +469,20 @@ static int launch_branch3(const CUtensorMap* maps, const BranchArgs& a, cudaStre
   }
   const long long items = ((a.M + TC_BM - 1) / TC_BM) * (a.C / 256);
   const int grid = (int)(items < 148 ? items : 148);
-  k_branch3<ACT><<<grid, BF_THREADS, BF_SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(BF_THREADS);
+  cfg.dynamicSmemBytes = BF_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(&attr[0]);
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, k_branch3<ACT>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a);
+  if (err != cudaSuccess) {
+    set_error("k_branch3: launch failed: %s", cudaGetErrorString(err));
+    return -1;
+  }
   return check_launch("k_branch3");
 }
 

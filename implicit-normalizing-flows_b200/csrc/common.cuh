@@ -12,6 +12,35 @@ namespace impflow {
 // thread-local error string behind impflow_last_error()
 void set_error(const char* fmt, ...);
 extern long long g_launch_count;
+extern int g_pdl;     // programmatic dependent launch of the tile kernels (impflow_set_pdl)
+
+// Programmatic dependent launch (PDL).  A tile kernel launched with the stream-serialisation attribute may be
+// scheduled while its predecessor still runs: its prologue (barrier init, TMEM allocation, tensor-map prefetch)
+// overlaps the predecessor's tail, and pdl_wait() — executed by every thread before the first global-memory
+// access — blocks until the predecessor grid has completed and its writes are visible.  pdl_trigger() in a
+// predecessor lets such a dependent be scheduled as soon as all of the predecessor's CTAs have started.  Both are
+// no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline int pdl_attr(cudaLaunchAttribute* a) {
+  if (!g_pdl) return 0;
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}
+// <<<grid, block, 0, s>>> with the PDL attribute; the kernel must call pdl_wait() before its first global access
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(&attr[0]);
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -73,11 +73,12 @@ static int conv3_forward(const impflow_conv3_plan* p, const float* x_rows, float
   }
   const int N3 = 9 * p->c;
   if (use_tile_kernel(p)) {
-    if (impflow_im2col3x3(xin, w.x0, p->B, p->H, p->W, p->c, 32, stream)) return -1;
+    // zero first: the tile kernel then directly follows im2col and its set-up overlaps it (PDL, common.cuh)
     if (p->C > 256 && cudaMemsetAsync(w.Y, 0, sizeof(float) * (size_t)M * N3, (cudaStream_t)stream) != cudaSuccess) {
       set_error("conv3_forward: memset failed");
       return -1;
     }
+    if (impflow_im2col3x3(xin, w.x0, p->B, p->H, p->W, p->c, 32, stream)) return -1;
     if (impflow_branch3_tc(w.x0, 32, p->W1f_hi, p->W1f_lo, p->W2f_hi, p->W2f_lo, p->W3f_hi, p->W3f_lo, p->b1, p->b2,
                            nullptr, nullptr, pre1, pre2, w.Y, N3, M, p->C, N3, p->act_kind, p->beta1, p->beta2,
                            stream))
@@ -111,11 +112,11 @@ static int conv3_vjp(const impflow_conv3_plan* p, const float* pre0, const float
   const Conv3Ws w = carve(p->ws, M, p->c, p->C, p->k0);
   const int N3 = 9 * p->c;
   if (use_tile_kernel(p)) {
-    if (impflow_im2col3x3(v_rows, w.x0, p->B, p->H, p->W, p->c, 32, stream)) return -1;
     if (p->C > 256 && cudaMemsetAsync(w.Y, 0, sizeof(float) * (size_t)M * N3, (cudaStream_t)stream) != cudaSuccess) {
       set_error("conv3_vjp: memset failed");
       return -1;
     }
+    if (impflow_im2col3x3(v_rows, w.x0, p->B, p->H, p->W, p->c, 32, stream)) return -1;
     if (impflow_branch3_tc(w.x0, 32, p->W3b_hi, p->W3b_lo, p->W2b_hi, p->W2b_lo, p->W1b_hi, p->W1b_lo, nullptr,
                            nullptr, d2, d1, nullptr, nullptr, w.Y, N3, M, p->C, N3, IMPFLOW_ACT_NONE, nullptr, nullptr,
                            stream))

@@ -8,6 +8,7 @@ namespace impflow {
 
 static thread_local char g_err[512] = "";
 long long g_launch_count = 0;
+int g_pdl = 1;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -203,6 +204,8 @@ k_sum_col_partials(const float* __restrict__ part, float* __restrict__ out, int 
 __global__ void __launch_bounds__(256)
 k_lincomb3(const float* __restrict__ a, float ca, const float* __restrict__ b, float cb,
            const float* __restrict__ c, float cc, float* __restrict__ out, long long n, int vec) {
+  pdl_trigger();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (vec) {
@@ -307,6 +310,8 @@ k_transpose(const float* __restrict__ a, float* __restrict__ out, long long M, l
 // x[p,c] = sum_tap col[p - off(tap), tap, c] followed by the fused epilogue.
 __global__ void __launch_bounds__(256)
 k_col2im3x3(const float* __restrict__ col, int B, int H, int W, int C, Epilogue ep_in) {
+  pdl_trigger();
+  pdl_wait();
   const Epilogue ep = resolve_beta(ep_in);
   const long long total = (long long)B * H * W * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -341,6 +346,7 @@ k_split_tf32(const float* __restrict__ a, float* __restrict__ hi, float* __restr
 }
 __global__ void __launch_bounds__(256)
 k_split_tf32_v4(const float4* __restrict__ a, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 v = a[i];
@@ -394,6 +400,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 k_im2col3x3_rows(const float* __restrict__ x, float* __restrict__ col, float* __restrict__ col_lo, int B, int H,
                  int W, int C, int ld) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = ld / VEC;
   const long long total = (long long)B * H * W * groups;
   const int K = 9 * C;
@@ -592,6 +600,11 @@ extern "C" int impflow_actnorm_backward(const float* gy, const float* y, const f
 extern "C" int impflow_version(void) { return IMPFLOW_ABI_VERSION; }
 extern "C" const char* impflow_last_error(void) { return impflow::g_err; }
 extern "C" long long impflow_launch_count(void) { return impflow::g_launch_count; }
+extern "C" int impflow_set_pdl(int on) {
+  const int prev = impflow::g_pdl;
+  impflow::g_pdl = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" int impflow_act_mul(const float* x, const float* g, float* out, long long n, int kind, int order,
                                const float* beta_sp, void* stream) {

@@ -106,6 +106,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
   uint64_t* tempty = tfull + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  pdl_trigger();     // a dependent tile kernel may be scheduled as this one's CTAs retire
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = K / TC_BK;
@@ -155,6 +156,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
   if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlapped the predecessor; no global memory was touched yet
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -502,13 +504,13 @@ static int launch_tc(const float* Ahi, const float* Alo, long long lda, const fl
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = TcCfg<BN, PAIR>::kSmemBytes;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1 + pdl_attr(&attr[1]);
     const cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_tc3<BN, PAIR>, mAh, mAl, mBh, mBl, mo[0], mo[1], mo[2], mo[3],
                                                tma_store, M, N, K, ep, splits, ws);
     if (err != cudaSuccess) {
@@ -518,8 +520,23 @@ static int launch_tc(const float* Ahi, const float* Alo, long long lda, const fl
     return check_launch("k_gemm_tc3<pair>");
   }
   const int grid = (int)(tiles < 148 ? tiles : 148);
-  k_gemm_tc3<BN, PAIR><<<grid, TC_THREADS, TcCfg<BN, PAIR>::kSmemBytes, s>>>(mAh, mAl, mBh, mBl, mo[0], mo[1], mo[2], mo[3],
-                                                                              tma_store, M, N, K, ep, splits, ws);
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TcCfg<BN, PAIR>::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_attr(&attr[0]);
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_tc3<BN, PAIR>, mAh, mAl, mBh, mBl, mo[0], mo[1], mo[2], mo[3],
+                                               tma_store, M, N, K, ep, splits, ws);
+    if (err != cudaSuccess) {
+      set_error("k_gemm_tc3: launch failed: %s", cudaGetErrorString(err));
+      return -1;
+    }
+  }
   if (check_launch("k_gemm_tc3")) return -1;
   if (splits > 1) {
     long long blocks = (M * N + 255) / 256;

@@ -232,6 +232,11 @@ int impflow_gemm_tc_set_tma_store(int on);
  * clusters of two CTAs (tcgen05.mma.cta_group::2, 256x256 tiles, each CTA stages half of the weight tile),
  * 0 = single-CTA tiles only.  Returns the previous setting. */
 int impflow_gemm_tc_set_pair(int on);
+/* Programmatic dependent launch of the tile kernels (k_gemm_tc3, k_branch3): 1 (default) = they are launched with
+ * the stream-serialisation attribute, so their set-up (barriers, tensor memory, tensor-map prefetch) overlaps the
+ * tail of the preceding kernel and every thread executes griddepcontrol.wait before the first global-memory access;
+ * 0 = ordinary launches.  Returns the previous setting. */
+int impflow_set_pdl(int on);
 /* Weight-gradient contraction dW[N1,N2] = G[Mpix,N1]^T A[Mpix,N2] (K = all pixels) straight from the row-major
  * hi/lo planes: both operands are fed to tcgen05 as MN-major tiles (TMA boxes of 32 pixels x 32 channels), so
  * no transposed copies are made (replaces the autograd weight gradients of F.conv2d / F.linear,

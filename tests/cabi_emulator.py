@@ -411,6 +411,9 @@ class EmulatedLib(object):
     def impflow_gemm_tc_set_pair(self, on):
         return 1
 
+    def impflow_set_pdl(self, on):
+        return 1
+
     def impflow_gemm_tc_set_wide_tiles(self, on):
         return 1
 
