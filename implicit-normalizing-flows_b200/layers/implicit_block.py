@@ -129,7 +129,18 @@ def _sync_twin(dst, src):
         d = list(dst.parameters()) + list(dst.buffers())
         s = list(src.parameters()) + list(src.buffers())
         if len(d) == len(s) and all(a.shape == b.shape and a.dtype == b.dtype for a, b in zip(d, s)):
-            torch._foreach_copy_(d, [t.detach() for t in s])
+            # the multi-tensor fast path needs one dtype per call and equal strides: group by dtype and copy
+            # flat views (a mixed list silently degrades to one cudaMemcpy per tensor)
+            groups = {}
+            for a, b in zip(d, s):
+                if a.is_contiguous() and b.is_contiguous():
+                    groups.setdefault(a.dtype, ([], []))
+                    groups[a.dtype][0].append(a.view(-1))
+                    groups[a.dtype][1].append(b.detach().view(-1))
+                else:
+                    a.copy_(b)
+            for da, sa in groups.values():
+                torch._foreach_copy_(da, sa)
             for m in dst.modules():           # python mirrors of buffers that load_state_dict would reset
                 if hasattr(m, '_hw'):
                     m._hw = None

@@ -74,8 +74,10 @@ class FlatGradBucket(object):
             if g is None:
                 empty.append(v)        # stays zero also when the caller used zero_grad() instead of zero()
             elif g.data_ptr() != v.data_ptr():
-                dst.append(v)
-                src.append(g.detach() if g.shape == v.shape else g.detach().reshape(v.shape))
+                # flat views on both sides: the multi-tensor fast path needs equal strides (size-1 dimensions
+                # of conv weights can carry different ones), else it degrades to one cudaMemcpy per tensor
+                dst.append(v.view(-1))
+                src.append(g.detach().reshape(-1))
             p.grad = v
         with torch.no_grad():
             if empty:
