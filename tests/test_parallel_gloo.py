@@ -78,3 +78,39 @@ def test_shard_batch_covers_ragged_batches():
     assert [p.shape[0] for p in parts] == [3, 3, 3, 1]
     assert torch.equal(torch.cat(parts), x)
     assert impflow_b200.parallel.shard_batch(x[:2], 3, 4).shape[0] == 0     # empty shard
+
+
+def test_flat_bucket_gather_semantics():
+    """FlatGradBucket: gradients arrive outside the bucket (the .grad slots are emptied by zero()), one gather moves
+    them into the flat buffer; parameters without a gradient keep zeros — also after zero_grad(set_to_none=True)
+    instead of zero() — and are reported in had_grad; a second gather of the same step is a no-op; gradients whose
+    size-1 dimensions carry unusual strides are gathered correctly."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import impflow_b200
+    par = impflow_b200.parallel
+    torch.manual_seed(1)
+    ps = [torch.nn.Parameter(torch.randn(4, 3, 1, 1)), torch.nn.Parameter(torch.randn(5)),
+          torch.nn.Parameter(torch.randn(())), torch.nn.Parameter(torch.randn(2, 2))]
+    bucket = par.FlatGradBucket(ps)
+    assert bucket.flat.numel() % 1024 == 0 and all(o % bucket.ALIGN == 0 for o in bucket.offsets)
+    bucket.zero()
+    assert all(p.grad is None for p in ps)
+    g0 = torch.randn(4, 3).as_strided((4, 3, 1, 1), (3, 1, 7, 7))        # odd strides on the size-1 dimensions
+    ps[0].grad, ps[1].grad, ps[3].grad = g0, torch.randn(5), torch.randn(2, 2)
+    want = [g0.clone(), ps[1].grad.clone(), torch.zeros(()), ps[3].grad.clone()]
+    bucket.gather_strays()
+    assert bucket.had_grad == [True, True, False, True]
+    for p, v, w in zip(ps, bucket.views, want):
+        assert p.grad is v and torch.equal(v, w)
+    snapshot = bucket.flat.clone()
+    bucket.gather_strays()                                               # e.g. the optimiser after allreduce_mean
+    assert torch.equal(bucket.flat, snapshot) and bucket.had_grad == [True, True, False, True]
+    # a caller that uses zero_grad(set_to_none=True) instead of zero(): stale values must not survive
+    for p in ps:
+        p.grad = None
+    ps[1].grad = torch.ones(5)
+    bucket.gather_strays()
+    assert bucket.had_grad == [False, True, False, False]
+    assert torch.equal(bucket.views[1], torch.ones(5))
+    assert float(bucket.flat.abs().sum()) == 5.0
