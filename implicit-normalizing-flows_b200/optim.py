@@ -54,6 +54,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.ema = self.flat_p.clone() if ema_decay is not None else None
         self.step_count = 0
         self.last_grad_norm_sq = None        # device scalar of the latest step (sqrt it to log the norm)
+        self._ever_grad = [False] * len(self.bucket.params)
 
     def zero_grad(self, set_to_none=True):
         self.bucket.zero()
@@ -81,7 +82,9 @@ class FusedAdam(torch.optim.Optimizer):
         # that received no gradient (the roulette rates geom_p / lamb: the vendored Adam skips them,
         # lib/optimizers.py:70-72) keep value and version — a zero gradient leaves them bit-identical here too —
         # so caches of their host copies (imBlock._rate) stay valid and nothing re-reads them from the device
-        torch.autograd.graph.increment_version([p for p, h in zip(self.bucket.params, self.bucket.had_grad) if h])
+        # (a parameter that had a gradient in ANY earlier step still moves with its momentum: its version follows)
+        self._ever_grad = [e or h for e, h in zip(self._ever_grad, self.bucket.had_grad)]
+        torch.autograd.graph.increment_version([p for p, e in zip(self.bucket.params, self._ever_grad) if e])
         return loss
 
     def grad_norm(self):
