@@ -6,7 +6,7 @@
 
 namespace impflow {
 
-constexpr int kSnThreads = 512;
+constexpr int kSnThreads = 1024;
 constexpr int kSnWarps = kSnThreads / 32;
 
 __device__ float block_sum(float v, float* scratch) {
@@ -40,12 +40,41 @@ __device__ void mat_vec(const float* __restrict__ W, const float* x, float* y, i
   }
   __syncthreads();
 }
-// y[c] = sum_r W[r,c] x[r]   (thread per column, coalesced across threads)
-__device__ void mat_t_vec(const float* __restrict__ W, const float* x, float* y, int out_f, int in_f) {
+// y[c] = sum_r W[r,c] x[r].  Rows are dealt round-robin to the warps (one coalesced row segment per load, 32
+// independent rows in flight per CTA instead of one dependent chain per column); the per-warp partial sums are
+// combined in warp order through `part` ([kSnWarps][in_f] floats of shared memory): deterministic.
+__device__ void mat_t_vec(const float* __restrict__ W, const float* x, float* y, int out_f, int in_f, float* part) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (part == nullptr) {            // no room for the partials: one thread per column
+    for (int c = threadIdx.x; c < in_f; c += kSnThreads) {
+      float acc = 0.f;
+      for (int r = 0; r < out_f; ++r) acc += W[(long long)r * in_f + c] * x[r];
+      y[c] = acc;
+    }
+    __syncthreads();
+    return;
+  }
+  for (int c0 = 0; c0 < in_f; c0 += 32 * 8) {          // 8 columns per lane and pass
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = warp; r < out_f; r += kSnWarps) {
+      const float xr = x[r];
+      const float* row = W + (long long)r * in_f + c0 + lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + lane + 32 * j < in_f) acc[j] = fmaf(row[32 * j], xr, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + lane + 32 * j < in_f) part[warp * in_f + c0 + lane + 32 * j] = acc[j];
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < in_f; c += kSnThreads) {
-    float acc = 0.f;
-    for (int r = 0; r < out_f; ++r) acc += W[(long long)r * in_f + c] * x[r];
-    y[c] = acc;
+    float t = 0.f;
+#pragma unroll 8
+    for (int w = 0; w < kSnWarps; ++w) t += part[w * in_f + c];
+    y[c] = t;
   }
   __syncthreads();
 }
@@ -61,12 +90,13 @@ __device__ void l2_normalize(float* y, int n, float* scratch) {
 __global__ void __launch_bounds__(kSnThreads)
 k_sn_power_iter(const float* __restrict__ W, float* __restrict__ u_g, float* __restrict__ v_g,
                 float* __restrict__ sigma, int* __restrict__ iters, int out_f, int in_f, int n_iterations,
-                float atol, float rtol) {
+                float atol, float rtol, int with_partials) {
   extern __shared__ float sm[];
   float* u = sm;
   float* v = u + out_f;
   float* ou = v + in_f;
   float* ov = ou + out_f;
+  float* part = with_partials ? ov + in_f : nullptr;     // [kSnWarps][in_f]
   __shared__ float scratch[kSnWarps];
   for (int i = threadIdx.x; i < out_f; i += kSnThreads) u[i] = u_g[i];
   for (int i = threadIdx.x; i < in_f; i += kSnThreads) v[i] = v_g[i];
@@ -80,7 +110,7 @@ k_sn_power_iter(const float* __restrict__ W, float* __restrict__ u_g, float* __r
     __syncthreads();
     mat_vec(W, v, u, out_f, in_f);
     l2_normalize(u, out_f, scratch);
-    mat_t_vec(W, u, v, out_f, in_f);
+    mat_t_vec(W, u, v, out_f, in_f, part);
     l2_normalize(v, in_f, scratch);
     ++used;
     if (tol_mode) {
@@ -288,8 +318,11 @@ extern "C" int impflow_sn_scale_grad_layout(const float* Wbar, long long ldw, co
 extern "C" int impflow_sn_power_iter(const float* W, float* u, float* v, float* sigma, int* iters, int out_f,
                                      int in_f, int n_iterations, float atol, float rtol, void* stream) {
   IMPFLOW_REQUIRE(out_f >= 1 && in_f >= 1, "sn_power_iter: empty matrix");
-  const size_t smem = sizeof(float) * 2 * ((size_t)out_f + in_f);
+  size_t smem = sizeof(float) * 2 * ((size_t)out_f + in_f);
   IMPFLOW_REQUIRE(smem <= 200 * 1024, "sn_power_iter: out+in=%d too large for one CTA", out_f + in_f);
+  const size_t with_part = smem + sizeof(float) * (size_t)kSnWarps * in_f;
+  const int with_partials = with_part <= 200 * 1024 ? 1 : 0;
+  if (with_partials) smem = with_part;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(k_sn_power_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess) {
@@ -298,6 +331,6 @@ extern "C" int impflow_sn_power_iter(const float* W, float* u, float* v, float* 
     }
   }
   k_sn_power_iter<<<1, kSnThreads, smem, (cudaStream_t)stream>>>(W, u, v, sigma, iters, out_f, in_f,
-                                                                  n_iterations, atol, rtol);
+                                                                  n_iterations, atol, rtol, with_partials);
   return check_launch("k_sn_power_iter");
 }

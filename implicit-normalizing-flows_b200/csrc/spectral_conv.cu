@@ -22,7 +22,7 @@ namespace cg = cooperative_groups;
 
 namespace impflow {
 
-constexpr int kPcThreads = 256;
+constexpr int kPcThreads = 1024;      // 32 warps: the per-CTA convolutions are shared-memory-latency bound (was 256: 2x slower)
 constexpr int kPcWarps = kPcThreads / 32;
 
 struct PcArgs {
