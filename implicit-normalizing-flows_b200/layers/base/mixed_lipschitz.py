@@ -134,8 +134,13 @@ class InducedNormLinear(nn.Module):
             rtol = self.rtol if rtol is None else atol      # reference quirk (mixed_lipschitz.py:94)
             if n_iterations is None and (atol is None or rtol is None):
                 raise ValueError('Need one of n_iteration or (atol, rtol).')
+            only = UPDATE_ONLY['on'] and not torch.is_grad_enabled()
             with torch.no_grad():
-                sig, _ = ops.sn_power_iter(self.weight.detach(), self.u, self.v, n_iterations, atol, rtol)
+                sig, _ = ops.sn_power_iter(self.weight.detach(), self.u, self.v, n_iterations, atol, rtol,
+                                           sigma_out=self.scale if only else None)
+            if only:         # update_lipschitz: the kernel left sigma in `scale`; nobody reads the weight
+                self._scale_for = _state_key(self)
+                return None
             if not torch.is_grad_enabled():
                 out = ops.sn_rescale(self.weight.detach(), sig, self.coeff, scale_out=self.scale)
                 self._scale_for = _state_key(self)
@@ -316,8 +321,13 @@ class InducedNormConv2d(nn.Module):
     def _compute_weight_1x1(self, update, n_iterations, atol, rtol):
         W2 = self.weight.view(self.out_channels, self.in_channels)
         if update:
+            only = UPDATE_ONLY['on'] and not torch.is_grad_enabled()
             with torch.no_grad():
-                sig, _ = ops.sn_power_iter(W2.detach(), self.u, self.v, n_iterations, atol, rtol)
+                sig, _ = ops.sn_power_iter(W2.detach(), self.u, self.v, n_iterations, atol, rtol,
+                                           sigma_out=self.scale if only else None)
+            if only:
+                self._scale_for = _state_key(self)
+                return None
             if not torch.is_grad_enabled():
                 out = ops.sn_rescale(W2.detach(), sig, self.coeff, scale_out=self.scale).view(
                     self.out_channels, self.in_channels, 1, 1)
@@ -335,15 +345,20 @@ class InducedNormConv2d(nn.Module):
             h, w = self._spatial()
             tol_mode = n_iterations is None and atol is not None and rtol is not None
             res = None
+            only = UPDATE_ONLY['on'] and not torch.is_grad_enabled()
             if tol_mode or n_iterations is not None:
                 with torch.no_grad():
                     res = ops.sn_power_iter_conv(self.weight.detach(), self.u, self.v, h, w,
-                                                 None if tol_mode else n_iterations, atol, rtol, want_D=True)
+                                                 None if tol_mode else n_iterations, atol, rtol, want_D=True,
+                                                 sigma_out=self.scale if only else None)
             if res is not None:
                 update = False
                 # the kernel also leaves d sigma / d W for the new (u, v): what sigma_gradient() would recompute
                 self._sigma_grad = ((self.u._version, self.v._version, self.u.data_ptr(), self.v.data_ptr()), res[2])
-                if not torch.is_grad_enabled():      # update_lipschitz: nothing differentiates this result
+                if only:         # update_lipschitz: sigma went straight into `scale`; nobody reads the weight
+                    self._scale_for = _state_key(self)
+                    return None
+                if not torch.is_grad_enabled():      # nothing differentiates this result
                     out = ops.sn_rescale(self.weight.detach(), res[0], self.coeff, scale_out=self.scale)
                     self._scale_for = _state_key(self)      # `scale` now holds sigma of exactly this state
                     return out
@@ -395,6 +410,7 @@ class InducedNormConv2d(nn.Module):
 
 
 _side_streams = {}
+UPDATE_ONLY = {'on': False}     # set by update_lipschitz: compute_weight(update=True) only refreshes u, v and sigma
 
 
 def update_lipschitz(model, n_iterations=None, n_streams=8):
@@ -405,11 +421,27 @@ def update_lipschitz(model, n_iterations=None, n_streams=8):
     power iteration or the cooperative conv one), so they are fanned out over side streams and joined
     back into the current stream.  The frozen `*_copy` twins are skipped: imBlock.forward overwrites
     them from the live nets before their next use (SURVEY.md quirk #11)."""
-    mods = [m for name, m in model.named_modules()
-            if '_copy' not in name and isinstance(m, (InducedNormConv2d, InducedNormLinear))]
+    # the walk over every sub-module costs ~1 ms of host time per step at the CIFAR model: keep the list on the
+    # model (rebuilt when sub-modules were added or removed)
+    cached = model.__dict__.get('_lipschitz_layers')
+    n_children = sum(1 for _ in model.children())
+    if cached is None or cached[0] != n_children:
+        mods = [m for name, m in model.named_modules()
+                if '_copy' not in name and isinstance(m, (InducedNormConv2d, InducedNormLinear))]
+        model.__dict__['_lipschitz_layers'] = (n_children, mods)
+    else:
+        mods = cached[1]
     if not mods:
         return
     dev = mods[0].weight.device
+    UPDATE_ONLY['on'] = True
+    try:
+        _update_all(mods, dev, n_iterations, n_streams)
+    finally:
+        UPDATE_ONLY['on'] = False
+
+
+def _update_all(mods, dev, n_iterations, n_streams):
     with torch.no_grad():
         ready = all((not isinstance(m, InducedNormConv2d)) or m.is_initialized() for m in mods)
         if dev.type != 'cuda' or n_streams <= 1 or len(mods) < 2 or not ready:

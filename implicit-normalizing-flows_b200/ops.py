@@ -488,11 +488,12 @@ def _mark_written(*tensors):
     torch.autograd.graph.increment_version(tensors)
 
 
-def sn_power_iter(W2d, u, v, n_iterations, atol, rtol):
-    """In-place power iteration on (u, v); returns (sigma (1,), iters (1,) int32) device tensors."""
+def sn_power_iter(W2d, u, v, n_iterations, atol, rtol, sigma_out=None):
+    """In-place power iteration on (u, v); returns (sigma (1,), iters (1,) int32) device tensors.  sigma_out: a
+    1-element fp32 tensor (e.g. the layer's `scale` buffer) that receives sigma directly."""
     W2d = W2d.contiguous()
-    sigma = torch.empty(1, device=W2d.device, dtype=torch.float32)
-    iters = torch.zeros(1, device=W2d.device, dtype=torch.int32)
+    sigma = torch.empty(1, device=W2d.device, dtype=torch.float32) if sigma_out is None else sigma_out.view(1)
+    iters = torch.empty(1, device=W2d.device, dtype=torch.int32)       # always written by the kernel
     n_it = -1 if n_iterations is None else int(n_iterations)
     _cabi.check(_lib().impflow_sn_power_iter(_cabi.ptr(W2d), _cabi.ptr(u), _cabi.ptr(v), _cabi.ptr(sigma),
                                              _cabi.iptr(iters), W2d.shape[0], W2d.shape[1], n_it,
@@ -501,10 +502,12 @@ def sn_power_iter(W2d, u, v, n_iterations, atol, rtol):
                 'sn_power_iter')
     if n_it != 0:
         _mark_written(u, v)
+    if sigma_out is not None:
+        _mark_written(sigma_out)
     return sigma, iters
 
 
-def sn_power_iter_conv(W, u, v, h, w, n_iterations, atol, rtol, want_D=False):
+def sn_power_iter_conv(W, u, v, h, w, n_iterations, atol, rtol, want_D=False, sigma_out=None):
     """In-place power iteration of the 3x3 conv W (Cout,Cin,3,3) on one h x w image: one cooperative launch.
     Returns (sigma (1,), iters (1,) int32[, D = d sigma / d W]) device tensors, or None when the shape is not
     supported by the kernel (narrow side too large for shared memory) and the caller has to iterate itself."""
@@ -514,8 +517,8 @@ def sn_power_iter_conv(W, u, v, h, w, n_iterations, atol, rtol, want_D=False):
     if n_ws == 0:
         return None
     ws = torch.empty(n_ws, device=W.device, dtype=torch.float32)
-    sigma = torch.empty(1, device=W.device, dtype=torch.float32)
-    iters = torch.zeros(1, device=W.device, dtype=torch.int32)
+    sigma = torch.empty(1, device=W.device, dtype=torch.float32) if sigma_out is None else sigma_out.view(1)
+    iters = torch.empty(1, device=W.device, dtype=torch.int32)         # always written by the kernel
     n_it = -1 if n_iterations is None else int(n_iterations)
     D = torch.empty_like(W) if want_D else None
     _cabi.check(_lib().impflow_sn_power_iter_conv3x3(
@@ -524,6 +527,8 @@ def sn_power_iter_conv(W, u, v, h, w, n_iterations, atol, rtol, want_D=False):
         _cabi.ptr(D, 'D', True), _cabi.stream()), 'sn_power_iter_conv3x3')
     if n_it != 0:
         _mark_written(u, v)
+    if sigma_out is not None:
+        _mark_written(sigma_out)
     return (sigma, iters, D) if want_D else (sigma, iters)
 
 
