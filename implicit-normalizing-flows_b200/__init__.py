@@ -10,9 +10,11 @@ from . import _cabi  # noqa: F401
 from . import ops  # noqa: F401
 from . import layers  # noqa: F401
 from . import implicit_flow  # noqa: F401
+from . import resflow  # noqa: F401
 from . import parallel  # noqa: F401
 from . import optim  # noqa: F401
 from . import compat  # noqa: F401
 from .implicit_flow import ImplicitFlow  # noqa: F401
+from .resflow import ResidualFlow  # noqa: F401
 
 __version__ = '0.1.0'

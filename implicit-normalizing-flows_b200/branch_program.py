@@ -253,8 +253,10 @@ class BranchProgram(object):
         qualify: plain Linear/act/.../Linear MLP, one activation kind, d <= 128, widths <= 256."""
         if not self.is_linear or self.post_act is not None or self.stages[0][0] is not None:
             return None
+        if any(a is None for a, _ in self.stages[1:]):
+            return None
         kinds = {a.kind for a, _ in self.stages[1:]}
-        if len(kinds) > 1 or any(a is None for a, _ in self.stages[1:]):
+        if len(kinds) > 1:
             return None
         rows, meta = self._to_rows(x)
         ws = self._prep(rows.shape[0], meta)
@@ -266,9 +268,10 @@ class BranchProgram(object):
         if cached is None or cached[0] != key:
             Wt = [w.fwd[:, :w.cin].t().contiguous() for w in ws]
             cached = self._mlp_spec = (key, Wt)
-        act = self.stages[1][0] if len(self.stages) > 1 else None
-        return (cached[1], [w.bias for w in ws], dims, act.kind if act is not None else ops.ACT_NONE,
-                act.beta_sp() if act is not None else None)
+        acts = [a for a, _ in self.stages[1:]]          # acts[l] sits behind layer l; each Swish owns its beta
+        kind = acts[0].kind if acts else ops.ACT_NONE
+        betas = [a.beta_sp() for a in acts] if kind == ops.ACT_LIPSWISH else None
+        return (cached[1], [w.bias for w in ws], dims, kind, betas)
 
     def mlp_vjp_spec(self, saved):
         """Arguments of the persistent solver's implicit-backward mode (impflow_mlp_broyden_solve_vjp) at the point

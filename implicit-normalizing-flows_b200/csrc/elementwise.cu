@@ -464,7 +464,10 @@ k_clip_adam_ema(float* __restrict__ p, float* __restrict__ g, float* __restrict_
     m[i] = mi;
     v[i] = vi;
     p[i] = pi;
-    if (ema != nullptr) ema[i] = ema_decay * ema[i] + (1.f - ema_decay) * pi;
+    if (ema != nullptr) {      // shadow -= (1 - decay) * (shadow - param)   (lib/utils.py:143-146)
+      const float e = ema[i];
+      ema[i] = e - (1.f - ema_decay) * (e - pi);
+    }
   }
 }
 

@@ -35,7 +35,7 @@ struct MlpDesc {
   const float* bias[kMaxLayers];
   const float* dmul[kMaxLayers];   // vjp mode: per-sample multiplier (B, dims[l+1]) on the output of layer l, or null
   int act_kind;
-  const float* beta;
+  const float* beta[kMaxLayers];   // softplus(beta) of the LipSwish behind layer l (every Swish module owns its beta)
   int mode;                    // 0: g(z) = x_embed - f(z) - z (forward / inverse solve)
                                // 1: g(v) = v^T J + v - rhs   (implicit backward; f is the transposed linear chain)
 };
@@ -86,8 +86,7 @@ __device__ void mlp_layer(const float* __restrict__ Wt, int ld, const float* __r
 }
 
 // f(zin) for the tile's samples; result left in the returned smem buffer ([kTile][kMaxWidth], first d cols).
-__device__ float* mlp_eval(const MlpDesc& net, const float* __restrict__ zin, int s0, int B, float* bufA, float* bufB,
-                           float beta) {
+__device__ float* mlp_eval(const MlpDesc& net, const float* __restrict__ zin, int s0, int B, float* bufA, float* bufB) {
   const int d = net.dims[0];
   for (int i = threadIdx.x; i < kTile * d; i += kMlpThreads) {
     const int s = i / d, c = i % d;
@@ -97,6 +96,7 @@ __device__ float* mlp_eval(const MlpDesc& net, const float* __restrict__ zin, in
   float* cur = bufA;
   float* nxt = bufB;
   for (int l = 0; l < net.L; ++l) {
+    const float beta = net.beta[l] != nullptr ? __ldg(net.beta[l]) : 0.f;
     mlp_layer(net.Wt[l], net.ld[l], net.bias[l], cur, nxt, net.dims[l], net.dims[l + 1], net.act_kind, beta,
               net.mode == 0 && l + 1 < net.L, net.dmul[l], s0, B);
     __syncthreads();
@@ -206,7 +206,6 @@ k_mlp_broyden(MlpDesc net, const float* __restrict__ x_embed, float* za, float* 
   __shared__ float tile_sq[kTile];
   const int d = net.dims[0];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float beta = net.beta != nullptr ? __ldg(net.beta) : 0.f;
   const int n_tiles = (B + kTile - 1) / kTile;
   float *z_old = za, *g_old = ga, *zn = zb, *gn = gb;
 
@@ -217,7 +216,7 @@ k_mlp_broyden(MlpDesc net, const float* __restrict__ x_embed, float* za, float* 
     double cta_sum = 0.0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int s0 = tile * kTile;
-      float* f = mlp_eval(net, zin, s0, B, bufA, bufB, beta);
+      float* f = mlp_eval(net, zin, s0, B, bufA, bufB);
       if (tid < kTile) tile_sq[tid] = 0.f;
       __syncthreads();
       // g = x_embed - f(z) - z (mode 0) or f(v) + v - rhs (mode 1), one warp handles samples warp, warp+8
@@ -337,7 +336,7 @@ extern "C" size_t impflow_mlp_solver_partial_doubles(void) { return 2 * 148 * 8;
 // params: L transposed weight matrices Wt_l [dims[l]][dims[l+1]] and L bias vectors (pointers on the HOST,
 // pointing to device memory); biases may be NULL.
 extern "C" int impflow_mlp_broyden_solve(const float* x_embed, const float* const* Wt, const float* const* bias,
-                                         const int* dims, int L, int act_kind, const float* beta_sp, float* za,
+                                         const int* dims, int L, int act_kind, const float* const* beta_sp, float* za,
                                          float* ga, float* zb, float* gb, float* low_z, float* low_g, float* Ut,
                                          float* Vt, float* sample_sq, float* low_sq, double* partial,
                                          impflow_broyden_state* state, int B, int threshold, double eps_scaled,
@@ -346,6 +345,9 @@ extern "C" int impflow_mlp_broyden_solve(const float* x_embed, const float* cons
   IMPFLOW_REQUIRE(threshold >= 1 && threshold <= 63, "mlp_broyden_solve: threshold %d not in [1,63]", threshold);
   IMPFLOW_REQUIRE(dims[0] == dims[L] && dims[0] <= 128, "mlp_broyden_solve: needs d_in == d_out <= 128");
   IMPFLOW_REQUIRE(act_kind != IMPFLOW_ACT_LIPSWISH || beta_sp != nullptr, "mlp_broyden_solve: LipSwish needs beta");
+  if (act_kind == IMPFLOW_ACT_LIPSWISH)
+    for (int l = 0; l + 1 < L; ++l)
+      IMPFLOW_REQUIRE(beta_sp[l] != nullptr, "mlp_broyden_solve: LipSwish behind layer %d has no beta", l);
   MlpDesc net;
   memset(&net, 0, sizeof(net));
   net.L = L;
@@ -360,7 +362,7 @@ extern "C" int impflow_mlp_broyden_solve(const float* x_embed, const float* cons
   }
   for (int l = 0; l < L; ++l) net.ld[l] = dims[l + 1];
   net.act_kind = act_kind;
-  net.beta = beta_sp;
+  for (int l = 0; l + 1 < L; ++l) net.beta[l] = beta_sp != nullptr ? beta_sp[l] : nullptr;
   net.mode = 0;
   return launch_mlp_solver(net, x_embed, za, ga, zb, gb, low_z, low_g, Ut, Vt, sample_sq, low_sq, partial, state, B,
                            threshold, eps_scaled, stream);

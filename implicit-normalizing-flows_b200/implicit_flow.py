@@ -28,6 +28,7 @@ def _parse_vnorms(vnorms):
 
 
 class ImplicitFlow(nn.Module):
+    _stack = None      # set below: StackedImplicitBlocks (lib/resflow.py's ResidualFlow uses StackediResBlocks)
 
     def __init__(self, input_size, n_blocks=[16, 16], intermediate_dim=64, factor_out=True, quadratic=False,
                  init_layer=None, actnorm=False, fc_actnorm=False, batchnorm=False, dropout=0, fc=False, coeff=0.9,
@@ -56,7 +57,7 @@ class ImplicitFlow(nn.Module):
         _, c, h, w = input_size
         transforms = []
         for i in range(self.n_scale):
-            transforms.append(StackedImplicitBlocks(
+            transforms.append(self._stack(
                 initial_size=(c, h, w), squeeze=(i < self.n_scale - 1), init_layer=init_layer if i == 0 else None,
                 n_blocks=n_blocks[i], first_resblock=first_resblock and (i == 0), **shared))
             c, h, w = (c * 2 if factor_out else c * 4), h // 2, w // 2
@@ -150,12 +151,15 @@ class ImplicitFlow(nn.Module):
 
 
 class StackedImplicitBlocks(layers.SequentialFlow):
+    _implicit = True       # imBlock(nnet_x, nnet_z); StackediResBlocks (resflow.py) builds iResBlock(nnet)
 
     def __init__(self, initial_size, idim, squeeze=True, init_layer=None, n_blocks=1, actnorm=False,
                  fc_actnorm=False, fc=False, coeff=0.9, vnorms='122f', n_lipschitz_iters=None, sn_atol=None,
                  sn_rtol=None, n_power_series=5, n_dist='geometric', n_samples=1, kernels='3-1-3',
-                 activation_fn='elu', fc_end=True, fc_nblocks=2, fc_idim=128, n_exact_terms=0, preact=False,
+                 activation_fn='elu', fc_end=True, fc_nblocks=None, fc_idim=128, n_exact_terms=0, preact=False,
                  neumann_grad=True, grad_in_forward=False, first_resblock=True):
+        if fc_nblocks is None:
+            fc_nblocks = 2 if self._implicit else 4       # implicit_flow.py:280, resflow.py:281
         domains, codomains = _parse_vnorms(vnorms)
         ks = list(map(int, kernels.split('-')))
         assert len(domains) == len(ks)
@@ -188,10 +192,11 @@ class StackedImplicitBlocks(layers.SequentialFlow):
                          sn_atol=sn_atol, sn_rtol=sn_rtol, learn_p=False)
 
         def _resblock(as_fc, width=idim, first=True):
-            if as_fc:
-                return layers.imBlock(fc_net(width), fc_net(width), **block_kw)
             lead = (not first) and preact
-            return layers.imBlock(conv_branch(lead), conv_branch(lead), **block_kw)
+            net = (lambda: fc_net(width)) if as_fc else (lambda: conv_branch(lead))
+            if self._implicit:
+                return layers.imBlock(net(), net(), **block_kw)
+            return layers.iResBlock(net(), **block_kw)
 
         chain = []
         if init_layer is not None:
@@ -214,6 +219,9 @@ class StackedImplicitBlocks(layers.SequentialFlow):
                 if actnorm or fc_actnorm:
                     chain.append(_actnorm(initial_size, True))
         super(StackedImplicitBlocks, self).__init__(chain)
+
+
+ImplicitFlow._stack = StackedImplicitBlocks
 
 
 class FCNet(nn.Module):

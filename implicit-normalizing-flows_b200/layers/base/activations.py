@@ -1,14 +1,17 @@
 """Lipschitz activations of the residual branches, evaluated by the act_mul CUDA kernel.
 
 API mirror of lib/layers/base/activations.py (Sin :7-12, Swish :64-71, Identity :15-18,
-Zero :20-23).  Only the activations the hot-path configs use run custom kernels."""
+Zero :20-23, FullSort :25-28, MaxMin :31-38, LipschitzCube :41-44).  Only the activations the hot-path
+configs use (Sin, Swish, ReLU) run custom kernels; the group-sort / cube activations exist because the train
+scripts build their ACTIVATION_FNS tables from them at import (train_toy.py:27-30, train_tabular.py:29-32) and
+run as plain tensor expressions (a branch that uses one is evaluated through the module / autograd path)."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import ops
 
-__all__ = ['Sin', 'Swish', 'Identity', 'Zero', 'ReLU']
+__all__ = ['Sin', 'Swish', 'Identity', 'Zero', 'ReLU', 'FullSort', 'MaxMin', 'LipschitzCube']
 
 
 class Sin(nn.Module):
@@ -55,3 +58,25 @@ class Zero(nn.Module):
 
     def forward(self, x):
         return torch.zeros_like(x)
+
+
+class FullSort(nn.Module):
+    """Sort the features of every sample (1-Lipschitz, gradient-norm preserving)."""
+
+    def forward(self, x):
+        return torch.sort(x, 1)[0]
+
+
+class MaxMin(nn.Module):
+    """Pairs of neighbouring features -> (all maxima, all minima)."""
+
+    def forward(self, x):
+        pairs = x.view(x.shape[0], x.shape[1] // 2, 2)
+        return torch.cat([pairs.max(2)[0], pairs.min(2)[0]], 1)
+
+
+class LipschitzCube(nn.Module):
+    """x^3/3 inside (-1, 1), continued with slope 1 outside."""
+
+    def forward(self, x):
+        return torch.where(x >= 1, x - 2 / 3, torch.where(x <= -1, x + 2 / 3, x ** 3 / 3))

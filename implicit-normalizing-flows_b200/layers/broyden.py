@@ -75,7 +75,7 @@ def _result_dict(ws, state, shape, eps_scaled, threshold):
 def broyden_mlp(spec, x_embed, z0, threshold, eps):
     """Whole forward/inverse solve of x_embed - f(z) - z = 0 in ONE persistent cooperative kernel
     (csrc/mlp_solver.cu) for small-d MLP branches.  `spec` comes from BranchProgram.mlp_solver_spec():
-    (Wt list, bias list, dims, act_kind, beta_sp).  Same return dict as broyden()."""
+    (Wt list, bias list, dims, act_kind, per-layer softplus(beta) list or None).  Same return dict as broyden()."""
     _cabi.require_device(z0, 'broyden_mlp z0')
     lib = _cabi.load()
     Wt, bias, dims, act_kind, beta_sp = spec
@@ -95,9 +95,13 @@ def broyden_mlp(spec, x_embed, z0, threshold, eps):
     wt_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in Wt])
     b_arr = (ctypes.c_void_p * L)(*[(b.data_ptr() if b is not None else None) for b in bias])
     dims_arr = (ctypes.c_int * (L + 1))(*dims)
+    # one device scalar per activation: every Swish module owns its own learnable beta (activations.py:64-71)
+    beta_arr = None
+    if beta_sp is not None:
+        beta_arr = (ctypes.c_void_p * L)(*([_cabi.ptr(b, 'beta') for b in beta_sp] + [None] * (L - len(beta_sp))))
     xe = x_embed.reshape(B, d).contiguous()
     _cabi.check(lib.impflow_mlp_broyden_solve(
-        _cabi.ptr(xe), wt_arr, b_arr, dims_arr, L, act_kind, _cabi.ptr(beta_sp, 'beta', True), _cabi.ptr(ws.xa),
+        _cabi.ptr(xe), wt_arr, b_arr, dims_arr, L, act_kind, beta_arr, _cabi.ptr(ws.xa),
         _cabi.ptr(ws.ga), _cabi.ptr(ws.xb), _cabi.ptr(ws.gb), _cabi.ptr(ws.low_x), _cabi.ptr(ws.low_g),
         _cabi.ptr(ws.Ut), _cabi.ptr(ws.Vt), _cabi.ptr(ws.sample_sq), _cabi.ptr(ws.low_sq),
         ctypes.c_void_p(ws.partial_d.data_ptr()), ctypes.c_void_p(ws.state.data_ptr()), B, threshold,

@@ -11,6 +11,7 @@ import torch.nn as nn
 from torch.nn import Parameter
 
 from .. import ops
+from .extras import Normalize, ZeroMeanTransform  # noqa: F401  (lib/layers/elemwise.py exports them too)
 
 FUSED_ACTNORM = {'on': True}     # A/B switch: fused kernels against the plain tensor expressions
 

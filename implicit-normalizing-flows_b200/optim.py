@@ -51,7 +51,10 @@ class FusedAdam(torch.optim.Optimizer):
                 p.data = v
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
-        self.ema = self.flat_p.clone() if ema_decay is not None else None
+        # EMA shadow (lib/utils.py:126-146): the reference initialises it on the FIRST apply(), i.e. from the
+        # parameters AFTER the first optimiser step (and after any data-dependent init); later applies blend
+        self.ema = torch.zeros_like(self.flat_p) if ema_decay is not None else None
+        self._ema_started = False
         self.step_count = 0
         self.last_grad_norm_sq = None        # device scalar of the latest step (sqrt it to log the norm)
         self._ever_grad = [False] * len(self.bucket.params)
@@ -64,6 +67,11 @@ class FusedAdam(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         self.bucket.gather_strays()
         g = self.bucket.flat
+        base = self.flat_p.data_ptr()
+        for p, off in zip(self.bucket.params, self.bucket.offsets):
+            if p.data_ptr() != base + 4 * off:
+                raise RuntimeError('FusedAdam: a parameter no longer lives in the flat buffer (model.to() / .float() / '
+                                   'p.data = ... after the optimiser was built); build the optimiser last')
         self.step_count += 1
         group = self.param_groups[0]
         beta1, beta2 = group['betas']
@@ -75,9 +83,13 @@ class FusedAdam(torch.optim.Optimizer):
             self.last_grad_norm_sq = gsq
         _cabi.check(_cabi.load().impflow_clip_adam_ema(
             _cabi.ptr(self.flat_p), _cabi.ptr(g), _cabi.ptr(self.exp_avg), _cabi.ptr(self.exp_avg_sq),
-            _cabi.ptr(self.ema, 'ema', True), g.numel(), _cabi.ptr(gsq, 'gnorm_sq', True),
+            _cabi.ptr(self.ema if self._ema_started else None, 'ema', True), g.numel(),
+            _cabi.ptr(gsq, 'gnorm_sq', True),
             float(self.max_grad_norm or 0.0), float(step_size), float(beta1), float(beta2), float(group['eps']),
             float(self.ema_decay or 0.0), _cabi.stream()), 'clip_adam_ema')
+        if self.ema is not None and not self._ema_started:
+            self.ema.copy_(self.flat_p)          # first apply(): copy only (lib/utils.py:140-142)
+            self._ema_started = True
         # the kernel wrote through raw pointers: the host caches are keyed on the tensors' versions.  Parameters
         # that received no gradient (the roulette rates geom_p / lamb: the vendored Adam skips them,
         # lib/optimizers.py:70-72) keep value and version — a zero gradient leaves them bit-identical here too —
@@ -86,6 +98,53 @@ class FusedAdam(torch.optim.Optimizer):
         self._ever_grad = [e or h for e, h in zip(self._ever_grad, self.bucket.had_grad)]
         torch.autograd.graph.increment_version([p for p, e in zip(self.bucket.params, self._ever_grad) if e])
         return loss
+
+    # ---- checkpointing: the layout of torch.optim / lib.optimizers.Adam state dicts (train_img.py:846,854:
+    # 'optimizer_state_dict'), so a checkpoint written by the reference's Adam loads here and vice versa; the EMA
+    # shadow travels under the extra key 'impflow_ema' (the reference pickles its EMA object separately)
+    def _views(self, flat):
+        return [flat[off:off + p.numel()].view_as(p) for p, off in zip(self.bucket.params, self.bucket.offsets)]
+
+    def ema_params(self):
+        """EMA shadow of every optimised parameter (views, parameter order), or None before the first step."""
+        return self._views(self.ema) if (self.ema is not None and self._ema_started) else None
+
+    def _publish_state(self):
+        self.state.clear()
+        if self.step_count > 0:
+            for p, m, v in zip(self.bucket.params, self._views(self.exp_avg), self._views(self.exp_avg_sq)):
+                self.state[p] = {'step': self.step_count, 'exp_avg': m, 'exp_avg_sq': v}
+
+    def state_dict(self):
+        self._publish_state()
+        sd = super(FusedAdam, self).state_dict()
+        ema = self.ema_params()
+        sd['impflow_ema'] = None if ema is None else [e.clone() for e in ema]
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        ema = state_dict.pop('impflow_ema', None)
+        super(FusedAdam, self).load_state_dict(state_dict)
+        steps = []
+        for p, m, v in zip(self.bucket.params, self._views(self.exp_avg), self._views(self.exp_avg_sq)):
+            st = self.state.get(p)
+            if st:
+                m.copy_(st['exp_avg'])
+                v.copy_(st['exp_avg_sq'])
+                steps.append(int(st['step']))
+            else:              # the vendored Adam keeps no state for parameters that never had a gradient
+                m.zero_()
+                v.zero_()
+        self.step_count = max(steps) if steps else 0
+        self._ever_grad = [bool(self.state.get(p)) for p in self.bucket.params]
+        self._publish_state()
+        if self.ema is not None:
+            self._ema_started = ema is not None
+            if ema is not None:
+                for dst, src in zip(self._views(self.ema), ema):
+                    dst.copy_(src)
 
     def grad_norm(self):
         """||g|| before clipping of the latest step, as a device scalar (what clip_grad_norm_ returns)."""

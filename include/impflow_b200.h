@@ -95,13 +95,15 @@ int impflow_broyden_step(float* x_old, const float* g_old, const float* xn, cons
  * rank-1 updates — replacing the host-driven loop of broyden.py:123-193 + implicit_block.py:68-80.
  *   Wt[l]  : DEVICE pointer to the transposed effective weight [dims[l]][dims[l+1]] (HOST array of L)
  *   bias[l]: DEVICE pointer or NULL (HOST array of L, or NULL)
+ *   beta_sp[l]: DEVICE scalar softplus(beta) of the LipSwish module behind layer l, l < L-1 (HOST array of L-1
+ *            pointers; every Swish owns its own learnable beta, activations.py:64-71); NULL for Sin / ReLU
  *   za     : start point z0 (B,d) on entry; za/ga/zb/gb are (B,d) scratch afterwards
  *   low_z  : best iterate on return; state: as in impflow_broyden_step
  *   partial: impflow_mlp_solver_partial_doubles() doubles of workspace */
 int impflow_mlp_solver_limits(int* max_layers, int* max_width, int* max_d);
 size_t impflow_mlp_solver_partial_doubles(void);
 int impflow_mlp_broyden_solve(const float* x_embed, const float* const* Wt, const float* const* bias,
-                              const int* dims, int L, int act_kind, const float* beta_sp, float* za, float* ga,
+                              const int* dims, int L, int act_kind, const float* const* beta_sp, float* za, float* ga,
                               float* zb, float* gb, float* low_z, float* low_g, float* Ut, float* Vt,
                               float* sample_sq, float* low_sq, double* partial, impflow_broyden_state* state,
                               int B, int threshold, double eps_scaled, void* stream);

@@ -442,6 +442,19 @@ def batch_jacobian(g, x, create_graph=True):
     return torch.cat(rows, 1)
 
 
+def logdet_exact_trace(g, x, coeffs):
+    """Power series with the exact trace of the Jacobian powers (implicit_block.py:327-343,
+    iresblock.py:147-158): tr(J) + sum_{k>=2} (-1)^(k+1)/k coeff(k) tr(J^k)."""
+    J = batch_jacobian(g, x)
+    tr = lambda M: M.view(M.shape[0], -1)[:, ::M.shape[1] + 1].sum(1)
+    out = tr(J)
+    Jk = J
+    for k in range(2, len(coeffs) + 1):
+        Jk = torch.bmm(J, Jk)
+        out = out + (-1) ** (k + 1) / k * coeffs[k - 1] * tr(Jk)
+    return out
+
+
 def logdetgrad(net_x, net_z, z, x, cfg, training, n_draws=None, probes=None):
     """``imBlock._logdetgrad`` (implicit_block.py:245-350) for the branches the configs use:
     brute force (d<=10, eval or brute_force flag) and Hutchinson roulette (basic / Neumann,
@@ -466,6 +479,11 @@ def logdetgrad(net_x, net_z, z, x, cfg, training, n_draws=None, probes=None):
                 n_draws = draw_n(cfg['n_dist'], cfg['n_samples'], cfg.get('geom_p', 0.5), cfg.get('lamb', 2.0))
             _, coeffs = roulette_coefficients(n_draws, cfg['n_exact_terms_test'], cfg['n_dist'],
                                               cfg.get('geom_p', 0.5), cfg.get('lamb', 2.0))
+        if cfg.get('exact_trace'):
+            x = x.requires_grad_(True)
+            z = z.requires_grad_(True)
+            ld = logdet_exact_trace(net_x(x), x, coeffs) - logdet_exact_trace(net_z(z), z, coeffs)
+            return ld.view(-1, 1), n_draws, None
         if probes is None:
             vx = rademacher_like(x)
             vz = rademacher_like(z)
@@ -550,6 +568,102 @@ def imblock_inverse(net_x, net_z, z, cfg, stats=None):
     return x
 
 
+# --------------------------------------------------------------------------------------
+# iResBlock  (lib/layers/iresblock.py:54-164, 186-235)
+# --------------------------------------------------------------------------------------
+
+
+class _MemEffLogDetWithOutput(torch.autograd.Function):
+    """The iResBlock flavour of ``MemoryEfficientLogDetEstimator`` (iresblock.py:186-235): also returns g
+    and, in backward, adds the vjp of grad_g through the kept graph to the scaled stored gradients."""
+
+    @staticmethod
+    def forward(ctx, est, net, x, coeffs, vareps, training, *params):
+        ctx.training = training
+        with torch.enable_grad():
+            x = x.detach().requires_grad_(True)
+            g = net(x)
+            ctx.g, ctx.x = g, x
+            val = est(g, x, coeffs, vareps, training)
+            if training:
+                gx, *gp = torch.autograd.grad(val.sum(), (x,) + params, retain_graph=True, allow_unused=True)
+                if gx is None:
+                    gx = torch.zeros_like(x)
+                ctx.params = params
+                ctx.stored = (gx, gp)
+        return g.detach().requires_grad_(g.requires_grad), val.detach().requires_grad_(val.requires_grad)
+
+    @staticmethod
+    def backward(ctx, grad_g, grad_val):
+        if not ctx.training:
+            raise ValueError('Provide training=True if using backward.')
+        gx, gp = ctx.stored
+        with torch.enable_grad():
+            dg_x, *dg_p = torch.autograd.grad(ctx.g, [ctx.x] + list(ctx.params), grad_g, allow_unused=True)
+        dL = grad_val[0].detach()
+        with torch.no_grad():
+            gx = gx * dL + dg_x
+            out = []
+            for d, j in zip(dg_p, gp):
+                j = None if j is None else j * dL
+                out.append(d if j is None else (j if d is None else d + j))
+        return (None, None, gx, None, None, None) + tuple(out)
+
+
+def ires_logdetgrad(net, x, cfg, training, n_draws=None, probe=None):
+    """``iResBlock._logdetgrad`` (iresblock.py:81-164): returns (g(x), logdet (B,1), n_draws, probe).
+    2x2 closed form when d == 2 (brute_force flag or eval); eval uses 20 exact terms; Gaussian probe."""
+    with torch.enable_grad():
+        if (cfg['brute_force'] or not training) and (x.ndimension() == 2 and x.shape[1] == 2):
+            x = x.requires_grad_(True)
+            g = net(x)
+            J = batch_jacobian(g, x)
+            det = (J[:, 0, 0] + 1) * (J[:, 1, 1] + 1) - J[:, 0, 1] * J[:, 1, 0]
+            return g, torch.log(torch.abs(det)).view(-1, 1), None, None
+        if training and cfg.get('n_power_series') is not None:
+            coeffs = [1.] * cfg['n_power_series']
+        else:
+            if n_draws is None:
+                n_draws = draw_n(cfg['n_dist'], cfg['n_samples'], cfg.get('geom_p', 0.5), cfg.get('lamb', 2.0))
+            _, coeffs = roulette_coefficients(n_draws, cfg['n_exact_terms'] if training else 20, cfg['n_dist'],
+                                              cfg.get('geom_p', 0.5), cfg.get('lamb', 2.0))
+        if cfg.get('exact_trace'):
+            x = x.requires_grad_(True)
+            g = net(x)
+            return g, logdet_exact_trace(g, x, coeffs).view(-1, 1), n_draws, None
+        if probe is None:
+            probe = torch.randn_like(x)
+        est = logdet_neumann if (training and cfg['neumann_grad']) else logdet_basic
+        if training and cfg['grad_in_forward']:
+            g, ld = _MemEffLogDetWithOutput.apply(est, net, x, coeffs, probe, training, *net.parameters())
+        else:
+            x = x.requires_grad_(True)
+            g = net(x)
+            ld = est(g, x, coeffs, probe, training)
+        return g, ld.view(-1, 1), n_draws, probe
+
+
+def ires_forward(net, x, logpx, cfg, training=True, n_draws=None, probe=None):
+    """``iResBlock.forward`` (iresblock.py:54-60)."""
+    if logpx is None:
+        return x + net(x)
+    g, ld, _, _ = ires_logdetgrad(net, x, cfg, training, n_draws, probe)
+    return x + g, logpx - ld
+
+
+def ires_inverse(net, y, atol=1e-5, rtol=1e-5):
+    """``iResBlock._inverse_fixed_point`` (iresblock.py:69-79): returns (x, iterations)."""
+    x, x_prev = y - net(y), y
+    i = 0
+    tol = atol + y.abs() * rtol
+    while not torch.all((x - x_prev) ** 2 / tol < 1):
+        x, x_prev = y - net(x), x
+        i += 1
+        if i > 1000:
+            break
+    return x, i
+
+
 DEFAULT_CFG = dict(brute_force=False, n_dist='geometric', n_samples=1, n_exact_terms=2, n_exact_terms_test=20,
                    n_power_series=None, neumann_grad=True, grad_in_forward=True, eps_forward=1e-6,
                    eps_backward=1e-10, eps_sample=1e-5, threshold=30, geom_p=0.5, lamb=2.0)
@@ -602,7 +716,9 @@ def clip_adam_ema_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas, eps,
                        ema_decay=None):
     """One step of train_img.py:652-658 on lists of tensors (updated in place): clip_grad_norm_ over all
     gradients, the vendored Adam (denom = sqrt(v) + eps; step = lr * sqrt(1-b2^t) / (1-b1^t); its weight-decay
-    line is a no-op) and ExponentialMovingAverage.apply (shadow += (1 - decay) * (param - shadow))."""
+    line is a no-op) and ExponentialMovingAverage.apply: the FIRST apply() only copies the (already updated)
+    parameters into the shadow (lib/utils.py:140-142), later ones do shadow -= (1 - decay) * (shadow - param)
+    (:143-146).  Pinned by tests/golden/step_tail.npz."""
     with torch.no_grad():
         if max_norm is not None:
             total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
@@ -616,4 +732,7 @@ def clip_adam_ema_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas, eps,
             v.mul_(b2).addcmul_(g, g, value=1 - b2)
             p.addcdiv_(m, v.sqrt().add_(eps), value=-step_size)
             if ema is not None:
-                ema[i].add_((1 - ema_decay) * (p - ema[i]))
+                if step == 1:
+                    ema[i].copy_(p)
+                else:
+                    ema[i].sub_((1 - ema_decay) * (ema[i] - p))

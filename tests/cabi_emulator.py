@@ -242,7 +242,7 @@ class EmulatedLib(object):
                                   Ut, Vt, sample_sq, low_sq, partial, state, B, T, eps, stream):
         dims = [int(v) for v in dims]
         d = dims[0]
-        beta = _beta(beta_sp)
+        betas = [(_beta(beta_sp[l]) if (beta_sp and l + 1 < L and beta_sp[l]) else None) for l in range(L)]
         Ws = [_f32(Wt[l], dims[l] * dims[l + 1]).reshape(dims[l], dims[l + 1]) for l in range(L)]
         bs = [(_f32(bias[l], dims[l + 1]) if bias[l] else None) for l in range(L)]
         xe = _f32(x_embed, B * d).reshape(B, d)
@@ -254,7 +254,7 @@ class EmulatedLib(object):
                 if bs[l] is not None:
                     h = h + bs[l]
                 if l + 1 < L:
-                    h = _act(act_kind, h, 0, beta).astype(np.float32)
+                    h = _act(act_kind, h, 0, betas[l]).astype(np.float32)
             return h
 
         bufs = {'x': za, 'g': ga, 'xn': zb, 'gn': gb}
@@ -358,7 +358,7 @@ class EmulatedLib(object):
         P[:] = P - f(step_size) * M / (np.sqrt(V) + f(eps))
         if _addr(ema) is not None:
             E = _f32(ema, n)
-            E[:] = f(ema_decay) * E + f(1 - ema_decay) * P
+            E[:] = E - f(1 - ema_decay) * (E - P)
         self.launches += 1
         return 0
 

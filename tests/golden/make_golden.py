@@ -447,11 +447,269 @@ def gen_flow():
     save('flow_small', **out)
 
 
+# ----------------------------------------------------------------------------------------------
+# 7. iResBlock (lib/layers/iresblock.py): forward / log-det estimators / fixed-point inverse
+# ----------------------------------------------------------------------------------------------
+
+def run_ires(tag, blk, x, seed, out, weight_perturb=None):
+    """One training step (log-det estimate + gradients), the eval-mode estimate and the fixed-point inverse."""
+    if weight_perturb:
+        with torch.no_grad():
+            for n, p in blk.named_parameters():
+                if n.endswith('weight') and p.requires_grad:
+                    p.mul_(weight_perturb)
+    blk.train()
+    for k, v in sd_np(blk).items():
+        out[tag + '_sd_' + k] = v
+    xg = x.clone().requires_grad_(True)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    y, dlogp = blk(xg, torch.zeros(x.shape[0], 1))
+    logpy = std_normal_logprob(y).view(y.size(0), -1).sum(1, keepdim=True)
+    loss = -(logpy - dlogp).mean()
+    loss.backward()
+    out[tag + '_x'], out[tag + '_y'], out[tag + '_dlogp'] = x.numpy(), y.detach().numpy(), dlogp.detach().numpy()
+    out[tag + '_loss'] = np.array(loss.item())
+    out[tag + '_grad_x'] = xg.grad.numpy()
+    for n, p in blk.named_parameters():
+        if p.grad is not None:
+            out[tag + '_grad_' + n] = p.grad.numpy()
+    out[tag + '_n_draws'] = blk.last_n_samples.numpy().copy()
+    torch.manual_seed(seed)
+    out[tag + '_vareps'] = torch.randn_like(x).numpy()          # the Gaussian probe _logdetgrad drew (:129)
+    out[tag + '_seed'] = np.array(seed)
+    # eval mode: 20 exact terms, basic estimator, no graph
+    blk.eval()
+    np.random.seed(seed + 1)
+    torch.manual_seed(seed + 1)
+    rate = torch.sigmoid(blk.geom_p).item() if blk.n_dist == 'geometric' else blk.lamb.item()
+    ye, dlogpe = blk(x.clone(), torch.zeros(x.shape[0], 1))
+    out[tag + 'eval_y'], out[tag + 'eval_dlogp'] = ye.detach().numpy(), dlogpe.detach().numpy()
+    np.random.seed(seed + 1)
+    draw = np.random.geometric(rate, blk.n_samples) if blk.n_dist == 'geometric' else np.random.poisson(rate, blk.n_samples)
+    out[tag + 'eval_n_draws'] = draw.astype(np.float32)
+    torch.manual_seed(seed + 1)
+    out[tag + 'eval_vareps'] = torch.randn_like(x).numpy()
+    with torch.no_grad():
+        x_rec = blk.inverse(y.detach())
+    out[tag + '_x_rec'] = x_rec.numpy()
+    print(tag, 'dlogp[:2]', dlogp.detach().flatten()[:2].numpy(), 'eval', dlogpe.detach().flatten()[:2].numpy(),
+          'n', blk.last_n_samples.numpy(), 'rec err', float((x_rec - x).abs().max()))
+
+
+def gen_ires():
+    out = {}
+    torch.manual_seed(40)
+    np.random.seed(40)
+    # train_toy.py:205-223 --arch iresnet: d=2, closed-form 2x2 determinant
+    blk = layers.iResBlock(build_mlp([2, 32, 32, 2], 0.9, 20, None, 2), n_dist='geometric', brute_force=True,
+                           n_samples=1, neumann_grad=False, grad_in_forward=False)
+    run_ires('mlp2', blk, torch.rand(50, 2) * 4 - 2, 41, out, weight_perturb=300.)
+    # basic estimator with the double-backward training gradient, geometric roulette
+    torch.manual_seed(42)
+    blk = layers.iResBlock(build_mlp([6, 64, 64, 6], 0.9, None, 1e-3, 6), n_dist='geometric', n_samples=1,
+                           n_exact_terms=2, neumann_grad=False, grad_in_forward=False)
+    run_ires('mlp6', blk, torch.randn(40, 6), 43, out, weight_perturb=300.)
+    # Neumann gradient estimator + memory-efficient backward (the variant that also returns g, :186-235)
+    torch.manual_seed(44)
+    blk = layers.iResBlock(build_mlp([6, 64, 64, 6], 0.9, None, 1e-3, 6), n_dist='poisson', n_samples=2,
+                           n_exact_terms=3, neumann_grad=True, grad_in_forward=True)
+    run_ires('mlp6n', blk, torch.randn(40, 6), 45, out, weight_perturb=300.)
+    # conv branch of the image flows (resflow.py:344-392), Neumann + memory-efficient
+    torch.manual_seed(46)
+    c, idim, hw, B = 4, 32, 8, 4
+    blk = layers.iResBlock(build_conv_branch(c, idim, 0.9, 1e-3, True), n_dist='poisson', n_samples=1,
+                           n_exact_terms=3, neumann_grad=True, grad_in_forward=True)
+    x = torch.randn(B, c, hw, hw)
+    with torch.no_grad():
+        blk(x)                      # lazy u / v shaping
+    run_ires('conv', blk, x, 47, out)
+    save('iresblock', **out)
+
+
+# ----------------------------------------------------------------------------------------------
+# 8. imBlock branches the shipped configs do not reach: Banach fallback after a protective break
+#    (implicit_block.py:17-28,74-75), exact_trace (:327-343), n_samples > 1, fixed n_power_series, FCNet
+# ----------------------------------------------------------------------------------------------
+
+class Affine(torch.nn.Module):
+    """y = a * x: a deterministic stand-in branch (no parameters)."""
+
+    def __init__(self, a):
+        super(Affine, self).__init__()
+        self.a = a
+
+    def forward(self, x):
+        return self.a * x
+
+
+class Cliff(torch.nn.Module):
+    """-0.5 z on z > -1 (where the Banach iteration lives), a 1e8-steep wall below: Broyden's first step from
+    zeros, z1 = -g(0) = -x_embed (quirk #1), lands behind the wall and trips the 1e6 protective break."""
+
+    def forward(self, z):
+        return torch.where(z > -1, -0.5 * z, -0.5 * z + 1e8 * (z + 1))
+
+
+def gen_edge():
+    out = {}
+    # --- Banach fallback
+    blk = layers.imBlock(Affine(0.1), Cliff())
+    x = torch.rand(6, 5) * 2 + 2
+    info = {}
+    orig = ref_broyden_mod.broyden
+
+    def spy(g, x0, threshold, eps, ls=False, name='unknown'):
+        res = orig(g, x0, threshold, eps, ls=ls, name=name)
+        info.update(nstep=res['nstep'], prot=res['prot_break'])
+        return res
+    ref_imblock_mod.broyden = spy
+    try:
+        with torch.no_grad():
+            z = blk(x)
+    finally:
+        ref_imblock_mod.broyden = orig
+    assert info['prot'], 'the case must trip the protective break'
+    out['banach_x'], out['banach_z'] = x.numpy(), z.numpy()
+    out['banach_ints'] = np.array([info['nstep'], int(info['prot'])], dtype=np.int64)
+    print('banach: nstep', info['nstep'], 'prot', info['prot'], 'residual',
+          float((z + Cliff()(z) - x - 0.1 * x).abs().max()))
+
+    # --- exact trace (Jacobian powers), training
+    torch.manual_seed(50)
+    np.random.seed(50)
+    blk = layers.imBlock(build_mlp([6, 32, 32, 6], 0.9, None, 1e-3, 6), build_mlp([6, 32, 32, 6], 0.9, None, 1e-3, 6),
+                         n_dist='geometric', exact_trace=True, n_samples=1, n_exact_terms=2, neumann_grad=False,
+                         grad_in_forward=False, eps_forward=1e-5)
+    run_block('exact', blk, torch.randn(16, 6), 51, True, out, weight_perturb=300.)
+    # --- three roulette samples per call
+    torch.manual_seed(52)
+    np.random.seed(52)
+    blk = layers.imBlock(build_mlp([12, 32, 32, 12], 0.9, None, 1e-3, 12),
+                         build_mlp([12, 32, 32, 12], 0.9, None, 1e-3, 12), n_dist='geometric', n_samples=3,
+                         n_exact_terms=2, neumann_grad=False, grad_in_forward=False, eps_forward=1e-5)
+    run_block('ns3', blk, torch.randn(16, 12), 53, True, out, weight_perturb=300.)
+    # --- truncated series (biased), Neumann + memory-efficient
+    torch.manual_seed(54)
+    np.random.seed(54)
+    blk = layers.imBlock(build_mlp([12, 32, 32, 12], 0.9, None, 1e-3, 12),
+                         build_mlp([12, 32, 32, 12], 0.9, None, 1e-3, 12), n_dist='poisson', n_power_series=4,
+                         neumann_grad=True, grad_in_forward=True, eps_forward=1e-5)
+    run_block('nps', blk, torch.randn(16, 12), 55, True, out, weight_perturb=300.)
+    # --- FC tail block (implicit_flow.py:321-356,430-433): FCNet branches on an image-shaped input
+    from lib.implicit_flow import FCNet
+    torch.manual_seed(56)
+    np.random.seed(56)
+    shape = (2, 4, 4)
+    fc = lambda: FCNet(input_shape=shape, idim=24, lipschitz_layer=base_layers.get_linear, nhidden=2, coeff=0.9,
+                       domains=[2., 2., 2.], codomains=[2., 2., 2.], n_iterations=None, activation_fn='swish',
+                       preact=True, dropout=0, sn_atol=1e-3, sn_rtol=1e-3, learn_p=False)
+    blk = layers.imBlock(fc(), fc(), n_dist='poisson', n_samples=1, n_exact_terms=3, neumann_grad=True,
+                         grad_in_forward=True)
+    run_block('fc', blk, torch.randn(8, *shape), 57, True, out, weight_perturb=3.)
+    save('imblock_edge', **out)
+
+
+# ----------------------------------------------------------------------------------------------
+# 9. step tail: clip_grad_norm_ + lib/optimizers.Adam + utils.ExponentialMovingAverage (train_img.py:652-658)
+# ----------------------------------------------------------------------------------------------
+
+def gen_step_tail():
+    import lib.optimizers as ref_optim
+    import lib.utils as ref_utils
+    out = {}
+    torch.manual_seed(60)
+    shapes = [(8, 3, 3, 3), (8,), (7, 5), (1,), (16, 8, 1, 1)]
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super(Holder, self).__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*s)) for s in shapes])
+    m = Holder()
+    opt = ref_optim.Adam(m.parameters(), lr=1e-2, betas=(0.9, 0.99), weight_decay=1e-3)   # decay line is a no-op
+    ema = ref_utils.ExponentialMovingAverage(m, decay=0.9)
+    for i, p in enumerate(m.ps):
+        out['p0_%d' % i] = p.detach().numpy().copy()
+    n_steps = 4
+    for t in range(n_steps):
+        opt.zero_grad()
+        for i, p in enumerate(m.ps):
+            g = torch.randn(*shapes[i]) * (3.0 if t % 2 == 0 else 0.01)          # clipped and unclipped steps
+            out['g%d_%d' % (t, i)] = g.numpy().copy()
+            p.grad = g.clone()
+        total = torch.nn.utils.clip_grad.clip_grad_norm_(m.parameters(), 1.)
+        opt.step()
+        ema.apply()
+        out['gnorm%d' % t] = np.array(float(total))
+        for i, p in enumerate(m.ps):
+            out['p%d_%d' % (t + 1, i)] = p.detach().numpy().copy()
+            out['ema%d_%d' % (t + 1, i)] = ema.shadow_params['ps.%d' % i].numpy().copy()
+    out['meta'] = np.array([n_steps, len(shapes), 1e-2, 0.9, 0.99, 1e-8, 1.0, 0.9], dtype=np.float64)
+    save('step_tail', **out)
+
+
+# ----------------------------------------------------------------------------------------------
+# 10. how reproducible are the reference's own implicit-backward iteration counts?  The backward solves run
+#     with eps_backward = 1e-10 * sqrt(B d), below fp32 round-off, so the count depends on the summation order
+#     of the BLAS kernels.  Re-run the stored fixtures' training step with 1 / 2 / 4 / 8 intra-op threads.
+# ----------------------------------------------------------------------------------------------
+
+def gen_bwd_band():
+    out = {}
+    fxm, fxc, fxe = (dict(np.load(os.path.join(HERE, n + '.npz'))) for n in ('imblock_mlp', 'imblock_conv',
+                                                                              'imblock_edge'))
+    cases = []
+    mk_mlp = lambda dims, n_it, tol, **kw: layers.imBlock(build_mlp(dims, 0.99, n_it, tol, dims[0]),
+                                                          build_mlp(dims, 0.99, n_it, tol, dims[0]), **kw)
+    cases.append(('toy', fxm, lambda: mk_mlp([2, 32, 32, 2], 20, None, n_dist='geometric', brute_force=True,
+                                             n_samples=1, neumann_grad=False, grad_in_forward=False)))
+    for tag, d in (('tab6', 6), ('tab43', 43)):
+        cases.append((tag, fxm, lambda d=d: mk_mlp([d, 64, 64, d], None, 1e-3, n_dist='geometric', n_samples=1,
+                                                   n_exact_terms=2, neumann_grad=False, grad_in_forward=False,
+                                                   eps_forward=1e-5)))
+    cases.append(('cifar', fxc, lambda: layers.imBlock(
+        build_conv_branch(4, 32, 0.9, 1e-3, True), build_conv_branch(4, 32, 0.9, 1e-3, True), n_dist='poisson',
+        n_samples=1, n_exact_terms=3, neumann_grad=True, grad_in_forward=True)))
+    cases.append(('cifar_basic', fxc, lambda: layers.imBlock(
+        build_conv_branch(4, 32, 0.9, 1e-3, False), build_conv_branch(4, 32, 0.9, 1e-3, False), n_dist='poisson',
+        n_samples=1, n_exact_terms=3, neumann_grad=False, grad_in_forward=False)))
+    old_threads = torch.get_num_threads()
+    for tag, fx, make in cases:
+        counts = []
+        for nt in (1, 2, 4, 8):
+            torch.set_num_threads(nt)
+            blk = make()
+            x = torch.from_numpy(fx[tag + '_x'])
+            with torch.no_grad():
+                blk(x, restore=True)
+            sd = {k[len(tag + '_sd_'):]: torch.from_numpy(v) for k, v in fx.items() if k.startswith(tag + '_sd_')}
+            blk.load_state_dict(sd, strict=True)
+            blk.train()
+            seed = int(fx[tag + '_seed'])
+            np.random.seed(seed)
+            torch.manual_seed(seed)
+            xg = x.clone().requires_grad_(True)
+            with SolveRecorder() as rec:
+                z, dlogp = blk(xg, torch.zeros(x.shape[0], 1))
+                loss = -(std_normal_logprob(z).view(z.size(0), -1).sum(1, keepdim=True) - dlogp).mean()
+                loss.backward()
+            counts.append([int(rec.nsteps('forward')[0]), int(rec.nsteps('backward')[0])])
+        out[tag + '_threads'] = np.array([1, 2, 4, 8])
+        out[tag + '_fwd_bwd_nstep'] = np.array(counts, dtype=np.int64)
+        print(tag, 'fwd/bwd nstep by thread count', counts)
+    torch.set_num_threads(old_threads)
+    save('bwd_band', **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['broyden', 'mlp', 'conv', 'norm', 'act', 'flow']
+    which = sys.argv[1:] or ['broyden', 'mlp', 'conv', 'norm', 'act', 'flow', 'ires', 'edge', 'tail', 'band']
     if 'broyden' in which: gen_broyden()
     if 'mlp' in which: gen_imblock_mlp()
     if 'conv' in which: gen_imblock_conv()
     if 'norm' in which: gen_induced_norm()
     if 'act' in which: gen_activations()
     if 'flow' in which: gen_flow()
+    if 'ires' in which: gen_ires()
+    if 'edge' in which: gen_edge()
+    if 'tail' in which: gen_step_tail()
+    if 'band' in which: gen_bwd_band()

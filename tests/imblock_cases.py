@@ -493,3 +493,242 @@ def case_actnorm_fused_matches_expression():
                     continue
                 scale = max(float(v.abs().max()), 1e-30)
                 assert float((u - v).abs().max()) / scale < 5e-6
+
+
+def case_mlp_solver_per_layer_beta():
+    """Every Swish module owns its learnable beta (activations.py:64-71): the persistent small-d solver must
+    evaluate layer l's activation with layer l's beta (regression: it used the first one for all).  Forward and
+    inverse solves of an MLP imBlock with diverged betas, persistent kernel vs the host-driven loop."""
+    pkg = _pkg()
+    layers = pkg.layers
+    from impflow_b200.layers import implicit_block
+    dev = DEV['device']
+    torch.manual_seed(21)
+    d, dims = 6, [6, 32, 32, 32, 6]
+
+    def net():
+        mods = []
+        for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+            if i > 0:
+                mods.append(layers.base.Swish())
+            mods.append(layers.base.get_linear(a, b, coeff=0.9, n_iterations=None, atol=1e-3, rtol=1e-3, domain=2,
+                                               codomain=2))
+        return torch.nn.Sequential(*mods)
+    blk = layers.imBlock(net(), net(), n_dist='geometric', neumann_grad=False, grad_in_forward=False,
+                         eps_forward=1e-6).to(dev)
+    with torch.no_grad():
+        betas = [m.beta for m in blk.modules() if isinstance(m, layers.base.Swish)]
+        for i, b in enumerate(betas):
+            b.fill_(-1.5 + 1.1 * i)                   # softplus(beta) from 0.2 to > 4
+        for n, p in blk.named_parameters():
+            if n.endswith('weight') and p.requires_grad:
+                p.mul_(4.0)
+        layers.base.update_lipschitz(blk)
+    blk.eval()
+    x = torch.randn(64, d, device=dev)
+    outs = {}
+    for persistent in (True, False):
+        implicit_block.PERSISTENT_MLP['on'] = persistent
+        try:
+            with torch.no_grad():
+                z = blk(x)
+                xr = blk.inverse(z)
+            outs[persistent] = (z.cpu(), xr.cpu(), blk.solver_stats['fwd']['nstep'], blk.solver_stats['inv']['nstep'])
+        finally:
+            implicit_block.PERSISTENT_MLP['on'] = True
+    a, b = outs[True], outs[False]
+    assert a[2] == b[2] and a[3] == b[3], (a[2:], b[2:])
+    assert rel_err(a[0], b[0]) < 1e-5 and rel_err(a[1], b[1]) < 1e-5
+    assert rel_err(a[1], x.cpu()) < 1e-3
+    # and the solved point really satisfies the block equation of the *module* networks
+    with torch.no_grad():
+        res = a[0].to(dev) + blk.nnet_z(a[0].to(dev)) - x - blk.nnet_x(x)
+    assert float(res.norm()) < 1e-4 * float(x.norm())
+
+
+# ---- round 2: iResBlock, the imBlock branches no shipped config reaches, the step tail against the reference ----
+
+IRES = {
+    'mlp2': dict(dims=[2, 32, 32, 2], n_it=20, tol=None, kw=dict(n_dist='geometric', brute_force=True, n_samples=1,
+                                                                 neumann_grad=False, grad_in_forward=False)),
+    'mlp6': dict(dims=[6, 64, 64, 6], n_it=None, tol=1e-3, kw=dict(n_dist='geometric', n_samples=1, n_exact_terms=2,
+                                                                   neumann_grad=False, grad_in_forward=False)),
+    'mlp6n': dict(dims=[6, 64, 64, 6], n_it=None, tol=1e-3, kw=dict(n_dist='poisson', n_samples=2, n_exact_terms=3,
+                                                                    neumann_grad=True, grad_in_forward=True)),
+    'conv': dict(dims=None, kw=dict(n_dist='poisson', n_samples=1, n_exact_terms=3, neumann_grad=True,
+                                    grad_in_forward=True)),
+}
+
+
+# @parametrize('tag', list(IRES))
+def case_iresblock(golden, tag):
+    """iResBlock (lib/layers/iresblock.py:54-164,186-235) against fixtures of the reference: training step with the
+    roulette draw and the Gaussian probe injected (y, log-det, loss, all gradients), the eval-mode estimate
+    (20 exact terms / 2x2 closed form) and the fixed-point inverse."""
+    pkg = _pkg()
+    layers = pkg.layers
+    fx = golden('iresblock')
+    c = IRES[tag]
+    dvc = DEV['device']
+    if c['dims'] is None:
+        net = build_conv_branch(layers, 4, 32, 0.9, 1e-3, True)
+    else:
+        net = build_mlp(layers, c['dims'], 0.9, c['n_it'], c['tol'], c['dims'][0])
+    blk = layers.iResBlock(net, **c['kw']).to(dvc)
+    x0 = torch.from_numpy(fx[tag + '_x']).to(dvc)
+    with torch.no_grad():
+        blk(x0)                      # lazy u / v shaping
+    sd = {k: v.to(dvc) for k, v in sub_sd(fx, tag + '_sd_').items()}
+    missing, unexpected = blk.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    blk.train()
+    blk._inject_n = fx[tag + '_n_draws'].astype(np.int64)
+    blk._inject_probes = torch.from_numpy(fx[tag + '_vareps'])
+    x = x0.clone().requires_grad_(True)
+    y, dlogp = blk(x, torch.zeros(x.shape[0], 1, device=dvc))
+    loss = -(std_normal_logprob(y).reshape(y.size(0), -1).sum(1, keepdim=True) - dlogp).mean()
+    loss.backward()
+    assert rel_err(y.detach().cpu(), fx[tag + '_y']) < 1e-5
+    assert rel_err(dlogp.detach().cpu(), fx[tag + '_dlogp']) < 1e-4
+    np.testing.assert_allclose(loss.item(), fx[tag + '_loss'], rtol=1e-5)
+    assert rel_err(x.grad.cpu(), fx[tag + '_grad_x']) < 2e-3
+    worst = 0.0
+    for n, p in blk.named_parameters():
+        key = tag + '_grad_' + n
+        if key in fx and np.linalg.norm(fx[key]) > 1e-7:
+            assert p.grad is not None, n
+            worst = max(worst, rel_err(p.grad.cpu(), fx[key]))
+    assert worst < 5e-3, worst
+    if c['kw'].get('brute_force') is not True:
+        np.testing.assert_array_equal(blk.last_n_samples.cpu().numpy(), fx[tag + '_n_draws'])
+    blk.eval()
+    blk._inject_n = fx[tag + 'eval_n_draws'].astype(np.int64)
+    blk._inject_probes = torch.from_numpy(fx[tag + 'eval_vareps'])
+    ye, dle = blk(x0.clone(), torch.zeros(x.shape[0], 1, device=dvc))
+    assert rel_err(ye.detach().cpu(), fx[tag + 'eval_y']) < 1e-5
+    assert rel_err(dle.detach().cpu(), fx[tag + 'eval_dlogp']) < 1e-4
+    with torch.no_grad():
+        x_rec = blk.inverse(torch.from_numpy(fx[tag + '_y']).to(dvc))
+    assert rel_err(x_rec.cpu(), fx[tag + '_x_rec']) < 1e-5
+    assert rel_err(x_rec.cpu(), fx[tag + '_x']) < 1e-3
+    assert blk.inverse_iterations is not None and blk.inverse_iterations < 1000
+
+
+class Affine(torch.nn.Module):
+    """y = a x: stand-in x-branch of the Banach fixture (tests/golden/make_golden.py)."""
+
+    def __init__(self, a):
+        super(Affine, self).__init__()
+        self.a = a
+
+    def forward(self, x):
+        return self.a * x
+
+
+class Cliff(torch.nn.Module):
+    """-0.5 z on z > -1, a 1e8-steep wall below: Broyden's first step from zeros (z1 = -x_embed) lands behind the
+    wall and trips the 1e6 protective break; the Banach iteration from z0 = x stays on the contractive side."""
+
+    def forward(self, z):
+        return torch.where(z > -1, -0.5 * z, -0.5 * z + 1e8 * (z + 1))
+
+
+def case_imblock_banach_fallback(golden):
+    """prot_break -> find_fixed_point (implicit_block.py:17-28,74-75) through the block API."""
+    pkg = _pkg()
+    fx = golden('imblock_edge')
+    blk = pkg.layers.imBlock(Affine(0.1), Cliff()).to(DEV['device'])
+    x = torch.from_numpy(fx['banach_x']).to(DEV['device'])
+    with torch.no_grad():
+        z = blk(x)
+    info = blk.solver_stats['fwd']
+    assert [info['nstep'], int(info['prot_break'])] == fx['banach_ints'].tolist()
+    assert rel_err(z.cpu(), fx['banach_z']) < 1e-6
+
+
+EDGE = {
+    'exact': dict(dims=[6, 32, 32, 6], kw=dict(n_dist='geometric', exact_trace=True, n_samples=1, n_exact_terms=2,
+                                               neumann_grad=False, grad_in_forward=False, eps_forward=1e-5)),
+    'ns3': dict(dims=[12, 32, 32, 12], kw=dict(n_dist='geometric', n_samples=3, n_exact_terms=2, neumann_grad=False,
+                                               grad_in_forward=False, eps_forward=1e-5)),
+    'nps': dict(dims=[12, 32, 32, 12], kw=dict(n_dist='poisson', n_power_series=4, neumann_grad=True,
+                                               grad_in_forward=True, eps_forward=1e-5)),
+}
+
+
+# @parametrize('tag', list(EDGE))
+def case_imblock_edge_train(golden, tag):
+    """exact_trace (implicit_block.py:327-343), n_samples = 3 (:270-289) and a fixed n_power_series (:275-277)."""
+    layers = _pkg().layers
+    fx = golden('imblock_edge')
+    c = EDGE[tag]
+    d = c['dims'][0]
+    blk = layers.imBlock(build_mlp(layers, c['dims'], 0.9, None, 1e-3, d), build_mlp(layers, c['dims'], 0.9, None, 1e-3, d),
+                         **c['kw'])
+    blk = load_block(blk, fx, tag, torch.from_numpy(fx[tag + '_x']).to(DEV["device"]))
+    blk.train()
+    x = torch.from_numpy(fx[tag + '_x']).to(DEV["device"]).requires_grad_(True)
+    if tag != 'nps':
+        blk._inject_n = fx[tag + '_n_draws'].astype(np.int64)
+    if tag != 'exact':
+        blk._inject_probes = (torch.from_numpy(fx[tag + '_vareps_x']), torch.from_numpy(fx[tag + '_vareps_z']))
+    z, dlogp = blk(x, torch.zeros(x.shape[0], 1, device=DEV["device"]))
+    loss = -(std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True) - dlogp).mean()
+    loss.backward()
+    check_train(blk, fx, tag, x, z, dlogp, loss, grad_tol=2e-3)
+    if tag == 'ns3':
+        np.testing.assert_array_equal(blk.last_n_samples.cpu().numpy(), fx[tag + '_n_draws'])
+
+
+def case_imblock_fc_tail(golden):
+    """imBlock over FCNet branches (implicit_flow.py:321-356,437-474: the `fc_end` tail of the image flows)."""
+    pkg = _pkg()
+    layers = pkg.layers
+    from impflow_b200.implicit_flow import FCNet
+    fx = golden('imblock_edge')
+    shape = (2, 4, 4)
+    fc = lambda: FCNet(input_shape=shape, idim=24, lipschitz_layer=layers.base.get_linear, nhidden=2, coeff=0.9,
+                       domains=[2., 2., 2.], codomains=[2., 2., 2.], n_iterations=None, activation_fn='swish',
+                       preact=True, dropout=0, sn_atol=1e-3, sn_rtol=1e-3, learn_p=False)
+    blk = layers.imBlock(fc(), fc(), n_dist='poisson', n_samples=1, n_exact_terms=3, neumann_grad=True,
+                         grad_in_forward=True)
+    blk = load_block(blk, fx, 'fc', torch.from_numpy(fx['fc_x']).to(DEV["device"]))
+    x, z, dlogp, loss = run_train(blk, fx, 'fc')
+    check_train(blk, fx, 'fc', x, z, dlogp, loss, grad_tol=2e-3)
+
+
+def case_fused_adam_matches_reference_golden(golden):
+    """optim.FusedAdam against the reference's own clip_grad_norm_ + lib/optimizers.Adam + ExponentialMovingAverage
+    (tests/golden/step_tail.npz): parameters and EMA shadow after each of four steps, incl. the copy-only first
+    EMA apply (lib/utils.py:140-142); then a state_dict round trip into a fresh optimiser."""
+    pkg = _pkg()
+    dev = DEV['device']
+    fx = golden('step_tail')
+    n_steps, n_p, lr, b1, b2, eps, max_norm, decay = fx['meta']
+    n_steps, n_p = int(n_steps), int(n_p)
+
+    def fresh(values):
+        ps = [torch.nn.Parameter(torch.from_numpy(v).clone().to(dev)) for v in values]
+        bucket = pkg.parallel.FlatGradBucket(ps)
+        return ps, bucket, pkg.optim.FusedAdam(ps, lr=lr, betas=(b1, b2), eps=eps, weight_decay=1e-3, bucket=bucket,
+                                               max_grad_norm=max_norm, ema_decay=decay)
+    params, bucket, opt = fresh([fx['p0_%d' % i] for i in range(n_p)])
+
+    def do_step(ps, bucket, opt, t):
+        bucket.zero()
+        for i, p in enumerate(ps):
+            p.grad = torch.from_numpy(fx['g%d_%d' % (t, i)]).to(dev)
+        opt.step()
+
+    for t in range(n_steps):
+        if t == 2:        # checkpoint / resume in the middle of the trajectory
+            state = opt.state_dict()
+            params, bucket, opt2 = fresh([p.detach().cpu().numpy() for p in params])
+            opt2.load_state_dict(state)
+            opt = opt2
+        do_step(params, bucket, opt, t)
+        np.testing.assert_allclose(float(opt.grad_norm()), float(fx['gnorm%d' % t]), rtol=1e-5)
+        shadow = opt.ema_params()
+        for i, p in enumerate(params):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), fx['p%d_%d' % (t + 1, i)], rtol=3e-6, atol=1e-7)
+            np.testing.assert_allclose(shadow[i].cpu().numpy(), fx['ema%d_%d' % (t + 1, i)], rtol=3e-6, atol=1e-7)

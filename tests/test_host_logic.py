@@ -59,6 +59,32 @@ def test_implicit_flow_density_step(golden):
     cases.case_implicit_flow_density_step(golden)
 
 
+def test_mlp_solver_per_layer_beta():
+    cases.case_mlp_solver_per_layer_beta()
+
+
+@pytest.mark.parametrize('tag', list(cases.IRES))
+def test_iresblock(golden, tag):
+    cases.case_iresblock(golden, tag)
+
+
+def test_imblock_banach_fallback(golden):
+    cases.case_imblock_banach_fallback(golden)
+
+
+@pytest.mark.parametrize('tag', list(cases.EDGE))
+def test_imblock_edge_train(golden, tag):
+    cases.case_imblock_edge_train(golden, tag)
+
+
+def test_imblock_fc_tail(golden):
+    cases.case_imblock_fc_tail(golden)
+
+
+def test_fused_adam_matches_reference_golden(golden):
+    cases.case_fused_adam_matches_reference_golden(golden)
+
+
 @pytest.mark.parametrize('tag', ['small', 'wide', 'capped', 'protbreak'])
 def test_broyden_host_loop(golden, tag):
     import impflow_b200

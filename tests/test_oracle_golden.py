@@ -207,3 +207,138 @@ def test_roulette_coefficients():
     assert n_ps == 5
     np.testing.assert_allclose(coeffs[3], 1 / (1 - np.exp(-2.0)))
     np.testing.assert_allclose(coeffs[4], 1 / (1 - np.exp(-2.0) * (1 + 2.0)))
+
+
+# ---- round 2: branches of the block the shipped configs do not reach, iResBlock, the step tail -------------------
+
+class _Cliff(object):
+    """nnet_z of the Banach fixture (tests/golden/make_golden.py: Cliff)."""
+
+    def __call__(self, z):
+        return torch.where(z > -1, -0.5 * z, -0.5 * z + 1e8 * (z + 1))
+
+
+def test_banach_fallback_after_protective_break(golden):
+    fx = golden('imblock_edge')
+    x = torch.from_numpy(fx['banach_x'])
+    _, info = orc.root_find(_Cliff(), lambda t: 0.1 * t, x.clone(), x, 1e-6, 30)
+    assert [info['nstep'], int(info['prot_break'])] == fx['banach_ints'].tolist()
+    with torch.no_grad():       # solve + re-attach, as imBlock.forward does (implicit_block.py:224-227)
+        z = orc.imblock_forward(lambda t: 0.1 * t, _Cliff(), x, None, dict(orc.DEFAULT_CFG), True)
+    np.testing.assert_array_equal(z.numpy(), fx['banach_z'])
+
+
+EDGE_CASES = {
+    'exact': dict(act='sin', cfg=dict(orc.DEFAULT_CFG, exact_trace=True, neumann_grad=False, grad_in_forward=False,
+                                      eps_forward=1e-5)),
+    'ns3': dict(act='sin', cfg=dict(orc.DEFAULT_CFG, n_samples=3, neumann_grad=False, grad_in_forward=False,
+                                    eps_forward=1e-5)),
+    'nps': dict(act='sin', cfg=dict(orc.DEFAULT_CFG, n_dist='poisson', n_power_series=4, neumann_grad=True,
+                                    grad_in_forward=True, eps_forward=1e-5)),
+}
+
+
+@pytest.mark.parametrize('tag', list(EDGE_CASES))
+def test_imblock_edge_train(golden, tag):
+    fx = golden('imblock_edge')
+    case = EDGE_CASES[tag]
+    z, dlogp, stats, grads, _ = _run_oracle_block(fx, tag, case['act'], 0.9, case['cfg'], True, 1e-3, None)
+    assert stats['fwd_nstep'] == fx[tag + '_fwd_nstep'].tolist()
+    assert stats['bwd_nstep'] == fx[tag + '_bwd_nstep'].tolist()
+    assert rel_err(z.detach(), fx[tag + '_z']) < 1e-6
+    assert rel_err(dlogp.detach(), fx[tag + '_dlogp']) < 1e-5
+    assert rel_err(grads['x'], fx[tag + '_grad_x']) < 1e-4
+    for k, g in grads.items():
+        if k != 'x' and g is not None:
+            assert rel_err(g, fx[tag + '_grad_' + k]) < 5e-4, k
+
+
+class _FC(object):
+    """FCNet wrapper of an oracle branch (implicit_flow.py:437-474): flatten, MLP, reshape."""
+
+    def __init__(self, branch, shape):
+        self.branch, self.shape = branch, shape
+
+    def __call__(self, x):
+        return self.branch(x.reshape(x.shape[0], -1)).view(x.shape[0], *self.shape)
+
+    def parameters(self):
+        return self.branch.parameters()
+
+
+def test_imblock_fc_tail_block(golden):
+    fx = golden('imblock_edge')
+    sd_x, sd_z = sub_sd(fx, 'fc_sd_nnet_x.nnet.'), sub_sd(fx, 'fc_sd_nnet_z.nnet.')
+    bx = _FC(oracle_branch(sd_x, 'swish', 0.9, 1e-3), (2, 4, 4))
+    bz = _FC(oracle_branch(sd_z, 'swish', 0.9, 1e-3), (2, 4, 4))
+    cfg = dict(orc.DEFAULT_CFG, n_dist='poisson', n_exact_terms=3, neumann_grad=True, grad_in_forward=True)
+    x = torch.from_numpy(fx['fc_x']).clone().requires_grad_(True)
+    stats = {}
+    z, dlogp = orc.imblock_forward(bx, bz, x, torch.zeros(x.shape[0], 1), cfg, True,
+                                   n_draws=fx['fc_n_draws'].astype(np.int64),
+                                   probes=(torch.from_numpy(fx['fc_vareps_x']), torch.from_numpy(fx['fc_vareps_z'])),
+                                   stats=stats)
+    loss = -(_std_normal_logprob(z).view(z.size(0), -1).sum(1, keepdim=True) - dlogp).mean()
+    loss.backward()
+    assert stats['fwd_nstep'] == fx['fc_fwd_nstep'].tolist()
+    assert rel_err(z.detach(), fx['fc_z']) < 1e-6
+    assert rel_err(dlogp.detach(), fx['fc_dlogp']) < 1e-5
+    assert rel_err(x.grad, fx['fc_grad_x']) < 1e-4
+
+
+IRES_CASES = {
+    'mlp2': dict(act='sin', n_it=20, tol=None, cfg=dict(orc.DEFAULT_CFG, brute_force=True, neumann_grad=False,
+                                                        grad_in_forward=False)),
+    'mlp6': dict(act='sin', n_it=None, tol=1e-3, cfg=dict(orc.DEFAULT_CFG, neumann_grad=False, grad_in_forward=False)),
+    'mlp6n': dict(act='sin', n_it=None, tol=1e-3, cfg=dict(orc.DEFAULT_CFG, n_dist='poisson', n_samples=2,
+                                                           n_exact_terms=3, neumann_grad=True, grad_in_forward=True)),
+    'conv': dict(act='swish', n_it=None, tol=1e-3, cfg=dict(orc.DEFAULT_CFG, n_dist='poisson', n_exact_terms=3,
+                                                            neumann_grad=True, grad_in_forward=True)),
+}
+
+
+@pytest.mark.parametrize('tag', list(IRES_CASES))
+def test_iresblock(golden, tag):
+    fx = golden('iresblock')
+    case = IRES_CASES[tag]
+    sd = sub_sd(fx, tag + '_sd_nnet.')
+    net = oracle_branch(sd, case['act'], 0.9, case['tol'], case['n_it'])
+    x = torch.from_numpy(fx[tag + '_x']).clone().requires_grad_(True)
+    y, dlogp = orc.ires_forward(net, x, torch.zeros(x.shape[0], 1), case['cfg'], True,
+                                n_draws=fx[tag + '_n_draws'].astype(np.int64), probe=torch.from_numpy(fx[tag + '_vareps']))
+    loss = -(_std_normal_logprob(y).view(y.size(0), -1).sum(1, keepdim=True) - dlogp).mean()
+    loss.backward()
+    assert rel_err(y.detach(), fx[tag + '_y']) < 1e-6
+    assert rel_err(dlogp.detach(), fx[tag + '_dlogp']) < 1e-5
+    np.testing.assert_allclose(loss.item(), fx[tag + '_loss'], rtol=1e-6)
+    assert rel_err(x.grad, fx[tag + '_grad_x']) < 1e-4
+    for name, p in zip(branch_param_names(sd), net.parameters()):
+        if tag + '_grad_nnet.' + name in fx and p.grad is not None:
+            assert rel_err(p.grad, fx[tag + '_grad_nnet.' + name]) < 5e-4, name
+    # eval mode (20 exact terms / closed form) and the fixed-point inverse
+    ye, dle = orc.ires_forward(net, torch.from_numpy(fx[tag + '_x']).clone(), torch.zeros(x.shape[0], 1), case['cfg'],
+                               False, n_draws=fx[tag + 'eval_n_draws'].astype(np.int64),
+                               probe=torch.from_numpy(fx[tag + 'eval_vareps']))
+    assert rel_err(ye.detach(), fx[tag + 'eval_y']) < 1e-6
+    assert rel_err(dle.detach(), fx[tag + 'eval_dlogp']) < 1e-5
+    with torch.no_grad():
+        x_rec, _ = orc.ires_inverse(net, torch.from_numpy(fx[tag + '_y']))
+    assert rel_err(x_rec, fx[tag + '_x_rec']) < 1e-6
+    assert rel_err(x_rec, fx[tag + '_x']) < 1e-3
+
+
+def test_step_tail_matches_reference_adam_and_ema(golden):
+    """clip_grad_norm_ + lib/optimizers.Adam + utils.ExponentialMovingAverage over four steps (fixture produced by
+    the reference's own classes): parameters and EMA shadow after every step, incl. the copy-only first apply()."""
+    fx = golden('step_tail')
+    n_steps, n_p, lr, b1, b2, eps, max_norm, decay = fx['meta']
+    n_steps, n_p = int(n_steps), int(n_p)
+    ps = [torch.from_numpy(fx['p0_%d' % i]).clone() for i in range(n_p)]
+    ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    ema = [torch.zeros_like(p) for p in ps]
+    for t in range(n_steps):
+        gs = [torch.from_numpy(fx['g%d_%d' % (t, i)]).clone() for i in range(n_p)]
+        orc.clip_adam_ema_step(ps, gs, ms, vs, t + 1, lr, (b1, b2), eps, max_norm, ema, decay)
+        for i in range(n_p):
+            np.testing.assert_allclose(ps[i].numpy(), fx['p%d_%d' % (t + 1, i)], rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(ema[i].numpy(), fx['ema%d_%d' % (t + 1, i)], rtol=2e-6, atol=1e-7)
