@@ -674,9 +674,16 @@ def gen_bwd_band():
         build_conv_branch(4, 32, 0.9, 1e-3, False), build_conv_branch(4, 32, 0.9, 1e-3, False), n_dist='poisson',
         n_samples=1, n_exact_terms=3, neumann_grad=False, grad_in_forward=False)))
     old_threads = torch.get_num_threads()
+    # variants: intra-op thread counts, and mathematically equivalent re-orderings of the batch (per-sample
+    # arithmetic unchanged; only the order of the batch-global sums and the GEMM row blocking move)
     for tag, fx, make in cases:
-        counts = []
-        for nt in (1, 2, 4, 8):
+        B = fx[tag + '_x'].shape[0]
+        rs = np.random.RandomState(7)
+        variants = [('threads1', 1, np.arange(B)), ('threads2', 2, np.arange(B)), ('threads8', 8, np.arange(B)),
+                    ('reversed', 4, np.arange(B)[::-1].copy()), ('perm_a', 4, rs.permutation(B)),
+                    ('perm_b', 4, rs.permutation(B))]
+        counts, last = [], []
+        for name, nt, perm in variants:
             torch.set_num_threads(nt)
             blk = make()
             x = torch.from_numpy(fx[tag + '_x'])
@@ -686,17 +693,33 @@ def gen_bwd_band():
             blk.load_state_dict(sd, strict=True)
             blk.train()
             seed = int(fx[tag + '_seed'])
-            np.random.seed(seed)
-            torch.manual_seed(seed)
-            xg = x.clone().requires_grad_(True)
-            with SolveRecorder() as rec:
-                z, dlogp = blk(xg, torch.zeros(x.shape[0], 1))
-                loss = -(std_normal_logprob(z).view(z.size(0), -1).sum(1, keepdim=True) - dlogp).mean()
-                loss.backward()
+            np.random.seed(seed)            # same roulette draw
+            vx, vz = torch.from_numpy(fx[tag + '_vareps_x'])[perm], torch.from_numpy(fx[tag + '_vareps_z'])[perm]
+            probes = iter([vx, vz])
+
+            class _Replay(object):          # the block's two Bernoulli draws, re-ordered with the batch
+                def __init__(self, *a, **k):
+                    pass
+
+                def sample(self, shape):
+                    return (next(probes) + 1) / 2
+            orig_b = torch.distributions.bernoulli.Bernoulli
+            torch.distributions.bernoulli.Bernoulli = _Replay
+            try:
+                xg = x[perm].clone().requires_grad_(True)
+                with SolveRecorder() as rec:
+                    z, dlogp = blk(xg, torch.zeros(x.shape[0], 1))
+                    loss = -(std_normal_logprob(z).view(z.size(0), -1).sum(1, keepdim=True) - dlogp).mean()
+                    loss.backward()
+            finally:
+                torch.distributions.bernoulli.Bernoulli = orig_b
             counts.append([int(rec.nsteps('forward')[0]), int(rec.nsteps('backward')[0])])
-        out[tag + '_threads'] = np.array([1, 2, 4, 8])
+            tr = rec.traces('backward')[0]
+            last.append(float(tr[~np.isnan(tr)][-1]))
+        out[tag + '_variants'] = np.array([v[0] for v in variants])
         out[tag + '_fwd_bwd_nstep'] = np.array(counts, dtype=np.int64)
-        print(tag, 'fwd/bwd nstep by thread count', counts)
+        out[tag + '_bwd_last_residual'] = np.array(last)
+        print(tag, 'fwd/bwd nstep by variant', counts, 'last backward residual', ['%.3g' % v for v in last])
     torch.set_num_threads(old_threads)
     save('bwd_band', **out)
 
