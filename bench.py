@@ -8,6 +8,14 @@ A "step" is one training step of the CIFAR-10-shape ImplicitFlow of run_cifar10.
 (train_img.py:591-660): forward (6 imBlocks: Broyden solve + power-series log-det), bits/dim,
 backward (implicit-differentiation Broyden solves), gradient all-reduce (N>1), clip, Adam,
 update_lipschitz — on synthetic U[0,1) images with random-init weights.
+
+Other configurations of BASELINE.json (`--workload`): toy / tabular-* (train_toy.py, train_tabular.py MLP flows),
+classifier (train_classification.py ImplicitResNet18, solver + spectral-norm path, no log-det).
+`--scaling strong` keeps the GLOBAL batch at the workload's batch and shards it over the ranks.
+
+The reference arm (`--impl reference`, and the `cpu_baseline` key of this repo's line) runs the UNMODIFIED
+reference from oracle/_ref (bytecode compiled by oracle/build_ref.py) on the host cores when it is present
+(`kind: "reference"`), else the oracle port (`kind: "port"`); its config line states the batch it really ran.
 """
 import argparse
 import json
@@ -39,11 +47,67 @@ WORKLOADS = {
                             n_lipschitz_iters=None, brute_force=False, eps_forward=1e-5),
     'toy': dict(kind='mlp', d=2, hidden=[128] * 2, n_blocks=6, batch=5000, coeff=0.99, sn_tol=None,
                 n_lipschitz_iters=20, brute_force=True, eps_forward=1e-6),
+    # run_classification.sh + train_classification.py:135-282: ImplicitResNet18, 4 imBlocks of 3x3-ReLU-3x3-ReLU
+    # conv branches on (64ch,32x32), (64,32x32), (128,16x16), (256,8x8): d = 65536 / 65536 / 32768 / 16384, no log-det
+    'classifier': dict(kind='cls', input=(3, 32, 32), batch=128, coeff=0.9, n_classes=100),
+}
+WORKLOAD_TEXT = {
+    'cifar': 'cifar10-shape ImplicitFlow train step (run_cifar10.sh: nblocks 2-2-2, idim 512, k3-1-3, LipSwish, '
+             '10 exact terms, Neumann grad, mem-eff)',
+    'classifier': 'ImplicitResNet18 train step (run_classification.sh: 4 conv imBlocks, ReLU, coeff 0.9, '
+                  'cross-entropy, no log-det)',
 }
 
 
 def std_normal_logprob(z):
     return -0.5 * np.log(2 * np.pi) - z.pow(2) / 2
+
+
+def build_classifier(pkg, wl):
+    """ImplicitResNet18 of train_classification.py:135-282 on the given layers namespace (this repo's package
+    or the reference): conv stem, four BasicImplicitBlocks (imBlock over two 3x3-ReLU-3x3-ReLU induced-norm conv
+    branches, then a strided 1x1 conv + BatchNorm + ReLU downsample), average pool, linear head."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    layers = pkg.layers
+    coeff = wl['coeff']
+
+    class BasicImplicitBlock(nn.Module):
+        def __init__(self, in_planes, hidden, planes, stride):
+            super(BasicImplicitBlock, self).__init__()
+            self.initialized = False
+            conv = lambda a, b: layers.base.get_conv2d(a, b, kernel_size=3, stride=1, padding=1, bias=False,
+                                                       coeff=coeff, n_iterations=None, domain=2, codomain=2,
+                                                       atol=1e-3, rtol=1e-3)
+            net = lambda: nn.Sequential(conv(in_planes, hidden), nn.ReLU(), conv(hidden, in_planes), nn.ReLU())
+            self.block = layers.imBlock(net(), net())
+            self.downsample = nn.Sequential()
+            if stride != 1 or in_planes != planes:
+                self.downsample = nn.Sequential(nn.Conv2d(in_planes, planes, kernel_size=1, stride=stride, bias=False),
+                                                nn.BatchNorm2d(planes), nn.ReLU())
+
+        def forward(self, x):
+            out = self.block(x) if self.initialized else self.block(x, restore=True)
+            self.initialized = True
+            return self.downsample(out)
+
+    class ImplicitResNet18(nn.Module):
+        def __init__(self, num_classes):
+            super(ImplicitResNet18, self).__init__()
+            self.conv1 = nn.Conv2d(3, 64, kernel_size=3, stride=1, padding=1, bias=False)
+            self.bn1 = nn.BatchNorm2d(64)
+            self.layer1 = nn.Sequential(BasicImplicitBlock(64, 64, 64, 1))
+            self.layer2 = nn.Sequential(BasicImplicitBlock(64, 128, 128, 2))
+            self.layer3 = nn.Sequential(BasicImplicitBlock(128, 256, 256, 2))
+            self.layer4 = nn.Sequential(BasicImplicitBlock(256, 512, 512, 2))
+            self.linear = nn.Linear(512, num_classes)
+
+        def forward(self, x, restore=False):
+            out = F.relu(self.bn1(self.conv1(x)))
+            out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
+            out = F.avg_pool2d(out, 4)
+            return self.linear(out.view(out.size(0), -1))
+    return ImplicitResNet18(wl['n_classes'])
 
 
 def build_mlp_flow(pkg, wl):
@@ -70,6 +134,8 @@ def build_mlp_flow(pkg, wl):
 def build_model(pkg, wl, batch):
     if wl.get('kind') == 'mlp':
         return build_mlp_flow(pkg, wl)
+    if wl.get('kind') == 'cls':
+        return build_classifier(pkg, wl)
     layers = pkg.layers
     c, h, w = wl['input']
     return pkg.ImplicitFlow(
@@ -139,7 +205,101 @@ class ClockSampler(object):
         return out
 
 
+def scale_mlp_last_layers(model, wl):
+    """The zero-initialised last layers of the MLP branches (zero_init: weights / 1000) make a fresh flow the
+    identity; move them away from zero so that the solves and estimators do real work (both arms)."""
+    with torch.no_grad():
+        for n_, p_ in model.named_parameters():
+            if n_.endswith('weight') and p_.dim() == 2 and p_.requires_grad and p_.shape[0] == wl['d']:
+                p_.mul_(30.0)
+
+
+def synthetic_batch(wl, batch, gen):
+    """Synthetic inputs of SURVEY.md section 8d: z-scored tabular rows, U[0,1) images (+ uniform labels)."""
+    if wl.get('kind') == 'mlp':
+        return torch.randn(batch, wl['d'], generator=gen), None
+    c, h, w = wl['input']
+    y = torch.randint(0, wl['n_classes'], (batch,), generator=gen) if wl.get('kind') == 'cls' else None
+    return torch.rand(batch, c, h, w, generator=gen), y
+
+
+def loss_of(model, wl, x, y):
+    """The training objective of the three script families (train_img.py:517-549, train_tabular.py:398-407 /
+    train_toy.py:108-116, train_classification.py:357-359)."""
+    kind = wl.get('kind')
+    if kind == 'cls':
+        return torch.nn.functional.cross_entropy(model(x), y, reduction='sum')
+    if kind == 'mlp':
+        z, dlogp = model(x, torch.zeros(x.shape[0], 1, device=x.device))
+        logpz = std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True)
+        return -(logpz - dlogp).mean()
+    n_dims = int(np.prod(wl['input']))
+    z, dlogp = model(x, 0)
+    logpz = std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True)
+    logpx = logpz - dlogp - np.log(256) * n_dims
+    return -torch.mean(logpx) / n_dims / np.log(2)
+
+
+def run_reference_impl(wl_name, steps, warmup, batch, threads=None):
+    """The UNMODIFIED reference (oracle/_ref, compiled from /root/reference by oracle/build_ref.py) on the host
+    cores: the reference's own model classes, vendored Adam, EMA and update_lipschitz loop, one training step of
+    the named workload per step (train_img.py:591-660 / train_tabular.py:447-500 / train_toy.py:283-297 /
+    train_classification.py:352-366) on `batch` synthetic samples."""
+    from oracle import ref_runner
+    ns = ref_runner.load()
+    wl = WORKLOADS[wl_name]
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = build_model(ns, wl, batch)
+    kind = wl.get('kind')
+    if kind == 'mlp':
+        scale_mlp_last_layers(model, wl)
+    x, y = synthetic_batch(wl, batch, torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        model(x, restore=True)           # ActNorm data init + lazy u/v shaping (train_img.py:502-507)
+    model.train()
+    is_toy = wl_name == 'toy'
+    opt = ns.optim.Adam(model.parameters(), lr=1e-3, **({} if (is_toy or kind == 'cls') else {'betas': (0.9, 0.99)}))
+    ema = None if is_toy else ns.utils.ExponentialMovingAverage(model)
+    times, fwd, bwd, loss = [], [], [], None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        with ref_runner.SolveCounter(ns) as rec:
+            loss = loss_of(model, wl, x, y)
+            loss.backward()
+            if kind != 'cls' and not is_toy:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), 1.)
+            opt.step()
+            opt.zero_grad()
+            ref_runner.update_lipschitz(ns, model, wl.get('n_lipschitz_iters'))
+            if ema is not None:
+                ema.apply()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        fwd, bwd = rec.nsteps('forward'), rec.nsteps('backward')
+    ms = float(np.mean(times) * 1e3)
+    n_blocks = len(fwd)
+    return {'value': batch / (ms / 1e3), 'ms_per_step': ms, 'cores': threads, 'batch': batch, 'bpd': float(loss),
+            'fwd_nstep': fwd, 'bwd_nstep': bwd, 'kind': 'reference',
+            'solves_per_step': 2 * n_blocks * batch}
+
+
 def run_cpu_reference(wl_name, steps, warmup, batch, threads=None):
+    """CPU arm: the unmodified reference when oracle/_ref is present, else the oracle port of the same step."""
+    from oracle import ref_runner
+    if ref_runner.available():
+        return run_reference_impl(wl_name, steps, warmup, batch, threads)
+    if WORKLOADS[wl_name].get('kind') == 'cls':
+        raise RuntimeError('the classifier workload has no oracle port; build oracle/_ref (python oracle/build_ref.py)')
+    res = run_cpu_port(wl_name, steps, warmup, batch, threads)
+    res['kind'] = 'port'
+    return res
+
+
+def run_cpu_port(wl_name, steps, warmup, batch, threads=None):
     """The reference algorithm (oracle port, PyTorch CPU like the reference itself) on host cores."""
     from oracle import flow_oracle
     import impflow_b200 as pkg
@@ -320,8 +480,12 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cifar', choices=list(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (weak scaling)')
-    ap.add_argument('--cpu-batch', type=int, default=4, help='images per CPU-baseline step (bounded sample)')
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (weak scaling) / global batch (strong)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: per-GPU batch fixed; strong: global batch fixed and sharded over the ranks')
+    ap.add_argument('--cpu-batch', type=int, default=None,
+                    help='samples per step of the reference arm (bounded sample; default: a quarter of the batch, '
+                         'capped so that K + W steps end within minutes)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--probe-mode', default='device', choices=['reference', 'device'])
     ap.add_argument('--unfused', action='store_true', help='disable the graph-free branch programs (A/B)')
@@ -331,10 +495,14 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     wl = WORKLOADS[args.workload]
-    batch = args.batch or wl['batch']
-    config = {'workload': ('cifar10-shape ImplicitFlow train step (run_cifar10.sh: nblocks 2-2-2, idim 512, k3-1-3, '
-                           'LipSwish, 10 exact terms, Neumann grad, mem-eff)' if args.workload == 'cifar'
-                           else args.workload),
+    kind = wl.get('kind', 'img')
+    wl_batch = args.batch or wl['batch']
+    if args.scaling == 'strong':
+        assert wl_batch % world == 0, 'strong scaling: the global batch must divide by the number of ranks'
+        batch = wl_batch // world
+    else:
+        batch = wl_batch
+    config = {'workload': WORKLOAD_TEXT.get(args.workload, args.workload),
               'per_gpu_batch': batch, 'global_batch': batch * world, 'parallelism': 'dp%d' % world,
               'l2': 'per-step working set (>1 GB of activations) exceeds the 126 MB L2; 256 MB flush between steps',
               'gemm': '3xTF32 on tcgen05 (fp32-accurate; ceiling = 1/6 of the bf16 peak)',
@@ -343,16 +511,25 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        cpu_batch = args.cpu_batch
-        res = run_cpu_reference(args.workload, max(args.steps, 1), max(min(args.warmup, 1), 0), cpu_batch)
+        # a bounded sample of the workload per step, stated in the line's own config: the metric is per sample
+        default_cpu = {'img': 8, 'cls': 4, 'mlp': max(wl_batch // 8, 1)}[kind]
+        cpu_batch = args.cpu_batch or min(default_cpu, wl_batch)
+        res = run_cpu_reference(args.workload, max(args.steps, 1), max(args.warmup, 0), cpu_batch)
+        ref_cfg = {'workload': config['workload'], 'per_gpu_batch': cpu_batch, 'global_batch': cpu_batch,
+                   'parallelism': 'cpu', 'workload_batch': wl_batch,
+                   'sample': 'each step trains on %d of the workload\'s %d samples (bounded CPU sample; the metric '
+                             'is per sample)' % (cpu_batch, wl_batch),
+                   'arithmetic': 'fp32 ATen on %d host threads' % res['cores']}
+        solver = {'fwd': res['fwd_nstep'], 'bwd': res['bwd_nstep']}
         line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': 0,
-                'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': res['ms_per_step'],
-                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': config,
-                'cpu_baseline': {'value': res['value'], 'unit': UNIT, 'cores': res['cores'], 'kind': 'port',
-                                 'sample': '%d-image steps of the same model (samples/s is per image)' % cpu_batch},
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': res['ms_per_step'],
+                'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': ref_cfg,
+                'cpu_baseline': {'value': res['value'], 'unit': UNIT, 'cores': res['cores'], 'kind': res['kind'],
+                                 'sample': '%d timed + %d warm-up steps of %d samples each of the same model'
+                                           % (args.steps, args.warmup, cpu_batch)},
                 'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-                'solver_iterations': {'fwd': res['fwd_nstep'], 'bwd': res['bwd_nstep']}}
+                'solver_iterations': solver}
         print(json.dumps(line))
         return
 
@@ -392,19 +569,19 @@ def main():
     torch.manual_seed(0)
     np.random.seed(0)
     model = build_model(pkg, wl, batch).to(dev)
-    is_mlp = wl.get('kind') == 'mlp'
+    is_mlp = kind == 'mlp'
+    is_cls = kind == 'cls'
     gen = torch.Generator().manual_seed(1234 + rank)
     if is_mlp:
-        c, h, w = wl['d'], 1, 1
-        x_host = torch.randn(batch, wl['d'], generator=gen).pin_memory()     # z-scored tabular data
-        with torch.no_grad():        # move the near-zero last layers so the solves do real work
-            for n_, p_ in model.named_parameters():
-                if n_.endswith('weight') and p_.dim() == 2 and p_.requires_grad:
-                    p_.mul_(30.0 if p_.shape[0] == wl['d'] else 1.0)
+        scale_mlp_last_layers(model, wl)      # move the near-zero last layers so the solves do real work
+        n_dims = wl['d']
     else:
-        c, h, w = wl['input']
-        x_host = torch.rand(batch, c, h, w, generator=gen).pin_memory()
+        n_dims = int(np.prod(wl['input']))
+    x_host, y_host = synthetic_batch(wl, batch, gen)
+    x_host = x_host.pin_memory()
+    y_host = y_host.pin_memory() if y_host is not None else None
     x_dev = x_host.to(dev)
+    y_dev = y_host.to(dev) if y_host is not None else None
     with torch.no_grad():
         model(x_dev, restore=True)           # ActNorm data init + lazy u/v shaping (train_img.py:502-507)
     if world > 1:
@@ -415,28 +592,22 @@ def main():
     params = [p for p in model.parameters() if p.requires_grad]
     bucket = pkg.parallel.FlatGradBucket(params)
     # step tail of train_img.py:652-658 in one fused pass: clip_grad_norm_(1.) + the vendored Adam + parameter EMA
-    opt = pkg.optim.FusedAdam(params, lr=1e-3, betas=(0.9, 0.99), bucket=bucket,
-                              max_grad_norm=None if is_mlp else 1., ema_decay=None if is_mlp else 0.999)
-    n_dims = c * h * w
+    # (train_toy.py: no clipping, no EMA; train_classification.py: EMA, no clipping)
+    is_toy = args.workload == 'toy'
+    opt = pkg.optim.FusedAdam(params, lr=1e-3, betas=(0.9, 0.999) if (is_toy or is_cls) else (0.9, 0.99),
+                              bucket=bucket, max_grad_norm=None if (is_toy or is_cls) else 1.,
+                              ema_decay=None if is_toy else 0.999)
     flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)
     blocks = [m for m in model.modules() if isinstance(m, pkg.layers.imBlock)]
 
-    def step(x):
+    def step(x, y=None):
         bucket.zero()
-        if is_mlp:          # train_tabular.py:398-407 / train_toy.py:108-116
-            z, dlogp = model(x, torch.zeros(x.shape[0], 1, device=x.device))
-            logpz = std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True)
-            bpd = -(logpz - dlogp).mean()
-        else:
-            z, dlogp = model(x, 0)
-            logpz = std_normal_logprob(z).reshape(z.size(0), -1).sum(1, keepdim=True)
-            logpx = logpz - dlogp - np.log(256) * n_dims
-            bpd = -torch.mean(logpx) / n_dims / np.log(2)
-        bpd.backward()
+        loss = loss_of(model, wl, x, y)
+        loss.backward()
         bucket.allreduce_mean()
         opt.step()
         update_lipschitz(pkg, model, wl.get('n_lipschitz_iters'))
-        return bpd
+        return loss
 
     def sync_all():
         if world > 1:
@@ -444,7 +615,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step(x_dev)
+        step(x_dev, y_dev)
     sync_all()
     if os.environ.get('IMPFLOW_BENCH_GC', '') == 'freeze':      # diagnostic: cost of Python's cyclic GC in the loop
         import gc
@@ -460,29 +631,40 @@ def main():
         sampler.start()
     pkg.ops.GEMM_PROFILE['on'] = True
     pkg.ops.GEMM_PROFILE['shapes'] = {}
+    implicit_block.SOLVER_TIMING['on'], implicit_block.SOLVER_TIMING['events'] = True, []
     launches0 = pkg._cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     solves = 0
     fwd_its, bwd_its = [], []
     sync_all()
-    torch.cuda.nvtx.range_push('timed')      # ncu --nvtx --nvtx-include "timed/" isolates these launches
+    torch.cuda.nvtx.range_push('timed')
+    if os.environ.get('IMPFLOW_PROFILER_API', '') == '1':      # ncu --profile-from-start off: every thread's launches
+        torch.cuda.cudart().cudaProfilerStart()
     ev0.record()
     for _ in range(args.steps):
         flush.zero_()
-        step(x_dev)
+        step(x_dev, y_dev)
         solves += 2 * len(blocks) * batch
         fwd_its.append([b.solver_stats['fwd']['nstep'] for b in blocks])
+        bwd_its.append([b.solver_stats['bwd']['nstep'] if 'bwd' in b.solver_stats else None for b in blocks])
     ev1.record()
     sync_all()
+    if os.environ.get('IMPFLOW_PROFILER_API', '') == '1':
+        torch.cuda.cudart().cudaProfilerStop()
     torch.cuda.nvtx.range_pop()
     ms_total = ev0.elapsed_time(ev1)
     launches = pkg._cabi.launch_count() - launches0
     pkg.ops.GEMM_PROFILE['on'] = False
+    implicit_block.SOLVER_TIMING['on'] = False
+    solver_ms = {'fwd': 0.0, 'bwd': 0.0}
+    for k_, e0_, e1_ in implicit_block.SOLVER_TIMING['events']:
+        solver_ms[k_] += e0_.elapsed_time(e1_)
+    implicit_block.SOLVER_TIMING['events'] = []
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev)
+    t = torch.tensor([ms_total, solver_ms['fwd'] + solver_ms['bwd']], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total, solver_ms_total = float(t[0].item()), float(t[1].item())
     ms_step = ms_total / args.steps
     value = batch * world / (ms_step / 1e3)
 
@@ -524,7 +706,8 @@ def main():
     last = None
     for _ in range(args.steps):
         xb = x_host.to(dev, non_blocking=True)
-        last = step(xb).item()                     # device -> host read of the step's loss
+        yb = y_host.to(dev, non_blocking=True) if y_host is not None else None
+        last = step(xb, yb).item()                     # device -> host read of the step's loss
     sync_all()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     te = torch.tensor([e2e_ms], device=dev)
@@ -534,7 +717,7 @@ def main():
 
     # ---------------- generation path: forward-only Broyden solves (model.inverse, train_img.py:756-761) ----------
     inv = None
-    if not is_mlp:
+    if kind == 'img':
         model.eval()
         with torch.no_grad():
             zs = torch.randn(batch, n_dims, device=dev)
@@ -596,13 +779,21 @@ def main():
     order = sorted(kern, key=lambda n: -kern[n]['ms'])
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic', 'config': config, 'clocks': clocks,
         'e2e': {'value': batch * world / (e2e_ms / 1e3), 'unit': UNIT, 'ms_per_step': e2e_ms,
-                'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': 4, 'last_bpd': last},
+                'h2d_bytes_per_step': int(x_host.numel() * 4 + (y_host.numel() * 8 if y_host is not None else 0)),
+                'd2h_bytes_per_step': 4, 'last_loss': last},
         'gpu_launches': int(launches),
-        'broyden_solves_per_sec': solves * world / (ms_total / 1e3),
+        # solves (samples x imBlocks x [forward + implicit-backward]) / time inside the solver
+        # phases (CUDA events around every solve); the whole-step figure beside it
+        'broyden_solves_per_sec': solves * world / (solver_ms_total / 1e3) if solver_ms_total > 0 else None,
+        'broyden_solves_per_sec_whole_step': solves * world / (ms_total / 1e3),
+        'solver_phase': {'ms_per_step': solver_ms_total / args.steps, 'share_of_step': solver_ms_total / ms_total,
+                         'fwd_ms_per_step': solver_ms['fwd'] / args.steps,
+                         'bwd_ms_per_step': solver_ms['bwd'] / args.steps},
         'solver_iterations_fwd_last_step': fwd_its[-1] if fwd_its else None,
+        'solver_iterations_bwd_last_step': bwd_its[-1] if bwd_its else None,
         'inverse_sampling': inv,
         'roofline': roof(order[0]) if order else None,
     }
@@ -610,24 +801,33 @@ def main():
         line['roofline_secondary'] = roof(order[1])
     if len(order) > 2:
         line['roofline_tertiary'] = roof(order[2])
-    if not is_mlp:
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    hsrc = 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
+    if kind != 'mlp':
         # the solver-algebra phase against the HBM roofline: the bench shape (latency-bound: 0.8 MB per
         # vector) and the classifier shape of SURVEY.md section 8 (B=128, d=65536: 2 GB of history)
-        hbm = peaks.get('hbm_gbs', 6650.0)
-        hsrc = 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
         try:
-            line['roofline_solver'] = [solver_roofline(pkg, batch, n_dims, 30, 6, flush, hbm, hsrc),
-                                       solver_roofline(pkg, 128, 65536, 30, 8, flush, hbm, hsrc)]
+            d_solver = n_dims if kind == 'img' else 65536
+            line['roofline_solver'] = [solver_roofline(pkg, batch, d_solver, 30, 6, flush, hbm, hsrc)] + \
+                ([solver_roofline(pkg, 128, 65536, 30, 8, flush, hbm, hsrc)] if kind == 'img' else [])
         except Exception as exc:
             line['roofline_solver'] = 'failed: %r' % (exc,)
+    if not order and line.get('roofline') is None and isinstance(line.get('roofline_solver'), list):
+        line['roofline'] = line['roofline_solver'][0]       # no tensor-core launch in this workload: HBM-bound solver
     if world == 1 and not args.no_cpu_baseline:
         try:
-            res = run_cpu_reference(args.workload, 2, 1, args.cpu_batch)
-            line['cpu_baseline'] = {'value': res['value'], 'unit': UNIT, 'cores': res['cores'], 'kind': 'port',
-                                    'sample': '2 timed + 1 warm-up steps of %d images of the same model on host '
-                                              'cores' % args.cpu_batch}
+            # one warm-up + one timed step on a bounded sample of the batch (about 15-30 s of CPU work: the unmodified
+            # reference needs > 1 min per 64-image step of the CIFAR flow; DESIGN.md lists its measured per-image
+            # throughput at batch 4 / 8 / 16 / 32 / 64)
+            cb = {'img': min(16, wl_batch), 'cls': 8, 'mlp': max(wl_batch // 4, 1)}[kind]
+            cb = args.cpu_batch or cb
+            res = run_cpu_reference(args.workload, 1, 1, cb)
+            line['cpu_baseline'] = {'value': res['value'], 'unit': UNIT, 'cores': res['cores'], 'kind': res['kind'],
+                                    'sample': '1 timed + 1 warm-up step of %d samples (workload batch %d) of the same '
+                                              'model on host cores' % (cb, wl_batch),
+                                    'solver_iterations': {'fwd': res['fwd_nstep'], 'bwd': res['bwd_nstep']}}
         except Exception as exc:      # the baseline must never hide the GPU number
-            line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+            line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'reference',
                                     'sample': 'failed: %r' % (exc,)}
     print(json.dumps(line))
     if world > 1:

@@ -28,9 +28,15 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+LAST_BUILD_COMPILED = False
+
+
 def build(force=False, verbose=False):
+    global LAST_BUILD_COMPILED
+    LAST_BUILD_COMPILED = False
     if not force and not needs_build():
         return OUT
+    LAST_BUILD_COMPILED = True
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs = []
     procs = []

@@ -88,6 +88,22 @@ def branch_apply(nnet, x):
     return _BranchApply.apply(x, prog, *prog.params)
 
 
+# Solver-phase timing for bench.py (Broyden solves/s = solves / time spent in solver phases): when
+# on, every forward / inverse / implicit-backward solve is bracketed by CUDA events on the current stream.
+SOLVER_TIMING = {'on': False, 'events': []}
+
+
+def _timed(kind, like, fn):
+    if not (SOLVER_TIMING['on'] and like.is_cuda):
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    SOLVER_TIMING['events'].append((kind, e0, e1))
+    return out
+
+
 # Independent halves of a block's work (the log-det estimates of the x- and z-branch) on two streams.
 OVERLAP = {'on': True}
 _side = {}
@@ -224,7 +240,7 @@ class RootFind(Function):
         root_find = RootFind.broyden_find_root if method == 'broyden' else RootFind.banach_find_root
         ctx.args_len = len(args)
         with torch.no_grad():
-            return root_find(nnet_z, nnet_x, z0, x, *args)
+            return _timed('fwd', x, lambda: root_find(nnet_z, nnet_x, z0, x, *args))
 
     @staticmethod
     def backward(ctx, grad_z):
@@ -276,6 +292,7 @@ class imBlock(nn.Module):
         solve v^T (I + J_z) = grad with Broyden, then dl_dx = v^T (I + J_x)."""
         last_info = None
         x_alias = None
+        stats_sink = None        # the calling block's solver_stats dict: receives the backward solve's info as 'bwd'
 
         @staticmethod
         def forward(ctx, nnet_z, nnet_x, z, x, *args):
@@ -283,6 +300,7 @@ class imBlock(nn.Module):
             ctx.nnet_z = nnet_z
             ctx.nnet_x = nnet_x
             ctx.args = args
+            ctx.stats, imBlock.Backward.stats_sink = imBlock.Backward.stats_sink, None
             # a detached tensor with x's values whose saved forward the x-branch program may still hold
             ctx.x_alias, imBlock.Backward.x_alias = imBlock.Backward.x_alias, None
             return z
@@ -300,15 +318,21 @@ class imBlock(nn.Module):
                 with torch.no_grad():
                     z, x = z.detach(), x.detach()
                     _, saved_z = prog_z.forward_saved(z)
-                    info = prog_z.broyden_solve(1, grad, saved_z, threshold, eps)
-                    if info is None:
-                        spec = prog_z.mlp_vjp_spec(saved_z)
-                        if spec is not None:       # small-d MLP: the whole solve in one persistent kernel
-                            info = broyden_mlp_vjp(spec, grad, threshold, eps)
-                    if info is None:
-                        info = broyden(lambda v: ops.lincomb3(prog_z.vjp(v, saved_z), 1.0, v, 1.0, grad, -1.0),
-                                       torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
+
+                    def solve():
+                        info = prog_z.broyden_solve(1, grad, saved_z, threshold, eps)
+                        if info is None:
+                            spec = prog_z.mlp_vjp_spec(saved_z)
+                            if spec is not None:       # small-d MLP: the whole solve in one persistent kernel
+                                info = broyden_mlp_vjp(spec, grad, threshold, eps)
+                        if info is None:
+                            info = broyden(lambda v: ops.lincomb3(prog_z.vjp(v, saved_z), 1.0, v, 1.0, grad, -1.0),
+                                           torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
+                        return info
+                    info = _timed('bwd', grad, solve)
                     imBlock.Backward.last_info = info
+                    if ctx.stats is not None:
+                        ctx.stats['bwd'] = info
                     dl_dh = info['result']
                     xa = ctx.x_alias if (ctx.x_alias is not None and ctx.x_alias.shape == x.shape) else x
                     _, saved_x = prog_x.forward_saved(xa)
@@ -324,8 +348,11 @@ class imBlock(nn.Module):
                     (vJ,) = torch.autograd.grad(Fz, z, v, retain_graph=True)
                 return ops.lincomb3(vJ, 1.0, grad, -1.0)
 
-            info = broyden(g, torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
+            info = _timed('bwd', grad, lambda: broyden(g, torch.zeros_like(grad), threshold=threshold, eps=eps,
+                                                       name='backward'))
             imBlock.Backward.last_info = info
+            if ctx.stats is not None:
+                ctx.stats['bwd'] = info
             dl_dh = info['result']
             del Fz
             with torch.enable_grad():
@@ -351,6 +378,7 @@ class imBlock(nn.Module):
             self.nnet_z_copy._impflow_program = _program(self.nnet_z)
             self.nnet_x_copy._impflow_program = _program(self.nnet_x)
         imBlock.Backward.x_alias = z0
+        imBlock.Backward.stats_sink = self.solver_stats
         z = self.Backward.apply(self.nnet_z_copy, self.nnet_x_copy, z, x, 'broyden', self.eps_backward,
                                 self.threshold)
         if logpx is None:

@@ -24,8 +24,17 @@ def broadcast_module(module, src=0):
     """Rank `src` initialises (data-dependent ActNorm init, lazy u/v shaping); everyone else
     receives parameters and buffers."""
     with torch.no_grad():
-        for t in list(module.parameters()) + list(module.buffers()):
+        tensors = list(module.parameters()) + list(module.buffers())
+        for t in tensors:
             dist.broadcast(t.data, src=src)
+        # the collective writes through the raw storage: bump the version counters so that every host cache keyed
+        # on them (effective weights, sigma, d sigma / dW, roulette rates) is rebuilt from the received values
+        torch.autograd.graph.increment_version(tensors)
+        for m in module.modules():           # python mirrors of buffers (lazy conv u / v shapes, ActNorm init flag)
+            if hasattr(m, '_hw'):
+                m._hw = None
+            if hasattr(m, '_init_known'):
+                m._init_known = None
 
 
 class FlatGradBucket(object):

@@ -26,7 +26,10 @@ def _worker(rank, world, port, q):
     par = impflow_b200.parallel
     torch.manual_seed(7 + rank)                       # ranks start with DIFFERENT weights
     model = torch.nn.Sequential(torch.nn.Linear(5, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
+    versions = [p._version for p in model.parameters()]
     par.broadcast_module(model, 0)                    # ... and end up with rank 0's
+    if rank != 0:      # the receive must be visible to the version-keyed host caches (effective weights, sigma)
+        assert all(p._version > v for p, v in zip(model.parameters(), versions))
     torch.manual_seed(0)
     x = torch.randn(12, 5)                            # same global batch everywhere
     xs = par.shard_batch(x)
