@@ -533,10 +533,29 @@ class BranchProgram(object):
         arr = (ctypes.c_double * max(n, 1))(*[float(c) for c in coeffs])
         pre0, d1, d2 = self._vjp_operands(saved, P)
         _cabi.check(_cabi.load().impflow_conv3_power_series(self._plan_ptr(P), pre0, d1, d2, _cabi.ptr(t), arr, n,
-                                                            _cabi.ptr(w_rows), _cabi.stream()), 'conv3_power_series')
+                                                            _cabi.ptr(w_rows), None, None, _cabi.stream()),
+                    'conv3_power_series')
         if ops.GEMM_PROFILE['on']:
             self._record_conv3(P, True, False, n)
         return self._from_rows(w_rows, saved.meta)
+
+    def hutchinson_series(self, saved, vareps, dot_coeffs):
+        """sum_k dot_coeffs[k-1] <v^T J^k, v> per sample — the basic estimator's no-graph form (eval mode,
+        implicit_block.py:418-426) — in one C call, or None if this branch has no native plan."""
+        P = self._conv3(self._prep(saved.M), saved.meta)
+        if P is None:
+            return None
+        t, _ = self._to_rows(vareps)
+        n = len(dot_coeffs)
+        out = torch.empty(vareps.shape[0], device=t.device, dtype=torch.float32)
+        arr = (ctypes.c_double * max(n, 1))(*[float(c) for c in dot_coeffs])
+        pre0, d1, d2 = self._vjp_operands(saved, P)
+        _cabi.check(_cabi.load().impflow_conv3_power_series(self._plan_ptr(P), pre0, d1, d2, _cabi.ptr(t), None, n,
+                                                            None, arr, _cabi.ptr(out), _cabi.stream()),
+                    'conv3_power_series')
+        if ops.GEMM_PROFILE['on']:
+            self._record_conv3(P, True, False, n)
+        return out
 
     def broyden_solve(self, mode, rhs, saved, threshold, eps):
         """Whole Broyden solve in one C call (mode 0: rhs - nnet(z) - z = 0 from z = 0; mode 1:
@@ -568,7 +587,7 @@ class BranchProgram(object):
             self._plan_ptr(P), mode, _cabi.ptr(rows), pre0, d1, d2, vp(wk.xa), vp(wk.xb), vp(wk.ga), vp(wk.gb),
             vp(wk.low_x), vp(wk.low_g), vp(wk.Ut), vp(wk.Vt), vp(wk.sample_sq), vp(wk.low_sq), vp(wk.partial),
             vp(wk.state), vp(wk.state_host), threshold, float(eps_scaled), _cabi.stream()), 'conv3_broyden')
-        state = wk.state_host.numpy().view(_b._STATE_DTYPE)[0]
+        state = wk.host_state()
         info = _b._result_dict(wk, state, (B, d), eps_scaled, threshold)
         info['result'] = self._from_rows(info['result'].view(M, P.c), meta)
         if ops.GEMM_PROFILE['on']:
@@ -796,9 +815,10 @@ class BranchProgram(object):
         return gx, self._finish_param_grads(ws, wbars, bbars, betabars)
 
     # ---------------------------------------------------------------- Neumann estimator gradient
-    def neumann(self, saved, w_vec, v_vec, seed_scale=None):
+    def neumann(self, saved, w_vec, v_vec, seed_scale=None, want_tangent=False):
         """S_b = <w_b^T J_b, v_b> together with dS/dx and dS/dtheta of S = sum_b c_b S_b
-        (c = seed_scale or 1), by one tangent sweep and one two-adjoint reverse sweep."""
+        (c = seed_scale or 1), by one tangent sweep and one two-adjoint reverse sweep.
+        want_tangent: also return J v (module layout), the by-product of the tangent sweep."""
         meta, M, pres, ains = saved.meta, saved.M, saved.pres, self._ains(saved)
         ws = self._prep(M)
         n = len(self.stages)
@@ -883,4 +903,6 @@ class BranchProgram(object):
             gx = self._from_rows(Ybar.f32(), meta)
         else:
             gx = torch.zeros_like(v_vec)
+        if want_tangent:
+            return S, gx, self._finish_param_grads(ws, wbars, bbars, betabars), self._from_rows(tout, meta)
         return S, gx, self._finish_param_grads(ws, wbars, bbars, betabars)

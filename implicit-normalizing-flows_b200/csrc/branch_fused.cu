@@ -50,6 +50,7 @@ struct BranchArgs {
   int N3;
   const float* beta1;    // device scalars softplus(beta) (LipSwish) or null
   const float* beta2;
+  const int* gate;       // device gate of the sync-free solver loop (common.cuh) or null
 };
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -165,7 +166,7 @@ k_branch3(const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ C
   const int n_halves = args.C / 256;
   const int NC3 = 256 / TC_BK;             // K chunks of layer 3 per item
   const long long m_tiles = (args.M + TC_BM - 1) / TC_BM;
-  const long long num_items = m_tiles * n_halves;
+  long long num_items = m_tiles * n_halves;
 
   pdl_trigger();     // col2im behind this kernel may be scheduled as its CTAs retire
   if (warp == 0 && lane == 0) {
@@ -205,6 +206,7 @@ k_branch3(const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();        // the set-up above overlapped the predecessor (im2col); no global memory was touched yet
+  if (gate_closed(args.gate)) num_items = 0;   // speculative solver iteration after the loop ended (uniform)
 
   if (warp == 0) {
     // ================= TMA producer: weight chunks =================
@@ -517,7 +519,7 @@ extern "C" int impflow_branch3_tc(const float* x0, long long ldx, const float* W
       make_map(&maps[2], W2_hi, C, C, C, 256) || make_map(&maps[3], W2_lo, C, C, C, 256) ||
       make_map(&maps[4], W3_hi, N3, C, C, 32) || make_map(&maps[5], W3_lo, N3, C, C, 32))
     return -1;
-  BranchArgs a{x0, ldx, bias1, bias2, mul1, mul2, pre1_out, pre2_out, out, ldo, M, C, N3, beta1, beta2};
+  BranchArgs a{x0, ldx, bias1, bias2, mul1, mul2, pre1_out, pre2_out, out, ldo, M, C, N3, beta1, beta2, g_gate};
   cudaStream_t s = (cudaStream_t)stream;
   switch (act_kind) {
     case IMPFLOW_ACT_LIPSWISH: return launch_branch3<IMPFLOW_ACT_LIPSWISH>(maps, a, s);

@@ -75,7 +75,10 @@ __device__ void decide(impflow_broyden_state* st, double total, bool init) {
 // grid (S, B): CTA (s,b) reduces slice s of sample b.
 __global__ void __launch_bounds__(kThreads)
 k_norm_decide(const float* __restrict__ g, float* __restrict__ partial, float* __restrict__ sample_sq,
-              float* __restrict__ low_sq, impflow_broyden_state* st, int B, long long d, int S, int init) {
+              float* __restrict__ low_sq, impflow_broyden_state* st, int B, long long d, int S, int init, int gated,
+              BroydenProgress* progress) {
+  // speculative iteration of the sync-free loop: the while-condition already failed on the device (uniform)
+  if (gated && ((volatile impflow_broyden_state*)st)->active == 0) return;
   const int b = blockIdx.y, s = blockIdx.x;
   const long long chunk = (d + S - 1) / S;
   const long long lo = (long long)s * chunk;
@@ -125,6 +128,13 @@ k_norm_decide(const float* __restrict__ g, float* __restrict__ partial, float* _
     st->counter = 0;
     decide(st, t, init != 0);
     __threadfence();
+    if (progress != nullptr) {      // mapped pinned host memory: the host polls this record instead of syncing
+      volatile BroydenProgress* pr = progress + st->nstep;
+      pr->active = st->active;
+      __threadfence_system();
+      pr->seq = st->nstep;
+      __threadfence_system();
+    }
   }
   __syncthreads();
   if (init || ((volatile impflow_broyden_state*)st)->new_lowest) {
@@ -161,10 +171,11 @@ __global__ void __launch_bounds__(kThreads)
 k_update(float* __restrict__ x_old, const float* __restrict__ g_old, const float* __restrict__ xn,
          const float* __restrict__ gn, float* __restrict__ Ut, float* __restrict__ Vt,
          float* __restrict__ low_x, float* __restrict__ low_g, const impflow_broyden_state* st, long long d,
-         int T, int SL) {
+         int T, int SL, int expect_nstep) {
   const int do_update = st->do_update;
   const int new_low = st->new_lowest;
   if (!do_update && !new_low) return;  // uniform over the whole grid
+  if (expect_nstep >= 0 && st->nstep != expect_nstep) return;   // this iteration's decision kernel was gated off
 
   cg::cluster_group cluster = cg::this_cluster();
   const int C = cluster.num_blocks();
@@ -365,10 +376,11 @@ __global__ void __launch_bounds__(kThreads)
 k_update_small(float* __restrict__ x_old, const float* __restrict__ g_old, const float* __restrict__ xn,
                const float* __restrict__ gn, float* __restrict__ Ut, float* __restrict__ Vt,
                float* __restrict__ low_x, float* __restrict__ low_g, const impflow_broyden_state* st, int B,
-               int d, int T) {
+               int d, int T, int expect_nstep) {
   const int do_update = st->do_update;
   const int new_low = st->new_lowest;
   if (!do_update && !new_low) return;
+  if (expect_nstep >= 0 && st->nstep != expect_nstep) return;
   const int b = blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
@@ -474,12 +486,21 @@ extern "C" size_t impflow_broyden_workspace_floats(int B, long long d, int thres
 }
 
 static int launch_norm(const float* g, float* partial, float* sample_sq, float* low_sq,
-                       impflow_broyden_state* state, int B, long long d, int init, cudaStream_t s);
+                       impflow_broyden_state* state, int B, long long d, int init, int gated,
+                       BroydenProgress* progress, cudaStream_t s);
 
 extern "C" int impflow_broyden_begin(const float* x0, const float* g0, float* xn, float* low_x, float* low_g,
                                      float* sample_sq, float* low_sq, float* partial,
                                      impflow_broyden_state* state, int B, long long d, int threshold,
                                      double eps_scaled, void* stream) {
+  return broyden_begin_ex(x0, g0, xn, low_x, low_g, sample_sq, low_sq, partial, state, B, d, threshold, eps_scaled,
+                          nullptr, stream);
+}
+
+int impflow::broyden_begin_ex(const float* x0, const float* g0, float* xn, float* low_x, float* low_g,
+                              float* sample_sq, float* low_sq, float* partial, impflow_broyden_state* state, int B,
+                              long long d, int threshold, double eps_scaled, BroydenProgress* progress,
+                              void* stream) {
   IMPFLOW_REQUIRE(threshold >= 1 && threshold <= kMaxT, "broyden: threshold %d not in [1,%d]", threshold, kMaxT);
   IMPFLOW_REQUIRE(B >= 1 && d >= 1, "broyden: empty problem B=%d d=%lld", B, d);
   cudaStream_t s = (cudaStream_t)stream;
@@ -488,14 +509,15 @@ extern "C" int impflow_broyden_begin(const float* x0, const float* g0, float* xn
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_begin<<<blocks, 256, 0, s>>>(x0, g0, xn, low_x, low_g, n, state, threshold, eps_scaled);
   if (check_launch("k_begin")) return -1;
-  return launch_norm(g0, partial, sample_sq, low_sq, state, B, d, 1, s);
+  return launch_norm(g0, partial, sample_sq, low_sq, state, B, d, 1, 0, progress, s);
 }
 
 static int launch_norm(const float* g, float* partial, float* sample_sq, float* low_sq,
-                       impflow_broyden_state* state, int B, long long d, int init, cudaStream_t s) {
+                       impflow_broyden_state* state, int B, long long d, int init, int gated,
+                       BroydenProgress* progress, cudaStream_t s) {
   const int S = pick_splits(B, d);
   dim3 grid(S, B);
-  k_norm_decide<<<grid, kThreads, 0, s>>>(g, partial, sample_sq, low_sq, state, B, d, S, init);
+  k_norm_decide<<<grid, kThreads, 0, s>>>(g, partial, sample_sq, low_sq, state, B, d, S, init, gated, progress);
   return check_launch("k_norm_decide");
 }
 
@@ -503,13 +525,21 @@ extern "C" int impflow_broyden_step(float* x_old, const float* g_old, const floa
                                     float* Ut, float* Vt, float* low_x, float* low_g, float* sample_sq,
                                     float* low_sq, float* partial, impflow_broyden_state* state, int B,
                                     long long d, int threshold, void* stream) {
+  return broyden_step_ex(x_old, g_old, xn, gn, Ut, Vt, low_x, low_g, sample_sq, low_sq, partial, state, B, d,
+                         threshold, 0, -1, nullptr, stream);
+}
+
+int impflow::broyden_step_ex(float* x_old, const float* g_old, const float* xn, const float* gn, float* Ut,
+                             float* Vt, float* low_x, float* low_g, float* sample_sq, float* low_sq, float* partial,
+                             impflow_broyden_state* state, int B, long long d, int threshold, int gated,
+                             int expect_nstep, BroydenProgress* progress, void* stream) {
   IMPFLOW_REQUIRE(threshold >= 1 && threshold <= kMaxT, "broyden: threshold %d not in [1,%d]", threshold, kMaxT);
   cudaStream_t s = (cudaStream_t)stream;
-  if (launch_norm(gn, partial, sample_sq, low_sq, state, B, d, 0, s)) return -1;
+  if (launch_norm(gn, partial, sample_sq, low_sq, state, B, d, 0, gated, progress, s)) return -1;
   if (d <= 128) {
     const int blocks = (B + kWarps - 1) / kWarps;
     k_update_small<<<blocks, kThreads, 0, s>>>(x_old, g_old, xn, gn, Ut, Vt, low_x, low_g, state, B, (int)d,
-                                               threshold);
+                                               threshold, expect_nstep);
     return check_launch("k_update_small");
   }
   IMPFLOW_REQUIRE(d <= 8LL * 8192, "broyden: d=%lld exceeds the cluster kernel limit 65536", d);
@@ -537,7 +567,7 @@ extern "C" int impflow_broyden_step(float* x_old, const float* g_old, const floa
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, x_old, g_old, xn, gn, Ut, Vt, low_x, low_g,
-                                     (const impflow_broyden_state*)state, d, threshold, SL);
+                                     (const impflow_broyden_state*)state, d, threshold, SL, expect_nstep);
   if (e != cudaSuccess) {
     set_error("broyden_step: cluster launch failed: %s", cudaGetErrorString(e));
     return -1;

@@ -14,6 +14,33 @@ void set_error(const char* fmt, ...);
 extern long long g_launch_count;
 extern int g_pdl;     // programmatic dependent launch of the tile kernels (impflow_set_pdl)
 
+// Device-side gate of the sync-free Broyden loop (conv3_plan.cu).  The host enqueues solver iterations AHEAD of the
+// device-side convergence decision; every kernel of such a speculative iteration receives the address of
+// state->active and turns into a no-op when the loop has already ended on the device (broyden.py:153 evaluated
+// by k_norm_decide).  The launchers of the gated kernels read this thread-local; nullptr = not gated.
+extern thread_local const int* g_gate;
+struct GateScope {
+  const int* prev;
+  explicit GateScope(const int* gate) : prev(g_gate) { g_gate = gate; }
+  ~GateScope() { g_gate = prev; }
+};
+__device__ __forceinline__ bool gate_closed(const int* gate) { return gate != nullptr && __ldcg(gate) == 0; }
+
+// Progress record of the sync-free loop, written by the device into MAPPED PINNED host memory (one per iteration,
+// index = nstep) and polled by the host: seq == nstep once iteration nstep has been decided.
+struct BroydenProgress {
+  int seq;
+  int active;
+};
+int broyden_begin_ex(const float* x0, const float* g0, float* xn, float* low_x, float* low_g, float* sample_sq,
+                     float* low_sq, float* partial, impflow_broyden_state* state, int B, long long d, int threshold,
+                     double eps_scaled, BroydenProgress* progress, void* stream);
+// expect_nstep >= 0: k_update only acts if the decision kernel of THIS iteration really ran (state->nstep == expect)
+int broyden_step_ex(float* x_old, const float* g_old, const float* xn, const float* gn, float* Ut, float* Vt,
+                    float* low_x, float* low_g, float* sample_sq, float* low_sq, float* partial,
+                    impflow_broyden_state* state, int B, long long d, int threshold, int gated, int expect_nstep,
+                    BroydenProgress* progress, void* stream);
+
 // Programmatic dependent launch (PDL).  A tile kernel launched with the stream-serialisation attribute may be
 // scheduled while its predecessor still runs: its prologue (barrier init, TMEM allocation, tensor-map prefetch)
 // overlaps the predecessor's tail, and pdl_wait() — executed by every thread before the first global-memory

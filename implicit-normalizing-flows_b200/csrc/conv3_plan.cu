@@ -61,90 +61,255 @@ static int plan_check(const impflow_conv3_plan* p, const char* who) {
   return 0;
 }
 
-// y_rows = nnet(x_rows); pre1/pre2 (optional) receive the pre-activations of the two hidden layers.
-static int conv3_forward(const impflow_conv3_plan* p, const float* x_rows, float* y_rows, float* pre1, float* pre2,
-                         void* stream) {
-  const long long M = (long long)p->B * p->H * p->W;
-  const Conv3Ws w = carve(p->ws, M, p->c, p->C, p->k0);
-  const float* xin = x_rows;
-  if (p->act0_kind != IMPFLOW_ACT_NONE) {
-    if (impflow_act_mul(x_rows, nullptr, w.xin, M * p->c, p->act0_kind, 0, p->beta0, stream)) return -1;
-    xin = w.xin;
-  }
-  const int N3 = 9 * p->c;
-  if (use_tile_kernel(p)) {
-    // zero first: the tile kernel then directly follows im2col and its set-up overlaps it (PDL, common.cuh)
-    if (p->C > 256 && cudaMemsetAsync(w.Y, 0, sizeof(float) * (size_t)M * N3, (cudaStream_t)stream) != cudaSuccess) {
-      set_error("conv3_forward: memset failed");
-      return -1;
-    }
-    if (impflow_im2col3x3(xin, w.x0, p->B, p->H, p->W, p->c, 32, stream)) return -1;
-    if (impflow_branch3_tc(w.x0, 32, p->W1f_hi, p->W1f_lo, p->W2f_hi, p->W2f_lo, p->W3f_hi, p->W3f_lo, p->b1, p->b2,
-                           nullptr, nullptr, pre1, pre2, w.Y, N3, M, p->C, N3, p->act_kind, p->beta1, p->beta2,
-                           stream))
-      return -1;
-  } else {
-    float* x0_hi = w.x0;
-    float* x0_lo = w.x0 + (size_t)M * p->k0;
-    float* h1_hi = w.h1;
-    float* h1_lo = w.h1 + (size_t)M * p->C;
-    float* h2_hi = w.h2;
-    float* h2_lo = w.h2 + (size_t)M * p->C;
-    if (impflow_im2col3x3_split(xin, x0_hi, x0_lo, p->B, p->H, p->W, p->c, p->k0, stream)) return -1;
-    if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W1f_hi, p->W1f_lo, p->k0, p->b1, pre1, nullptr, nullptr, h1_hi,
-                           h1_lo, p->C, M, p->C, p->k0, p->act_kind, p->beta1, nullptr, stream))
-      return -1;
-    if (impflow_gemm_nt_tc(h1_hi, h1_lo, p->C, p->W2f_hi, p->W2f_lo, p->C, p->b2, pre2, nullptr, nullptr, h2_hi, h2_lo,
-                           p->C, M, p->C, p->C, p->act_kind, p->beta2, nullptr, stream))
-      return -1;
-    if (impflow_gemm_nt_tc(h2_hi, h2_lo, p->C, p->W3f_hi, p->W3f_lo, p->C, nullptr, w.Y, nullptr, nullptr, nullptr,
-                           nullptr, N3, M, N3, p->C, IMPFLOW_ACT_NONE, nullptr, nullptr, stream))
-      return -1;
-  }
-  return impflow_col2im3x3(w.Y, p->B, p->H, p->W, p->c, p->b3, y_rows, nullptr, nullptr, IMPFLOW_ACT_NONE, nullptr,
-                           stream);
+// ------------------------------------------------------------------------------------------------------------
+// Glue kernels either side of the tile kernel / GEMM chain, one launch each (they replace act_mul + im2col
+// (+ memset) in front and col2im + lincomb3 behind):
+//
+//   k_conv3_in :  X0[p, (ky,kx,ci)] = act0(x)[p + (ky-1,kx-1), ci]   fp32 rows (tile kernel) or tf32 hi/lo planes
+//                 (GEMM chain), tail columns zero; also zero-fills the tap accumulator Y when the tile kernel
+//                 sums two channel halves into it.
+//   k_conv3_out:  val = col2im(Y) (+ bias3)            forward
+//                     = col2im(Y) * act0'(pre0)        transposed sweep with a leading activation
+//                 and, in the same pass,
+//                   plain    : out = val
+//                   fwd resid: out = (rhs - val) - x           g(z) = x_embed - f(z) - z   (implicit_block.py:72)
+//                   bwd resid: out = (val + x) - rhs           g(v) = v^T J + v - grad     (:199-203)
+//                   chain    : out = val, acc = fma(val, coeff, acc)   w += c_k v^T J^k    (:431-435)
+//                 (the same roundings, in the same order, as the separate lincomb3 launches they replace)
+// Both honour the device gate of the sync-free solver loop (common.cuh).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32_1(float v, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  hi = __uint_as_float(h);
+  lo = v - hi;
 }
 
-// out_rows = v^T J at the saved point (pre0 = the branch input rows when it has a leading activation).
-static int conv3_vjp(const impflow_conv3_plan* p, const float* pre0, const float* d1, const float* d2,
-                     const float* v_rows, float* out_rows, void* stream) {
+__global__ void __launch_bounds__(256)
+k_conv3_in(const float* __restrict__ x, float* __restrict__ col, float* __restrict__ col_lo, float* __restrict__ zero,
+           long long zero_n4, int B, int H, int W, int C, int ld, int act0_kind, const float* __restrict__ beta0,
+           const int* gate) {
+  pdl_trigger();
+  pdl_wait();
+  if (gate_closed(gate)) return;
+  const float beta = (beta0 != nullptr) ? __ldg(beta0) : 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (zero != nullptr) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = tid; i < zero_n4; i += stride) reinterpret_cast<float4*>(zero)[i] = z;
+  }
+  const int groups = ld / 4;
+  const long long total = (long long)B * H * W * groups;
+  const int K = 9 * C;
+  for (long long i = tid; i < total; i += stride) {
+    const long long p = i / groups;
+    const int k0 = (int)(i - p * groups) * 4;
+    const int xx = (int)(p % W);
+    const int yy = (int)((p / W) % H);
+    const long long img = p - (long long)yy * W - xx;
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u;
+      v[u] = 0.f;
+      if (k < K) {
+        const int tap = k / C, c = k - tap * C;
+        const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+          const float xv = __ldg(x + (img + (long long)sy * W + sx) * C + c);
+          v[u] = act0_kind == IMPFLOW_ACT_NONE ? xv : act_dispatch(act0_kind, xv, 0, beta);
+        }
+      }
+    }
+    float* dst = col + p * ld + k0;
+    if (col_lo != nullptr) {
+      float h[4], l[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) split_tf32_1(v[u], h[u], l[u]);
+      *reinterpret_cast<float4*>(dst) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(col_lo + p * ld + k0) = make_float4(l[0], l[1], l[2], l[3]);
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+enum { OUT_PLAIN = 0, OUT_FWD_RESIDUAL = 1, OUT_BWD_RESIDUAL = 2, OUT_CHAIN = 3 };
+
+struct Conv3Out {
+  const float* col;     // [M, 9c] tap-major accumulator
+  const float* bias;    // [c] or null
+  const float* pre0;    // [M, c] or null: multiply by act0'(pre0)
+  const float* beta0;
+  int act0_kind;
+  int mode;
+  const float* x;       // residual modes: the iterate
+  const float* rhs;     // residual modes: x_embed / incoming gradient
+  float* out;           // [M, c]
+  float* acc;           // chain mode: w
+  float coeff;
+  const int* gate;
+};
+
+__global__ void __launch_bounds__(256) k_conv3_out(int B, int H, int W, int C, Conv3Out a) {
+  pdl_trigger();
+  pdl_wait();
+  if (gate_closed(a.gate)) return;
+  const float beta = (a.beta0 != nullptr) ? __ldg(a.beta0) : 0.f;
+  const long long total = (long long)B * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long p = i / C;
+    const int xx = (int)(p % W);
+    const int yy = (int)((p / W) % H);
+    const long long b = p / ((long long)W * H);
+    float sum = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sy = yy - (tap / 3 - 1), sx = xx - (tap % 3 - 1);
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) sum += a.col[(((b * H + sy) * W + sx) * 9 + tap) * C + c];
+    }
+    float val;
+    if (a.pre0 != nullptr) {
+      val = sum * act_dispatch(a.act0_kind, a.pre0[i], 1, beta);
+    } else {
+      val = sum + (a.bias != nullptr ? a.bias[c] : 0.f);
+    }
+    float r = val;
+    if (a.mode == OUT_FWD_RESIDUAL) {
+      r = a.rhs[i] - val;
+      r = r - a.x[i];
+    } else if (a.mode == OUT_BWD_RESIDUAL) {
+      r = val + a.x[i];
+      r = r - a.rhs[i];
+    } else if (a.mode == OUT_CHAIN) {
+      a.acc[i] = fmaf(val, a.coeff, a.acc[i]);
+    }
+    a.out[i] = r;
+  }
+}
+
+static inline int grid_cap(long long n, int per) {
+  long long g = (n + per - 1) / per;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static int launch_in(const impflow_conv3_plan* p, const float* x_rows, int act0_kind, const float* beta0, float* col,
+                     float* col_lo, int ld, float* zero, long long zero_n, cudaStream_t s) {
   const long long M = (long long)p->B * p->H * p->W;
-  const Conv3Ws w = carve(p->ws, M, p->c, p->C, p->k0);
-  const int N3 = 9 * p->c;
-  if (use_tile_kernel(p)) {
-    if (p->C > 256 && cudaMemsetAsync(w.Y, 0, sizeof(float) * (size_t)M * N3, (cudaStream_t)stream) != cudaSuccess) {
-      set_error("conv3_vjp: memset failed");
+  if ((zero_n & 3) != 0) {       // odd tap-accumulator size: fall back to a memset (never the case for M % 128 == 0)
+    if (zero != nullptr && cudaMemsetAsync(zero, 0, sizeof(float) * (size_t)zero_n, s) != cudaSuccess) {
+      set_error("conv3: memset failed");
       return -1;
     }
-    if (impflow_im2col3x3(v_rows, w.x0, p->B, p->H, p->W, p->c, 32, stream)) return -1;
-    if (impflow_branch3_tc(w.x0, 32, p->W3b_hi, p->W3b_lo, p->W2b_hi, p->W2b_lo, p->W1b_hi, p->W1b_lo, nullptr,
-                           nullptr, d2, d1, nullptr, nullptr, w.Y, N3, M, p->C, N3, IMPFLOW_ACT_NONE, nullptr, nullptr,
-                           stream))
-      return -1;
-  } else {
-    float* x0_hi = w.x0;
-    float* x0_lo = w.x0 + (size_t)M * p->k0;
-    float* t3_hi = w.h1;
-    float* t3_lo = w.h1 + (size_t)M * p->C;
-    float* t2_hi = w.h2;
-    float* t2_lo = w.h2 + (size_t)M * p->C;
-    if (impflow_im2col3x3_split(v_rows, x0_hi, x0_lo, p->B, p->H, p->W, p->c, p->k0, stream)) return -1;
-    if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W3b_hi, p->W3b_lo, p->k0, nullptr, nullptr, nullptr, d2, t3_hi,
-                           t3_lo, p->C, M, p->C, p->k0, IMPFLOW_ACT_MULTIPLIER, nullptr, nullptr, stream))
-      return -1;
-    if (impflow_gemm_nt_tc(t3_hi, t3_lo, p->C, p->W2b_hi, p->W2b_lo, p->C, nullptr, nullptr, nullptr, d1, t2_hi, t2_lo,
-                           p->C, M, p->C, p->C, IMPFLOW_ACT_MULTIPLIER, nullptr, nullptr, stream))
-      return -1;
-    if (impflow_gemm_nt_tc(t2_hi, t2_lo, p->C, p->W1b_hi, p->W1b_lo, p->C, nullptr, w.Y, nullptr, nullptr, nullptr,
-                           nullptr, N3, M, N3, p->C, IMPFLOW_ACT_NONE, nullptr, nullptr, stream))
-      return -1;
+    zero = nullptr;
   }
-  if (p->act0_kind != IMPFLOW_ACT_NONE)
-    return impflow_col2im3x3(w.Y, p->B, p->H, p->W, p->c, nullptr, out_rows, nullptr, pre0, p->act0_kind, p->beta0,
-                             stream);
-  return impflow_col2im3x3(w.Y, p->B, p->H, p->W, p->c, nullptr, out_rows, nullptr, nullptr, IMPFLOW_ACT_NONE, nullptr,
-                           stream);
+  const cudaError_t e = launch_pdl(k_conv3_in, grid_cap(M * (ld / 4), 256), 256, s, x_rows, col, col_lo, zero,
+                                   zero_n >> 2, p->B, p->H, p->W, p->c, ld, act0_kind, beta0, g_gate);
+  if (e != cudaSuccess) {
+    set_error("k_conv3_in: launch failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return check_launch("k_conv3_in");
 }
+
+static int launch_out(const impflow_conv3_plan* p, Conv3Out a, cudaStream_t s) {
+  const long long total = (long long)p->B * p->H * p->W * p->c;
+  a.gate = g_gate;
+  const cudaError_t e = launch_pdl(k_conv3_out, grid_cap(total, 256), 256, s, p->B, p->H, p->W, p->c, a);
+  if (e != cudaSuccess) {
+    set_error("k_conv3_out: launch failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return check_launch("k_conv3_out");
+}
+
+// Y (tap accumulator, [M, 9c]) = the three-layer chain applied to x_rows, forward (act0 applied to the input on the fly).
+static int conv3_chain_forward(const impflow_conv3_plan* p, const Conv3Ws& w, const float* x_rows, float* pre1,
+                               float* pre2, void* stream) {
+  const long long M = (long long)p->B * p->H * p->W;
+  const int N3 = 9 * p->c;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (use_tile_kernel(p)) {
+    if (launch_in(p, x_rows, p->act0_kind, p->beta0, w.x0, nullptr, 32, p->C > 256 ? w.Y : nullptr, M * N3, s)) return -1;
+    return impflow_branch3_tc(w.x0, 32, p->W1f_hi, p->W1f_lo, p->W2f_hi, p->W2f_lo, p->W3f_hi, p->W3f_lo, p->b1, p->b2,
+                              nullptr, nullptr, pre1, pre2, w.Y, N3, M, p->C, N3, p->act_kind, p->beta1, p->beta2,
+                              stream);
+  }
+  float* x0_hi = w.x0;
+  float* x0_lo = w.x0 + (size_t)M * p->k0;
+  float* h1_hi = w.h1;
+  float* h1_lo = w.h1 + (size_t)M * p->C;
+  float* h2_hi = w.h2;
+  float* h2_lo = w.h2 + (size_t)M * p->C;
+  if (launch_in(p, x_rows, p->act0_kind, p->beta0, x0_hi, x0_lo, p->k0, nullptr, 0, s)) return -1;
+  if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W1f_hi, p->W1f_lo, p->k0, p->b1, pre1, nullptr, nullptr, h1_hi,
+                         h1_lo, p->C, M, p->C, p->k0, p->act_kind, p->beta1, nullptr, stream))
+    return -1;
+  if (impflow_gemm_nt_tc(h1_hi, h1_lo, p->C, p->W2f_hi, p->W2f_lo, p->C, p->b2, pre2, nullptr, nullptr, h2_hi, h2_lo,
+                         p->C, M, p->C, p->C, p->act_kind, p->beta2, nullptr, stream))
+    return -1;
+  return impflow_gemm_nt_tc(h2_hi, h2_lo, p->C, p->W3f_hi, p->W3f_lo, p->C, nullptr, w.Y, nullptr, nullptr, nullptr,
+                            nullptr, N3, M, N3, p->C, IMPFLOW_ACT_NONE, nullptr, nullptr, stream);
+}
+
+// Y = the transposed chain applied to v_rows (d1, d2 = act'(pre) of the two hidden layers).
+static int conv3_chain_vjp(const impflow_conv3_plan* p, const Conv3Ws& w, const float* d1, const float* d2,
+                           const float* v_rows, void* stream) {
+  const long long M = (long long)p->B * p->H * p->W;
+  const int N3 = 9 * p->c;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (use_tile_kernel(p)) {
+    if (launch_in(p, v_rows, IMPFLOW_ACT_NONE, nullptr, w.x0, nullptr, 32, p->C > 256 ? w.Y : nullptr, M * N3, s))
+      return -1;
+    return impflow_branch3_tc(w.x0, 32, p->W3b_hi, p->W3b_lo, p->W2b_hi, p->W2b_lo, p->W1b_hi, p->W1b_lo, nullptr,
+                              nullptr, d2, d1, nullptr, nullptr, w.Y, N3, M, p->C, N3, IMPFLOW_ACT_NONE, nullptr, nullptr,
+                              stream);
+  }
+  float* x0_hi = w.x0;
+  float* x0_lo = w.x0 + (size_t)M * p->k0;
+  float* t3_hi = w.h1;
+  float* t3_lo = w.h1 + (size_t)M * p->C;
+  float* t2_hi = w.h2;
+  float* t2_lo = w.h2 + (size_t)M * p->C;
+  if (launch_in(p, v_rows, IMPFLOW_ACT_NONE, nullptr, x0_hi, x0_lo, p->k0, nullptr, 0, s)) return -1;
+  if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W3b_hi, p->W3b_lo, p->k0, nullptr, nullptr, nullptr, d2, t3_hi,
+                         t3_lo, p->C, M, p->C, p->k0, IMPFLOW_ACT_MULTIPLIER, nullptr, nullptr, stream))
+    return -1;
+  if (impflow_gemm_nt_tc(t3_hi, t3_lo, p->C, p->W2b_hi, p->W2b_lo, p->C, nullptr, nullptr, nullptr, d1, t2_hi, t2_lo,
+                         p->C, M, p->C, p->C, IMPFLOW_ACT_MULTIPLIER, nullptr, nullptr, stream))
+    return -1;
+  return impflow_gemm_nt_tc(t2_hi, t2_lo, p->C, p->W1b_hi, p->W1b_lo, p->C, nullptr, w.Y, nullptr, nullptr, nullptr,
+                            nullptr, N3, M, N3, p->C, IMPFLOW_ACT_NONE, nullptr, nullptr, stream);
+}
+
+static Conv3Out out_forward(const impflow_conv3_plan* p, const Conv3Ws& w, float* out) {
+  Conv3Out a;
+  memset(&a, 0, sizeof(a));
+  a.col = w.Y;
+  a.bias = p->b3;
+  a.act0_kind = IMPFLOW_ACT_NONE;
+  a.mode = OUT_PLAIN;
+  a.out = out;
+  return a;
+}
+
+static Conv3Out out_vjp(const impflow_conv3_plan* p, const Conv3Ws& w, const float* pre0, float* out) {
+  Conv3Out a;
+  memset(&a, 0, sizeof(a));
+  a.col = w.Y;
+  a.act0_kind = p->act0_kind;
+  a.beta0 = p->beta0;
+  a.pre0 = p->act0_kind != IMPFLOW_ACT_NONE ? pre0 : nullptr;
+  a.mode = OUT_PLAIN;
+  a.out = out;
+  return a;
+}
+
+static int g_runahead = 2;     // iterations the host may enqueue beyond the last decision it has seen (0 = sync per iteration)
 
 }  // namespace impflow
 
@@ -157,7 +322,11 @@ extern "C" size_t impflow_conv3_workspace_floats(int B, int H, int W, int c, int
 extern "C" int impflow_conv3_forward(const impflow_conv3_plan* plan, const float* x_rows, float* y_rows, float* pre1,
                                      float* pre2, void* stream) {
   if (plan_check(plan, "conv3_forward")) return -3;
-  return conv3_forward(plan, x_rows, y_rows, pre1, pre2, stream);
+  const long long M = (long long)plan->B * plan->H * plan->W;
+  const Conv3Ws w = carve(plan->ws, M, plan->c, plan->C, plan->k0);
+  GateScope ungated(nullptr);
+  if (conv3_chain_forward(plan, w, x_rows, pre1, pre2, stream)) return -1;
+  return launch_out(plan, out_forward(plan, w, y_rows), (cudaStream_t)stream);
 }
 
 extern "C" int impflow_conv3_prepare_vjp(const impflow_conv3_plan* plan, const float* pre1, const float* pre2,
@@ -172,27 +341,56 @@ extern "C" int impflow_conv3_vjp(const impflow_conv3_plan* plan, const float* pr
                                  const float* v_rows, float* out_rows, void* stream) {
   if (plan_check(plan, "conv3_vjp")) return -3;
   IMPFLOW_REQUIRE(plan->act0_kind == IMPFLOW_ACT_NONE || pre0 != nullptr, "conv3_vjp: pre0 missing");
-  return conv3_vjp(plan, pre0, d1, d2, v_rows, out_rows, stream);
+  const long long M = (long long)plan->B * plan->H * plan->W;
+  const Conv3Ws w = carve(plan->ws, M, plan->c, plan->C, plan->k0);
+  GateScope ungated(nullptr);
+  if (conv3_chain_vjp(plan, w, d1, d2, v_rows, stream)) return -1;
+  return launch_out(plan, out_vjp(plan, w, pre0, out_rows), (cudaStream_t)stream);
 }
 
 extern "C" int impflow_conv3_power_series(const impflow_conv3_plan* plan, const float* pre0, const float* d1,
                                           const float* d2, const float* v_rows, const double* coeffs, int n,
-                                          float* w_rows, void* stream) {
+                                          float* w_rows, const double* dot_coeffs, float* dot_out, void* stream) {
   if (plan_check(plan, "conv3_power_series")) return -3;
   IMPFLOW_REQUIRE(plan->act0_kind == IMPFLOW_ACT_NONE || pre0 != nullptr, "conv3_power_series: pre0 missing");
+  IMPFLOW_REQUIRE((w_rows != nullptr && coeffs != nullptr) || (dot_out != nullptr && dot_coeffs != nullptr),
+                  "conv3_power_series: neither the Neumann sum nor the Hutchinson dots were requested");
+  IMPFLOW_REQUIRE((dot_out == nullptr) == (dot_coeffs == nullptr), "conv3_power_series: dot_out and dot_coeffs go together");
   const long long M = (long long)plan->B * plan->H * plan->W;
   const long long nel = M * plan->c;
+  const long long d = nel / plan->B;
   const Conv3Ws w = carve(plan->ws, M, plan->c, plan->C, plan->k0);
-  if (impflow_lincomb3(v_rows, 1.f, nullptr, 0.f, nullptr, 0.f, w_rows, nel, stream)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  GateScope ungated(nullptr);
+  if (w_rows != nullptr && impflow_lincomb3(v_rows, 1.f, nullptr, 0.f, nullptr, 0.f, w_rows, nel, stream)) return -1;
   const float* cur = v_rows;
   float* bufs[2] = {w.chain_a, w.chain_b};
   for (int k = 0; k < n; ++k) {
     float* nxt = bufs[k & 1];
-    if (conv3_vjp(plan, pre0, d1, d2, cur, nxt, stream)) return -1;
-    if (impflow_lincomb3(w_rows, 1.f, nxt, (float)coeffs[k], nullptr, 0.f, w_rows, nel, stream)) return -1;
+    if (conv3_chain_vjp(plan, w, d1, d2, cur, stream)) return -1;
+    Conv3Out a = out_vjp(plan, w, pre0, nxt);
+    if (w_rows != nullptr) {        // w += c_k v^T J^k in the col2im epilogue (implicit_block.py:435)
+      a.mode = OUT_CHAIN;
+      a.acc = w_rows;
+      a.coeff = (float)coeffs[k];
+    }
+    if (launch_out(plan, a, s)) return -1;
+    if (dot_out != nullptr &&       // Hutchinson term alpha_k <v^T J^k, v> per sample (:423)
+        impflow_rowdot(nxt, v_rows, dot_out, plan->B, d, (float)dot_coeffs[k], k == 0 ? 0.f : 1.f, stream))
+      return -1;
     cur = nxt;
   }
   return 0;
+}
+
+extern "C" int impflow_conv3_set_runahead(int iterations) {
+  const int prev = g_runahead;
+  g_runahead = iterations < 0 ? 0 : (iterations > 8 ? 8 : iterations);
+  return prev;
+}
+
+extern "C" size_t impflow_conv3_broyden_host_bytes(int threshold) {
+  return sizeof(impflow_broyden_state) + sizeof(BroydenProgress) * (size_t)(threshold + 2);
 }
 
 extern "C" int impflow_conv3_broyden(const impflow_conv3_plan* plan, int mode, const float* rhs_rows,
@@ -204,20 +402,27 @@ extern "C" int impflow_conv3_broyden(const impflow_conv3_plan* plan, int mode, c
   if (plan_check(plan, "conv3_broyden")) return -3;
   IMPFLOW_REQUIRE(mode == 0 || mode == 1, "conv3_broyden: mode must be 0 (forward) or 1 (implicit backward)");
   IMPFLOW_REQUIRE(mode == 0 || plan->act0_kind == IMPFLOW_ACT_NONE || pre0 != nullptr, "conv3_broyden: pre0 missing");
+  IMPFLOW_REQUIRE(threshold >= 1 && threshold <= 63, "conv3_broyden: threshold %d not in [1,63]", threshold);
   const long long M = (long long)plan->B * plan->H * plan->W;
   const long long d = (long long)plan->H * plan->W * plan->c;
-  const long long nel = M * plan->c;
   const Conv3Ws w = carve(plan->ws, M, plan->c, plan->C, plan->k0);
   cudaStream_t s = (cudaStream_t)stream;
-  // residual: forward  g(z) = x_embed - f(z) - z   (implicit_block.py:72)
-  //           backward g(v) = v^T J + v - grad      (:199-203)
+  // residual, written by the col2im epilogue:  forward  g(z) = x_embed - f(z) - z   (implicit_block.py:72)
+  //                                            backward g(v) = v^T J + v - grad      (:199-203)
   auto eval_g = [&](const float* x, float* g) -> int {
+    Conv3Out a;
     if (mode == 0) {
-      if (conv3_forward(plan, x, w.t_rows, nullptr, nullptr, stream)) return -1;
-      return impflow_lincomb3(rhs_rows, 1.f, w.t_rows, -1.f, x, -1.f, g, nel, stream);
+      if (conv3_chain_forward(plan, w, x, nullptr, nullptr, stream)) return -1;
+      a = out_forward(plan, w, g);
+      a.mode = OUT_FWD_RESIDUAL;
+    } else {
+      if (conv3_chain_vjp(plan, w, d1, d2, x, stream)) return -1;
+      a = out_vjp(plan, w, pre0, g);
+      a.mode = OUT_BWD_RESIDUAL;
     }
-    if (conv3_vjp(plan, pre0, d1, d2, x, w.t_rows, stream)) return -1;
-    return impflow_lincomb3(w.t_rows, 1.f, x, 1.f, rhs_rows, -1.f, g, nel, stream);
+    a.x = x;
+    a.rhs = rhs_rows;
+    return launch_out(plan, a, s);
   };
   auto read_state = [&]() -> int {
     if (cudaMemcpyAsync(state_host, state_dev, sizeof(impflow_broyden_state), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
@@ -227,24 +432,81 @@ extern "C" int impflow_conv3_broyden(const impflow_conv3_plan* plan, int mode, c
     }
     return 0;
   };
-  float *x_old = xa, *xn = xb, *g_old = ga, *gn = gb;
-  if (eval_g(x_old, g_old)) return -1;
-  if (impflow_broyden_begin(x_old, g_old, xn, low_x, low_g, sample_sq, low_sq, partial, state_dev, plan->B, d,
-                            threshold, eps_scaled, stream))
-    return -1;
-  if (read_state()) return -1;
-  while (state_host->active) {
-    if (eval_g(xn, gn)) return -1;
-    if (impflow_broyden_step(x_old, g_old, xn, gn, Ut, Vt, low_x, low_g, sample_sq, low_sq, partial, state_dev,
-                             plan->B, d, threshold, stream))
-      return -1;
-    float* t = x_old;      // the kernel wrote the next iterate into the old buffer
-    x_old = xn;
-    xn = t;
-    t = g_old;
-    g_old = gn;
-    gn = t;
-    if (read_state()) return -1;
+  float* xs[2] = {xa, xb};      // iteration it evaluates g at xs[it & 1] (the update kernel writes the next iterate
+  float* gs[2] = {ga, gb};      // into the other buffer): the roles alternate unconditionally, so they are known ahead
+
+  // progress records in mapped pinned memory behind the state record (impflow_conv3_broyden_host_bytes)
+  BroydenProgress* prog_host = reinterpret_cast<BroydenProgress*>(state_host + 1);
+  BroydenProgress* prog_dev = nullptr;
+  int runahead = g_runahead;
+  if (runahead > 0 &&
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&prog_dev), prog_host, 0) != cudaSuccess) {
+    cudaGetLastError();
+    runahead = 0;               // not mapped memory: fall back to one synchronisation per iteration
+    prog_dev = nullptr;
   }
-  return 0;
+
+  if (runahead == 0) {
+    GateScope ungated(nullptr);
+    if (eval_g(xs[0], gs[0])) return -1;
+    if (impflow_broyden_begin(xs[0], gs[0], xs[1], low_x, low_g, sample_sq, low_sq, partial, state_dev, plan->B, d,
+                              threshold, eps_scaled, stream))
+      return -1;
+    if (read_state()) return -1;
+    for (int it = 1; state_host->active; ++it) {
+      if (eval_g(xs[it & 1], gs[it & 1])) return -1;
+      if (impflow_broyden_step(xs[(it - 1) & 1], gs[(it - 1) & 1], xs[it & 1], gs[it & 1], Ut, Vt, low_x, low_g,
+                               sample_sq, low_sq, partial, state_dev, plan->B, d, threshold, stream))
+        return -1;
+      if (read_state()) return -1;
+    }
+    return 0;
+  }
+
+  // ---- sync-free loop: the host enqueues up to `runahead` iterations beyond the last decision it has seen; the
+  // device decides (k_norm_decide), speculative kernels behind the end of the loop are no-ops (gate), and the host
+  // learns the decisions from the progress records instead of draining the stream (broyden.py:153-181 unchanged)
+  volatile BroydenProgress* vp = prog_host;
+  for (int i = 0; i <= threshold + 1; ++i) vp[i].seq = -1;
+  auto wait_for = [&](int it) -> int {
+    long long spins = 0;
+    while (vp[it].seq != it) {
+      if ((++spins & 0x3ff) == 0) {
+        const cudaError_t q = cudaStreamQuery(s);
+        if (q != cudaSuccess && q != cudaErrorNotReady) {
+          set_error("conv3_broyden: stream failed while waiting for iteration %d: %s", it, cudaGetErrorString(q));
+          return -1;
+        }
+        if (q == cudaSuccess && vp[it].seq != it) {
+          set_error("conv3_broyden: iteration %d never reported (stream idle)", it);
+          return -1;
+        }
+      }
+    }
+    return 0;
+  };
+  {
+    GateScope ungated(nullptr);
+    if (eval_g(xs[0], gs[0])) return -1;
+    if (broyden_begin_ex(xs[0], gs[0], xs[1], low_x, low_g, sample_sq, low_sq, partial, state_dev, plan->B, d, threshold,
+                         eps_scaled, prog_dev, stream))
+      return -1;
+  }
+  int seen = -1, enq = 0;      // enq = iterations enqueued so far; record 0 belongs to the start point
+  {
+    GateScope gated(&state_dev->active);
+    for (;;) {
+      while (enq < seen + 1 + runahead && enq < threshold) {
+        const int it = ++enq;
+        if (eval_g(xs[it & 1], gs[it & 1])) return -1;
+        if (broyden_step_ex(xs[(it - 1) & 1], gs[(it - 1) & 1], xs[it & 1], gs[it & 1], Ut, Vt, low_x, low_g, sample_sq,
+                            low_sq, partial, state_dev, plan->B, d, threshold, 1, it, prog_dev, stream))
+          return -1;
+      }
+      if (wait_for(seen + 1)) return -1;
+      ++seen;
+      if (!vp[seen].active) break;
+    }
+  }
+  return read_state();        // full state record (trace, flags) + one stream drain per solve
 }

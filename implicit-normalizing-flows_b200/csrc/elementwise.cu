@@ -9,6 +9,7 @@ namespace impflow {
 static thread_local char g_err[512] = "";
 long long g_launch_count = 0;
 int g_pdl = 1;
+thread_local const int* g_gate = nullptr;
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -94,7 +94,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
            const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
            const __grid_constant__ CUtensorMap mapPre, const __grid_constant__ CUtensorMap mapAct,
            const __grid_constant__ CUtensorMap mapShi, const __grid_constant__ CUtensorMap mapSlo, int tma_store,
-           long long M, int N, int K, TcEpilogue ep, int splits, float* __restrict__ splitk_ws) {
+           long long M, int N, int K, TcEpilogue ep, int splits, float* __restrict__ splitk_ws, const int* gate) {
   using Cfg = TcCfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -118,7 +118,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
   const long long n_streams = PAIR ? (gridDim.x >> 1) : gridDim.x;
   // split-K (weight-gradient shapes: small M x N, K = all pixels): work item = (tile, k-slice);
   // raw partial accumulators go to splitk_ws[slice][M][N] and k_splitk_reduce finishes the job.
-  const long long num_tiles = m_tiles * n_tiles * splits;
+  long long num_tiles = m_tiles * n_tiles * splits;
   const int kb_per = (num_kb + splits - 1) / splits;
 
   if (warp == 0 && lane == 0) {
@@ -157,6 +157,7 @@ k_gemm_tc3(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();        // everything above overlapped the predecessor; no global memory was touched yet
+  if (gate_closed(gate)) num_tiles = 0;   // speculative solver iteration after the loop ended: no tiles (uniform)
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -512,7 +513,7 @@ static int launch_tc(const float* Ahi, const float* Alo, long long lda, const fl
     cfg.attrs = attr;
     cfg.numAttrs = 1 + pdl_attr(&attr[1]);
     const cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_tc3<BN, PAIR>, mAh, mAl, mBh, mBl, mo[0], mo[1], mo[2], mo[3],
-                                               tma_store, M, N, K, ep, splits, ws);
+                                               tma_store, M, N, K, ep, splits, ws, g_gate);
     if (err != cudaSuccess) {
       set_error("k_gemm_tc3 (pair): launch failed: %s", cudaGetErrorString(err));
       return -1;
@@ -531,7 +532,7 @@ static int launch_tc(const float* Ahi, const float* Alo, long long lda, const fl
     cfg.attrs = attr;
     cfg.numAttrs = pdl_attr(&attr[0]);
     const cudaError_t err = cudaLaunchKernelEx(&cfg, k_gemm_tc3<BN, PAIR>, mAh, mAl, mBh, mBl, mo[0], mo[1], mo[2], mo[3],
-                                               tma_store, M, N, K, ep, splits, ws);
+                                               tma_store, M, N, K, ep, splits, ws, g_gate);
     if (err != cudaSuccess) {
       set_error("k_gemm_tc3: launch failed: %s", cudaGetErrorString(err));
       return -1;

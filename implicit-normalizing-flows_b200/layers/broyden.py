@@ -39,12 +39,18 @@ class _Workspace(object):
         nbytes = int(lib.impflow_broyden_state_bytes())
         assert nbytes == _STATE_DTYPE.itemsize, 'state layout mismatch between header and host'
         self.state = torch.zeros(nbytes, device=device, dtype=torch.uint8)
-        self.state_host = _cabi.pinned_bytes(nbytes)
+        # pinned (and therefore device-mapped) host memory: the final state record, followed by the per-iteration
+        # progress records the sync-free conv solver polls (impflow_conv3_broyden_host_bytes)
+        self.state_nbytes = nbytes
+        self.state_host = _cabi.pinned_bytes(max(nbytes, int(lib.impflow_conv3_broyden_host_bytes(T))))
 
     def read_state(self):
-        self.state_host.copy_(self.state, non_blocking=True)
+        self.state_host[:self.state_nbytes].copy_(self.state, non_blocking=True)
         _cabi.sync_stream()
-        return self.state_host.numpy().view(_STATE_DTYPE)[0]
+        return self.host_state()
+
+    def host_state(self):
+        return self.state_host[:self.state_nbytes].numpy().view(_STATE_DTYPE)[0]
 
 
 def _workspace(B, d, T, device):

@@ -600,6 +600,55 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
         return (None, None, grad_x, None, None, None, None, None) + grad_params
 
 
+GRAPH_FREE_BASIC = {'on': True}     # hand-derived training gradient of the basic estimator (off = autograd double backward)
+
+
+class _GraphFreeBasic(Function):
+    """The basic power-series estimator S = sum_k c_k v^T J^k v (implicit_block.py:418-426) WITH its training
+    gradient, graph-free.  The reference builds the n-term vjp chain with create_graph=True and lets autograd
+    differentiate through it (double backward).  Here:
+        forward : l_0 = v, l_k = J^T l_{k-1} (fused vjp kernels), S = sum_k c_k <l_k, v>
+        backward: dS = sum_k c_k sum_{i=1..k} l_{i-1}^T (dJ) r_{k-i},  r_m = J^m v,  which regroups to
+                  dS = sum_{m=0..n-1} w_m^T (dJ) r_m,   w_m = sum_{a=0..n-1-m} c_{a+m+1} l_a
+                  i.e. n bilinear-form gradients d(w^T J r): each is one tangent sweep (which also yields
+                  r_{m+1} = J r_m) and one two-adjoint reverse sweep (BranchProgram.neumann), seeded with the
+                  per-sample upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, x, prog, vareps, coeffs, *params):
+        xd = x.detach()
+        _, saved = prog.forward_saved(xd)
+        ls = [vareps]
+        out = torch.zeros(xd.shape[0], device=xd.device, dtype=torch.float32)
+        for c in coeffs:
+            ls.append(prog.vjp(ls[-1], saved))
+            ops.rowdot(ls[-1], vareps, out=out, alpha=float(c), beta=1.0)
+        ctx.prog, ctx.saved_fwd, ctx.ls, ctx.coeffs = prog, saved, ls, coeffs
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        prog, saved, ls, coeffs = ctx.prog, ctx.saved_fwd, ctx.ls, ctx.coeffs
+        n = len(coeffs)
+        seed = gout.reshape(-1).contiguous()
+        gx, gparams, r = None, None, ls[0]
+        for m in range(n):
+            w = None
+            for a in range(n - m):                  # w_m = sum_a c_{a+m+1} l_a
+                c = float(coeffs[a + m])
+                w = ops.lincomb3(ls[a], c) if w is None else ops.lincomb3(w, 1.0, ls[a], c)
+            _, gx_m, gp_m, r = prog.neumann(saved, w, r, seed_scale=seed, want_tangent=True)
+            gx = gx_m if gx is None else ops.lincomb3(gx, 1.0, gx_m, 1.0)
+            if gparams is None:
+                gparams = list(gp_m)
+            else:
+                gparams = [b if a_ is None else (a_ if b is None else ops.lincomb3(a_, 1.0, b, 1.0))
+                           for a_, b in zip(gparams, gp_m)]
+        ctx.ls = ctx.saved_fwd = None
+        return (gx, None, None, None) + tuple(gparams)
+
+
 def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, program=None):
     """sum_k (-1)^(k+1)/k coeff(k) <v^T J^k, v>  (implicit_block.py:418-426)."""
     vjp = vareps
@@ -607,12 +656,20 @@ def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, pro
         # eval mode builds no graph: the whole chain runs on the fused vjp kernels, the Hutchinson
         # dots accumulate in place
         with torch.no_grad():
-            program.forward(x.detach(), save=True)
+            _, saved = program.forward_saved(x.detach())
+            program._saved = saved
+            dots = program.hutchinson_series(saved, vareps, [(-1) ** (k + 1) / k * coeff_fn(k)
+                                                              for k in range(1, n_power_series + 1)])
+            if dots is not None:        # conv branch: the whole chain and its dots in one C call
+                return dots
             out = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
             for k in range(1, n_power_series + 1):
                 vjp = program.vjp(vjp)
                 ops.rowdot(vjp, vareps, out=out, alpha=float((-1) ** (k + 1) / k * coeff_fn(k)), beta=1.0)
         return out
+    if training and program is not None and GRAPH_FREE_BASIC['on'] and n_power_series >= 1:
+        coeffs = [(-1) ** (k + 1) / k * coeff_fn(k) for k in range(1, n_power_series + 1)]
+        return _GraphFreeBasic.apply(x, program, vareps, coeffs, *program.params)
     logdetgrad = torch.zeros((), device=x.device, dtype=x.dtype)
     for k in range(1, n_power_series + 1):
         with ops.activations_only():

@@ -308,17 +308,32 @@ int impflow_conv3_prepare_vjp(const impflow_conv3_plan* plan, const float* pre1,
 /* out_rows = v^T J at the saved point; pre0 = the branch input rows (needed when act0_kind != NONE) */
 int impflow_conv3_vjp(const impflow_conv3_plan* plan, const float* pre0, const float* d1, const float* d2,
                       const float* v_rows, float* out_rows, void* stream);
-/* w = v + sum_{k=1..n} coeffs[k-1] * v^T J^k  — the no-grad chain of the Neumann gradient estimator
- * (implicit_block.py:431-435); coeffs is a HOST array */
+/* The n-term vjp chain v^T J^k of the power-series estimators in ONE call, with both accumulations fused into
+ * the chain (no separate linear-combination launches):
+ *   w_rows  (optional, with coeffs):     w = v + sum_k coeffs[k-1] * v^T J^k     — the no-grad Neumann sum of the
+ *                                         gradient estimator (implicit_block.py:431-435), added in the col2im epilogue
+ *   dot_out (optional, with dot_coeffs): dot_out[b] = sum_k dot_coeffs[k-1] * <v^T J^k, v>_b — the Hutchinson terms
+ *                                         of the basic estimator (:418-426, eval mode)
+ * coeffs / dot_coeffs are HOST arrays of n doubles; at least one of the two outputs must be requested. */
 int impflow_conv3_power_series(const impflow_conv3_plan* plan, const float* pre0, const float* d1, const float* d2,
-                               const float* v_rows, const double* coeffs, int n, float* w_rows, void* stream);
+                               const float* v_rows, const double* coeffs, int n, float* w_rows,
+                               const double* dot_coeffs, float* dot_out, void* stream);
 /* Whole Broyden solve (broyden.py:123-193) with the residual evaluated by this branch:
  *   mode 0: g(z) = rhs - nnet(z) - z        (forward / inverse solve, implicit_block.py:68-80; rhs = x_embed)
  *   mode 1: g(v) = v^T J + v - rhs          (implicit backward, :199-207; rhs = incoming gradient)
  * xa holds the start point; xa/xb/ga/gb are (B,d) scratch; the other buffers are those of
- * impflow_broyden_step.  state_host is PINNED host memory: the routine copies the device state there and
- * synchronises the stream once per iteration (the only host decision of the loop); on return it holds the
- * final state and low_x the best iterate. */
+ * impflow_broyden_step.  The loop is SYNC-FREE: the residual (branch evaluation + the x_embed - f - z / vJ + v - grad
+ * combination in the col2im epilogue), the norms, the reference's break rules (broyden.py:153-181) and the rank-1
+ * update all run on the device; the host enqueues up to `runahead` iterations (impflow_conv3_set_runahead, default 2)
+ * beyond the last decision it has seen, kernels enqueued behind the end of the loop turn into no-ops through a
+ * device-side gate, and the host learns each decision from a progress record the decision kernel writes into mapped
+ * pinned host memory.  The stream is drained ONCE per solve, for the final state record.
+ * state_host: PINNED host memory of impflow_conv3_broyden_host_bytes(threshold) bytes (state record + progress
+ * records); on return it starts with the final state and low_x holds the best iterate. */
+size_t impflow_conv3_broyden_host_bytes(int threshold);
+/* A/B switch: iterations enqueued ahead of the device's decision (0 = copy the state and synchronise the stream after
+ * every iteration, the round-1 behaviour).  Returns the previous setting. */
+int impflow_conv3_set_runahead(int iterations);
 int impflow_conv3_broyden(const impflow_conv3_plan* plan, int mode, const float* rhs_rows, const float* pre0,
                           const float* d1, const float* d2, float* xa, float* xb, float* ga, float* gb, float* low_x,
                           float* low_g, float* Ut, float* Vt, float* sample_sq, float* low_sq, float* partial,

@@ -630,19 +630,35 @@ class EmulatedLib(object):
             return self.impflow_col2im3x3(Yp, P.B, P.H, P.W, P.c, None, out_rows, None, pre0, P.act0_kind, P.beta0, None)
         return self.impflow_col2im3x3(Yp, P.B, P.H, P.W, P.c, None, out_rows, None, None, ACT_NONE, None, None)
 
-    def impflow_conv3_power_series(self, plan, pre0, d1, d2, v_rows, coeffs, n, w_rows, stream):
+    def impflow_conv3_power_series(self, plan, pre0, d1, d2, v_rows, coeffs, n, w_rows, dot_coeffs, dot_out, stream):
         P = self._plan(plan)
         nel = P.B * P.H * P.W * P.c
-        w = _f32(w_rows, nel)
-        w[:] = _f32(v_rows, nel)
+        v = _f32(v_rows, nel)
+        w = None
+        if _addr(w_rows) is not None:
+            w = _f32(w_rows, nel)
+            w[:] = v
+        dots = None
+        if _addr(dot_out) is not None:
+            dots = _f32(dot_out, P.B)
+            dots[:] = 0
         cur, curp = self._tmp(nel)
-        cur[:] = w
+        cur[:] = v
         for k in range(n):
             nxt, nxtp = self._tmp(nel)
             assert self.impflow_conv3_vjp(plan, pre0, d1, d2, curp, nxtp, None) == 0
-            w += np.float32(coeffs[k]) * nxt
+            if w is not None:
+                w += np.float32(coeffs[k]) * nxt
+            if dots is not None:
+                dots += np.float32(dot_coeffs[k]) * (nxt.reshape(P.B, -1) * v.reshape(P.B, -1)).sum(1, dtype=np.float32)
             cur, curp = nxt, nxtp
         return 0
+
+    def impflow_conv3_broyden_host_bytes(self, threshold):
+        return STATE_DTYPE.itemsize + 8 * (threshold + 2)
+
+    def impflow_conv3_set_runahead(self, iterations):
+        return 2
 
     def impflow_conv3_broyden(self, plan, mode, rhs_rows, pre0, d1, d2, xa, xb, ga, gb, low_x, low_g, Ut, Vt, sample_sq,
                               low_sq, partial, state_dev, state_host, threshold, eps_scaled, stream):
