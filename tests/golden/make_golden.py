@@ -682,6 +682,10 @@ def gen_bwd_band():
         variants = [('threads1', 1, np.arange(B)), ('threads2', 2, np.arange(B)), ('threads8', 8, np.arange(B)),
                     ('reversed', 4, np.arange(B)[::-1].copy()), ('perm_a', 4, rs.permutation(B)),
                     ('perm_b', 4, rs.permutation(B))]
+        if tag in ('toy', 'tab6', 'tab43'):
+            # the same function with the hidden units of both branches re-numbered: every per-sample sum runs in a
+            # different order (what any re-implementation - another BLAS, FMA contraction, a GPU - also does)
+            variants += [('hidden_perm_' + ch, 4, np.arange(B)) for ch in 'abcdefghijkl']
         counts, last = [], []
         for name, nt, perm in variants:
             torch.set_num_threads(nt)
@@ -690,6 +694,25 @@ def gen_bwd_band():
             with torch.no_grad():
                 blk(x, restore=True)
             sd = {k[len(tag + '_sd_'):]: torch.from_numpy(v) for k, v in fx.items() if k.startswith(tag + '_sd_')}
+            if name.startswith('hidden_perm'):
+                hrs = np.random.RandomState(ord(name[-1]))
+                for net in ('nnet_x', 'nnet_z', 'nnet_x_copy', 'nnet_z_copy'):
+                    h = sd[net + '.0.weight'].shape[0]
+                    hrs2 = np.random.RandomState(hrs.randint(1 << 30) if net in ('nnet_x', 'nnet_z') else 0)
+                    if net.endswith('_copy'):      # the frozen twins follow their live nets
+                        p1, p2 = perms[net[:-5]]
+                    else:
+                        p1, p2 = torch.from_numpy(hrs2.permutation(h)), torch.from_numpy(hrs2.permutation(h))
+                        perms = dict(locals().get('perms', {}), **{net: (p1, p2)})
+                    sd[net + '.0.weight'] = sd[net + '.0.weight'][p1]
+                    sd[net + '.0.bias'] = sd[net + '.0.bias'][p1]
+                    sd[net + '.0.u'] = sd[net + '.0.u'][p1]
+                    sd[net + '.2.weight'] = sd[net + '.2.weight'][p2][:, p1]
+                    sd[net + '.2.bias'] = sd[net + '.2.bias'][p2]
+                    sd[net + '.2.u'] = sd[net + '.2.u'][p2]
+                    sd[net + '.2.v'] = sd[net + '.2.v'][p1]
+                    sd[net + '.4.weight'] = sd[net + '.4.weight'][:, p2]
+                    sd[net + '.4.v'] = sd[net + '.4.v'][p2]
             blk.load_state_dict(sd, strict=True)
             blk.train()
             seed = int(fx[tag + '_seed'])
