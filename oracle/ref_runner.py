@@ -12,10 +12,11 @@ import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, '_ref')
+ARCHIVE = os.path.join(REF_DIR, 'reference_lib.bin')      # zip container of sourceless bytecode (build_ref.py)
 
 
 def available():
-    return os.path.isfile(os.path.join(REF_DIR, 'lib', 'implicit_flow.pyc'))
+    return os.path.isfile(ARCHIVE)
 
 
 _ns = None
@@ -38,7 +39,7 @@ def load():
         tc = types.ModuleType('termcolor')
         tc.colored = lambda s, *a, **k: s                     # lib/layers/broyden.py:11
         sys.modules['termcolor'] = tc
-    sys.path.insert(0, REF_DIR)
+    sys.path.insert(0, ARCHIVE)
     try:
         import lib.layers as layers
         import lib.layers.base as base_layers
@@ -48,7 +49,7 @@ def load():
         import lib.utils as utils
         from lib.implicit_flow import ImplicitFlow
     finally:
-        sys.path.remove(REF_DIR)
+        sys.path.remove(ARCHIVE)
         for k in [k for k in sys.modules if k == 'lib' or k.startswith('lib.')]:
             del sys.modules[k]
         sys.modules.update(saved)
