@@ -54,6 +54,9 @@ SIGNATURES = {
     'impflow_gemm_nt_tc': (_i, [_c_fp, _c_fp, _ll, _c_fp, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp,
                                 _ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
     'impflow_branch3_tc': (_i, [_c_fp, _ll] + [_c_fp] * 13 + [_ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
+    'impflow_chain23_parts': (_i, [_i]),
+    'impflow_chain23_tc': (_i, [_c_fp, _c_fp, _ll] + [_c_fp] * 8 + [_ll, _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
+    'impflow_conv3_set_chain23': (_i, [_i]),
     'impflow_conv3_workspace_floats': (ctypes.c_size_t, [_i] * 6),
     'impflow_conv3_forward': (_i, [_c_fp] * 6),
     'impflow_conv3_prepare_vjp': (_i, [_c_fp] * 6),

@@ -469,6 +469,9 @@ class BranchProgram(object):
         for _ in range(count):
             if tile:
                 ops.record_branch3(M, P.C, 9 * P.c, is_vjp, save)
+            elif P.allow_fused and P.C % 128 == 0 and ops.CHAIN23['on']:
+                ops.record_gemm(M, P.C, P.k0, save, False, is_vjp, True, False)
+                ops.record_chain23(M, P.C, 9 * P.c, is_vjp, save)
             else:
                 ops.record_gemm(M, P.C, P.k0, save, False, is_vjp, True, False)
                 ops.record_gemm(M, P.C, P.C, save, False, is_vjp, True, False)

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libimpflow_b200.so')
-SOURCES = ['elementwise.cu', 'broyden.cu', 'gemm_simt.cu', 'gemm_tcgen05.cu', 'wgrad_tcgen05.cu', 'branch_fused.cu', 'conv3_plan.cu', 'spectral.cu', 'spectral_conv.cu', 'mlp_solver.cu']
+SOURCES = ['elementwise.cu', 'broyden.cu', 'gemm_simt.cu', 'gemm_tcgen05.cu', 'wgrad_tcgen05.cu', 'branch_fused.cu', 'chain23_fused.cu', 'conv3_plan.cu', 'spectral.cu', 'spectral_conv.cu', 'mlp_solver.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

@@ -37,7 +37,7 @@ static Conv3Ws carve(float* base, long long M, int c, int C, int k0) {
   w.x0 = take(2 * (size_t)M * k0);
   w.h1 = take(2 * (size_t)M * C);
   w.h2 = take(2 * (size_t)M * C);
-  w.Y = take((size_t)M * 9 * c);
+  w.Y = take((size_t)M * 9 * c * (size_t)(C % 128 == 0 ? C / 128 : 1));   // room for the chain23 partials
   w.t_rows = take((size_t)M * c);
   w.chain_a = take((size_t)M * c);
   w.chain_b = take((size_t)M * c);
@@ -48,6 +48,13 @@ static Conv3Ws carve(float* base, long long M, int c, int C, int k0) {
 static inline bool use_tile_kernel(const impflow_conv3_plan* p) {
   return p->allow_fused && p->k0 == 32 && (p->C % 256) == 0 && 9 * p->c <= 32;
 }
+
+// layers 2 + 3 in one launch (chain23_fused.cu) whenever the tile kernel does not apply and C splits into quarters
+static int g_chain23 = 1;
+static inline bool use_chain23(const impflow_conv3_plan* p) {
+  return g_chain23 && p->allow_fused && !use_tile_kernel(p) && (p->C % 128) == 0;
+}
+static inline int y_parts(const impflow_conv3_plan* p) { return use_chain23(p) ? p->C / 128 : 1; }
 
 static int plan_check(const impflow_conv3_plan* p, const char* who) {
   if (p == nullptr || p->ws == nullptr) {
@@ -138,6 +145,8 @@ k_conv3_in(const float* __restrict__ x, float* __restrict__ col, float* __restri
 enum { OUT_PLAIN = 0, OUT_FWD_RESIDUAL = 1, OUT_BWD_RESIDUAL = 2, OUT_CHAIN = 3 };
 
 struct Conv3Out {
+  int nparts;           // partial accumulators to sum (chain23: one per 128-channel quarter), fixed order
+  long long part_stride;
   const float* col;     // [M, 9c] tap-major accumulator
   const float* bias;    // [c] or null
   const float* pre0;    // [M, c] or null: multiply by act0'(pre0)
@@ -169,7 +178,12 @@ __global__ void __launch_bounds__(256) k_conv3_out(int B, int H, int W, int C, C
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int sy = yy - (tap / 3 - 1), sx = xx - (tap % 3 - 1);
-      if (sy >= 0 && sy < H && sx >= 0 && sx < W) sum += a.col[(((b * H + sy) * W + sx) * 9 + tap) * C + c];
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+        const float* src = a.col + (((b * H + sy) * W + sx) * 9 + tap) * C + c;
+        float v = src[0];
+        for (int part = 1; part < a.nparts; ++part) v += src[part * a.part_stride];
+        sum += v;
+      }
     }
     float val;
     if (a.pre0 != nullptr) {
@@ -249,6 +263,9 @@ static int conv3_chain_forward(const impflow_conv3_plan* p, const Conv3Ws& w, co
   if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W1f_hi, p->W1f_lo, p->k0, p->b1, pre1, nullptr, nullptr, h1_hi,
                          h1_lo, p->C, M, p->C, p->k0, p->act_kind, p->beta1, nullptr, stream))
     return -1;
+  if (use_chain23(p))
+    return impflow_chain23_tc(h1_hi, h1_lo, p->C, p->W2f_hi, p->W2f_lo, p->W3f_hi, p->W3f_lo, p->b2, nullptr, pre2, w.Y,
+                              N3, M * N3, M, p->C, N3, p->act_kind, p->beta2, stream);
   if (impflow_gemm_nt_tc(h1_hi, h1_lo, p->C, p->W2f_hi, p->W2f_lo, p->C, p->b2, pre2, nullptr, nullptr, h2_hi, h2_lo,
                          p->C, M, p->C, p->C, p->act_kind, p->beta2, nullptr, stream))
     return -1;
@@ -279,6 +296,9 @@ static int conv3_chain_vjp(const impflow_conv3_plan* p, const Conv3Ws& w, const 
   if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W3b_hi, p->W3b_lo, p->k0, nullptr, nullptr, nullptr, d2, t3_hi,
                          t3_lo, p->C, M, p->C, p->k0, IMPFLOW_ACT_MULTIPLIER, nullptr, nullptr, stream))
     return -1;
+  if (use_chain23(p))
+    return impflow_chain23_tc(t3_hi, t3_lo, p->C, p->W2b_hi, p->W2b_lo, p->W1b_hi, p->W1b_lo, nullptr, d1, nullptr, w.Y,
+                              N3, M * N3, M, p->C, N3, IMPFLOW_ACT_NONE, nullptr, stream);
   if (impflow_gemm_nt_tc(t3_hi, t3_lo, p->C, p->W2b_hi, p->W2b_lo, p->C, nullptr, nullptr, nullptr, d1, t2_hi, t2_lo,
                          p->C, M, p->C, p->C, IMPFLOW_ACT_MULTIPLIER, nullptr, nullptr, stream))
     return -1;
@@ -289,6 +309,8 @@ static int conv3_chain_vjp(const impflow_conv3_plan* p, const Conv3Ws& w, const 
 static Conv3Out out_forward(const impflow_conv3_plan* p, const Conv3Ws& w, float* out) {
   Conv3Out a;
   memset(&a, 0, sizeof(a));
+  a.nparts = y_parts(p);
+  a.part_stride = (long long)p->B * p->H * p->W * 9 * p->c;
   a.col = w.Y;
   a.bias = p->b3;
   a.act0_kind = IMPFLOW_ACT_NONE;
@@ -300,6 +322,8 @@ static Conv3Out out_forward(const impflow_conv3_plan* p, const Conv3Ws& w, float
 static Conv3Out out_vjp(const impflow_conv3_plan* p, const Conv3Ws& w, const float* pre0, float* out) {
   Conv3Out a;
   memset(&a, 0, sizeof(a));
+  a.nparts = y_parts(p);
+  a.part_stride = (long long)p->B * p->H * p->W * 9 * p->c;
   a.col = w.Y;
   a.act0_kind = p->act0_kind;
   a.beta0 = p->beta0;
@@ -381,6 +405,12 @@ extern "C" int impflow_conv3_power_series(const impflow_conv3_plan* plan, const 
     cur = nxt;
   }
   return 0;
+}
+
+extern "C" int impflow_conv3_set_chain23(int on) {
+  const int prev = g_chain23;
+  g_chain23 = on ? 1 : 0;
+  return prev;
 }
 
 extern "C" int impflow_conv3_set_runahead(int iterations) {

@@ -27,6 +27,9 @@ _BACKEND = {'mode': 'auto', 'min_flops_tc': 2 * 128 * 128 * 64, 'min_flops_tc_au
 GEMM_PROFILE = {'on': False, 'shapes': {}}
 
 
+CHAIN23 = {'on': True}      # mirrors impflow_conv3_set_chain23 (bookkeeping of the launches a native call makes)
+
+
 def record_gemm(M, N, K, has_pre, has_act, has_dmul, has_split, split_k):
     key = (int(M), int(N), int(K), bool(has_pre), bool(has_act), bool(has_dmul), bool(has_split), bool(split_k))
     GEMM_PROFILE['shapes'][key] = GEMM_PROFILE['shapes'].get(key, 0) + 1
@@ -475,6 +478,62 @@ def branch3_tc(x0, W1s, W2s, W3s, N3, bias1=None, bias2=None, mul1=None, mul2=No
     if GEMM_PROFILE['on']:
         record_branch3(M, C, N3, mul1 is not None, save_pre)
     return out, pre1, pre2
+
+
+def chain23_tc(A_split, W2s, W3s, N3, bias2=None, mul2=None, act_kind=ACT_NONE, beta2=None, save_pre=False):
+    """Fused layers 2 + 3 (csrc/chain23_fused.cu): returns (partials (Q, M, N3) with Q = C/128, pre2 or None);
+    the layer output is partials.sum(0) (summed in fixed order by the col2im kernel on the product path).
+
+    A_split = (hi, lo) tf32 planes of the (M, C) layer-2 input; W2s / W3s = planes of the (C, C) and (N3, C)
+    K-major weights; mul2 given: psi2(t) = t * mul2, else psi2(t) = act(t + bias2)."""
+    M, C = A_split[0].shape
+    dev = A_split[0].device
+    Q = int(_lib().impflow_chain23_parts(C))
+    pre2 = torch.empty(M, C, device=dev, dtype=torch.float32) if save_pre else None
+    out = torch.empty(Q, M, N3, device=dev, dtype=torch.float32)
+    _cabi.check(_lib().impflow_chain23_tc(
+        _cabi.ptr(A_split[0]), _cabi.ptr(A_split[1]), C, _cabi.ptr(W2s[0]), _cabi.ptr(W2s[1]), _cabi.ptr(W3s[0]),
+        _cabi.ptr(W3s[1]), _cabi.ptr(bias2, 'bias2', True), _cabi.ptr(mul2, 'mul2', True), _cabi.ptr(pre2, 'pre2', True),
+        _cabi.ptr(out), N3, M * N3, M, C, N3, act_kind, _cabi.ptr(beta2, 'beta2', True), _cabi.stream()), 'chain23_tc')
+    if GEMM_PROFILE['on']:
+        record_chain23(M, C, N3, mul2 is not None, save_pre)
+    return out, pre2
+
+
+def record_chain23(M, C, N3, is_vjp, save_pre):
+    key = ('chain23', int(M), int(C), int(N3), bool(is_vjp), bool(save_pre))
+    GEMM_PROFILE['shapes'][key] = GEMM_PROFILE['shapes'].get(key, 0) + 1
+
+
+def time_chain23_shape(key, reps=5, flush=None):
+    """Median CUDA-event duration (ms) of one fused layer-2+3 launch of the recorded shape."""
+    _, M, C, N3, is_vjp, save_pre = key
+    dev = torch.device('cuda', torch.cuda.current_device())
+    A = split_tf32(torch.randn(M, C, device=dev))
+    W2 = split_tf32(torch.randn(C, C, device=dev) / C ** 0.5)
+    W3 = split_tf32(torch.randn(N3, C, device=dev) / C ** 0.5)
+    b2 = torch.randn(C, device=dev)
+    beta = torch.full((1,), 0.97, device=dev)
+    m2 = torch.randn(M, C, device=dev) if is_vjp else None
+    if flush is None:
+        flush = torch.empty(64 * 1024 * 1024, device=dev)
+    was = GEMM_PROFILE['on']
+    GEMM_PROFILE['on'] = False
+    times = []
+    for i in range(reps + 1):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if is_vjp:
+            chain23_tc(A, W2, W3, N3, mul2=m2)
+        else:
+            chain23_tc(A, W2, W3, N3, bias2=b2, act_kind=ACT_LIPSWISH, beta2=beta, save_pre=save_pre)
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            times.append(e0.elapsed_time(e1))
+    GEMM_PROFILE['on'] = was
+    return sorted(times)[len(times) // 2]
 
 
 def record_branch3(M, C, N3, is_vjp, save_pre):

@@ -271,12 +271,27 @@ int impflow_branch3_tc(const float* x0, long long ldx, const float* W1_hi, const
                        float* out, long long ldo, long long M, int C, int N3, int act_kind, const float* beta1,
                        const float* beta2, void* stream);
 
+/* Fused layers 2 + 3 of the same branch for the wider scales (9c = 108 / 432 tap columns; implicit_flow.py:359-398
+ * at c = 12 / 48), forward or transposed, one launch (csrc/chain23_fused.cu):
+ *     out_q[M,N3] = psi2( A1[M,C] W2[C,C]^T )[:, q] W3[N3, q]^T      for every 128-channel quarter q of layer 2
+ *   A1 comes as the tf32 hi/lo planes the layer-1 GEMM (impflow_gemm_nt_tc, split outputs) wrote; psi2 as in
+ *   impflow_branch3_tc (bias2 + activation with optional pre2_out, or * mul2).  The C-wide layer-2 output stays in
+ *   tensor memory.  `out` receives impflow_chain23_parts(C) = C/128 PARTIAL results, part_stride floats apart
+ *   (>= M*ldo); the caller sums them in fixed order (impflow_conv3_* do it in the col2im epilogue).
+ * Needs C % 128 == 0 and 16-byte aligned rows (returns -2 otherwise).  Replaces two impflow_gemm_nt_tc launches and
+ * the plane traffic between them. */
+int impflow_chain23_parts(int C);
+int impflow_chain23_tc(const float* A_hi, const float* A_lo, long long lda, const float* W2_hi, const float* W2_lo,
+                       const float* W3_hi, const float* W3_lo, const float* bias2, const float* mul2, float* pre2_out,
+                       float* out, long long ldo, long long part_stride, long long M, int C, int N3, int act_kind,
+                       const float* beta2, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Native host runtime of the 3x3 / 1x1 / 3x3 conv residual branch (implicit_flow.py:359-398): one C call per
  * branch evaluation, per Neumann power-series chain and per Broyden solve (csrc/conv3_plan.cu).  All
  * tensors are NHWC "rows": M = B*H*W rows of c floats; a sample is a contiguous block of H*W*c floats.
- * Shapes with 9c <= 32 and C % 256 == 0 run on impflow_branch3_tc, the others on im2col planes + three
- * impflow_gemm_nt_tc + col2im.  The caller owns every buffer; `ws` holds
+ * Shapes with 9c <= 32 and C % 256 == 0 run on impflow_branch3_tc, the others on im2col planes + the layer-1
+ * impflow_gemm_nt_tc + impflow_chain23_tc (C % 128 == 0; else two more GEMMs) + col2im.  The caller owns every buffer; `ws` holds
  * impflow_conv3_workspace_floats(B,H,W,c,C,k0) floats and may be shared by all plans used on one stream.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -331,6 +346,9 @@ int impflow_conv3_power_series(const impflow_conv3_plan* plan, const float* pre0
  * state_host: PINNED host memory of impflow_conv3_broyden_host_bytes(threshold) bytes (state record + progress
  * records); on return it starts with the final state and low_x holds the best iterate. */
 size_t impflow_conv3_broyden_host_bytes(int threshold);
+/* A/B switch: 1 (default) = layers 2 + 3 of the wider scales run as impflow_chain23_tc, 0 = two GEMM launches.
+ * Returns the previous setting. */
+int impflow_conv3_set_chain23(int on);
 /* A/B switch: iterations enqueued ahead of the device's decision (0 = copy the state and synchronise the stream after
  * every iteration, the round-1 behaviour).  Returns the previous setting. */
 int impflow_conv3_set_runahead(int iterations);

@@ -574,6 +574,33 @@ class EmulatedLib(object):
         a = np.zeros(shape, dtype=np.float32)
         return a, ctypes.c_void_p(a.ctypes.data)
 
+    def impflow_chain23_parts(self, C):
+        return C // 128
+
+    def impflow_conv3_set_chain23(self, on):
+        return 1
+
+    def impflow_chain23_tc(self, A_hi, A_lo, lda, W2_hi, W2_lo, W3_hi, W3_lo, bias2, mul2, pre2_out, out, ldo,
+                           part_stride, M, C, N3, act_kind, beta2, stream):
+        A = (_f32(A_hi, M * lda) + _f32(A_lo, M * lda)).reshape(M, lda)[:, :C]
+        W2 = (_f32(W2_hi, C * C) + _f32(W2_lo, C * C)).reshape(C, C)
+        W3 = (_f32(W3_hi, N3 * C) + _f32(W3_lo, N3 * C)).reshape(N3, C)
+        H = (A @ W2.T).astype(np.float32)
+        if _addr(mul2) is not None:
+            A2 = H * _f32(mul2, M * C).reshape(M, C)
+        else:
+            if _addr(bias2) is not None:
+                H = H + _f32(bias2, C)
+            if _addr(pre2_out) is not None:
+                _f32(pre2_out, M * C)[:] = H.ravel()
+            A2 = _act(act_kind, H, 0, _beta(beta2)).astype(np.float32)
+        for q in range(C // 128):
+            part = (A2[:, q * 128:(q + 1) * 128] @ W3[:, q * 128:(q + 1) * 128].T).astype(np.float32)
+            dst = _f32(out, (C // 128 - 1) * part_stride + M * ldo)[q * part_stride:q * part_stride + M * ldo]
+            dst.reshape(M, ldo)[:, :N3] = part
+        self.launches += 1
+        return 0
+
     def impflow_conv3_workspace_floats(self, B, H, W, c, C, k0):
         return 64
 

@@ -239,6 +239,40 @@ def test_branch3_fused_chain(ops, M, C, N3, mode):
     assert rel_err(y.cpu(), ry) < 1e-5            # three chained: the north_star bound
 
 
+@pytest.mark.parametrize('M,C,N3,mode', [(128, 128, 108, 'fwd'), (300, 512, 108, 'fwd'), (4096, 512, 432, 'fwd'),
+                                         (4096, 512, 432, 'vjp'), (16384, 512, 108, 'vjp'), (128 * 41 + 5, 256, 200, 'fwd'),
+                                         (640, 512, 27, 'vjp'), (128 * 149, 384, 130, 'fwd')])
+def test_chain23_fused_layers(ops, M, C, N3, mode):
+    """Fused layer 2 + 3 kernel of the wider scales (csrc/chain23_fused.cu) against the same chain in fp64:
+    forward with bias + LipSwish and the saved pre-activation, and the vjp form with an act' multiplier; one and
+    several 128-column passes, ragged M, several items per CTA, C/128 = 1..4 partial sums."""
+    g = torch.Generator().manual_seed(M + C + N3)
+    A = torch.randn(M, C, generator=g)
+    W2 = torch.randn(C, C, generator=g) / C ** 0.5
+    W3 = torch.randn(N3, C, generator=g) / C ** 0.5
+    b2 = torch.randn(C, generator=g) * 0.1
+    beta2 = torch.tensor([1.3])
+    dev = _dev()
+    sp = lambda t: ops.split_tf32(t.to(dev))
+    if mode == 'fwd':
+        parts, p2 = ops.chain23_tc(sp(A), sp(W2), sp(W3), N3, bias2=b2.to(dev), act_kind=ops.ACT_LIPSWISH,
+                                   beta2=beta2.to(dev), save_pre=True)
+        r2 = A.double() @ W2.double().t() + b2.double()
+        ry = (r2 * torch.sigmoid(r2 * beta2.double()) / 1.1) @ W3.double().t()
+        assert rel_err(p2.cpu(), r2) < 3e-6
+    else:
+        m2 = torch.randn(M, C, generator=g)
+        parts, _ = ops.chain23_tc(sp(A), sp(W2), sp(W3), N3, mul2=m2.to(dev))
+        ry = ((A.double() @ W2.double().t()) * m2.double()) @ W3.double().t()
+    assert parts.shape == (C // 128, M, N3)
+    assert rel_err(parts.sum(0).cpu(), ry) < 6e-6
+    # each partial is the contribution of one 128-channel quarter
+    if mode == 'vjp':
+        q = C // 128 - 1
+        h = ((A.double() @ W2.double().t()) * m2.double())[:, q * 128:(q + 1) * 128]
+        assert rel_err(parts[q].cpu(), h @ W3.double()[:, q * 128:(q + 1) * 128].t()) < 6e-6
+
+
 def test_activation_orders_vs_golden(ops, golden):
     fx = golden('activations')
     x = torch.from_numpy(fx['x']).cuda()
