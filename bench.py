@@ -682,6 +682,12 @@ def main():
                 t = pkg.ops.time_branch3_shape(key, reps=3, flush=flush)
                 fl = 2.0 * M_ * (N3_ * C_ + C_ * C_ + C_ * N3_)      # algorithmic: unpadded 9c tap columns
                 desc = {'M': M_, 'C': C_, 'taps': N3_, 'mode': 'vjp' if is_vjp else ('fwd+save' if save_pre else 'fwd')}
+            elif key[0] == 'chain23':
+                _, M_, C_, N3_, is_vjp, save_pre = key
+                name = 'k_chain23'
+                t = pkg.ops.time_chain23_shape(key, reps=3, flush=flush)
+                fl = 2.0 * M_ * (C_ * C_ + C_ * N3_)
+                desc = {'M': M_, 'C': C_, 'taps': N3_, 'mode': 'vjp' if is_vjp else ('fwd+save' if save_pre else 'fwd')}
             elif key[0] == 'wgrad':
                 _, M_, N1_, N2_ = key
                 name = 'k_wgrad_tc3'
@@ -753,6 +759,8 @@ def main():
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PF sustained (B200_PROFILING.md)'
     KNAMES = {'k_branch3': 'k_branch3 (fused 3-layer residual-branch tile kernel, tcgen05 3xTF32, operands in TMEM)',
               'k_gemm_tc3': 'k_gemm_tc3 (tcgen05 3xTF32 residual-branch GEMM)',
+              'k_chain23': 'k_chain23 (fused layers 2+3 of the wider-scale conv branches, tcgen05 3xTF32, layer-2 output '
+                           'kept in TMEM)',
               'k_wgrad_tc3': 'k_wgrad_tc3 (tcgen05 3xTF32 weight gradient, MN-major operands)'}
 
     # DRAM bytes per launch of each kernel from the committed `ncu --set full` captures (profiles/)

@@ -259,18 +259,18 @@ def test_chain23_fused_layers(ops, M, C, N3, mode):
                                    beta2=beta2.to(dev), save_pre=True)
         r2 = A.double() @ W2.double().t() + b2.double()
         ry = (r2 * torch.sigmoid(r2 * beta2.double()) / 1.1) @ W3.double().t()
-        assert rel_err(p2.cpu(), r2) < 3e-6
+        assert rel_err(p2.cpu(), r2) < 6e-6       # one 3xTF32 GEMM over K = C
     else:
         m2 = torch.randn(M, C, generator=g)
         parts, _ = ops.chain23_tc(sp(A), sp(W2), sp(W3), N3, mul2=m2.to(dev))
         ry = ((A.double() @ W2.double().t()) * m2.double()) @ W3.double().t()
     assert parts.shape == (C // 128, M, N3)
-    assert rel_err(parts.sum(0).cpu(), ry) < 6e-6
+    assert rel_err(parts.sum(0).cpu(), ry) < 1e-5        # two chained: the north_star bound
     # each partial is the contribution of one 128-channel quarter
     if mode == 'vjp':
         q = C // 128 - 1
         h = ((A.double() @ W2.double().t()) * m2.double())[:, q * 128:(q + 1) * 128]
-        assert rel_err(parts[q].cpu(), h @ W3.double()[:, q * 128:(q + 1) * 128].t()) < 6e-6
+        assert rel_err(parts[q].cpu(), h @ W3.double()[:, q * 128:(q + 1) * 128].t()) < 1e-5
 
 
 def test_activation_orders_vs_golden(ops, golden):
