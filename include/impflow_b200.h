@@ -281,6 +281,9 @@ int impflow_branch3_tc(const float* x0, long long ldx, const float* W1_hi, const
  * Needs C % 128 == 0 and 16-byte aligned rows (returns -2 otherwise).  Replaces two impflow_gemm_nt_tc launches and
  * the plane traffic between them. */
 int impflow_chain23_parts(int C);
+/* A/B switch: 1 (default) = with C = 512 the four quarter-CTAs of a row tile run as a thread-block cluster and share
+ * the A1 chunks by TMA multicast; 0 = independent CTAs.  Returns the previous setting. */
+int impflow_chain23_set_multicast(int on);
 int impflow_chain23_tc(const float* A_hi, const float* A_lo, long long lda, const float* W2_hi, const float* W2_lo,
                        const float* W3_hi, const float* W3_lo, const float* bias2, const float* mul2, float* pre2_out,
                        float* out, long long ldo, long long part_stride, long long M, int C, int N3, int act_kind,
