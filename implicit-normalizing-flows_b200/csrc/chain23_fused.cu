@@ -183,8 +183,7 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
             umma_tf32(t_acc2, dah, dbh, idesc2, 1u);                               // hi * hi
           }
           if (MC) umma_commit_mc(&empty[st], (uint16_t)0xF);
-          else if (MC) umma_commit_mc(&empty[st], (uint16_t)0xF);
-            else umma_commit(&empty[st]);
+          else umma_commit(&empty[st]);
           if (kc == NC - 1) umma_commit(acc2_full);
         }
         __syncwarp();
@@ -211,7 +210,8 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
               umma_tf32_ts(t_acc3, t_a2hi + col, dbl, idesc3, 1u);
               umma_tf32_ts(t_acc3, t_a2hi + col, dbh, idesc3, 1u);
             }
-            umma_commit(&empty[st]);
+            if (MC) umma_commit_mc(&empty[st], (uint16_t)0xF);
+            else umma_commit(&empty[st]);
             if (c2 == NC3 - 1) {
               umma_commit(acc3_full);
               if (j == args.npass - 1) umma_commit(a2_empty);
