@@ -311,7 +311,7 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
   }
 }
 
-static int g_chain23_mc = 1;     // A/B switch of the cluster-multicast variant (impflow_chain23_set_multicast)
+static int g_chain23_mc = 0;     // cluster-multicast variant (impflow_chain23_set_multicast): measured SLOWER (91 vs 123 TFLOP/s), off
 
 template <int ACT, bool MC>
 static int launch_chain23(const CUtensorMap* maps, const Chain23Args& a, cudaStream_t s) {

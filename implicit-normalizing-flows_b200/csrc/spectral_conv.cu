@@ -351,14 +351,28 @@ k_sn_power_iter_conv3x3(const PcArgs a) {
   }
 }
 
+// CTAs per layer.  The solve is bound by its grid barriers, not by arithmetic, and update_lipschitz runs the 24
+// conv layers of the CIFAR flow on side streams: with 128 CTAs per launch (the round-1 choice) no two cooperative
+// launches fit on the 148 SMs together and the layers serialise (24 x 125 us at the END of every step, on the
+// critical path); with 32 CTAs four layers run side by side and each grid barrier is cheaper.
+static int g_pc_ctas = 32;
+
 static int pc_plan(int Cout, int Cin, int H, int Wd, int* chans, int* grid, size_t* smem) {
   const int Cw = Cout >= Cin ? Cout : Cin, Cn = Cout >= Cin ? Cin : Cout;
   const long long HW = (long long)H * Wd;
-  int c = (Cw + 127) / 128;                 // <= 128 CTAs: co-resident on 148 SMs at one CTA per SM
+  int c = (Cw + g_pc_ctas - 1) / g_pc_ctas;
   if (c < 1) c = 1;
+  // the CTA's slice of the wide vector and of W must fit in shared memory beside the narrow vector
+  auto floats = [&](int ch) { return 2 * Cn * HW + 2 * ch * HW + (long long)ch * Cn * 9; };
+  while (c > 1 && floats(c) * 4 > 200 * 1024) --c;
   *chans = c;
   *grid = (Cw + c - 1) / c;
-  const long long fl = 2 * Cn * HW + 2 * c * HW + (long long)c * Cn * 9;
+  if (*grid > 128) {                        // <= 128 CTAs: co-resident on 148 SMs at one CTA per SM
+    c = (Cw + 127) / 128;
+    *chans = c;
+    *grid = (Cw + c - 1) / c;
+  }
+  const long long fl = floats(c);
   *smem = (size_t)fl * sizeof(float);
   return (fl * 4 <= 200 * 1024) ? 0 : -1;
 }
@@ -366,6 +380,12 @@ static int pc_plan(int Cout, int Cin, int H, int Wd, int* chans, int* grid, size
 }  // namespace impflow
 
 using namespace impflow;
+
+extern "C" int impflow_sn_conv_set_ctas(int ctas) {
+  const int prev = g_pc_ctas;
+  g_pc_ctas = ctas < 1 ? 1 : (ctas > 128 ? 128 : ctas);
+  return prev;
+}
 
 extern "C" size_t impflow_sn_conv_workspace_floats(int Cout, int Cin, int H, int Wd) {
   int chans, grid;

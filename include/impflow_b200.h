@@ -282,7 +282,8 @@ int impflow_branch3_tc(const float* x0, long long ldx, const float* W1_hi, const
  * the plane traffic between them. */
 int impflow_chain23_parts(int C);
 /* A/B switch: 1 (default) = with C = 512 the four quarter-CTAs of a row tile run as a thread-block cluster and share
- * the A1 chunks by TMA multicast; 0 = independent CTAs.  Returns the previous setting. */
+ * the A1 chunks by TMA multicast; 0 (default: the lock-step of four SMs measured slower, 91 vs 123 TFLOP/s) =
+ * independent CTAs.  Returns the previous setting. */
 int impflow_chain23_set_multicast(int on);
 int impflow_chain23_tc(const float* A_hi, const float* A_lo, long long lda, const float* W2_hi, const float* W2_lo,
                        const float* W3_hi, const float* W3_lo, const float* bias2, const float* mul2, float* pre2_out,
@@ -380,6 +381,10 @@ int impflow_sn_power_iter(const float* W, float* u, float* v, float* sigma, int*
  * `ws` holds impflow_sn_conv_workspace_floats() floats; that function returns 0 (and the solver -2) when the
  * narrow side of the layer does not fit in shared memory (the caller then keeps its own loop). */
 size_t impflow_sn_conv_workspace_floats(int Cout, int Cin, int H, int W);
+/* CTAs one 3x3 power-iteration launch spreads its wide channels over (default 32, so that the independent layers of
+ * update_lipschitz run side by side; 128 = the widest the cooperative launch allows).  Returns the previous value;
+ * query impflow_sn_conv_workspace_floats again after changing it. */
+int impflow_sn_conv_set_ctas(int ctas);
 int impflow_sn_power_iter_conv3x3(const float* W, float* u, float* v, float* sigma, int* iters, int Cout, int Cin,
                                   int H, int Wd, int n_iterations, float atol, float rtol, float* ws, float* D,
                                   void* stream);

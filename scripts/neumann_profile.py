@@ -81,3 +81,17 @@ for name, fn in [('backward_full', lambda: prog.backward_full(saved, w)), ('neum
     for e in rows[:16]:
         print('  %8.0f us %5.1f%% n=%3d  %s' % (e.self_device_time_total, 100 * e.self_device_time_total / tot, e.count,
                                                 e.key[:70]))
+
+
+# KERNEL TABLE of one neumann() and one backward_full() call
+for name, fn in [('neumann', lambda: prog.neumann(saved, w, v)), ('backward_full', lambda: prog.backward_full(saved, w))]:
+    with torch.no_grad():
+        fn()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+    print('--- kernels of one %s call (scale %d)' % (name, scale))
+    rows = sorted(prof.key_averages(), key=lambda e: -e.self_device_time_total)
+    for e in rows[:14]:
+        print('   %8.0f us  n=%3d  %s' % (e.self_device_time_total, e.count, e.key[:70]))

@@ -583,6 +583,9 @@ class EmulatedLib(object):
     def impflow_chain23_set_multicast(self, on):
         return 1
 
+    def impflow_sn_conv_set_ctas(self, ctas):
+        return 32
+
     def impflow_chain23_tc(self, A_hi, A_lo, lda, W2_hi, W2_lo, W3_hi, W3_lo, bias2, mul2, pre2_out, out, ldo,
                            part_stride, M, C, N3, act_kind, beta2, stream):
         A = (_f32(A_hi, M * lda) + _f32(A_lo, M * lda)).reshape(M, lda)[:, :C]
