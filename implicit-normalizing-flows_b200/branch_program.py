@@ -817,6 +817,48 @@ class BranchProgram(object):
         gx = self._from_rows(G.f32(), meta) if need_input_grad else None
         return gx, self._finish_param_grads(ws, wbars, bbars, betabars)
 
+    # ---------------------------------------------------------------- tangent sweep / batched bilinear gradients
+    def tangent(self, saved, v_vec):
+        """J v at the point of `saved` (forward-mode sweep t_l = W phi'(p) t_{l-1}), module layout."""
+        meta, M, pres = saved.meta, saved.M, saved.pres
+        ws = self._prep(M)
+        n = len(self.stages)
+        acts = self._acts()
+        tp0, _ = self._to_rows(v_vec)
+        TA = _T(f=tp0)
+        if acts[0] is not None:
+            TA = _T(f=ops.act_mul(pres[0], tp0, acts[0].kind, 1, acts[0].beta_sp()))
+        for i in range(n):
+            w = ws[i]
+            last = i == n - 1
+            nxt = acts[i + 1]
+            want_split = (not last) and self._wants_planes(ws[i + 1], False, w.cout)
+            if nxt is not None:
+                prod, _, split = self._apply(w, TA, meta, False, act=_MULT, want_pre=(last or not want_split),
+                                             dmul_pre=self._deriv(saved, i + 1), want_split=want_split)
+                TA = _T(f=prod, s=split)
+            else:
+                pre, _, split = self._apply(w, TA, meta, False, want_pre=True, want_split=want_split)
+                TA = _T(f=pre, s=split)
+        return self._from_rows(TA.f32(), meta)
+
+    def tile_saved(self, saved, n):
+        """The saved forward of the batch repeated n times along the batch dimension: lets n bilinear-form gradients
+        d(w_m^T J r_m), m = 1..n, at the SAME point run as one sweep over an n-fold batch (rows are sample-major)."""
+        t = _Saved()
+        rep = lambda a: a.repeat(n, 1) if a is not None else None
+        t.rows, t.M = rep(saved.rows), saved.M * n
+        t.pres = [rep(p) for p in saved.pres]
+        t.ains = None
+        t.derivs = {k: rep(v) for k, v in saved.derivs.items()}
+        if saved.meta[0] == 'lin':
+            shape = tuple(saved.meta[1])
+            t.meta = ('lin', (shape[0] * n,) + shape[1:])
+        else:
+            B, H, W = saved.meta[1]
+            t.meta = ('conv', (B * n, H, W))
+        return t
+
     # ---------------------------------------------------------------- Neumann estimator gradient
     def neumann(self, saved, w_vec, v_vec, seed_scale=None, want_tangent=False):
         """S_b = <w_b^T J_b, v_b> together with dS/dx and dS/dtheta of S = sum_b c_b S_b

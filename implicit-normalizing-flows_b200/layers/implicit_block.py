@@ -631,20 +631,27 @@ class _GraphFreeBasic(Function):
     def backward(ctx, gout):
         prog, saved, ls, coeffs = ctx.prog, ctx.saved_fwd, ctx.ls, ctx.coeffs
         n = len(coeffs)
+        B = ls[0].shape[0]
         seed = gout.reshape(-1).contiguous()
-        gx, gparams, r = None, None, ls[0]
+        # right vectors r_m = J^m v (n - 1 tangent sweeps) and left combinations w_m = sum_a c_{a+m+1} l_a
+        rs = [ls[0]]
+        for _ in range(n - 1):
+            rs.append(prog.tangent(saved, rs[-1]))
+        wsum = []
         for m in range(n):
             w = None
-            for a in range(n - m):                  # w_m = sum_a c_{a+m+1} l_a
+            for a in range(n - m):
                 c = float(coeffs[a + m])
                 w = ops.lincomb3(ls[a], c) if w is None else ops.lincomb3(w, 1.0, ls[a], c)
-            _, gx_m, gp_m, r = prog.neumann(saved, w, r, seed_scale=seed, want_tangent=True)
-            gx = gx_m if gx is None else ops.lincomb3(gx, 1.0, gx_m, 1.0)
-            if gparams is None:
-                gparams = list(gp_m)
-            else:
-                gparams = [b if a_ is None else (a_ if b is None else ops.lincomb3(a_, 1.0, b, 1.0))
-                           for a_, b in zip(gparams, gp_m)]
+            wsum.append(w)
+        # all n bilinear-form gradients in ONE two-adjoint sweep over an n-fold batch (same point, same weights:
+        # the parameter gradients are sums over rows anyway; the input gradient is summed over the n copies)
+        if n > 1:
+            saved_n = prog.tile_saved(saved, n)
+            _, gx_n, gparams = prog.neumann(saved_n, torch.cat(wsum, 0), torch.cat(rs, 0), seed_scale=seed.repeat(n))
+            gx = gx_n.reshape((n, B) + tuple(gx_n.shape[1:])).sum(0)
+        else:
+            _, gx, gparams = prog.neumann(saved, wsum[0], rs[0], seed_scale=seed)
         ctx.ls = ctx.saved_fwd = None
         return (gx, None, None, None) + tuple(gparams)
 
