@@ -48,6 +48,15 @@ ncu)
       -c 20000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
   echo "ncu launches exit $?"; wc -l gpurun_out/${TAG}_launches.csv
   python scripts/summarise_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launch_summary.txt 2>&1; head -40 gpurun_out/${TAG}_launch_summary.txt ;;
+ncufull)
+  # one --set full capture per tile kernel on its micro-benchmark (each after the same command exited 0 without ncu)
+  for k in chain23 branch3; do
+    CMD="python scripts/${k}_bench.py"
+    timeout -s KILL 300 $CMD > gpurun_out/${TAG}_${k}_bench.txt 2>&1 &&
+    timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:k_${k} -s 4 -c 3 \
+        -o gpurun_out/${TAG}_prof_${k} -f $CMD > gpurun_out/${TAG}_ncu_full_${k}.log 2>&1
+    echo "ncu full $k exit $?"; cat gpurun_out/${TAG}_${k}_bench.txt
+  done ;;
 insitu)
   timeout -s KILL 900 python scripts/kernel_time.py > gpurun_out/${TAG}_insitu.txt 2>&1; head -45 gpurun_out/${TAG}_insitu.txt ;;
 strong)
