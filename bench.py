@@ -489,6 +489,10 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--probe-mode', default='device', choices=['reference', 'device'])
     ap.add_argument('--unfused', action='store_true', help='disable the graph-free branch programs (A/B)')
+    ap.add_argument('--roulette', default='shared', choices=['shared', 'per-rank'],
+                    help='N > 1: the Russian-roulette term counts n are drawn from one seed on every rank (equal work '
+                         'per rank; each rank\'s estimate stays unbiased, probes and data stay per-rank) or per rank '
+                         '(what the reference\'s DataParallel threads do; the step then waits for the unluckiest rank)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -506,7 +510,7 @@ def main():
               'per_gpu_batch': batch, 'global_batch': batch * world, 'parallelism': 'dp%d' % world,
               'l2': 'per-step working set (>1 GB of activations) exceeds the 126 MB L2; 256 MB flush between steps',
               'gemm': '3xTF32 on tcgen05 (fp32-accurate; ceiling = 1/6 of the bf16 peak)',
-              'probe_mode': args.probe_mode}
+              'probe_mode': args.probe_mode, 'roulette_draws': args.roulette if world > 1 else 'single rank'}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -586,8 +590,8 @@ def main():
         model(x_dev, restore=True)           # ActNorm data init + lazy u/v shaping (train_img.py:502-507)
     if world > 1:
         pkg.parallel.broadcast_module(model, 0)
-    np.random.seed(100 + rank)
-    torch.manual_seed(100 + rank)
+    np.random.seed(100 if args.roulette == 'shared' else 100 + rank)     # the roulette draws use the NumPy RNG
+    torch.manual_seed(100 + rank)                                        # probes: per rank
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     bucket = pkg.parallel.FlatGradBucket(params)
