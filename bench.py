@@ -569,6 +569,13 @@ def main():
         pkg._cabi.load().impflow_gemm_tc_set_pair(0)
     if os.environ.get('IMPFLOW_PDL', '') == '0':             # A/B: ordinary launches of the tile kernels
         pkg._cabi.load().impflow_set_pdl(0)
+    if os.environ.get('IMPFLOW_SN_CTAS', ''):                # A/B: CTAs per 3x3 power-iteration launch
+        pkg._cabi.load().impflow_sn_conv_set_ctas(int(os.environ['IMPFLOW_SN_CTAS']))
+    if os.environ.get('IMPFLOW_RUNAHEAD', ''):               # A/B: 0 = synchronise the solver loop every iteration
+        pkg._cabi.load().impflow_conv3_set_runahead(int(os.environ['IMPFLOW_RUNAHEAD']))
+    if os.environ.get('IMPFLOW_CHAIN23', '') == '0':         # A/B: two GEMM launches instead of k_chain23
+        pkg._cabi.load().impflow_conv3_set_chain23(0)
+        pkg.ops.CHAIN23['on'] = False
 
     torch.manual_seed(0)
     np.random.seed(0)
