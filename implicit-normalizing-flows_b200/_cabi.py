@@ -21,6 +21,7 @@ SIGNATURES = {
     'impflow_version': (_i, []),
     'impflow_last_error': (ctypes.c_char_p, []),
     'impflow_launch_count': (_ll, []),
+    'impflow_add_launch_count': (None, [_ll]),
     'impflow_broyden_state_bytes': (ctypes.c_size_t, []),
     'impflow_broyden_workspace_floats': (ctypes.c_size_t, [_i, _ll, _i]),
     'impflow_broyden_begin': (_i, [_c_fp] * 9 + [_i, _ll, _i, _d, _c_fp]),

@@ -41,7 +41,7 @@ from . import _cabi, ops
 from .layers.base.activations import ReLU, Sin, Swish
 from .layers.base.mixed_lipschitz import InducedNormConv2d, InducedNormLinear, sigma_of
 
-__all__ = ['BranchProgram', 'compile_branch', 'FUSED3', 'CONV3_NATIVE', 'MEMO']
+__all__ = ['BranchProgram', 'compile_branch', 'FUSED3', 'CONV3_NATIVE', 'MEMO', 'SWEEP_GRAPHS']
 
 # One-launch tile kernel for the 3-layer conv branch (csrc/branch_fused.cu); off = three GEMM launches.
 FUSED3 = {'on': True}
@@ -59,6 +59,9 @@ NEUMANN_FUSED = {'on': True}
 # re-attach and for the log-det estimate; nnet_z(z) for the estimate and again in the implicit backward).  The
 # last saved forward of a program is kept and handed out again while input storage, version and weights match.
 MEMO = {'on': True}
+# CUDA graphs of the Python-driven gradient sweeps (BranchProgram.backward_full / neumann) where they are host-bound:
+# row counts up to max_rows (the two deeper CIFAR scales, the MLP flows), captured after `warmup` eager calls.
+SWEEP_GRAPHS = {'on': True, 'max_rows': 20000, 'warmup': 2}
 
 _conv3_ws = {}      # (device index, stream) -> workspace tensor shared by every plan used on that stream
 
@@ -176,6 +179,8 @@ class BranchProgram(object):
         self._key = None
         self._weights = None
         self._saved = None
+        self._D_static = None           # d sigma / d W twins while a sweep graph is captured (see _graphed)
+        self._sweep_graphs = {}
 
     # ---------------------------------------------------------------- weights
     def _acts(self):
@@ -752,7 +757,7 @@ class BranchProgram(object):
             if wbars[i] is not None:
                 w, Wbar = ws[i], wbars[i]
                 W = m.weight.detach()
-                D = m.sigma_gradient()
+                D = self._D_static[id(m)] if self._D_static is not None else m.sigma_gradient()
                 if FUSED_SN_GRAD['on'] and Wbar.dim() == 2 and Wbar.stride(1) == 1 and W.is_contiguous() \
                         and D.is_contiguous() and D.shape == W.shape:
                     kind = 0 if w.kind == 'mm' else (1 if w.a_type else 2)
@@ -781,6 +786,12 @@ class BranchProgram(object):
 
     def backward_full(self, saved, gout, need_input_grad=True):
         """First-order backward of y = nnet(x): returns (g^T J or None, [dL/dp for p in parameters()])."""
+        if self._graphable(saved, gout):
+            out = self._graphed('backward_full', saved, (gout,), (bool(need_input_grad),))
+            return out[0], list(out[1:])
+        return self._backward_full_eager(saved, gout, need_input_grad)
+
+    def _backward_full_eager(self, saved, gout, need_input_grad=True):
         meta, M, pres, ains = saved.meta, saved.M, saved.pres, self._ains(saved)
         ws = self._prep(M)
         n = len(self.stages)
@@ -816,6 +827,108 @@ class BranchProgram(object):
             G = _T(f=pbar, s=split)
         gx = self._from_rows(G.f32(), meta) if need_input_grad else None
         return gx, self._finish_param_grads(ws, wbars, bbars, betabars)
+
+    # ---------------------------------------------------------------- CUDA graphs of the gradient sweeps
+    # backward_full() and neumann() are fixed sequences of 35 / 50 launches with no data-dependent control flow.  At
+    # the deeper scales (and for the MLP flows) the GPU finishes them faster than Python can issue them, so after
+    # SWEEP_GRAPHS['warmup'] eager calls a sweep is captured once into a CUDA graph over STATIC copies of everything
+    # it reads that changes between steps (saved pre-activations, the incoming vectors, the prepared weight planes,
+    # softplus(beta), sigma and d sigma / d W), and every later call is: one multi-tensor copy into the static
+    # inputs, one graph launch, one multi-tensor copy of the results out of the graph's private pool.
+    def _graphable(self, saved, like):
+        return (SWEEP_GRAPHS['on'] and like.is_cuda and saved.M <= SWEEP_GRAPHS['max_rows']
+                and not torch.cuda.is_current_stream_capturing())
+
+    def _dynamic_inputs(self, saved, vecs):
+        ws = self._prep(saved.M)
+        dyn = [saved.rows] + [p for p in saved.pres if p is not None and p is not saved.rows]
+        dyn += [v for v in vecs if v is not None]
+        for w in ws:
+            dyn += [w.fwd, w.bwd, w.sigma]
+            dyn += list(w.fwd_split) if w.fwd_split is not None else []
+            dyn += list(w.bwd_split) if w.bwd_split is not None else []
+        dyn += [a._beta for a in self._acts() if a is not None and a.beta_sp() is not None]
+        dyn += [m.sigma_gradient() for _, m in self.stages]
+        return dyn, ws
+
+    def _graphed(self, kind, saved, vecs, flags):
+        dyn, ws = self._dynamic_inputs(saved, vecs)
+        key = (kind, flags, saved.M, saved.meta, tuple(v is None for v in vecs),
+               tuple((tuple(t.shape), t.dtype) for t in dyn), tuple(p.data_ptr() for p in self.params),
+               ops.get_gemm_backend(), dyn[0].device.index)
+        G = self._sweep_graphs.get(key)
+        if G is None:
+            if len(self._sweep_graphs) > 8:
+                self._sweep_graphs.clear()
+            G = self._sweep_graphs[key] = {'calls': 0, 'graph': None}
+        eager = self._backward_full_eager if kind == 'backward_full' else self._neumann_eager
+        if G['graph'] is None:
+            G['calls'] += 1
+            if G['calls'] <= SWEEP_GRAPHS['warmup']:
+                out = eager(saved, *vecs, *flags)
+                return self._flatten_sweep(kind, out, flags)
+            self._capture_sweep(G, kind, eager, saved, vecs, flags, dyn, ws)
+        else:
+            torch._foreach_copy_(G['static_in'], dyn)
+        G['graph'].replay()
+        if ops.GEMM_PROFILE['on']:
+            for k, c in G['gemm_profile'].items():
+                ops.GEMM_PROFILE['shapes'][k] = ops.GEMM_PROFILE['shapes'].get(k, 0) + c
+        _cabi.load().impflow_add_launch_count(G['launches'])
+        live = [o for o in G['outputs'] if o is not None]
+        fresh = [torch.empty_like(o) for o in live]
+        torch._foreach_copy_(fresh, live)
+        it = iter(fresh)
+        return [None if o is None else next(it) for o in G['outputs']]
+
+    @staticmethod
+    def _flatten_sweep(kind, out, flags):
+        if kind == 'backward_full':
+            return [out[0]] + list(out[1])
+        if flags[0]:
+            return [out[0], out[1]] + list(out[2]) + [out[3]]
+        return [out[0], out[1]] + list(out[2])
+
+    def _capture_sweep(self, G, kind, eager, saved, vecs, flags, dyn, ws):
+        static_in = [t.clone() for t in dyn]
+        twin = {id(t): s_ for t, s_ in zip(dyn, static_in)}
+        T = lambda t: None if t is None else twin[id(t)]
+        saved_s = _Saved()
+        saved_s.rows, saved_s.meta, saved_s.M = T(saved.rows), saved.meta, saved.M
+        saved_s.pres = [T(p) for p in saved.pres]
+        saved_s.ains, saved_s.derivs = None, {}
+        ws_s = []
+        for w in ws:
+            w2 = _Weights()
+            for name in _Weights.__slots__:
+                setattr(w2, name, getattr(w, name, None))
+            w2.fwd, w2.bwd, w2.sigma = T(w.fwd), T(w.bwd), T(w.sigma)
+            w2.fwd_split = tuple(T(t) for t in w.fwd_split) if w.fwd_split is not None else None
+            w2.bwd_split = tuple(T(t) for t in w.bwd_split) if w.bwd_split is not None else None
+            ws_s.append(w2)
+        acts = [a for a in self._acts() if a is not None and a._beta is not None]
+        old_betas = [a._beta for a in acts]
+        old_weights = self._weights
+        launches0 = _cabi.launch_count()
+        prof_on, prof_old = ops.GEMM_PROFILE['on'], ops.GEMM_PROFILE['shapes']
+        graph = torch.cuda.CUDAGraph()
+        try:
+            for a in acts:
+                a._beta = T(a._beta)
+            self._weights = ws_s
+            self._D_static = {id(m): T(m.sigma_gradient()) for _, m in self.stages}
+            ops.GEMM_PROFILE['on'], ops.GEMM_PROFILE['shapes'] = True, {}
+            with torch.cuda.graph(graph):
+                out = eager(saved_s, *[T(v) for v in vecs], *flags)
+            G['gemm_profile'] = dict(ops.GEMM_PROFILE['shapes'])
+        finally:
+            ops.GEMM_PROFILE['on'], ops.GEMM_PROFILE['shapes'] = prof_on, prof_old
+            self._weights = old_weights
+            self._D_static = None
+            for a, b in zip(acts, old_betas):
+                a._beta = b
+        G['launches'] = _cabi.launch_count() - launches0
+        G['static_in'], G['outputs'], G['graph'] = static_in, self._flatten_sweep(kind, out, flags), graph
 
     # ---------------------------------------------------------------- tangent sweep / batched bilinear gradients
     def tangent(self, saved, v_vec):
@@ -864,6 +977,14 @@ class BranchProgram(object):
         """S_b = <w_b^T J_b, v_b> together with dS/dx and dS/dtheta of S = sum_b c_b S_b
         (c = seed_scale or 1), by one tangent sweep and one two-adjoint reverse sweep.
         want_tangent: also return J v (module layout), the by-product of the tangent sweep."""
+        if self._graphable(saved, w_vec):
+            out = self._graphed('neumann', saved, (w_vec, v_vec, seed_scale), (bool(want_tangent),))
+            if want_tangent:
+                return out[0], out[1], list(out[2:-1]), out[-1]
+            return out[0], out[1], list(out[2:])
+        return self._neumann_eager(saved, w_vec, v_vec, seed_scale, want_tangent)
+
+    def _neumann_eager(self, saved, w_vec, v_vec, seed_scale=None, want_tangent=False):
         meta, M, pres, ains = saved.meta, saved.M, saved.pres, self._ains(saved)
         ws = self._prep(M)
         n = len(self.stages)

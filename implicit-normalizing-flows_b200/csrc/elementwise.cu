@@ -604,6 +604,7 @@ extern "C" int impflow_actnorm_backward(const float* gy, const float* y, const f
 extern "C" int impflow_version(void) { return IMPFLOW_ABI_VERSION; }
 extern "C" const char* impflow_last_error(void) { return impflow::g_err; }
 extern "C" long long impflow_launch_count(void) { return impflow::g_launch_count; }
+extern "C" void impflow_add_launch_count(long long n) { impflow::g_launch_count += n; }
 extern "C" int impflow_set_pdl(int on) {
   const int prev = impflow::g_pdl;
   impflow::g_pdl = on ? 1 : 0;

@@ -39,6 +39,8 @@ int impflow_version(void);
 const char* impflow_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py gpu_launches) */
 long long impflow_launch_count(void);
+/* kernels of this library launched by replaying a CUDA graph the host captured (they do not pass the launchers) */
+void impflow_add_launch_count(long long n);
 
 /* ------------------------------------------------------------------------------------------
  * Broyden solver algebra — replaces lib/layers/broyden.py:101-193 (rmatvec, matvec, the

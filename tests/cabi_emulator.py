@@ -583,6 +583,9 @@ class EmulatedLib(object):
     def impflow_chain23_set_multicast(self, on):
         return 1
 
+    def impflow_add_launch_count(self, n):
+        self.launches += int(n)
+
     def impflow_sn_conv_set_ctas(self, ctas):
         return 32
 

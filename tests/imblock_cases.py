@@ -751,3 +751,54 @@ def case_fused_adam_matches_reference_golden(golden):
         for i, p in enumerate(params):
             np.testing.assert_allclose(p.detach().cpu().numpy(), fx['p%d_%d' % (t + 1, i)], rtol=3e-6, atol=1e-7)
             np.testing.assert_allclose(shadow[i].cpu().numpy(), fx['ema%d_%d' % (t + 1, i)], rtol=3e-6, atol=1e-7)
+
+
+def case_sweep_graphs_match_eager():
+    """BranchProgram.neumann / backward_full replayed from their CUDA graphs (branch_program.SWEEP_GRAPHS) against
+    the eager launch sequences, over several "steps" in which the inputs, the saved forward, the weights, the betas
+    and the singular vectors all change: a graph must read every one of them through its static inputs."""
+    pkg = _pkg()
+    from impflow_b200 import branch_program as bp
+    from impflow_b200.branch_program import compile_branch
+    L = pkg.layers
+    dev = DEV['device']
+    if dev == 'cpu':
+        pytest.skip('CUDA graphs need the GPU')
+    torch.manual_seed(17)
+    for kind in ('conv', 'mlp'):
+        if kind == 'conv':
+            net = build_conv_branch(L, 4, 64, 0.9, 1e-3, True).to(dev)
+            shape = (4, 4, 8, 8)
+        else:
+            net = build_mlp(L, [6, 32, 32, 6], 0.9, None, 1e-3, 6).to(dev)
+            shape = (40, 6)
+        with torch.no_grad():
+            net(torch.randn(*shape, device=dev))
+        prog = compile_branch(net)
+        calls_before = len(prog._sweep_graphs)
+        for step in range(6):
+            with torch.no_grad():
+                for p in net.parameters():                    # an "optimiser step": weights, biases and betas move
+                    p.add_(0.05 * torch.randn_like(p))
+                torch.autograd.graph.increment_version(list(net.parameters()))
+                L.base.update_lipschitz(net)
+                x = torch.randn(*shape, device=dev)
+                w, v = torch.randn(*shape, device=dev), torch.randn(*shape, device=dev)
+                seed = torch.rand(shape[0], device=dev) + 0.5
+                got, want = [], []
+                for on, sink in ((True, got), (False, want)):
+                    bp.SWEEP_GRAPHS['on'] = on
+                    try:
+                        _, saved = prog.forward_saved(x)
+                        S, gx, gp, tang = prog.neumann(saved, w, v, seed_scale=seed, want_tangent=True)
+                        gx2, gp2 = prog.backward_full(saved, w)
+                        sink.extend([S, gx, tang, gx2] + [g for g in gp if g is not None] +
+                                    [g for g in gp2 if g is not None])
+                    finally:
+                        bp.SWEEP_GRAPHS['on'] = True
+                assert len(got) == len(want)
+                for a, b in zip(got, want):
+                    scale = max(float(b.abs().max()), 1e-30)
+                    assert float((a - b).abs().max()) / scale < 1e-5, (kind, step)
+        graphs = [g for g in prog._sweep_graphs.values() if g['graph'] is not None]
+        assert len(graphs) == 2, 'both sweeps must have been captured and replayed'

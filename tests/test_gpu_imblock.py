@@ -56,6 +56,10 @@ def test_mlp_solver_per_layer_beta():
     cases.case_mlp_solver_per_layer_beta()
 
 
+def test_sweep_graphs_match_eager():
+    cases.case_sweep_graphs_match_eager()
+
+
 @pytest.mark.parametrize('tag', list(cases.IRES))
 def test_iresblock(golden, tag):
     cases.case_iresblock(golden, tag)
