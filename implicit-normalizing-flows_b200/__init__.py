@@ -8,6 +8,7 @@ package under the reference's import names (`lib.layers`, `lib.layers.base`, `li
 so the reference train scripts run unchanged."""
 from . import _cabi  # noqa: F401
 from . import ops  # noqa: F401
+from . import branch_program  # noqa: F401
 from . import layers  # noqa: F401
 from . import implicit_flow  # noqa: F401
 from . import resflow  # noqa: F401

@@ -836,7 +836,9 @@ class BranchProgram(object):
     # softplus(beta), sigma and d sigma / d W), and every later call is: one multi-tensor copy into the static
     # inputs, one graph launch, one multi-tensor copy of the results out of the graph's private pool.
     def _graphable(self, saved, like):
-        return (SWEEP_GRAPHS['on'] and like.is_cuda and saved.M <= SWEEP_GRAPHS['max_rows']
+        # conv branches only: the row count of an MLP flow's batched sweep changes with the roulette draw of every
+        # step (n-fold batch), which would mean a new capture (device sync + allocator reset) per distinct n
+        return (SWEEP_GRAPHS['on'] and like.is_cuda and not self.is_linear and saved.M <= SWEEP_GRAPHS['max_rows']
                 and not torch.cuda.is_current_stream_capturing())
 
     def _dynamic_inputs(self, saved, vecs):
