@@ -60,8 +60,10 @@ NEUMANN_FUSED = {'on': True}
 # last saved forward of a program is kept and handed out again while input storage, version and weights match.
 MEMO = {'on': True}
 # CUDA graphs of the Python-driven gradient sweeps (BranchProgram.backward_full / neumann) where they are host-bound:
-# row counts up to max_rows (the two deeper CIFAR scales, the MLP flows), captured after `warmup` eager calls.
-SWEEP_GRAPHS = {'on': True, 'max_rows': 20000, 'warmup': 2}
+# conv branches with at most max_rows pixel rows (B=64: the deepest CIFAR scale; smaller per-GPU batches, i.e. strong
+# scaling: more of them), captured after `warmup` eager calls.  Measured (bench.py, e2e ms/step, B200): B=64 71.6 ->
+# 69.6 (max_rows 8192; 20000: 70.9), B=16 46.8 -> 38.0.
+SWEEP_GRAPHS = {'on': True, 'max_rows': 8192, 'warmup': 2}
 
 _conv3_ws = {}      # (device index, stream) -> workspace tensor shared by every plan used on that stream
 
