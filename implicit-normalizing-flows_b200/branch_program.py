@@ -922,8 +922,20 @@ class BranchProgram(object):
             self._weights = ws_s
             self._D_static = {id(m): T(m.sigma_gradient()) for _, m in self.stages}
             ops.GEMM_PROFILE['on'], ops.GEMM_PROFILE['shapes'] = True, {}
-            with torch.cuda.graph(graph):
-                out = eager(saved_s, *[T(v) for v in vecs], *flags)
+            # capture_begin / capture_end directly: the torch.cuda.graph context manager also synchronises the device
+            # and EMPTIES the caching allocator, after which the following steps re-allocate everything
+            cur = torch.cuda.current_stream()
+            side = SWEEP_GRAPHS.get('stream')
+            if side is None or side.device != cur.device:
+                side = SWEEP_GRAPHS['stream'] = torch.cuda.Stream(device=cur.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                graph.capture_begin()
+                try:
+                    out = eager(saved_s, *[T(v) for v in vecs], *flags)
+                finally:
+                    graph.capture_end()
+            cur.wait_stream(side)
             G['gemm_profile'] = dict(ops.GEMM_PROFILE['shapes'])
         finally:
             ops.GEMM_PROFILE['on'], ops.GEMM_PROFILE['shapes'] = prof_on, prof_old
