@@ -573,6 +573,8 @@ def main():
         pkg.branch_program.SWEEP_GRAPHS['on'] = False
     if os.environ.get('IMPFLOW_SWEEP_ROWS', ''):             # A/B: largest row count whose sweeps are graphed
         pkg.branch_program.SWEEP_GRAPHS['max_rows'] = int(os.environ['IMPFLOW_SWEEP_ROWS'])
+    if os.environ.get('IMPFLOW_WGRAD_ORDER', '') == '0':     # A/B: tile-major weight-gradient work order
+        pkg._cabi.load().impflow_wgrad_set_slice_major(0)
     if os.environ.get('IMPFLOW_SN_CTAS', ''):                # A/B: CTAs per 3x3 power-iteration launch
         pkg._cabi.load().impflow_sn_conv_set_ctas(int(os.environ['IMPFLOW_SN_CTAS']))
     if os.environ.get('IMPFLOW_RUNAHEAD', ''):               # A/B: 0 = synchronise the solver loop every iteration

@@ -46,7 +46,7 @@ template <int BN>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 k_wgrad_tc3(const __grid_constant__ CUtensorMap mapGhi, const __grid_constant__ CUtensorMap mapGlo,
             const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo, long long Mpix,
-            int N1, int N2, int splits, float* __restrict__ ws) {
+            int N1, int N2, int splits, float* __restrict__ ws, int slice_major) {
   using Cfg = WgCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -100,7 +100,7 @@ k_wgrad_tc3(const __grid_constant__ CUtensorMap mapGhi, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int mn = item % mn_tiles, ks = item / mn_tiles;   // slice-major: see num_items
+        const int mn = slice_major ? item % mn_tiles : item / splits, ks = slice_major ? item / mn_tiles : item % splits;
         const int n1_0 = (mn / n_tiles) * 128, n2_0 = (mn % n_tiles) * BN;
         const int kb_end = min(num_kb, (ks + 1) * kb_per);
         for (int kb = ks * kb_per; kb < kb_end; ++kb) {
@@ -132,7 +132,7 @@ k_wgrad_tc3(const __grid_constant__ CUtensorMap mapGhi, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int ks = item / mn_tiles;
+      const int ks = slice_major ? item / mn_tiles : item % splits;
       const int kb_begin = ks * kb_per, kb_end = min(num_kb, kb_begin + kb_per);
       mbar_wait(tempty, acc_phase ^ 1);
       tc_fence_after();
@@ -172,7 +172,7 @@ k_wgrad_tc3(const __grid_constant__ CUtensorMap mapGhi, const __grid_constant__ 
     const int q = warp & 3;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int mn = item % mn_tiles, ks = item / mn_tiles;   // slice-major: see num_items
+      const int mn = slice_major ? item % mn_tiles : item / splits, ks = slice_major ? item / mn_tiles : item % splits;
       const int n1 = (mn / n_tiles) * 128 + q * 32 + lane;
       const int n2_0 = (mn % n_tiles) * BN;
       mbar_wait(tfull, acc_phase);
@@ -244,6 +244,8 @@ static int wg_splits(long long Mpix, int N1, int N2) {
   return s < 1 ? 1 : (int)s;
 }
 
+static int g_wgrad_slice_major = 1;
+
 template <int BN>
 static int launch_wgrad(const CUtensorMap* maps, long long Mpix, int N1, int N2, int splits, float* ws,
                         cudaStream_t s) {
@@ -259,13 +261,19 @@ static int launch_wgrad(const CUtensorMap* maps, long long Mpix, int N1, int N2,
   const long long items = (long long)((N1 + 127) / 128) * ((N2 + BN - 1) / BN) * splits;
   const int grid = (int)(items < 148 ? items : 148);
   k_wgrad_tc3<BN><<<grid, WG_THREADS, WgCfg<BN>::kSmemBytes, s>>>(maps[0], maps[1], maps[2], maps[3], Mpix, N1, N2,
-                                                                   splits, ws);
+                                                                   splits, ws, g_wgrad_slice_major);
   return check_launch("k_wgrad_tc3");
 }
 
 }  // namespace impflow
 
 using namespace impflow;
+
+extern "C" int impflow_wgrad_set_slice_major(int on) {
+  const int prev = g_wgrad_slice_major;
+  g_wgrad_slice_major = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" size_t impflow_wgrad_tc_workspace_floats(long long Mpix, int N1, int N2) {
   return (size_t)wg_splits(Mpix, N1, N2) * (size_t)N1 * (size_t)N2;

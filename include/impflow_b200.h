@@ -248,6 +248,9 @@ int impflow_set_pdl(int on);
  * out[n1*ldo + n2] (or out[n2*ldo + n1] when transpose_out) receives the fixed-order sum of the split-K
  * partials; ws holds impflow_wgrad_tc_workspace_floats() floats. */
 size_t impflow_wgrad_tc_workspace_floats(long long Mpix, int N1, int N2);
+/* A/B switch: 1 (default) = work items in slice-major order (all output tiles of a K slice side by side: every
+ * operand slice leaves DRAM once), 0 = tile-major (round 1).  Returns the previous setting. */
+int impflow_wgrad_set_slice_major(int on);
 int impflow_wgrad_tc(const float* G_hi, const float* G_lo, long long ldg, const float* A_hi, const float* A_lo,
                      long long lda, float* out, long long ldo, int transpose_out, long long Mpix, int N1, int N2,
                      float* ws, void* stream);

@@ -583,6 +583,9 @@ class EmulatedLib(object):
     def impflow_chain23_set_multicast(self, on):
         return 1
 
+    def impflow_wgrad_set_slice_major(self, on):
+        return 1
+
     def impflow_add_launch_count(self, n):
         self.launches += int(n)
 
