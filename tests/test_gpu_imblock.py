@@ -56,6 +56,16 @@ def test_mlp_solver_per_layer_beta():
     cases.case_mlp_solver_per_layer_beta()
 
 
+@pytest.mark.parametrize('c,hw', [(3, 32), (12, 16), (48, 8)])
+def test_block_at_cifar_scale_real_width(c, hw):
+    """One training step of a conv imBlock at each CIFAR scale with the REAL hidden width (C = 512; c = 3 @ 32x32,
+    12 @ 16x16, 48 @ 8x8; B = 8) against the CPU oracle on the same weights, roulette draw and probes: forward
+    iteration count exact, z <= 1e-5, log-det <= 1e-4, gradients.  Scale 0 runs on k_branch3, scales 1 / 2 on the
+    layer-1 GEMM + k_chain23."""
+    res = cases.case_wide_conv_block_vs_oracle(width=512, c=c, hw=hw, batch=8, verbose=True)
+    assert res['fwd_nstep'][0] == res['fwd_nstep'][1]
+
+
 def test_sweep_graphs_match_eager():
     cases.case_sweep_graphs_match_eager()
 
