@@ -20,6 +20,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from .. import ops
+from ..parallel import sink_grads
 from .broyden import broyden, broyden_mlp, broyden_mlp_vjp
 
 __all__ = ['imBlock']
@@ -77,7 +78,8 @@ class _BranchApply(Function):
     def backward(ctx, gout):
         gx, pgrads = ctx.prog.backward_full(ctx.saved_state, gout, need_input_grad=ctx.need_x)
         ctx.saved_state = None
-        return (gx, None) + tuple(pgrads)
+        # finished gradients go straight into the flat bucket when there is one (no AccumulateGrad launches)
+        return (gx, None) + tuple(sink_grads(ctx.prog.params, pgrads))
 
 
 def branch_apply(nnet, x):
@@ -563,6 +565,7 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
     @staticmethod
     def forward(ctx, estimator_fn, gnet, x, n_power_series, vareps, coeff_fn, training, payload, *g_params):
         ctx.training = training
+        ctx.g_params = g_params
         if payload is None:
             payload = MemoryEfficientLogDetEstimator.payload(estimator_fn, gnet, x, n_power_series, vareps, coeff_fn,
                                                              training)
@@ -596,7 +599,7 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
             live = [grad_x] + [gp for gp, m in zip(grad_params, ctx.none_mask) if not m]
             scaled = iter(torch._foreach_mul(live, dL.reshape(())))
             grad_x = next(scaled)
-            grad_params = tuple(None if m else next(scaled) for m in ctx.none_mask)
+            grad_params = tuple(sink_grads(ctx.g_params, [None if m else next(scaled) for m in ctx.none_mask]))
         return (None, None, grad_x, None, None, None, None, None) + grad_params
 
 
@@ -653,7 +656,7 @@ class _GraphFreeBasic(Function):
         else:
             _, gx, gparams = prog.neumann(saved, wsum[0], rs[0], seed_scale=seed)
         ctx.ls = ctx.saved_fwd = None
-        return (gx, None, None, None) + tuple(gparams)
+        return (gx, None, None, None) + tuple(sink_grads(prog.params, gparams))
 
 
 def basic_logdet_estimator(g, x, n_power_series, vareps, coeff_fn, training, program=None):

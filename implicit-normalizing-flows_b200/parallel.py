@@ -8,7 +8,7 @@ torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)."""
 import torch
 import torch.distributed as dist
 
-__all__ = ['shard_batch', 'broadcast_module', 'FlatGradBucket', 'allreduce_mean_scalar']
+__all__ = ['shard_batch', 'broadcast_module', 'FlatGradBucket', 'allreduce_mean_scalar', 'sink_grads']
 
 
 def shard_batch(x, rank=None, world_size=None):
@@ -44,8 +44,12 @@ class FlatGradBucket(object):
 
     ALIGN = 64      # floats
 
-    def __init__(self, params):
+    def __init__(self, params, direct=True):
+        """direct: the graph-free backward sweeps of this package add their finished parameter gradients straight
+        into the bucket (sink_grads) instead of handing them to autograd's per-parameter AccumulateGrad nodes."""
         self.params = [p for p in params if p.requires_grad]
+        self.direct = direct
+        self._armed = False
         # every tensor starts on a 256-byte boundary (the kernels read biases / weights with vector loads);
         # the padding stays zero, so norms and the all-reduce are unaffected
         self.offsets, off = [], 0
@@ -58,10 +62,13 @@ class FlatGradBucket(object):
         self.flat = torch.zeros(off, device=dev, dtype=torch.float32)
         self.views = []
         self.had_grad = [True] * len(self.params)      # of the latest gather_strays()
-        for p, o in zip(self.params, self.offsets):
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
             v = self.flat[o:o + p.numel()].view_as(p)
             p.grad = v
             self.views.append(v)
+            if direct:
+                p._impflow_grad_sink = (self, i)
+        self._touched = [False] * len(self.params)
 
     def zero(self):
         """Start of a step.  The .grad slots are emptied rather than pointed at the (zeroed) views: autograd then
@@ -70,29 +77,48 @@ class FlatGradBucket(object):
         self.flat.zero_()
         for p in self.params:
             p.grad = None
+        self._touched = [False] * len(self.params)
+        self._armed = self.direct       # between zero() and the gather, finished gradients may be added directly
+
+    def sink(self, idxs, grads):
+        """views[i] += grads[i] for all i in one multi-tensor launch (called by sink_grads)."""
+        with torch.no_grad():
+            torch._foreach_add_([self.views[i].view(-1) for i in idxs], [g.detach().reshape(-1) for g in grads])
+        for i in idxs:
+            self._touched[i] = True
 
     def gather_strays(self):
         """Copy the gradients autograd produced outside the bucket into it (one multi-tensor launch) and point
         every .grad at its view; parameters without a gradient keep the zeros."""
         if all(p.grad is v for p, v in zip(self.params, self.views)):
             return      # nothing outside the bucket (e.g. the optimiser's call after allreduce_mean's)
-        dst, src, empty = [], [], []
-        self.had_grad = [p.grad is not None for p in self.params]
-        for p, v in zip(self.params, self.views):
+        dst, src, add_dst, add_src, empty = [], [], [], [], []
+        touched = self._touched
+        self.had_grad = [p.grad is not None or t for p, t in zip(self.params, touched)]
+        for p, v, t in zip(self.params, self.views, touched):
             g = p.grad
             if g is None:
-                empty.append(v)        # stays zero also when the caller used zero_grad() instead of zero()
+                if not t:
+                    empty.append(v)    # stays zero also when the caller used zero_grad() instead of zero()
             elif g.data_ptr() != v.data_ptr():
                 # flat views on both sides: the multi-tensor fast path needs equal strides (size-1 dimensions
                 # of conv weights can carry different ones), else it degrades to one cudaMemcpy per tensor
-                dst.append(v.view(-1))
-                src.append(g.detach().reshape(-1))
+                if t:                  # part of the gradient was added directly, the rest came through autograd
+                    add_dst.append(v.view(-1))
+                    add_src.append(g.detach().reshape(-1))
+                else:
+                    dst.append(v.view(-1))
+                    src.append(g.detach().reshape(-1))
             p.grad = v
+        self._armed = False
+        self._touched = [False] * len(self.params)
         with torch.no_grad():
             if empty:
                 torch._foreach_zero_(empty)
             if dst:
                 torch._foreach_copy_(dst, src)
+            if add_dst:
+                torch._foreach_add_(add_dst, add_src)
 
     def allreduce_mean(self, group=None):
         self.gather_strays()
@@ -100,6 +126,27 @@ class FlatGradBucket(object):
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(dist.get_world_size(group))
         return self.flat
+
+
+def sink_grads(params, grads):
+    """Finished parameter gradients of a graph-free backward sweep -> straight into the flat bucket (one multi-tensor
+    add per bucket) where the parameter has one that is armed (between FlatGradBucket.zero() and the gather); the
+    entries that were taken come back as None, so autograd has nothing to accumulate for them.  Without a bucket
+    the list is returned unchanged."""
+    out, per_bucket = list(grads), {}
+    for i, (p, g) in enumerate(zip(params, grads)):
+        if g is None:
+            continue
+        s = getattr(p, '_impflow_grad_sink', None)
+        if s is None or not s[0]._armed or s[0].params[s[1]] is not p:
+            continue
+        idxs, gs = per_bucket.setdefault(id(s[0]), (s[0], [], []))[1:]
+        idxs.append(s[1])
+        gs.append(g)
+        out[i] = None
+    for bucket, idxs, gs in per_bucket.values():
+        bucket.sink(idxs, gs)
+    return out
 
 
 def allreduce_mean_scalar(t, group=None):

@@ -798,3 +798,53 @@ def case_sweep_graphs_match_eager():
                     assert float((a - b).abs().max()) / scale < 1e-5, (kind, step)
         graphs = [g for g in prog._sweep_graphs.values() if g['graph'] is not None]
         assert len(graphs) == 2, 'both sweeps must have been captured and replayed'
+
+
+def case_direct_grad_sink_matches_autograd(golden):
+    """FlatGradBucket(direct=True): the graph-free backward sweeps add their finished parameter gradients straight
+    into the bucket (parallel.sink_grads) instead of returning them to autograd; the flat gradient after one step of
+    the small multiscale flow must equal the one autograd's AccumulateGrad nodes build (direct=False)."""
+    pkg = _pkg()
+    layers = pkg.layers
+    fx = golden('flow_small')
+    B, c, hw = 4, 3, 8
+    flats = []
+    for direct in (True, False):
+        torch.manual_seed(0)
+        model = pkg.ImplicitFlow(
+            (B, c, hw, hw), n_blocks=[1, 1], intermediate_dim=16, factor_out=False, quadratic=False,
+            init_layer=layers.LogitTransform(0.05), actnorm=True, fc_actnorm=False, batchnorm=False, dropout=0.,
+            fc=False, coeff=0.9, vnorms='2222', n_lipschitz_iters=None, sn_atol=1e-3, sn_rtol=1e-3,
+            n_power_series=None, n_dist='poisson', n_samples=1, kernels='3-1-3', activation_fn='swish', fc_end=False,
+            fc_idim=128, n_exact_terms=3, preact=True, neumann_grad=True, grad_in_forward=True, first_resblock=True,
+            learn_p=False, classification=False, classification_hdim=64, n_classes=10).to(DEV["device"])
+        x = torch.from_numpy(fx['x']).to(DEV["device"])
+        with torch.no_grad():
+            model(x, restore=True)
+        model.load_state_dict({k: v.to(DEV["device"]) for k, v in sub_sd(fx, 'sd_').items()}, strict=True)
+        model.train()
+        params = [p for p in model.parameters() if p.requires_grad]
+        bucket = pkg.parallel.FlatGradBucket(params, direct=direct)
+        np.random.seed(int(fx['seed']))
+        torch.manual_seed(int(fx['seed']))
+        bucket.zero()
+        z, dlogp = model(x, 0)
+        ndim = c * hw * hw
+        logpz = std_normal_logprob(z).view(z.size(0), -1).sum(1, keepdim=True)
+        bpd = -torch.mean(logpz - dlogp - np.log(256) * ndim) / ndim / np.log(2)
+        bpd.backward()
+        if direct:
+            assert any(bucket._touched), 'no gradient took the direct path'
+        bucket.gather_strays()
+        assert all(p.grad is v for p, v in zip(bucket.params, bucket.views))
+        flats.append((bucket.flat.detach().cpu().clone(), list(bucket.had_grad)))
+    (a, ha), (b, hb) = flats
+    assert ha == hb
+    assert rel_err(a, b) < 1e-6
+    # and against the reference's gradients
+    worst = 0.0
+    for (n, p), v in zip([(n, p) for n, p in model.named_parameters() if p.requires_grad], bucket.views):
+        ref = fx.get('grad_' + n)
+        if ref is not None and np.linalg.norm(ref) > 1e-6:
+            worst = max(worst, rel_err(v.detach().cpu(), ref))
+    assert worst < 5e-3, worst

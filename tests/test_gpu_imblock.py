@@ -56,6 +56,10 @@ def test_mlp_solver_per_layer_beta():
     cases.case_mlp_solver_per_layer_beta()
 
 
+def test_direct_grad_sink_matches_autograd(golden):
+    cases.case_direct_grad_sink_matches_autograd(golden)
+
+
 @pytest.mark.parametrize('c,hw', [(3, 32), (12, 16), (48, 8)])
 def test_block_at_cifar_scale_real_width(c, hw):
     """One training step of a conv imBlock at each CIFAR scale with the REAL hidden width (C = 512; c = 3 @ 32x32,

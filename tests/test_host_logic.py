@@ -63,6 +63,10 @@ def test_mlp_solver_per_layer_beta():
     cases.case_mlp_solver_per_layer_beta()
 
 
+def test_direct_grad_sink_matches_autograd(golden):
+    cases.case_direct_grad_sink_matches_autograd(golden)
+
+
 @pytest.mark.parametrize('tag', list(cases.IRES))
 def test_iresblock(golden, tag):
     cases.case_iresblock(golden, tag)
