@@ -579,6 +579,8 @@ def main():
         pkg._cabi.load().impflow_sn_conv_set_ctas(int(os.environ['IMPFLOW_SN_CTAS']))
     if os.environ.get('IMPFLOW_RUNAHEAD', ''):               # A/B: 0 = synchronise the solver loop every iteration
         pkg._cabi.load().impflow_conv3_set_runahead(int(os.environ['IMPFLOW_RUNAHEAD']))
+    if os.environ.get('IMPFLOW_CHAIN23_A32', '') == '1':     # A/B: one fp32 plane between layer 1 and k_chain23
+        pkg._cabi.load().impflow_conv3_set_chain23_a32(1)
     if os.environ.get('IMPFLOW_CHAIN23', '') == '0':         # A/B: two GEMM launches instead of k_chain23
         pkg._cabi.load().impflow_conv3_set_chain23(0)
         pkg.ops.CHAIN23['on'] = False

@@ -59,6 +59,7 @@ SIGNATURES = {
     'impflow_chain23_set_multicast': (_i, [_i]),
     'impflow_chain23_tc': (_i, [_c_fp, _c_fp, _ll] + [_c_fp] * 8 + [_ll, _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
     'impflow_conv3_set_chain23': (_i, [_i]),
+    'impflow_conv3_set_chain23_a32': (_i, [_i]),
     'impflow_conv3_workspace_floats': (ctypes.c_size_t, [_i] * 6),
     'impflow_conv3_forward': (_i, [_c_fp] * 6),
     'impflow_conv3_prepare_vjp': (_i, [_c_fp] * 6),

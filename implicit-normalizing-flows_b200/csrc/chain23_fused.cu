@@ -34,6 +34,13 @@ constexpr int C23_SMEM_BYTES = C23_NS * C23_STAGE_BYTES + 1024 + 256;
 constexpr int C23_THREADS = 128 + 32 * BF_XF_WARPS;
 constexpr uint32_t C23_COL_ACC2 = 0, C23_COL_A2HI = 128, C23_COL_A2LO = 256, C23_COL_ACC3 = 384;
 
+// round to nearest, ties away (= cvt.rna.tf32.f32 for finite values) in two full-rate integer ops - the same
+// expression as the GEMM epilogue's split, so both routes give the layer-2 MMAs bit-identical operands
+__device__ __forceinline__ void split_tf32_c23(float v, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+  lo = v - hi;
+}
+
 struct Chain23Args {
   const float* bias2;    // [C] or null
   const float* mul2;     // [M, C] or null: psi2 = H * mul2
@@ -50,7 +57,11 @@ struct Chain23Args {
   const int* gate;
 };
 
-template <int ACT, bool MC>
+// A32: the layer-2 input arrives as ONE plain fp32 plane (what the layer-1 GEMM writes with half the bytes); warps 2
+// and 3 split every landed chunk into tf32 hi / lo planes in shared memory (round-to-nearest hi in place, lo = a - hi
+// beside it) before the MMAs read it.  A CTA then pulls 48 KB instead of 64 KB through L2 per K chunk - the stream that
+// bounds this kernel - and the layer-1 GEMM's epilogue writes 4 instead of 8 bytes per element.
+template <int ACT, bool MC, bool A32>
 __global__ void __launch_bounds__(C23_THREADS, 1)
 k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
           const __grid_constant__ CUtensorMap mapW2hi, const __grid_constant__ CUtensorMap mapW2lo,
@@ -67,7 +78,8 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
   uint64_t* a2_empty = a2_full + 1;         // MMA -> transform (phase B retired: A2 may be overwritten)
   uint64_t* acc3_full = a2_empty + 1;       // MMA -> epilogue
   uint64_t* acc3_empty = acc3_full + 1;     // epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc3_empty + 1);
+  uint64_t* ready = acc3_empty + 1;         // [NS] split warps -> MMA (A32: hi / lo planes of the stage are in place)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + C23_NS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,6 +102,7 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
     for (int s = 0; s < C23_NS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], MC ? 4 : 1);      // MC: the MMA commits of all four CTAs of the cluster
+      mbar_init(&ready[s], 2);               // warps 2 and 3
     }
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, BF_XF_WARPS);
@@ -125,8 +138,10 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
           const int st = gw % C23_NS;
           mbar_wait(&empty[st], ((gw / C23_NS) & 1) ^ 1);
           uint8_t* sp = smem + st * C23_STAGE_BYTES;
-          mbar_expect_tx(&full[st], C23_STAGE_BYTES);
-          if (MC) {      // this CTA's 32 rows of the shared A1 chunk, multicast to the four CTAs of the row tile
+          mbar_expect_tx(&full[st], A32 ? 3 * C23_PLANE : C23_STAGE_BYTES);
+          if (A32) {     // one fp32 plane; the lo plane of the stage is produced on chip
+            tma_load_2d(&mapAhi, &full[st], sp, kc * TC_BK, m0);
+          } else if (MC) {      // this CTA's 32 rows of the shared A1 chunk, multicast to the four CTAs of the row tile
             tma_load_2d_mc(&mapAhi, &full[st], sp + crank * 4096, kc * TC_BK, m0 + (int)crank * 32, (uint16_t)0xF);
             tma_load_2d_mc(&mapAlo, &full[st], sp + C23_PLANE + crank * 4096, kc * TC_BK, m0 + (int)crank * 32,
                            (uint16_t)0xF);
@@ -165,7 +180,7 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
       tc_fence_after();
       for (int kc = 0; kc < NC; ++kc, ++gw) {
         const uint32_t st = gw % C23_NS;
-        mbar_wait(&full[st], (gw / C23_NS) & 1);
+        mbar_wait(A32 ? &ready[st] : &full[st], (gw / C23_NS) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_hi = smem_u32(smem + st * C23_STAGE_BYTES);
@@ -196,7 +211,7 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
         tc_fence_after();
         for (int c2 = 0; c2 < NC3; ++c2, ++gw) {
           const uint32_t st = gw % C23_NS;
-          mbar_wait(&full[st], (gw / C23_NS) & 1);
+          mbar_wait(A32 ? &ready[st] : &full[st], (gw / C23_NS) & 1);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t b_hi = smem_u32(smem + st * C23_STAGE_BYTES + 2 * C23_PLANE);
@@ -219,6 +234,36 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
           }
           __syncwarp();
         }
+      }
+    }
+  } else if (A32 && (warp == 2 || warp == 3)) {
+    // ================= split warps: fp32 A chunk -> tf32 hi / lo planes, in shared memory =================
+    uint32_t gw = 0;
+    for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int kc = 0; kc < NC; ++kc, ++gw) {
+        const uint32_t st = gw % C23_NS;
+        mbar_wait(&full[st], (gw / C23_NS) & 1);
+        float4* ph = reinterpret_cast<float4*>(smem + st * C23_STAGE_BYTES);
+        float4* pl = ph + C23_PLANE / 16;
+#pragma unroll 4
+        for (int i = (warp - 2) * 32 + lane; i < C23_PLANE / 16; i += 64) {
+          const float4 v = ph[i];
+          float4 h, l;
+          split_tf32_c23(v.x, h.x, l.x);
+          split_tf32_c23(v.y, h.y, l.y);
+          split_tf32_c23(v.z, h.z, l.z);
+          split_tf32_c23(v.w, h.w, l.w);
+          ph[i] = h;
+          pl[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> the MMA's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[st]);
+      }
+      for (int u = 0; u < args.npass * NC3; ++u, ++gw) {     // layer-3 stages carry weights only: pass them on
+        const uint32_t st = gw % C23_NS;
+        mbar_wait(&full[st], (gw / C23_NS) & 1);
+        if (lane == 0) mbar_arrive(&ready[st]);
       }
     }
   } else if (warp >= 4) {
@@ -313,11 +358,11 @@ k_chain23(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CU
 
 static int g_chain23_mc = 0;     // cluster-multicast variant (impflow_chain23_set_multicast): measured SLOWER (91 vs 123 TFLOP/s), off
 
-template <int ACT, bool MC>
+template <int ACT, bool MC, bool A32>
 static int launch_chain23(const CUtensorMap* maps, const Chain23Args& a, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_chain23<ACT, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C23_SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(k_chain23<ACT, MC, A32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C23_SMEM_BYTES) !=
         cudaSuccess) {
       set_error("chain23_tc: cannot set %d bytes of dynamic shared memory", C23_SMEM_BYTES);
       return -1;
@@ -344,7 +389,7 @@ static int launch_chain23(const CUtensorMap* maps, const Chain23Args& a, cudaStr
   }
   na += pdl_attr(&attr[na]);
   cfg.numAttrs = na;
-  const cudaError_t err = cudaLaunchKernelEx(&cfg, k_chain23<ACT, MC>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a);
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, k_chain23<ACT, MC, A32>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a);
   if (err != cudaSuccess) {
     set_error("k_chain23: launch failed: %s", cudaGetErrorString(err));
     return -1;
@@ -374,6 +419,7 @@ extern "C" int impflow_chain23_tc(const float* A_hi, const float* A_lo, long lon
               "ldo=%lld part_stride=%lld)", C, lda, ldo, part_stride);
     return -2;
   }
+  IMPFLOW_REQUIRE(A_hi != nullptr, "chain23_tc: A missing");
   const uintptr_t al = reinterpret_cast<uintptr_t>(A_hi) | reinterpret_cast<uintptr_t>(A_lo) |
                        reinterpret_cast<uintptr_t>(W2_hi) | reinterpret_cast<uintptr_t>(W2_lo) |
                        reinterpret_cast<uintptr_t>(W3_hi) | reinterpret_cast<uintptr_t>(W3_lo) |
@@ -383,9 +429,11 @@ extern "C" int impflow_chain23_tc(const float* A_hi, const float* A_lo, long lon
     set_error("chain23_tc: operand base pointers must be 16-byte aligned");
     return -2;
   }
-  const bool mc = g_chain23_mc && C == 512;      // four quarter-CTAs per row tile = one cluster
+  const bool a32 = A_lo == nullptr;              // one fp32 plane, split on chip
+  const bool mc = !a32 && g_chain23_mc && C == 512;      // four quarter-CTAs per row tile = one cluster
   CUtensorMap maps[6];
-  if (make_map(&maps[0], A_hi, M, C, lda, mc ? 32 : 128) || make_map(&maps[1], A_lo, M, C, lda, mc ? 32 : 128) ||
+  if (make_map(&maps[0], A_hi, M, C, lda, mc ? 32 : 128) ||
+      make_map(&maps[1], a32 ? A_hi : A_lo, M, C, lda, mc ? 32 : 128) ||
       make_map(&maps[2], W2_hi, C, C, C, 128) || make_map(&maps[3], W2_lo, C, C, C, 128) ||
       make_map(&maps[4], W3_hi, N3, C, C, 128) || make_map(&maps[5], W3_lo, N3, C, C, 128))
     return -1;
@@ -398,18 +446,26 @@ extern "C" int impflow_chain23_tc(const float* A_hi, const float* A_lo, long lon
   a.beta2 = beta2;
   a.gate = g_gate;
   cudaStream_t s = (cudaStream_t)stream;
+  if (a32) {
+    switch (act_kind) {
+      case IMPFLOW_ACT_LIPSWISH: return launch_chain23<IMPFLOW_ACT_LIPSWISH, false, true>(maps, a, s);
+      case IMPFLOW_ACT_RELU: return launch_chain23<IMPFLOW_ACT_RELU, false, true>(maps, a, s);
+      case IMPFLOW_ACT_SIN: return launch_chain23<IMPFLOW_ACT_SIN, false, true>(maps, a, s);
+      default: return launch_chain23<IMPFLOW_ACT_NONE, false, true>(maps, a, s);
+    }
+  }
   if (mc) {
     switch (act_kind) {
-      case IMPFLOW_ACT_LIPSWISH: return launch_chain23<IMPFLOW_ACT_LIPSWISH, true>(maps, a, s);
-      case IMPFLOW_ACT_RELU: return launch_chain23<IMPFLOW_ACT_RELU, true>(maps, a, s);
-      case IMPFLOW_ACT_SIN: return launch_chain23<IMPFLOW_ACT_SIN, true>(maps, a, s);
-      default: return launch_chain23<IMPFLOW_ACT_NONE, true>(maps, a, s);
+      case IMPFLOW_ACT_LIPSWISH: return launch_chain23<IMPFLOW_ACT_LIPSWISH, true, false>(maps, a, s);
+      case IMPFLOW_ACT_RELU: return launch_chain23<IMPFLOW_ACT_RELU, true, false>(maps, a, s);
+      case IMPFLOW_ACT_SIN: return launch_chain23<IMPFLOW_ACT_SIN, true, false>(maps, a, s);
+      default: return launch_chain23<IMPFLOW_ACT_NONE, true, false>(maps, a, s);
     }
   }
   switch (act_kind) {
-    case IMPFLOW_ACT_LIPSWISH: return launch_chain23<IMPFLOW_ACT_LIPSWISH, false>(maps, a, s);
-    case IMPFLOW_ACT_RELU: return launch_chain23<IMPFLOW_ACT_RELU, false>(maps, a, s);
-    case IMPFLOW_ACT_SIN: return launch_chain23<IMPFLOW_ACT_SIN, false>(maps, a, s);
-    default: return launch_chain23<IMPFLOW_ACT_NONE, false>(maps, a, s);
+    case IMPFLOW_ACT_LIPSWISH: return launch_chain23<IMPFLOW_ACT_LIPSWISH, false, false>(maps, a, s);
+    case IMPFLOW_ACT_RELU: return launch_chain23<IMPFLOW_ACT_RELU, false, false>(maps, a, s);
+    case IMPFLOW_ACT_SIN: return launch_chain23<IMPFLOW_ACT_SIN, false, false>(maps, a, s);
+    default: return launch_chain23<IMPFLOW_ACT_NONE, false, false>(maps, a, s);
   }
 }

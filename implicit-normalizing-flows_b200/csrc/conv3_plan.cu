@@ -55,6 +55,10 @@ static inline bool use_chain23(const impflow_conv3_plan* p) {
   return g_chain23 && p->allow_fused && !use_tile_kernel(p) && (p->C % 128) == 0;
 }
 static inline int y_parts(const impflow_conv3_plan* p) { return use_chain23(p) ? p->C / 128 : 1; }
+// layer 1 hands layer 2 ONE fp32 plane (k_chain23 splits it on chip) instead of tf32 hi/lo planes.  Measured SLOWER
+// (k_chain23 79 -> 101 us at M = 16384, step 69.3 -> 71.2 ms): the kernel is bound by the SM's shared-memory port
+// (SS-form N = 128 MMAs read 128 B/clk, the TMA writes come on top), and the on-chip split adds 48 KB per chunk to it.
+static int g_chain23_a32 = 0;
 
 static int plan_check(const impflow_conv3_plan* p, const char* who) {
   if (p == nullptr || p->ws == nullptr) {
@@ -260,11 +264,13 @@ static int conv3_chain_forward(const impflow_conv3_plan* p, const Conv3Ws& w, co
   float* h2_hi = w.h2;
   float* h2_lo = w.h2 + (size_t)M * p->C;
   if (launch_in(p, x_rows, p->act0_kind, p->beta0, x0_hi, x0_lo, p->k0, nullptr, 0, s)) return -1;
-  if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W1f_hi, p->W1f_lo, p->k0, p->b1, pre1, nullptr, nullptr, h1_hi,
-                         h1_lo, p->C, M, p->C, p->k0, p->act_kind, p->beta1, nullptr, stream))
+  const bool a32 = use_chain23(p) && g_chain23_a32;
+  if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W1f_hi, p->W1f_lo, p->k0, p->b1, pre1, a32 ? h1_hi : nullptr, nullptr,
+                         a32 ? nullptr : h1_hi, a32 ? nullptr : h1_lo, p->C, M, p->C, p->k0, p->act_kind, p->beta1,
+                         nullptr, stream))
     return -1;
   if (use_chain23(p))
-    return impflow_chain23_tc(h1_hi, h1_lo, p->C, p->W2f_hi, p->W2f_lo, p->W3f_hi, p->W3f_lo, p->b2, nullptr, pre2, w.Y,
+    return impflow_chain23_tc(h1_hi, a32 ? nullptr : h1_lo, p->C, p->W2f_hi, p->W2f_lo, p->W3f_hi, p->W3f_lo, p->b2, nullptr, pre2, w.Y,
                               N3, M * N3, M, p->C, N3, p->act_kind, p->beta2, stream);
   if (impflow_gemm_nt_tc(h1_hi, h1_lo, p->C, p->W2f_hi, p->W2f_lo, p->C, p->b2, pre2, nullptr, nullptr, h2_hi, h2_lo,
                          p->C, M, p->C, p->C, p->act_kind, p->beta2, nullptr, stream))
@@ -293,11 +299,13 @@ static int conv3_chain_vjp(const impflow_conv3_plan* p, const Conv3Ws& w, const 
   float* t2_hi = w.h2;
   float* t2_lo = w.h2 + (size_t)M * p->C;
   if (launch_in(p, v_rows, IMPFLOW_ACT_NONE, nullptr, x0_hi, x0_lo, p->k0, nullptr, 0, s)) return -1;
-  if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W3b_hi, p->W3b_lo, p->k0, nullptr, nullptr, nullptr, d2, t3_hi,
-                         t3_lo, p->C, M, p->C, p->k0, IMPFLOW_ACT_MULTIPLIER, nullptr, nullptr, stream))
+  const bool a32 = use_chain23(p) && g_chain23_a32;     // dmul mode: pre_out receives acc * act'(d2)
+  if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W3b_hi, p->W3b_lo, p->k0, nullptr, a32 ? t3_hi : nullptr, nullptr, d2,
+                         a32 ? nullptr : t3_hi, a32 ? nullptr : t3_lo, p->C, M, p->C, p->k0, IMPFLOW_ACT_MULTIPLIER,
+                         nullptr, nullptr, stream))
     return -1;
   if (use_chain23(p))
-    return impflow_chain23_tc(t3_hi, t3_lo, p->C, p->W2b_hi, p->W2b_lo, p->W1b_hi, p->W1b_lo, nullptr, d1, nullptr, w.Y,
+    return impflow_chain23_tc(t3_hi, a32 ? nullptr : t3_lo, p->C, p->W2b_hi, p->W2b_lo, p->W1b_hi, p->W1b_lo, nullptr, d1, nullptr, w.Y,
                               N3, M * N3, M, p->C, N3, IMPFLOW_ACT_NONE, nullptr, stream);
   if (impflow_gemm_nt_tc(t3_hi, t3_lo, p->C, p->W2b_hi, p->W2b_lo, p->C, nullptr, nullptr, nullptr, d1, t2_hi, t2_lo,
                          p->C, M, p->C, p->C, IMPFLOW_ACT_MULTIPLIER, nullptr, nullptr, stream))
@@ -410,6 +418,12 @@ extern "C" int impflow_conv3_power_series(const impflow_conv3_plan* plan, const 
 extern "C" int impflow_conv3_set_chain23(int on) {
   const int prev = g_chain23;
   g_chain23 = on ? 1 : 0;
+  return prev;
+}
+
+extern "C" int impflow_conv3_set_chain23_a32(int on) {
+  const int prev = g_chain23_a32;
+  g_chain23_a32 = on ? 1 : 0;
   return prev;
 }
 

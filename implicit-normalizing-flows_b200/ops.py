@@ -484,15 +484,18 @@ def chain23_tc(A_split, W2s, W3s, N3, bias2=None, mul2=None, act_kind=ACT_NONE, 
     """Fused layers 2 + 3 (csrc/chain23_fused.cu): returns (partials (Q, M, N3) with Q = C/128, pre2 or None);
     the layer output is partials.sum(0) (summed in fixed order by the col2im kernel on the product path).
 
-    A_split = (hi, lo) tf32 planes of the (M, C) layer-2 input; W2s / W3s = planes of the (C, C) and (N3, C)
+    A_split = (hi, lo) tf32 planes of the (M, C) layer-2 input, or ONE fp32 tensor (the kernel then derives the planes
+    on chip: same roundings, same result); W2s / W3s = planes of the (C, C) and (N3, C)
     K-major weights; mul2 given: psi2(t) = t * mul2, else psi2(t) = act(t + bias2)."""
+    if torch.is_tensor(A_split):
+        A_split = (A_split, None)
     M, C = A_split[0].shape
     dev = A_split[0].device
     Q = int(_lib().impflow_chain23_parts(C))
     pre2 = torch.empty(M, C, device=dev, dtype=torch.float32) if save_pre else None
     out = torch.empty(Q, M, N3, device=dev, dtype=torch.float32)
     _cabi.check(_lib().impflow_chain23_tc(
-        _cabi.ptr(A_split[0]), _cabi.ptr(A_split[1]), C, _cabi.ptr(W2s[0]), _cabi.ptr(W2s[1]), _cabi.ptr(W3s[0]),
+        _cabi.ptr(A_split[0]), _cabi.ptr(A_split[1], 'A_lo', True), C, _cabi.ptr(W2s[0]), _cabi.ptr(W2s[1]), _cabi.ptr(W3s[0]),
         _cabi.ptr(W3s[1]), _cabi.ptr(bias2, 'bias2', True), _cabi.ptr(mul2, 'mul2', True), _cabi.ptr(pre2, 'pre2', True),
         _cabi.ptr(out), N3, M * N3, M, C, N3, act_kind, _cabi.ptr(beta2, 'beta2', True), _cabi.stream()), 'chain23_tc')
     if GEMM_PROFILE['on']:

@@ -290,6 +290,7 @@ int impflow_chain23_parts(int C);
  * the A1 chunks by TMA multicast; 0 (default: the lock-step of four SMs measured slower, 91 vs 123 TFLOP/s) =
  * independent CTAs.  Returns the previous setting. */
 int impflow_chain23_set_multicast(int on);
+/* A_lo = NULL: A_hi is the plain fp32 layer-2 input; the kernel splits every landed chunk into hi / lo on chip. */
 int impflow_chain23_tc(const float* A_hi, const float* A_lo, long long lda, const float* W2_hi, const float* W2_lo,
                        const float* W3_hi, const float* W3_lo, const float* bias2, const float* mul2, float* pre2_out,
                        float* out, long long ldo, long long part_stride, long long M, int C, int N3, int act_kind,
@@ -358,6 +359,11 @@ size_t impflow_conv3_broyden_host_bytes(int threshold);
 /* A/B switch: 1 (default) = layers 2 + 3 of the wider scales run as impflow_chain23_tc, 0 = two GEMM launches.
  * Returns the previous setting. */
 int impflow_conv3_set_chain23(int on);
+/* A/B switch: 1 = the layer-1 GEMM in front of impflow_chain23_tc writes ONE fp32 plane and the fused kernel
+ * derives the tf32 hi / lo planes in shared memory (A_lo = NULL), 0 (default: measured faster, the fused kernel is
+ * bound by the shared-memory port) = hi / lo planes through HBM.  Same roundings, bit-identical results.  Returns the
+ * previous setting. */
+int impflow_conv3_set_chain23_a32(int on);
 /* A/B switch: iterations enqueued ahead of the device's decision (0 = copy the state and synchronise the stream after
  * every iteration, the round-1 behaviour).  Returns the previous setting. */
 int impflow_conv3_set_runahead(int iterations);

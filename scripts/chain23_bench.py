@@ -29,8 +29,11 @@ def timeit(fn, reps=7):
     return sorted(ts)[len(ts) // 2]
 
 
+A32 = 'a32' in sys.argv[1:]          # layer-2 input as one fp32 plane, split on chip
 for M, C, N3 in [(16384, 512, 108), (4096, 512, 432)]:
-    A = ops.split_tf32(torch.randn(M, C, device=dev))
+    A = torch.randn(M, C, device=dev)
+    if not A32:
+        A = ops.split_tf32(A)
     W2 = ops.split_tf32(torch.randn(C, C, device=dev) / 22)
     W3 = ops.split_tf32(torch.randn(N3, C, device=dev) / 22)
     b2 = torch.randn(C, device=dev)

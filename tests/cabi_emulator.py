@@ -577,6 +577,9 @@ class EmulatedLib(object):
     def impflow_chain23_parts(self, C):
         return C // 128
 
+    def impflow_conv3_set_chain23_a32(self, on):
+        return 1
+
     def impflow_conv3_set_chain23(self, on):
         return 1
 
@@ -594,7 +597,8 @@ class EmulatedLib(object):
 
     def impflow_chain23_tc(self, A_hi, A_lo, lda, W2_hi, W2_lo, W3_hi, W3_lo, bias2, mul2, pre2_out, out, ldo,
                            part_stride, M, C, N3, act_kind, beta2, stream):
-        A = (_f32(A_hi, M * lda) + _f32(A_lo, M * lda)).reshape(M, lda)[:, :C]
+        A = _f32(A_hi, M * lda) + (_f32(A_lo, M * lda) if _addr(A_lo) is not None else 0)
+        A = A.reshape(M, lda)[:, :C]
         W2 = (_f32(W2_hi, C * C) + _f32(W2_lo, C * C)).reshape(C, C)
         W3 = (_f32(W3_hi, N3 * C) + _f32(W3_lo, N3 * C)).reshape(N3, C)
         H = (A @ W2.T).astype(np.float32)

@@ -273,6 +273,28 @@ def test_chain23_fused_layers(ops, M, C, N3, mode):
         assert rel_err(parts[q].cpu(), h @ W3.double()[:, q * 128:(q + 1) * 128].t()) < 1e-5
 
 
+@pytest.mark.parametrize('M,C,N3,mode', [(300, 512, 108, 'fwd'), (4096, 512, 432, 'vjp'), (128 * 149 + 7, 384, 130, 'fwd')])
+def test_chain23_single_plane_input(ops, M, C, N3, mode):
+    """Layer-2 input as ONE fp32 plane (A_lo = NULL: the kernel derives the tf32 hi / lo planes in shared memory)
+    gives bit-identical results to the route through hi / lo planes in HBM."""
+    g = torch.Generator().manual_seed(M + C + N3 + 1)
+    dev = _dev()
+    A = torch.randn(M, C, generator=g).to(dev)
+    W2 = ops.split_tf32((torch.randn(C, C, generator=g) / C ** 0.5).to(dev))
+    W3 = ops.split_tf32((torch.randn(N3, C, generator=g) / C ** 0.5).to(dev))
+    if mode == 'fwd':
+        kw = dict(bias2=(torch.randn(C, generator=g) * 0.1).to(dev), act_kind=ops.ACT_LIPSWISH,
+                  beta2=torch.tensor([1.3]).to(dev), save_pre=True)
+    else:
+        kw = dict(mul2=torch.randn(M, C, generator=g).to(dev))
+    for rep in range(3):          # several launches: the split ring's phases line up across items
+        pa, p2a = ops.chain23_tc(ops.split_tf32(A), W2, W3, N3, **kw)
+        pb, p2b = ops.chain23_tc(A, W2, W3, N3, **kw)
+        assert torch.equal(pa, pb)
+        if p2a is not None:
+            assert torch.equal(p2a, p2b)
+
+
 def test_activation_orders_vs_golden(ops, golden):
     fx = golden('activations')
     x = torch.from_numpy(fx['x']).cuda()
