@@ -57,6 +57,7 @@ SIGNATURES = {
     'impflow_branch3_tc': (_i, [_c_fp, _ll] + [_c_fp] * 13 + [_ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
     'impflow_chain23_parts': (_i, [_i]),
     'impflow_chain23_set_multicast': (_i, [_i]),
+    'impflow_broyden_set_chunk': (_i, [_i]),
     'impflow_chain23_tc': (_i, [_c_fp, _c_fp, _ll] + [_c_fp] * 8 + [_ll, _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
     'impflow_conv3_set_chain23': (_i, [_i]),
     'impflow_conv3_set_chain23_a32': (_i, [_i]),

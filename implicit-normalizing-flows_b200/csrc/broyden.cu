@@ -371,6 +371,227 @@ k_update(float* __restrict__ x_old, const float* __restrict__ g_old, const float
   cluster.sync();  // peers may still be reading part1 through DSMEM
 }
 
+// ------------------------------------------------------------------------------------------
+// rank-1 update, cluster per sample, history read from DRAM ONCE (d % 4 == 0).
+// The coefficient of history row j in phase 2 (a_j, b_j, c_j) depends on row j alone, so the history is
+// walked in chunks of G rows: dots of the chunk (first read: DRAM) -> cluster exchange -> accumulation of
+// the chunk into vT, w, S (second read: the rows a CTA touched a few microseconds ago, still in L2 as long
+// as `resident CTAs x 2 G SL 4` bytes fit).  k_update<4> does the same arithmetic with G = k; per-row
+// reduction order, order of the accumulation over j and the expressions are unchanged, so the results are
+// bit-identical.  The running sums live in registers (IT float4 groups per thread = SL / 1024).
+// ------------------------------------------------------------------------------------------
+template <int IT>
+__global__ void __launch_bounds__(kThreads)
+k_update_chunked(float* __restrict__ x_old, const float* __restrict__ g_old, const float* __restrict__ xn,
+                 const float* __restrict__ gn, float* __restrict__ Ut, float* __restrict__ Vt,
+                 float* __restrict__ low_x, float* __restrict__ low_g, const impflow_broyden_state* st, long long d,
+                 int T, int SL, int expect_nstep, int G) {
+  const int do_update = st->do_update;
+  const int new_low = st->new_lowest;
+  if (!do_update && !new_low) return;  // uniform over the whole grid
+  if (expect_nstep >= 0 && st->nstep != expect_nstep) return;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = cluster.num_blocks();
+  const int r = cluster.block_rank();
+  const int b = blockIdx.x / C;
+  const int k = st->nstep - 1;
+
+  extern __shared__ __align__(16) float smem[];
+  float* sdx = smem;
+  float* sdg = sdx + SL;
+  float* sgn = sdg + SL;
+  float* wsum = sgn + SL;                 // [3*T][kWarps]
+  float* part0 = wsum + 3 * T * kWarps;   // [3*T]
+  float* part1 = part0 + 3 * T;           // [2]
+  float* tot = part1 + 2;                 // [3*T + 2]
+
+  const long long base = (long long)b * d + (long long)r * SL;
+  long long rem = d - (long long)r * SL;
+  const int len = rem <= 0 ? 0 : (rem < SL ? (int)rem : SL);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- phase 0 ----
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid * 4 + it * kThreads * 4;
+    if (i < len) {
+      const float4 xo = *reinterpret_cast<const float4*>(x_old + base + i);
+      const float4 xv = *reinterpret_cast<const float4*>(xn + base + i);
+      const float4 go = *reinterpret_cast<const float4*>(g_old + base + i);
+      const float4 gv = *reinterpret_cast<const float4*>(gn + base + i);
+      *reinterpret_cast<float4*>(sdx + i) = make_float4(xv.x - xo.x, xv.y - xo.y, xv.z - xo.z, xv.w - xo.w);
+      *reinterpret_cast<float4*>(sdg + i) = make_float4(gv.x - go.x, gv.y - go.y, gv.z - go.z, gv.w - go.w);
+      *reinterpret_cast<float4*>(sgn + i) = gv;
+      if (new_low) {
+        *reinterpret_cast<float4*>(low_x + base + i) = xv;
+        *reinterpret_cast<float4*>(low_g + base + i) = gv;
+      }
+    }
+  }
+  if (!do_update) return;  // uniform
+  __syncthreads();
+
+  const float* Ub = Ut + (long long)b * T * d + (long long)r * SL;
+  const float* Vb = Vt + (long long)b * T * d + (long long)r * SL;
+
+  float vT[IT][4], w[IT][4], S[IT][4];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid * 4 + it * kThreads * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      vT[it][e] = (i < len) ? -sdx[i + e] : 0.f;
+      w[it][e] = (i < len) ? -sdg[i + e] : 0.f;
+      S[it][e] = 0.f;
+    }
+  }
+
+  for (int j0 = 0; j0 < k; j0 += G) {
+    const int j1 = (j0 + G < k) ? j0 + G : k;
+    // ---- phase 1 of the chunk: a_j = dx.U_j, b_j = V_j.dg, c_j = V_j.gn (:108,:119) ----
+    for (int j = j0; j < j1; ++j) {
+      const float* uj = Ub + (long long)j * d;
+      const float* vj = Vb + (long long)j * d;
+      float4 u4[IT], v4[IT];
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int i = tid * 4 + it * kThreads * 4;
+        if (i < len) {
+          u4[it] = __ldg(reinterpret_cast<const float4*>(uj + i));
+          v4[it] = __ldg(reinterpret_cast<const float4*>(vj + i));
+        }
+      }
+      float a = 0.f, bb = 0.f, c = 0.f;
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int i = tid * 4 + it * kThreads * 4;
+        if (i < len) {
+          const float4 dx = *reinterpret_cast<const float4*>(sdx + i);
+          const float4 dg = *reinterpret_cast<const float4*>(sdg + i);
+          const float4 gg = *reinterpret_cast<const float4*>(sgn + i);
+          a += dx.x * u4[it].x + dx.y * u4[it].y + dx.z * u4[it].z + dx.w * u4[it].w;
+          bb += v4[it].x * dg.x + v4[it].y * dg.y + v4[it].z * dg.z + v4[it].w * dg.w;
+          c += v4[it].x * gg.x + v4[it].y * gg.y + v4[it].z * gg.z + v4[it].w * gg.w;
+        }
+      }
+      a = warp_sum(a);
+      bb = warp_sum(bb);
+      c = warp_sum(c);
+      if (lane == 0) {
+        wsum[(3 * j + 0) * kWarps + warp] = a;
+        wsum[(3 * j + 1) * kWarps + warp] = bb;
+        wsum[(3 * j + 2) * kWarps + warp] = c;
+      }
+    }
+    __syncthreads();
+    for (int t = 3 * j0 + tid; t < 3 * j1; t += kThreads) {
+      float s = 0.f;
+      for (int q = 0; q < kWarps; ++q) s += wsum[t * kWarps + q];
+      part0[t] = s;
+    }
+    cluster.sync();      // slots 3*j0 .. 3*j1 are written once per launch: no second barrier per chunk
+    for (int t = 3 * j0 + tid; t < 3 * j1; t += kThreads) {
+      float s = 0.f;
+      for (int q = 0; q < C; ++q) s += cluster.map_shared_rank(part0, q)[t];
+      tot[t] = s;
+    }
+    __syncthreads();
+    // ---- phase 2 of the chunk: vT += a_j V_j, w += b_j U_j, S += c_j U_j (rows re-read from L2) ----
+    for (int j = j0; j < j1; ++j) {
+      const float* uj = Ub + (long long)j * d;
+      const float* vj = Vb + (long long)j * d;
+      const float aj = tot[3 * j + 0], bj = tot[3 * j + 1], cj = tot[3 * j + 2];
+      float4 u4[IT], v4[IT];
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int i = tid * 4 + it * kThreads * 4;
+        if (i < len) {
+          u4[it] = __ldg(reinterpret_cast<const float4*>(uj + i));
+          v4[it] = __ldg(reinterpret_cast<const float4*>(vj + i));
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int i = tid * 4 + it * kThreads * 4;
+        if (i < len) {
+          const float u1[4] = {u4[it].x, u4[it].y, u4[it].z, u4[it].w};
+          const float v1[4] = {v4[it].x, v4[it].y, v4[it].z, v4[it].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            vT[it][e] += aj * v1[e];
+            w[it][e] += bj * u1[e];
+            S[it][e] += cj * u1[e];
+          }
+        }
+      }
+    }
+  }
+
+  // ---- den = vT.dg, c_k = vT_scrubbed.gn; numerator of u and S into smem; store vT (:176-179) ----
+  float den = 0.f, ck = 0.f;
+  float* vk = Vt + (long long)b * T * d + (long long)k * d + (long long)r * SL;
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid * 4 + it * kThreads * 4;
+    if (i < len) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float dx = sdx[i + e], dg = sdg[i + e], gg = sgn[i + e];
+        den += vT[it][e] * dg;                                         // unscrubbed vT in the denominator (:176)
+        vT[it][e] = (vT[it][e] != vT[it][e]) ? 0.f : vT[it][e];        // :177
+        ck += vT[it][e] * gg;
+        sdx[i + e] = dx - w[it][e];                                    // numerator of u
+        sdg[i + e] = S[it][e];
+      }
+      *reinterpret_cast<float4*>(vk + i) = make_float4(vT[it][0], vT[it][1], vT[it][2], vT[it][3]);  // :179
+    }
+  }
+  den = warp_sum(den);
+  ck = warp_sum(ck);
+  if (lane == 0) {
+    wsum[warp] = den;
+    wsum[kWarps + warp] = ck;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float s = 0.f;
+    for (int q = 0; q < kWarps; ++q) s += wsum[tid * kWarps + q];
+    part1[tid] = s;
+  }
+  cluster.sync();
+  if (tid < 2) {
+    float s = 0.f;
+    for (int q = 0; q < C; ++q) s += cluster.map_shared_rank(part1, q)[tid];
+    tot[3 * T + tid] = s;
+  }
+  __syncthreads();
+  const float den_t = tot[3 * T + 0], ck_t = tot[3 * T + 1];
+
+  // ---- phase 3: u (scrub), next direction and next iterate (:176-181, :90) ----
+  float* uk = Ut + (long long)b * T * d + (long long)k * d + (long long)r * SL;
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid * 4 + it * kThreads * 4;
+    if (i < len) {
+      const float4 x4 = *reinterpret_cast<const float4*>(xn + base + i);
+      const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+      float u[4], xnext[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float q = sdx[i + e] / den_t;
+        q = (q != q) ? 0.f : q;                        // :178
+        u[e] = q;
+        const float upd = -((-sgn[i + e]) + (sdg[i + e] + q * ck_t));  // -matvec(U[:nstep], V[:nstep], gx) :181
+        xnext[e] = xv[e] + upd;
+      }
+      *reinterpret_cast<float4*>(uk + i) = make_float4(u[0], u[1], u[2], u[3]);   // :180
+      *reinterpret_cast<float4*>(x_old + base + i) = make_float4(xnext[0], xnext[1], xnext[2], xnext[3]);
+    }
+  }
+  cluster.sync();  // peers may still be reading part1 through DSMEM
+}
+
 // small-d variant: one warp per sample, d <= 128 (toy / tabular shapes).
 __global__ void __launch_bounds__(kThreads)
 k_update_small(float* __restrict__ x_old, const float* __restrict__ g_old, const float* __restrict__ xn,
@@ -457,6 +678,10 @@ k_update_small(float* __restrict__ x_old, const float* __restrict__ g_old, const
   }
 }
 
+// rows of history per chunk of k_update_chunked: -1 = automatic (L2 budget), 0 = always k_update<4> (re-reads the
+// history from DRAM when it exceeds L2), n > 0 = fixed
+static int g_update_chunk = -1;
+
 static int pick_splits(int B, long long d) {
   int S = 1;
   while ((long long)B * S < 592 && d / (S * 2) >= 2048 && S < 64) S *= 2;
@@ -477,6 +702,12 @@ static void pick_cluster(int B, long long d, int* C_out, int* SL_out) {
 }  // namespace impflow
 
 using namespace impflow;
+
+extern "C" int impflow_broyden_set_chunk(int rows) {
+  const int was = g_update_chunk;
+  g_update_chunk = rows;
+  return was;
+}
 
 extern "C" size_t impflow_broyden_state_bytes(void) { return sizeof(impflow_broyden_state); }
 
@@ -548,8 +779,30 @@ int impflow::broyden_step_ex(float* x_old, const float* g_old, const float* xn, 
   const size_t smem = sizeof(float) * ((size_t)3 * SL + (size_t)3 * threshold * kWarps + 3 * threshold + 2 +
                                        3 * threshold + 2 + 8);
   const bool vec = (d % 4 == 0);
-  auto kern = vec ? k_update<4> : k_update<1>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+  // Rows of history per chunk of the read-once kernel.  Whole history within the L2 budget: one chunk (the second pass
+  // of k_update<4> hits L2 anyway).  Otherwise as many rows as keep `resident CTAs x (U_j, V_j slices)` inside it.
+  int G = 0;
+  if (vec && g_update_chunk != 0) {
+    const double l2_budget = 40e6;
+    if (g_update_chunk > 0) {
+      G = g_update_chunk;
+    } else if ((double)B * threshold * d * 8.0 > l2_budget) {
+      const long long per_sm = SL > 4096 ? 1 : 2;       // k_update_chunked<8> holds its sums in 253 registers
+      const long long resident = (long long)B * C < 148 * per_sm ? (long long)B * C : 148 * per_sm;
+      G = (int)(l2_budget / ((double)resident * 8.0 * SL));
+      if (G < 1) G = 1;
+    }
+  }
+  void (*kern)(float*, const float*, const float*, const float*, float*, float*, float*, float*,
+               const impflow_broyden_state*, long long, int, int, int) = vec ? k_update<4> : k_update<1>;
+  void (*kern_c)(float*, const float*, const float*, const float*, float*, float*, float*, float*,
+                 const impflow_broyden_state*, long long, int, int, int, int) = nullptr;
+  if (G > 0) {
+    kern_c = SL <= 1024 ? k_update_chunked<1> : SL <= 2048 ? k_update_chunked<2> : SL <= 4096 ? k_update_chunked<4>
+                                                                                             : k_update_chunked<8>;
+  }
+  if ((kern_c ? cudaFuncSetAttribute(kern_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+              : cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
     set_error("broyden_step: cannot set %zu bytes of dynamic shared memory", smem);
     return -1;
   }
@@ -566,8 +819,10 @@ int impflow::broyden_step_ex(float* x_old, const float* g_old, const float* xn, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, x_old, g_old, xn, gn, Ut, Vt, low_x, low_g,
-                                     (const impflow_broyden_state*)state, d, threshold, SL, expect_nstep);
+  cudaError_t e = kern_c ? cudaLaunchKernelEx(&cfg, kern_c, x_old, g_old, xn, gn, Ut, Vt, low_x, low_g,
+                                              (const impflow_broyden_state*)state, d, threshold, SL, expect_nstep, G)
+                         : cudaLaunchKernelEx(&cfg, kern, x_old, g_old, xn, gn, Ut, Vt, low_x, low_g,
+                                              (const impflow_broyden_state*)state, d, threshold, SL, expect_nstep);
   if (e != cudaSuccess) {
     set_error("broyden_step: cluster launch failed: %s", cudaGetErrorString(e));
     return -1;

@@ -91,6 +91,12 @@ int impflow_broyden_step(float* x_old, const float* g_old, const float* xn, cons
                          float* partial, impflow_broyden_state* state, int B, long long d, int threshold,
                          void* stream);
 
+/* A/B switch of the rank-1 update kernel for d % 4 == 0: -1 (default) = walk the history in chunks of rows sized so
+ * that the second pass of a chunk hits L2 (history read from DRAM once: (6+2i) d 4 bytes per sample);
+ * 0 = one chunk (the whole history is read twice, from DRAM when it exceeds L2); n > 0 = n rows per chunk.  The
+ * results are bit-identical in every setting.  Returns the previous setting. */
+int impflow_broyden_set_chunk(int rows);
+
 /* Persistent small-d solver (toy / tabular MLP branches, d <= 128, widths <= 256): ONE cooperative
  * launch runs the whole solve of x_embed - f(z) - z = 0 — branch evaluations (fused fp32 MLP with the
  * activation `act_kind` between its L linear layers), batch-global norms, break rules, best iterate and

@@ -586,6 +586,9 @@ class EmulatedLib(object):
     def impflow_chain23_set_multicast(self, on):
         return 1
 
+    def impflow_broyden_set_chunk(self, rows):
+        return -1
+
     def impflow_wgrad_set_slice_major(self, on):
         return 1
 

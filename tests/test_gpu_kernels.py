@@ -565,6 +565,50 @@ def test_broyden_shapes_against_oracle(B, d):
     np.testing.assert_allclose(res['trace'][:-1], ref['trace'][:-1], rtol=2e-3)
 
 
+@pytest.mark.parametrize('B,d', [(3, 1028), (2, 5000), (4, 3072), (2, 16384), (2, 65536), (1, 40004)])
+def test_broyden_update_history_read_once(B, d):
+    """k_update_chunked (history walked in chunks of rows so that each row leaves DRAM once) against k_update<4>
+    (two passes over the whole history): same reduction orders, so iterates and history must be bit-identical for
+    every chunk size, ragged slices included."""
+    import ctypes
+    import impflow_b200
+    from impflow_b200.layers import broyden as bmod
+    cabi = impflow_b200._cabi
+    lib = cabi.load()
+    T, n_iter = 12, 9
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def run(chunk):
+        was = lib.impflow_broyden_set_chunk(chunk)
+        try:
+            gen = torch.Generator(device='cuda').manual_seed(d + B)
+            wk = bmod._Workspace(B, d, T, torch.device('cuda', torch.cuda.current_device()))
+            wk.Ut.zero_()
+            wk.Vt.zero_()
+            gs = [0.1 * torch.randn(B, d, device='cuda', generator=gen) for _ in range(n_iter + 1)]
+            wk.xa.copy_(torch.randn(B, d, device='cuda', generator=gen))
+            cabi.check(lib.impflow_broyden_begin(vp(wk.xa), vp(gs[0]), vp(wk.xb), vp(wk.low_x), vp(wk.low_g),
+                                                 vp(wk.sample_sq), vp(wk.low_sq), vp(wk.partial), vp(wk.state), B, d, T,
+                                                 1e-30, cabi.stream()), 'begin')
+            x_old, xn = wk.xa, wk.xb
+            for i in range(1, n_iter + 1):
+                cabi.check(lib.impflow_broyden_step(vp(x_old), vp(gs[i - 1]), vp(xn), vp(gs[i]), vp(wk.Ut), vp(wk.Vt),
+                                                    vp(wk.low_x), vp(wk.low_g), vp(wk.sample_sq), vp(wk.low_sq),
+                                                    vp(wk.partial), vp(wk.state), B, d, T, cabi.stream()), 'step')
+                x_old, xn = xn, x_old
+            torch.cuda.synchronize()
+            return [t.clone().view(torch.int32) for t in (xn, wk.Ut[:, :n_iter], wk.Vt[:, :n_iter], wk.low_x)]
+        finally:
+            lib.impflow_broyden_set_chunk(was)
+
+    ref = run(0)
+    assert bool(torch.isfinite(ref[0].view(torch.float32)).all())
+    for chunk in (1, 2, 3, 5, 100):
+        out = run(chunk)
+        for a, b in zip(ref, out):
+            assert torch.equal(a, b), chunk
+
+
 @pytest.mark.parametrize('B,d,hidden,nh,act', [(5000, 2, 128, 2, 'sin'), (1000, 6, 128, 4, 'sin'), (1000, 63, 128, 4, 'sin'),
                                               (37, 43, 64, 2, 'swish'), (1, 5, 16, 1, 'relu')])
 def test_persistent_mlp_solver(B, d, hidden, nh, act):
