@@ -393,26 +393,48 @@ def solver_roofline(pkg, B, d, T, n_iter, flush, hbm_gbs, peak_src):
                'broyden_begin')
     x_old, xn, g_old, gn = wk.xa, wk.xb, g[0], g[1]
     t_ms, bytes_alg = 0.0, 0.0
+    # a history larger than L2 (classifier shape: 2 GB) needs no flush: the iterations are enqueued back to back as the
+    # sync-free solver loop does, one event between them; the iterate / residual vectors were just written, as they
+    # are after a branch evaluation.  The bench shape (47 MB of history) is flushed between iterations.
+    streamed = 8.0 * B * T * d > 256e6
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_iter + 1)]
+    gs = [torch.randn(B, d, device=dev) for _ in range(n_iter)] if streamed else None
+    if streamed:
+        torch.cuda.synchronize()
+        torch.cuda._sleep(2000000)        # the device stays busy while the host enqueues
+        evs[0].record()
     for i in range(1, n_iter + 1):
-        gn.normal_()
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        if streamed:
+            gn = gs[i - 1]
+        else:
+            gn.normal_()
+            flush.zero_()
+            evs[i - 1].record()
         cabi.check(lib.impflow_broyden_step(vp(x_old), vp(g_old), vp(xn), vp(gn), vp(wk.Ut), vp(wk.Vt), vp(wk.low_x),
                                             vp(wk.low_g), vp(wk.sample_sq), vp(wk.low_sq), vp(wk.partial),
                                             vp(wk.state), B, d, T, cabi.stream()), 'broyden_step')
-        e1.record()
-        torch.cuda.synchronize()
-        t_ms += e0.elapsed_time(e1)
+        evs[i].record()
+        if not streamed:
+            torch.cuda.synchronize()
+            t_ms += evs[i - 1].elapsed_time(evs[i])
         bytes_alg += (6 + 2 * i) * d * 4.0 * B
-        x_old, xn, g_old, gn = xn, x_old, gn, g_old
+        if streamed:
+            x_old, xn, g_old = xn, x_old, gn
+        else:
+            x_old, xn, g_old, gn = xn, x_old, gn, g_old
+    if streamed:
+        torch.cuda.synchronize()
+        t_ms = evs[0].elapsed_time(evs[n_iter])
     ach = bytes_alg / (t_ms / 1e3) / 1e9
     return {'kernel': 'k_norm_decide + k_update (Broyden rank-1 update and break rules, csrc/broyden.cu)',
             'bound': 'hbm', 'achieved': ach, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': ach / hbm_gbs, 'traffic': None,
             'peak_source': peak_src, 'shape': {'B': B, 'd': d, 'iterations': n_iter},
             'us_per_iteration': t_ms * 1e3 / n_iter,
-            'note': 'algorithmic bytes (6+2i)*d*4 per sample for iteration i; the kernel re-reads the rank-(i-1) '
-                    'history once more than the minimum (see DESIGN.md section 4)'}
+            'l2': 'history %.0f MB > L2, iterations back to back, no flush' % (8.0 * B * T * d / 1e6) if streamed
+                  else '256 MB flush between iterations',
+            'note': 'algorithmic bytes (6+2i)*d*4 per sample for iteration i; the kernel reads the rank-(i-1) history '
+                    'twice (dots, then combinations); the read-once variants measured slower, see '
+                    'profiles/r02_update_bench.txt and DESIGN.md section 4'}
 
 
 def _host_init_lazy_buffers(sd, wl, x):

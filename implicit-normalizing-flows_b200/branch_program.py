@@ -63,7 +63,7 @@ MEMO = {'on': True}
 # conv branches with at most max_rows pixel rows (B=64: the deepest CIFAR scale; smaller per-GPU batches, i.e. strong
 # scaling: more of them), captured after `warmup` eager calls.  Measured (bench.py, e2e ms/step, B200): B=64 71.6 ->
 # 69.6 (max_rows 8192; 20000: 70.9), B=16 46.8 -> 38.0.
-SWEEP_GRAPHS = {'on': True, 'max_rows': 8192, 'warmup': 2}
+SWEEP_GRAPHS = {'on': True, 'max_rows': 16384, 'warmup': 2}
 
 _conv3_ws = {}      # (device index, stream) -> workspace tensor shared by every plan used on that stream
 

@@ -91,10 +91,13 @@ int impflow_broyden_step(float* x_old, const float* g_old, const float* xn, cons
                          float* partial, impflow_broyden_state* state, int B, long long d, int threshold,
                          void* stream);
 
-/* A/B switch of the rank-1 update kernel for d % 4 == 0: -1 (default) = walk the history in chunks of rows sized so
- * that the second pass of a chunk hits L2 (history read from DRAM once: (6+2i) d 4 bytes per sample);
- * 0 = one chunk (the whole history is read twice, from DRAM when it exceeds L2); n > 0 = n rows per chunk.  The
- * results are bit-identical in every setting.  Returns the previous setting. */
+/* A/B selection of the rank-1 update kernel (d % 4 == 0).  -1 or 0 (default) = two-pass cluster kernel (history read
+ * for the dots, then again for the combinations; 16 independent loads per thread in flight); -3 = the same with 512
+ * threads per CTA; -2 = history-streaming kernel: every history row crosses the SM boundary once ((6+2i) d 4 bytes per
+ * sample) — 1-D bulk copies into a shared-memory ring, per-row dots pushed into the peers' shared memory
+ * of a <= 16-CTA cluster (d >= 2048); n > 0 = two passes in chunks of n rows whose second pass hits L2 (bit-identical
+ * to the default).  Measured (B = 128, d = 65536): the default is the fastest; see csrc/broyden.cu.  Returns the
+ * previous setting. */
 int impflow_broyden_set_chunk(int rows);
 
 /* Persistent small-d solver (toy / tabular MLP branches, d <= 128, widths <= 256): ONE cooperative

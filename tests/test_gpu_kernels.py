@@ -607,6 +607,12 @@ def test_broyden_update_history_read_once(B, d):
         out = run(chunk)
         for a, b in zip(ref, out):
             assert torch.equal(a, b), chunk
+    # k_update_stream (history rows streamed once through a shared-memory ring by bulk copies, dots exchanged by
+    # pushes into the peers' shared memory): other slice lengths, hence agreement to round-off only
+    out = run(-2)
+    for a, b in zip(ref, out):
+        a, b = a.view(torch.float32), b.view(torch.float32)
+        assert float((a - b).abs().max()) <= 2e-4 * float(a.abs().max()), float((a - b).abs().max())
 
 
 @pytest.mark.parametrize('B,d,hidden,nh,act', [(5000, 2, 128, 2, 'sin'), (1000, 6, 128, 4, 'sin'), (1000, 63, 128, 4, 'sin'),
