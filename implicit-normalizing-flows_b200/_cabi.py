@@ -52,6 +52,8 @@ SIGNATURES = {
     'impflow_col2im3x3': (_i, [_c_fp, _i, _i, _i, _i, _c_fp, _c_fp, _c_fp, _c_fp, _i, _c_fp, _c_fp]),
     'impflow_gemm_nt': (_i, [_c_fp, _ll, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _ll, _ll, _i, _i, _i, _c_fp, _c_fp]),
     'impflow_gemm_strided': (_i, [_c_fp, _ll, _ll, _c_fp, _ll, _ll, _c_fp, _c_fp, _ll, _ll, _i, _i, _c_fp]),
+    'impflow_wgrad_simt_workspace_floats': (ctypes.c_size_t, [_ll, _i, _i]),
+    'impflow_wgrad_simt': (_i, [_c_fp, _ll, _c_fp, _ll, _c_fp, _ll, _ll, _i, _i, _c_fp, _c_fp]),
     'impflow_gemm_nt_tc': (_i, [_c_fp, _c_fp, _ll, _c_fp, _c_fp, _ll, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp,
                                 _ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),
     'impflow_branch3_tc': (_i, [_c_fp, _ll] + [_c_fp] * 13 + [_ll, _ll, _i, _i, _i, _c_fp, _c_fp, _c_fp]),

@@ -63,7 +63,10 @@ MEMO = {'on': True}
 # conv branches with at most max_rows pixel rows (B=64: the deepest CIFAR scale; smaller per-GPU batches, i.e. strong
 # scaling: more of them), captured after `warmup` eager calls.  Measured (bench.py, e2e ms/step, B200): B=64 71.6 ->
 # 69.6 (max_rows 8192; 20000: 70.9), B=16 46.8 -> 38.0.
-SWEEP_GRAPHS = {'on': True, 'max_rows': 16384, 'warmup': 2}
+# 'mlp': graphs of the MLP flows' batched sweeps, one per distinct n-fold row count (opt-in: a tabular step drops from
+# 259 to ~195 ms once every (program, n) pair has been captured, but each capture costs ~28 ms and a 20-block flow
+# needs ~200 of them, which only pays off over a training run, not over a 20-step benchmark)
+SWEEP_GRAPHS = {'on': True, 'max_rows': 16384, 'warmup': 2, 'mlp': False}
 
 _conv3_ws = {}      # (device index, stream) -> workspace tensor shared by every plan used on that stream
 
@@ -183,6 +186,8 @@ class BranchProgram(object):
         self._saved = None
         self._D_static = None           # d sigma / d W twins while a sweep graph is captured (see _graphed)
         self._sweep_graphs = {}
+        self._sweep_eager = {}      # MLP programs: eager calls per sweep kind before the first capture
+        self._sweep_pool = None
 
     # ---------------------------------------------------------------- weights
     def _acts(self):
@@ -838,9 +843,13 @@ class BranchProgram(object):
     # softplus(beta), sigma and d sigma / d W), and every later call is: one multi-tensor copy into the static
     # inputs, one graph launch, one multi-tensor copy of the results out of the graph's private pool.
     def _graphable(self, saved, like):
-        # conv branches only: the row count of an MLP flow's batched sweep changes with the roulette draw of every
-        # step (n-fold batch), which would mean a new capture (device sync + allocator reset) per distinct n
-        return (SWEEP_GRAPHS['on'] and like.is_cuda and not self.is_linear and saved.M <= SWEEP_GRAPHS['max_rows']
+        # MLP flows: the row count of the batched sweep follows the roulette draw of every step (n-fold batch), so a
+        # program collects one graph per distinct n (a handful: n = exact terms + a geometric draw); they share one
+        # private memory pool per program (never replayed concurrently) and are captured at their first occurrence
+        # once the program has run eagerly SWEEP_GRAPHS['warmup'] times
+        if self.is_linear and not SWEEP_GRAPHS['mlp']:
+            return False
+        return (SWEEP_GRAPHS['on'] and like.is_cuda and saved.M <= SWEEP_GRAPHS['max_rows']
                 and not torch.cuda.is_current_stream_capturing())
 
     def _dynamic_inputs(self, saved, vecs):
@@ -862,13 +871,18 @@ class BranchProgram(object):
                ops.get_gemm_backend(), dyn[0].device.index)
         G = self._sweep_graphs.get(key)
         if G is None:
-            if len(self._sweep_graphs) > 8:
+            if len(self._sweep_graphs) > (32 if self.is_linear else 8):
                 self._sweep_graphs.clear()
+                self._sweep_pool = None
             G = self._sweep_graphs[key] = {'calls': 0, 'graph': None}
         eager = self._backward_full_eager if kind == 'backward_full' else self._neumann_eager
         if G['graph'] is None:
             G['calls'] += 1
-            if G['calls'] <= SWEEP_GRAPHS['warmup']:
+            # conv programs: warm-up per key; MLP programs: per program and kind (every n-fold batch size is a new
+            # key, but the lazy set-up the warm-up calls are there for does not depend on the row count)
+            warm = self._sweep_eager.get(kind, 0) if self.is_linear else G['calls'] - 1
+            if warm < SWEEP_GRAPHS['warmup']:
+                self._sweep_eager[kind] = self._sweep_eager.get(kind, 0) + 1
                 out = eager(saved, *vecs, *flags)
                 return self._flatten_sweep(kind, out, flags)
             self._capture_sweep(G, kind, eager, saved, vecs, flags, dyn, ws)
@@ -929,8 +943,16 @@ class BranchProgram(object):
             if side is None or side.device != cur.device:
                 side = SWEEP_GRAPHS['stream'] = torch.cuda.Stream(device=cur.device)
             side.wait_stream(cur)
+            pool = None
+            if self.is_linear:        # one pool for all graphs of this program (sequential replays only)
+                if getattr(self, '_sweep_pool', None) is None:
+                    self._sweep_pool = torch.cuda.graph_pool_handle()
+                pool = self._sweep_pool
             with torch.cuda.stream(side):
-                graph.capture_begin()
+                if pool is not None:
+                    graph.capture_begin(pool=pool)
+                else:
+                    graph.capture_begin()
                 try:
                     out = eager(saved_s, *[T(v) for v in vecs], *flags)
                 finally:

@@ -164,6 +164,97 @@ k_gemm_strided(const float* __restrict__ A, long long sAm, long long sAk, const 
   }
 }
 
+// Weight-gradient contraction of the small / ragged shapes (MLP flows: N1, N2 <= 128, rows = n x batch, any count):
+//     dW[N1,N2] = G[M,N1]^T A[M,N2]
+// straight from the row-major operands (no transposed copies) and SPLIT ALONG THE ROWS: one 64x64 output tile would
+// otherwise walk all M rows on a single SM (93 us per launch at M = 6000; 858 launches = half of the GPU time of a
+// tabular step).  grid = (column tiles, row tiles, splits); the partials are summed in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+k_wgrad_simt(const float* __restrict__ G, long long ldg, const float* __restrict__ A, long long lda,
+             float* __restrict__ ws, long long M, int N1, int N2, long long rows_per_split) {
+  constexpr int BM = 64, BN = 64, TM = 4, TN = 4;
+  __shared__ float Gs[BK][BM + 4];
+  __shared__ float As[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int n1_0 = blockIdx.y * BM, n2_0 = blockIdx.x * BN;
+  const long long m_begin = (long long)blockIdx.z * rows_per_split;
+  const long long m_end = m_begin + rows_per_split < M ? m_begin + rows_per_split : M;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  for (long long m0 = m_begin; m0 < m_end; m0 += BK) {
+#pragma unroll
+    for (int e = tid; e < BM * BK; e += 256) {       // consecutive threads follow the channel (contiguous) dimension
+      const int r = e % BM, kk = e / BM;
+      const long long gm = m0 + kk;
+      Gs[kk][r] = (gm < m_end && n1_0 + r < N1) ? G[gm * ldg + n1_0 + r] : 0.f;
+      As[kk][r] = (gm < m_end && n2_0 + r < N2) ? A[gm * lda + n2_0 + r] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 ta = *reinterpret_cast<const float4*>(&Gs[kk][ty * 4]);
+      const float4 tb = *reinterpret_cast<const float4*>(&As[kk][tx * 4]);
+      const float a[4] = {ta.x, ta.y, ta.z, ta.w};
+      const float b[4] = {tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* dst = ws + (long long)blockIdx.z * N1 * N2;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int n1 = n1_0 + ty * 4 + i;
+    if (n1 >= N1) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n2 = n2_0 + tx * 4 + j;
+      if (n2 < N2) dst[(long long)n1 * N2 + n2] = acc[i][j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_wgrad_simt_reduce(const float* __restrict__ ws, float* __restrict__ out, long long total, int splits, long long ldo,
+                    int N2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + i];     // fixed order
+    out[(i / N2) * ldo + (i % N2)] = acc;
+  }
+}
+
+int wgrad_simt_splits(long long M, int N1, int N2) {
+  const long long tiles = (long long)((N1 + 63) / 64) * ((N2 + 63) / 64);
+  long long s = (444 + tiles - 1) / tiles;           // about three CTAs per SM
+  const long long max_s = (M + 63) / 64;             // at least 64 rows per split
+  if (s > max_s) s = max_s;
+  if (s > 256) s = 256;
+  return s < 1 ? 1 : (int)s;
+}
+
+int wgrad_simt(const float* G, long long ldg, const float* A, long long lda, float* out, long long ldo, long long M,
+               int N1, int N2, float* ws, cudaStream_t s) {
+  const int splits = wgrad_simt_splits(M, N1, N2);
+  long long rows = (M + splits - 1) / splits;
+  rows = (rows + BK - 1) / BK * BK;
+  dim3 grid((unsigned)((N2 + 63) / 64), (unsigned)((N1 + 63) / 64), (unsigned)splits);
+  k_wgrad_simt<<<grid, 256, 0, s>>>(G, ldg, A, lda, ws, M, N1, N2, rows);
+  if (check_launch("k_wgrad_simt")) return -1;
+  const long long total = (long long)N1 * N2;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  k_wgrad_simt_reduce<<<(int)blocks, 256, 0, s>>>(ws, out, total, splits, ldo, N2);
+  return check_launch("k_wgrad_simt_reduce");
+}
+
 int gemm_strided_simt(const float* A, long long sAm, long long sAk, const float* Bm, long long sBn, long long sBk,
                       const float* bias, float* out, long long ldc, long long M, int N, int K, cudaStream_t s) {
   const long long col_tiles = (N + 63) / 64;
@@ -197,3 +288,17 @@ int gemm_nt_simt(const float* A, long long lda, const float* Bm, long long ldb, 
 }
 
 }  // namespace impflow
+
+using namespace impflow;
+
+extern "C" size_t impflow_wgrad_simt_workspace_floats(long long M, int N1, int N2) {
+  return (size_t)wgrad_simt_splits(M, N1, N2) * (size_t)N1 * (size_t)N2;
+}
+
+extern "C" int impflow_wgrad_simt(const float* G, long long ldg, const float* A, long long lda, float* out,
+                                  long long ldo, long long M, int N1, int N2, float* ws, void* stream) {
+  IMPFLOW_REQUIRE(M >= 1 && N1 >= 1 && N2 >= 1, "wgrad_simt: empty problem M=%lld N1=%d N2=%d", M, N1, N2);
+  IMPFLOW_REQUIRE(ldg >= N1 && lda >= N2 && ldo >= N2, "wgrad_simt: row strides too small");
+  IMPFLOW_REQUIRE(out != nullptr && ws != nullptr, "wgrad_simt: output or workspace missing");
+  return wgrad_simt(G, ldg, A, lda, out, ldo, M, N1, N2, ws, (cudaStream_t)stream);
+}

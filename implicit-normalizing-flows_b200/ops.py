@@ -361,7 +361,14 @@ def wgrad_gemm(G, A, G_split=None, A_split=None):
         A = lincomb3(A_split[0], 1.0, A_split[1], 1.0)
     if _tc_ok(N1, N2, M, M, M):
         return gemm_nt(None, None, A_split=transpose_split(G), B_split=transpose_split(A))[0]
-    return gemm_nt(transpose2d(G), transpose2d(A))[0]
+    # small / ragged shapes (MLP flows): exact fp32, split along the rows, no transposed copies
+    lib = _lib()
+    G, A = G.contiguous(), A.contiguous()
+    out = torch.empty(N1, N2, device=dev, dtype=torch.float32)
+    ws = torch.empty(max(int(lib.impflow_wgrad_simt_workspace_floats(M, N1, N2)), 1), device=dev, dtype=torch.float32)
+    _cabi.check(lib.impflow_wgrad_simt(_cabi.ptr(G), G.stride(0), _cabi.ptr(A), A.stride(0), _cabi.ptr(out), N2, M,
+                                       N1, N2, _cabi.ptr(ws), _cabi.stream()), 'wgrad_simt')
+    return out
 
 
 def col2im3x3(col, B, H, W, C, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, want_act=False,

@@ -227,6 +227,12 @@ int impflow_gemm_nt(const float* A, long long lda, const float* Bm, long long ld
  * the autograd primitives of the small shapes use it for A B, A^T B, A B^T, A^T B^T without transposed copies. */
 int impflow_gemm_strided(const float* A, long long sAm, long long sAk, const float* Bm, long long sBn, long long sBk,
                          const float* bias, float* out, long long ldc, long long M, int N, int K, void* stream);
+/* Exact-fp32 weight-gradient contraction dW[N1,N2] = G[M,N1]^T A[M,N2] straight from the row-major operands, split
+ * along the M rows over the SMs with a fixed-order reduce (small / ragged shapes: the MLP flows' 128-wide layers over
+ * n x batch rows, where impflow_wgrad_tc does not apply).  ws: impflow_wgrad_simt_workspace_floats(M, N1, N2) floats. */
+size_t impflow_wgrad_simt_workspace_floats(long long M, int N1, int N2);
+int impflow_wgrad_simt(const float* G, long long ldg, const float* A, long long lda, float* out, long long ldo,
+                       long long M, int N1, int N2, float* ws, void* stream);
 int impflow_gemm_nt_tc(const float* A_hi, const float* A_lo, long long lda, const float* B_hi,
                        const float* B_lo, long long ldb, const float* bias, float* pre_out, float* act_out,
                        const float* dmul_pre, float* split_hi, float* split_lo, long long ldc, long long M,

@@ -498,6 +498,16 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_wgrad_simt_workspace_floats(self, M, N1, N2):
+        return N1 * N2
+
+    def impflow_wgrad_simt(self, G, ldg, A, lda, out, ldo, M, N1, N2, ws, stream):
+        g = _f32(G, M * ldg).reshape(M, ldg)[:, :N1]
+        a = _f32(A, M * lda).reshape(M, lda)[:, :N2]
+        _f32(out, N1 * ldo).reshape(N1, ldo)[:, :N2] = (g.T.astype(np.float64) @ a.astype(np.float64)).astype(np.float32)
+        self.launches += 2
+        return 0
+
     def impflow_gemm_nt_tc(self, A_hi, A_lo, lda, B_hi, B_lo, ldb, bias, pre_out, act_out, dmul_pre, split_hi,
                            split_lo, ldc, M, N, K, act_kind, beta_sp, splitk_ws, stream):
         if K % 32 or lda % 4 or ldb % 4:

@@ -800,6 +800,55 @@ def case_sweep_graphs_match_eager():
         assert len(graphs) == 2, 'both sweeps must have been captured and replayed'
 
 
+def case_sweep_graphs_mlp_match_eager():
+    """The same for an MLP branch (tabular flows): the batched two-adjoint sweep runs over an n-fold batch whose n
+    follows the roulette draw, so the program collects one graph per row count, all in one private pool; every graph
+    must reproduce the eager sweep while weights and inputs move, in any order of the row counts."""
+    pkg = _pkg()
+    from impflow_b200 import branch_program as bp
+    from impflow_b200.branch_program import compile_branch
+    L = pkg.layers
+    dev = DEV['device']
+    if dev == 'cpu':
+        pytest.skip('CUDA graphs need the GPU')
+    torch.manual_seed(23)
+    d, B = 6, 50
+    dims = [d, 64, 64, d]
+    mods = []
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        if i > 0:
+            mods.append(L.base.Swish())
+        mods.append(L.base.get_linear(a, b, coeff=0.9, n_iterations=None, atol=1e-3, rtol=1e-3, domain=2, codomain=2))
+    net = torch.nn.Sequential(*mods).to(dev)
+    prog = compile_branch(net)
+    for step, n in enumerate([3, 3, 4, 3, 5, 4, 3, 5, 4, 3]):
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+            torch.autograd.graph.increment_version(list(net.parameters()))
+            L.base.update_lipschitz(net)
+            x = torch.randn(B, d, device=dev)
+            w, v = torch.randn(n * B, d, device=dev), torch.randn(n * B, d, device=dev)
+            seed = torch.rand(n * B, device=dev) + 0.5
+            got, want = [], []
+            for on, sink in ((True, got), (False, want)):
+                bp.SWEEP_GRAPHS['on'], bp.SWEEP_GRAPHS['mlp'] = on, True
+                try:
+                    _, saved = prog.forward_saved(x)
+                    saved_n = prog.tile_saved(saved, n)
+                    S, gx, gp = prog.neumann(saved_n, w, v, seed_scale=seed)
+                    gx2, gp2 = prog.backward_full(saved, w[:B].contiguous())
+                    sink.extend([S, gx, gx2] + [g for g in gp if g is not None] + [g for g in gp2 if g is not None])
+                finally:
+                    bp.SWEEP_GRAPHS['on'], bp.SWEEP_GRAPHS['mlp'] = True, False
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                scale = max(float(b.abs().max()), 1e-30)
+                assert float((a - b).abs().max()) / scale < 1e-5, (step, n)
+    graphs = [g for g in prog._sweep_graphs.values() if g['graph'] is not None]
+    assert len(graphs) == 4, 'three row counts of the batched sweep + the first-order backward: %d' % len(graphs)
+
+
 def case_direct_grad_sink_matches_autograd(golden):
     """FlatGradBucket(direct=True): the graph-free backward sweeps add their finished parameter gradients straight
     into the bucket (parallel.sink_grads) instead of returning them to autograd; the flat gradient after one step of

@@ -74,6 +74,10 @@ def test_sweep_graphs_match_eager():
     cases.case_sweep_graphs_match_eager()
 
 
+def test_sweep_graphs_mlp_match_eager():
+    cases.case_sweep_graphs_mlp_match_eager()
+
+
 @pytest.mark.parametrize('tag', list(cases.IRES))
 def test_iresblock(golden, tag):
     cases.case_iresblock(golden, tag)

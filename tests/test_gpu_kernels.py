@@ -363,6 +363,25 @@ def test_wgrad_mn_major(ops, M, N1, N2):
     assert rel_err(out.cpu(), old.cpu()) < 1e-5
 
 
+@pytest.mark.parametrize('M,N1,N2', [(1000, 128, 128), (3000, 128, 6), (5000, 6, 128), (37, 5, 3), (6000, 63, 128),
+                                     (1, 2, 2), (4001, 130, 70)])
+def test_wgrad_simt_ragged_rows(ops, M, N1, N2):
+    """dW = G^T A of the small / ragged shapes (MLP flows: rows = n x batch, not a multiple of 32): exact-fp32 CUDA-core
+    kernel split along the rows (csrc/gemm_simt.cu k_wgrad_simt) against fp64; planes as inputs; strided views."""
+    g = torch.Generator().manual_seed(M + N1 + N2)
+    G = torch.randn(M, N1, generator=g).cuda()
+    A = torch.randn(M, N2, generator=g).cuda()
+    ref = G.double().t() @ A.double()
+    out = ops.wgrad_gemm(G, A)
+    assert out.shape == (N1, N2)
+    assert rel_err(out.cpu(), ref.cpu()) < 2e-6
+    out2 = ops.wgrad_gemm(G, A)
+    assert torch.equal(out, out2)                     # fixed-order reduction: deterministic
+    if N1 % 4 == 0 and N2 % 4 == 0:
+        out3 = ops.wgrad_gemm(None, None, G_split=ops.split_tf32(G), A_split=ops.split_tf32(A))
+        assert rel_err(out3.cpu(), ref.cpu()) < 2e-6
+
+
 @pytest.mark.parametrize('M,N,with_ab', [(4096, 512, True), (1000, 256, True), (65536, 512, False), (77, 64, True)])
 def test_neumann_act_bwd_fused(ops, M, N, with_ab):
     """One-pass activation step of the Neumann reverse sweep against the separate kernels / fp64."""
