@@ -657,9 +657,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    trace = os.environ.get('IMPFLOW_TRACE_CAPTURE', '') == '1'
+    for i_ in range(args.warmup):
+        if trace:
+            torch.cuda.synchronize()
+            sys.stderr.write('[warm-up step %d] t=%.3f\n' % (i_, time.perf_counter()))
         step(x_dev, y_dev)
     sync_all()
+    if trace:
+        sys.stderr.write('[timed region] t=%.3f\n' % time.perf_counter())
     if os.environ.get('IMPFLOW_BENCH_GC', '') == 'freeze':      # diagnostic: cost of Python's cyclic GC in the loop
         import gc
         gc.collect()

@@ -32,6 +32,7 @@ autograd's double backward:
     tbar_p = phi'(p) tbar_a            pbar = phi''(p) t_p tbar_a + phi'(p) abar
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -519,6 +520,13 @@ class BranchProgram(object):
         return (_cabi.ptr(saved.pres[0], 'pre0', True), _cabi.ptr(self._deriv(saved, 1)),
                 _cabi.ptr(self._deriv(saved, 2)))
 
+    def prepare_vjp(self, saved):
+        """Evaluate what vjp(., saved) needs beyond the vector (the act' multipliers of a native plan) now, so that a
+        later vjp call is a single launch sequence with no set-up in front of it."""
+        P = self._conv3(self._prep(saved.M), saved.meta)
+        if P is not None:
+            self._vjp_operands(saved, P)
+
     def _native_vjp(self, P, v, saved):
         t, _ = self._to_rows(v)
         out = torch.empty_like(t)
@@ -640,8 +648,13 @@ class BranchProgram(object):
     # ---------------------------------------------------------------- forward
     def forward_saved(self, x, save=True):
         """(nnet(x), saved) without a graph; saved feeds vjp / backward_full / neumann."""
-        rows, meta = self._to_rows(x)
-        M = rows.shape[0]
+        if not self.is_linear and x.dim() == 4:
+            # shape bookkeeping first: a memo hit must not pay for the NCHW -> rows copy of _to_rows
+            meta = ('conv', (x.shape[0], x.shape[2], x.shape[3]))
+            M, rows = x.shape[0] * x.shape[2] * x.shape[3], None
+        else:
+            rows, meta = self._to_rows(x)
+            M = rows.shape[0]
         ws = self._prep(M, meta)
         memo_key = None
         if save and MEMO['on']:
@@ -651,6 +664,8 @@ class BranchProgram(object):
             m = getattr(self, '_memo', None)
             if m is not None and m[0] == memo_key:
                 return m[2], m[3]
+        if rows is None:
+            rows, meta = self._to_rows(x)
         out = self._forward_saved_impl(rows, meta, M, ws, save)
         if memo_key is not None:
             self._memo = (memo_key, x, out[0], out[1])
@@ -908,6 +923,10 @@ class BranchProgram(object):
         return [out[0], out[1]] + list(out[2])
 
     def _capture_sweep(self, G, kind, eager, saved, vecs, flags, dyn, ws):
+        if os.environ.get('IMPFLOW_TRACE_CAPTURE', '') == '1':       # diagnostic: when do captures happen
+            import sys
+            import time
+            sys.stderr.write('[capture] t=%.3f %s rows=%d flags=%s\n' % (time.perf_counter(), kind, saved.M, flags))
         static_in = [t.clone() for t in dyn]
         twin = {id(t): s_ for t, s_ in zip(dyn, static_in)}
         T = lambda t: None if t is None else twin[id(t)]

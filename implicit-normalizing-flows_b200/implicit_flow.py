@@ -46,14 +46,14 @@ class ImplicitFlow(nn.Module):
         self.n_classes = n_classes
         if not self.n_scale > 0:
             raise ValueError('Could not compute number of scales for input of size (%d,%d,%d,%d)' % input_size)
-        if quadratic or batchnorm or learn_p or dropout:
-            raise NotImplementedError('impflow_b200: quadratic / batchnorm / learn_p / dropout are outside the '
+        if quadratic or batchnorm or dropout:
+            raise NotImplementedError('impflow_b200: quadratic / batchnorm / dropout are outside the '
                                       'hot-path scope (dead or unused in the reference configs)')
         shared = dict(idim=intermediate_dim, actnorm=actnorm, fc_actnorm=fc_actnorm, fc=fc, coeff=coeff, vnorms=vnorms,
                       n_lipschitz_iters=n_lipschitz_iters, sn_atol=sn_atol, sn_rtol=sn_rtol,
                       n_power_series=n_power_series, n_dist=n_dist, n_samples=n_samples, kernels=kernels,
                       activation_fn=activation_fn, fc_end=fc_end, fc_idim=fc_idim, n_exact_terms=n_exact_terms,
-                      preact=preact, neumann_grad=neumann_grad, grad_in_forward=grad_in_forward)
+                      preact=preact, neumann_grad=neumann_grad, grad_in_forward=grad_in_forward, learn_p=learn_p)
         _, c, h, w = input_size
         transforms = []
         for i in range(self.n_scale):
@@ -157,7 +157,7 @@ class StackedImplicitBlocks(layers.SequentialFlow):
                  fc_actnorm=False, fc=False, coeff=0.9, vnorms='122f', n_lipschitz_iters=None, sn_atol=None,
                  sn_rtol=None, n_power_series=5, n_dist='geometric', n_samples=1, kernels='3-1-3',
                  activation_fn='elu', fc_end=True, fc_nblocks=None, fc_idim=128, n_exact_terms=0, preact=False,
-                 neumann_grad=True, grad_in_forward=False, first_resblock=True):
+                 neumann_grad=True, grad_in_forward=False, first_resblock=True, learn_p=False):
         if fc_nblocks is None:
             fc_nblocks = 2 if self._implicit else 4       # implicit_flow.py:280, resflow.py:281
         domains, codomains = _parse_vnorms(vnorms)
@@ -175,21 +175,25 @@ class StackedImplicitBlocks(layers.SequentialFlow):
         def conv_branch(leading_act):
             # [act] conv(c->idim) act conv(idim->idim)... act conv(idim->c)   (implicit_flow.py:359-398)
             chans = [initial_size[0]] + [idim] * (len(ks) - 1) + [initial_size[0]]
+            doms, cods = domains, codomains
+            if learn_p:       # learnable orders, one per layer boundary, shared by neighbours (implicit_flow.py:364-366)
+                doms = [nn.Parameter(torch.tensor(0.)) for _ in range(len(ks))]
+                cods = doms[1:] + [doms[0]]
             mods = []
             if leading_act:
                 mods.append(ACT_FNS[activation_fn](False))
             for i, k in enumerate(ks):
                 if i > 0:
                     mods.append(ACT_FNS[activation_fn](True))
-                mods.append(base_layers.get_conv2d(chans[i], chans[i + 1], k, 1, k // 2, domain=domains[i],
-                                                   codomain=codomains[i], **lip_kw))
+                mods.append(base_layers.get_conv2d(chans[i], chans[i + 1], k, 1, k // 2, domain=doms[i],
+                                                   codomain=cods[i], **lip_kw))
             return nn.Sequential(*mods)
 
         def fc_net(width):
             return FCNet(input_shape=initial_size, idim=width, lipschitz_layer=base_layers.get_linear,
                          nhidden=len(ks) - 1, coeff=coeff, domains=domains, codomains=codomains,
                          n_iterations=n_lipschitz_iters, activation_fn=activation_fn, preact=preact, dropout=0,
-                         sn_atol=sn_atol, sn_rtol=sn_rtol, learn_p=False)
+                         sn_atol=sn_atol, sn_rtol=sn_rtol, learn_p=learn_p)
 
         def _resblock(as_fc, width=idim, first=True):
             lead = (not first) and preact
@@ -229,8 +233,11 @@ class FCNet(nn.Module):
     def __init__(self, input_shape, idim, lipschitz_layer, nhidden, coeff, domains, codomains, n_iterations,
                  activation_fn, preact, dropout, sn_atol, sn_rtol, learn_p, div_in=1):
         super(FCNet, self).__init__()
-        if learn_p or dropout:
-            raise NotImplementedError('impflow_b200: learn_p / dropout are outside the hot-path scope')
+        if dropout:
+            raise NotImplementedError('impflow_b200: dropout is outside the hot-path scope')
+        if learn_p:           # implicit_flow.py:450-452
+            domains = [nn.Parameter(torch.tensor(0.)) for _ in range(len(domains))]
+            codomains = domains[1:] + [domains[0]]
         self.input_shape = input_shape
         c, h, w = self.input_shape
         dim = c * h * w

@@ -1,10 +1,14 @@
-"""Induced-2-norm constrained Linear / Conv2d — API and state-dict mirror of
+"""Induced-norm constrained Linear / Conv2d — API and state-dict mirror of
 lib/layers/base/mixed_lipschitz.py (InducedNormLinear :12-146, InducedNormConv2d :149-403).
 
-Only domain = codomain = 2 (every shipped config) is implemented; other
-norms raise.  Forward math runs on the impflow CUDA kernels (GEMM / im2col / power iteration);
-there is no CPU execution path except the constructor-time power iteration that the reference
-also performs on the host before the model is moved to the GPU."""
+domain = codomain = 2 (every shipped config) runs on the power-iteration kernels
+(csrc/spectral*.cu).  Other induced p -> q norms and learnable orders (`learn_p`) take the
+general iteration below: the same W v / W^T u products on the impflow GEMM / conv kernels, the dual-norm
+normalisations of mixed_lipschitz.py:414-444 on the (small) vectors between them, the reference's random restarts
+at initialisation.  The soft rescale W / max(1, sigma/coeff) with sigma = u^T W v does not depend on the norm, so
+everything above the layer (branch programs, weight gradients) is unchanged.  There is no CPU execution path except
+the constructor-time power iteration that the reference also performs on the host before the model is moved to the
+GPU."""
 import math
 
 import torch
@@ -14,15 +18,76 @@ import torch.nn.init as init
 
 from ... import _cabi, ops
 
-__all__ = ['InducedNormLinear', 'InducedNormConv2d', 'update_lipschitz', 'sigma_of']
+__all__ = ['InducedNormLinear', 'InducedNormConv2d', 'update_lipschitz', 'sigma_of', 'normalize_u', 'normalize_v',
+           'projmax_', 'vector_norm', 'asym_squash', 'leaky_elu']
 
 
-def _check_norms(domain, codomain):
-    if torch.is_tensor(domain) or torch.is_tensor(codomain):
-        raise NotImplementedError('impflow_b200: learnable induced-norm orders (learn_p) are out of scope')
-    if not (domain == 2 and codomain == 2):
-        raise NotImplementedError('impflow_b200: only domain=codomain=2 is implemented, got %r -> %r'
-                                  % (domain, codomain))
+def _is_two(p):
+    """The reference's test `not torch.is_tensor(p) and p == 2` (a learnable order is never "2")."""
+    return (not torch.is_tensor(p)) and p == 2
+
+
+def _plain_l2(domain, codomain):
+    return _is_two(domain) and _is_two(codomain)
+
+
+# ---- dual-norm normalisations of the general power iteration (mixed_lipschitz.py:406-444; the algorithm of
+# http://www.qetlab.com/InducedMatrixNorm that the reference cites) --------------------------------------------------
+
+def vector_norm(x, p):
+    x = x.reshape(-1)
+    return torch.sum(x ** p) ** (1 / p)
+
+
+def projmax_(v):
+    """In place: the unit vector at the entry of largest magnitude."""
+    ind = torch.argmax(torch.abs(v))
+    v.zero_()
+    v[ind] = 1
+    return v
+
+
+def _dual_direction(x, power, norm_p):
+    """sign(x) * m / ||m||_{norm_p} with m = (|x| / max|x|)^power, sign(0) = 1."""
+    mag = torch.abs(x)
+    sgn = x / mag
+    sgn[torch.isnan(sgn)] = 1
+    mag = (mag / torch.max(mag)) ** power
+    return sgn * mag / vector_norm(mag, norm_p)
+
+
+def normalize_v(v, domain, out=None):
+    if _is_two(domain):
+        return F.normalize(v, p=2, dim=0, out=out)
+    if domain == 1:
+        return projmax_(v)
+    return _dual_direction(v, 1 / (domain - 1), domain)
+
+
+def normalize_u(u, codomain, out=None):
+    if _is_two(codomain):
+        return F.normalize(u, p=2, dim=0, out=out)
+    if codomain == float('inf'):
+        return projmax_(u)
+    if codomain == 1:
+        return _dual_direction(u, codomain - 1, float('inf'))
+    return _dual_direction(u, codomain - 1, codomain / (codomain - 1))
+
+
+def leaky_elu(x, a=0.3):
+    return a * x + (1 - a) * F.elu(x)
+
+
+def asym_squash(x):
+    """Learnable order -> (1, 5), 2 at x = 0 (mixed_lipschitz.py:451-452)."""
+    return torch.tanh(-leaky_elu(-x + 0.5493061829986572)) * 2 + 3
+
+
+def _converged(u, v, old_u, old_v, atol, rtol):
+    """The reference's stopping rule (:115-120); one host read per iteration, as there."""
+    err_u = torch.norm(u - old_u) / (u.nelement() ** 0.5)
+    err_v = torch.norm(v - old_v) / (v.nelement() ** 0.5)
+    return bool((err_u < atol + rtol * torch.max(u)) & (err_v < atol + rtol * torch.max(v)))
 
 
 def _require_cuda(t, what):
@@ -55,13 +120,42 @@ def _soft_rescale(weight, sigma, coeff):
     return weight / factor
 
 
+def _mv(W2d, v):
+    """W v for a dense (out, in) matrix: the impflow strided GEMM on the device, torch.mv at construction time on
+    the host (the reference's constructor runs there too)."""
+    if W2d.is_cuda:
+        return ops.gemm_strided(v.reshape(1, -1), False, W2d, True).reshape(-1)
+    return torch.mv(W2d, v)
+
+
+def _mtv(W2d, u):
+    if W2d.is_cuda:
+        return ops.gemm_strided(u.reshape(1, -1), False, W2d, False).reshape(-1)
+    return torch.mv(W2d.t(), u)
+
+
+def _general_power_iteration(apply_w, apply_wt, u, v, domain, codomain, n_iterations, atol, rtol):
+    """u <- normalize_u(W v), v <- normalize_v(W^T u) until the reference's tolerance rule or the iteration cap
+    (mixed_lipschitz.py:104-120, :293-311, :343-366).  Returns (u, v, iterations used)."""
+    max_itrs = 200 if n_iterations is None else n_iterations
+    tol_mode = n_iterations is None and atol is not None and rtol is not None
+    used = 0
+    for _ in range(max_itrs):
+        old_u, old_v = u, v
+        u = normalize_u(apply_w(v), codomain)
+        v = normalize_v(apply_wt(u), domain)
+        used += 1
+        if tol_mode and _converged(u, v, old_u, old_v, atol, rtol):
+            break
+    return u, v, used
+
+
 class InducedNormLinear(nn.Module):
 
     def __init__(self, in_features, out_features, bias=True, coeff=0.97, domain=2, codomain=2, n_iterations=None,
                  atol=None, rtol=None, zero_init=False, **unused_kwargs):
         del unused_kwargs
         super(InducedNormLinear, self).__init__()
-        _check_norms(domain, codomain)
         self.in_features = in_features
         self.out_features = out_features
         self.coeff = coeff
@@ -76,11 +170,16 @@ class InducedNormLinear(nn.Module):
         else:
             self.register_parameter('bias', None)
         self.reset_parameters(zero_init)
+        with torch.no_grad():
+            dom, cod = self.compute_domain_codomain()
         h, w = self.weight.shape
         self.register_buffer('scale', torch.tensor(0.))
-        self.register_buffer('u', F.normalize(self.weight.new_empty(h).normal_(0, 1), dim=0))
-        self.register_buffer('v', F.normalize(self.weight.new_empty(w).normal_(0, 1), dim=0))
-        self._init_power_iteration_host(200)
+        self.register_buffer('u', normalize_u(self.weight.new_empty(h).normal_(0, 1), cod))
+        self.register_buffer('v', normalize_v(self.weight.new_empty(w).normal_(0, 1), dom))
+        if _plain_l2(dom, cod):
+            self._init_power_iteration_host(200)
+        else:
+            self._init_general(dom, cod, h, w)
 
     def reset_parameters(self, zero_init=False):
         # same draws as the reference (mixed_lipschitz.py:58-66)
@@ -108,7 +207,35 @@ class InducedNormLinear(nn.Module):
             self.v.copy_(v)
             self.scale.copy_(torch.dot(u, torch.mv(W, v)))
 
+    def _init_general(self, dom, cod, h, w):
+        """Non-2 norms: 200 iterations from the first start, then the reference's ten random restarts, which keep the
+        start whose sigma beats the FIRST one (its best_scale is never raised, mixed_lipschitz.py:44-56)."""
+        with torch.no_grad():
+            W = self.weight.detach()
+            sigma = self._iterate_general(W, dom, cod, 200, None, None)
+            best_scale, best_u, best_v = sigma.clone(), self.u.clone(), self.v.clone()
+            for _ in range(10):
+                self.u.copy_(normalize_u(W.new_empty(h).normal_(0, 1), cod))
+                self.v.copy_(normalize_v(W.new_empty(w).normal_(0, 1), dom))
+                sigma = self._iterate_general(W, dom, cod, 200, None, None)
+                if sigma > best_scale:
+                    best_u, best_v = self.u.clone(), self.v.clone()
+            self.u.copy_(best_u)
+            self.v.copy_(best_v)
+
+    def _iterate_general(self, W, dom, cod, n_iterations, atol, rtol):
+        """General-norm power iteration on the buffers; returns sigma = u^T W v (also left in `scale`)."""
+        u, v, _ = _general_power_iteration(lambda x: _mv(W, x), lambda x: _mtv(W, x), self.u.clone(), self.v.clone(),
+                                           dom, cod, n_iterations, atol, rtol)
+        self.u.copy_(u)
+        self.v.copy_(v)
+        sigma = torch.dot(self.u, _mv(W, self.v))
+        self.scale.copy_(sigma)
+        return sigma
+
     def compute_domain_codomain(self):
+        if torch.is_tensor(self.domain):          # learnable orders (learn_p): asym_squash of the raw parameters
+            return asym_squash(self.domain), asym_squash(self.codomain)
         return self.domain, self.codomain
 
     def sigma_gradient(self):
@@ -122,6 +249,13 @@ class InducedNormLinear(nn.Module):
 
     def compute_one_iter(self):
         _require_cuda(self.weight, 'InducedNormLinear.weight')
+        dom, cod = self.compute_domain_codomain()
+        if not _plain_l2(dom, cod):
+            with torch.no_grad():
+                W = self.weight.detach()
+                u = normalize_u(_mv(W, self.v.detach()), cod)
+                v = normalize_v(_mtv(W, u), dom)
+                return torch.dot(u, _mv(W, v))
         u, v = self.u.clone(), self.v.clone()
         sigma, _ = ops.sn_power_iter(self.weight.detach(), u, v, 1, 0.0, 0.0)
         return sigma[0]
@@ -134,17 +268,23 @@ class InducedNormLinear(nn.Module):
             rtol = self.rtol if rtol is None else atol      # reference quirk (mixed_lipschitz.py:94)
             if n_iterations is None and (atol is None or rtol is None):
                 raise ValueError('Need one of n_iteration or (atol, rtol).')
-            only = UPDATE_ONLY['on'] and not torch.is_grad_enabled()
-            with torch.no_grad():
-                sig, _ = ops.sn_power_iter(self.weight.detach(), self.u, self.v, n_iterations, atol, rtol,
-                                           sigma_out=self.scale if only else None)
-            if only:         # update_lipschitz: the kernel left sigma in `scale`; nobody reads the weight
-                self._scale_for = _state_key(self)
-                return None
-            if not torch.is_grad_enabled():
-                out = ops.sn_rescale(self.weight.detach(), sig, self.coeff, scale_out=self.scale)
-                self._scale_for = _state_key(self)
-                return out
+            dom, cod = self.compute_domain_codomain()
+            if not _plain_l2(dom, cod):
+                # general p -> q norm: host-driven iteration over the GEMM kernels; sigma below as always
+                with torch.no_grad():
+                    self._iterate_general(self.weight.detach(), dom, cod, n_iterations, atol, rtol)
+            else:
+                only = UPDATE_ONLY['on'] and not torch.is_grad_enabled()
+                with torch.no_grad():
+                    sig, _ = ops.sn_power_iter(self.weight.detach(), self.u, self.v, n_iterations, atol, rtol,
+                                               sigma_out=self.scale if only else None)
+                if only:         # update_lipschitz: the kernel left sigma in `scale`; nobody reads the weight
+                    self._scale_for = _state_key(self)
+                    return None
+                if not torch.is_grad_enabled():
+                    out = ops.sn_rescale(self.weight.detach(), sig, self.coeff, scale_out=self.scale)
+                    self._scale_for = _state_key(self)
+                    return out
         sigma = _Sigma.apply(self.weight, self.u, self.v)
         with torch.no_grad():
             self.scale.copy_(sigma[0])
@@ -180,7 +320,6 @@ class InducedNormConv2d(nn.Module):
                  codomain=2, n_iterations=None, atol=None, rtol=None, **unused_kwargs):
         del unused_kwargs
         super(InducedNormConv2d, self).__init__()
-        _check_norms(domain, codomain)
         self.in_channels = in_channels
         self.out_channels = out_channels
         self.kernel_size = _pair(kernel_size)
@@ -212,6 +351,8 @@ class InducedNormConv2d(nn.Module):
         self._init_known = None     # python mirror of the `initialized` buffer (reading it syncs the stream)
 
     def compute_domain_codomain(self):
+        if torch.is_tensor(self.domain):          # learnable orders (learn_p)
+            return asym_squash(self.domain), asym_squash(self.codomain)
         return self.domain, self.codomain
 
     def reset_parameters(self):
@@ -271,30 +412,87 @@ class InducedNormConv2d(nn.Module):
         return cached[1]
 
     def _initialize_u_v(self):
-        # mixed_lipschitz.py:195-239 (domain = codomain = 2: a single start, no restarts)
+        # mixed_lipschitz.py:195-239: one start for domain = codomain = 2, ten more random starts otherwise
         with torch.no_grad():
+            dom, cod = self.compute_domain_codomain()
             if self.kernel_size == (1, 1):
-                self.u.resize_(self.out_channels).normal_(0, 1)
-                self.u.copy_(F.normalize(self.u, dim=0))
-                self.v.resize_(self.in_channels).normal_(0, 1)
-                self.v.copy_(F.normalize(self.v, dim=0))
+                n_u, n_v = self.out_channels, self.in_channels
             else:
-                c = self.in_channels
                 h, w = self._spatial()
-                self.v.resize_(c * h * w).normal_(0, 1)
-                self.v.copy_(F.normalize(self.v, dim=0))
-                self.u.resize_(self.out_channels * h * w).normal_(0, 1)
-                self.u.copy_(F.normalize(self.u, dim=0))
+                n_u, n_v = self.out_channels * h * w, self.in_channels * h * w
+            # the reference draws v first for k x k kernels, u first for 1 x 1 ones
+            if self.kernel_size == (1, 1):
+                self.u.resize_(n_u).normal_(0, 1)
+                self.u.copy_(normalize_u(self.u, cod))
+                self.v.resize_(n_v).normal_(0, 1)
+                self.v.copy_(normalize_v(self.v, dom))
+            else:
+                self.v.resize_(n_v).normal_(0, 1)
+                self.v.copy_(normalize_v(self.v, dom))
+                self.u.resize_(n_u).normal_(0, 1)
+                self.u.copy_(normalize_u(self.u, cod))
             self.initialized.fill_(1)
             self._init_known = True
             self.compute_weight(True)
+            if not _plain_l2(dom, cod):
+                # restarts keep the start whose sigma beats the FIRST one (best_scale is never raised, :223-235)
+                best_scale = self.scale.clone()
+                best_u, best_v = self.u.clone(), self.v.clone()
+                for _ in range(10):
+                    if self.kernel_size == (1, 1):
+                        self.u.copy_(normalize_u(self.weight.new_empty(n_u).normal_(0, 1), cod))
+                        self.v.copy_(normalize_v(self.weight.new_empty(n_v).normal_(0, 1), dom))
+                    else:     # host generator, as in the reference (torch.randn(...).to(weight))
+                        self.u.copy_(normalize_u(torch.randn(n_u).to(self.weight), cod))
+                        self.v.copy_(normalize_v(torch.randn(n_v).to(self.weight), dom))
+                    self.compute_weight(True, n_iterations=200)
+                    if self.scale > best_scale:
+                        best_u, best_v = self.u.clone(), self.v.clone()
+                self.u.copy_(best_u)
+                self.v.copy_(best_v)
             self.u = self.u.clone(memory_format=torch.contiguous_format)
             self.v = self.v.clone(memory_format=torch.contiguous_format)
+
+    def _general_update(self, dom, cod, n_iterations, atol, rtol):
+        """General p -> q power iteration on the buffers (mixed_lipschitz.py:293-318, :343-372): W v / W^T u on the
+        GEMM / conv kernels, dual-norm normalisations in between.  Which buffer is written back follows the
+        reference branch by branch (a 1x1 layer keeps its stored v for domain 1 and its stored u for codomain inf)."""
+        if self.kernel_size == (1, 1):
+            W2 = self.weight.detach().view(self.out_channels, self.in_channels)
+            fw, bw = (lambda x: _mv(W2, x)), (lambda x: _mtv(W2, x))
+        else:
+            wt = self.weight.detach()
+            fw, bw = (lambda x: self._conv_vec(x, wt)), (lambda x: self._conv_vec(x, wt, transpose=True))
+        u, v, used = _general_power_iteration(fw, bw, self.u.clone(), self.v.clone(), dom, cod, n_iterations, atol,
+                                              rtol)
+        if used > 0:
+            if self.kernel_size == (1, 1):
+                keep_v, keep_u = (dom == 1 or _is_two(dom)), (_is_two(cod) or cod == float('inf'))
+            else:
+                keep_v, keep_u = _is_two(dom), _is_two(cod)
+            # a 2-norm side is normalised IN PLACE in the reference (F.normalize(out=buffer)): written either way
+            if not keep_v or _is_two(dom):
+                self.v.copy_(v)
+            if not keep_u or _is_two(cod):
+                self.u.copy_(u)
+        return u, v
 
     def compute_one_iter(self):
         if not self.is_initialized():
             raise ValueError('Layer needs to be initialized first.')
         _require_cuda(self.weight, 'InducedNormConv2d.weight')
+        dom, cod = self.compute_domain_codomain()
+        if not _plain_l2(dom, cod):
+            with torch.no_grad():
+                if self.kernel_size == (1, 1):
+                    W2 = self.weight.detach().view(self.out_channels, self.in_channels)
+                    fw, bw = (lambda x: _mv(W2, x)), (lambda x: _mtv(W2, x))
+                else:
+                    wt = self.weight.detach()
+                    fw, bw = (lambda x: self._conv_vec(x, wt)), (lambda x: self._conv_vec(x, wt, transpose=True))
+                u = normalize_u(fw(self.v.detach()), cod)
+                v = normalize_v(bw(u), dom)
+                return torch.dot(u, fw(v))
         if self.kernel_size == (1, 1):
             W2 = self.weight.detach().view(self.out_channels, self.in_channels)
             sigma, _ = ops.sn_power_iter(W2, self.u.clone(), self.v.clone(), 1, 0.0, 0.0)
@@ -320,6 +518,17 @@ class InducedNormConv2d(nn.Module):
 
     def _compute_weight_1x1(self, update, n_iterations, atol, rtol):
         W2 = self.weight.view(self.out_channels, self.in_channels)
+        dom, cod = self.compute_domain_codomain()
+        if not _plain_l2(dom, cod):
+            u, v = self.u, self.v
+            if update:
+                with torch.no_grad():
+                    u, v = self._general_update(dom, cod, n_iterations, atol, rtol)
+            # sigma from the iterates of THIS call (the stored buffers may lag behind them, see _general_update)
+            sigma = _Sigma.apply(W2, u.detach().contiguous(), v.detach().contiguous())
+            with torch.no_grad():
+                self.scale.copy_(sigma[0])
+            return _soft_rescale(W2, sigma, self.coeff).view(self.out_channels, self.in_channels, 1, 1)
         if update:
             only = UPDATE_ONLY['on'] and not torch.is_grad_enabled()
             with torch.no_grad():
@@ -340,6 +549,16 @@ class InducedNormConv2d(nn.Module):
 
     def _compute_weight_kxk(self, update, n_iterations, atol, rtol):
         u, v = self.u, self.v
+        dom, cod = self.compute_domain_codomain()
+        if not _plain_l2(dom, cod):
+            if update:
+                with torch.no_grad():
+                    u, v = self._general_update(dom, cod, n_iterations, atol, rtol)
+            weight_v = self._conv_vec(v.detach(), self.weight)
+            sigma = ops.rowdot_fn(u.detach().view(1, -1), weight_v.view(1, -1))
+            with torch.no_grad():
+                self.scale.copy_(sigma[0])
+            return _soft_rescale(self.weight, sigma, self.coeff)
         if update and self.kernel_size == (3, 3):
             # the whole iteration (and sigma) in one cooperative launch; no host synchronisation
             h, w = self._spatial()

@@ -108,6 +108,7 @@ def _timed(kind, like, fn):
 
 # Independent halves of a block's work (the log-det estimates of the x- and z-branch) on two streams.
 OVERLAP = {'on': True}
+HOST_AHEAD = {'on': True}     # imBlock.forward: twin refresh and random draws in front of the forward solve
 _side = {}
 
 
@@ -139,32 +140,69 @@ class _overlap(object):
         return False
 
 
-def _sync_twin(dst, src):
+def _twin_slots(net):
+    """(dict, name) of every parameter / buffer slot of `net` in module order.  The tensors are looked up through the
+    slots on every call (a buffer may have been re-registered, a parameter's storage re-pointed); only the walk
+    over the module tree is cached (it cost 0.3 ms of host time per call, right after a solve has drained the
+    stream, i.e. while the GPU idles)."""
+    slots = net.__dict__.get('_impflow_twin_slots')
+    n_mod = sum(1 for _ in net.children())
+    if slots is None or slots[0] != n_mod:
+        lst = []
+        for m in net.modules():
+            lst += [(m._parameters, k) for k, v in m._parameters.items() if v is not None]
+        for m in net.modules():
+            lst += [(m._buffers, k) for k, v in m._buffers.items() if v is not None]
+        mirrors = [m for m in net.modules() if hasattr(m, '_hw')]
+        slots = net.__dict__['_impflow_twin_slots'] = (n_mod, lst, mirrors)
+    return slots
+
+
+def _twin_versions(net):
+    _, slots, _ = _twin_slots(net)
+    return [dct[k]._version for dct, k in slots]
+
+
+def _sync_twin(dst, src, fallback=True):
     """dst.load_state_dict(src.state_dict()) for two structurally identical nets, as one multi-tensor copy
     (the reference refreshes the frozen twins after every forward, implicit_block.py:228-229).  Falls back
-    to load_state_dict whenever a shape differs (lazily shaped u / v before their first use)."""
+    to load_state_dict whenever a shape differs (lazily shaped u / v before their first use) — or, with
+    fallback=False, does nothing then and returns False (the caller retries later)."""
     with torch.no_grad():
-        d = list(dst.parameters()) + list(dst.buffers())
-        s = list(src.parameters()) + list(src.buffers())
-        if len(d) == len(s) and all(a.shape == b.shape and a.dtype == b.dtype for a, b in zip(d, s)):
-            # the multi-tensor fast path needs one dtype per call and equal strides: group by dtype and copy
-            # flat views (a mixed list silently degrades to one cudaMemcpy per tensor)
-            groups = {}
-            for a, b in zip(d, s):
-                if a.is_contiguous() and b.is_contiguous():
-                    groups.setdefault(a.dtype, ([], []))
-                    groups[a.dtype][0].append(a.view(-1))
-                    groups[a.dtype][1].append(b.detach().view(-1))
-                else:
+        _, dslots, mirrors = _twin_slots(dst)
+        _, sslots, _ = _twin_slots(src)
+        d = [dct[k] for dct, k in dslots]
+        s = [dct[k] for dct, k in sslots]
+        if len(d) == len(s):
+            key = tuple([(t.data_ptr(), t.numel()) for t in d] + [(t.data_ptr(), t.numel()) for t in s])
+            cache = dst.__dict__.get('_impflow_twin_cache')
+            if cache is None or cache[0] != key:
+                cache = None
+                if all(a.shape == b.shape and a.dtype == b.dtype for a, b in zip(d, s)):
+                    # the multi-tensor fast path needs one dtype per call and equal strides: group by dtype and copy
+                    # flat views (a mixed list silently degrades to one cudaMemcpy per tensor)
+                    groups, singles = {}, []
+                    for a, b in zip(d, s):
+                        if a.is_contiguous() and b.is_contiguous():
+                            groups.setdefault(a.dtype, ([], []))
+                            groups[a.dtype][0].append(a.view(-1))
+                            groups[a.dtype][1].append(b.detach().view(-1))
+                        else:
+                            singles.append((a, b))
+                    cache = dst.__dict__['_impflow_twin_cache'] = (key, list(groups.values()), singles)
+            if cache is not None:
+                for a, b in cache[2]:
                     a.copy_(b)
-            for da, sa in groups.values():
-                torch._foreach_copy_(da, sa)
-            for m in dst.modules():           # python mirrors of buffers that load_state_dict would reset
-                if hasattr(m, '_hw'):
+                for da, sa in cache[1]:
+                    torch._foreach_copy_(da, sa)
+                for m in mirrors:                 # python mirrors of buffers that load_state_dict would reset
                     m._hw = None
                     m._init_known = None
-            return
+                return True
+    if not fallback:
+        return False
     dst.load_state_dict(src.state_dict())
+    return True
 
 
 _pinned = {}
@@ -320,6 +358,11 @@ class imBlock(nn.Module):
                 with torch.no_grad():
                     z, x = z.detach(), x.detach()
                     _, saved_z = prog_z.forward_saved(z)
+                    # everything the x-branch vjp behind the solve needs is set up in front of it (the solve drains
+                    # the stream: host work after it runs while the GPU idles)
+                    xa = ctx.x_alias if (ctx.x_alias is not None and ctx.x_alias.shape == x.shape) else x
+                    _, saved_x = prog_x.forward_saved(xa)
+                    prog_x.prepare_vjp(saved_x)
 
                     def solve():
                         info = prog_z.broyden_solve(1, grad, saved_z, threshold, eps)
@@ -336,8 +379,6 @@ class imBlock(nn.Module):
                     if ctx.stats is not None:
                         ctx.stats['bwd'] = info
                     dl_dh = info['result']
-                    xa = ctx.x_alias if (ctx.x_alias is not None and ctx.x_alias.shape == x.shape) else x
-                    _, saved_x = prog_x.forward_saved(xa)
                     dl_dx = ops.lincomb3(prog_x.vjp(dl_dh, saved_x), 1.0, dl_dh, 1.0)
                 return (None, None, dl_dh, dl_dx) + (None,) * len(args)
             z = z.clone().detach().requires_grad_()
@@ -370,12 +411,28 @@ class imBlock(nn.Module):
             with torch.no_grad():
                 _ = self.nnet_x_copy(z0)
                 _ = self.nnet_z_copy(z0)
+        # Host-side work that does not depend on the solve goes IN FRONT of it: the solve drains the stream, so
+        # whatever the host still has to do afterwards runs while the GPU idles.  The twin refresh copies weights the
+        # solve does not change; the roulette draw and the probes come from generators the solve does not touch, in
+        # the reference's order (n, then vareps_x, vareps_z; :270-298), so every stream position is unchanged.
+        early = HOST_AHEAD['on'] and x.is_cuda
+        synced = False
+        if early:
+            # == load_state_dict(state_dict()) (:228-229); before the first use of a net its u / v are not shaped yet
+            # (the solve does that): then the refresh stays behind the solve
+            synced = _sync_twin(self.nnet_x_copy, self.nnet_x, fallback=False) and \
+                _sync_twin(self.nnet_z_copy, self.nnet_z, fallback=False)
+            versions = _twin_versions(self.nnet_x) + _twin_versions(self.nnet_z) if synced else None
+            self._pre = self._predraw(z0) if logpx is not None else None
         z = RootFind.apply(self.nnet_z, self.nnet_x, z0, z0, 'broyden', self.eps_forward, self.threshold)
         self.solver_stats['fwd'] = RootFind.last_info
         # re-attach: gradients reach the branch parameters through this expression (:227)
         z = branch_apply(self.nnet_x, z0) - branch_apply(self.nnet_z, z.detach()) + z0
-        _sync_twin(self.nnet_x_copy, self.nnet_x)         # == load_state_dict(state_dict()) (:228-229)
-        _sync_twin(self.nnet_z_copy, self.nnet_z)
+        if synced and versions != _twin_versions(self.nnet_x) + _twin_versions(self.nnet_z):
+            synced = False          # the forward wrote a buffer of the live nets (scale, lazily shaped u / v)
+        if not synced:
+            _sync_twin(self.nnet_x_copy, self.nnet_x)
+            _sync_twin(self.nnet_z_copy, self.nnet_z)
         if FUSED['on']:      # the frozen twins hold the same weights: share the live nets' programs
             self.nnet_z_copy._impflow_program = _program(self.nnet_z)
             self.nnet_x_copy._impflow_program = _program(self.nnet_x)
@@ -387,6 +444,7 @@ class imBlock(nn.Module):
             return z
         out = z, logpx - self._logdetgrad(z, x)
         self._z0 = None
+        self._pre = None
         return out
 
     def inverse(self, z, logpy=None):
@@ -439,8 +497,20 @@ class imBlock(nn.Module):
         vz = _upload(bern.sample(z.shape).reshape(z.shape) * 2 - 1, z)
         return vx, vz
 
+    def _predraw(self, x):
+        """The random inputs of the coming _logdetgrad(z, x) call (z has x's shape), drawn before the solve: the
+        roulette sample count and the two probe tensors, or None where _logdetgrad draws nothing / something else
+        (brute force, exact trace, evaluation mode)."""
+        if not self.training or self.exact_trace:
+            return None
+        if self.brute_force and x.ndimension() == 2 and x.shape[1] <= 10:
+            return None
+        n_samples = self._draw_n() if self.n_power_series is None else None
+        return n_samples, self._draw_probes(x, x)
+
     def _logdetgrad(self, z, x):
         """logdet |dz/dx| = logdet(I + J_x) - logdet(I + J_z)  (implicit_block.py:245-350)."""
+        pre, self._pre = getattr(self, '_pre', None), None
         with torch.enable_grad():
             if (self.brute_force or not self.training) and (x.ndimension() == 2 and x.shape[1] <= 10):
                 x = x.requires_grad_(True)
@@ -455,12 +525,12 @@ class imBlock(nn.Module):
                 coeff_fn = lambda k: 1.
             else:
                 n_exact = self.n_exact_terms if self.training else self.n_exact_terms_test
-                n_samples = self._draw_n()
+                n_samples = pre[0] if pre is not None else self._draw_n()
                 n_power_series = int(max(n_samples) + n_exact)
                 coeff_fn = lambda k: 1 / self._rcdf(k, n_exact) * sum(n_samples >= k - n_exact) / len(n_samples)
 
             if not self.exact_trace:
-                vareps_x, vareps_z = self._draw_probes(x, z)
+                vareps_x, vareps_z = pre[1] if pre is not None else self._draw_probes(x, z)
                 if self.training and self.neumann_grad:
                     estimator_fn = neumann_logdet_estimator
                 else:

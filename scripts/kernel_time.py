@@ -65,10 +65,16 @@ print('GPU kernel time per step: %.1f ms over %d kernels' % (T / 1e3, sum(cnt.va
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:25]:
     print('%9.0f us %5.1f%% n=%5d avg=%8.1f  %s' % (v, 100 * v / T, cnt[k], v / cnt[k], k))
 # GPU busy time = union of the kernel intervals over all streams; idle = first start .. last end minus busy
-iv = sorted((ev.time_range.start, ev.time_range.end, ev.name.split('(')[0][:50]) for ev in prof.events()
+def _short(n):
+    n = n.replace('void ', '').replace('at::native::', '').replace('(anonymous namespace)::', '')
+    return n[:110]
+
+
+iv = sorted((ev.time_range.start, ev.time_range.end, _short(ev.name)) for ev in prof.events()
             if ev.device_type == torch.autograd.DeviceType.CUDA)
 busy, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
 gaps = []
+pairs = []
 late = collections.defaultdict(float)      # idle time by the kernel that ends the gap ("who was late")
 late_n = collections.Counter()
 prev_name = iv[0][2]
@@ -77,6 +83,7 @@ for s, e, nm in iv[1:]:
     if s > cur_e:
         busy += cur_e - cur_s
         gaps.append(s - cur_e)
+        pairs.append((s - cur_e, prev_name, nm))
         late[nm] += s - cur_e
         late_n[nm] += 1
         after[prev_name] += s - cur_e
@@ -98,3 +105,6 @@ for k, v in sorted(late.items(), key=lambda kv: -kv[1])[:16]:
 print('idle time by the kernel that precedes the gap:')
 for k, v in sorted(after.items(), key=lambda kv: -kv[1])[:10]:
     print('   %8.0f us after %s' % (v, k))
+print('largest gaps (us, kernel before -> kernel after):')
+for g, a, b in sorted(pairs, key=lambda t: -t[0])[:45]:
+    print('   %7.1f  %s  ->  %s' % (g, a[:70], b[:90]))

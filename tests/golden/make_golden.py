@@ -378,6 +378,85 @@ def gen_induced_norm():
     save('induced_norm', **out)
 
 
+def gen_mixed_norm():
+    """Induced p -> q norms other than 2 -> 2 and learnable orders (mixed_lipschitz.py:414-444, learn_p):
+    constructor with its random restarts, tolerance-mode update after a weight change, one-iteration estimate,
+    forward, weight gradient through sigma; Linear, 1x1 (incl. the orders whose buffer is NOT written back) and 3x3."""
+    out = {}
+    INF = float('inf')
+    lin_cases = {'l23': (2, 3), 'l33': (3, 3), 'l13': (1, 3), 'l3i': (3, INF), 'l15_25': (1.5, 2.5)}
+    for i, (tag, (dom, cod)) in enumerate(lin_cases.items()):
+        torch.manual_seed(40 + i)
+        lin = base_layers.InducedNormLinear(6, 7, coeff=0.6, domain=dom, codomain=cod, atol=1e-3, rtol=1e-3)
+        for k, v in sd_np(lin).items():
+            out[tag + '_init_' + k] = v
+        with torch.no_grad():
+            lin.weight.add_(0.3 * torch.randn_like(lin.weight))
+        out[tag + '_weight2'] = lin.weight.detach().numpy().copy()
+        out[tag + '_one_iter'] = lin.compute_one_iter().detach().numpy().copy()
+        W = lin.compute_weight(update=True)
+        out[tag + '_W_tol'] = W.detach().numpy()
+        out[tag + '_u_tol'], out[tag + '_v_tol'] = lin.u.numpy().copy(), lin.v.numpy().copy()
+        out[tag + '_scale_tol'] = lin.scale.numpy().copy()
+        xin = torch.randn(4, 6)
+        out[tag + '_x'] = xin.numpy()
+        out[tag + '_y'] = lin(xin).detach().numpy()
+        lin.zero_grad()
+        lin(xin).pow(2).sum().backward()
+        out[tag + '_grad_weight'] = lin.weight.grad.numpy().copy()
+        out[tag + '_norms'] = np.array([dom, cod], dtype=np.float64)
+    conv_cases = {'c1_3i': (1, (3, INF)), 'c1_13': (1, (1, 3)), 'c1_33': (1, (3, 3)), 'c3_23': (3, (2, 3)),
+                  'c3_33': (3, (3, 3)), 'c3_32': (3, (3, 2))}
+    for i, (tag, (k, (dom, cod))) in enumerate(conv_cases.items()):
+        torch.manual_seed(60 + i)
+        conv = base_layers.InducedNormConv2d(3, 4, k, 1, k // 2, coeff=0.5, domain=dom, codomain=cod, atol=1e-3,
+                                             rtol=1e-3)
+        xin = torch.randn(2, 3, 5, 5)
+        y0 = conv(xin)                                   # lazy init with the restarts
+        for kk, v in sd_np(conv).items():
+            out[tag + '_init_' + kk] = v
+        out[tag + '_x'], out[tag + '_y'] = xin.numpy(), y0.detach().numpy()
+        with torch.no_grad():
+            conv.weight.add_(0.2 * torch.randn_like(conv.weight))
+        out[tag + '_weight2'] = conv.weight.detach().numpy().copy()
+        out[tag + '_one_iter'] = conv.compute_one_iter().detach().numpy().copy()
+        W = conv.compute_weight(update=True)
+        out[tag + '_W_tol'] = W.detach().numpy()
+        out[tag + '_u_tol'], out[tag + '_v_tol'] = conv.u.numpy().copy(), conv.v.numpy().copy()
+        out[tag + '_scale_tol'] = conv.scale.numpy().copy()
+        out[tag + '_y2'] = conv(xin).detach().numpy()
+        conv.zero_grad()
+        conv(xin).pow(2).sum().backward()
+        out[tag + '_grad_weight'] = conv.weight.grad.numpy().copy()
+        out[tag + '_norms'] = np.array([dom, cod, k], dtype=np.float64)
+    # learnable orders: two shared raw parameters, p = asym_squash(raw)
+    torch.manual_seed(80)
+    pd, pc = torch.nn.Parameter(torch.tensor(0.)), torch.nn.Parameter(torch.tensor(0.4))
+    lin = base_layers.InducedNormLinear(5, 6, coeff=0.6, domain=pd, codomain=pc, atol=1e-3, rtol=1e-3)
+    for k, v in sd_np(lin).items():
+        out['lp_init_' + k] = v
+    out['lp_orders'] = np.array([float(o) for o in lin.compute_domain_codomain()])
+    with torch.no_grad():
+        lin.weight.add_(0.3 * torch.randn_like(lin.weight))
+    out['lp_weight2'] = lin.weight.detach().numpy().copy()
+    W = lin.compute_weight(update=True)
+    out['lp_W_tol'] = W.detach().numpy()
+    out['lp_u_tol'], out['lp_v_tol'] = lin.u.numpy().copy(), lin.v.numpy().copy()
+    out['lp_scale_tol'] = lin.scale.numpy().copy()
+    # state-dict keys of a learn_p flow (the shared order parameters appear under every layer that holds them)
+    torch.manual_seed(81)
+    flow = ImplicitFlow((2, 3, 8, 8), n_blocks=[1, 1], intermediate_dim=8, factor_out=False, quadratic=False,
+                        init_layer=None, actnorm=False, fc_actnorm=False, batchnorm=False, dropout=0., fc=False,
+                        coeff=0.9, vnorms='2222', n_lipschitz_iters=None, sn_atol=1e-3, sn_rtol=1e-3,
+                        n_power_series=None, n_dist='poisson', n_samples=1, kernels='3-1-3', activation_fn='swish',
+                        fc_end=False, fc_idim=16, n_exact_terms=2, preact=True, neumann_grad=True,
+                        grad_in_forward=True, first_resblock=True, learn_p=True, classification=False,
+                        classification_hdim=64, n_classes=10)
+    out['lp_flow_keys'] = np.array(sorted(flow.state_dict().keys()))
+    out['lp_flow_nparams'] = np.array([sum(p.numel() for p in flow.parameters())])
+    save('mixed_norm', **out)
+
+
 # ----------------------------------------------------------------------------------------------
 # 5. activations
 # ----------------------------------------------------------------------------------------------
@@ -748,11 +827,12 @@ def gen_bwd_band():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['broyden', 'mlp', 'conv', 'norm', 'act', 'flow', 'ires', 'edge', 'tail', 'band']
+    which = sys.argv[1:] or ['broyden', 'mlp', 'conv', 'norm', 'mixed', 'act', 'flow', 'ires', 'edge', 'tail', 'band']
     if 'broyden' in which: gen_broyden()
     if 'mlp' in which: gen_imblock_mlp()
     if 'conv' in which: gen_imblock_conv()
     if 'norm' in which: gen_induced_norm()
+    if 'mixed' in which: gen_mixed_norm()
     if 'act' in which: gen_activations()
     if 'flow' in which: gen_flow()
     if 'ires' in which: gen_ires()

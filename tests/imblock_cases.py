@@ -849,6 +849,94 @@ def case_sweep_graphs_mlp_match_eager():
     assert len(graphs) == 4, 'three row counts of the batched sweep + the first-order backward: %d' % len(graphs)
 
 
+def case_mixed_norm_layers(golden):
+    """Induced p -> q norms other than 2 -> 2 and learnable orders against the reference (golden mixed_norm.npz):
+    constructor incl. the random restarts (same seed: u, v, scale), one-iteration estimate, tolerance-mode update
+    after a weight change (u, v as stored — including the orders whose buffer the reference does not write back —,
+    sigma, rescaled weight), forward and the weight gradient through sigma."""
+    pkg = _pkg()
+    BL = pkg.layers.base
+    dev = DEV['device']
+    fx = golden('mixed_norm')
+    tn = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    close = lambda got, want, rtol=2e-4, atol=2e-5: np.testing.assert_allclose(got.detach().cpu().numpy(), want,
+                                                                               rtol=rtol, atol=atol)
+    for i, tag in enumerate(['l23', 'l33', 'l13', 'l3i', 'l15_25']):
+        dom, cod = [float(t) for t in fx[tag + '_norms']]
+        torch.manual_seed(40 + i)
+        lin = BL.InducedNormLinear(6, 7, coeff=0.6, domain=dom, codomain=cod, atol=1e-3, rtol=1e-3)
+        for k in ('weight', 'bias', 'u', 'v', 'scale'):      # the constructor ran on the host: same draws, same restarts
+            close(getattr(lin, k), fx[tag + '_init_' + k], rtol=1e-4, atol=1e-5)
+        lin = lin.to(dev)
+        with torch.no_grad():
+            lin.weight.copy_(tn(fx[tag + '_weight2']))
+        close(lin.compute_one_iter(), fx[tag + '_one_iter'])
+        W = lin.compute_weight(update=True)
+        close(lin.u, fx[tag + '_u_tol'])
+        close(lin.v, fx[tag + '_v_tol'])
+        close(lin.scale, fx[tag + '_scale_tol'])
+        close(W, fx[tag + '_W_tol'])
+        x = tn(fx[tag + '_x'])
+        close(lin(x), fx[tag + '_y'])
+        lin.zero_grad()
+        lin(x).pow(2).sum().backward()
+        close(lin.weight.grad, fx[tag + '_grad_weight'], rtol=2e-3, atol=1e-4)
+    for tag in ['c1_3i', 'c1_13', 'c1_33', 'c3_23', 'c3_33', 'c3_32']:
+        dom, cod, k = [float(t) for t in fx[tag + '_norms']]
+        k = int(k)
+        conv = BL.InducedNormConv2d(3, 4, k, 1, k // 2, coeff=0.5, domain=dom, codomain=cod, atol=1e-3, rtol=1e-3)
+        conv = conv.to(dev)
+        x = tn(fx[tag + '_x'])
+        with torch.no_grad():
+            conv(x)                                        # lazy shaping (device generator: values replaced below)
+        conv.load_state_dict({kk[len(tag + '_init_'):]: tn(v) for kk, v in fx.items() if kk.startswith(tag + '_init_')})
+        close(conv(x), fx[tag + '_y'])
+        with torch.no_grad():
+            conv.weight.copy_(tn(fx[tag + '_weight2']))
+        close(conv.compute_one_iter(), fx[tag + '_one_iter'])
+        W = conv.compute_weight(update=True)
+        close(conv.u, fx[tag + '_u_tol'])
+        close(conv.v, fx[tag + '_v_tol'])
+        close(conv.scale, fx[tag + '_scale_tol'])
+        close(W, fx[tag + '_W_tol'])
+        close(conv(x), fx[tag + '_y2'])
+        conv.zero_grad()
+        conv(x).pow(2).sum().backward()
+        close(conv.weight.grad, fx[tag + '_grad_weight'], rtol=2e-3, atol=1e-4)
+    # learnable orders
+    torch.manual_seed(80)
+    pd, pc = torch.nn.Parameter(torch.tensor(0.)), torch.nn.Parameter(torch.tensor(0.4))
+    lin = BL.InducedNormLinear(5, 6, coeff=0.6, domain=pd, codomain=pc, atol=1e-3, rtol=1e-3)
+    assert sorted(lin.state_dict().keys()) == sorted(k[len('lp_init_'):] for k in fx if k.startswith('lp_init_'))
+    for k in ('weight', 'u', 'v', 'scale', 'domain', 'codomain'):
+        close(getattr(lin, k), fx['lp_init_' + k], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose([float(o) for o in lin.compute_domain_codomain()], fx['lp_orders'], rtol=1e-6)
+    lin = lin.to(dev)
+    with torch.no_grad():
+        lin.weight.copy_(tn(fx['lp_weight2']))
+    W = lin.compute_weight(update=True)
+    close(lin.u, fx['lp_u_tol'])
+    close(lin.v, fx['lp_v_tol'])
+    close(W, fx['lp_W_tol'])
+
+
+def case_learn_p_flow_state_dict(golden):
+    """ImplicitFlow(learn_p=True): the shared order parameters appear under the same state-dict keys as in the
+    reference, with the same parameter count."""
+    pkg = _pkg()
+    fx = golden('mixed_norm')
+    torch.manual_seed(81)
+    flow = pkg.ImplicitFlow((2, 3, 8, 8), n_blocks=[1, 1], intermediate_dim=8, factor_out=False, quadratic=False,
+                            init_layer=None, actnorm=False, fc_actnorm=False, batchnorm=False, dropout=0., fc=False,
+                            coeff=0.9, vnorms='2222', n_lipschitz_iters=None, sn_atol=1e-3, sn_rtol=1e-3,
+                            n_power_series=None, n_dist='poisson', n_samples=1, kernels='3-1-3',
+                            activation_fn='swish', fc_end=False, fc_idim=16, n_exact_terms=2, preact=True,
+                            neumann_grad=True, grad_in_forward=True, first_resblock=True, learn_p=True,
+                            classification=False, classification_hdim=64, n_classes=10)
+    assert sorted(flow.state_dict().keys()) == [str(k) for k in fx['lp_flow_keys']]
+    assert sum(p.numel() for p in flow.parameters()) == int(fx['lp_flow_nparams'][0])
+
+
 def case_direct_grad_sink_matches_autograd(golden):
     """FlatGradBucket(direct=True): the graph-free backward sweeps add their finished parameter gradients straight
     into the bucket (parallel.sink_grads) instead of returning them to autograd; the flat gradient after one step of

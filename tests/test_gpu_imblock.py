@@ -74,6 +74,10 @@ def test_sweep_graphs_match_eager():
     cases.case_sweep_graphs_match_eager()
 
 
+def test_mixed_norm_layers_vs_golden(golden):
+    cases.case_mixed_norm_layers(golden)
+
+
 def test_sweep_graphs_mlp_match_eager():
     cases.case_sweep_graphs_mlp_match_eager()
 

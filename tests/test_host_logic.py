@@ -179,6 +179,14 @@ def test_induced_norm_layers_vs_golden(golden):
     np.testing.assert_allclose(W.detach().numpy(), fx['c1_W_tol'], rtol=1e-5, atol=1e-6)
 
 
+def test_mixed_norm_layers_vs_golden(golden):
+    cases.case_mixed_norm_layers(golden)
+
+
+def test_learn_p_flow_state_dict(golden):
+    cases.case_learn_p_flow_state_dict(golden)
+
+
 @pytest.mark.parametrize('name', branch_cases.NAMES)
 @pytest.mark.parametrize('backend', ['simt', 'tc'])
 def test_branch_program_matches_module_autograd(name, backend):
