@@ -67,7 +67,7 @@ MEMO = {'on': True}
 # 'mlp': graphs of the MLP flows' batched sweeps, one per distinct n-fold row count (opt-in: a tabular step drops from
 # 259 to ~195 ms once every (program, n) pair has been captured, but each capture costs ~28 ms and a 20-block flow
 # needs ~200 of them, which only pays off over a training run, not over a 20-step benchmark)
-SWEEP_GRAPHS = {'on': True, 'max_rows': 16384, 'warmup': 2, 'mlp': False}
+SWEEP_GRAPHS = {'on': True, 'max_rows': 16384, 'warmup': 1, 'mlp': False}
 
 _conv3_ws = {}      # (device index, stream) -> workspace tensor shared by every plan used on that stream
 
