@@ -155,14 +155,23 @@ def update_lipschitz(pkg, model, n_iterations=None):
 
 
 class ClockSampler(object):
+    """`nvidia-smi -lms 200` next to the benchmark.  The process is started BEFORE the warm-up steps: its start-up (NVML
+    initialisation) holds driver locks for ~100 ms, which used to land in the first timed steps (per_step_ms showed
+    150-300 ms there in one run out of three); only the samples taken between mark_begin() and stop() — the timed region —
+    are reported."""
     QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp')
 
     def __init__(self, gpu_index):
         self.path = tempfile.mktemp(suffix='.csv')
         self.proc = None
         self.gpu = gpu_index
+        self.t_begin = None
+
+    def mark_begin(self):
+        import datetime
+        self.t_begin = datetime.datetime.now()
 
     def start(self):
         try:
@@ -181,27 +190,36 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         try:
             for line in open(self.path):
                 f = [t.strip() for t in line.split(',')]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    row = [float(f[1]), float(f[2])]
                 except ValueError:
                     continue
-                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
-                                     f[5:9]):
-                    if val.lower().startswith('active'):
-                        reasons.add(name)
+                ts = None
+                if len(f) >= 10:
+                    try:
+                        ts = datetime.datetime.strptime(f[9], '%Y/%m/%d %H:%M:%S.%f')
+                    except ValueError:
+                        ts = None
+                rs = [name for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                                 'sw_power_cap'), f[5:9]) if val.lower().startswith('active')]
+                rows.append((ts, row[0], row[1], rs))
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
-                   'samples': len(sm)}
+        timed = [r for r in rows if self.t_begin is not None and r[0] is not None and r[0] >= self.t_begin]
+        window = 'timed region'
+        if not timed:           # region shorter than the sampling period (or no timestamps): everything since the start
+            timed, window = rows, 'warm-up + timed region'
+        if timed:
+            out = {'sm_mhz': float(np.median([r[1] for r in timed])), 'sm_max_mhz': float(max(r[2] for r in timed)),
+                   'reasons': sorted({n for r in timed for n in r[3]}), 'samples': len(timed), 'window': window}
         return out
 
 
@@ -657,6 +675,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock poller starts in front of the warm-up (its start-up stalls CUDA calls for ~100 ms, see ClockSampler)
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and os.environ.get('IMPFLOW_BENCH_NOSAMPLER', '') != '1':     # diagnostic switch: cost of the poller
+        sampler.start()
     trace = os.environ.get('IMPFLOW_TRACE_CAPTURE', '') == '1'
     for i_ in range(args.warmup):
         if trace:
@@ -675,9 +697,7 @@ def main():
         gc.disable()
 
     # ---------------- timed region: K steps, inputs resident in HBM ----------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0 and os.environ.get('IMPFLOW_BENCH_NOSAMPLER', '') != '1':     # diagnostic switch: cost of the poller
-        sampler.start()
+    sampler.mark_begin()
     launches0 = pkg._cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     solves = 0

@@ -610,8 +610,9 @@ class BranchProgram(object):
             self._plan_ptr(P), mode, _cabi.ptr(rows), pre0, d1, d2, vp(wk.xa), vp(wk.xb), vp(wk.ga), vp(wk.gb),
             vp(wk.low_x), vp(wk.low_g), vp(wk.Ut), vp(wk.Vt), vp(wk.sample_sq), vp(wk.low_sq), vp(wk.partial),
             vp(wk.state), vp(wk.state_host), threshold, float(eps_scaled), _cabi.stream()), 'conv3_broyden')
+        best = wk.low_x.clone()         # first: the stream is empty after the solve, host work comes after the launch
         state = wk.host_state()
-        info = _b._result_dict(wk, state, (B, d), eps_scaled, threshold)
+        info = _b._result_dict(wk, state, (B, d), eps_scaled, threshold, result=best)
         info['result'] = self._from_rows(info['result'].view(M, P.c), meta)
         if ops.GEMM_PROFILE['on']:
             self._record_conv3(P, mode == 1, False, info['nstep'] + 1)

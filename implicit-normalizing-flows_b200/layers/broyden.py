@@ -63,10 +63,11 @@ def _workspace(B, d, T, device):
     return ws
 
 
-def _result_dict(ws, state, shape, eps_scaled, threshold):
-    """The reference's return dict (broyden.py:184-193)."""
+def _result_dict(ws, state, shape, eps_scaled, threshold, result=None):
+    """The reference's return dict (broyden.py:184-193).  `result`: a copy of ws.low_x the caller already took (the
+    copy is the first thing enqueued after a solve: the stream is empty at that point)."""
     nstep = int(state['nstep'])
-    return {'result': ws.low_x.clone().view(shape),
+    return {'result': (result if result is not None else ws.low_x.clone()).view(shape),
             'nstep': nstep,
             'tnstep': nstep,
             'lowest_step': int(state['lowest_step']),

@@ -270,10 +270,8 @@ class RootFind(Function):
             info = broyden(g, torch.zeros_like(z0), threshold=threshold, eps=eps, name='forward')
         RootFind.last_info = info
         if info['prot_break']:
-            z_est = RootFind.banach_find_root(nnet_z, nnet_x, z0, x, eps, 1000)
-        else:
-            z_est = info['result']
-        return z_est.clone().detach()
+            return RootFind.banach_find_root(nnet_z, nnet_x, z0, x, eps, 1000)
+        return info['result'].detach()          # already a private copy of the solver's best iterate
 
     @staticmethod
     def forward(ctx, nnet_z, nnet_x, z0, x, method, *args):
@@ -426,8 +424,10 @@ class imBlock(nn.Module):
             self._pre = self._predraw(z0) if logpx is not None else None
         z = RootFind.apply(self.nnet_z, self.nnet_x, z0, z0, 'broyden', self.eps_forward, self.threshold)
         self.solver_stats['fwd'] = RootFind.last_info
-        # re-attach: gradients reach the branch parameters through this expression (:227)
-        z = branch_apply(self.nnet_x, z0) - branch_apply(self.nnet_z, z.detach()) + z0
+        # re-attach: gradients reach the branch parameters through this expression (:227).  The z-branch evaluation is
+        # issued first: it launches kernels on an empty stream, the x-branch value is a memo hit (host work only)
+        fz = branch_apply(self.nnet_z, z.detach())
+        z = branch_apply(self.nnet_x, z0) - fz + z0
         if synced and versions != _twin_versions(self.nnet_x) + _twin_versions(self.nnet_z):
             synced = False          # the forward wrote a buffer of the live nets (scale, lazily shaped u / v)
         if not synced:
