@@ -609,6 +609,8 @@ def main():
         pkg._cabi.load().impflow_gemm_tc_set_pair(0)
     if os.environ.get('IMPFLOW_PDL', '') == '0':             # A/B: ordinary launches of the tile kernels
         pkg._cabi.load().impflow_set_pdl(0)
+    if os.environ.get('IMPFLOW_CHAIN_FUSE', '') in ('0', '1'):    # A/B: power-series epilogue writes the next term's input
+        pkg._cabi.load().impflow_conv3_set_chain_fuse(int(os.environ['IMPFLOW_CHAIN_FUSE']))
     if os.environ.get('IMPFLOW_SWEEP_MLP', '') in ('0', '1'):     # A/B: CUDA graphs of the MLP flows' batched sweeps
         pkg.branch_program.SWEEP_GRAPHS['mlp'] = os.environ['IMPFLOW_SWEEP_MLP'] == '1'
     if os.environ.get('IMPFLOW_SWEEP_GRAPHS', '') == '0':    # A/B: eager gradient sweeps instead of CUDA graphs

@@ -70,6 +70,7 @@ SIGNATURES = {
     'impflow_conv3_power_series': (_i, [_c_fp] * 6 + [_i, _c_fp, _c_fp, _c_fp, _c_fp]),
     'impflow_conv3_broyden_host_bytes': (ctypes.c_size_t, [_i]),
     'impflow_conv3_set_runahead': (_i, [_i]),
+    'impflow_conv3_set_chain_fuse': (_i, [_i]),
     'impflow_conv3_broyden': (_i, [_c_fp, _i] + [_c_fp] * 17 + [_i, _d, _c_fp]),
     'impflow_wgrad_set_slice_major': (_i, [_i]),
     'impflow_wgrad_tc_workspace_floats': (ctypes.c_size_t, [_ll, _i, _i]),

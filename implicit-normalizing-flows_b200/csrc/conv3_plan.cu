@@ -21,7 +21,7 @@ namespace impflow {
 static inline size_t pad64(size_t n) { return (n + 63) / 64 * 64; }
 
 struct Conv3Ws {
-  float *xin, *x0, *h1, *h2, *Y, *t_rows, *chain_a, *chain_b;
+  float *xin, *x0, *h1, *h2, *Y, *Y2, *t_rows, *chain_a, *chain_b;
   size_t total;
 };
 
@@ -38,6 +38,9 @@ static Conv3Ws carve(float* base, long long M, int c, int C, int k0) {
   w.h1 = take(2 * (size_t)M * C);
   w.h2 = take(2 * (size_t)M * C);
   w.Y = take((size_t)M * 9 * c * (size_t)(C % 128 == 0 ? C / 128 : 1));   // room for the chain23 partials
+  // second tap accumulator of the power-series chain on the tile kernel (its two channel halves are summed into a
+  // ZEROED accumulator: term k's epilogue zeroes the one term k + 1 accumulates into)
+  w.Y2 = take((k0 == 32 && 9 * c <= 32) ? (size_t)M * 9 * c : 0);
   w.t_rows = take((size_t)M * c);
   w.chain_a = take((size_t)M * c);
   w.chain_b = take((size_t)M * c);
@@ -163,6 +166,13 @@ struct Conv3Out {
   float* acc;           // chain mode: w
   float coeff;
   const int* gate;
+  // power-series chain: the result is also the input of the NEXT evaluation, so its im2col rows are written here
+  // (what a k_conv3_in launch would produce from `out`): fp32 rows, or tf32 hi / lo planes when next_lo is set
+  float* next_col;
+  float* next_lo;
+  int next_ld;
+  float* zero;          // tap accumulator of the next evaluation to clear (tile kernel), zero_n4 float4 groups
+  long long zero_n4;
 };
 
 __global__ void __launch_bounds__(256) k_conv3_out(int B, int H, int W, int C, Conv3Out a) {
@@ -206,6 +216,34 @@ __global__ void __launch_bounds__(256) k_conv3_out(int B, int H, int W, int C, C
       a.acc[i] = fmaf(val, a.coeff, a.acc[i]);
     }
     a.out[i] = r;
+    if (a.next_col != nullptr) {
+      // im2col of the next evaluation, scattered: X0[p - delta][tap][c] = r for every tap whose source pixel is p;
+      // the slots of THIS row whose source pixel lies outside the image are zero
+      float hi = r, lo = 0.f;
+      if (a.next_lo != nullptr) split_tf32_1(r, hi, lo);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int ty = yy - dy, tx = xx - dx;              // row that reads pixel p through `tap`
+        if (ty >= 0 && ty < H && tx >= 0 && tx < W) {
+          const long long slot = ((b * H + ty) * W + tx) * a.next_ld + tap * C + c;
+          a.next_col[slot] = hi;
+          if (a.next_lo != nullptr) a.next_lo[slot] = lo;
+        }
+        const int sy = yy + dy, sx = xx + dx;              // source pixel of this row's `tap`
+        if (sy < 0 || sy >= H || sx < 0 || sx >= W) {
+          const long long slot = p * a.next_ld + tap * C + c;
+          a.next_col[slot] = 0.f;
+          if (a.next_lo != nullptr) a.next_lo[slot] = 0.f;
+        }
+      }
+    }
+  }
+  if (a.zero != nullptr) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.zero_n4;
+         i += (long long)gridDim.x * blockDim.x)
+      reinterpret_cast<float4*>(a.zero)[i] = z;
   }
 }
 
@@ -280,16 +318,20 @@ static int conv3_chain_forward(const impflow_conv3_plan* p, const Conv3Ws& w, co
 }
 
 // Y = the transposed chain applied to v_rows (d1, d2 = act'(pre) of the two hidden layers).
+// skip_in: the im2col rows of v_rows (and, for the tile kernel, the cleared accumulator) were already produced by the
+// epilogue of the previous evaluation (power-series chain); Yt: tap accumulator to use (default w.Y)
 static int conv3_chain_vjp(const impflow_conv3_plan* p, const Conv3Ws& w, const float* d1, const float* d2,
-                           const float* v_rows, void* stream) {
+                           const float* v_rows, void* stream, bool skip_in = false, float* Yt = nullptr) {
   const long long M = (long long)p->B * p->H * p->W;
   const int N3 = 9 * p->c;
   cudaStream_t s = (cudaStream_t)stream;
+  float* const Y = Yt != nullptr ? Yt : w.Y;
   if (use_tile_kernel(p)) {
-    if (launch_in(p, v_rows, IMPFLOW_ACT_NONE, nullptr, w.x0, nullptr, 32, p->C > 256 ? w.Y : nullptr, M * N3, s))
+    if (!skip_in &&
+        launch_in(p, v_rows, IMPFLOW_ACT_NONE, nullptr, w.x0, nullptr, 32, p->C > 256 ? Y : nullptr, M * N3, s))
       return -1;
     return impflow_branch3_tc(w.x0, 32, p->W3b_hi, p->W3b_lo, p->W2b_hi, p->W2b_lo, p->W1b_hi, p->W1b_lo, nullptr,
-                              nullptr, d2, d1, nullptr, nullptr, w.Y, N3, M, p->C, N3, IMPFLOW_ACT_NONE, nullptr, nullptr,
+                              nullptr, d2, d1, nullptr, nullptr, Y, N3, M, p->C, N3, IMPFLOW_ACT_NONE, nullptr, nullptr,
                               stream);
   }
   float* x0_hi = w.x0;
@@ -298,7 +340,7 @@ static int conv3_chain_vjp(const impflow_conv3_plan* p, const Conv3Ws& w, const 
   float* t3_lo = w.h1 + (size_t)M * p->C;
   float* t2_hi = w.h2;
   float* t2_lo = w.h2 + (size_t)M * p->C;
-  if (launch_in(p, v_rows, IMPFLOW_ACT_NONE, nullptr, x0_hi, x0_lo, p->k0, nullptr, 0, s)) return -1;
+  if (!skip_in && launch_in(p, v_rows, IMPFLOW_ACT_NONE, nullptr, x0_hi, x0_lo, p->k0, nullptr, 0, s)) return -1;
   const bool a32 = use_chain23(p) && g_chain23_a32;     // dmul mode: pre_out receives acc * act'(d2)
   if (impflow_gemm_nt_tc(x0_hi, x0_lo, p->k0, p->W3b_hi, p->W3b_lo, p->k0, nullptr, a32 ? t3_hi : nullptr, nullptr, d2,
                          a32 ? nullptr : t3_hi, a32 ? nullptr : t3_lo, p->C, M, p->C, p->k0, IMPFLOW_ACT_MULTIPLIER,
@@ -341,6 +383,9 @@ static Conv3Out out_vjp(const impflow_conv3_plan* p, const Conv3Ws& w, const flo
   return a;
 }
 
+// power-series chain: the col2im epilogue of term k also writes the im2col rows of term k + 1 (one k_conv3_in launch
+// less per term); impflow_conv3_set_chain_fuse for A/B
+static int g_chain_fuse = 1;
 static int g_runahead = 2;     // iterations the host may enqueue beyond the last decision it has seen (0 = sync per iteration)
 
 }  // namespace impflow
@@ -397,10 +442,24 @@ extern "C" int impflow_conv3_power_series(const impflow_conv3_plan* plan, const 
   if (w_rows != nullptr && impflow_lincomb3(v_rows, 1.f, nullptr, 0.f, nullptr, 0.f, w_rows, nel, stream)) return -1;
   const float* cur = v_rows;
   float* bufs[2] = {w.chain_a, w.chain_b};
+  const bool tile = use_tile_kernel(plan);
+  const int N3 = 9 * plan->c;
+  const bool fuse = g_chain_fuse && ((M * N3) % 4 == 0) && (!tile || w.Y2 != nullptr);
   for (int k = 0; k < n; ++k) {
     float* nxt = bufs[k & 1];
-    if (conv3_chain_vjp(plan, w, d1, d2, cur, stream)) return -1;
+    float* Yk = (tile && fuse && (k & 1)) ? w.Y2 : w.Y;
+    if (conv3_chain_vjp(plan, w, d1, d2, cur, stream, fuse && k > 0, Yk)) return -1;
     Conv3Out a = out_vjp(plan, w, pre0, nxt);
+    a.col = Yk;
+    if (fuse && k + 1 < n) {        // this epilogue prepares the next evaluation's input
+      a.next_col = w.x0;
+      a.next_lo = tile ? nullptr : w.x0 + (size_t)M * plan->k0;
+      a.next_ld = tile ? 32 : plan->k0;
+      if (tile && plan->C > 256) {
+        a.zero = (k & 1) ? w.Y : w.Y2;
+        a.zero_n4 = (M * N3) >> 2;
+      }
+    }
     if (w_rows != nullptr) {        // w += c_k v^T J^k in the col2im epilogue (implicit_block.py:435)
       a.mode = OUT_CHAIN;
       a.acc = w_rows;
@@ -424,6 +483,12 @@ extern "C" int impflow_conv3_set_chain23(int on) {
 extern "C" int impflow_conv3_set_chain23_a32(int on) {
   const int prev = g_chain23_a32;
   g_chain23_a32 = on ? 1 : 0;
+  return prev;
+}
+
+extern "C" int impflow_conv3_set_chain_fuse(int on) {
+  const int prev = g_chain_fuse;
+  g_chain_fuse = on ? 1 : 0;
   return prev;
 }
 

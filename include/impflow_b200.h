@@ -382,6 +382,10 @@ int impflow_conv3_set_chain23_a32(int on);
 /* A/B switch: iterations enqueued ahead of the device's decision (0 = copy the state and synchronise the stream after
  * every iteration, the round-1 behaviour).  Returns the previous setting. */
 int impflow_conv3_set_runahead(int iterations);
+/* A/B switch: 1 (default) = in impflow_conv3_power_series the col2im epilogue of term k also writes the im2col rows
+ * (and clears the tap accumulator) of term k + 1, so every term but the first is two launches (tile kernel) instead
+ * of three; 0 = a k_conv3_in launch per term.  Same values either way.  Returns the previous setting. */
+int impflow_conv3_set_chain_fuse(int on);
 int impflow_conv3_broyden(const impflow_conv3_plan* plan, int mode, const float* rhs_rows, const float* pre0,
                           const float* d1, const float* d2, float* xa, float* xb, float* ga, float* gb, float* low_x,
                           float* low_g, float* Ut, float* Vt, float* sample_sq, float* low_sq, float* partial,

@@ -716,6 +716,9 @@ class EmulatedLib(object):
     def impflow_conv3_set_runahead(self, iterations):
         return 2
 
+    def impflow_conv3_set_chain_fuse(self, on):
+        return 1
+
     def impflow_conv3_broyden(self, plan, mode, rhs_rows, pre0, d1, d2, xa, xb, ga, gb, low_x, low_g, Ut, Vt, sample_sq,
                               low_sq, partial, state_dev, state_host, threshold, eps_scaled, stream):
         P = self._plan(plan)

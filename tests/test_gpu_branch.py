@@ -44,3 +44,47 @@ def test_fused3_matches_unfused_program():
             branch_program.FUSED3['on'] = True
     for a, b in zip(*outs):
         assert rel_err(a.cpu(), b.cpu()) < 4e-6
+
+
+@pytest.mark.parametrize('c,hw,width,lead', [(3, 8, 512, True), (3, 12, 256, False), (12, 8, 512, True),
+                                             (48, 4, 512, True), (5, 6, 128, False)])
+@pytest.mark.parametrize('n', [1, 2, 5])
+def test_power_series_chain_fused_epilogue(c, hw, width, lead, n):
+    """impflow_conv3_power_series with the col2im epilogue of term k also writing the im2col rows (and clearing the
+    tap accumulator) of term k + 1 against a k_conv3_in launch per term: Neumann sum and Hutchinson dots bit-identical
+    (tile kernel: c = 3, 5; layer-1 GEMM + k_chain23: c = 12, 48), with and without a leading activation."""
+    import torch
+    import impflow_b200 as pkg
+    from impflow_b200.branch_program import compile_branch
+    from tests.imblock_cases import build_conv_branch
+    torch.manual_seed(c * 100 + hw + n)
+    net = build_conv_branch(pkg.layers, c, width, 0.9, 1e-3, lead).cuda()
+    x = torch.randn(4, c, hw, hw, device='cuda')
+    with torch.no_grad():
+        net(x)
+    prog = compile_branch(net)
+    lib = pkg._cabi.load()
+    v = torch.randn_like(x)
+    coeffs = [(-1) ** k / (k + 1.0) for k in range(n)]
+    outs = []
+    for on in (1, 0):
+        was = lib.impflow_conv3_set_chain_fuse(on)
+        try:
+            with torch.no_grad():
+                _, saved = prog.forward_saved(x)
+                assert prog.native_plan(x) is not None
+                w = prog.neumann_chain(saved, v, coeffs)
+                dots = prog.hutchinson_series(saved, v, coeffs)
+            outs.append((w.clone(), dots.clone()))
+        finally:
+            lib.impflow_conv3_set_chain_fuse(was)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    # and against the chain of single vjp evaluations
+    with torch.no_grad():
+        _, saved = prog.forward_saved(x)
+        cur, ref = v, v.clone()
+        for k in range(n):
+            cur = prog.vjp(cur, saved)
+            ref = ref + coeffs[k] * cur
+    assert float((outs[0][0] - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
