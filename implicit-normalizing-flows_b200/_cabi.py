@@ -30,6 +30,7 @@ SIGNATURES = {
     'impflow_mlp_solver_partial_doubles': (ctypes.c_size_t, []),
     'impflow_mlp_broyden_solve': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _i, _i, _c_fp] + [_c_fp] * 12 + [_i, _i, _d, _c_fp]),
     'impflow_mlp_broyden_solve_vjp': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _i] + [_c_fp] * 12 + [_i, _i, _d, _c_fp]),
+    'impflow_mlp_series': (_i, [_c_fp] * 6 + [_i, _i, _i, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _c_fp]),
     'impflow_act_mul': (_i, [_c_fp, _c_fp, _c_fp, _ll, _i, _i, _c_fp, _c_fp]),
     'impflow_act_split': (_i, [_c_fp, _c_fp, _c_fp, _ll, _i, _i, _c_fp, _c_fp]),
     'impflow_reduce_workspace_floats': (ctypes.c_size_t, [_ll]),

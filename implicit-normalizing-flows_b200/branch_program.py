@@ -42,7 +42,7 @@ from . import _cabi, ops
 from .layers.base.activations import ReLU, Sin, Swish
 from .layers.base.mixed_lipschitz import InducedNormConv2d, InducedNormLinear, sigma_of
 
-__all__ = ['BranchProgram', 'compile_branch', 'FUSED3', 'CONV3_NATIVE', 'MEMO', 'SWEEP_GRAPHS']
+__all__ = ['BranchProgram', 'compile_branch', 'FUSED3', 'CONV3_NATIVE', 'MEMO', 'SWEEP_GRAPHS', 'MLP_SERIES']
 
 # One-launch tile kernel for the 3-layer conv branch (csrc/branch_fused.cu); off = three GEMM launches.
 FUSED3 = {'on': True}
@@ -67,6 +67,7 @@ MEMO = {'on': True}
 # 'mlp': graphs of the MLP flows' batched sweeps, one per distinct n-fold row count (opt-in: a tabular step drops from
 # 259 to ~195 ms once every (program, n) pair has been captured, but each capture costs ~28 ms and a 20-block flow
 # needs ~200 of them, which only pays off over a training run, not over a 20-step benchmark)
+MLP_SERIES = {'on': True}      # one-launch vjp / tangent chains of the basic estimator's training path (MLP branches)
 SWEEP_GRAPHS = {'on': True, 'max_rows': 16384, 'warmup': 1, 'mlp': False}
 
 _conv3_ws = {}      # (device index, stream) -> workspace tensor shared by every plan used on that stream
@@ -304,6 +305,20 @@ class BranchProgram(object):
         if any(t.shape != (saved.M, dims[i]) for i, t in enumerate(dmul) if t is not None):
             return None
         return [w.fwd for w in ws], [w.fwd.stride(0) for w in ws], dmul, dims
+
+    def mlp_series_spec(self, saved):
+        """Arguments of the one-launch MLP power series (impflow_mlp_series) at the point of `saved`, or None if the
+        branch does not qualify (same conditions as the persistent solver)."""
+        vs = self.mlp_vjp_spec(saved) if MLP_SERIES['on'] else None
+        if vs is None:
+            return None
+        W, ldw, dmul, dims = vs
+        ws = self._prep(saved.M)
+        key = ('mlp', self._key)
+        cached = getattr(self, '_mlp_spec', None)
+        if cached is None or cached[0] != key:
+            cached = self._mlp_spec = (key, [w.fwd[:, :w.cin].t().contiguous() for w in ws])
+        return W, ldw, cached[1], dmul, dims
 
     # ---------------------------------------------------------------- plumbing
     def _to_rows(self, x):

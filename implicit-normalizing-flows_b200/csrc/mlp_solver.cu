@@ -315,6 +315,83 @@ k_mlp_broyden(MlpDesc net, const float* __restrict__ x_embed, float* za, float* 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Power series of a small-d MLP branch in ONE launch (north-star kernel (c) for the MLP flows): the training path of
+// the basic estimator (implicit_block.py:418-426 with create_graph=True) needs, at one saved point and for one probe v,
+//     left vectors   l_k = (J^T)^k v, k = 1..n      (vjp chain)          S = sum_k c_k <l_k, v>
+//     right vectors  r_m = J^m v,     m = 1..n-1    (tangent chain)
+//     combinations   w_m = sum_{a=0}^{n-1-m} c_{a+m} l_a, m = 0..n-1     (left factors of the n bilinear-form gradients)
+// Host-driven this is ~60 launches per call (5 GEMMs + 4 multiplier passes per chain step, n row dots, n(n+1)/2 linear
+// combinations, 2 concatenations).  Here a CTA takes 16 samples through both chains with the activations in shared
+// memory (mlp_eval in its linear-chain mode: no bias, no activation, the saved act' multipliers on the layer outputs).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kSeriesMaxTerms = 32;
+struct SeriesCoeffs {
+  float c[kSeriesMaxTerms];
+};
+
+__global__ void __launch_bounds__(kMlpThreads)
+k_mlp_series(MlpDesc vjp, MlpDesc tan, SeriesCoeffs co, const float* __restrict__ v, float* Ls, float* Rs,
+             float* __restrict__ Wm, float* __restrict__ S, int B, int n) {
+  __shared__ __align__(16) float bufA[kTile * kMaxWidth];
+  __shared__ __align__(16) float bufB[kTile * kMaxWidth];
+  __shared__ float vt[kTile * 128];
+  __shared__ float sacc[kTile];
+  const int d = vjp.dims[0];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long plane = (long long)B * d;
+  for (int s0 = blockIdx.x * kTile; s0 < B; s0 += gridDim.x * kTile) {
+    for (int i = tid; i < kTile * d; i += kMlpThreads) {
+      const int s = i / d, c = i % d;
+      const float x = (s0 + s < B) ? v[(long long)(s0 + s) * d + c] : 0.f;
+      vt[s * 128 + c] = x;
+      if (s0 + s < B) {
+        Ls[(long long)(s0 + s) * d + c] = x;      // l_0 = r_0 = v
+        Rs[(long long)(s0 + s) * d + c] = x;
+      }
+    }
+    if (tid < kTile) sacc[tid] = 0.f;
+    __syncthreads();
+    // ---- vjp chain: l_k = J^T l_{k-1}, S += c_k <l_k, v> ----
+    for (int k = 1; k <= n; ++k) {
+      const float* cur = mlp_eval(vjp, Ls + (k - 1) * plane, s0, B, bufA, bufB);
+      for (int i = tid; i < kTile * d; i += kMlpThreads) {
+        const int s = i / d, c = i % d;
+        if (s0 + s < B) Ls[k * plane + (long long)(s0 + s) * d + c] = cur[s * kMaxWidth + c];
+      }
+      for (int s = warp; s < kTile; s += kMlpWarps) {
+        float acc = 0.f;
+        for (int c = lane; c < d; c += 32) acc += cur[s * kMaxWidth + c] * vt[s * 128 + c];
+        acc = warp_sum(acc);
+        if (lane == 0) sacc[s] = fmaf(co.c[k - 1], acc, sacc[s]);
+      }
+      __syncthreads();      // l_k is in global memory (visible to this block) before the next step reads it
+    }
+    // ---- tangent chain: r_m = J r_{m-1} ----
+    for (int m = 1; m < n; ++m) {
+      const float* cur = mlp_eval(tan, Rs + (m - 1) * plane, s0, B, bufA, bufB);
+      for (int i = tid; i < kTile * d; i += kMlpThreads) {
+        const int s = i / d, c = i % d;
+        if (s0 + s < B) Rs[m * plane + (long long)(s0 + s) * d + c] = cur[s * kMaxWidth + c];
+      }
+      __syncthreads();
+    }
+    // ---- w_m = sum_a c_{a+m} l_a (a ascending, as the host loop of linear combinations did) ----
+    for (int i = tid; i < n * kTile * d; i += kMlpThreads) {
+      const int m = i / (kTile * d), rest = i % (kTile * d);
+      const int s = rest / d, c = rest % d;
+      if (s0 + s >= B) continue;
+      const long long off = (long long)(s0 + s) * d + c;
+      float w = co.c[m] * Ls[off];
+      for (int a = 1; a < n - m; ++a) w = fmaf(co.c[a + m], Ls[a * plane + off], w);
+      Wm[m * plane + off] = w;
+    }
+    if (tid < kTile && s0 + tid < B) S[s0 + tid] = sacc[tid];
+    __syncthreads();
+  }
+}
+
 }  // namespace impflow
 
 namespace impflow {
@@ -433,3 +510,47 @@ int launch_mlp_solver(MlpDesc net, const float* x_embed, float* za, float* ga, f
   return check_launch("k_mlp_broyden");
 }
 }  // namespace impflow
+
+/* One-launch power series of a small-d MLP branch at a saved point (see k_mlp_series):
+ *   W[l], ldw[l] : effective weight of layer l, [dims[l+1]][ldw[l]] row-major (vjp chain, as in ..._solve_vjp)
+ *   Wt[l]        : its transpose [dims[l]][dims[l+1]] contiguous (tangent chain, as in impflow_mlp_broyden_solve)
+ *   dmul[l]      : act'(pre-activation in front of layer l), (B, dims[l]); dmul[0] must be NULL
+ *   v            : probe (B, d); coeffs: n HOST doubles c_1..c_n
+ *   Ls (n+1, B, d): l_0 = v, l_k = (J^T)^k v;  Rs (n, B, d): r_0 = v, r_m = J^m v;  Wm (n, B, d): w_m;  S (B) */
+extern "C" int impflow_mlp_series(const float* v, const float* const* W, const int* ldw, const float* const* Wt,
+                                  const float* const* dmul, const int* dims, int L, int B, int n, const double* coeffs,
+                                  float* Ls, float* Rs, float* Wm, float* S, void* stream) {
+  IMPFLOW_REQUIRE(L >= 1 && L <= kMaxLayers, "mlp_series: %d layers not in [1,%d]", L, kMaxLayers);
+  IMPFLOW_REQUIRE(n >= 1 && n <= kSeriesMaxTerms, "mlp_series: %d terms not in [1,%d]", n, kSeriesMaxTerms);
+  IMPFLOW_REQUIRE(dims[0] == dims[L] && dims[0] <= 128, "mlp_series: needs d_in == d_out <= 128");
+  IMPFLOW_REQUIRE(dmul[0] == nullptr, "mlp_series: no activation in front of the first layer");
+  IMPFLOW_REQUIRE(B >= 1, "mlp_series: empty batch");
+  MlpDesc vjp, tan;
+  memset(&vjp, 0, sizeof(vjp));
+  memset(&tan, 0, sizeof(tan));
+  vjp.L = tan.L = L;
+  for (int l = 0; l <= L; ++l) {
+    IMPFLOW_REQUIRE(dims[l] >= 1 && dims[l] <= kMaxWidth, "mlp_series: width %d not in [1,%d]", dims[l], kMaxWidth);
+    vjp.dims[l] = dims[L - l];          // the vjp chain runs from the output side
+    tan.dims[l] = dims[l];
+  }
+  for (int j = 0; j < L; ++j) {
+    const int l = L - 1 - j;
+    IMPFLOW_REQUIRE(ldw[l] >= dims[l], "mlp_series: row stride %d < %d", ldw[l], dims[l]);
+    vjp.Wt[j] = W[l];
+    vjp.ld[j] = ldw[l];
+    vjp.dmul[j] = dmul[l];
+    tan.Wt[j] = Wt[j];
+    tan.ld[j] = dims[j + 1];
+    tan.dmul[j] = (j + 1 < L) ? dmul[j + 1] : nullptr;
+  }
+  vjp.act_kind = tan.act_kind = IMPFLOW_ACT_NONE;
+  vjp.mode = tan.mode = 1;
+  SeriesCoeffs co;
+  memset(&co, 0, sizeof(co));
+  for (int k = 0; k < n; ++k) co.c[k] = (float)coeffs[k];
+  const int n_tiles = (B + kTile - 1) / kTile;
+  const int grid = n_tiles < 148 * 4 ? n_tiles : 148 * 4;
+  k_mlp_series<<<grid, kMlpThreads, 0, (cudaStream_t)stream>>>(vjp, tan, co, v, Ls, Rs, Wm, S, B, n);
+  return check_launch("k_mlp_series");
+}

@@ -691,6 +691,14 @@ class _GraphFreeBasic(Function):
     def forward(ctx, x, prog, vareps, coeffs, *params):
         xd = x.detach()
         _, saved = prog.forward_saved(xd)
+        ctx.series = None
+        spec = prog.mlp_series_spec(saved) if (xd.dim() == 2 and 1 <= len(coeffs) <= 32) else None
+        if spec is not None:
+            # small-d MLP branch: both chains, the combinations and the estimate in ONE launch (k_mlp_series)
+            out, _, Rs, Wm = ops.mlp_series(spec, vareps, coeffs)
+            ctx.series = (Rs, Wm)
+            ctx.prog, ctx.saved_fwd, ctx.ls, ctx.coeffs = prog, saved, None, coeffs
+            return out
         ls = [vareps]
         out = torch.zeros(xd.shape[0], device=xd.device, dtype=torch.float32)
         for c in coeffs:
@@ -704,8 +712,19 @@ class _GraphFreeBasic(Function):
     def backward(ctx, gout):
         prog, saved, ls, coeffs = ctx.prog, ctx.saved_fwd, ctx.ls, ctx.coeffs
         n = len(coeffs)
-        B = ls[0].shape[0]
         seed = gout.reshape(-1).contiguous()
+        if ctx.series is not None:
+            Rs, Wm = ctx.series             # (n, B, d) each: r_m and w_m from the forward's launch
+            B, d = Rs.shape[1], Rs.shape[2]
+            if n > 1:
+                saved_n = prog.tile_saved(saved, n)
+                _, gx_n, gparams = prog.neumann(saved_n, Wm.view(n * B, d), Rs.view(n * B, d), seed_scale=seed.repeat(n))
+                gx = gx_n.reshape(n, B, d).sum(0)
+            else:
+                _, gx, gparams = prog.neumann(saved, Wm[0], Rs[0], seed_scale=seed)
+            ctx.series = ctx.saved_fwd = None
+            return (gx, None, None, None) + tuple(sink_grads(prog.params, gparams))
+        B = ls[0].shape[0]
         # right vectors r_m = J^m v (n - 1 tangent sweeps) and left combinations w_m = sum_a c_{a+m+1} l_a
         rs = [ls[0]]
         for _ in range(n - 1):

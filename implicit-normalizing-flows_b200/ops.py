@@ -8,6 +8,8 @@ Two kinds of entry points:
     expressed with the same primitives, so the graph can be differentiated repeatedly (the
     log-det estimators differentiate through vjps: implicit_block.py:386-388, 418-438).
 """
+import ctypes
+
 import torch
 
 from . import _cabi
@@ -369,6 +371,32 @@ def wgrad_gemm(G, A, G_split=None, A_split=None):
     _cabi.check(lib.impflow_wgrad_simt(_cabi.ptr(G), G.stride(0), _cabi.ptr(A), A.stride(0), _cabi.ptr(out), N2, M,
                                        N1, N2, _cabi.ptr(ws), _cabi.stream()), 'wgrad_simt')
     return out
+
+
+def mlp_series(spec, v, coeffs):
+    """Left / right vectors, their combinations and the estimate of the basic power series of a small-d MLP branch in
+    one launch (csrc/mlp_solver.cu k_mlp_series).  spec: BranchProgram.mlp_series_spec(saved).  Returns
+    (S (B,), Ls (n+1, B, d), Rs (n, B, d), Wm (n, B, d))."""
+    W, ldw, Wt, dmul, dims = spec
+    lib = _lib()
+    v2 = v.reshape(v.shape[0], -1).contiguous()
+    B, d = v2.shape
+    n, L = len(coeffs), len(W)
+    dev = v2.device
+    Ls = torch.empty(n + 1, B, d, device=dev, dtype=torch.float32)
+    Rs = torch.empty(n, B, d, device=dev, dtype=torch.float32)
+    Wm = torch.empty(n, B, d, device=dev, dtype=torch.float32)
+    S = torch.empty(B, device=dev, dtype=torch.float32)
+    w_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in W])
+    ld_arr = (ctypes.c_int * L)(*[int(t) for t in ldw])
+    wt_arr = (ctypes.c_void_p * L)(*[w.data_ptr() for w in Wt])
+    dm_arr = (ctypes.c_void_p * L)(*[(t.data_ptr() if t is not None else None) for t in dmul])
+    dims_arr = (ctypes.c_int * (L + 1))(*dims)
+    c_arr = (ctypes.c_double * n)(*[float(c) for c in coeffs])
+    _cabi.check(lib.impflow_mlp_series(_cabi.ptr(v2), w_arr, ld_arr, wt_arr, dm_arr, dims_arr, L, B, n, c_arr,
+                                       _cabi.ptr(Ls), _cabi.ptr(Rs), _cabi.ptr(Wm), _cabi.ptr(S), _cabi.stream()),
+                'mlp_series')
+    return S, Ls, Rs, Wm
 
 
 def col2im3x3(col, B, H, W, C, bias=None, act_kind=ACT_NONE, beta_sp=None, want_pre=True, want_act=False,

@@ -130,6 +130,17 @@ int impflow_mlp_broyden_solve_vjp(const float* rhs, const float* const* W, const
                                   float* low_g, float* Ut, float* Vt, float* sample_sq, float* low_sq, double* partial,
                                   impflow_broyden_state* state, int B, int threshold, double eps_scaled, void* stream);
 
+/* One-launch power series of a small-d MLP branch at a saved point and for one probe v — the training path of the
+ * basic estimator (implicit_block.py:418-426 with create_graph=True, taken graph-free):
+ *     Ls (n+1, B, d): l_0 = v, l_k = (J^T)^k v      Rs (n, B, d): r_0 = v, r_m = J^m v
+ *     S (B) = sum_k c_k <l_k, v>                    Wm (n, B, d): w_m = sum_{a=0}^{n-1-m} c_{a+m} l_a
+ *   W[l], ldw[l]: effective weight of layer l, [dims[l+1]][ldw[l]] row-major;  Wt[l]: its transpose
+ *   [dims[l]][dims[l+1]] contiguous;  dmul[l]: act'(pre-activation in front of layer l), (B, dims[l]), dmul[0] NULL
+ *   (HOST arrays of L DEVICE pointers);  coeffs: n HOST doubles, n <= 32.  Same limits as the persistent solver. */
+int impflow_mlp_series(const float* v, const float* const* W, const int* ldw, const float* const* Wt,
+                       const float* const* dmul, const int* dims, int L, int B, int n, const double* coeffs,
+                       float* Ls, float* Rs, float* Wm, float* S, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Elementwise / reductions on the path
  * ------------------------------------------------------------------------------------------ */

@@ -309,6 +309,54 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_mlp_series(self, v, W, ldw, Wt, dmul, dims, L, B, n, coeffs, Ls, Rs, Wm, S, stream):
+        dims = [int(t) for t in dims]
+        d = dims[0]
+        Ws = []
+        for l in range(L):
+            ld = int(ldw[l])
+            full = np.lib.stride_tricks.as_strided(_f32(W[l], (dims[l + 1] - 1) * ld + dims[l]),
+                                                   shape=(dims[l + 1], dims[l]), strides=(4 * ld, 4))
+            Ws.append(np.array(full))
+        Ds = [(_f32(dmul[l], B * dims[l]).reshape(B, dims[l]) if dmul[l] else None) for l in range(L)]
+        c = [float(coeffs[k]) for k in range(n)]
+        v0 = _f32(v, B * d).reshape(B, d)
+
+        def vjp(h):
+            for l in range(L - 1, -1, -1):
+                h = (h @ Ws[l]).astype(np.float32)
+                if Ds[l] is not None:
+                    h = h * Ds[l]
+            return h
+
+        def tan(h):
+            for l in range(L):
+                h = (h @ Ws[l].T).astype(np.float32)
+                if l + 1 < L:
+                    h = h * Ds[l + 1]
+            return h
+
+        ls, rs = [v0.copy()], [v0.copy()]
+        for _ in range(n):
+            ls.append(vjp(ls[-1]))
+        for _ in range(n - 1):
+            rs.append(tan(rs[-1]))
+        _f32(Ls, (n + 1) * B * d)[:] = np.stack(ls).ravel()
+        _f32(Rs, n * B * d)[:] = np.stack(rs).ravel()
+        s_out = np.zeros(B, np.float32)
+        for k in range(1, n + 1):
+            s_out += np.float32(c[k - 1]) * (ls[k] * v0).sum(1).astype(np.float32)
+        _f32(S, B)[:] = s_out
+        wm = []
+        for m in range(n):
+            w = np.float32(c[m]) * ls[0]
+            for a in range(1, n - m):
+                w = w + np.float32(c[a + m]) * ls[a]
+            wm.append(w.astype(np.float32))
+        _f32(Wm, n * B * d)[:] = np.stack(wm).ravel()
+        self.launches += 1
+        return 0
+
     # ---- elementwise (csrc/elementwise.cu) ----
     def impflow_act_mul(self, x, g, out, n, kind, order, beta_sp, stream):
         xv, gv, ov = _f32(x, n), _f32(g, n), _f32(out, n)

@@ -88,3 +88,52 @@ def test_power_series_chain_fused_epilogue(c, hw, width, lead, n):
             cur = prog.vjp(cur, saved)
             ref = ref + coeffs[k] * cur
     assert float((outs[0][0] - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('B,d,hidden,nh,act,n', [(1000, 6, 128, 4, 'sin', 4), (37, 43, 64, 2, 'swish', 3),
+                                                 (5, 2, 16, 1, 'relu', 1), (130, 63, 128, 4, 'sin', 7)])
+def test_mlp_series_one_launch(B, d, hidden, nh, act, n):
+    """k_mlp_series (left / right vectors, their combinations and the estimate of the basic power series in one
+    launch) against the host-driven chains of fused vjp / tangent evaluations it replaces."""
+    import torch
+    import impflow_b200 as pkg
+    from impflow_b200.branch_program import compile_branch
+    L = pkg.layers
+    torch.manual_seed(B + d + n)
+    acts = {'sin': L.base.Sin, 'swish': L.base.Swish, 'relu': L.base.ReLU}
+    dims = [d] + [hidden] * nh + [d]
+    mods = []
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        if i > 0:
+            mods.append(acts[act]())
+        mods.append(L.base.get_linear(a, b, coeff=0.9, n_iterations=None, atol=1e-3, rtol=1e-3, domain=2, codomain=2))
+    net = torch.nn.Sequential(*mods)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() > 1:
+                p.mul_(3.0)
+    net = net.cuda()
+    prog = compile_branch(net)
+    x = torch.randn(B, d, device='cuda')
+    v = torch.randn(B, d, device='cuda')
+    coeffs = [(-1) ** k / (k + 1.0) * (1.0 + 0.1 * k) for k in range(n)]
+    with torch.no_grad():
+        _, saved = prog.forward_saved(x)
+        spec = prog.mlp_series_spec(saved)
+        assert spec is not None
+        S, Ls, Rs, Wm = pkg.ops.mlp_series(spec, v, coeffs)
+        ls, rs = [v], [v]
+        S_ref = torch.zeros(B, device='cuda')
+        for k in range(n):
+            ls.append(prog.vjp(ls[-1], saved))
+            S_ref += coeffs[k] * (ls[-1] * v).sum(1)
+        for _ in range(n - 1):
+            rs.append(prog.tangent(saved, rs[-1]))
+        close = lambda a, b: float((a - b).abs().max()) <= 2e-5 * max(float(b.abs().max()), 1e-6)
+        for k in range(n + 1):
+            assert close(Ls[k], ls[k]), k
+        for m in range(n):
+            assert close(Rs[m], rs[m]), m
+            w = sum(coeffs[a + m] * ls[a] for a in range(n - m))
+            assert close(Wm[m], w), m
+        assert close(S, S_ref)
