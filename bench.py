@@ -155,7 +155,7 @@ def update_lipschitz(pkg, model, n_iterations=None):
 
 
 class ClockSampler(object):
-    """`nvidia-smi -lms 200` next to the benchmark.  The process is started BEFORE the warm-up steps: its start-up (NVML
+    """`nvidia-smi -lms 400` next to the benchmark.  The process is started BEFORE the warm-up steps: its start-up (NVML
     initialisation) holds driver locks for ~100 ms, which used to land in the first timed steps (per_step_ms showed
     150-300 ms there in one run out of three); only the samples taken between mark_begin() and stop() — the timed region —
     are reported."""
@@ -176,7 +176,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '400'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

@@ -64,11 +64,12 @@ MEMO = {'on': True}
 # conv branches with at most max_rows pixel rows (B=64: the deepest CIFAR scale; smaller per-GPU batches, i.e. strong
 # scaling: more of them), captured after `warmup` eager calls.  Measured (bench.py, e2e ms/step, B200): B=64 71.6 ->
 # 69.6 (max_rows 8192; 20000: 70.9), B=16 46.8 -> 38.0.
-# 'mlp': graphs of the MLP flows' batched sweeps, one per distinct n-fold row count (opt-in: a tabular step drops from
-# 259 to ~195 ms once every (program, n) pair has been captured, but each capture costs ~28 ms and a 20-block flow
-# needs ~200 of them, which only pays off over a training run, not over a 20-step benchmark)
+# 'mlp': graphs of the MLP flows' sweeps too.  The basic estimator's n bilinear-form gradients then run as n replays of
+# ONE graph over B rows (layers/implicit_block.py _GraphFreeBasic.backward) instead of one sweep over an n-fold batch,
+# whose row count follows the roulette draw and would need a graph per distinct n (~200 captures of ~28 ms for a
+# 20-block flow); with one graph per program and sweep kind the 80 captures fall into the first two steps.
 MLP_SERIES = {'on': True}      # one-launch vjp / tangent chains of the basic estimator's training path (MLP branches)
-SWEEP_GRAPHS = {'on': True, 'max_rows': 16384, 'warmup': 1, 'mlp': False}
+SWEEP_GRAPHS = {'on': True, 'max_rows': 16384, 'warmup': 1, 'mlp': True}
 
 _conv3_ws = {}      # (device index, stream) -> workspace tensor shared by every plan used on that stream
 
@@ -882,6 +883,10 @@ class BranchProgram(object):
             return False
         return (SWEEP_GRAPHS['on'] and like.is_cuda and saved.M <= SWEEP_GRAPHS['max_rows']
                 and not torch.cuda.is_current_stream_capturing())
+
+    def sweep_graphable(self, saved, like):
+        """Would neumann() / backward_full() at this saved forward replay a CUDA graph?"""
+        return self._graphable(saved, like)
 
     def _dynamic_inputs(self, saved, vecs):
         ws = self._prep(saved.M)

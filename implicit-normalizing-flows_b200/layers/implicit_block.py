@@ -716,7 +716,20 @@ class _GraphFreeBasic(Function):
         if ctx.series is not None:
             Rs, Wm = ctx.series             # (n, B, d) each: r_m and w_m from the forward's launch
             B, d = Rs.shape[1], Rs.shape[2]
-            if n > 1:
+            if n > 1 and prog.sweep_graphable(saved, Rs):
+                # CUDA-graph mode of the MLP flows: the n bilinear-form gradients as n replays of ONE graph over B rows
+                # (an n-fold batch would need a graph per distinct n, i.e. per roulette draw)
+                gx, gparams = None, None
+                for m in range(n):
+                    _, gx_m, gp_m = prog.neumann(saved, Wm[m], Rs[m], seed_scale=seed)
+                    if gx is None:
+                        gx, gparams = gx_m, list(gp_m)
+                    else:
+                        gx = gx + gx_m
+                        live = [(a, b) for a, b in zip(gparams, gp_m) if a is not None and b is not None]
+                        if live:
+                            torch._foreach_add_([a for a, _ in live], [b for _, b in live])
+            elif n > 1:
                 saved_n = prog.tile_saved(saved, n)
                 _, gx_n, gparams = prog.neumann(saved_n, Wm.view(n * B, d), Rs.view(n * B, d), seed_scale=seed.repeat(n))
                 gx = gx_n.reshape(n, B, d).sum(0)

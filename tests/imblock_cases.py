@@ -840,7 +840,7 @@ def case_sweep_graphs_mlp_match_eager():
                     gx2, gp2 = prog.backward_full(saved, w[:B].contiguous())
                     sink.extend([S, gx, gx2] + [g for g in gp if g is not None] + [g for g in gp2 if g is not None])
                 finally:
-                    bp.SWEEP_GRAPHS['on'], bp.SWEEP_GRAPHS['mlp'] = True, False
+                    bp.SWEEP_GRAPHS['on'], bp.SWEEP_GRAPHS['mlp'] = True, True
             assert len(got) == len(want)
             for a, b in zip(got, want):
                 scale = max(float(b.abs().max()), 1e-30)
