@@ -513,6 +513,11 @@ class imBlock(nn.Module):
         pre, self._pre = getattr(self, '_pre', None), None
         with torch.enable_grad():
             if (self.brute_force or not self.training) and (x.ndimension() == 2 and x.shape[1] <= 10):
+                px, pz = _program(self.nnet_x), _program(self.nnet_z)
+                if GRAPH_FREE_BRUTE['on'] and px is not None and pz is not None:
+                    # graph-free: Jacobian columns from d tangent sweeps, the gradient from d bilinear-form sweeps
+                    return (_GraphFreeBruteForce.apply(x, px, *px.params) -
+                            _GraphFreeBruteForce.apply(z, pz, *pz.params)).view(-1, 1)
                 x = x.requires_grad_(True)
                 z = z.requires_grad_(True)
                 Jx = batch_jacobian(x + self.nnet_x(x), x)
@@ -671,6 +676,50 @@ class MemoryEfficientLogDetEstimator(torch.autograd.Function):
             grad_x = next(scaled)
             grad_params = tuple(sink_grads(ctx.g_params, [None if m else next(scaled) for m in ctx.none_mask]))
         return (None, None, grad_x, None, None, None, None, None) + grad_params
+
+
+GRAPH_FREE_BRUTE = {'on': True}     # brute-force log-det (d <= 10) without the autograd double backward
+
+
+class _GraphFreeBruteForce(Function):
+    """logdet(I + J(x)) of a small-d branch (implicit_block.py:249-260) WITH its gradient, graph-free.  The reference
+    assembles J from d autograd passes with create_graph=True and differentiates torch.logdet through them.  Here:
+        forward : column j of J = J e_j from one tangent sweep (d sweeps), logdet(I + J) by the library LU on (B, d, d)
+        backward: d logdet = tr((I + J)^-1 dJ) = sum_j a_j^T (dJ) e_j with a_j = row j of (I + J)^-1: d bilinear-form
+                  gradients at the saved point (BranchProgram.neumann), seeded with the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, x, prog, *params):
+        xd = x.detach()
+        B, d = xd.shape
+        _, saved = prog.forward_saved(xd)
+        eye = torch.eye(d, device=xd.device, dtype=xd.dtype)
+        cols = [prog.tangent(saved, eye[j].expand(B, d).contiguous()) for j in range(d)]
+        M = torch.stack(cols, 2) + eye                    # M[b, i, j] = delta_ij + d g_i / d x_j
+        ctx.prog, ctx.saved_fwd, ctx.M = prog, saved, M
+        return torch.logdet(M)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        prog, saved, M = ctx.prog, ctx.saved_fwd, ctx.M
+        B, d = M.shape[0], M.shape[1]
+        Minv = torch.linalg.inv(M)                        # (B, d, d), d <= 10
+        eye = torch.eye(d, device=M.device, dtype=M.dtype)
+        seed = gout.reshape(-1).contiguous()
+        gx, gparams = None, None
+        for j in range(d):
+            w_j = Minv[:, j, :].contiguous()              # row j of the inverse
+            _, gx_j, gp_j = prog.neumann(saved, w_j, eye[j].expand(B, d).contiguous(), seed_scale=seed)
+            if gx is None:
+                gx, gparams = gx_j, list(gp_j)
+            else:
+                gx = gx + gx_j
+                live = [(a, b) for a, b in zip(gparams, gp_j) if a is not None and b is not None]
+                if live:
+                    torch._foreach_add_([a for a, _ in live], [b for _, b in live])
+        ctx.saved_fwd = ctx.M = None
+        return (gx, None) + tuple(sink_grads(prog.params, gparams))
 
 
 GRAPH_FREE_BASIC = {'on': True}     # hand-derived training gradient of the basic estimator (off = autograd double backward)
