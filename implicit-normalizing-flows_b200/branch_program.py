@@ -68,6 +68,7 @@ MEMO = {'on': True}
 # ONE graph over B rows (layers/implicit_block.py _GraphFreeBasic.backward) instead of one sweep over an n-fold batch,
 # whose row count follows the roulette draw and would need a graph per distinct n (~200 captures of ~28 ms for a
 # 20-block flow); with one graph per program and sweep kind the 80 captures fall into the first two steps.
+TC_MIN_FLOPS = {'program': 2.5e8}      # smallest GEMM a branch program sends to the tcgen05 kernel in 'auto' mode
 MLP_SERIES = {'on': True}      # one-launch vjp / tangent chains of the basic estimator's training path (MLP branches)
 SWEEP_GRAPHS = {'on': True, 'max_rows': 16384, 'warmup': 1, 'mlp': True}
 
@@ -212,6 +213,11 @@ class BranchProgram(object):
             return False
         if mode == 'tc':
             return True
+        # below ~0.25 GFLOP a tcgen05 launch is all fill / drain (21 us for the 33 MFLOP MLP layers of the tabular flows
+        # against 6 us on the CUDA cores, which are exact fp32 as well)
+        # (MLP programs only: a conv branch takes the native tile-kernel plan, which needs every layer on tensor-core planes)
+        if self.is_linear and 2.0 * M * N * K < TC_MIN_FLOPS['program']:
+            return False
         return M >= 64 and N >= 8 and K >= 32
 
     def _prep(self, M, meta=None):

@@ -103,11 +103,12 @@ k_gemm_nt(const float* __restrict__ A, long long lda, const float* __restrict__ 
 //   C[m,n] = sum_k A[m*sAm + k*sAk] * B[n*sBn + k*sBk] (+ bias[n])
 // so that A B, A^T B, A B^T and A^T B^T all run without materialising a transpose (the derivative of a GEMM
 // is a GEMM with transposed operands; with double backward the transposes used to be 25 % of all launches).
-template <int BM>      // rows per CTA: 64, or 32 / 16 when the problem has few row tiles (more CTAs in flight)
-__global__ void __launch_bounds__(256)
+template <int BM, bool EP = false>      // rows per CTA: 64, or 32 / 16 when the problem has few row tiles (more CTAs in flight)
+__global__ void __launch_bounds__(256)                      // EP: the fused branch epilogue of k_gemm_nt instead of (+ bias)
 k_gemm_strided(const float* __restrict__ A, long long sAm, long long sAk, const float* __restrict__ Bm, long long sBn,
                long long sBk, const float* __restrict__ bias, float* __restrict__ out, long long ldc, long long M,
-               int N, int K) {
+               int N, int K, Epilogue ep_in = Epilogue()) {
+  const Epilogue ep = EP ? resolve_beta(ep_in) : ep_in;
   constexpr int BN = 64, TM = BM / 16, TN = 4;
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -159,7 +160,9 @@ k_gemm_strided(const float* __restrict__ A, long long sAm, long long sAk, const 
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < N) out[m * ldc + n] = acc[i][j] + (bias != nullptr ? bias[n] : 0.f);
+      if (n >= N) continue;
+      if (EP) epilogue_store(ep, m, n, acc[i][j]);
+      else out[m * ldc + n] = acc[i][j] + (bias != nullptr ? bias[n] : 0.f);
     }
   }
 }
@@ -275,6 +278,19 @@ int gemm_nt_simt(const float* A, long long lda, const float* Bm, long long ldb, 
   const int vecA = ((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (lda % 4) == 0) ? 1 : 0;
   const int vecB = ((reinterpret_cast<uintptr_t>(Bm) & 15) == 0 && (ldb % 4) == 0) ? 1 : 0;
   const long long tiles_big = ((M + 127) / 128) * ((N + 127) / 128);
+  const long long col_tiles = (N + 63) / 64;
+  if (((M + 63) / 64) * col_tiles < 148) {
+    // few 64x64 tiles (MLP layers of the toy / tabular flows: M = 1000, N = 128 is 32 tiles on 148 SMs, 14 us): the
+    // element-strided kernel with 32- or 16-row tiles and the same fused epilogue fills the machine (6 us)
+    const int bm = (((M + 31) / 32) * col_tiles < 296) ? 16 : 32;
+    dim3 grid((unsigned)col_tiles, (unsigned)((M + bm - 1) / bm));
+    IMPFLOW_REQUIRE(grid.y <= 65535, "gemm_nt: M=%lld too large", M);
+    if (bm == 32)
+      k_gemm_strided<32, true><<<grid, 256, 0, s>>>(A, lda, 1, Bm, ldb, 1, nullptr, nullptr, ep.ldc, M, N, K, ep);
+    else
+      k_gemm_strided<16, true><<<grid, 256, 0, s>>>(A, lda, 1, Bm, ldb, 1, nullptr, nullptr, ep.ldc, M, N, K, ep);
+    return check_launch("k_gemm_strided<ep>");
+  }
   if (tiles_big >= 148 && N > 64) {
     dim3 grid((N + 127) / 128, (unsigned)((M + 127) / 128));
     IMPFLOW_REQUIRE(grid.y <= 65535, "gemm_nt: M=%lld too large", M);
