@@ -341,18 +341,33 @@ k_mlp_series(MlpDesc vjp, MlpDesc tan, SeriesCoeffs co, const float* __restrict_
   const int d = vjp.dims[0];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long plane = (long long)B * d;
-  for (int s0 = blockIdx.x * kTile; s0 < B; s0 += gridDim.x * kTile) {
+  // the two chains of a tile are independent: even CTAs take the vjp chain (+ combinations, estimate), odd CTAs the
+  // tangent chain, so a batch of 1000 samples (63 tiles) covers 126 SMs instead of 63
+  const int chain = blockIdx.x & 1;
+  for (int s0 = (blockIdx.x >> 1) * kTile; s0 < B; s0 += (gridDim.x >> 1) * kTile) {
     for (int i = tid; i < kTile * d; i += kMlpThreads) {
       const int s = i / d, c = i % d;
       const float x = (s0 + s < B) ? v[(long long)(s0 + s) * d + c] : 0.f;
       vt[s * 128 + c] = x;
       if (s0 + s < B) {
-        Ls[(long long)(s0 + s) * d + c] = x;      // l_0 = r_0 = v
-        Rs[(long long)(s0 + s) * d + c] = x;
+        if (chain == 0) Ls[(long long)(s0 + s) * d + c] = x;      // l_0 = r_0 = v
+        else Rs[(long long)(s0 + s) * d + c] = x;
       }
     }
     if (tid < kTile) sacc[tid] = 0.f;
     __syncthreads();
+    if (chain == 1) {
+      // ---- tangent chain: r_m = J r_{m-1} ----
+      for (int m = 1; m < n; ++m) {
+        const float* cur = mlp_eval(tan, Rs + (m - 1) * plane, s0, B, bufA, bufB);
+        for (int i = tid; i < kTile * d; i += kMlpThreads) {
+          const int s = i / d, c = i % d;
+          if (s0 + s < B) Rs[m * plane + (long long)(s0 + s) * d + c] = cur[s * kMaxWidth + c];
+        }
+        __syncthreads();
+      }
+      continue;
+    }
     // ---- vjp chain: l_k = J^T l_{k-1}, S += c_k <l_k, v> ----
     for (int k = 1; k <= n; ++k) {
       const float* cur = mlp_eval(vjp, Ls + (k - 1) * plane, s0, B, bufA, bufB);
@@ -367,15 +382,6 @@ k_mlp_series(MlpDesc vjp, MlpDesc tan, SeriesCoeffs co, const float* __restrict_
         if (lane == 0) sacc[s] = fmaf(co.c[k - 1], acc, sacc[s]);
       }
       __syncthreads();      // l_k is in global memory (visible to this block) before the next step reads it
-    }
-    // ---- tangent chain: r_m = J r_{m-1} ----
-    for (int m = 1; m < n; ++m) {
-      const float* cur = mlp_eval(tan, Rs + (m - 1) * plane, s0, B, bufA, bufB);
-      for (int i = tid; i < kTile * d; i += kMlpThreads) {
-        const int s = i / d, c = i % d;
-        if (s0 + s < B) Rs[m * plane + (long long)(s0 + s) * d + c] = cur[s * kMaxWidth + c];
-      }
-      __syncthreads();
     }
     // ---- w_m = sum_a c_{a+m} l_a (a ascending, as the host loop of linear combinations did) ----
     for (int i = tid; i < n * kTile * d; i += kMlpThreads) {
@@ -550,7 +556,7 @@ extern "C" int impflow_mlp_series(const float* v, const float* const* W, const i
   memset(&co, 0, sizeof(co));
   for (int k = 0; k < n; ++k) co.c[k] = (float)coeffs[k];
   const int n_tiles = (B + kTile - 1) / kTile;
-  const int grid = n_tiles < 148 * 4 ? n_tiles : 148 * 4;
+  const int grid = 2 * (n_tiles < 148 * 2 ? n_tiles : 148 * 2);      // (vjp CTA, tangent CTA) per tile
   k_mlp_series<<<grid, kMlpThreads, 0, (cudaStream_t)stream>>>(vjp, tan, co, v, Ls, Rs, Wm, S, B, n);
   return check_launch("k_mlp_series");
 }
