@@ -726,6 +726,14 @@ class BranchProgram(object):
             saved.rows, saved.meta, saved.M, saved.pres, saved.ains, saved.derivs = rows, meta, M, pres, ains, {}
         return self._from_rows(out, meta), saved
 
+    def forward_rows(self, rows, meta):
+        """nnet applied to activations already in rows (NHWC) layout, result in rows layout: no layout copies.  The
+        generic Broyden loop of a conv branch without a native plan iterates in this layout (a sample is a contiguous
+        block either way; the solver algebra does not care about the order inside it)."""
+        M = rows.shape[0]
+        y, _ = self._forward_saved_impl(rows, meta, M, self._prep(M, meta), False)
+        return y.permute(0, 2, 3, 1).reshape(M, -1) if meta[0] == 'conv' else y.reshape(M, -1)
+
     def forward(self, x, save=False):
         y, saved = self.forward_saved(x, save)
         if save:
@@ -743,8 +751,14 @@ class BranchProgram(object):
         P = self._conv3(ws, meta)
         if P is not None:
             return self._native_vjp(P, v, saved)
-        n = len(self.stages)
         t, _ = self._to_rows(v)
+        return self._from_rows(self.vjp_rows(t, saved), meta)
+
+    def vjp_rows(self, t, saved):
+        """v^T J with v and the result in rows (NHWC) layout (generic launch sequence; see forward_rows)."""
+        meta, M, pres = saved.meta, saved.M, saved.pres
+        ws = self._prep(M)
+        n = len(self.stages)
         T = _T(f=t)
         if self.post_act is not None:
             T = _T(f=ops.act_mul(pres[n], t, self.post_act.kind, 1, self.post_act.beta_sp()))
@@ -756,7 +770,7 @@ class BranchProgram(object):
             pre, _, split = self._apply(w, T, meta, True, act=(_MULT if act is not None else None),
                                         want_pre=not want_split, dmul_pre=dm, want_split=want_split)
             T = _T(f=pre, s=split)
-        return self._from_rows(T.f32(), meta)
+        return T.f32()
 
     # ---------------------------------------------------------------- parameter gradients
     def _wgrad_gemm_layout(self, w, meta, G, Xin):

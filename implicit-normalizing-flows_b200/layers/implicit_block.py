@@ -108,6 +108,7 @@ def _timed(kind, like, fn):
 
 # Independent halves of a block's work (the log-det estimates of the x- and z-branch) on two streams.
 OVERLAP = {'on': True}
+ROWS_SOLVE = {'on': True}      # generic Broyden loop of a conv branch iterates in rows (NHWC) layout
 HOST_AHEAD = {'on': True}     # imBlock.forward: twin refresh and random draws in front of the forward solve
 _side = {}
 
@@ -263,6 +264,19 @@ class RootFind(Function):
         elif prog_z is not None:
             # conv branch: the whole solve in one call of the native runtime (csrc/conv3_plan.cu)
             info = prog_z.broyden_solve(0, x_embed, None, threshold, eps)
+        if info is None and prog_z is not None and not prog_z.is_linear and x_embed.dim() == 4 and ROWS_SOLVE['on']:
+            # conv branch without a native plan (classifier: 3x3 - 3x3): iterate in rows (NHWC) layout, no layout copy
+            # per evaluation (the solver's per-sample dots and norms do not depend on the order inside a sample)
+            rows_e, meta = prog_z._to_rows(x_embed)
+            B, M = x_embed.shape[0], rows_e.shape[0]
+
+            def g_rows(z2d):
+                zr = z2d.view(M, -1)
+                return ops.lincomb3(rows_e, 1.0, prog_z.forward_rows(zr, meta), -1.0, zr, -1.0).view(B, -1)
+
+            info = broyden(g_rows, torch.zeros(B, rows_e.numel() // B, device=x_embed.device), threshold=threshold,
+                           eps=eps, name='forward')
+            info['result'] = prog_z._from_rows(info['result'].view(M, -1), meta)
         if info is None:
             def g(z):     # x_embed - nnet_z(z) - z in one kernel (implicit_block.py:72)
                 return ops.lincomb3(x_embed, 1.0, branch_eval(nnet_z, z), -1.0, z, -1.0)
@@ -368,6 +382,17 @@ class imBlock(nn.Module):
                             spec = prog_z.mlp_vjp_spec(saved_z)
                             if spec is not None:       # small-d MLP: the whole solve in one persistent kernel
                                 info = broyden_mlp_vjp(spec, grad, threshold, eps)
+                        if info is None and not prog_z.is_linear and grad.dim() == 4 and ROWS_SOLVE['on']:
+                            grows, meta = prog_z._to_rows(grad)          # rows-layout iteration, see RootFind
+                            B, M = grad.shape[0], grows.shape[0]
+
+                            def g_rows(v2d):
+                                vr = v2d.view(M, -1)
+                                return ops.lincomb3(prog_z.vjp_rows(vr, saved_z), 1.0, vr, 1.0, grows, -1.0).view(B, -1)
+
+                            info = broyden(g_rows, torch.zeros(B, grows.numel() // B, device=grad.device),
+                                           threshold=threshold, eps=eps, name='backward')
+                            info['result'] = prog_z._from_rows(info['result'].view(M, -1), meta)
                         if info is None:
                             info = broyden(lambda v: ops.lincomb3(prog_z.vjp(v, saved_z), 1.0, v, 1.0, grad, -1.0),
                                            torch.zeros_like(grad), threshold=threshold, eps=eps, name='backward')
