@@ -94,10 +94,6 @@ PROF['on'] = False
 bwd_thread_profile = PROF['bwd']
 
 
-def _stop(ctx, *a):
-    return None
-
-
 # the profiler of the autograd thread has to be switched off from that thread: one more backward does it
 class _Off(torch.autograd.Function):
     @staticmethod
