@@ -621,6 +621,8 @@ def main():
         pkg._cabi.load().impflow_wgrad_set_slice_major(0)
     if os.environ.get('IMPFLOW_SN_CTAS', ''):                # A/B: CTAs per 3x3 power-iteration launch
         pkg._cabi.load().impflow_sn_conv_set_ctas(int(os.environ['IMPFLOW_SN_CTAS']))
+    if os.environ.get('IMPFLOW_SN_BATCH', '') == '0':        # A/B: one power-iteration launch per dense layer
+        pkg.layers.base.mixed_lipschitz.BATCH_DENSE['on'] = False
     if os.environ.get('IMPFLOW_RUNAHEAD', ''):               # A/B: 0 = synchronise the solver loop every iteration
         pkg._cabi.load().impflow_conv3_set_runahead(int(os.environ['IMPFLOW_RUNAHEAD']))
     if os.environ.get('IMPFLOW_CHAIN23_A32', '') == '1':     # A/B: one fp32 plane between layer 1 and k_chain23
@@ -682,6 +684,18 @@ def main():
     if rank == 0 and os.environ.get('IMPFLOW_BENCH_NOSAMPLER', '') != '1':     # diagnostic switch: cost of the poller
         sampler.start()
     trace = os.environ.get('IMPFLOW_TRACE_CAPTURE', '') == '1'
+    if trace:                      # diagnostic: log every cyclic-GC pass (generation, duration) next to the captures
+        import gc
+        _gc_t = {}
+
+        def _gc_cb(phase, info):
+            if phase == 'start':
+                _gc_t['t'] = time.perf_counter()
+            elif info.get('generation', 0) >= 1:
+                sys.stderr.write('[gc] t=%.3f gen=%d %.1f ms collected=%d\n' % (
+                    time.perf_counter(), info['generation'], 1e3 * (time.perf_counter() - _gc_t.get('t', 0.0)),
+                    info.get('collected', 0)))
+        gc.callbacks.append(_gc_cb)
     for i_ in range(args.warmup):
         if trace:
             torch.cuda.synchronize()
@@ -710,7 +724,9 @@ def main():
         torch.cuda.cudart().cudaProfilerStart()
     ev0.record()
     step_evs = [ev0]
-    for _ in range(args.steps):
+    for i_ in range(args.steps):
+        if trace:
+            sys.stderr.write('[timed step %d] t=%.3f\n' % (i_, time.perf_counter()))
         flush.zero_()
         step(x_dev, y_dev)
         step_evs.append(torch.cuda.Event(enable_timing=True))

@@ -90,9 +90,16 @@ SIGNATURES = {
     'impflow_sn_conv_set_ctas': (_i, [_i]),
     'impflow_sn_conv_workspace_floats': (ctypes.c_size_t, [_i, _i, _i, _i]),
     'impflow_sn_power_iter_conv3x3': (_i, [_c_fp] * 5 + [_i, _i, _i, _i, _i, _f, _f, _c_fp, _c_fp, _c_fp]),
+    'impflow_sn_power_iter_batch': (_i, [_c_fp, _i, _i, _i, _i, _f, _f, _c_fp]),
     'impflow_sn_power_iter': (_i, [_c_fp, _c_fp, _c_fp, _c_fp, _c_fp, _i, _i, _i, _f, _f, _c_fp]),
 }
 
+
+
+class SnDesc(ctypes.Structure):
+    """impflow_sn_desc of include/impflow_b200.h (48 bytes)."""
+    _fields_ = [('W', ctypes.c_void_p), ('u', ctypes.c_void_p), ('v', ctypes.c_void_p), ('sigma', ctypes.c_void_p),
+                ('iters', ctypes.c_void_p), ('out_f', ctypes.c_int32), ('in_f', ctypes.c_int32)]
 
 
 class Conv3Plan(ctypes.Structure):

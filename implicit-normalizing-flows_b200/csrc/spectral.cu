@@ -87,11 +87,10 @@ __device__ void l2_normalize(float* y, int n, float* scratch) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSnThreads)
-k_sn_power_iter(const float* __restrict__ W, float* __restrict__ u_g, float* __restrict__ v_g,
-                float* __restrict__ sigma, int* __restrict__ iters, int out_f, int in_f, int n_iterations,
-                float atol, float rtol, int with_partials) {
-  extern __shared__ float sm[];
+// one CTA: the whole power iteration of one dense layer (body shared by the single-layer and the batched kernel)
+__device__ void sn_power_iter_body(const float* __restrict__ W, float* __restrict__ u_g, float* __restrict__ v_g,
+                                   float* __restrict__ sigma, int* __restrict__ iters, int out_f, int in_f,
+                                   int n_iterations, float atol, float rtol, int with_partials, float* sm) {
   float* u = sm;
   float* v = u + out_f;
   float* ou = v + in_f;
@@ -145,6 +144,28 @@ k_sn_power_iter(const float* __restrict__ W, float* __restrict__ u_g, float* __r
     for (int i = threadIdx.x; i < out_f; i += kSnThreads) u_g[i] = u[i];
     for (int i = threadIdx.x; i < in_f; i += kSnThreads) v_g[i] = v[i];
   }
+}
+
+__global__ void __launch_bounds__(kSnThreads)
+k_sn_power_iter(const float* __restrict__ W, float* __restrict__ u_g, float* __restrict__ v_g,
+                float* __restrict__ sigma, int* __restrict__ iters, int out_f, int in_f, int n_iterations,
+                float atol, float rtol, int with_partials) {
+  extern __shared__ float sm[];
+  sn_power_iter_body(W, u_g, v_g, sigma, iters, out_f, in_f, n_iterations, atol, rtol, with_partials, sm);
+}
+
+// All dense layers of a model in ONE launch, one CTA per layer (the refresh after every optimiser step touches every
+// layer; the layers are independent): update_lipschitz issued one launch per layer (100+ for a tabular flow).
+__global__ void __launch_bounds__(kSnThreads)
+k_sn_power_iter_batch(const impflow_sn_desc* __restrict__ descs, int n_iterations, float atol, float rtol,
+                      int smem_floats) {
+  extern __shared__ float sm[];
+  const impflow_sn_desc d = descs[blockIdx.x];
+  // the single-layer launch's rule (200 KB with the per-warp partials, else without); the host sized the shared
+  // memory as min(200 KB, need of the widest layer), so a layer that passes this test fits
+  const long long need = 2LL * (d.out_f + d.in_f) + (long long)kSnWarps * d.in_f;
+  sn_power_iter_body(d.W, d.u, d.v, d.sigma, d.iters, d.out_f, d.in_f, n_iterations, atol, rtol,
+                     (need * 4 <= 200 * 1024 && need <= smem_floats) ? 1 : 0, sm);
 }
 
 // W / max(1, sigma/coeff) with sigma read from the device (mixed_lipschitz.py:128-131), and its
@@ -333,4 +354,23 @@ extern "C" int impflow_sn_power_iter(const float* W, float* u, float* v, float* 
   k_sn_power_iter<<<1, kSnThreads, smem, (cudaStream_t)stream>>>(W, u, v, sigma, iters, out_f, in_f,
                                                                   n_iterations, atol, rtol, with_partials);
   return check_launch("k_sn_power_iter");
+}
+
+extern "C" int impflow_sn_power_iter_batch(const impflow_sn_desc* descs_dev, int n, int max_out, int max_in,
+                                           int n_iterations, float atol, float rtol, void* stream) {
+  IMPFLOW_REQUIRE(n >= 1 && descs_dev != nullptr, "sn_power_iter_batch: no layers");
+  IMPFLOW_REQUIRE(max_out >= 1 && max_in >= 1, "sn_power_iter_batch: empty matrix");
+  size_t smem = sizeof(float) * 2 * ((size_t)max_out + max_in);
+  IMPFLOW_REQUIRE(smem <= 200 * 1024, "sn_power_iter_batch: out+in=%d too large for one CTA", max_out + max_in);
+  const size_t with_part = smem + sizeof(float) * (size_t)kSnWarps * max_in;
+  smem = with_part <= 200 * 1024 ? with_part : 200 * 1024;      // narrow layers of a mixed batch keep their partials
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(k_sn_power_iter_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess) {
+    set_error("sn_power_iter_batch: cannot set dynamic shared memory");
+    return -1;
+  }
+  k_sn_power_iter_batch<<<n, kSnThreads, smem, (cudaStream_t)stream>>>(descs_dev, n_iterations, atol, rtol,
+                                                                       (int)(smem / sizeof(float)));
+  return check_launch("k_sn_power_iter_batch");
 }

@@ -660,8 +660,81 @@ def update_lipschitz(model, n_iterations=None, n_streams=8):
         UPDATE_ONLY['on'] = False
 
 
+BATCH_DENSE = {'on': True}      # update_lipschitz: all dense (Linear / 1x1) 2-norm layers in one launch
+
+_desc_cache = {}
+
+
+def _dense_settings(m, n_iterations):
+    """(n_iterations or -1, atol, rtol) a dense layer's compute_weight(update=True) would run with, or None if the
+    layer does not qualify for the batched launch."""
+    if isinstance(m, InducedNormConv2d):
+        if m.kernel_size != (1, 1) or not m.is_initialized():
+            return None
+    elif not isinstance(m, InducedNormLinear):
+        return None
+    if not _plain_l2(*m.compute_domain_codomain()):
+        return None
+    n_it = m.n_iterations if n_iterations is None else n_iterations
+    atol = m.atol
+    rtol = m.rtol if atol is None else atol             # the reference's quirk (mixed_lipschitz.py:94, :279)
+    if n_it is None and (atol is None or rtol is None):
+        return None                                      # the per-layer path raises the reference's ValueError
+    return (-1 if n_it is None else int(n_it), float(atol or 0.0), float(rtol or 0.0))
+
+
+def _update_dense_batched(mods, n_iterations):
+    """Power iteration of every qualifying dense layer in ONE launch per (n_iterations, atol, rtol) group
+    (csrc/spectral.cu k_sn_power_iter_batch, one CTA per layer).  Returns the modules it did NOT handle."""
+    import ctypes
+    import numpy as np
+    groups, rest = {}, []
+    for m in mods:
+        key = _dense_settings(m, n_iterations) if BATCH_DENSE['on'] else None
+        if key is None:
+            rest.append(m)
+        else:
+            groups.setdefault(key, []).append(m)
+    lib = _cabi.load()
+    for (n_it, atol, rtol), ms in groups.items():
+        if len(ms) < 2:
+            rest += ms
+            continue
+        Ws = [m.weight.detach().view(m.weight.shape[0], -1) for m in ms]
+        ck = tuple((W.data_ptr(), m.u.data_ptr(), m.v.data_ptr(), m.scale.data_ptr(), W.shape) for W, m in zip(Ws, ms))
+        cached = _desc_cache.get(ck)
+        if cached is None:
+            if len(_desc_cache) > 64:
+                _desc_cache.clear()
+            iters = torch.zeros(len(ms), device=Ws[0].device, dtype=torch.int32)
+            host = (_cabi.SnDesc * len(ms))()
+            for i, (W, m) in enumerate(zip(Ws, ms)):
+                assert W.is_contiguous() and m.u.is_contiguous() and m.v.is_contiguous()
+                host[i].W, host[i].u, host[i].v = W.data_ptr(), m.u.data_ptr(), m.v.data_ptr()
+                host[i].sigma, host[i].iters = m.scale.data_ptr(), iters.data_ptr() + 4 * i
+                host[i].out_f, host[i].in_f = W.shape[0], W.shape[1]
+            raw = np.frombuffer(bytes(host), dtype=np.uint8).copy()
+            descs = torch.from_numpy(raw).to(Ws[0].device)
+            cached = _desc_cache[ck] = (descs, iters, max(W.shape[0] for W in Ws), max(W.shape[1] for W in Ws))
+        descs, iters, max_out, max_in = cached
+        _cabi.check(lib.impflow_sn_power_iter_batch(ctypes.c_void_p(descs.data_ptr()), len(ms), max_out, max_in, n_it,
+                                                    atol, rtol, _cabi.stream()), 'sn_power_iter_batch')
+        touched = []
+        for m in ms:
+            touched += [m.u, m.v, m.scale] if n_it != 0 else [m.scale]
+        torch.autograd.graph.increment_version(touched)      # written through raw pointers: version-keyed host caches
+        for m in ms:
+            m._scale_for = _state_key(m)
+    return rest
+
+
 def _update_all(mods, dev, n_iterations, n_streams):
     with torch.no_grad():
+        if UPDATE_ONLY['on']:
+            _require_cuda(mods[0].weight, 'update_lipschitz: layer weights')
+            mods = _update_dense_batched(mods, n_iterations)
+            if not mods:
+                return
         ready = all((not isinstance(m, InducedNormConv2d)) or m.is_initialized() for m in mods)
         if dev.type != 'cuda' or n_streams <= 1 or len(mods) < 2 or not ready:
             for m in mods:

@@ -411,6 +411,19 @@ int impflow_conv3_broyden(const impflow_conv3_plan* plan, int mode, const float*
  * ------------------------------------------------------------------------------------------ */
 int impflow_sn_power_iter(const float* W, float* u, float* v, float* sigma, int* iters, int out_f,
                           int in_f, int n_iterations, float atol, float rtol, void* stream);
+/* The same for n dense layers in ONE launch (one CTA per layer): descs is a DEVICE array of n descriptors; every layer
+ * runs with the same n_iterations / atol / rtol; max_out / max_in bound the shared memory.  update_lipschitz refreshes
+ * all dense layers of a model this way (train_img.py:786-792 loops over them). */
+typedef struct {
+  const float* W;   /* (out_f, in_f) row-major */
+  float* u;         /* (out_f) in / out */
+  float* v;         /* (in_f) in / out */
+  float* sigma;     /* 1 float out */
+  int* iters;       /* 1 int out (may be NULL) */
+  int out_f, in_f;
+} impflow_sn_desc;
+int impflow_sn_power_iter_batch(const impflow_sn_desc* descs, int n, int max_out, int max_in, int n_iterations,
+                                float atol, float rtol, void* stream);
 
 /* The same power iteration for a 3x3 / stride 1 / pad 1 convolution acting on ONE H x W image — replaces the
  * host loop of mixed_lipschitz.py:328-386 (_compute_weight_kxk: 1-sample conv2d / conv_transpose2d,

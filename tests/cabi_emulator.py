@@ -920,6 +920,17 @@ class EmulatedLib(object):
         self.launches += 1
         return 0
 
+    def impflow_sn_power_iter_batch(self, descs, n, max_out, max_in, n_iterations, atol, rtol, stream):
+        from impflow_b200._cabi import SnDesc
+        arr = (SnDesc * n).from_address(_addr(descs))
+        for d in arr:
+            self.impflow_sn_power_iter(ctypes.c_void_p(d.W), ctypes.c_void_p(d.u), ctypes.c_void_p(d.v),
+                                       ctypes.c_void_p(d.sigma), ctypes.c_void_p(d.iters) if d.iters else None,
+                                       d.out_f, d.in_f, n_iterations, atol, rtol, stream)
+            self.launches -= 1
+        self.launches += 1
+        return 0
+
     def impflow_sn_conv_workspace_floats(self, Cout, Cin, H, W):
         narrow = min(Cout, Cin) * H * W
         return 0 if 2 * narrow * 4 > 160 * 1024 else 128 * narrow + narrow + 5 * 128

@@ -277,6 +277,64 @@ def case_implicit_flow_density_step(golden):
     assert rel_err(x_rec.cpu(), fx['x']) < 1e-3
 
 
+def case_update_lipschitz_batched_dense():
+    """update_lipschitz refreshes every dense (Linear / 1x1) 2-norm layer of a model in ONE launch
+    (impflow_sn_power_iter_batch, one CTA per layer): u, v and sigma equal the per-layer launches' bit for bit, for
+    fixed iteration counts and for the tolerance mode, with mixed shapes in one batch (train_img.py:786-792)."""
+    import copy
+    import impflow_b200
+    from impflow_b200.layers.base import mixed_lipschitz as ML
+    L = impflow_b200.layers
+    dev = DEV['device']
+    for kw in (dict(n_iterations=None, atol=1e-3, rtol=1e-3), dict(n_iterations=5, atol=None, rtol=None)):
+        torch.manual_seed(11)
+        lin = lambda a, b: L.base.get_linear(a, b, coeff=0.9, domain=2, codomain=2, **kw)
+        conv = lambda a, b, k: L.base.get_conv2d(a, b, k, 1, k // 2, coeff=0.9, domain=2, codomain=2, **kw)
+        mlp = torch.nn.Sequential(lin(6, 128), L.base.Swish(), lin(128, 128), L.base.Swish(), lin(128, 40),
+                                  L.base.Swish(), lin(40, 6))
+        cnn = torch.nn.Sequential(conv(3, 32, 3), L.base.Swish(), conv(32, 48, 1), L.base.Swish(), conv(48, 3, 3))
+        model = torch.nn.ModuleList([mlp, cnn]).to(dev)
+        with torch.no_grad():
+            cnn(torch.randn(2, 3, 8, 8, device=dev))          # shapes the conv layers' u / v
+            for p in model.parameters():
+                if p.dim() > 1:
+                    p.copy_(torch.randn_like(p))
+        twin = copy.deepcopy(model)
+        launches = getattr(impflow_b200._cabi.load(), 'launches', None)
+        ML.BATCH_DENSE['on'] = True
+        try:
+            L.base.update_lipschitz(model, kw['n_iterations'])
+            if launches is not None:        # the emulator counts launches: 1 for the 5 dense layers + 2 conv 3x3
+                assert impflow_b200._cabi.load().launches - launches == 3
+            ML.BATCH_DENSE['on'] = False
+            L.base.update_lipschitz(twin, kw['n_iterations'])
+        finally:
+            ML.BATCH_DENSE['on'] = True
+        n = 0
+        for a, b in zip(model.modules(), twin.modules()):
+            if hasattr(a, 'sigma_gradient'):
+                n += 1
+                assert torch.equal(a.u, b.u) and torch.equal(a.v, b.v) and torch.equal(a.scale, b.scale), type(a)
+                assert ML.sigma_of(a) is not None
+                assert float(a.scale) > 0
+        assert n == 7
+        # a second refresh reuses the cached descriptor table and still writes the live buffers
+        with torch.no_grad():
+            for m, t in zip(model.modules(), twin.modules()):
+                if hasattr(m, 'sigma_gradient'):
+                    m.weight.mul_(1.5)
+                    t.weight.mul_(1.5)
+        L.base.update_lipschitz(model, kw['n_iterations'])
+        ML.BATCH_DENSE['on'] = False
+        try:
+            L.base.update_lipschitz(twin, kw['n_iterations'])
+        finally:
+            ML.BATCH_DENSE['on'] = True
+        for a, b in zip(model.modules(), twin.modules()):
+            if hasattr(a, 'sigma_gradient'):
+                assert torch.equal(a.scale, b.scale) and torch.equal(a.u, b.u)
+
+
 def case_sigma_cache_follows_power_iteration():
     """u / v are updated in place by the power-iteration kernels: every host cache keyed on them (d sigma/d W,
     the effective weights of the branch programs) must see the change (regression: stale sigma after

@@ -109,6 +109,10 @@ def test_smoke_entry():
     __graft_entry__.smoke()
 
 
+def test_update_lipschitz_batched_dense():
+    cases.case_update_lipschitz_batched_dense()
+
+
 def test_sigma_cache_follows_power_iteration():
     cases.case_sigma_cache_follows_power_iteration()
 

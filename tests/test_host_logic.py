@@ -253,6 +253,10 @@ def test_fused_paths_are_taken(golden, monkeypatch):
     assert counts['chain'] == 2 and counts['solve'] >= 2 and counts['vjp'] == 1      # 1: dl_dx = v^T (I + J_x)
 
 
+def test_update_lipschitz_batched_dense():
+    cases.case_update_lipschitz_batched_dense()
+
+
 def test_sigma_cache_follows_power_iteration():
     cases.case_sigma_cache_follows_power_iteration()
 
