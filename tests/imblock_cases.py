@@ -1043,3 +1043,56 @@ def case_direct_grad_sink_matches_autograd(golden):
         if ref is not None and np.linalg.norm(ref) > 1e-6:
             worst = max(worst, rel_err(v.detach().cpu(), ref))
     assert worst < 5e-3, worst
+
+
+def workload_round_trip(workload, batch=None):
+    """Size-independent properties of a whole bench workload (bench.WORKLOADS, the BASELINE.json configurations at
+    their FULL sizes on the GPU; a reduced one on the emulator): data -> latent -> data round trip through every
+    imBlock's forward and inverse Broyden solve (implicit_flow.py:221-251, train_img.py:756-761), the fixed-point
+    residual  z + f(z) - x - g(x)  of every block (implicit_block.py:51-100), and run-to-run determinism of the
+    forward (fixed-order reductions, no atomics).  Returns the measured figures; the tests hold the thresholds."""
+    import bench
+    pkg = _pkg()
+    dev = DEV['device']
+    wl = bench.WORKLOADS[workload]
+    batch = batch or wl['batch']
+    is_mlp = wl.get('kind') == 'mlp'
+    is_cls = wl.get('kind') == 'cls'      # a classifier is not invertible as a whole: residuals and determinism only
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = bench.build_model(pkg, wl, batch).to(dev)
+    if is_mlp:
+        bench.scale_mlp_last_layers(model, wl)
+    x, _ = bench.synthetic_batch(wl, batch, torch.Generator().manual_seed(1234))
+    x = x.to(dev)
+    with torch.no_grad():
+        if is_mlp:
+            model(x)
+        else:
+            model(x, restore=True)           # ActNorm data init + lazy u / v shaping
+        if is_cls:
+            for b_ in model.modules():         # BasicImplicitBlock: the first call was the restore pass
+                if type(b_).__name__ == 'BasicImplicitBlock':
+                    b_.initialized = True
+    model.eval()
+    blocks = [m for m in model.modules() if isinstance(m, pkg.layers.imBlock)]
+    seen = {}
+    hooks = [b.register_forward_hook(lambda m, inp, out, i=i: seen.__setitem__(i, (inp[0].detach(), (
+        out[0] if isinstance(out, tuple) else out).detach()))) for i, b in enumerate(blocks)]
+    with torch.no_grad():
+        z = model(x)
+        for h in hooks:
+            h.remove()
+        z2 = model(x)
+        x_rec = None if is_cls else model.inverse(z) if is_mlp else model(z, inverse=True)
+        residual = 0.0
+        for i, b in enumerate(blocks):
+            xb, zb = seen[i]
+            r = zb + b.nnet_z(zb) - xb - b.nnet_x(xb)
+            residual = max(residual, float(r.norm() / xb.norm()))
+    assert len(seen) == len(blocks) and bool(torch.isfinite(z).all())
+    assert is_cls or bool(torch.isfinite(x_rec).all())
+    return {'round_trip': None if is_cls else rel_err(x_rec.cpu(), x.cpu()), 'residual': residual, 'deterministic': bool(torch.equal(z, z2)),
+            'blocks': len(blocks), 'batch': batch,
+            'fwd_nstep': [b.solver_stats['fwd']['nstep'] for b in blocks if 'fwd' in b.solver_stats],
+            'inv_nstep': [b.solver_stats['inv']['nstep'] for b in blocks if 'inv' in b.solver_stats]}

@@ -257,6 +257,16 @@ def test_update_lipschitz_batched_dense():
     cases.case_update_lipschitz_batched_dense()
 
 
+def test_workload_round_trip_reduced():
+    """The full-size GPU property test (tests/test_gpu_fullsize.py) at a reduced size on the emulator."""
+    r = cases.workload_round_trip('cifar-small', batch=2)
+    print(r)
+    assert r['round_trip'] < 1e-3 and r['residual'] < 1e-4 and r['deterministic'], r
+    r = cases.workload_round_trip('tabular-power', batch=16)
+    print(r)
+    assert r['round_trip'] < 1e-3 and r['residual'] < 1e-4 and r['deterministic'], r
+
+
 def test_sigma_cache_follows_power_iteration():
     cases.case_sigma_cache_follows_power_iteration()
 
