@@ -826,8 +826,66 @@ def gen_bwd_band():
     save('bwd_band', **out)
 
 
+# ----------------------------------------------------------------------------------------------
+# 12. closed-form operator-norm layers (lipschitz.py:274-366) and a block under vnorms '122f'
+# ----------------------------------------------------------------------------------------------
+def gen_lop():
+    """LopLinear / LopConv2d for the five (domain, codomain) pairs with a closed-form operator norm, local and global
+    constraint: effective weight, scale buffer, forward, gradients w.r.t. the weight and the input; then a training
+    step of an imBlock whose conv branches are built by the factories under vnorms '122f' (first layer 1 -> 2 and
+    last layer 2 -> inf are Lop layers, the middle one an induced 2 -> 2 layer)."""
+    out = {}
+    INF = float('inf')
+    pairs = {'11': (1, 1), '12': (1, 2), '1i': (1, INF), '2i': (2, INF), 'ii': (INF, INF)}
+    i = 0
+    for ptag, (dom, cod) in pairs.items():
+        for local in (True, False):
+            for kind in ('lin', 'c1', 'c3'):
+                tag = 'lop_%s_%s_%s' % (kind, ptag, 'loc' if local else 'glob')
+                torch.manual_seed(300 + i)
+                i += 1
+                if kind == 'lin':
+                    m = base_layers.get_linear(6, 7, coeff=0.3, domain=dom, codomain=cod, local_constraint=local)
+                    xin = torch.randn(5, 6)
+                else:
+                    k = 1 if kind == 'c1' else 3
+                    m = base_layers.get_conv2d(3, 4, k, 1, k // 2, coeff=0.3, domain=dom, codomain=cod,
+                                               local_constraint=local)
+                    xin = torch.randn(2, 3, 5, 5)
+                assert type(m).__name__ in ('LopLinear', 'LopConv2d')
+                xin.requires_grad_(True)
+                y = m(xin)
+                y.pow(2).sum().backward()
+                for k_, v in sd_np(m).items():
+                    out[tag + '_sd_' + k_] = v
+                out[tag + '_x'], out[tag + '_y'] = xin.detach().numpy(), y.detach().numpy()
+                out[tag + '_W'] = m.compute_weight().detach().numpy()
+                out[tag + '_grad_weight'] = m.weight.grad.numpy().copy()
+                out[tag + '_grad_bias'] = m.bias.grad.numpy().copy()
+                out[tag + '_grad_x'] = xin.grad.numpy().copy()
+                out[tag + '_norms'] = np.array([dom, cod, 1.0 if local else 0.0])
+    out['lop_tags'] = np.array(sorted({k.rsplit('_sd_', 1)[0] for k in out if '_sd_' in k}))
+
+    def branch(c, idim, coeff, tol):
+        doms, cods = [1, 2, 2], [2, 2, INF]           # vnorms '122f' (implicit_flow.py:361-363)
+        mk = lambda a, b, k, j: base_layers.get_conv2d(a, b, k, 1, k // 2, coeff=coeff, n_iterations=None,
+                                                       domain=doms[j], codomain=cods[j], atol=tol, rtol=tol)
+        return torch.nn.Sequential(base_layers.Swish(), mk(c, idim, 3, 0), base_layers.Swish(), mk(idim, idim, 1, 1),
+                                   base_layers.Swish(), mk(idim, c, 3, 2))
+    torch.manual_seed(13)
+    np.random.seed(13)
+    c, idim, hw, B = 4, 16, 6, 3
+    blk = layers.imBlock(branch(c, idim, 0.9, 1e-3), branch(c, idim, 0.9, 1e-3), n_dist='poisson', n_samples=1,
+                         n_exact_terms=3, neumann_grad=True, grad_in_forward=True)
+    x = torch.randn(B, c, hw, hw)
+    with torch.no_grad():
+        blk(x, restore=True)
+    run_block('lopblk', blk, x, 23, True, out, weight_perturb=3.0)
+    save('lop', **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['broyden', 'mlp', 'conv', 'norm', 'mixed', 'act', 'flow', 'ires', 'edge', 'tail', 'band']
+    which = sys.argv[1:] or ['broyden', 'mlp', 'conv', 'norm', 'mixed', 'act', 'flow', 'ires', 'edge', 'tail', 'band', 'lop']
     if 'broyden' in which: gen_broyden()
     if 'mlp' in which: gen_imblock_mlp()
     if 'conv' in which: gen_imblock_conv()
@@ -839,3 +897,4 @@ if __name__ == '__main__':
     if 'edge' in which: gen_edge()
     if 'tail' in which: gen_step_tail()
     if 'band' in which: gen_bwd_band()
+    if 'lop' in which: gen_lop()

@@ -1096,3 +1096,66 @@ def workload_round_trip(workload, batch=None):
             'blocks': len(blocks), 'batch': batch,
             'fwd_nstep': [b.solver_stats['fwd']['nstep'] for b in blocks if 'fwd' in b.solver_stats],
             'inv_nstep': [b.solver_stats['inv']['nstep'] for b in blocks if 'inv' in b.solver_stats]}
+
+
+def case_lop_layers(golden):
+    """LopLinear / LopConv2d (lipschitz.py:274-366) against the reference: effective weight, `scale` buffer, forward
+    and all three gradients for the five closed-form (domain, codomain) pairs, local and global constraint."""
+    pkg = _pkg()
+    L = pkg.layers.base
+    fx = golden('lop')
+    dev = DEV['device']
+    tags = [str(t) for t in fx['lop_tags']]
+    assert len(tags) == 30
+    for tag in tags:
+        kind = tag.split('_')[1]
+        dom, cod, local = [float(v) for v in fx[tag + '_norms']]
+        dom = int(dom) if dom != float('inf') else dom
+        cod = int(cod) if cod != float('inf') else cod
+        if kind == 'lin':
+            m = L.get_linear(6, 7, coeff=0.3, domain=dom, codomain=cod, local_constraint=bool(local))
+        else:
+            k = 1 if kind == 'c1' else 3
+            m = L.get_conv2d(3, 4, k, 1, k // 2, coeff=0.3, domain=dom, codomain=cod, local_constraint=bool(local))
+        assert type(m).__name__ == ('LopLinear' if kind == 'lin' else 'LopConv2d')
+        m = m.to(dev)
+        sd = {k_: v.to(dev) for k_, v in sub_sd(fx, tag + '_sd_').items()}
+        sd['scale'] = torch.zeros_like(sd['scale'])            # recomputed by the forward
+        missing, unexpected = m.load_state_dict(sd, strict=True)
+        assert not missing and not unexpected
+        x = torch.from_numpy(fx[tag + '_x']).to(dev).requires_grad_(True)
+        y = m(x)
+        y.pow(2).sum().backward()
+        assert rel_err(m.compute_weight().detach().cpu(), fx[tag + '_W']) < 1e-6, tag
+        assert abs(float(m.scale) - float(fx[tag + '_sd_scale'])) < 1e-6 * max(1.0, abs(float(m.scale))), tag
+        assert rel_err(y.detach().cpu(), fx[tag + '_y']) < 1e-5, tag
+        assert rel_err(x.grad.cpu(), fx[tag + '_grad_x']) < 1e-5, tag
+        assert rel_err(m.weight.grad.cpu(), fx[tag + '_grad_weight']) < 1e-5, tag
+        assert rel_err(m.bias.grad.cpu(), fx[tag + '_grad_bias']) < 1e-5, tag
+
+
+def case_imblock_lop_train(golden):
+    """A training step of an imBlock whose conv branches the factories build under vnorms '122f'
+    (implicit_flow.py:359-398: first layer 1 -> 2 and last layer 2 -> inf are Lop layers, the 1x1 in the middle an
+    induced 2 -> 2 layer): forward count, z, log-det, loss and every gradient against the reference."""
+    pkg = _pkg()
+    layers = pkg.layers
+    fx = golden('lop')
+    INF = float('inf')
+
+    def branch(c, idim, coeff, tol):
+        doms, cods = [1, 2, 2], [2, 2, INF]
+        mk = lambda a, b, k, j: layers.base.get_conv2d(a, b, k, 1, k // 2, coeff=coeff, n_iterations=None,
+                                                       domain=doms[j], codomain=cods[j], atol=tol, rtol=tol)
+        return torch.nn.Sequential(layers.base.Swish(), mk(c, idim, 3, 0), layers.base.Swish(), mk(idim, idim, 1, 1),
+                                   layers.base.Swish(), mk(idim, c, 3, 2))
+    blk = layers.imBlock(branch(4, 16, 0.9, 1e-3), branch(4, 16, 0.9, 1e-3), n_dist='poisson', n_samples=1,
+                         n_exact_terms=3, neumann_grad=True, grad_in_forward=True)
+    assert type(blk.nnet_x[1]).__name__ == 'LopConv2d' and type(blk.nnet_x[5]).__name__ == 'LopConv2d'
+    blk = load_block(blk, fx, 'lopblk', torch.from_numpy(fx['lopblk_x']).to(DEV["device"]))
+    x, z, dlogp, loss = run_train(blk, fx, 'lopblk')
+    check_train(blk, fx, 'lopblk', x, z, dlogp, loss, grad_tol=2e-3)
+    blk.eval()
+    with torch.no_grad():
+        x_rec = blk.inverse(z.detach())
+    assert rel_err(x_rec.cpu(), fx['lopblk_x_rec']) < 1e-4

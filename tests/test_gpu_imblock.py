@@ -113,6 +113,14 @@ def test_update_lipschitz_batched_dense():
     cases.case_update_lipschitz_batched_dense()
 
 
+def test_lop_layers(golden):
+    cases.case_lop_layers(golden)
+
+
+def test_imblock_lop_train(golden):
+    cases.case_imblock_lop_train(golden)
+
+
 def test_sigma_cache_follows_power_iteration():
     cases.case_sigma_cache_follows_power_iteration()
 

@@ -267,6 +267,14 @@ def test_workload_round_trip_reduced():
     assert r['round_trip'] < 1e-3 and r['residual'] < 1e-4 and r['deterministic'], r
 
 
+def test_lop_layers(golden):
+    cases.case_lop_layers(golden)
+
+
+def test_imblock_lop_train(golden):
+    cases.case_imblock_lop_train(golden)
+
+
 def test_sigma_cache_follows_power_iteration():
     cases.case_sigma_cache_follows_power_iteration()
 
