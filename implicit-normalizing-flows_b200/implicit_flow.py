@@ -41,15 +41,22 @@ class ImplicitFlow(nn.Module):
         self.n_blocks = n_blocks
         self.intermediate_dim = intermediate_dim
         self.factor_out = factor_out
+        # every constructor argument is kept as an attribute, as in the reference (implicit_flow.py:58-89); the init
+        # layer is thereby ALSO registered as `init_layer` (its buffers appear under both names in a state dict)
+        self.quadratic, self.init_layer, self.actnorm, self.fc_actnorm = quadratic, init_layer, actnorm, fc_actnorm
+        self.batchnorm, self.dropout, self.fc, self.coeff, self.vnorms = batchnorm, dropout, fc, coeff, vnorms
+        self.n_lipschitz_iters, self.sn_atol, self.sn_rtol = n_lipschitz_iters, sn_atol, sn_rtol
+        self.n_power_series, self.n_dist, self.n_samples, self.kernels = n_power_series, n_dist, n_samples, kernels
+        self.activation_fn, self.fc_end, self.fc_idim, self.n_exact_terms = activation_fn, fc_end, fc_idim, n_exact_terms
+        self.preact, self.neumann_grad, self.grad_in_forward = preact, neumann_grad, grad_in_forward
+        self.first_resblock, self.learn_p = first_resblock, learn_p
         self.classification = classification
         self.classification_hdim = classification_hdim
         self.n_classes = n_classes
         if not self.n_scale > 0:
             raise ValueError('Could not compute number of scales for input of size (%d,%d,%d,%d)' % input_size)
-        if quadratic or batchnorm or dropout:
-            raise NotImplementedError('impflow_b200: quadratic / batchnorm / dropout are outside the '
-                                      'hot-path scope (dead or unused in the reference configs)')
-        shared = dict(idim=intermediate_dim, actnorm=actnorm, fc_actnorm=fc_actnorm, fc=fc, coeff=coeff, vnorms=vnorms,
+        shared = dict(idim=intermediate_dim, quadratic=quadratic, actnorm=actnorm, fc_actnorm=fc_actnorm,
+                      batchnorm=batchnorm, dropout=dropout, fc=fc, coeff=coeff, vnorms=vnorms,
                       n_lipschitz_iters=n_lipschitz_iters, sn_atol=sn_atol, sn_rtol=sn_rtol,
                       n_power_series=n_power_series, n_dist=n_dist, n_samples=n_samples, kernels=kernels,
                       activation_fn=activation_fn, fc_end=fc_end, fc_idim=fc_idim, n_exact_terms=n_exact_terms,
@@ -153,11 +160,16 @@ class ImplicitFlow(nn.Module):
 class StackedImplicitBlocks(layers.SequentialFlow):
     _implicit = True       # imBlock(nnet_x, nnet_z); StackediResBlocks (resflow.py) builds iResBlock(nnet)
 
-    def __init__(self, initial_size, idim, squeeze=True, init_layer=None, n_blocks=1, actnorm=False,
-                 fc_actnorm=False, fc=False, coeff=0.9, vnorms='122f', n_lipschitz_iters=None, sn_atol=None,
-                 sn_rtol=None, n_power_series=5, n_dist='geometric', n_samples=1, kernels='3-1-3',
-                 activation_fn='elu', fc_end=True, fc_nblocks=None, fc_idim=128, n_exact_terms=0, preact=False,
-                 neumann_grad=True, grad_in_forward=False, first_resblock=True, learn_p=False):
+    def __init__(self, initial_size, idim, squeeze=True, init_layer=None, n_blocks=1, quadratic=False, actnorm=False,
+                 fc_actnorm=False, batchnorm=False, dropout=0, fc=False, coeff=0.9, vnorms='122f',
+                 n_lipschitz_iters=None, sn_atol=None, sn_rtol=None, n_power_series=5, n_dist='geometric', n_samples=1,
+                 kernels='3-1-3', activation_fn='elu', fc_end=True, fc_nblocks=None, fc_idim=128, n_exact_terms=0,
+                 preact=False, neumann_grad=True, grad_in_forward=False, first_resblock=True, learn_p=False):
+        if quadratic:
+            # implicit_flow.py:309-315: Glow's InvertibleConv2d / InvertibleLinear in front of every block; those
+            # layers belong to the Glow baseline (lib/layers/glow.py), no run script sets --quadratic
+            raise NotImplementedError('impflow_b200: quadratic=True (Glow invertible 1x1 layers between the blocks) is '
+                                      'outside the hot-path scope')
         if fc_nblocks is None:
             fc_nblocks = 2 if self._implicit else 4       # implicit_flow.py:280, resflow.py:281
         domains, codomains = _parse_vnorms(vnorms)
@@ -179,20 +191,29 @@ class StackedImplicitBlocks(layers.SequentialFlow):
             if learn_p:       # learnable orders, one per layer boundary, shared by neighbours (implicit_flow.py:364-366)
                 doms = [nn.Parameter(torch.tensor(0.)) for _ in range(len(ks))]
                 cods = doms[1:] + [doms[0]]
+            # batchnorm / dropout (implicit_flow.py:374-396; no run script sets them): mean-only MovingBatchNorm2d
+            # after every conv (and in front of a pre-activation), Dropout2d in front of the last conv.  Such a branch
+            # has no graph-free program: it runs through the module / autograd path over the same conv kernels.
             mods = []
             if leading_act:
+                if batchnorm:
+                    mods.append(layers.MovingBatchNorm2d(chans[0]))
                 mods.append(ACT_FNS[activation_fn](False))
             for i, k in enumerate(ks):
                 if i > 0:
                     mods.append(ACT_FNS[activation_fn](True))
+                if dropout and i == len(ks) - 1:
+                    mods.append(nn.Dropout2d(dropout))      # the reference's is in place; same draws, same values
                 mods.append(base_layers.get_conv2d(chans[i], chans[i + 1], k, 1, k // 2, domain=doms[i],
                                                    codomain=cods[i], **lip_kw))
+                if batchnorm:
+                    mods.append(layers.MovingBatchNorm2d(chans[i + 1]))
             return nn.Sequential(*mods)
 
         def fc_net(width):
             return FCNet(input_shape=initial_size, idim=width, lipschitz_layer=base_layers.get_linear,
                          nhidden=len(ks) - 1, coeff=coeff, domains=domains, codomains=codomains,
-                         n_iterations=n_lipschitz_iters, activation_fn=activation_fn, preact=preact, dropout=0,
+                         n_iterations=n_lipschitz_iters, activation_fn=activation_fn, preact=preact, dropout=dropout,
                          sn_atol=sn_atol, sn_rtol=sn_rtol, learn_p=learn_p)
 
         def _resblock(as_fc, width=idim, first=True):
@@ -233,8 +254,6 @@ class FCNet(nn.Module):
     def __init__(self, input_shape, idim, lipschitz_layer, nhidden, coeff, domains, codomains, n_iterations,
                  activation_fn, preact, dropout, sn_atol, sn_rtol, learn_p, div_in=1):
         super(FCNet, self).__init__()
-        if dropout:
-            raise NotImplementedError('impflow_b200: dropout is outside the hot-path scope')
         if learn_p:           # implicit_flow.py:450-452
             domains = [nn.Parameter(torch.tensor(0.)) for _ in range(len(domains))]
             codomains = domains[1:] + [domains[0]]
@@ -249,6 +268,8 @@ class FCNet(nn.Module):
             if i > 0:
                 mods.append(ACT_FNS[activation_fn](True))
             j = min(i, len(domains) - 1) if i < nhidden else -1
+            if dropout and i == nhidden:
+                mods.append(nn.Dropout(dropout))            # implicit_flow.py:463 (in place there)
             mods.append(lipschitz_layer(widths[i], widths[i + 1], coeff=coeff, n_iterations=n_iterations,
                                         domain=domains[j], codomain=codomains[j], atol=sn_atol, rtol=sn_rtol))
         self.nnet = nn.Sequential(*mods)

@@ -881,6 +881,39 @@ def gen_lop():
     with torch.no_grad():
         blk(x, restore=True)
     run_block('lopblk', blk, x, 23, True, out, weight_perturb=3.0)
+
+    # the stack builders' optional layers (implicit_flow.py:374-396, 463): MovingBatchNorm2d after every conv, Dropout
+    # in front of the last layer, under vnorms '122f' with the FC tail.  One training-mode forward moves the running
+    # means; the fixture is the state dict after it and the eval-mode latent (dropout off, running means frozen).
+    torch.manual_seed(14)
+    np.random.seed(14)
+    flow = ImplicitFlow((2, 3, 8, 8), n_blocks=[1, 1], intermediate_dim=8, factor_out=False, quadratic=False,
+                        init_layer=layers.LogitTransform(0.05), actnorm=True, fc_actnorm=False, batchnorm=True,
+                        dropout=0.2, fc=False, coeff=0.9, vnorms='122f', n_lipschitz_iters=None, sn_atol=1e-3,
+                        sn_rtol=1e-3, n_power_series=None, n_dist='poisson', n_samples=1, kernels='3-1-3',
+                        activation_fn='swish', fc_end=True, fc_idim=16, n_exact_terms=2, preact=True,
+                        neumann_grad=True, grad_in_forward=True, first_resblock=True, learn_p=False,
+                        classification=False, classification_hdim=64, n_classes=10)
+    x = torch.rand(2, 3, 8, 8)
+    with torch.no_grad():
+        flow(x, restore=True)
+    flow.train()
+    with torch.no_grad():
+        for n_, p_ in flow.named_parameters():
+            if n_.endswith('weight') and p_.dim() > 1:
+                p_.mul_(2.0)
+            if n_.endswith('bias') and 'nnet' in n_:
+                p_.add_(0.1 * torch.randn_like(p_))
+    flow(x, 0)[0].sum().backward()        # one training evaluation: running means move, gradients exist
+    flow.eval()
+    with torch.no_grad():
+        z = flow(x)
+    for k, v in sd_np(flow).items():
+        out['fopt_sd_' + k] = v
+    out['fopt_x'], out['fopt_z'] = x.numpy(), z.numpy()
+    out['fopt_modules'] = np.array([type(m).__name__ for m in flow.modules()])
+    bn = [v for k, v in sd_np(flow).items() if k.endswith('running_mean') and '_copy' not in k]
+    print('fopt: |running_mean| max', max(float(np.abs(v).max()) for v in bn), 'z[:4]', z.flatten()[:4].numpy())
     save('lop', **out)
 
 

@@ -121,6 +121,10 @@ def test_imblock_lop_train(golden):
     cases.case_imblock_lop_train(golden)
 
 
+def test_flow_options(golden):
+    cases.case_flow_options(golden)
+
+
 def test_sigma_cache_follows_power_iteration():
     cases.case_sigma_cache_follows_power_iteration()
 
