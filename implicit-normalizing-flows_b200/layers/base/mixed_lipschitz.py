@@ -685,9 +685,9 @@ def _dense_settings(m, n_iterations):
 
 def _update_dense_batched(mods, n_iterations):
     """Power iteration of every qualifying dense layer in ONE launch per (n_iterations, atol, rtol) group
-    (csrc/spectral.cu k_sn_power_iter_batch, one CTA per layer).  Returns the modules it did NOT handle."""
-    import ctypes
-    import numpy as np
+    (csrc/spectral.cu k_sn_power_iter_batch, one CTA per layer).  Returns (the modules it does NOT handle, the
+    launches as closures): the caller issues them on the current stream AFTER it has started the other layers on the
+    side streams, so that the handful of single-CTA problems run next to the 3x3 layers' launches."""
     groups, rest = {}, []
     for m in mods:
         key = _dense_settings(m, n_iterations) if BATCH_DENSE['on'] else None
@@ -696,47 +696,58 @@ def _update_dense_batched(mods, n_iterations):
         else:
             groups.setdefault(key, []).append(m)
     lib = _cabi.load()
-    for (n_it, atol, rtol), ms in groups.items():
+    launches = []
+    for key, ms in groups.items():
         if len(ms) < 2:
             rest += ms
-            continue
-        Ws = [m.weight.detach().view(m.weight.shape[0], -1) for m in ms]
-        ck = tuple((W.data_ptr(), m.u.data_ptr(), m.v.data_ptr(), m.scale.data_ptr(), W.shape) for W, m in zip(Ws, ms))
-        cached = _desc_cache.get(ck)
-        if cached is None:
-            if len(_desc_cache) > 64:
-                _desc_cache.clear()
-            iters = torch.zeros(len(ms), device=Ws[0].device, dtype=torch.int32)
-            host = (_cabi.SnDesc * len(ms))()
-            for i, (W, m) in enumerate(zip(Ws, ms)):
-                assert W.is_contiguous() and m.u.is_contiguous() and m.v.is_contiguous()
-                host[i].W, host[i].u, host[i].v = W.data_ptr(), m.u.data_ptr(), m.v.data_ptr()
-                host[i].sigma, host[i].iters = m.scale.data_ptr(), iters.data_ptr() + 4 * i
-                host[i].out_f, host[i].in_f = W.shape[0], W.shape[1]
-            raw = np.frombuffer(bytes(host), dtype=np.uint8).copy()
-            descs = torch.from_numpy(raw).to(Ws[0].device)
-            cached = _desc_cache[ck] = (descs, iters, max(W.shape[0] for W in Ws), max(W.shape[1] for W in Ws))
-        descs, iters, max_out, max_in = cached
-        _cabi.check(lib.impflow_sn_power_iter_batch(ctypes.c_void_p(descs.data_ptr()), len(ms), max_out, max_in, n_it,
-                                                    atol, rtol, _cabi.stream()), 'sn_power_iter_batch')
-        touched = []
-        for m in ms:
-            touched += [m.u, m.v, m.scale] if n_it != 0 else [m.scale]
-        torch.autograd.graph.increment_version(touched)      # written through raw pointers: version-keyed host caches
-        for m in ms:
-            m._scale_for = _state_key(m)
-    return rest
+        else:
+            launches.append(lambda key=key, ms=ms: _launch_dense_group(lib, key, ms))
+    return rest, launches
+
+
+def _launch_dense_group(lib, key, ms):
+    """One k_sn_power_iter_batch launch for the layers `ms` (all with the settings `key`); the descriptor table lives
+    on the device, cached by the layers' buffer addresses."""
+    import ctypes
+    import numpy as np
+    n_it, atol, rtol = key
+    Ws = [m.weight.detach().view(m.weight.shape[0], -1) for m in ms]
+    ck = tuple((W.data_ptr(), m.u.data_ptr(), m.v.data_ptr(), m.scale.data_ptr(), W.shape) for W, m in zip(Ws, ms))
+    cached = _desc_cache.get(ck)
+    if cached is None:
+        if len(_desc_cache) > 64:
+            _desc_cache.clear()
+        iters = torch.zeros(len(ms), device=Ws[0].device, dtype=torch.int32)
+        host = (_cabi.SnDesc * len(ms))()
+        for i, (W, m) in enumerate(zip(Ws, ms)):
+            assert W.is_contiguous() and m.u.is_contiguous() and m.v.is_contiguous()
+            host[i].W, host[i].u, host[i].v = W.data_ptr(), m.u.data_ptr(), m.v.data_ptr()
+            host[i].sigma, host[i].iters = m.scale.data_ptr(), iters.data_ptr() + 4 * i
+            host[i].out_f, host[i].in_f = W.shape[0], W.shape[1]
+        raw = np.frombuffer(bytes(host), dtype=np.uint8).copy()
+        descs = torch.from_numpy(raw).to(Ws[0].device)
+        cached = _desc_cache[ck] = (descs, iters, max(W.shape[0] for W in Ws), max(W.shape[1] for W in Ws))
+    descs, iters, max_out, max_in = cached
+    _cabi.check(lib.impflow_sn_power_iter_batch(ctypes.c_void_p(descs.data_ptr()), len(ms), max_out, max_in, n_it,
+                                                atol, rtol, _cabi.stream()), 'sn_power_iter_batch')
+    touched = []
+    for m in ms:
+        touched += [m.u, m.v, m.scale] if n_it != 0 else [m.scale]
+    torch.autograd.graph.increment_version(touched)      # written through raw pointers: version-keyed host caches
+    for m in ms:
+        m._scale_for = _state_key(m)
 
 
 def _update_all(mods, dev, n_iterations, n_streams):
     with torch.no_grad():
+        batched = []
         if UPDATE_ONLY['on']:
             _require_cuda(mods[0].weight, 'update_lipschitz: layer weights')
-            mods = _update_dense_batched(mods, n_iterations)
-            if not mods:
-                return
+            mods, batched = _update_dense_batched(mods, n_iterations)
         ready = all((not isinstance(m, InducedNormConv2d)) or m.is_initialized() for m in mods)
         if dev.type != 'cuda' or n_streams <= 1 or len(mods) < 2 or not ready:
+            for launch in batched:
+                launch()
             for m in mods:
                 m.compute_weight(update=True, n_iterations=n_iterations)
             return
@@ -752,6 +763,8 @@ def _update_all(mods, dev, n_iterations, n_streams):
         for i, m in enumerate(mods):
             with torch.cuda.stream(used[i % len(used)]):
                 m.compute_weight(update=True, n_iterations=n_iterations)
+        for launch in batched:          # on the main stream, next to the side streams' work
+            launch()
         for s in used:
             done = torch.cuda.Event()
             done.record(s)
