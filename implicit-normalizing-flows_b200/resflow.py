@@ -5,7 +5,6 @@ the block type swapped, so the wiring is shared with implicit_flow.py here).
 In the reference this model cannot run: SequentialFlow passes `restore=` to every layer and iResBlock.forward
 does not take it.  Here iResBlock.forward accepts and ignores `restore`, so the
 constructor / forward / inverse API below is usable."""
-from . import layers
 from .implicit_flow import ACT_FNS, FCNet, FCWrapper, ImplicitFlow, StackedImplicitBlocks  # noqa: F401
 
 __all__ = ['ResidualFlow', 'StackediResBlocks', 'ACT_FNS']

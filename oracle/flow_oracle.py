@@ -6,7 +6,6 @@ dict out of the functional pieces in impflow_oracle.py, so that the reference's 
 (train_img.py:517-549, 591-660: forward, bits/dim, backward, Adam, update_lipschitz) can be
 timed on host cores as the CPU baseline of bench.py and used as the checker of smoke().
 Only bench.py's cpu_baseline / --impl reference legs and tests import this file."""
-import numpy as np
 import torch
 
 from . import impflow_oracle as orc
