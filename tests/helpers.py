@@ -1,5 +1,4 @@
 """Shared helpers for the parity tests: build oracle branches from golden state dicts."""
-
 import numpy as np
 import torch
 
