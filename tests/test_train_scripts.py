@@ -113,6 +113,25 @@ def test_train_tabular_runs_on_the_package(dropin, monkeypatch):
     assert os.path.isfile(dropin / 'tab' / 'models' / 'most_recent.pth')
 
 
+def test_train_tabular_with_closed_form_norms(dropin, monkeypatch):
+    """--vnorms 122f: the script's build_nnet (train_tabular.py:292-318) asks the factories for 1 -> 2 and 2 -> inf layers,
+    i.e. LopLinear first and last, an induced 2 -> 2 layer in between; the blocks run through the module / autograd
+    path, and the script's Lipschitz-constant logging reads the Lop layers' `scale` (train_tabular.py:565-571)."""
+    import impflow_b200
+    monkeypatch.setitem(sys.modules, 'lib.tabular', _fake_tabular())
+    ns = _run('train_tabular.py', ['--data', 'power', '--nblocks', '1', '--dims', '16-16', '--act', 'swish', '--coeff',
+                                   '0.9', '--vnorms', '122f', '--epsf', '1e-5', '--nepochs', '1', '--batchsize', '64',
+                                   '--val-batchsize', '64', '--nworkers', '0', '--seed', '0', '--save',
+                                   str(dropin / 'tab_lop')], monkeypatch)
+    model = ns['model']
+    kinds = [type(m).__name__ for m in model.modules() if hasattr(m, 'compute_weight') and '_copy' not in type(m).__name__]
+    assert kinds.count('LopLinear') >= 2 and 'InducedNormLinear' in kinds, kinds
+    blk = [m for m in model.modules() if isinstance(m, impflow_b200.layers.imBlock)][0]
+    assert 'fwd' in blk.solver_stats and np.isfinite(ns['best_test_bpd'])
+    lop = [m for m in model.modules() if isinstance(m, impflow_b200.layers.base.LopLinear)]
+    assert all(float(m.scale) > 0 for m in lop)
+
+
 def test_all_four_script_preambles_import(dropin, monkeypatch):
     """Everything the four train scripts touch on `lib.layers` / `lib.layers.base` / `lib.implicit_flow` at
     import or model-construction time exists (train_toy.py:21-32, train_tabular.py:23-35, train_img.py:15-20,230,
